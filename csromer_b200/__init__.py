@@ -1,0 +1,21 @@
+"""csromer_b200 -- B200-native implementation of CS-ROMER's reconstruction hot path.
+
+Same public classes as the reference (``Dataset``, ``Parameter``, ``NDFT1D``/``DFT1D``, ``NUFFT1D``, ``Chi2``,
+``L1``, ``OFunction``, ``FISTA``, ``DiscreteWavelet``, ``UndecimatedWavelet``, the synthetic sources), with the
+lambda^2 <-> phi transforms, the Chi2 gradient, the L1 / wavelet proximal steps and the FISTA loop running on
+sm_100a CUDA kernels for every line of sight of a cube at once.  See DESIGN.md.
+"""
+from .base import Dataset
+from .dictionaries import DiscreteWavelet, UndecimatedWavelet, Wavelet
+from .objectivefunction import L1, Chi2, Fi, OFunction
+from .optimization import FISTA, Optimizer
+from .reconstruction import Parameter
+from .simulation import FaradaySource, FaradayThickSource, FaradayThinSource
+from .transformers import DFT1D, FT, NDFT1D, NUFFT1D
+
+__version__ = "0.1.0"
+__all__ = [
+    "Dataset", "Parameter", "FT", "NDFT1D", "DFT1D", "NUFFT1D", "Wavelet", "DiscreteWavelet", "UndecimatedWavelet",
+    "Fi", "Chi2", "L1", "OFunction", "Optimizer", "FISTA", "FaradaySource", "FaradayThinSource",
+    "FaradayThickSource",
+]

@@ -1,0 +1,262 @@
+"""Device plumbing between the reference-shaped Python objects and the C ABI.
+
+PyTorch is used for device memory, streams and host<->device copies only; every arithmetic kernel on the
+hot path lives in ``libcsromer_b200.so``.  Layout contract: user-facing arrays are
+frequency / phi FIRST (``(m,)``, ``(m, P)``, ``(m, Y, X)``) like the reference's ``cube[:, i, j]``; on the device
+everything is pixel-major planar fp32: ``[P, ld2m]`` and ``[P, ld2n]`` with ``[Re | Im]`` packing.
+"""
+import ctypes
+import hashlib
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import CsrError
+
+
+def require_cuda():
+    if not torch.cuda.is_available():
+        raise CsrError("csromer_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+
+
+def stream_ptr():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def tptr(t):
+    return ctypes.c_void_p(0 if t is None else t.data_ptr())
+
+
+def is_torch(a):
+    return isinstance(a, torch.Tensor)
+
+
+def pixel_shape(arr, lead):
+    """(pixel shape tuple, P) of an array whose axis 0 has length ``lead``."""
+    if arr.shape[0] != lead:
+        raise ValueError("leading axis has length %d, expected %d" % (arr.shape[0], lead))
+    pix = tuple(arr.shape[1:])
+    return pix, int(np.prod(pix)) if pix else 1
+
+
+def to_device(a, dtype=None, device=None):
+    """numpy / torch -> torch tensor on the CUDA device (pinned staging for host arrays)."""
+    require_cuda()
+    if is_torch(a):
+        t = a.to(device=device or "cuda", non_blocking=True)
+    else:
+        h = torch.from_numpy(np.ascontiguousarray(a))
+        t = h.pin_memory().to(device or "cuda", non_blocking=True)
+    return t if dtype is None else t.to(dtype)
+
+
+def pack_planar(a, length, ld, device=None):
+    """complex ``(length, *pix)`` or real ``(2*length, *pix)`` -> fp32 ``[P, ld]`` planar on the device."""
+    t = to_device(a, device=device)
+    if t.is_complex():
+        pix, P = pixel_shape(t, length)
+        t = t.reshape(length, P)
+        out = torch.zeros((P, ld), dtype=torch.float32, device=t.device)
+        out[:, :length] = t.real.t()
+        out[:, length:2 * length] = t.imag.t()
+    else:
+        pix, P = pixel_shape(t, 2 * length)
+        out = torch.zeros((P, ld), dtype=torch.float32, device=t.device)
+        out[:, :2 * length] = t.reshape(2 * length, P).t()
+    return out, pix
+
+
+def pack_real(a, length, ld, device=None):
+    """real ``(length, *pix)`` -> fp32 ``[P, ld]``."""
+    t = to_device(a, device=device)
+    pix, P = pixel_shape(t, length)
+    out = torch.zeros((P, ld), dtype=torch.float32, device=t.device)
+    out[:, :length] = t.reshape(length, P).t()
+    return out, pix
+
+
+def unpack_complex(t, length, pix, like_torch=False):
+    """fp32 ``[P, ld]`` planar -> complex64 ``(length, *pix)`` (numpy unless ``like_torch``)."""
+    c = torch.complex(t[:, :length], t[:, length:2 * length]).t().contiguous().reshape((length,) + tuple(pix))
+    return c if like_torch else c.cpu().numpy()
+
+
+def unpack_real(t, length, pix, like_torch=False):
+    r = t[:, :length].t().contiguous().reshape((length,) + tuple(pix))
+    return r if like_torch else r.cpu().numpy()
+
+
+def per_pixel_vector(v, P, device, name):
+    """scalar or (P,)/pixel-shaped array -> fp32 [P] on the device."""
+    if is_torch(v):
+        t = v.to(device=device, dtype=torch.float32).reshape(-1)
+    else:
+        t = torch.as_tensor(np.asarray(v, dtype=np.float64).reshape(-1), dtype=torch.float32).to(device)
+    if t.numel() == 1:
+        t = t.expand(P).contiguous()
+    if t.numel() != P:
+        raise ValueError("%s has %d entries, expected 1 or %d" % (name, t.numel(), P))
+    return t.contiguous()
+
+
+class Workspace:
+    """grow-only scratch buffer"""
+
+    def __init__(self):
+        self.buf = None
+
+    def get(self, nbytes, device):
+        if self.buf is None or self.buf.numel() < nbytes or self.buf.device != device:
+            self.buf = None
+            self.buf = torch.empty(int(nbytes) + 256, dtype=torch.uint8, device=device)
+        return self.buf
+
+
+class DevicePlan:
+    """Owns a ``csr_plan`` (twiddle tables) for one (lambda2, l2_ref, phi) sampling on one GPU."""
+
+    _cache = {}
+
+    @classmethod
+    def get(cls, lambda2, l2_ref, phi, device=None):
+        require_cuda()
+        dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        l2 = np.ascontiguousarray(lambda2, dtype=np.float64)
+        ph = np.ascontiguousarray(phi, dtype=np.float64)
+        key = (hashlib.sha1(l2.tobytes()).hexdigest(), hashlib.sha1(ph.tobytes()).hexdigest(), float(l2_ref),
+               dev.index)
+        plan = cls._cache.get(key)
+        if plan is None:
+            if len(cls._cache) >= 4:  # tables are large (64 MB .. 4 GB): keep only a few
+                cls._cache.pop(next(iter(cls._cache))).close()
+            plan = cls(l2, float(l2_ref), ph, dev)
+            cls._cache[key] = plan
+        return plan
+
+    def __init__(self, lambda2, l2_ref, phi, device):
+        self.lib = _lib.load()
+        self.device = device
+        self.m, self.n = int(lambda2.shape[0]), int(phi.shape[0])
+        handle = ctypes.c_void_p()
+        _lib.check(self.lib.csr_plan_create(ctypes.byref(handle), _lib.dptr(lambda2), self.m, l2_ref, _lib.dptr(phi),
+                                            self.n, device.index), "csr_plan_create")
+        self.handle = handle
+        m_, n_, ld2m, ld2n, tb = ctypes.c_int(), ctypes.c_int(), ctypes.c_int(), ctypes.c_int(), ctypes.c_size_t()
+        _lib.check(self.lib.csr_plan_dims(handle, m_, n_, ld2m, ld2n, tb), "csr_plan_dims")
+        self.ld2m, self.ld2n, self.table_bytes = ld2m.value, ld2n.value, tb.value
+        self.ws = Workspace()
+
+    def close(self):
+        if self.handle:
+            self.lib.csr_plan_destroy(self.handle)
+            self.handle = None
+
+    def _transform(self, fn, name, inp, ld_out, chan_scale, row_scale):
+        P = inp.shape[0]
+        out = torch.empty((P, ld_out), dtype=torch.float32, device=self.device)
+        need = self.lib.csr_transform_ws_bytes(self.handle, P)
+        ws = self.ws.get(need, self.device)
+        per_pixel = 0
+        if chan_scale is not None:
+            chan_scale = chan_scale.contiguous()
+            per_pixel = int(chan_scale.dim() == 2)
+        _lib.check(fn(self.handle, tptr(inp), tptr(chan_scale), per_pixel, tptr(row_scale), tptr(out), P, tptr(ws),
+                      ws.numel(), stream_ptr()), name)
+        return out
+
+    def forward(self, x, chan_scale=None, row_scale=None):
+        """[P, ld2n] -> [P, ld2m]; out = row_scale * chan_scale * (E x)"""
+        return self._transform(self.lib.csr_forward, "csr_forward", x, self.ld2m, chan_scale, row_scale)
+
+    def adjoint(self, b, chan_scale=None, row_scale=None):
+        """[P, ld2m] -> [P, ld2n]; out = row_scale * E^H (chan_scale * b)"""
+        return self._transform(self.lib.csr_adjoint, "csr_adjoint", b, self.ld2n, chan_scale, row_scale)
+
+    def derotate(self, data, phi_gal):
+        _lib.check(self.lib.csr_derotate(self.handle, tptr(data), tptr(phi_gal), data.shape[0], stream_ptr()),
+                   "csr_derotate")
+
+    def fista(self, data, w, s, k, x, lambda0, noise, iters, step=1.0, norm_factor=1.0, wavelet=None,
+              use_dirty_as_guess=False, want_dirty=True, want_model=True, want_delta=False, iter_cap=None):
+        """Run the fused loop.  All tensors are fp32 on the device; ``x`` ([P, ldx]) is updated in place.
+        Returns dict(f_dirty, model, residual, cost[P,2], delta)."""
+        P = data.shape[0]
+        dev = self.device
+        out = dict(f_dirty=None, model=None, residual=None, cost=None, delta=None)
+        if want_dirty:
+            out["f_dirty"] = torch.empty((P, self.ld2n), dtype=torch.float32, device=dev)
+        if want_model:
+            out["model"] = torch.empty((P, self.ld2m), dtype=torch.float32, device=dev)
+            out["residual"] = torch.zeros((P, self.ld2m), dtype=torch.float32, device=dev)
+            out["cost"] = torch.empty((P, 2), dtype=torch.float32, device=dev)
+        if want_delta:
+            out["delta"] = torch.zeros((P,), dtype=torch.float32, device=dev)
+        whandle = wavelet.handle if wavelet is not None else None
+        need = self.lib.csr_fista_ws_bytes(self.handle, whandle, P)
+        ws = self.ws.get(need, dev)
+        a = _lib.FistaArgs()
+        a.P, a.iters, a.step, a.norm_factor = P, int(iters), float(step), float(norm_factor)
+        a.w_per_pixel = int(w.dim() == 2)
+        a.data, a.w, a.s, a.k = data.data_ptr(), w.data_ptr(), s.data_ptr(), k.data_ptr()
+        a.x, a.ldx = x.data_ptr(), x.shape[1]
+        a.lambda0, a.noise = lambda0.data_ptr(), noise.data_ptr()
+        a.iter_cap = iter_cap.data_ptr() if iter_cap is not None else None
+        for key in ("f_dirty", "model", "residual", "cost", "delta"):
+            setattr(a, key, out[key].data_ptr() if out[key] is not None else None)
+        a.use_dirty_as_guess = int(bool(use_dirty_as_guess))
+        _lib.check(self.lib.csr_fista(self.handle, whandle, ctypes.byref(a), tptr(ws), ws.numel(), stream_ptr()),
+                   "csr_fista")
+        return out
+
+
+class DeviceWavelet:
+    """Owns a ``csr_wavelet`` for one (filter bank, level, N) configuration."""
+
+    def __init__(self, kind, bank, level, N, append_signal, norm, device=None):
+        require_cuda()
+        self.lib = _lib.load()
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        fs = [np.ascontiguousarray(f, dtype=np.float64) for f in bank]
+        F = fs[0].shape[0]
+        handle = ctypes.c_void_p()
+        _lib.check(self.lib.csr_wavelet_create(ctypes.byref(handle), int(kind), _lib.dptr(fs[0]), _lib.dptr(fs[1]),
+                                               _lib.dptr(fs[2]), _lib.dptr(fs[3]), F, int(level), int(N),
+                                               int(bool(append_signal)), int(bool(norm)), self.device.index),
+                   "csr_wavelet_create")
+        self.handle = handle
+        self.N = int(N)
+        self.ncoef = self.lib.csr_wavelet_ncoef(handle)
+        self.levels = self.lib.csr_wavelet_levels(handle)
+        sizes = (ctypes.c_int * 40)()
+        nb = self.lib.csr_wavelet_level_sizes(handle, sizes, 40)
+        self.sizes = [sizes[i] for i in range(nb)]
+        self.ldc = (self.ncoef + 7) // 8 * 8
+        self.ldn = (self.N + 7) // 8 * 8
+        self.ws = Workspace()
+
+    def __del__(self):
+        try:
+            if self.handle:
+                self.lib.csr_wavelet_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+    def decompose(self, signal):
+        """[P, ld >= N] -> [P, ldc]"""
+        P = signal.shape[0]
+        coef = torch.zeros((P, self.ldc), dtype=torch.float32, device=self.device)
+        ws = self.ws.get(self.lib.csr_wavelet_ws_bytes(self.handle, P), self.device)
+        _lib.check(self.lib.csr_wavelet_decompose(self.handle, tptr(signal), signal.shape[1], tptr(coef), self.ldc, P,
+                                                  tptr(ws), ws.numel(), stream_ptr()), "csr_wavelet_decompose")
+        return coef
+
+    def reconstruct(self, coef):
+        """[P, ld >= ncoef] -> [P, ldn]"""
+        P = coef.shape[0]
+        sig = torch.zeros((P, self.ldn), dtype=torch.float32, device=self.device)
+        ws = self.ws.get(self.lib.csr_wavelet_ws_bytes(self.handle, P), self.device)
+        _lib.check(self.lib.csr_wavelet_reconstruct(self.handle, tptr(coef), coef.shape[1], tptr(sig), self.ldn, P,
+                                                    tptr(ws), ws.numel(), stream_ptr()), "csr_wavelet_reconstruct")
+        return sig

@@ -1,0 +1,402 @@
+// dft_gemm.cu -- the lambda^2 <-> phi transform of every line of sight at once, as a dense real GEMM on the
+// 5th-generation tensor cores (tcgen05.mma, kind::f16, fp32 accumulators in TMEM, operands staged by TMA).
+//
+// Replaces: np.dot(x, np.exp(2j*l2*phi)) in transformers/dfts/ndft.py:17-36 (and the pynufft calls of
+// transformers/dfts/nufft.py:50-71), with the work that follows each transform inside the FISTA loop fused
+// into the epilogue: the residual/weighting of objectivefunction/priors/chi2.py:49-52 + base/dataset.py:374
+// (EPI_RESID) and z - grad, the L1 prox of priors/l1.py:30-32 and the momentum step of
+// optimization/methods/fista.py:80-86 (EPI_FISTA).
+//
+// Math.  With the planar packing [Re|Im], forward is  Y[P,2m] = X[P,2n] * T^T  and adjoint is
+// G[P,2n] = R[P,2m] * T  for the real matrix T = [[cos,-sin],[sin,cos]] (2m x 2n).  Both operands are
+// K-major fp16 "hi + lo" pairs (value * 2^k = hi + lo to ~2^-22), and every K block issues the three
+// products  A_hi*B_hi + A_lo*B_hi + A_hi*B_lo  into one fp32 accumulator: fp32-class accuracy at one third
+// of the fp16 tensor rate (the dropped A_lo*B_lo term is ~2^-22 relative).
+//
+// Structure (one CTA per SM, persistent over tiles):
+//   warp 0   : TMA producer   (cp.async.bulk.tensor -> 128B-swizzled smem ring, mbarrier complete_tx)
+//   warp 1   : MMA issuer     (one thread issues tcgen05.mma; tcgen05.commit frees smem stages / publishes
+//                              the accumulator); also owns the TMEM allocation
+//   warps 2-9: epilogue       (tcgen05.ld 32x32b -> register accumulators -> smem transpose -> coalesced I/O)
+// TMEM holds two 128x256 fp32 accumulators used ping-pong per K CHUNK: the tensor core's fp32 accumulate
+// truncates, so partial sums are moved to registers (round-to-nearest adds) every `chunk_kb` K blocks while the
+// next chunk runs; the fused epilogue of tile t overlaps the first chunks of tile t+1 the same way.
+#include <stdlib.h>
+
+#include "plan.cuh"
+
+namespace csr {
+
+constexpr int STAGES = 2;
+constexpr int A_TILE_BYTES = BM * BK * 2;  // 16 KiB
+constexpr int B_TILE_BYTES = BN * BK * 2;  // 32 KiB
+constexpr int STAGE_BYTES = 2 * A_TILE_BYTES + 2 * B_TILE_BYTES;  // A_hi, A_lo, B_hi, B_lo = 96 KiB
+constexpr int EPI_WARPS = 8;               // 4 TMEM lane quarters x 2 column halves
+constexpr int EPI_COLS = BN / 2;           // accumulator columns held in registers per epilogue thread
+constexpr int NUM_THREADS = 64 + 32 * EPI_WARPS;
+constexpr int TMEM_COLS = 512;
+constexpr int TBUF_FLOATS = 32 * 33;
+constexpr int SMEM_BYTES = 1024 /*alignment slack*/ + STAGES * STAGE_BYTES + EPI_WARPS * TBUF_FLOATS * 4 + 256;
+constexpr int RASTER_GROUP = 16;  // pixel tiles per rasterisation group (keeps A and B panels L2-resident)
+static_assert(SMEM_BYTES <= 232448, "shared memory budget exceeded");
+
+__device__ __forceinline__ void tile_coords(int t, int MT, int NT, int& mt, int& nt) {
+    const int per_group = RASTER_GROUP * NT;
+    const int g = t / per_group;
+    const int first = g * RASTER_GROUP;
+    const int gsize = min(RASTER_GROUP, MT - first);
+    const int local = t - g * per_group;
+    mt = first + local % gsize;
+    nt = local / gsize;
+}
+
+// acc[j] += TMEM[lane quarter, col0 + j]  for the 128 columns this thread owns
+__device__ __forceinline__ void drain_chunk(uint32_t taddr, float (&acc)[EPI_COLS]) {
+#pragma unroll
+    for (int g = 0; g < EPI_COLS / 32; ++g) {
+        float v[32];
+        tmem_ld_32x32(taddr + (uint32_t)(g * 32), v);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) acc[g * 32 + j] += v[j];
+    }
+}
+
+// Fused epilogue on the register accumulators of one thread: row (row0 + sub*32 + lane), columns
+// [col0, col0 + EPI_COLS).  Each 32x32 block is transposed through shared memory so that every global access of
+// a warp is one contiguous 128-byte (fp32) / 64-byte (fp16) row segment.
+template <int MODE>
+__device__ __forceinline__ void epilogue_tile(const GemmEpilogue& epi, const float (&acc)[EPI_COLS], float* tb, int sub,
+                                              int lane, int row0, int col0) {
+    const int row_base = row0 + sub * 32;
+    const int my_row = row_base + lane;
+    const bool my_row_ok = my_row < epi.P;
+    // per-row parameters live in the lane that owns the row and are broadcast with shuffles
+    float descale_l = 0.f, oscale_l = 0.f, rs_l = 1.f, thr_l = 0.f;
+    int active_l = 0;
+    if (my_row_ok) {
+        descale_l = kTwiddleDescale / epi.a_scale[my_row];
+        if (MODE == EPI_PLAIN) {
+            rs_l = epi.row_scale ? epi.row_scale[my_row] : 1.f;
+        } else {
+            oscale_l = epi.out_scale[my_row];
+        }
+        if (MODE == EPI_FISTA) {
+            const float l0 = epi.lambda0[my_row], nz = epi.noise[my_row];
+            const float lam = l0 - (float)epi.iter * nz;
+            active_l = (nz < l0) && (epi.iter == 0 || lam > 0.f) && (!epi.iter_cap || epi.iter < epi.iter_cap[my_row]);
+            thr_l = epi.step * lam;
+            descale_l *= epi.step;
+        }
+    }
+    const int nrows = min(32, epi.P - row_base);
+
+#pragma unroll
+    for (int g = 0; g < EPI_COLS / 32; ++g) {
+        const int colbase = col0 + g * 32;
+        if (colbase < epi.N && nrows > 0) {  // warp-uniform
+#pragma unroll
+            for (int j = 0; j < 32; ++j) tb[lane * 33 + j] = acc[g * 32 + j];
+            __syncwarp();
+            const int col = colbase + lane;
+            const bool colok = col < epi.N;
+            int ch = 0;
+            if (MODE != EPI_FISTA) ch = (col >= epi.m) ? col - epi.m : col;
+#pragma unroll 4
+            for (int rr = 0; rr < nrows; ++rr) {
+                const float a = tb[rr * 33 + lane];
+                const int row = row_base + rr;
+                const size_t o = (size_t)row * epi.ld_out + col;
+                const float descale = __shfl_sync(0xffffffffu, descale_l, rr);
+                if (MODE == EPI_PLAIN) {
+                    const float rs = __shfl_sync(0xffffffffu, rs_l, rr);
+                    if (colok) {
+                        float cs = 1.f;
+                        if (epi.chan_scale) cs = epi.chan_scale[(epi.chan_per_pixel ? (size_t)row * epi.m : 0) + ch];
+                        epi.out[o] = a * descale * rs * cs;
+                    }
+                } else if (MODE == EPI_RESID) {
+                    const float os = __shfl_sync(0xffffffffu, oscale_l, rr);
+                    if (colok) {
+                        const float am = epi.chan_scale[(epi.chan_per_pixel ? (size_t)row * epi.m : 0) + ch];
+                        const float r = am * (a * descale) - epi.b[o];
+                        __half h, l;
+                        split_half(r * os, h, l);
+                        epi.out_hi[o] = h;
+                        epi.out_lo[o] = l;
+                    }
+                } else {  // EPI_FISTA
+                    const float os = __shfl_sync(0xffffffffu, oscale_l, rr);
+                    const float thr = __shfl_sync(0xffffffffu, thr_l, rr);
+                    const int active = __shfl_sync(0xffffffffu, active_l, rr);
+                    float d = 0.f;
+                    if (colok && active) {
+                        const float zo = epi.z[o];
+                        const float xo = epi.x[o];
+                        const float u = zo - a * descale;
+                        const float xn = copysignf(fmaxf(fabsf(u) - thr, 0.f), u);
+                        const float zn = xn + epi.beta * (xn - xo);
+                        epi.x[o] = xn;
+                        epi.z[o] = zn;
+                        __half h, l;
+                        split_half(zn * os, h, l);
+                        epi.out_hi[o] = h;
+                        epi.out_lo[o] = l;
+                        d = fabsf(xn - xo);
+                    }
+                    if (epi.delta != nullptr) {  // kernel-uniform
+#pragma unroll
+                        for (int s = 16; s > 0; s >>= 1) d += __shfl_xor_sync(0xffffffffu, d, s);
+                        if (lane == 0 && d != 0.f) atomicAdd(epi.delta + row, d);
+                    }
+                }
+            }
+            __syncwarp();
+        }
+    }
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+dft_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
+                const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
+                int K, int MT, int NT, int chunk_kb, const GemmEpilogue epi) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* stage_base = smem;
+    float* tbuf = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES + EPI_WARPS * TBUF_FLOATS * 4);
+    uint64_t* full = bars;                     // [STAGES]  TMA -> MMA
+    uint64_t* empty = bars + STAGES;           // [STAGES]  MMA -> TMA
+    uint64_t* tmem_full = bars + 2 * STAGES;   // [2]       MMA -> epilogue (one K chunk accumulated)
+    uint64_t* tmem_empty = bars + 2 * STAGES + 2;  // [2]   epilogue -> MMA (chunk drained to registers)
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int total_tiles = MT * NT;
+    const int KB = (K + BK - 1) / BK;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&map_a_hi);
+        tma_prefetch_desc(&map_a_lo);
+        tma_prefetch_desc(&map_b_hi);
+        tma_prefetch_desc(&map_b_lo);
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], 1);
+        }
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(&tmem_full[b], 1);
+            mbar_init(&tmem_empty[b], EPI_WARPS);
+        }
+        mbar_fence_init();
+    }
+    if (warp == 1) {
+        tmem_alloc(tmem_ptr, TMEM_COLS);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+                int mt, nt;
+                tile_coords(t, MT, NT, mt, nt);
+                for (int kb = 0; kb < KB; ++kb) {
+                    mbar_wait(&empty[stage], phase ^ 1);
+                    uint8_t* sb = stage_base + stage * STAGE_BYTES;
+                    mbar_arrive_expect_tx(&full[stage], STAGE_BYTES);
+                    tma_load_2d(sb, &map_a_hi, &full[stage], kb * BK, mt * BM);
+                    tma_load_2d(sb + A_TILE_BYTES, &map_a_lo, &full[stage], kb * BK, mt * BM);
+                    tma_load_2d(sb + 2 * A_TILE_BYTES, &map_b_hi, &full[stage], kb * BK, nt * BN);
+                    tma_load_2d(sb + 2 * A_TILE_BYTES + B_TILE_BYTES, &map_b_lo, &full[stage], kb * BK, nt * BN);
+                    if (++stage == STAGES) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        // The tensor core truncates when it adds into the fp32 accumulator, so the error of a long K loop grows
+        // linearly with K.  The accumulation is therefore cut into chunks of `chunk_kb` K blocks: each chunk
+        // starts a fresh TMEM accumulator (two of them, ping-pong) which the epilogue warps add into registers
+        // with round-to-nearest while the next chunk is being computed.
+        if (lane == 0) {
+            constexpr uint32_t idesc = umma_idesc_f16(BM, BN);
+            int stage = 0;
+            uint32_t phase = 0;
+            uint32_t chunk = 0;  // running chunk counter -> TMEM buffer = chunk & 1, parity = (chunk >> 1) & 1
+            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+                for (int kb0 = 0; kb0 < KB; kb0 += chunk_kb, ++chunk) {
+                    const int buf = chunk & 1;
+                    mbar_wait(&tmem_empty[buf], ((chunk >> 1) & 1) ^ 1);
+                    tc_fence_after();
+                    const uint32_t d_tmem = tmem_base + (uint32_t)(buf * BN);
+                    const int kb1 = min(KB, kb0 + chunk_kb);
+                    for (int kb = kb0; kb < kb1; ++kb) {
+                        mbar_wait(&full[stage], phase);
+                        tc_fence_after();
+                        const uint32_t sa_hi = smem_u32(stage_base + stage * STAGE_BYTES);
+                        const uint32_t sa_lo = sa_hi + A_TILE_BYTES;
+                        const uint32_t sb_hi = sa_hi + 2 * A_TILE_BYTES;
+                        const uint32_t sb_lo = sb_hi + B_TILE_BYTES;
+#pragma unroll
+                        for (int k4 = 0; k4 < BK / 16; ++k4) {
+                            const uint64_t da_hi = umma_desc_sw128(sa_hi + k4 * 32);
+                            const uint64_t da_lo = umma_desc_sw128(sa_lo + k4 * 32);
+                            const uint64_t db_hi = umma_desc_sw128(sb_hi + k4 * 32);
+                            const uint64_t db_lo = umma_desc_sw128(sb_lo + k4 * 32);
+                            umma_f16(d_tmem, da_hi, db_hi, idesc, (kb != kb0 || k4 != 0) ? 1u : 0u);
+                            umma_f16(d_tmem, da_lo, db_hi, idesc, 1u);
+                            umma_f16(d_tmem, da_hi, db_lo, idesc, 1u);
+                        }
+                        umma_commit(&empty[stage]);  // smem stage reusable once these MMAs have read it
+                        if (++stage == STAGES) {
+                            stage = 0;
+                            phase ^= 1;
+                        }
+                    }
+                    umma_commit(&tmem_full[buf]);  // chunk accumulator complete
+                }
+            }
+        }
+    } else {
+        // ===================== epilogue warps =====================
+        const int ew = warp - 2;
+        const int sub = warp & 3;        // TMEM lane quarter this warp may read (hardware rule: warp id mod 4)
+        const int half = ew >> 2;        // which 128 of the tile's 256 columns
+        float* tb = tbuf + ew * TBUF_FLOATS;
+        uint32_t chunk = 0;
+        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+            int mt, nt;
+            tile_coords(t, MT, NT, mt, nt);
+            float acc[EPI_COLS];
+#pragma unroll
+            for (int j = 0; j < EPI_COLS; ++j) acc[j] = 0.f;
+            for (int kb0 = 0; kb0 < KB; kb0 += chunk_kb, ++chunk) {
+                const int buf = chunk & 1;
+                mbar_wait(&tmem_full[buf], (chunk >> 1) & 1);
+                tc_fence_after();
+                drain_chunk(tmem_base + ((uint32_t)(sub * 32) << 16) + (uint32_t)(buf * BN + half * EPI_COLS), acc);
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tmem_empty[buf]);
+            }
+            epilogue_tile<MODE>(epi, acc, tb, sub, lane, mt * BM, nt * BN + half * EPI_COLS);
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, TMEM_COLS);
+    }
+}
+
+// ---- host side --------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (fn == nullptr) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+// fp16 row-major [rows, cols] matrix with pitch ld -> 2-D map with a {64 x box_rows} box, 128B swizzle.
+// Out-of-bounds parts of a box (K tail, ragged last pixel tile) read as zero.
+int make_operand_map(CUtensorMap* map, const void* base, int rows, int cols, int ld, int box_rows) {
+    EncodeTiledFn enc = get_encode_fn();
+    if (!enc) {
+        set_error("cuTensorMapEncodeTiled is not available from the CUDA driver");
+        return CSR_ERR_CUDA;
+    }
+    CSR_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0 && ld % 8 == 0,
+                "operand matrix must be 16-byte aligned with a pitch that is a multiple of 8 (ld=%d)", ld);
+    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+    cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled failed with CUresult %d (rows=%d cols=%d ld=%d)", (int)r, rows, cols, ld);
+        return CSR_ERR_CUDA;
+    }
+    return CSR_OK;
+}
+
+// K blocks accumulated inside the tensor core before the partial sum is moved to registers (CSR_CHUNK_KB, 1..64)
+static int gemm_chunk_kb() {
+    static int v = 0;
+    if (v == 0) {
+        const char* e = getenv("CSR_CHUNK_KB");
+        v = e ? atoi(e) : 4;
+        if (v < 1) v = 1;
+        if (v > 4096) v = 4096;
+    }
+    return v;
+}
+
+template <int MODE>
+static int launch_mode(const csr_plan* plan, bool adjoint, const CUtensorMap& a_hi, const CUtensorMap& a_lo, int P,
+                       const GemmEpilogue& epi, cudaStream_t stream) {
+    static bool configured = false;
+    if (!configured) {
+        CSR_CUDA(cudaFuncSetAttribute(dft_gemm_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        configured = true;
+    }
+    const int K = adjoint ? 2 * plan->m : 2 * plan->n;
+    const int N = adjoint ? 2 * plan->n : 2 * plan->m;
+    const int MT = (P + BM - 1) / BM;
+    const int NT = (N + BN - 1) / BN;
+    const int grid = min(MT * NT, plan->num_sms);
+    dft_gemm_kernel<MODE><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(
+        a_hi, a_lo, adjoint ? plan->map_adj_hi : plan->map_fwd_hi, adjoint ? plan->map_adj_lo : plan->map_fwd_lo, K,
+        MT, NT, gemm_chunk_kb(), epi);
+    CSR_LAUNCHED();
+    return CSR_OK;
+}
+
+int launch_dft_gemm(const csr_plan* plan, bool adjoint, const __half* a_hi, const __half* a_lo, int P,
+                    const GemmEpilogue& epi_in, cudaStream_t stream) {
+    CSR_REQUIRE(P > 0, "P must be positive");
+    GemmEpilogue epi = epi_in;
+    const int K = adjoint ? 2 * plan->m : 2 * plan->n;
+    const int ldk = adjoint ? plan->ld2m : plan->ld2n;
+    epi.P = P;
+    epi.N = adjoint ? 2 * plan->n : 2 * plan->m;
+    epi.ld_out = adjoint ? plan->ld2n : plan->ld2m;
+    epi.m = plan->m;
+    CUtensorMap ma_hi, ma_lo;
+    int rc = make_operand_map(&ma_hi, a_hi, P, K, ldk, BM);
+    if (rc) return rc;
+    rc = make_operand_map(&ma_lo, a_lo, P, K, ldk, BM);
+    if (rc) return rc;
+    switch (epi.mode) {
+        case EPI_PLAIN: return launch_mode<EPI_PLAIN>(plan, adjoint, ma_hi, ma_lo, P, epi, stream);
+        case EPI_RESID: return launch_mode<EPI_RESID>(plan, adjoint, ma_hi, ma_lo, P, epi, stream);
+        case EPI_FISTA: return launch_mode<EPI_FISTA>(plan, adjoint, ma_hi, ma_lo, P, epi, stream);
+    }
+    set_error("unknown epilogue mode %d", epi.mode);
+    return CSR_ERR_ARG;
+}
+
+}  // namespace csr

@@ -1,0 +1,277 @@
+// fista.cu -- host-side orchestration behind the C ABI: single transforms (NDFT1D / NUFFT1D methods) and the
+// fused fixed-iteration FISTA loop over all lines of sight (optimization/methods/fista.py:41-108 driving
+// objectivefunction/priors/chi2.py:43-56 and priors/l1.py:30-32).
+//
+// Delta basis, per iteration (2 kernel launches):
+//   forward GEMM  (A = z as fp16 hi/lo)  epilogue: r = 1[w>0]/n * (E z) - (w/(s k)) d      -> fp16 hi/lo
+//   adjoint GEMM  (A = r)                epilogue: z - step*g, soft threshold, momentum     -> x, z, z hi/lo
+// Wavelet basis, per iteration: synthesis -> split -> forward GEMM -> adjoint GEMM (plain) -> analysis ->
+// coefficient update.  No CPU fallback exists anywhere in this file.
+#include <math.h>
+
+#include "plan.cuh"
+
+namespace csr {
+
+int launch_split_rows(const float* in, int ld_in, int rows, int cols, const float* chan_scale, int chan_pp, int m,
+                      const float* ref2, int ld_ref2, __half* hi, __half* lo, int ld_out, float* scale,
+                      int fixed_scale, cudaStream_t stream);
+int launch_prepare(const csr_plan* plan, const csr_fista_args& a, float* b, float* amask, float* fwd_chan,
+                   cudaStream_t stream);
+int launch_finalize(const csr_plan* plan, const csr_fista_args& a, const float* model, float* residual,
+                    const float* x, int ldx, int ncoef, cudaStream_t stream);
+int launch_coef_update(const float* grad, float* x, float* z, int ld, int ncoef, int P, const float* lambda0,
+                       const float* noise, const int* iter_cap, int iter, float step, float beta, float* delta,
+                       cudaStream_t stream);
+int launch_scale_vec(float* v, int n, float f, cudaStream_t stream);
+int wavelet_ld(const csr_wavelet* w);
+int wavelet_decompose(const csr_wavelet* w, const float* signal, int ld_sig, float* coef, int ld_coef, int P,
+                      float* ws, cudaStream_t stream);
+int wavelet_reconstruct(const csr_wavelet* w, const float* coef, int ld_coef, float* signal, int ld_sig, int P,
+                        float* ws, cudaStream_t stream);
+
+struct Bump {
+    char* base;
+    size_t off;
+    template <typename T>
+    T* take(size_t count) {
+        T* p = base ? reinterpret_cast<T*>(base + off) : nullptr;
+        off += align256(count * sizeof(T));
+        return p;
+    }
+};
+
+struct TransformWs {
+    __half *a_hi, *a_lo;
+    float* a_scale;
+    size_t bytes;
+};
+static TransformWs carve_transform(const csr_plan* plan, int P, void* ws) {
+    Bump b{(char*)ws, 0};
+    TransformWs t;
+    const int ldk = plan->ld2n > plan->ld2m ? plan->ld2n : plan->ld2m;
+    t.a_hi = b.take<__half>((size_t)P * ldk);
+    t.a_lo = b.take<__half>((size_t)P * ldk);
+    t.a_scale = b.take<float>(P);
+    t.bytes = b.off;
+    return t;
+}
+
+struct FistaWs {
+    float *b, *amask, *fwd_chan, *rscale, *zscale, *z, *f_dirty, *model, *sig, *gcoef, *wav_ws;
+    __half *r_hi, *r_lo, *z_hi, *z_lo;
+    size_t bytes;
+};
+static FistaWs carve_fista(const csr_plan* plan, const csr_wavelet* wav, int P, void* ws) {
+    Bump b{(char*)ws, 0};
+    FistaWs f;
+    const int ldc = wav ? round_up(wav->ncoef, 8) : plan->ld2n;
+    f.b = b.take<float>((size_t)P * plan->ld2m);
+    f.amask = b.take<float>((size_t)P * plan->m);
+    f.fwd_chan = b.take<float>((size_t)P * plan->m);
+    f.rscale = b.take<float>(P);
+    f.zscale = b.take<float>(P);
+    f.z = b.take<float>((size_t)P * ldc);
+    f.f_dirty = b.take<float>((size_t)P * plan->ld2n);
+    f.model = b.take<float>((size_t)P * plan->ld2m);
+    f.r_hi = b.take<__half>((size_t)P * plan->ld2m);
+    f.r_lo = b.take<__half>((size_t)P * plan->ld2m);
+    f.z_hi = b.take<__half>((size_t)P * plan->ld2n);
+    f.z_lo = b.take<__half>((size_t)P * plan->ld2n);
+    f.sig = f.gcoef = f.wav_ws = nullptr;
+    if (wav) {
+        f.sig = b.take<float>((size_t)P * plan->ld2n);
+        f.gcoef = b.take<float>((size_t)P * ldc);
+        f.wav_ws = b.take<float>((size_t)2 * P * wavelet_ld(wav));
+    }
+    f.bytes = b.off;
+    return f;
+}
+
+static int transform(csr_plan* plan, bool adjoint, const float* in, const float* chan_scale, int chan_pp,
+                     const float* row_scale, float* out, int P, void* ws, size_t ws_bytes, cudaStream_t stream) {
+    CSR_REQUIRE(plan && in && out && P > 0, "transform: bad argument");
+    TransformWs t = carve_transform(plan, P, ws);
+    if (!ws || ws_bytes < t.bytes) {
+        set_error("transform: workspace too small (%zu < %zu)", ws_bytes, t.bytes);
+        return CSR_ERR_WORKSPACE;
+    }
+    CSR_CUDA(cudaSetDevice(plan->device));
+    const int cols = adjoint ? 2 * plan->m : 2 * plan->n;
+    const int ld = adjoint ? plan->ld2m : plan->ld2n;
+    int rc;
+    // adjoint: the channel factor (w/s) multiplies the INPUT (ndft.py:32-34); forward: the OUTPUT (ndft.py:26-28)
+    rc = launch_split_rows(in, ld, P, cols, adjoint ? chan_scale : nullptr, chan_pp, plan->m, nullptr, 0, t.a_hi, t.a_lo,
+                           ld, t.a_scale, 0, stream);
+    if (rc) return rc;
+    GemmEpilogue e = {};
+    e.mode = EPI_PLAIN;
+    e.a_scale = t.a_scale;
+    e.out = out;
+    e.row_scale = row_scale;
+    e.chan_scale = adjoint ? nullptr : chan_scale;
+    e.chan_per_pixel = chan_pp;
+    return launch_dft_gemm(plan, adjoint, t.a_hi, t.a_lo, P, e, stream);
+}
+
+}  // namespace csr
+
+using namespace csr;
+
+extern "C" size_t csr_transform_ws_bytes(const csr_plan* plan, int P) {
+    if (!plan || P <= 0) return 0;
+    return carve_transform(plan, P, nullptr).bytes;
+}
+
+extern "C" int csr_forward(csr_plan* plan, const float* x, const float* chan_scale, int chan_per_pixel,
+                           const float* row_scale, float* out, int P, void* ws, size_t ws_bytes, void* stream) {
+    return transform(plan, false, x, chan_scale, chan_per_pixel, row_scale, out, P, ws, ws_bytes, (cudaStream_t)stream);
+}
+
+extern "C" int csr_adjoint(csr_plan* plan, const float* b, const float* chan_scale, int chan_per_pixel,
+                           const float* row_scale, float* out, int P, void* ws, size_t ws_bytes, void* stream) {
+    return transform(plan, true, b, chan_scale, chan_per_pixel, row_scale, out, P, ws, ws_bytes, (cudaStream_t)stream);
+}
+
+extern "C" size_t csr_fista_ws_bytes(const csr_plan* plan, const csr_wavelet* wav, int P) {
+    if (!plan || P <= 0) return 0;
+    return carve_fista(plan, wav, P, nullptr).bytes;
+}
+
+extern "C" int csr_fista(csr_plan* plan, csr_wavelet* wav, const csr_fista_args* args, void* ws, size_t ws_bytes,
+                         void* stream_) {
+    CSR_REQUIRE(plan && args, "csr_fista: null plan or args");
+    const csr_fista_args& a = *args;
+    CSR_REQUIRE(a.P > 0 && a.iters >= 0, "csr_fista: P=%d iters=%d", a.P, a.iters);
+    CSR_REQUIRE(a.data && a.w && a.s && a.k && a.x && a.lambda0 && a.noise, "csr_fista: null input array");
+    const int P = a.P, m = plan->m, n = plan->n;
+    const int ncoef = wav ? wav->ncoef : 2 * n;
+    if (wav) CSR_REQUIRE(wav->N == 2 * n, "csr_fista: wavelet length %d does not match 2n = %d", wav->N, 2 * n);
+    CSR_REQUIRE(a.ldx >= ncoef && a.ldx % 8 == 0, "csr_fista: ldx=%d must be >= %d and a multiple of 8", a.ldx, ncoef);
+    if (!wav) CSR_REQUIRE(a.ldx == plan->ld2n, "csr_fista: delta basis needs ldx == ld2n (%d)", plan->ld2n);
+    FistaWs w = carve_fista(plan, wav, P, ws);
+    if (!ws || ws_bytes < w.bytes) {
+        set_error("csr_fista: workspace too small (%zu < %zu)", ws_bytes, w.bytes);
+        return CSR_ERR_WORKSPACE;
+    }
+    if (wav) CSR_REQUIRE(round_up(wav->ncoef, 8) == a.ldx, "csr_fista: wavelet basis needs ldx == round_up(ncoef, 8)");
+    cudaStream_t stream = (cudaStream_t)stream_;
+    CSR_CUDA(cudaSetDevice(plan->device));
+    int rc;
+    const int ld2m = plan->ld2m, ld2n = plan->ld2n, ldc = a.ldx;
+    float* f_dirty = a.f_dirty ? a.f_dirty : w.f_dirty;
+    float* model = a.model ? a.model : w.model;
+
+    // 1. diagonals and the data term b = (w/(s k)) d; its scale drives every residual operand
+    if ((rc = launch_prepare(plan, a, w.b, w.amask, w.fwd_chan, stream))) return rc;
+    if ((rc = launch_split_rows(w.b, ld2m, P, 2 * m, nullptr, 0, m, nullptr, 0, w.r_hi, w.r_lo, ld2m, w.rscale, 0, stream)))
+        return rc;
+
+    // 2. dirty spectrum F_dirty = backward(data) = E^H b   (chi2.py:18-19)
+    {
+        GemmEpilogue e = {};
+        e.mode = EPI_PLAIN;
+        e.a_scale = w.rscale;
+        e.out = f_dirty;
+        if ((rc = launch_dft_gemm(plan, true, w.r_hi, w.r_lo, P, e, stream))) return rc;
+    }
+
+    // 3. initial state: x0 (given, or F_dirty / its coefficients), z = x0
+    float* x = a.x;
+    if (a.use_dirty_as_guess) {
+        if (wav) {
+            if ((rc = wavelet_decompose(wav, f_dirty, ld2n, x, ldc, P, w.wav_ws, stream))) return rc;
+        } else {
+            CSR_CUDA(cudaMemcpyAsync(x, f_dirty, sizeof(float) * (size_t)P * ld2n, cudaMemcpyDeviceToDevice, stream));
+        }
+    }
+    CSR_CUDA(cudaMemcpyAsync(w.z, x, sizeof(float) * (size_t)P * ldc, cudaMemcpyDeviceToDevice, stream));
+    // operand scale of the phi-space vector: from the dirty spectrum and the starting point
+    if (wav) {
+        if ((rc = wavelet_reconstruct(wav, w.z, ldc, w.sig, ld2n, P, w.wav_ws, stream))) return rc;
+        if ((rc = launch_split_rows(w.sig, ld2n, P, 2 * n, nullptr, 0, m, f_dirty, ld2n, w.z_hi, w.z_lo, ld2n, w.zscale, 0, stream)))
+            return rc;
+    } else {
+        if ((rc = launch_split_rows(w.z, ld2n, P, 2 * n, nullptr, 0, m, f_dirty, ld2n, w.z_hi, w.z_lo, ld2n, w.zscale, 0, stream)))
+            return rc;
+    }
+    if (a.delta) CSR_CUDA(cudaMemsetAsync(a.delta, 0, sizeof(float) * P, stream));
+
+    // 4. iterations
+    double t = 1.0;
+    for (int it = 0; it < a.iters; ++it) {
+        const double t0 = t;
+        t = 0.5 * (1.0 + sqrt(1.0 + 4.0 * t * t));
+        const float beta = (float)((t0 - 1.0) / t);
+        const bool last = (it == a.iters - 1);
+        if (wav && it > 0) {  // (iteration 0 reuses the split made above)
+            if ((rc = wavelet_reconstruct(wav, w.z, ldc, w.sig, ld2n, P, w.wav_ws, stream))) return rc;
+            if ((rc = launch_split_rows(w.sig, ld2n, P, 2 * n, nullptr, 0, m, nullptr, 0, w.z_hi, w.z_lo, ld2n, w.zscale, 1, stream)))
+                return rc;
+        }
+        {
+            GemmEpilogue e = {};
+            e.mode = EPI_RESID;
+            e.a_scale = w.zscale;
+            e.chan_scale = w.amask;
+            e.chan_per_pixel = a.w_per_pixel;
+            e.b = w.b;
+            e.out_hi = w.r_hi;
+            e.out_lo = w.r_lo;
+            e.out_scale = w.rscale;
+            if ((rc = launch_dft_gemm(plan, false, w.z_hi, w.z_lo, P, e, stream))) return rc;
+        }
+        if (!wav) {
+            GemmEpilogue e = {};
+            e.mode = EPI_FISTA;
+            e.a_scale = w.rscale;
+            e.x = x;
+            e.z = w.z;
+            e.out_hi = w.z_hi;
+            e.out_lo = w.z_lo;
+            e.out_scale = w.zscale;
+            e.lambda0 = a.lambda0;
+            e.noise = a.noise;
+            e.iter_cap = a.iter_cap;
+            e.iter = it;
+            e.step = a.step;
+            e.beta = beta;
+            e.delta = (last && a.delta) ? a.delta : nullptr;
+            if ((rc = launch_dft_gemm(plan, true, w.r_hi, w.r_lo, P, e, stream))) return rc;
+        } else {
+            GemmEpilogue e = {};
+            e.mode = EPI_PLAIN;
+            e.a_scale = w.rscale;
+            e.out = w.sig;  // gradient in phi space
+            if ((rc = launch_dft_gemm(plan, true, w.r_hi, w.r_lo, P, e, stream))) return rc;
+            if ((rc = wavelet_decompose(wav, w.sig, ld2n, w.gcoef, ldc, P, w.wav_ws, stream))) return rc;
+            if ((rc = launch_coef_update(w.gcoef, x, w.z, ldc, ncoef, P, a.lambda0, a.noise, a.iter_cap, it, a.step, beta,
+                                         (last && a.delta) ? a.delta : nullptr, stream)))
+                return rc;
+        }
+    }
+    if (a.delta && a.iters > 0) {
+        if ((rc = launch_scale_vec(a.delta, P, 1.0f / (float)ncoef, stream))) return rc;
+    }
+
+    // 5. final evaluate F(x): model_data, residual, chi2 and L1 values (fista.py:107; chi2.py:21-32)
+    if (a.model || a.residual || a.cost) {
+        const float* xs = x;
+        if (wav) {
+            if ((rc = wavelet_reconstruct(wav, x, ldc, w.sig, ld2n, P, w.wav_ws, stream))) return rc;
+            xs = w.sig;
+        }
+        if ((rc = launch_split_rows(xs, ld2n, P, 2 * n, nullptr, 0, m, nullptr, 0, w.z_hi, w.z_lo, ld2n, w.zscale, 0, stream)))
+            return rc;
+        GemmEpilogue e = {};
+        e.mode = EPI_PLAIN;
+        e.a_scale = w.zscale;
+        e.out = model;
+        e.row_scale = a.k;
+        e.chan_scale = w.fwd_chan;
+        e.chan_per_pixel = a.w_per_pixel;
+        if ((rc = launch_dft_gemm(plan, false, w.z_hi, w.z_lo, P, e, stream))) return rc;
+        if ((rc = launch_finalize(plan, a, model, a.residual, x, ldc, ncoef, stream))) return rc;
+    }
+    return CSR_OK;
+}

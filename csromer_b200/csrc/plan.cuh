@@ -1,0 +1,72 @@
+// plan.cuh -- internal definitions shared by the translation units of libcsromer_b200.so
+#pragma once
+#include "common.cuh"
+
+struct csr_plan {
+    int device;
+    int m, n;        // channels, Faraday-depth samples
+    int ld2m, ld2n;  // row pitches (elements) of every [P, 2m] / [P, 2n] matrix, multiples of 8
+    int num_sms;
+    double l2_ref;
+    double* d_l2;    // [m]  lambda2_i as given (device, fp64); l2_ref is subtracted in the kernels
+    double* d_phi;   // [n]
+    // twiddle tables, real 2m x 2n matrix T = [[cos, -sin], [sin, cos]] scaled by kTwiddleScale, fp16 hi/lo
+    __half* T_hi;    // [2m rows, ld2n]  B operand of the forward GEMM  (N = 2m, K = 2n)
+    __half* T_lo;
+    __half* Tt_hi;   // [2n rows, ld2m]  B operand of the adjoint GEMM  (N = 2n, K = 2m)
+    __half* Tt_lo;
+    CUtensorMap map_fwd_hi, map_fwd_lo, map_adj_hi, map_adj_lo;
+    size_t table_bytes;
+};
+
+struct csr_wavelet {
+    int device;
+    int kind;  // 0 = undecimated (swt), 1 = decimated (dwt, periodization)
+    int F, levels, N, append_signal, norm;
+    int ncoef;             // total coefficient length incl. appended signal
+    int sizes[34];         // band lengths  [cA_L, cD_L, ..., cD_1]
+    int offsets[34];       // band offsets inside the coefficient vector (after the appended signal)
+    float dec_lo[64], dec_hi[64], rec_lo[64], rec_hi[64];  // host copies (norm already applied)
+};
+
+namespace csr {
+
+// GEMM geometry (dft_gemm.cu)
+constexpr int BM = 128;  // lines of sight per tile (UMMA M)
+constexpr int BN = 256;  // output columns per tile (UMMA N)
+constexpr int BK = 64;   // fp16 elements per K block = one 128-byte swizzle row
+
+enum EpilogueMode { EPI_PLAIN = 0, EPI_RESID = 1, EPI_FISTA = 2 };
+
+struct GemmEpilogue {
+    // common
+    int mode;
+    int P, N, ld_out;          // valid rows / columns, output pitch
+    int m;                     // channels (column -> channel index = c mod m) for chan_scale / a
+    const float* a_scale;      // [P] power-of-two scale the A operand rows were multiplied by
+    // EPI_PLAIN: out = row_scale[p] * chan_scale[p?, c mod m] * y
+    float* out;
+    const float* row_scale;    // [P] or null
+    const float* chan_scale;   // [m] / [P, m] or null
+    int chan_per_pixel;
+    // EPI_RESID: r = a[p?, c mod m] * y - b[p, c]  ->  fp16 hi/lo scaled by out_scale[p]
+    const float* b;            // [P, ld_out]
+    __half* out_hi;
+    __half* out_lo;
+    const float* out_scale;    // [P]
+    // EPI_FISTA: u = z - step*y ; x = soft(u, step*lam) ; z = x + beta (x - x_old)
+    float* x;
+    float* z;                  // z also written as fp16 hi/lo (out_hi/out_lo, scaled by out_scale)
+    const float* lambda0;
+    const float* noise;
+    const int* iter_cap;       // [P] per-line-of-sight iteration cap or null
+    int iter;
+    float step, beta;
+    float* delta;              // [P] sum |x - x_old| (atomicAdd), may be null
+};
+
+int make_operand_map(CUtensorMap* map, const void* base, int rows, int cols, int ld, int box_rows);
+int launch_dft_gemm(const csr_plan* plan, bool adjoint, const __half* a_hi, const __half* a_lo, int P,
+                    const GemmEpilogue& epi, cudaStream_t stream);
+
+}  // namespace csr

@@ -1,0 +1,86 @@
+"""``Parameter`` -- the Faraday-depth-space container (phi grid + the vector being reconstructed).
+
+Host-side mirror of the reference's ``reconstruction/parameter.py:26-137``.  ``data`` keeps phi (or the
+coefficient index) on axis 0, so a batch is ``(n, P)`` complex, ``(2n, P)`` planar real or ``(ncoef, P)``
+wavelet coefficients.  As in the reference, assigning ``data`` overwrites ``n`` with ``len(data)``
+ -- operators therefore use ``len(parameter.phi)``, never ``parameter.n``.
+``convolve`` (the restore step, parameter.py:139-169) is a "next" row of SURVEY.md section 8f and not built yet.
+"""
+import numpy as np
+
+from ..utils import complex_to_real, next_power_2, real_to_complex
+
+
+def _is_complex(a):
+    return np.iscomplexobj(a) if isinstance(a, np.ndarray) else bool(getattr(a, "is_complex", lambda: False)())
+
+
+class Parameter:
+
+    def __init__(self, phi=None, cellsize=None, data=None):
+        self._data = None
+        self._n = 0
+        self.phi = phi
+        self.cellsize = cellsize
+        self.rmtf_fwhm = 0.0
+        self.max_recovered_width = 0.0
+        self.max_faraday_depth = 0.0
+        if phi is not None:
+            self._n = len(phi)
+        self.data = data
+        if phi is not None:  # phi wins over data for the initial n, like the reference constructor
+            self._n = len(phi)
+
+    @property
+    def data(self):
+        return self._data
+
+    @data.setter
+    def data(self, val):
+        self._data = val
+        if val is not None:
+            self._n = len(val)
+
+    @property
+    def n(self):
+        return self._n
+
+    @n.setter
+    def n(self, val):
+        self._n = val
+
+    def calculate_cellsize(self, dataset=None, oversampling=None, cellsize=None, set_size_pow_2=False, verbose=True):
+        """phi grid from the lambda2 coverage: FWHM of the RMTF, largest recoverable scale, maximum depth,
+        ``n`` rounded down to a multiple of 32 (or up to a power of two)."""
+        if dataset is None:
+            return
+        l2 = np.asarray(dataset.lambda2)
+        l2_min = np.min(l2[np.nonzero(l2)])
+        l2_max = np.max(l2)
+        fwhm = 2.0 * np.sqrt(3.0) / (l2_max - l2_min)
+        widest = np.pi / l2_min
+        phi_max = max(np.sqrt(3) / dataset.delta_l2_mean, fwhm * 10.0)
+        self.rmtf_fwhm, self.max_recovered_width, self.max_faraday_depth = fwhm, widest, phi_max
+        if verbose:
+            print("FWHM of the main peak of the RMTF: {0:.3f} rad/m^2".format(fwhm))
+            print("Maximum recovered width structure: {0:.3f} rad/m^2".format(widest))
+            print("Maximum Faraday Depth to which one has more than 50% sensitivity: {0:.3f}".format(phi_max))
+        if oversampling is None:
+            oversampling = 8.0
+        phi_r = min(fwhm, widest) / oversampling if cellsize is None else cellsize
+        cells = int(np.int32(np.floor(2 * phi_max / phi_r)))
+        n = next_power_2(cells) if set_size_pow_2 else int(cells - cells % 32)
+        self.cellsize = 2 * phi_max / n
+        self.phi = self.cellsize * np.arange(-(n / 2), (n / 2), 1)
+        self.data = np.zeros_like(self.phi, dtype=np.complex64)
+        self._n = n
+
+    def complex_data_to_real(self):
+        if not _is_complex(self._data):
+            raise TypeError("Parameter data is not complex64")
+        self.data = complex_to_real(self._data)
+
+    def real_data_to_complex(self):
+        if _is_complex(self._data):
+            raise ValueError("Parameter data is not real")
+        self.data = real_to_complex(self._data)

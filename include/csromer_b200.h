@@ -1,0 +1,139 @@
+/* csromer_b200.h -- C ABI of the B200 (sm_100a) CS-ROMER reconstruction hot path.
+ *
+ * The reference (miguelcarcamov/csromer) is pure Python and has no FFI; its boundary for this path is the
+ * Python class API.  This header is the C-ABI a host binding (ctypes here, cgo/JNI elsewhere) talks to; each
+ * entry point names the reference method it replaces (paths relative to src/csromer/ in the reference).
+ *
+ * Conventions
+ *   - every function returns 0 on success or a negative csr_status; csr_last_error() gives the text
+ *     (thread-local).  Nothing throws.  There is NO CPU fallback: without a CUDA device every compute call
+ *     fails with CSR_ERR_CUDA.
+ *   - all array arguments are DEVICE pointers owned by the caller; calls are asynchronous on `stream`
+ *     (a cudaStream_t passed as void*).  Plans own the twiddle tables only.
+ *   - real "planar" packing everywhere: a complex vector of length L is 2L floats [Re(0..L) | Im(0..L)]
+ *     (utils/utilities.py:27-32).  Pixel-major: row p of a [P, ld] matrix is line of sight p; `ld` is the
+ *     row pitch in elements and must be a multiple of 8.
+ *   - "ws" is caller-provided scratch of at least the size the matching *_ws_bytes function returns,
+ *     256-byte aligned.
+ */
+#ifndef CSROMER_B200_H
+#define CSROMER_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct csr_plan csr_plan;
+typedef struct csr_wavelet csr_wavelet;
+
+typedef enum {
+    CSR_OK = 0,
+    CSR_ERR_ARG = -1,       /* bad argument (null pointer, size, pitch, alignment) */
+    CSR_ERR_CUDA = -2,      /* CUDA runtime / driver error, or no sm_100 device */
+    CSR_ERR_WORKSPACE = -3, /* workspace too small */
+    CSR_ERR_UNSUPPORTED = -4
+} csr_status;
+
+const char* csr_last_error(void);
+int csr_version(void);
+
+/* ---- plan: the shared twiddle matrix E[i,j] = exp(+2i (lambda2_i - l2_ref) phi_j) ----------------------
+ * Replaces the per-call np.exp(...) of transformers/dfts/ndft.py:19,25,34,42 and the pynufft plan of
+ * transformers/dfts/nufft.py:36-48.  lambda2/phi are HOST pointers (double).  Tables are built on the device
+ * in fp64 and stored as scaled fp16 hi/lo pairs in both operand orientations. */
+int csr_plan_create(csr_plan** out, const double* lambda2, int m, double l2_ref, const double* phi, int n,
+                    int device);
+void csr_plan_destroy(csr_plan* plan);
+int csr_plan_dims(const csr_plan* plan, int* m, int* n, int* ld2m, int* ld2n, size_t* table_bytes);
+
+/* ---- single transforms -------------------------------------------------------------------------------
+ * csr_forward : out[p, c] = row_scale[p] * chan_scale[p?, c mod m] * sum_j E x      [P, ld2n] -> [P, ld2m]
+ *               NDFT1D.forward / forward_normalized (ndft.py:17-28), NUFFT1D.forward* (nufft.py:50-59).
+ * csr_adjoint : out[p, j] = row_scale[p] * sum_i conj(E) (chan_scale[p?, i] * b)    [P, ld2m] -> [P, ld2n]
+ *               NDFT1D.backward / RMTF (ndft.py:30-43), NUFFT1D.backward / RMTF (nufft.py:61-77).
+ * chan_scale: [m] (chan_per_pixel = 0) or [P, m] (1) or NULL (= 1); row_scale: [P] or NULL (= 1). */
+size_t csr_transform_ws_bytes(const csr_plan* plan, int P);
+int csr_forward(csr_plan* plan, const float* x, const float* chan_scale, int chan_per_pixel,
+                const float* row_scale, float* out, int P, void* ws, size_t ws_bytes, void* stream);
+int csr_adjoint(csr_plan* plan, const float* b, const float* chan_scale, int chan_per_pixel,
+                const float* row_scale, float* out, int P, void* ws, size_t ws_bytes, void* stream);
+
+/* ---- Galactic-RM de-rotation: d_i <- d_i * exp(-2i phi_gal[p] lambda2_i) (base/dataset.py:377-381) ---- */
+int csr_derotate(csr_plan* plan, float* data, const float* phi_gal, int P, void* stream);
+
+/* ---- wavelet dictionaries (dictionaries/undecimated.py, dictionaries/discrete.py; PyWavelets semantics) --
+ * kind: 0 = undecimated (pywt.swt/iswt, trim_approx=True), 1 = decimated (pywt.wavedec/waverec,
+ * mode="periodization").  The transform acts on the real planar vector of length N = 2n as ONE signal
+ * (objectivefunction/priors/chi2.py:44-55).  Filters are HOST double arrays of length F (even). */
+int csr_wavelet_create(csr_wavelet** out, int kind, const double* dec_lo, const double* dec_hi,
+                       const double* rec_lo, const double* rec_hi, int F, int level, int N, int append_signal,
+                       int norm, int device);
+void csr_wavelet_destroy(csr_wavelet* wav);
+int csr_wavelet_ncoef(const csr_wavelet* wav);     /* coefficient vector length (incl. appended signal) */
+int csr_wavelet_levels(const csr_wavelet* wav);
+int csr_wavelet_level_sizes(const csr_wavelet* wav, int* sizes, int cap); /* [cA_L, cD_L, ..., cD_1] */
+size_t csr_wavelet_ws_bytes(const csr_wavelet* wav, int P);
+/* decompose: signal [P, ld_sig] -> coefficients [P, ld_coef];  reconstruct: the inverse */
+int csr_wavelet_decompose(csr_wavelet* wav, const float* signal, int ld_sig, float* coef, int ld_coef, int P,
+                          void* ws, size_t ws_bytes, void* stream);
+int csr_wavelet_reconstruct(csr_wavelet* wav, const float* coef, int ld_coef, float* signal, int ld_sig, int P,
+                            void* ws, size_t ws_bytes, void* stream);
+
+/* ---- fused fixed-iteration FISTA (optimization/methods/fista.py:41-108 with Chi2.calculate_gradient_fista,
+ * objectivefunction/priors/chi2.py:43-56, and L1.calculate_prox, priors/l1.py:30-32), all P lines of sight
+ * at once.
+ *   data      [P, ld2m]  measured polarisation, planar                                (Dataset.data)
+ *   w         [m] or [P, m]  weights, 0 = flagged                                      (Dataset.w)
+ *   s         [m]            spectral factor                                           (Dataset.s)
+ *   k         [P]            normaliser sum(w/s) as held by the dataset object         (Dataset.k)
+ *   x         [P, ldx]   in: initial guess; out: solution.  ldx = ld2n (delta basis) or the coefficient
+ *                         pitch (wavelet basis; wav != NULL)                           (Parameter.data)
+ *   lambda0, noise [P]   regularisation and its per-iteration decrement                (L1.reg, FISTA.noise)
+ *   iters                common iteration cap (FISTA.maxiter); a line of sight whose lambda would become
+ *                         <= 0 freezes (fista.py:100-106); noise >= lambda0 leaves x untouched (:74-77)
+ *   step                 gradient step (1.0 = reference behaviour)
+ * outputs (each optional, may be NULL):
+ *   f_dirty   [P, ld2n]  Chi2.F_dirty = backward(data)                                 (chi2.py:18-19)
+ *   model     [P, ld2m]  Dataset.model_data after the final evaluate                   (chi2.py:28)
+ *   residual  [P, ld2m]  Dataset.residual = data - model_data                          (dataset.py:374-375)
+ *   cost      [P, 2]     chi2 value, L1 value of the final x (F = chi2 + lambda_final * l1)
+ *   delta     [P]        sum |x_new - x_old| of the last iteration / len(x)            (fista.py:89)
+ */
+typedef struct {
+    int P;
+    int iters;
+    float step;
+    float norm_factor;
+    int w_per_pixel;
+    const float* data;
+    const float* w;
+    const float* s;
+    const float* k;
+    float* x;
+    int ldx;
+    const float* lambda0;
+    const float* noise;
+    const int* iter_cap;    /* [P] optional per-line-of-sight iteration cap (floor(lambda/noise) when
+                               FISTA.maxiter is None, fista.py:59-66); NULL = `iters` for everyone */
+    float* f_dirty;
+    float* model;
+    float* residual;
+    float* cost;
+    float* delta;
+    int use_dirty_as_guess; /* 1: ignore x on input and start from F_dirty (README.md:186) / its coefficients */
+} csr_fista_args;
+
+size_t csr_fista_ws_bytes(const csr_plan* plan, const csr_wavelet* wav, int P);
+int csr_fista(csr_plan* plan, csr_wavelet* wav, const csr_fista_args* args, void* ws, size_t ws_bytes,
+              void* stream);
+
+/* number of kernels launched by this library on the calling thread since the last reset (bench accounting) */
+long long csr_launch_count(int reset);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CSROMER_B200_H */

@@ -238,8 +238,8 @@ def _idwt_per(cA, cD, rec_lo, rec_hi):
 def iswt(coeffs, bank, norm=False):
     """pywt.iswt for the trim_approx list [cA_L, cD_L, ..., cD_1] (dictionaries/undecimated.py:159)."""
     rec_lo, rec_hi = bank[2], bank[3]
-    if norm:
-        rec_lo, rec_hi = rec_lo / np.sqrt(2), rec_hi / np.sqrt(2)
+    if norm:  # pywt.iswt(norm=True) rescales the bank by sqrt(2) (swt(norm=True) by 1/sqrt(2))
+        rec_lo, rec_hi = rec_lo * np.sqrt(2), rec_hi * np.sqrt(2)
     out = np.array(coeffs[0], dtype=np.float64, copy=True)
     L = len(coeffs) - 1
     N = out.shape[0]
