@@ -82,6 +82,14 @@ def unpack_complex(t, length, pix, like_torch=False):
     return c if like_torch else c.cpu().numpy()
 
 
+def unpack_complex_like(t, length, pix, like):
+    """as ``unpack_complex`` but typed and placed like ``like``: numpy in -> numpy out, torch in -> torch on the
+    same device (host tensors get the result copied back)."""
+    if not is_torch(like):
+        return unpack_complex(t, length, pix)
+    return unpack_complex(t, length, pix, like_torch=True).to(like.device)
+
+
 def unpack_real(t, length, pix, like_torch=False):
     r = t[:, :length].t().contiguous().reshape((length,) + tuple(pix))
     return r if like_torch else r.cpu().numpy()

@@ -86,7 +86,7 @@ class Dataset:
             return
         val = np.asarray(val, dtype=np.float64)
         # lambda2 ascending <=> frequency descending
-        self.lambda2 = ((SPEED_OF_LIGHT / val) ** 2)[::-1]
+        self.lambda2 = np.ascontiguousarray(((SPEED_OF_LIGHT / val) ** 2)[::-1])
 
     @property
     def lambda2(self):
@@ -99,7 +99,7 @@ class Dataset:
             return
         val = np.asarray(val, dtype=np.float64)
         if val.size > 1 and np.all(np.diff(val) < 0):
-            val = val[::-1]
+            val = np.ascontiguousarray(val[::-1])
         self._lambda2 = val
         self._m = len(val)
         self._nu = SPEED_OF_LIGHT / np.sqrt(val)

@@ -23,6 +23,8 @@
 // next chunk runs; the fused epilogue of tile t overlaps the first chunks of tile t+1 the same way.
 #include <stdlib.h>
 
+#include <vector>
+
 #include "plan.cuh"
 
 namespace csr {
@@ -355,6 +357,14 @@ static int gemm_chunk_kb() {
     return v;
 }
 
+// ---- optional per-launch timing (bench.py's roofline leg): CUDA events on the launching stream ----------
+struct ProfiledLaunch {
+    int kind;  // mode * 2 + adjoint
+    cudaEvent_t start, stop;
+};
+static bool g_profile = false;
+static std::vector<ProfiledLaunch> g_profiled;
+
 template <int MODE>
 static int launch_mode(const csr_plan* plan, bool adjoint, const CUtensorMap& a_hi, const CUtensorMap& a_lo, int P,
                        const GemmEpilogue& epi, cudaStream_t stream) {
@@ -368,10 +378,21 @@ static int launch_mode(const csr_plan* plan, bool adjoint, const CUtensorMap& a_
     const int MT = (P + BM - 1) / BM;
     const int NT = (N + BN - 1) / BN;
     const int grid = min(MT * NT, plan->num_sms);
+    ProfiledLaunch rec;
+    if (g_profile) {
+        rec.kind = MODE * 2 + (adjoint ? 1 : 0);
+        CSR_CUDA(cudaEventCreate(&rec.start));
+        CSR_CUDA(cudaEventCreate(&rec.stop));
+        CSR_CUDA(cudaEventRecord(rec.start, stream));
+    }
     dft_gemm_kernel<MODE><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(
         a_hi, a_lo, adjoint ? plan->map_adj_hi : plan->map_fwd_hi, adjoint ? plan->map_adj_lo : plan->map_fwd_lo, K,
         MT, NT, gemm_chunk_kb(), epi);
     CSR_LAUNCHED();
+    if (g_profile) {
+        CSR_CUDA(cudaEventRecord(rec.stop, stream));
+        g_profiled.push_back(rec);
+    }
     return CSR_OK;
 }
 
@@ -400,3 +421,30 @@ int launch_dft_gemm(const csr_plan* plan, bool adjoint, const __half* a_hi, cons
 }
 
 }  // namespace csr
+
+using namespace csr;
+
+// kinds: 0 plain-forward, 1 plain-adjoint, 2 resid-forward, 3 resid-adjoint, 4 fista-forward, 5 fista-adjoint
+extern "C" int csr_profile(int enable) {
+    g_profile = enable != 0;
+    return CSR_OK;
+}
+
+extern "C" int csr_profile_collect(double* ms_by_kind, long long* count_by_kind) {
+    CSR_REQUIRE(ms_by_kind && count_by_kind, "csr_profile_collect: null pointer");
+    for (int i = 0; i < 6; ++i) {
+        ms_by_kind[i] = 0.0;
+        count_by_kind[i] = 0;
+    }
+    for (auto& r : g_profiled) {
+        CSR_CUDA(cudaEventSynchronize(r.stop));
+        float ms = 0.f;
+        CSR_CUDA(cudaEventElapsedTime(&ms, r.start, r.stop));
+        ms_by_kind[r.kind] += ms;
+        count_by_kind[r.kind] += 1;
+        cudaEventDestroy(r.start);
+        cudaEventDestroy(r.stop);
+    }
+    g_profiled.clear();
+    return CSR_OK;
+}

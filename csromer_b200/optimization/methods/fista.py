@@ -140,7 +140,7 @@ class FISTA(Optimizer):
                          wavelet=engine, iter_cap=cap_t)
 
         # side effects the reference leaves behind
-        ds.model_data = dv.unpack_complex(out["model"], plan.m, pix, like_torch=dv.is_torch(ds.data))
+        ds.model_data = dv.unpack_complex_like(out["model"], plan.m, pix, ds.data)
         lam_final = _decayed_lambda(lam0, noise, iters if cap is None else np.minimum(cap, iters))
         l1.reg = lam_final
         cost_t = out["cost"].double().cpu().numpy()
@@ -152,7 +152,12 @@ class FISTA(Optimizer):
                 self.F_obj.values[0], self.F_obj.values[1] = chi_v, l1_v
             except (IndexError, TypeError):
                 pass
-        param = copy.deepcopy(self.guess_param)
+        # deep copy of the guess like the reference (fista.py:37-38), minus its (about to be replaced) data array
+        held, self.guess_param._data = self.guess_param._data, None
+        try:
+            param = copy.deepcopy(self.guess_param)
+        finally:
+            self.guess_param._data = held
         xr = dv.unpack_real(x, ncoef, pix, like_torch)
         param.data = xr if like_torch else xr.astype(x0.dtype if np.asarray(x0).dtype.kind == "f" else np.float32)
         self.F_dirty = out["f_dirty"]

@@ -8,6 +8,14 @@ import numpy as np
 from ..base.dataset import Dataset
 
 
+def per_pixel_columns(lambda2, s, *params):
+    """Broadcast helper for batched sources: returns lambda2 and s as columns ``(m, 1, ...)`` and the parameters as
+    float64 arrays of one common pixel shape (scalars stay 0-d, so a single line of sight stays 1-D)."""
+    arrays = np.broadcast_arrays(*[np.asarray(p, dtype=np.float64) for p in params])
+    extra = (1,) * arrays[0].ndim
+    return lambda2.reshape((-1,) + extra), np.asarray(s).reshape((-1,) + extra), arrays
+
+
 class FaradaySource(Dataset):
 
     def __init__(self, s_nu=None, **kwargs):

@@ -1,7 +1,7 @@
 """``FaradayThinSource`` -- a single Faraday-thin component (reference: simulation/thinsource.py:10-29)."""
 import numpy as np
 
-from .faradaysource import FaradaySource
+from .faradaysource import FaradaySource, per_pixel_columns
 
 
 class FaradayThinSource(FaradaySource):
@@ -13,7 +13,7 @@ class FaradayThinSource(FaradaySource):
 
     def simulate(self):
         """s_nu (nu/nu_0)^alpha [cos(2 phi lambda2) + i sin(2 phi lambda2 + dchi)]; ``phi_gal`` / ``s_nu`` may be
-        per-pixel arrays, giving data of shape (m, *pix)."""
-        phase = 2.0 * np.multiply.outer(self.lambda2, np.asarray(self.phi_gal, dtype=np.float64))
-        amp = np.multiply.outer(self.s, np.asarray(self.s_nu, dtype=np.float64))
-        self.data = amp * (np.cos(phase) + 1j * np.sin(phase + self.dchi))
+        per-pixel arrays (same pixel shape), giving data of shape (m, *pix)."""
+        l2, s, (phi, flux) = per_pixel_columns(self.lambda2, self.s, self.phi_gal, self.s_nu)
+        phase = 2.0 * phi * l2
+        self.data = flux * s * (np.cos(phase) + 1j * np.sin(phase + self.dchi))

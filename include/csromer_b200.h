@@ -130,6 +130,13 @@ size_t csr_fista_ws_bytes(const csr_plan* plan, const csr_wavelet* wav, int P);
 int csr_fista(csr_plan* plan, csr_wavelet* wav, const csr_fista_args* args, void* ws, size_t ws_bytes,
               void* stream);
 
+/* per-launch timing of the transform GEMMs with CUDA events on the launching stream (measurement aid).
+ * csr_profile(1) starts recording; csr_profile_collect sums elapsed ms and launch counts into 6-entry arrays
+ * indexed [0 plain-forward, 1 plain-adjoint, 2 resid-forward, 3 resid-adjoint, 4 fista-forward, 5 fista-adjoint]
+ * and clears the record. */
+int csr_profile(int enable);
+int csr_profile_collect(double* ms_by_kind, long long* count_by_kind);
+
 /* number of kernels launched by this library on the calling thread since the last reset (bench accounting) */
 long long csr_launch_count(int reset);
 

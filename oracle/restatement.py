@@ -94,7 +94,10 @@ class ExactDFT:
     ``k`` may also be passed explicitly because in-place flagging leaves it stale in the reference
     (transformers/flaggers/mean_flagger.py:42)."""
 
-    def __init__(self, lambda2, phi, w=None, s=None, k=None, l2_ref=0.0):
+    def __init__(self, lambda2, phi, w=None, s=None, k=None, l2_ref=0.0, rebuild_twiddles=False):
+        # rebuild_twiddles=True reproduces the reference's COST profile as well as its values: ndft.py:19,25,34,42
+        # call np.exp on the full m x n matrix inside every transform.  Used only by bench.py's CPU baseline.
+        self.rebuild_twiddles = rebuild_twiddles
         self.lambda2 = np.asarray(lambda2, dtype=np.float64)
         self.phi = np.asarray(phi, dtype=np.float64)
         self.m, self.n = self.lambda2.shape[0], self.phi.shape[0]
@@ -102,8 +105,14 @@ class ExactDFT:
         self.s = np.ones(self.m) if s is None else np.asarray(s, dtype=np.float64)
         s_b = self.s if self.w.ndim == 1 else self.s[:, None]
         self.k = np.sum(self.w / s_b, axis=0) if k is None else k
-        l2 = self.lambda2 - l2_ref
-        self.E = np.exp(2.0j * l2[:, None] * self.phi[None, :])  # (m, n)
+        self._l2 = self.lambda2 - l2_ref
+        self._E = None if rebuild_twiddles else np.exp(2.0j * self._l2[:, None] * self.phi[None, :])  # (m, n)
+
+    @property
+    def E(self):
+        if self._E is not None:
+            return self._E
+        return np.exp(2.0j * self._l2[:, None] * self.phi[None, :])
 
     def _col(self, v, like):
         return v[:, None] if (v.ndim == 1 and like.ndim == 2) else v
@@ -123,6 +132,8 @@ class ExactDFT:
     def backward(self, b):
         """ndft.py:30-36: F_j = (1/k) sum_i (w_i/s_i) b_i exp(-2i..)."""
         wt = self._col(self.w, b) / self._col(self.s, b)
+        if self.rebuild_twiddles:  # the reference builds the conjugate matrix directly (ndft.py:34)
+            return (np.exp(-2.0j * self.phi[:, None] * self._l2[None, :]) @ (wt * b)) / self.k
         return (self.E.conj().T @ (wt * b)) / self.k
 
     def rmtf(self):
