@@ -17,11 +17,12 @@
 //   warp 0   : TMA producer   (cp.async.bulk.tensor -> 128B-swizzled smem ring, mbarrier complete_tx)
 //   warp 1   : MMA issuer     (one thread issues tcgen05.mma; tcgen05.commit frees smem stages / publishes
 //                              the accumulator); also owns the TMEM allocation
-//   warps 2-9: epilogue       (tcgen05.ld 32x32b -> register accumulators -> smem transpose -> coalesced I/O)
+//   warps 2-9: epilogue       (tcgen05.ld 16x256b -> register accumulators -> float2 / half2 global I/O)
 // TMEM holds two 128x256 fp32 accumulators used ping-pong per K CHUNK: the tensor core's fp32 accumulate
 // truncates, so partial sums are moved to registers (round-to-nearest adds) every `chunk_kb` K blocks while the
 // next chunk runs; the fused epilogue of tile t overlaps the first chunks of tile t+1 the same way.
 #include <stdlib.h>
+#include <string.h>
 
 #include <vector>
 
@@ -35,10 +36,9 @@ constexpr int B_TILE_BYTES = BN * BK * 2;  // 32 KiB
 constexpr int STAGE_BYTES = 2 * A_TILE_BYTES + 2 * B_TILE_BYTES;  // A_hi, A_lo, B_hi, B_lo = 96 KiB
 constexpr int EPI_WARPS = 8;               // 4 TMEM lane quarters x 2 column halves
 constexpr int EPI_COLS = BN / 2;           // accumulator columns held in registers per epilogue thread
-constexpr int NUM_THREADS = 64 + 32 * EPI_WARPS;
+constexpr int NUM_THREADS = 128 + 32 * EPI_WARPS;  // warpgroup 0: TMA producer, MMA issuer, 2 idle; warpgroups 1-2: epilogue
 constexpr int TMEM_COLS = 512;
-constexpr int TBUF_FLOATS = 32 * 33;
-constexpr int SMEM_BYTES = 1024 /*alignment slack*/ + STAGES * STAGE_BYTES + EPI_WARPS * TBUF_FLOATS * 4 + 256;
+constexpr int SMEM_BYTES = 1024 /*alignment slack*/ + STAGES * STAGE_BYTES + 256;
 constexpr int RASTER_GROUP = 16;  // pixel tiles per rasterisation group (keeps A and B panels L2-resident)
 static_assert(SMEM_BYTES <= 232448, "shared memory budget exceeded");
 
@@ -52,107 +52,138 @@ __device__ __forceinline__ void tile_coords(int t, int MT, int NT, int& mt, int&
     nt = local / gsize;
 }
 
-// acc[j] += TMEM[lane quarter, col0 + j]  for the 128 columns this thread owns
+// ---- accumulator fragment --------------------------------------------------------------------------------------
+// Each epilogue warp owns 32 rows (its TMEM lane quarter) x 128 columns of the tile and reads them with
+// tcgen05.ld.16x256b: thread T then holds, for every 8-column block, the two consecutive columns 2(T%4), 2(T%4)+1
+// of rows T/4 and T/4+8 -- the mma-style fragment in which 4 neighbouring lanes cover one 32-byte sector of a row.
+// Global I/O of the fused epilogues is done straight from these registers as float2 / half2 (no shared-memory
+// transpose, no shuffles).  Register index of (lh, ch, jj, rh, e):
+//     row = T/4 + 8*rh + 16*lh,  col = 64*ch + 8*jj + 2*(T%4) + e,  idx = (((lh*2 + ch)*8 + jj)*2 + rh)*2 + e
+__device__ __forceinline__ void tmem_ld_16x256b_x8(uint32_t taddr, float (&v)[32]) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.16x256b.x8.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// acc += the chunk accumulator in TMEM (taddr: this warp's lane quarter, first of its 128 columns)
 __device__ __forceinline__ void drain_chunk(uint32_t taddr, float (&acc)[EPI_COLS]) {
 #pragma unroll
-    for (int g = 0; g < EPI_COLS / 32; ++g) {
-        float v[32];
-        tmem_ld_32x32(taddr + (uint32_t)(g * 32), v);
+    for (int lh = 0; lh < 2; ++lh) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) acc[g * 32 + j] += v[j];
+        for (int ch = 0; ch < 2; ++ch) {
+            float v[32];
+            tmem_ld_16x256b_x8(taddr + ((uint32_t)(16 * lh) << 16) + (uint32_t)(64 * ch), v);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) acc[(lh * 2 + ch) * 32 + j] += v[j];
+        }
     }
 }
 
-// Fused epilogue on the register accumulators of one thread: row (row0 + sub*32 + lane), columns
-// [col0, col0 + EPI_COLS).  Each 32x32 block is transposed through shared memory so that every global access of
-// a warp is one contiguous 128-byte (fp32) / 64-byte (fp16) row segment.
+// Fused epilogue on the register fragment of one thread.  row0 / col0: first row of the warp's 32 rows and first
+// of its 128 columns.  Every (row, 8-column block) costs one float2 access per array; the loads of 8 blocks of a row
+// are issued together before their results are used (x / z alias, the compiler cannot hoist them itself).
 template <int MODE>
-__device__ __forceinline__ void epilogue_tile(const GemmEpilogue& epi, const float (&acc)[EPI_COLS], float* tb, int sub,
-                                              int lane, int row0, int col0) {
-    const int row_base = row0 + sub * 32;
-    const int my_row = row_base + lane;
-    const bool my_row_ok = my_row < epi.P;
-    // per-row parameters live in the lane that owns the row and are broadcast with shuffles
-    float descale_l = 0.f, oscale_l = 0.f, rs_l = 1.f, thr_l = 0.f;
-    int active_l = 0;
-    if (my_row_ok) {
-        descale_l = kTwiddleDescale / epi.a_scale[my_row];
-        if (MODE == EPI_PLAIN) {
-            rs_l = epi.row_scale ? epi.row_scale[my_row] : 1.f;
-        } else {
-            oscale_l = epi.out_scale[my_row];
-        }
-        if (MODE == EPI_FISTA) {
-            const float l0 = epi.lambda0[my_row], nz = epi.noise[my_row];
-            const float lam = l0 - (float)epi.iter * nz;
-            active_l = (nz < l0) && (epi.iter == 0 || lam > 0.f) && (!epi.iter_cap || epi.iter < epi.iter_cap[my_row]);
-            thr_l = epi.step * lam;
-            descale_l *= epi.step;
-        }
-    }
-    const int nrows = min(32, epi.P - row_base);
-
+__device__ __forceinline__ void epilogue_tile(const GemmEpilogue& epi, const float (&acc)[EPI_COLS], int lane, int row0,
+                                              int col0) {
+    const int quad = lane & 3;
 #pragma unroll
-    for (int g = 0; g < EPI_COLS / 32; ++g) {
-        const int colbase = col0 + g * 32;
-        if (colbase < epi.N && nrows > 0) {  // warp-uniform
+    for (int lh = 0; lh < 2; ++lh) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) tb[lane * 33 + j] = acc[g * 32 + j];
-            __syncwarp();
-            const int col = colbase + lane;
-            const bool colok = col < epi.N;
-            int ch = 0;
-            if (MODE != EPI_FISTA) ch = (col >= epi.m) ? col - epi.m : col;
-#pragma unroll 4
-            for (int rr = 0; rr < nrows; ++rr) {
-                const float a = tb[rr * 33 + lane];
-                const int row = row_base + rr;
-                const size_t o = (size_t)row * epi.ld_out + col;
-                const float descale = __shfl_sync(0xffffffffu, descale_l, rr);
+        for (int rh = 0; rh < 2; ++rh) {
+            const int row = row0 + (lane >> 2) + 8 * rh + 16 * lh;
+            const bool row_ok = row < epi.P;
+            float descale = 0.f, oscale = 0.f, rs = 1.f, thr = 0.f;
+            bool active = row_ok;
+            if (row_ok) {
+                descale = kTwiddleDescale / __ldg(epi.a_scale + row);
                 if (MODE == EPI_PLAIN) {
-                    const float rs = __shfl_sync(0xffffffffu, rs_l, rr);
-                    if (colok) {
-                        float cs = 1.f;
-                        if (epi.chan_scale) cs = epi.chan_scale[(epi.chan_per_pixel ? (size_t)row * epi.m : 0) + ch];
-                        epi.out[o] = a * descale * rs * cs;
-                    }
-                } else if (MODE == EPI_RESID) {
-                    const float os = __shfl_sync(0xffffffffu, oscale_l, rr);
-                    if (colok) {
-                        const float am = epi.chan_scale[(epi.chan_per_pixel ? (size_t)row * epi.m : 0) + ch];
-                        const float r = am * (a * descale) - epi.b[o];
-                        __half h, l;
-                        split_half(r * os, h, l);
-                        epi.out_hi[o] = h;
-                        epi.out_lo[o] = l;
-                    }
-                } else {  // EPI_FISTA
-                    const float os = __shfl_sync(0xffffffffu, oscale_l, rr);
-                    const float thr = __shfl_sync(0xffffffffu, thr_l, rr);
-                    const int active = __shfl_sync(0xffffffffu, active_l, rr);
-                    float d = 0.f;
-                    if (colok && active) {
-                        const float zo = epi.z[o];
-                        const float xo = epi.x[o];
-                        const float u = zo - a * descale;
-                        const float xn = copysignf(fmaxf(fabsf(u) - thr, 0.f), u);
-                        const float zn = xn + epi.beta * (xn - xo);
-                        epi.x[o] = xn;
-                        epi.z[o] = zn;
-                        __half h, l;
-                        split_half(zn * os, h, l);
-                        epi.out_hi[o] = h;
-                        epi.out_lo[o] = l;
-                        d = fabsf(xn - xo);
-                    }
-                    if (epi.delta != nullptr) {  // kernel-uniform
+                    rs = epi.row_scale ? __ldg(epi.row_scale + row) : 1.f;
+                } else {
+                    oscale = __ldg(epi.out_scale + row);
+                }
+                if (MODE == EPI_FISTA) {
+                    const float l0 = __ldg(epi.lambda0 + row), nz = __ldg(epi.noise + row);
+                    const float lam = l0 - (float)epi.iter * nz;
+                    active = (nz < l0) && (epi.iter == 0 || lam > 0.f) && (!epi.iter_cap || epi.iter < __ldg(epi.iter_cap + row));
+                    thr = epi.step * lam;
+                    descale *= epi.step;
+                }
+            }
+            const size_t row_off = (size_t)row * epi.ld_out;
+            const float* cs_row = nullptr;
+            if (MODE != EPI_FISTA && epi.chan_scale) cs_row = epi.chan_scale + (epi.chan_per_pixel ? (size_t)row * epi.m : 0);
+            float dsum = 0.f;
 #pragma unroll
-                        for (int s = 16; s > 0; s >>= 1) d += __shfl_xor_sync(0xffffffffu, d, s);
-                        if (lane == 0 && d != 0.f) atomicAdd(epi.delta + row, d);
+            for (int ch = 0; ch < 2; ++ch) {
+                float2 in0[8], in1[8];
+                bool ok[8];
+#pragma unroll
+                for (int jj = 0; jj < 8; ++jj) {
+                    const int col = col0 + 64 * ch + 8 * jj + 2 * quad;  // even; N is even, so col + 1 < N too
+                    ok[jj] = active && col < epi.N;
+                    in0[jj] = make_float2(0.f, 0.f);
+                    in1[jj] = make_float2(1.f, 1.f);
+                    if (ok[jj]) {
+                        if (MODE == EPI_FISTA) {
+                            in0[jj] = __ldcg(reinterpret_cast<const float2*>(epi.z + row_off + col));
+                            in1[jj] = __ldcg(reinterpret_cast<const float2*>(epi.x + row_off + col));
+                        } else {
+                            if (MODE == EPI_RESID) in0[jj] = __ldcg(reinterpret_cast<const float2*>(epi.b + row_off + col));
+                            if (cs_row) {
+                                const int c0 = col >= epi.m ? col - epi.m : col;
+                                const int c1 = col + 1 >= epi.m ? col + 1 - epi.m : col + 1;
+                                in1[jj] = make_float2(__ldg(cs_row + c0), __ldg(cs_row + c1));
+                            }
+                        }
+                    }
+                }
+#pragma unroll
+                for (int jj = 0; jj < 8; ++jj) {
+                    if (!ok[jj]) continue;
+                    const int col = col0 + 64 * ch + 8 * jj + 2 * quad;
+                    const int ai = (((lh * 2 + ch) * 8 + jj) * 2 + rh) * 2;
+                    const float a0 = acc[ai] * descale, a1 = acc[ai + 1] * descale;
+                    if (MODE == EPI_PLAIN) {
+                        __stcs(reinterpret_cast<float2*>(epi.out + row_off + col), make_float2(a0 * rs * in1[jj].x, a1 * rs * in1[jj].y));
+                    } else if (MODE == EPI_RESID) {
+                        const float r0 = (in1[jj].x * a0 - in0[jj].x) * oscale, r1 = (in1[jj].y * a1 - in0[jj].y) * oscale;
+                        const __half2 h = __floats2half2_rn(r0, r1);
+                        const float2 hf = __half22float2(h);
+                        const __half2 l = __floats2half2_rn(r0 - hf.x, r1 - hf.y);
+                        *reinterpret_cast<__half2*>(epi.out_hi + row_off + col) = h;
+                        *reinterpret_cast<__half2*>(epi.out_lo + row_off + col) = l;
+                    } else {  // EPI_FISTA: u = z - step*g ; x = soft(u, step*lambda) ; z = x + beta (x - x_old)
+                        const float u0 = in0[jj].x - a0, u1 = in0[jj].y - a1;
+                        const float x0 = copysignf(fmaxf(fabsf(u0) - thr, 0.f), u0);
+                        const float x1 = copysignf(fmaxf(fabsf(u1) - thr, 0.f), u1);
+                        const float z0 = x0 + epi.beta * (x0 - in1[jj].x), z1 = x1 + epi.beta * (x1 - in1[jj].y);
+                        __stcs(reinterpret_cast<float2*>(epi.x + row_off + col), make_float2(x0, x1));
+                        __stcs(reinterpret_cast<float2*>(epi.z + row_off + col), make_float2(z0, z1));
+                        const __half2 h = __floats2half2_rn(z0 * oscale, z1 * oscale);
+                        const float2 hf = __half22float2(h);
+                        const __half2 l = __floats2half2_rn(z0 * oscale - hf.x, z1 * oscale - hf.y);
+                        __stcs(reinterpret_cast<unsigned int*>(epi.out_hi + row_off + col), *reinterpret_cast<const unsigned int*>(&h));
+                        __stcs(reinterpret_cast<unsigned int*>(epi.out_lo + row_off + col), *reinterpret_cast<const unsigned int*>(&l));
+                        dsum += fabsf(x0 - in1[jj].x) + fabsf(x1 - in1[jj].y);
                     }
                 }
             }
-            __syncwarp();
+            if (MODE == EPI_FISTA && epi.delta != nullptr) {  // kernel-uniform branch
+                dsum += __shfl_xor_sync(0xffffffffu, dsum, 1);
+                dsum += __shfl_xor_sync(0xffffffffu, dsum, 2);
+                if (quad == 0 && row_ok && dsum != 0.f) atomicAdd(epi.delta + row, dsum);
+            }
         }
     }
 }
@@ -161,12 +192,12 @@ template <int MODE>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 dft_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                 const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
-                int K, int MT, int NT, int chunk_kb, const GemmEpilogue epi) {
+                const __grid_constant__ CUtensorMap map_pf0, const __grid_constant__ CUtensorMap map_pf1,
+                int num_prefetch, int prefetch_lead, int K, int MT, int NT, int chunk_kb, const GemmEpilogue epi) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* stage_base = smem;
-    float* tbuf = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES + EPI_WARPS * TBUF_FLOATS * 4);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
     uint64_t* full = bars;                     // [STAGES]  TMA -> MMA
     uint64_t* empty = bars + STAGES;           // [STAGES]  MMA -> TMA
     uint64_t* tmem_full = bars + 2 * STAGES;   // [2]       MMA -> epilogue (one K chunk accumulated)
@@ -183,6 +214,8 @@ dft_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
         tma_prefetch_desc(&map_a_lo);
         tma_prefetch_desc(&map_b_hi);
         tma_prefetch_desc(&map_b_lo);
+        if (num_prefetch > 0) tma_prefetch_desc(&map_pf0);
+        if (num_prefetch > 1) tma_prefetch_desc(&map_pf1);
         for (int s = 0; s < STAGES; ++s) {
             mbar_init(&full[s], 1);
             mbar_init(&empty[s], 1);
@@ -202,7 +235,11 @@ dft_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
 
-    if (warp == 0) {
+    // register budget: the two single-thread roles need few registers, the epilogue warps hold a 128-register
+    // accumulator fragment each -- hand the registers over (64512 = 128*40 + 256*232)
+    if (warp < 4) {
+      asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+      if (warp == 0) {
         // ===================== TMA producer =====================
         if (lane == 0) {
             int stage = 0;
@@ -210,7 +247,15 @@ dft_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
             for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
                 int mt, nt;
                 tile_coords(t, MT, NT, mt, nt);
+                // Pull the fp32 tiles the fused epilogue of THIS tile will read (z and x_old, or b) into L2 shortly
+                // before the K loop ends, so the epilogue's loads see L2 latency instead of HBM latency.  Not earlier:
+                // more than an L2's worth of data streams through per tile period and would evict them again.
+                const int pf_kb = max(0, KB - prefetch_lead);
                 for (int kb = 0; kb < KB; ++kb) {
+                    if (kb == pf_kb) {
+                        if (num_prefetch > 0) tma_prefetch_2d(&map_pf0, nt * BN, mt * BM);
+                        if (num_prefetch > 1) tma_prefetch_2d(&map_pf1, nt * BN, mt * BM);
+                    }
                     mbar_wait(&empty[stage], phase ^ 1);
                     uint8_t* sb = stage_base + stage * STAGE_BYTES;
                     mbar_arrive_expect_tx(&full[stage], STAGE_BYTES);
@@ -270,12 +315,13 @@ dft_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
                 }
             }
         }
+      }
     } else {
         // ===================== epilogue warps =====================
-        const int ew = warp - 2;
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
+        const int ew = warp - 4;
         const int sub = warp & 3;        // TMEM lane quarter this warp may read (hardware rule: warp id mod 4)
         const int half = ew >> 2;        // which 128 of the tile's 256 columns
-        float* tb = tbuf + ew * TBUF_FLOATS;
         uint32_t chunk = 0;
         for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
             int mt, nt;
@@ -292,7 +338,7 @@ dft_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&tmem_empty[buf]);
             }
-            epilogue_tile<MODE>(epi, acc, tb, sub, lane, mt * BM, nt * BN + half * EPI_COLS);
+            epilogue_tile<MODE>(epi, acc, lane, mt * BM + sub * 32, nt * BN + half * EPI_COLS);
         }
     }
 
@@ -365,6 +411,27 @@ struct ProfiledLaunch {
 static bool g_profile = false;
 static std::vector<ProfiledLaunch> g_profiled;
 
+// fp32 row-major [rows, cols] matrix -> map with a {256 x 128} box used only for L2 prefetch of epilogue tiles
+static int make_prefetch_map(CUtensorMap* map, const void* base, int rows, int cols, int ld) {
+    EncodeTiledFn enc = get_encode_fn();
+    if (!enc) {
+        set_error("cuTensorMapEncodeTiled is not available from the CUDA driver");
+        return CSR_ERR_CUDA;
+    }
+    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+    cuuint32_t box[2] = {(cuuint32_t)BN, (cuuint32_t)BM};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled (prefetch map) failed with CUresult %d", (int)r);
+        return CSR_ERR_CUDA;
+    }
+    return CSR_OK;
+}
+
 template <int MODE>
 static int launch_mode(const csr_plan* plan, bool adjoint, const CUtensorMap& a_hi, const CUtensorMap& a_lo, int P,
                        const GemmEpilogue& epi, cudaStream_t stream) {
@@ -378,6 +445,24 @@ static int launch_mode(const csr_plan* plan, bool adjoint, const CUtensorMap& a_
     const int MT = (P + BM - 1) / BM;
     const int NT = (N + BN - 1) / BN;
     const int grid = min(MT * NT, plan->num_sms);
+    CUtensorMap pf0, pf1;
+    memset(&pf0, 0, sizeof(pf0));
+    memset(&pf1, 0, sizeof(pf1));
+    int num_prefetch = 0;
+    static const bool use_prefetch = getenv("CSR_NO_PREFETCH") == nullptr;
+    static const int prefetch_lead = getenv("CSR_PREFETCH_LEAD") ? atoi(getenv("CSR_PREFETCH_LEAD")) : 8;
+    if (use_prefetch && (reinterpret_cast<uintptr_t>(MODE == EPI_FISTA ? (const void*)epi.z : (const void*)epi.b) & 15) == 0) {
+        int rc = CSR_OK;
+        if (MODE == EPI_FISTA) {
+            rc = make_prefetch_map(&pf0, epi.z, P, N, epi.ld_out);
+            if (!rc) rc = make_prefetch_map(&pf1, epi.x, P, N, epi.ld_out);
+            num_prefetch = 2;
+        } else if (MODE == EPI_RESID) {
+            rc = make_prefetch_map(&pf0, epi.b, P, N, epi.ld_out);
+            num_prefetch = 1;
+        }
+        if (rc) return rc;
+    }
     ProfiledLaunch rec;
     if (g_profile) {
         rec.kind = MODE * 2 + (adjoint ? 1 : 0);
@@ -386,8 +471,8 @@ static int launch_mode(const csr_plan* plan, bool adjoint, const CUtensorMap& a_
         CSR_CUDA(cudaEventRecord(rec.start, stream));
     }
     dft_gemm_kernel<MODE><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(
-        a_hi, a_lo, adjoint ? plan->map_adj_hi : plan->map_fwd_hi, adjoint ? plan->map_adj_lo : plan->map_fwd_lo, K,
-        MT, NT, gemm_chunk_kb(), epi);
+        a_hi, a_lo, adjoint ? plan->map_adj_hi : plan->map_fwd_hi, adjoint ? plan->map_adj_lo : plan->map_fwd_lo, pf0,
+        pf1, num_prefetch, prefetch_lead, K, MT, NT, gemm_chunk_kb(), epi);
     CSR_LAUNCHED();
     if (g_profile) {
         CSR_CUDA(cudaEventRecord(rec.stop, stream));
