@@ -124,13 +124,14 @@ __device__ __forceinline__ void epilogue_tile(const GemmEpilogue& epi, const flo
             const float* cs_row = nullptr;
             if (MODE != EPI_FISTA && epi.chan_scale) cs_row = epi.chan_scale + (epi.chan_per_pixel ? (size_t)row * epi.m : 0);
             float dsum = 0.f;
+            {
+                // one batch = the thread's 16 float2 positions of this row (all 128 columns): 32 x 8-byte loads in
+                // flight per thread for the FISTA epilogue
+                float2 in0[16], in1[16];
+                bool ok[16];
 #pragma unroll
-            for (int ch = 0; ch < 2; ++ch) {
-                float2 in0[8], in1[8];
-                bool ok[8];
-#pragma unroll
-                for (int jj = 0; jj < 8; ++jj) {
-                    const int col = col0 + 64 * ch + 8 * jj + 2 * quad;  // even; N is even, so col + 1 < N too
+                for (int jj = 0; jj < 16; ++jj) {
+                    const int col = col0 + 8 * jj + 2 * quad;  // even; N is even, so col + 1 < N too
                     ok[jj] = active && col < epi.N;
                     in0[jj] = make_float2(0.f, 0.f);
                     in1[jj] = make_float2(1.f, 1.f);
@@ -149,10 +150,10 @@ __device__ __forceinline__ void epilogue_tile(const GemmEpilogue& epi, const flo
                     }
                 }
 #pragma unroll
-                for (int jj = 0; jj < 8; ++jj) {
+                for (int jj = 0; jj < 16; ++jj) {
                     if (!ok[jj]) continue;
-                    const int col = col0 + 64 * ch + 8 * jj + 2 * quad;
-                    const int ai = (((lh * 2 + ch) * 8 + jj) * 2 + rh) * 2;
+                    const int col = col0 + 8 * jj + 2 * quad;
+                    const int ai = (((lh * 2 + (jj >> 3)) * 8 + (jj & 7)) * 2 + rh) * 2;
                     const float a0 = acc[ai] * descale, a1 = acc[ai + 1] * descale;
                     if (MODE == EPI_PLAIN) {
                         __stcs(reinterpret_cast<float2*>(epi.out + row_off + col), make_float2(a0 * rs * in1[jj].x, a1 * rs * in1[jj].y));
