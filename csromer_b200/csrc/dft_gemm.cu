@@ -124,18 +124,29 @@ __device__ __forceinline__ void epilogue_tile(const GemmEpilogue& epi, const flo
             const float* cs_row = nullptr;
             if (MODE != EPI_FISTA && epi.chan_scale) cs_row = epi.chan_scale + (epi.chan_per_pixel ? (size_t)row * epi.m : 0);
             float dsum = 0.f;
+            // Sparsity shortcut (exact): FISTA's soft threshold leaves most of phi space identically zero.  A byte per
+            // (row, 128-column block) records "x and z are all zero here"; such a block needs no loads, and if its new
+            // values are zero again it needs no stores either.
+            unsigned char* flag_ptr = nullptr;
+            int flag_in = 1;
+            if (MODE == EPI_FISTA && epi.zero_flags != nullptr && row_ok && col0 < epi.N) {
+                flag_ptr = epi.zero_flags + (size_t)row * epi.flag_ld + (col0 >> 7);
+                flag_in = __ldcg(flag_ptr);
+            }
             {
                 // one batch = the thread's 16 float2 positions of this row (all 128 columns): 32 x 8-byte loads in
                 // flight per thread for the FISTA epilogue
                 float2 in0[16], in1[16];
                 bool ok[16];
+                int nonzero = 0;
 #pragma unroll
                 for (int jj = 0; jj < 16; ++jj) {
                     const int col = col0 + 8 * jj + 2 * quad;  // even; N is even, so col + 1 < N too
                     ok[jj] = active && col < epi.N;
                     in0[jj] = make_float2(0.f, 0.f);
                     in1[jj] = make_float2(1.f, 1.f);
-                    if (ok[jj]) {
+                    if (MODE == EPI_FISTA) in1[jj] = make_float2(0.f, 0.f);
+                    if (ok[jj] && flag_in && !(epi.debug & 1)) {
                         if (MODE == EPI_FISTA) {
                             in0[jj] = __ldcg(reinterpret_cast<const float2*>(epi.z + row_off + col));
                             in1[jj] = __ldcg(reinterpret_cast<const float2*>(epi.x + row_off + col));
@@ -151,7 +162,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmEpilogue& epi, const flo
                 }
 #pragma unroll
                 for (int jj = 0; jj < 16; ++jj) {
-                    if (!ok[jj]) continue;
+                    if (!ok[jj] || (epi.debug & 2)) continue;
                     const int col = col0 + 8 * jj + 2 * quad;
                     const int ai = (((lh * 2 + (jj >> 3)) * 8 + (jj & 7)) * 2 + rh) * 2;
                     const float a0 = acc[ai] * descale, a1 = acc[ai + 1] * descale;
@@ -169,15 +180,31 @@ __device__ __forceinline__ void epilogue_tile(const GemmEpilogue& epi, const flo
                         const float x0 = copysignf(fmaxf(fabsf(u0) - thr, 0.f), u0);
                         const float x1 = copysignf(fmaxf(fabsf(u1) - thr, 0.f), u1);
                         const float z0 = x0 + epi.beta * (x0 - in1[jj].x), z1 = x1 + epi.beta * (x1 - in1[jj].y);
-                        __stcs(reinterpret_cast<float2*>(epi.x + row_off + col), make_float2(x0, x1));
-                        __stcs(reinterpret_cast<float2*>(epi.z + row_off + col), make_float2(z0, z1));
-                        const __half2 h = __floats2half2_rn(z0 * oscale, z1 * oscale);
-                        const float2 hf = __half22float2(h);
-                        const __half2 l = __floats2half2_rn(z0 * oscale - hf.x, z1 * oscale - hf.y);
-                        __stcs(reinterpret_cast<unsigned int*>(epi.out_hi + row_off + col), *reinterpret_cast<const unsigned int*>(&h));
-                        __stcs(reinterpret_cast<unsigned int*>(epi.out_lo + row_off + col), *reinterpret_cast<const unsigned int*>(&l));
                         dsum += fabsf(x0 - in1[jj].x) + fabsf(x1 - in1[jj].y);
+                        in1[jj] = make_float2(x0, x1);  // keep the results; whether they are stored is decided below
+                        in0[jj] = make_float2(z0, z1);
+                        nonzero |= (x0 != 0.f) | (x1 != 0.f) | (z0 != 0.f) | (z1 != 0.f);
                     }
+                }
+                if (MODE == EPI_FISTA) {
+                    nonzero |= __shfl_xor_sync(0xffffffffu, nonzero, 1);
+                    nonzero |= __shfl_xor_sync(0xffffffffu, nonzero, 2);
+                    if ((flag_in | nonzero) && !(epi.debug & 2)) {
+#pragma unroll
+                        for (int jj = 0; jj < 16; ++jj) {
+                            if (!ok[jj]) continue;
+                            const int col = col0 + 8 * jj + 2 * quad;
+                            const float2 xv = in1[jj], zv = in0[jj];
+                            __stcs(reinterpret_cast<float2*>(epi.x + row_off + col), xv);
+                            __stcs(reinterpret_cast<float2*>(epi.z + row_off + col), zv);
+                            const __half2 h = __floats2half2_rn(zv.x * oscale, zv.y * oscale);
+                            const float2 hf = __half22float2(h);
+                            const __half2 l = __floats2half2_rn(zv.x * oscale - hf.x, zv.y * oscale - hf.y);
+                            __stcs(reinterpret_cast<unsigned int*>(epi.out_hi + row_off + col), *reinterpret_cast<const unsigned int*>(&h));
+                            __stcs(reinterpret_cast<unsigned int*>(epi.out_lo + row_off + col), *reinterpret_cast<const unsigned int*>(&l));
+                        }
+                    }
+                    if (flag_ptr != nullptr && quad == 0 && active && nonzero != flag_in) *flag_ptr = (unsigned char)nonzero;
                 }
             }
             if (MODE == EPI_FISTA && epi.delta != nullptr) {  // kernel-uniform branch
@@ -392,16 +419,19 @@ int make_operand_map(CUtensorMap* map, const void* base, int rows, int cols, int
     return CSR_OK;
 }
 
-// K blocks accumulated inside the tensor core before the partial sum is moved to registers (CSR_CHUNK_KB, 1..64)
-static int gemm_chunk_kb() {
-    static int v = 0;
-    if (v == 0) {
+// K blocks accumulated inside the tensor core before the partial sum is moved to registers.  Forward (K = 2n, long):
+// 4 (CSR_CHUNK_KB).  Adjoint (K = 2m, a few chunks only): 8 (CSR_CHUNK_KB_ADJ) -- the wider chunk lets the MMAs of the
+// next tile run further ahead while the fused epilogue of the current one does its global I/O.
+static int gemm_chunk_kb(bool adjoint) {
+    static int v[2] = {0, 0};
+    if (v[0] == 0) {
         const char* e = getenv("CSR_CHUNK_KB");
-        v = e ? atoi(e) : 4;
-        if (v < 1) v = 1;
-        if (v > 4096) v = 4096;
+        const char* ea = getenv("CSR_CHUNK_KB_ADJ");
+        v[0] = e ? atoi(e) : 4;
+        v[1] = ea ? atoi(ea) : (e ? atoi(e) : 8);
+        for (int i = 0; i < 2; ++i) v[i] = v[i] < 1 ? 1 : (v[i] > 4096 ? 4096 : v[i]);
     }
-    return v;
+    return v[adjoint ? 1 : 0];
 }
 
 // ---- optional per-launch timing (bench.py's roofline leg): CUDA events on the launching stream ----------
@@ -450,7 +480,7 @@ static int launch_mode(const csr_plan* plan, bool adjoint, const CUtensorMap& a_
     memset(&pf0, 0, sizeof(pf0));
     memset(&pf1, 0, sizeof(pf1));
     int num_prefetch = 0;
-    static const bool use_prefetch = getenv("CSR_NO_PREFETCH") == nullptr;
+    static const bool use_prefetch = getenv("CSR_PREFETCH") != nullptr;  // measured: no gain on B200, off by default
     static const int prefetch_lead = getenv("CSR_PREFETCH_LEAD") ? atoi(getenv("CSR_PREFETCH_LEAD")) : 8;
     if (use_prefetch && (reinterpret_cast<uintptr_t>(MODE == EPI_FISTA ? (const void*)epi.z : (const void*)epi.b) & 15) == 0) {
         int rc = CSR_OK;
@@ -473,7 +503,7 @@ static int launch_mode(const csr_plan* plan, bool adjoint, const CUtensorMap& a_
     }
     dft_gemm_kernel<MODE><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(
         a_hi, a_lo, adjoint ? plan->map_adj_hi : plan->map_fwd_hi, adjoint ? plan->map_adj_lo : plan->map_fwd_lo, pf0,
-        pf1, num_prefetch, prefetch_lead, K, MT, NT, gemm_chunk_kb(), epi);
+        pf1, num_prefetch, prefetch_lead, K, MT, NT, gemm_chunk_kb(adjoint), epi);
     CSR_LAUNCHED();
     if (g_profile) {
         CSR_CUDA(cudaEventRecord(rec.stop, stream));
@@ -486,6 +516,8 @@ int launch_dft_gemm(const csr_plan* plan, bool adjoint, const __half* a_hi, cons
                     const GemmEpilogue& epi_in, cudaStream_t stream) {
     CSR_REQUIRE(P > 0, "P must be positive");
     GemmEpilogue epi = epi_in;
+    static const int debug_flags = getenv("CSR_DEBUG_EPI") ? atoi(getenv("CSR_DEBUG_EPI")) : 0;  // measurement aid only
+    epi.debug = debug_flags;
     const int K = adjoint ? 2 * plan->m : 2 * plan->n;
     const int ldk = adjoint ? plan->ld2m : plan->ld2n;
     epi.P = P;

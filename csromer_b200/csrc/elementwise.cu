@@ -208,6 +208,25 @@ derotate_kernel(float* __restrict__ data, int ld2m, int m, const double* __restr
     }
 }
 
+// flags[p, blk] = 1 if any of the 128 values z[p, 128*blk .. 128*blk+127] is non-zero (the FISTA epilogue's
+// "all-zero block" shortcut starts from here; x == z at that point)
+__global__ void block_flags_kernel(const float* __restrict__ z, int ld, int cols, unsigned char* __restrict__ flags,
+                                   int flag_ld) {
+    const int p = blockIdx.x;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int blk = warp; blk < flag_ld; blk += EW_THREADS / 32) {
+        int nz = 0;
+        for (int c = blk * 128 + lane; c < min(cols, blk * 128 + 128); c += 32) nz |= (z[(size_t)p * ld + c] != 0.f);
+        nz = __any_sync(0xffffffffu, nz);
+        if (lane == 0) flags[(size_t)p * flag_ld + blk] = (unsigned char)nz;
+    }
+}
+int launch_block_flags(const float* z, int ld, int cols, int P, unsigned char* flags, int flag_ld, cudaStream_t stream) {
+    block_flags_kernel<<<P, EW_THREADS, 0, stream>>>(z, ld, cols, flags, flag_ld);
+    CSR_LAUNCHED();
+    return CSR_OK;
+}
+
 // scale a [P, ld] fp32 matrix in place by a scalar (used for the delta / len(x) normalisation)
 __global__ void scale_vec_kernel(float* v, int n, float f) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;

@@ -8,6 +8,7 @@
 // Wavelet basis, per iteration: synthesis -> split -> forward GEMM -> adjoint GEMM (plain) -> analysis ->
 // coefficient update.  No CPU fallback exists anywhere in this file.
 #include <math.h>
+#include <stdlib.h>
 
 #include "plan.cuh"
 
@@ -24,6 +25,7 @@ int launch_coef_update(const float* grad, float* x, float* z, int ld, int ncoef,
                        const float* noise, const int* iter_cap, int iter, float step, float beta, float* delta,
                        cudaStream_t stream);
 int launch_scale_vec(float* v, int n, float f, cudaStream_t stream);
+int launch_block_flags(const float* z, int ld, int cols, int P, unsigned char* flags, int flag_ld, cudaStream_t stream);
 int wavelet_ld(const csr_wavelet* w);
 int wavelet_decompose(const csr_wavelet* w, const float* signal, int ld_sig, float* coef, int ld_coef, int P,
                       float* ws, cudaStream_t stream);
@@ -60,6 +62,8 @@ static TransformWs carve_transform(const csr_plan* plan, int P, void* ws) {
 struct FistaWs {
     float *b, *amask, *fwd_chan, *rscale, *zscale, *z, *f_dirty, *model, *sig, *gcoef, *wav_ws;
     __half *r_hi, *r_lo, *z_hi, *z_lo;
+    unsigned char* zero_flags;
+    int flag_ld;
     size_t bytes;
 };
 static FistaWs carve_fista(const csr_plan* plan, const csr_wavelet* wav, int P, void* ws) {
@@ -78,6 +82,8 @@ static FistaWs carve_fista(const csr_plan* plan, const csr_wavelet* wav, int P, 
     f.r_lo = b.take<__half>((size_t)P * plan->ld2m);
     f.z_hi = b.take<__half>((size_t)P * plan->ld2n);
     f.z_lo = b.take<__half>((size_t)P * plan->ld2n);
+    f.flag_ld = (2 * plan->n + 127) / 128;
+    f.zero_flags = b.take<unsigned char>((size_t)P * f.flag_ld);
     f.sig = f.gcoef = f.wav_ws = nullptr;
     if (wav) {
         f.sig = b.take<float>((size_t)P * plan->ld2n);
@@ -195,6 +201,10 @@ extern "C" int csr_fista(csr_plan* plan, csr_wavelet* wav, const csr_fista_args*
         if ((rc = launch_split_rows(w.z, ld2n, P, 2 * n, nullptr, 0, m, f_dirty, ld2n, w.z_hi, w.z_lo, ld2n, w.zscale, 0, stream)))
             return rc;
     }
+    static const bool zero_skip = getenv("CSR_NO_ZERO_SKIP") == nullptr;
+    if (!wav && zero_skip) {
+        if ((rc = launch_block_flags(w.z, ld2n, 2 * n, P, w.zero_flags, w.flag_ld, stream))) return rc;
+    }
     if (a.delta) CSR_CUDA(cudaMemsetAsync(a.delta, 0, sizeof(float) * P, stream));
 
     // 4. iterations
@@ -237,6 +247,8 @@ extern "C" int csr_fista(csr_plan* plan, csr_wavelet* wav, const csr_fista_args*
             e.step = a.step;
             e.beta = beta;
             e.delta = (last && a.delta) ? a.delta : nullptr;
+            e.zero_flags = zero_skip ? w.zero_flags : nullptr;
+            e.flag_ld = w.flag_ld;
             if ((rc = launch_dft_gemm(plan, true, w.r_hi, w.r_lo, P, e, stream))) return rc;
         } else {
             GemmEpilogue e = {};

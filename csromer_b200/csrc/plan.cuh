@@ -63,6 +63,9 @@ struct GemmEpilogue {
     int iter;
     float step, beta;
     float* delta;              // [P] sum |x - x_old| (atomicAdd), may be null
+    unsigned char* zero_flags; // [P, flag_ld] 1 = block of 128 columns may hold non-zeros; null = no shortcut
+    int flag_ld;
+    int debug;                 // measurement aid (CSR_DEBUG_EPI): bit 0 skips epilogue loads, bit 1 skips stores
 };
 
 int make_operand_map(CUtensorMap* map, const void* base, int rows, int cols, int ld, int box_rows);
