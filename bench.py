@@ -123,6 +123,15 @@ def run_reference_arm(args):
     print(json.dumps(line))
 
 
+def ncu_traffic(P):
+    """DRAM bytes per GEMM launch from the committed `ncu --set full` capture (profiles/r1_traffic.json, taken at
+    16384 lines of sight per launch); None if the slab size differs or the file is missing."""
+    path = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    if P != 16384 or not os.path.exists(path):
+        return None
+    return json.load(open(path)).get("mean")
+
+
 def workload_config(args):
     return {"workload": "C3: 512x512 px x 1000 ch cube (JVLA 1.008-2.031 GHz), shared lambda^2, n_phi=7968, "
                         "delta-basis L1 FISTA, exact DFT operator",
@@ -317,7 +326,8 @@ def run_ours(args):
             per_kind[name] = {"launches": int(ms[1][idx]), "avg_ms": float(ms[0][idx] / ms[1][idx]),
                               "tflops": float(flops_launch * ms[1][idx] / (ms[0][idx] * 1e-3) / 1e12)}
     roofline = {"bound": "tensor", "kernel": "dft_gemm_kernel (forward + adjoint, fused epilogues)",
-                "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+                "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                "traffic": ncu_traffic(P),
                 "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (%s)" % peaks["source"],
                 "executed_tflops": 3.0 * achieved, "executed_frac": 3.0 * achieved / peak,
                 "note": "3 fp16 MMAs per algorithmic product (hi/lo split, fp32-class accuracy): frac <= 1/3",

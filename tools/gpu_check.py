@@ -154,6 +154,54 @@ def stage_bench(nch, P, K):
     print("finite:", bool(torch.isfinite(x).all()), "max|x|", float(x.abs().max()))
 
 
+def stage_wav_bench(P=4096, K=10, name="coif2", kind="swt"):
+    """wavelet-basis fused loop and the stand-alone transforms at C1 sampling: time and effective HBM GB/s"""
+    nu = np.linspace(1.008e9, 2.031e9, 1000)
+    src1 = cs.FaradayThinSource(nu=nu, s_nu=0.0035, phi_gal=-200.0, spectral_idx=1.0)
+    src1.simulate()
+    par = cs.Parameter()
+    par.calculate_cellsize(dataset=src1, oversampling=8, verbose=False)
+    plan = dv.DevicePlan.get(src1.lambda2, 0.0, par.phi)
+    dev = plan.device
+    m, n = plan.m, plan.n
+    wav = cs.UndecimatedWavelet(wavelet_name=name) if kind == "swt" else cs.DiscreteWavelet(wavelet_name=name, mode="periodization")
+    eng = wav.prepare(2 * n)
+    g = torch.Generator(device=dev).manual_seed(1234)
+    sig = torch.randn((P, eng.ldn), generator=g, device=dev)
+    for label, fn, inp in (("decompose", eng.decompose, sig), ("reconstruct", eng.reconstruct, None)):
+        if inp is None:
+            inp = eng.decompose(sig)
+        fn(inp)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(5):
+            fn(inp)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 5
+        alg = P * (eng.ncoef + eng.N) * 4.0  # read the input once, write the output once
+        print("%s %s %s N=%d ncoef=%d P=%d: %.3f ms  algorithmic %.0f GB/s" % (kind, name, label, eng.N, eng.ncoef, P, ms, alg / ms / 1e6))
+    data = 0.003 * torch.randn((P, plan.ld2m), generator=g, device=dev)
+    w = torch.full((m,), 1.0 / 0.0007 ** 2, device=dev)
+    s = torch.as_tensor(np.ascontiguousarray(src1.s), dtype=torch.float32, device=dev)
+    k = torch.full((P,), float((w / s).sum()), device=dev)
+    x = torch.zeros((P, eng.ldc), device=dev)
+    theo = 1.0 / np.sqrt(m / 0.0007 ** 2)
+    lam = torch.full((P,), 40 * theo, device=dev)
+    nz = torch.full((P,), 40 * theo / (2 * K), device=dev)
+    for rep in range(3):
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        plan.fista(data, w, s, k, x, lam, nz, K, use_dirty_as_guess=True, wavelet=eng)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        print("fista %s %s P=%d K=%d: %.1f ms  %.2f ms/iteration  %.0f LOS/s at K=100 (extrapolated)" %
+              (kind, name, P, K, ms, ms / K, P / (ms / K * 100) * 1e3))
+
+
 if __name__ == "__main__":
     stage = sys.argv[1]
     torch.cuda.set_device(0)
@@ -178,6 +226,9 @@ if __name__ == "__main__":
         stage_fista(200, 40, 30, wavelet="coif2")
     elif stage == "f_dwt":
         stage_fista(200, 40, 30, wavelet="dwt:db2")
+    elif stage == "wav_bench":
+        stage_wav_bench()
+        stage_wav_bench(name="db2", kind="dwt")
     elif stage == "bench_small":
         stage_bench(1000, 4096, 10)
     elif stage == "bench":
