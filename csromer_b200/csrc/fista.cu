@@ -27,6 +27,21 @@ int launch_coef_update(const float* grad, float* x, float* z, int ld, int ncoef,
 int launch_scale_vec(float* v, int n, float f, cudaStream_t stream);
 int launch_block_flags(const float* z, int ld, int cols, int P, unsigned char* flags, int flag_ld, cudaStream_t stream);
 int wavelet_ld(const csr_wavelet* w);
+bool wavelet_fusable(const csr_wavelet* w);
+struct CoefUpdate {
+    float* x;
+    float* z;
+    const float* lambda0;
+    const float* noise;
+    const int* iter_cap;
+    int iter;
+    float step, beta;
+    float* delta;
+};
+int swt_synth_fused(const csr_wavelet* w, const float* coef, int ld_coef, float* sig, int ld_sig, __half* hi,
+                    __half* lo, int ld_h, const float* scale, int P, cudaStream_t stream);
+int swt_analysis_fused(const csr_wavelet* w, const float* signal, int ld_sig, float* coef, int ld_coef, int P,
+                       const CoefUpdate* update, cudaStream_t stream);
 int wavelet_decompose(const csr_wavelet* w, const float* signal, int ld_sig, float* coef, int ld_coef, int P,
                       float* ws, cudaStream_t stream);
 int wavelet_reconstruct(const csr_wavelet* w, const float* coef, int ld_coef, float* signal, int ld_sig, int P,
@@ -207,6 +222,8 @@ extern "C" int csr_fista(csr_plan* plan, csr_wavelet* wav, const csr_fista_args*
     }
     if (a.delta) CSR_CUDA(cudaMemsetAsync(a.delta, 0, sizeof(float) * P, stream));
 
+    const bool fused_wavelet = wav && wavelet_fusable(wav) && getenv("CSR_NO_FUSED_WAVELET") == nullptr;
+
     // 4. iterations
     double t = 1.0;
     for (int it = 0; it < a.iters; ++it) {
@@ -215,9 +232,13 @@ extern "C" int csr_fista(csr_plan* plan, csr_wavelet* wav, const csr_fista_args*
         const float beta = (float)((t0 - 1.0) / t);
         const bool last = (it == a.iters - 1);
         if (wav && it > 0) {  // (iteration 0 reuses the split made above)
-            if ((rc = wavelet_reconstruct(wav, w.z, ldc, w.sig, ld2n, P, w.wav_ws, stream))) return rc;
-            if ((rc = launch_split_rows(w.sig, ld2n, P, 2 * n, nullptr, 0, m, nullptr, 0, w.z_hi, w.z_lo, ld2n, w.zscale, 1, stream)))
-                return rc;
+            if (fused_wavelet) {  // synthesis of all levels + operand split in one shared-memory-staged kernel
+                if ((rc = swt_synth_fused(wav, w.z, ldc, nullptr, 0, w.z_hi, w.z_lo, ld2n, w.zscale, P, stream))) return rc;
+            } else {
+                if ((rc = wavelet_reconstruct(wav, w.z, ldc, w.sig, ld2n, P, w.wav_ws, stream))) return rc;
+                if ((rc = launch_split_rows(w.sig, ld2n, P, 2 * n, nullptr, 0, m, nullptr, 0, w.z_hi, w.z_lo, ld2n, w.zscale, 1, stream)))
+                    return rc;
+            }
         }
         {
             GemmEpilogue e = {};
@@ -256,10 +277,15 @@ extern "C" int csr_fista(csr_plan* plan, csr_wavelet* wav, const csr_fista_args*
             e.a_scale = w.rscale;
             e.out = w.sig;  // gradient in phi space
             if ((rc = launch_dft_gemm(plan, true, w.r_hi, w.r_lo, P, e, stream))) return rc;
-            if ((rc = wavelet_decompose(wav, w.sig, ld2n, w.gcoef, ldc, P, w.wav_ws, stream))) return rc;
-            if ((rc = launch_coef_update(w.gcoef, x, w.z, ldc, ncoef, P, a.lambda0, a.noise, a.iter_cap, it, a.step, beta,
-                                         (last && a.delta) ? a.delta : nullptr, stream)))
-                return rc;
+            if (fused_wavelet) {  // analysis of all levels + threshold + momentum in one kernel
+                CoefUpdate up = {x, w.z, a.lambda0, a.noise, a.iter_cap, it, a.step, beta, (last && a.delta) ? a.delta : nullptr};
+                if ((rc = swt_analysis_fused(wav, w.sig, ld2n, nullptr, ldc, P, &up, stream))) return rc;
+            } else {
+                if ((rc = wavelet_decompose(wav, w.sig, ld2n, w.gcoef, ldc, P, w.wav_ws, stream))) return rc;
+                if ((rc = launch_coef_update(w.gcoef, x, w.z, ldc, ncoef, P, a.lambda0, a.noise, a.iter_cap, it, a.step, beta,
+                                             (last && a.delta) ? a.delta : nullptr, stream)))
+                    return rc;
+            }
         }
     }
     if (a.delta && a.iters > 0) {

@@ -10,6 +10,7 @@
 //   dwt (periodization): c[o] = sum_t f[t] x'[(2o + F/2 - t) mod N'],  x' = x with its last sample repeated
 //       once when N is odd;   idwt: x[(2o + t - F/2 + 1) mod N] += cA[o] rec_lo[t] + cD[o] rec_hi[t]
 // Every level is one gather kernel over [P, band] (grid.y = line of sight), memory-bound and coalesced.
+#include <stdlib.h>
 #include <string.h>
 
 #include "plan.cuh"
@@ -135,9 +136,258 @@ static inline dim3 grid_for(int cols, int P) { return dim3((cols + 255) / 256, P
 
 int wavelet_ld(const csr_wavelet* w) { return round_up(w->N, 8); }
 
+// ---- fused undecimated transforms: all levels of one tile of one line of sight in shared memory ---------------
+// A tile of T samples plus a halo of H = (F/2)(2^L - 1) samples on each side (the cumulative support of L a-trous
+// levels) is loaded once, every level is computed buffer-to-buffer in shared memory, and only final results touch
+// HBM.  Buffer index i <-> global sample (t0 - H + i) mod N (periodic signal).  At every level only the entries
+// whose taps stay inside the buffer are computed; the uncomputed rim lies inside the halo, never in the T valid outputs.
+constexpr int WAV_THREADS = 512;
+constexpr int WAV_SMEM_BUDGET = 72 * 1024;  // per CTA: three CTAs per SM overlap each other's load / compute phases
+
+struct FusedTiling {
+    int H, T, B, ntiles;
+};
+static FusedTiling fused_tiling(const csr_wavelet* w, int nbuf) {
+    FusedTiling t;
+    t.H = (w->F / 2) * ((1 << w->levels) - 1);
+    const int bmax = WAV_SMEM_BUDGET / (4 * nbuf);
+    const int tmax = bmax - 2 * t.H;
+    if (tmax < 256) {
+        t.T = t.B = t.ntiles = 0;  // filter/level combination too wide for the budget: caller falls back
+        return t;
+    }
+    t.ntiles = (w->N + tmax - 1) / tmax;
+    t.T = round_up((w->N + t.ntiles - 1) / t.ntiles, 32);
+    t.B = t.T + 2 * t.H;
+    return t;
+}
+bool wavelet_fusable(const csr_wavelet* w) {
+    return w->kind == 0 && !w->append_signal && w->levels >= 1 && fused_tiling(w, 3).T > 0;
+}
+
+__device__ __forceinline__ int wrap_index(int j, int N) {
+    j %= N;
+    return j < 0 ? j + N : j;
+}
+
+struct BandOffsets {
+    int off[34];
+};
+
+// coefficients [cA_L | cD_L | ... | cD_1] -> signal; writes fp32 (sig) and/or the scaled fp16 hi/lo GEMM operand
+__global__ void __launch_bounds__(WAV_THREADS)
+swt_synth_fused_kernel(const float* __restrict__ coef, int ld_coef, int N, int L, int H, int T, int B,
+                       const BandOffsets bands, const FilterPair f, float* __restrict__ sig, int ld_sig,
+                       __half* __restrict__ hi, __half* __restrict__ lo, int ld_h, const float* __restrict__ scale) {
+    extern __shared__ float wsm[];
+    float* a = wsm;
+    float* o = wsm + B;
+    float* d = wsm + 2 * B;
+    const int p = blockIdx.y;
+    const int t0 = blockIdx.x * T;
+    const int base = t0 - H;
+    const float* crow = coef + (size_t)p * ld_coef;
+    for (int i = threadIdx.x; i < B; i += WAV_THREADS) a[i] = crow[bands.off[0] + wrap_index(base + i, N)];
+    for (int lev = L; lev >= 1; --lev) {
+        const int step = 1 << (lev - 1);
+        const float* dband = crow + bands.off[L - lev + 1];
+        for (int i = threadIdx.x; i < B; i += WAV_THREADS) d[i] = dband[wrap_index(base + i, N)];
+        __syncthreads();
+        // only entries whose taps stay inside the buffer are computed (no per-tap clamping); the uncomputed rim
+        // grows by step*F/2 per level and is covered by the halo
+        const int rim = step * (f.F / 2);
+        for (int i = rim + threadIdx.x; i < B - rim; i += WAV_THREADS) {
+            const float* ap = a + i + step * (f.F / 2 - 1);
+            const float* dp = d + i + step * (f.F / 2 - 1);
+            float acc = 0.f;
+            for (int t = 0; t < f.F; ++t) {
+                acc = fmaf(f.lo[t], *ap, acc);
+                acc = fmaf(f.hi[t], *dp, acc);
+                ap -= step;
+                dp -= step;
+            }
+            o[i] = 0.5f * acc;
+        }
+        __syncthreads();
+        float* tmp = a;
+        a = o;
+        o = tmp;
+    }
+    const float sc = scale ? scale[p] : 1.f;
+    for (int i = H + threadIdx.x; i < H + T; i += WAV_THREADS) {
+        const int g = t0 + (i - H);
+        if (g >= N) break;
+        const float v = a[i];
+        if (sig) sig[(size_t)p * ld_sig + g] = v;
+        if (hi) {
+            __half h, l;
+            split_half(v * sc, h, l);
+            hi[(size_t)p * ld_h + g] = h;
+            lo[(size_t)p * ld_h + g] = l;
+        }
+    }
+}
+
+struct CoefUpdate {  // FISTA update applied to each coefficient as its gradient value is produced (may be disabled)
+    float* x;
+    float* z;
+    const float* lambda0;
+    const float* noise;
+    const int* iter_cap;
+    int iter;
+    float step, beta;
+    float* delta;
+};
+
+// signal -> coefficients.  UPDATE = false: write the coefficients (decompose).  UPDATE = true: the signal is the
+// gradient in phi space; every coefficient g of its analysis is consumed on the spot by
+// u = z - step g ; x = soft(u, step lambda) ; z = x + beta (x - x_old)   (fista.py:80-86, l1.py:30-32).
+template <bool UPDATE>
+__global__ void __launch_bounds__(WAV_THREADS)
+swt_analysis_fused_kernel(const float* __restrict__ signal, int ld_sig, int N, int L, int H, int T, int B,
+                          const BandOffsets bands, const FilterPair f, float* __restrict__ coef, int ld_coef,
+                          const CoefUpdate up) {
+    extern __shared__ float wsm[];
+    float* a = wsm;
+    float* o = wsm + B;
+    const int p = blockIdx.y;
+    const int t0 = blockIdx.x * T;
+    const int base = t0 - H;
+    float thr = 0.f;
+    bool active = true;
+    if (UPDATE) {
+        const float l0 = up.lambda0[p], nz = up.noise[p];
+        const float lam = l0 - (float)up.iter * nz;
+        active = (nz < l0) && (up.iter == 0 || lam > 0.f) && (!up.iter_cap || up.iter < up.iter_cap[p]);
+        thr = up.step * lam;
+        if (!active) return;  // whole CTA: this line of sight is frozen
+    }
+    const float* srow = signal + (size_t)p * ld_sig;
+    for (int i = threadIdx.x; i < B; i += WAV_THREADS) a[i] = srow[wrap_index(base + i, N)];
+    __syncthreads();
+    const size_t crow = (size_t)p * ld_coef;
+    float dsum = 0.f;
+    for (int lev = 1; lev <= L; ++lev) {
+        const int step = 1 << (lev - 1);
+        const int band = bands.off[L - lev + 1];
+        const int rim = step * (f.F / 2);
+        for (int i = rim + threadIdx.x; i < B - rim; i += WAV_THREADS) {
+            const int g = t0 + (i - H);
+            const bool valid = i >= H && i < H + T && g < N;
+            float zo = 0.f, xo = 0.f;
+            if (UPDATE && valid) {  // issue the state loads before the filter loop
+                zo = __ldcg(up.z + crow + band + g);
+                xo = __ldcg(up.x + crow + band + g);
+            }
+            const float* ap = a + i + (f.F * step) / 2;
+            float ca = 0.f, cd = 0.f;
+            for (int t = 0; t < f.F; ++t) {
+                const float v = *ap;
+                ca = fmaf(f.lo[t], v, ca);
+                cd = fmaf(f.hi[t], v, cd);
+                ap -= step;
+            }
+            o[i] = ca;
+            if (valid) {
+                if (UPDATE) {
+                    const float u = zo - up.step * cd;
+                    const float xn = copysignf(fmaxf(fabsf(u) - thr, 0.f), u);
+                    up.x[crow + band + g] = xn;
+                    up.z[crow + band + g] = xn + up.beta * (xn - xo);
+                    dsum += fabsf(xn - xo);
+                } else {
+                    coef[crow + band + g] = cd;
+                }
+            }
+        }
+        __syncthreads();
+        float* tmp = a;
+        a = o;
+        o = tmp;
+    }
+    for (int i = H + threadIdx.x; i < H + T; i += WAV_THREADS) {  // approximation band cA_L
+        const int g = t0 + (i - H);
+        if (g >= N) break;
+        const float ca = a[i];
+        if (UPDATE) {
+            const float zo = up.z[crow + bands.off[0] + g], xo = up.x[crow + bands.off[0] + g];
+            const float u = zo - up.step * ca;
+            const float xn = copysignf(fmaxf(fabsf(u) - thr, 0.f), u);
+            up.x[crow + bands.off[0] + g] = xn;
+            up.z[crow + bands.off[0] + g] = xn + up.beta * (xn - xo);
+            dsum += fabsf(xn - xo);
+        } else {
+            coef[crow + bands.off[0] + g] = ca;
+        }
+    }
+    if (UPDATE && up.delta != nullptr) {
+#pragma unroll
+        for (int sft = 16; sft > 0; sft >>= 1) dsum += __shfl_xor_sync(0xffffffffu, dsum, sft);
+        if ((threadIdx.x & 31) == 0 && dsum != 0.f) atomicAdd(up.delta + p, dsum);
+    }
+}
+
+static BandOffsets band_offsets(const csr_wavelet* w) {
+    BandOffsets b;
+    memset(&b, 0, sizeof(b));
+    for (int i = 0; i <= w->levels; ++i) b.off[i] = w->offsets[i];
+    return b;
+}
+
+template <typename K>
+static int set_wavelet_smem(K kernel, int bytes) {
+    CSR_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    return CSR_OK;
+}
+
+int swt_synth_fused(const csr_wavelet* w, const float* coef, int ld_coef, float* sig, int ld_sig, __half* hi,
+                    __half* lo, int ld_h, const float* scale, int P, cudaStream_t stream) {
+    const FusedTiling t = fused_tiling(w, 3);
+    const int smem = 3 * t.B * 4;
+    static bool configured = false;
+    if (!configured) {
+        int rc = set_wavelet_smem(swt_synth_fused_kernel, WAV_SMEM_BUDGET + 1024);
+        if (rc) return rc;
+        configured = true;
+    }
+    swt_synth_fused_kernel<<<dim3(t.ntiles, P), WAV_THREADS, smem, stream>>>(
+        coef, ld_coef, w->N, w->levels, t.H, t.T, t.B, band_offsets(w), make_pair(w->rec_lo, w->rec_hi, w->F), sig, ld_sig,
+        hi, lo, ld_h, scale);
+    CSR_LAUNCHED();
+    return CSR_OK;
+}
+
+int swt_analysis_fused(const csr_wavelet* w, const float* signal, int ld_sig, float* coef, int ld_coef, int P,
+                       const CoefUpdate* update, cudaStream_t stream) {
+    const FusedTiling t = fused_tiling(w, 2);
+    const int smem = 2 * t.B * 4;
+    static bool configured = false;
+    if (!configured) {
+        int rc = set_wavelet_smem(swt_analysis_fused_kernel<true>, WAV_SMEM_BUDGET + 1024);
+        if (!rc) rc = set_wavelet_smem(swt_analysis_fused_kernel<false>, WAV_SMEM_BUDGET + 1024);
+        if (rc) return rc;
+        configured = true;
+    }
+    const dim3 grid(t.ntiles, P);
+    const FilterPair f = make_pair(w->dec_lo, w->dec_hi, w->F);
+    if (update) {
+        swt_analysis_fused_kernel<true><<<grid, WAV_THREADS, smem, stream>>>(signal, ld_sig, w->N, w->levels, t.H, t.T, t.B,
+                                                                            band_offsets(w), f, coef, ld_coef, *update);
+    } else {
+        CoefUpdate none;
+        memset(&none, 0, sizeof(none));
+        swt_analysis_fused_kernel<false><<<grid, WAV_THREADS, smem, stream>>>(signal, ld_sig, w->N, w->levels, t.H, t.T, t.B,
+                                                                             band_offsets(w), f, coef, ld_coef, none);
+    }
+    CSR_LAUNCHED();
+    return CSR_OK;
+}
+
 // coefficient layout: [signal (N) if append_signal][cA_L][cD_L]...[cD_1]
 int wavelet_decompose(const csr_wavelet* w, const float* signal, int ld_sig, float* coef, int ld_coef, int P,
                       float* ws, cudaStream_t stream) {
+    if (wavelet_fusable(w) && getenv("CSR_NO_FUSED_WAVELET") == nullptr)
+        return swt_analysis_fused(w, signal, ld_sig, coef, ld_coef, P, nullptr, stream);
     const int N = w->N, L = w->levels;
     const int ldw = wavelet_ld(w);
     float* ping = ws;
@@ -184,6 +434,8 @@ int wavelet_decompose(const csr_wavelet* w, const float* signal, int ld_sig, flo
 
 int wavelet_reconstruct(const csr_wavelet* w, const float* coef, int ld_coef, float* signal, int ld_sig, int P,
                         float* ws, cudaStream_t stream) {
+    if (wavelet_fusable(w) && getenv("CSR_NO_FUSED_WAVELET") == nullptr)
+        return swt_synth_fused(w, coef, ld_coef, signal, ld_sig, nullptr, nullptr, 0, nullptr, P, stream);
     const int N = w->N, L = w->levels;
     const int ldw = wavelet_ld(w);
     float* ping = ws;
