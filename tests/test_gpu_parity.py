@@ -390,3 +390,108 @@ def test_full_size_linearity_and_adjointness():
     e[torch.arange(8, device=plan.device), idx] = 1.0
     diag = plan.adjoint(plan.forward(e))[torch.arange(8, device=plan.device), idx] / plan.n
     assert float((diag - plan.m / plan.n).abs().max()) < 1e-5
+
+
+# ---------------------------------------------------------------------------------------------------------
+# the BASELINE.json configurations beyond C1/C3 (reduced pixel counts; full samplings)
+# ---------------------------------------------------------------------------------------------------------
+def test_config2_single_los_wavelet_flagged_nufft():
+    """C2: one line of sight, thin + thick mixed source, undecimated coif2 basis, 20 % of the channels flagged as
+    w = 0 in RFI-like chunks, NUFFT1D API (exact operator)."""
+    rng = np.random.RandomState(42)
+    nu = np.linspace(1.008e9, 2.031e9, 1000)
+    thin = cs.FaradayThinSource(nu=nu, s_nu=0.0035, phi_gal=-200, spectral_idx=1.0)
+    thick = cs.FaradayThickSource(nu=nu, s_nu=0.0035, phi_fg=140, phi_center=200, spectral_idx=1.0)
+    thin.simulate()
+    thick.simulate()
+    src = thin + thick
+    src.apply_noise(0.2 * 0.0035, random_state=rng)
+    w = src.w.copy()
+    for start in rng.randint(0, 950, size=6):
+        w[start:start + 34] = 0.0
+    src.w = w
+    assert 0.1 < np.mean(src.w == 0) < 0.25
+    par = cs.Parameter()
+    par.calculate_cellsize(dataset=src, oversampling=8, verbose=False)
+    dft = cs.NDFT1D(dataset=src, parameter=par)
+    nufft = cs.NUFFT1D(dataset=src, parameter=par, solve=True)
+    wav = cs.UndecimatedWavelet(wavelet_name="coif2")
+    K = 40
+    lam0 = 40.0 * src.theo_noise
+    noise = lam0 / (2.0 * K)
+    par.data = dft.backward(src.data)
+    par.complex_data_to_real()
+    par.data = wav.decompose(par.data)
+    chi2 = cs.Chi2(dft_obj=nufft, wavelet=wav)
+    l1 = cs.L1(reg=lam0)
+    cost, X = cs.FISTA(guess_param=par, F_obj=cs.OFunction([chi2, l1]), fx=chi2, gx=cs.OFunction([l1]), noise=noise,
+                       maxiter=K, verbose=False).run()
+    op = oracle_operator(src, par)
+    owav = ob.WaveletDict("coif2", kind="swt")
+    ref = ob.fista(op, np.asarray(src.data), owav.decompose(ob.complex_to_real(op.backward(np.asarray(src.data)))), lam0,
+                   noise, K, wavelet=owav)
+    assert X.data.shape == (7 * 2 * 7968,)
+    check_fista(src, X, cost, l1, ref)
+    X.data = wav.reconstruct(X.data)
+    X.real_data_to_complex()
+    assert rel(X.data, ob.real_to_complex(owav.reconstruct(ref["x"]))) < TOL_MODEL
+
+
+def test_config4_sampling_per_pixel_weights_flags_galactic_rm():
+    """C4 sampling (2000 channels, n = 15968): per-pixel sigma, 10-20 % w = 0 flags per pixel, Galactic RM removed
+    per pixel with Dataset.subtract_galacticrm semantics; reduced to 48 lines of sight."""
+    rng = np.random.RandomState(1235)
+    P, K = 48, 12
+    nu = np.linspace(1.008e9, 2.031e9, 2000)
+    src = cs.FaradayThinSource(nu=nu, s_nu=0.0035 * rng.uniform(0.5, 1.5, size=P), phi_gal=rng.uniform(-500, 500, size=P),
+                               spectral_idx=1.0)
+    src.simulate()
+    src.apply_noise(0.2 * 0.0035, random_state=rng)
+    src.subtract_galacticrm(rng.normal(0, 30, size=P))
+    src.sigma = 0.0007 * rng.uniform(0.5, 2.0, size=(2000, P))
+    w = src.w.copy()
+    w[rng.uniform(size=w.shape) < rng.uniform(0.1, 0.2, size=P)] = 0.0
+    src.w = w
+    par = cs.Parameter()
+    par.calculate_cellsize(dataset=src, oversampling=8, verbose=False)
+    assert len(par.phi) == 15968
+    cost, X, l1, lam0, noise = run_fista(src, par, K)
+    ref = oracle_fista(src, par, K, lam0, noise)
+    check_fista(src, X, cost, l1, ref)
+
+
+def test_config5_sampling_transforms_and_properties():
+    """C5 sampling (4000 channels, MeerKAT band, n = 31968): transforms against the oracle for a few lines of
+    sight, adjointness at 300, and a short SWT-coif2 FISTA run against the oracle."""
+    from csromer_b200 import _device as dv
+    rng = np.random.RandomState(1236)
+    P = 6
+    nu = np.linspace(0.9e9, 1.67e9, 4000)
+    src = cs.FaradayThinSource(nu=nu, s_nu=0.0035 * rng.uniform(0.5, 1.5, size=P), phi_gal=rng.uniform(-500, 500, size=P),
+                               spectral_idx=1.0)
+    src.simulate()
+    src.apply_noise(0.2 * 0.0035, random_state=rng)
+    par = cs.Parameter()
+    par.calculate_cellsize(dataset=src, oversampling=8, verbose=False)
+    assert len(par.phi) == 31968
+    dft = cs.NDFT1D(dataset=src, parameter=par)
+    op = oracle_operator(src, par)
+    data = np.asarray(src.data)
+    assert rel(dft.backward(data), op.backward(data)) < TOL_TRANSFORM
+    x = (rng.normal(size=(31968, P)) + 1j * rng.normal(size=(31968, P))) * (rng.uniform(size=(31968, P)) < 0.01)
+    assert rel(dft.forward_normalized(x), op.forward_normalized(x)) < TOL_TRANSFORM
+    wav = cs.UndecimatedWavelet(wavelet_name="coif2")
+    owav = ob.WaveletDict("coif2", kind="swt")
+    K = 6
+    cost, X, l1, lam0, noise = run_fista(src, par, K, wav=wav)
+    ref = oracle_fista(src, par, K, lam0, noise, owav=owav)
+    assert X.data.shape == (7 * 2 * 31968, P)
+    check_fista(src, X, cost, l1, ref)
+    plan = dv.DevicePlan.get(src.lambda2, 0.0, par.phi)
+    g = torch.Generator(device=plan.device).manual_seed(5)
+    xs = torch.randn((300, plan.ld2n), generator=g, device=plan.device)
+    ys = torch.randn((300, plan.ld2m), generator=g, device=plan.device)
+    lhs = (plan.forward(xs).double() * ys.double()).sum(dim=1)
+    rhs = (xs.double() * plan.adjoint(ys).double()).sum(dim=1)
+    scale = plan.forward(xs).double().norm(dim=1) * ys.double().norm(dim=1)
+    assert float(((lhs - rhs).abs() / scale).max()) < 1e-6
