@@ -34,11 +34,12 @@ class Dataset:
         self._lambda2 = self._nu = self._nu_0 = None
         self._s = self._w = self._sigma = None
         self._data = self._model_data = None
+        self._residual = None
+        self._deferred = None  # (model thunk, residual thunk) left by the fused GPU loop, resolved on first read
         self._spectral_idx = 0.0
         self._m = None
         self.k = None
         self.theo_noise = None
-        self.residual = None
         self.delta_l2_min = self.delta_l2_max = self.delta_l2_mean = 0.0
         self.l2_ref = 0.0 if l2_ref is None else l2_ref
         self.gridded = bool(gridded) if gridded is not None else False
@@ -55,7 +56,7 @@ class Dataset:
         elif self._m is not None:
             self.sigma = np.ones(self._m)
         self.data = data
-        if self._data is not None and self._model_data is None:
+        if isinstance(self._data, np.ndarray) and self._model_data is None:
             self._model_data = np.zeros_like(self._data)
 
     # ---- sampling ------------------------------------------------------------------------------------
@@ -185,12 +186,38 @@ class Dataset:
         if self._model_data is None:
             self._model_data = np.zeros_like(np.asarray(val)) if isinstance(val, np.ndarray) else None
 
+    def defer_model(self, model_thunk, residual_thunk):
+        """Used by the fused FISTA loop: ``model_data`` / ``residual`` of the final evaluation stay on the GPU until
+        somebody reads them (for a cube they are large and often never read); the thunks convert to the type and
+        device of ``data`` on first access.  Same observable values as assigning ``model_data`` directly."""
+        self._deferred = (model_thunk, residual_thunk)
+        self._model_data = self._residual = None
+
+    def _resolve_deferred(self):
+        if self._deferred is not None:
+            model_thunk, residual_thunk = self._deferred
+            self._deferred = None
+            self._model_data = model_thunk()
+            self._residual = residual_thunk()
+
+    @property
+    def residual(self):
+        self._resolve_deferred()
+        return self._residual
+
+    @residual.setter
+    def residual(self, val):
+        self._deferred = None
+        self._residual = val
+
     @property
     def model_data(self):
+        self._resolve_deferred()
         return self._model_data
 
     @model_data.setter
     def model_data(self, val):
+        self._deferred = None
         if val is None:
             self._model_data = None
             return

@@ -174,6 +174,64 @@ struct BandOffsets {
     int off[34];
 };
 
+// Inner loops with the filter length known at compile time: the taps unroll, the coefficients become constant-bank
+// operands of the FMAs and the loads of one output are all issued before its FMAs.  FLEN = 0 is the generic loop.
+template <int FLEN>
+__device__ __forceinline__ void synth_level(const float* __restrict__ a, const float* __restrict__ d,
+                                            float* __restrict__ o, int B, int step, const FilterPair& f) {
+    const int F = FLEN ? FLEN : f.F;
+    const int rim = step * (F / 2);
+    for (int i = rim + threadIdx.x; i < B - rim; i += WAV_THREADS) {
+        const float* ap = a + i + step * (F / 2 - 1);
+        const float* dp = d + i + step * (F / 2 - 1);
+        float acc0 = 0.f, acc1 = 0.f;
+        if (FLEN) {
+#pragma unroll
+            for (int t = 0; t < FLEN; ++t) {
+                acc0 = fmaf(f.lo[t], ap[-t * step], acc0);
+                acc1 = fmaf(f.hi[t], dp[-t * step], acc1);
+            }
+        } else {
+            for (int t = 0; t < F; ++t) {
+                acc0 = fmaf(f.lo[t], ap[-t * step], acc0);
+                acc1 = fmaf(f.hi[t], dp[-t * step], acc1);
+            }
+        }
+        o[i] = 0.5f * (acc0 + acc1);
+    }
+}
+
+template <int FLEN>
+__device__ __forceinline__ void analysis_taps(const float* __restrict__ ap, int step, const FilterPair& f, float& ca,
+                                              float& cd) {
+    ca = 0.f;
+    cd = 0.f;
+    if (FLEN) {
+#pragma unroll
+        for (int t = 0; t < FLEN; ++t) {
+            const float v = ap[-t * step];
+            ca = fmaf(f.lo[t], v, ca);
+            cd = fmaf(f.hi[t], v, cd);
+        }
+    } else {
+        for (int t = 0; t < f.F; ++t) {
+            const float v = ap[-t * step];
+            ca = fmaf(f.lo[t], v, ca);
+            cd = fmaf(f.hi[t], v, cd);
+        }
+    }
+}
+
+#define CSR_DISPATCH_FLEN(FVAL, CALL) \
+    switch (FVAL) {                   \
+        case 2: { constexpr int FL = 2; CALL; } break;   \
+        case 4: { constexpr int FL = 4; CALL; } break;   \
+        case 6: { constexpr int FL = 6; CALL; } break;   \
+        case 8: { constexpr int FL = 8; CALL; } break;   \
+        case 12: { constexpr int FL = 12; CALL; } break; \
+        default: { constexpr int FL = 0; CALL; } break;  \
+    }
+
 // coefficients [cA_L | cD_L | ... | cD_1] -> signal; writes fp32 (sig) and/or the scaled fp16 hi/lo GEMM operand
 __global__ void __launch_bounds__(WAV_THREADS)
 swt_synth_fused_kernel(const float* __restrict__ coef, int ld_coef, int N, int L, int H, int T, int B,
@@ -195,19 +253,7 @@ swt_synth_fused_kernel(const float* __restrict__ coef, int ld_coef, int N, int L
         __syncthreads();
         // only entries whose taps stay inside the buffer are computed (no per-tap clamping); the uncomputed rim
         // grows by step*F/2 per level and is covered by the halo
-        const int rim = step * (f.F / 2);
-        for (int i = rim + threadIdx.x; i < B - rim; i += WAV_THREADS) {
-            const float* ap = a + i + step * (f.F / 2 - 1);
-            const float* dp = d + i + step * (f.F / 2 - 1);
-            float acc = 0.f;
-            for (int t = 0; t < f.F; ++t) {
-                acc = fmaf(f.lo[t], *ap, acc);
-                acc = fmaf(f.hi[t], *dp, acc);
-                ap -= step;
-                dp -= step;
-            }
-            o[i] = 0.5f * acc;
-        }
+        CSR_DISPATCH_FLEN(f.F, synth_level<FL>(a, d, o, B, step, f))
         __syncthreads();
         float* tmp = a;
         a = o;
@@ -280,13 +326,8 @@ swt_analysis_fused_kernel(const float* __restrict__ signal, int ld_sig, int N, i
                 xo = __ldcg(up.x + crow + band + g);
             }
             const float* ap = a + i + (f.F * step) / 2;
-            float ca = 0.f, cd = 0.f;
-            for (int t = 0; t < f.F; ++t) {
-                const float v = *ap;
-                ca = fmaf(f.lo[t], v, ca);
-                cd = fmaf(f.hi[t], v, cd);
-                ap -= step;
-            }
+            float ca, cd;
+            CSR_DISPATCH_FLEN(f.F, analysis_taps<FL>(ap, step, f, ca, cd))
             o[i] = ca;
             if (valid) {
                 if (UPDATE) {

@@ -140,7 +140,9 @@ class FISTA(Optimizer):
                          wavelet=engine, iter_cap=cap_t)
 
         # side effects the reference leaves behind
-        ds.model_data = dv.unpack_complex_like(out["model"], plan.m, pix, ds.data)
+        model_dev, resid_dev, like = out["model"], out["residual"], ds.data
+        ds.defer_model(lambda: dv.unpack_complex_like(model_dev, plan.m, pix, like),
+                       lambda: dv.unpack_complex_like(resid_dev, plan.m, pix, like))
         lam_final = _decayed_lambda(lam0, noise, iters if cap is None else np.minimum(cap, iters))
         l1.reg = lam_final
         cost_t = out["cost"].double().cpu().numpy()
