@@ -6,6 +6,7 @@ lambda^2 <-> phi transforms, the Chi2 gradient, the L1 / wavelet proximal steps 
 sm_100a CUDA kernels for every line of sight of a cube at once.  See DESIGN.md.
 """
 from .base import Dataset
+from .cube import estimate_lipschitz, reconstruct_cube
 from .dictionaries import DiscreteWavelet, UndecimatedWavelet, Wavelet
 from .objectivefunction import L1, Chi2, Fi, OFunction
 from .optimization import FISTA, Optimizer
@@ -17,5 +18,5 @@ __version__ = "0.1.0"
 __all__ = [
     "Dataset", "Parameter", "FT", "NDFT1D", "DFT1D", "NUFFT1D", "Wavelet", "DiscreteWavelet", "UndecimatedWavelet",
     "Fi", "Chi2", "L1", "OFunction", "Optimizer", "FISTA", "FaradaySource", "FaradayThinSource",
-    "FaradayThickSource",
+    "FaradayThickSource", "reconstruct_cube", "estimate_lipschitz",
 ]

@@ -268,3 +268,46 @@ class DeviceWavelet:
         _lib.check(self.lib.csr_wavelet_reconstruct(self.handle, tptr(coef), coef.shape[1], tptr(sig), self.ldn, P,
                                                     tptr(ws), ws.numel(), stream_ptr()), "csr_wavelet_reconstruct")
         return sig
+
+
+# ---- restore-step helpers (csrc/restore.cu) -----------------------------------------------------------------
+def gaussian_beam_taps(rmtf_fwhm, cellsize):
+    """The restore beam of ``Parameter.convolve`` (reconstruction/parameter.py:139-156): sigma in whole phi cells,
+    ``astropy.convolution.Gaussian1DKernel(stddev)`` = Gaussian sampled at integer offsets over an odd window of
+    about 8 sigma, normalised to unit sum.  (astropy is not a dependency here; parity of this kernel is unpinned.)"""
+    sigma_pix = int(np.round(rmtf_fwhm / (2.0 * np.sqrt(2.0 * np.log(2.0))) / cellsize))
+    if sigma_pix < 1:
+        return np.ones(1, dtype=np.float64), sigma_pix
+    size = int(np.ceil(8 * sigma_pix))
+    size += 1 - size % 2
+    x = np.arange(size) - size // 2
+    taps = np.exp(-0.5 * (x / float(sigma_pix)) ** 2) / (np.sqrt(2 * np.pi) * sigma_pix)
+    return taps / taps.sum(), sigma_pix
+
+
+def convolve_phi(x, n, taps, add=None):
+    """[P, ld >= 2n] planar -> same shape: beam * x (+ add)"""
+    lib = _lib.load()
+    out = torch.zeros_like(x)
+    t = np.ascontiguousarray(taps, dtype=np.float32)
+    _lib.check(lib.csr_convolve_phi(tptr(x), x.shape[1], int(n), x.shape[0], t.ctypes.data_as(ctypes.POINTER(ctypes.c_float)),
+                                    len(t), tptr(add), tptr(out), stream_ptr()), "csr_convolve_phi")
+    return out
+
+
+def edge_noise(F, n, edge_mask, eta=1.0):
+    """[P, ld] planar dirty spectra -> [P] noise estimate from the masked (edge) phi cells"""
+    lib = _lib.load()
+    noise = torch.empty((F.shape[0],), dtype=torch.float32, device=F.device)
+    _lib.check(lib.csr_edge_noise(tptr(F), F.shape[1], int(n), F.shape[0], tptr(edge_mask), float(eta), tptr(noise),
+                                  stream_ptr()), "csr_edge_noise")
+    return noise
+
+
+def peak_stats(F, n):
+    """[P, ld] planar -> (argmax [P] int32, stats [P, 3] = |F| at peak, parabola offset, parabola peak)"""
+    lib = _lib.load()
+    idx = torch.empty((F.shape[0],), dtype=torch.int32, device=F.device)
+    stats = torch.empty((F.shape[0], 3), dtype=torch.float32, device=F.device)
+    _lib.check(lib.csr_peak(tptr(F), F.shape[1], int(n), F.shape[0], tptr(idx), tptr(stats), stream_ptr()), "csr_peak")
+    return idx, stats

@@ -17,7 +17,8 @@ EXPORTS = [
     "csr_transform_ws_bytes", "csr_forward", "csr_adjoint", "csr_derotate", "csr_wavelet_create",
     "csr_wavelet_destroy", "csr_wavelet_ncoef", "csr_wavelet_levels", "csr_wavelet_level_sizes",
     "csr_wavelet_ws_bytes", "csr_wavelet_decompose", "csr_wavelet_reconstruct", "csr_fista_ws_bytes",
-    "csr_fista", "csr_launch_count", "csr_profile", "csr_profile_collect",
+    "csr_fista", "csr_launch_count", "csr_profile", "csr_profile_collect", "csr_edge_noise", "csr_convolve_phi",
+    "csr_peak",
 ]
 
 
@@ -75,6 +76,9 @@ def load():
     lib.csr_fista_ws_bytes.argtypes = [c_void_p, c_void_p, c_int]
     lib.csr_fista_ws_bytes.restype = c_size_t
     lib.csr_fista.argtypes = [c_void_p, c_void_p, POINTER(FistaArgs), c_void_p, c_size_t, c_void_p]
+    lib.csr_edge_noise.argtypes = [c_void_p, c_int, c_int, c_int, c_void_p, c_float, c_void_p, c_void_p]
+    lib.csr_convolve_phi.argtypes = [c_void_p, c_int, c_int, c_int, POINTER(c_float), c_int, c_void_p, c_void_p, c_void_p]
+    lib.csr_peak.argtypes = [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]
     lib.csr_profile.argtypes = [c_int]
     lib.csr_profile_collect.argtypes = [POINTER(c_double), POINTER(c_longlong)]
     lib.csr_launch_count.argtypes = [c_int]

@@ -163,6 +163,7 @@ class FISTA(Optimizer):
         xr = dv.unpack_real(x, ncoef, pix, like_torch)
         param.data = xr if like_torch else xr.astype(x0.dtype if np.asarray(x0).dtype.kind == "f" else np.float32)
         self.F_dirty = out["f_dirty"]
+        self.device_outputs = out  # planar device tensors of the run: f_dirty, model, residual, cost
         self._device_plan, self._pixel_shape = plan, pix
         return cost, param
 

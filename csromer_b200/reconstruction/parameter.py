@@ -4,7 +4,7 @@ Host-side mirror of the reference's ``reconstruction/parameter.py:26-137``.  ``d
 coefficient index) on axis 0, so a batch is ``(n, P)`` complex, ``(2n, P)`` planar real or ``(ncoef, P)``
 wavelet coefficients.  As in the reference, assigning ``data`` overwrites ``n`` with ``len(data)``
  -- operators therefore use ``len(parameter.phi)``, never ``parameter.n``.
-``convolve`` (the restore step, parameter.py:139-169) is a "next" row of SURVEY.md section 8f and not built yet.
+``convolve`` (the restore step, parameter.py:139-169) runs on the GPU (``csrc/restore.cu``).
 """
 import numpy as np
 
@@ -84,3 +84,25 @@ class Parameter:
         if _is_complex(self._data):
             raise ValueError("Parameter data is not real")
         self.data = real_to_complex(self._data)
+
+    def convolve(self, x=None, rmtf_fwhm=None, verbose=True):
+        """Restore beam: convolve the complex Faraday spectrum (``x`` or ``self.data``, ``(n,)`` or ``(n, *pix)``)
+        with a Gaussian of FWHM ``rmtf_fwhm`` (default: the RMTF's), real and imaginary parts separately,
+        ``mode="same"`` -- the reference's scipy/astropy pipeline, on the GPU for all lines of sight at once."""
+        from .. import _device as dv
+        if rmtf_fwhm is None:
+            rmtf_fwhm = self.rmtf_fwhm
+        taps, sigma_pix = dv.gaussian_beam_taps(rmtf_fwhm, self.cellsize)
+        if verbose:
+            fwhm_pix = int(np.round(rmtf_fwhm / self.cellsize))
+            sigma = rmtf_fwhm / (2.0 * np.sqrt(2.0 * np.log(2.0)))
+            print("Convolving with Gaussian kernel where FWHM {0:2.3f} rad/m^2 - pixels {1}, sigma {2:2.3f} rad/m^2 - "
+                  "pixels {3}".format(rmtf_fwhm, fwhm_pix, sigma, sigma_pix))
+        src = self._data if x is None else x
+        if not _is_complex(src):
+            raise TypeError("convolve expects the complex Faraday spectrum")
+        n = src.shape[0]
+        ld = (2 * n + 7) // 8 * 8
+        planar, pix = dv.pack_planar(src, n, ld)
+        out = dv.convolve_phi(planar, n, taps)
+        return dv.unpack_complex(out, n, pix, like_torch=dv.is_torch(src))

@@ -130,6 +130,20 @@ size_t csr_fista_ws_bytes(const csr_plan* plan, const csr_wavelet* wav, int P);
 int csr_fista(csr_plan* plan, csr_wavelet* wav, const csr_fista_args* args, void* ws, size_t ws_bytes,
               void* stream);
 
+/* ---- after the loop: the cube recipe's remaining per-line-of-sight steps ("next" rows) ----
+ * csr_edge_noise  : noise[p] = eta/2 (std Re F[edges] + std Im F[edges]), numpy.std semantics, over the phi cells whose
+ *                   byte in edge_mask[n] is non-zero                                      (README.md:336-338)
+ * csr_convolve_phi: out = conv_same(x, taps) (+ add), real and imaginary halves separately: Parameter.convolve with
+ *                   the Gaussian restore beam (reconstruction/parameter.py:139-169); taps is a HOST array (odd count
+ *                   <= 255); `add` = F_residual gives the restored spectrum (csromer_reconstructor.py:213)
+ * csr_peak        : argmax_j |F_j| and stats[p] = {|F| at the peak, parabola offset, parabola peak}
+ *                   (csromer_reconstructor.py:59-84, 134-136) */
+int csr_edge_noise(const float* F, int ld, int n, int P, const unsigned char* edge_mask, float eta, float* noise,
+                   void* stream);
+int csr_convolve_phi(const float* x, int ld, int n, int P, const float* taps_host, int ntaps, const float* add,
+                     float* out, void* stream);
+int csr_peak(const float* F, int ld, int n, int P, int* argmax, float* stats, void* stream);
+
 /* per-launch timing of the transform GEMMs with CUDA events on the launching stream (measurement aid).
  * csr_profile(1) starts recording; csr_profile_collect sums elapsed ms and launch counts into 6-entry arrays
  * indexed [0 plain-forward, 1 plain-adjoint, 2 resid-forward, 3 resid-adjoint, 4 fista-forward, 5 fista-adjoint]

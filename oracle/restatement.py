@@ -421,3 +421,75 @@ def subtract_galactic_rm(data, lambda2, phi_gal):
     """base/dataset.py:377-381 (phi_gal scalar or (P,))."""
     ph = np.multiply.outer(lambda2, np.asarray(phi_gal, dtype=np.float64))
     return data * np.exp(-2j * ph)
+
+
+# ----------------------------------------------------------------------------------------------------------
+# after the loop: the README cube recipe (README.md:319-376) and the restore step
+# (reconstruction/parameter.py:139-169, wrappers/reconstructors/csromer_reconstructor.py:59-84,205-213)
+# ----------------------------------------------------------------------------------------------------------
+def gaussian_beam(rmtf_fwhm, cellsize):
+    """astropy.convolution.Gaussian1DKernel(stddev = round(sigma / cellsize)) as parameter.py:144-155 builds it.
+    astropy is absent here: PARITY UNPINNED for this kernel (window = odd(8 sigma), unit-sum normalisation)."""
+    sigma_pix = int(np.round(rmtf_fwhm / (2.0 * np.sqrt(2.0 * np.log(2.0))) / cellsize))
+    if sigma_pix < 1:
+        return np.ones(1)
+    size = int(np.ceil(8 * sigma_pix))
+    size += 1 - size % 2
+    x = np.arange(size) - size // 2
+    k = np.exp(-0.5 * (x / float(sigma_pix)) ** 2) / (np.sqrt(2 * np.pi) * sigma_pix)
+    return k / k.sum()
+
+
+def convolve_beam(x, beam):
+    """parameter.py:157-169: scipy.signal.convolve(mode="same", method="fft") on the real and imaginary parts"""
+    from scipy import signal
+    return signal.convolve(x.real, beam, mode="same", method="fft") + 1j * signal.convolve(x.imag, beam, mode="same",
+                                                                                          method="fft")
+
+
+def edge_noise(F_dirty, phi, max_faraday_depth, eta=1.0):
+    """README.md:336-338"""
+    edges = np.abs(phi) > max_faraday_depth / 1.5
+    return eta * 0.5 * (np.std(F_dirty[edges].real) + np.std(F_dirty[edges].imag))
+
+
+def peak_parabola(fd, cellsize):
+    """csromer_reconstructor.py:59-78 -> (phi at the interpolated peak, interpolated peak)"""
+    n = len(fd)
+    i0 = int(np.argmax(np.abs(fd)))
+    c0, m1, p1 = np.abs(fd[i0]), np.abs(fd[i0 - 1]), np.abs(fd[i0 + 1])
+    pos = (p1 - m1) / (4 * c0 - 2 * m1 - 2 * p1)
+    return (i0 + pos - n / 2) * cellsize, c0 - 0.25 * (m1 - p1) * pos
+
+
+def cube_recipe(data, nu, sigma, spectral_idx=0.0, eta=1.0, wavelet="coif2", oversampling=8.0, step=1.0):
+    """README.md:319-376 pixel by pixel: data (m, P) -> F (4, n, P) = dirty, model, restored, residual"""
+    l2 = lambda2_from_nu(nu)
+    sc = dataset_scalars(l2, sigma, spectral_idx)
+    grid = phi_grid(l2, sc["w"], oversampling)
+    phi, n, m = grid["phi"], grid["n"], len(l2)
+    op = ExactDFT(l2, phi, sc["w"], sc["s"], sc["k"])
+    beam = gaussian_beam(grid["rmtf_fwhm"], grid["cellsize"])
+    P = data.shape[1]
+    F = np.zeros((4, n, P), dtype=np.complex128)
+    info = dict(noise=np.zeros(P), lambda_l1=np.zeros(P), rm_restored=np.zeros(P), rm_restored_interpolated=np.zeros(P),
+                peak_restored=np.zeros(P))
+    for p in range(P):
+        d = data[:, p]
+        dirty = op.backward(d)
+        noise = edge_noise(dirty, phi, grid["max_faraday_depth"], eta)
+        lam = np.sqrt(2 * m + np.sqrt(4 * m)) * noise
+        wav = WaveletDict(wavelet, kind="swt") if wavelet else None
+        x0 = complex_to_real(dirty)
+        if wav is not None:
+            x0 = wav.decompose(x0)
+        r = fista(op, d, x0, lam, noise, None, wavelet=wav, step=step)
+        xs = wav.reconstruct(r["x"]) if wav is not None else r["x"]
+        model = real_to_complex(xs)
+        f_res = op.backward(d - r["model"])
+        restored = convolve_beam(model, beam) + f_res
+        F[0, :, p], F[1, :, p], F[2, :, p], F[3, :, p] = dirty, model, restored, f_res
+        info["noise"][p], info["lambda_l1"][p] = noise, lam
+        info["rm_restored"][p] = phi[np.argmax(np.abs(restored))]
+        info["rm_restored_interpolated"][p], info["peak_restored"][p] = peak_parabola(restored, grid["cellsize"])
+    return F, info

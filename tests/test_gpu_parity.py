@@ -495,3 +495,61 @@ def test_config5_sampling_transforms_and_properties():
     rhs = (xs.double() * plan.adjoint(ys).double()).sum(dim=1)
     scale = plan.forward(xs).double().norm(dim=1) * ys.double().norm(dim=1)
     assert float(((lhs - rhs).abs() / scale).max()) < 1e-6
+
+
+# ---------------------------------------------------------------------------------------------------------
+# "next" rows: restore beam, FDF-edge noise, peak statistics and the batched cube recipe (README.md:282-377)
+# ---------------------------------------------------------------------------------------------------------
+def test_parameter_convolve_and_peak_statistics(capsys):
+    from csromer_b200 import _device as dv
+    src, par = make_batch(200, 19, seed=31, mixed=True)
+    dft = cs.NDFT1D(dataset=src, parameter=par)
+    F = dft.backward(src.data)
+    par.data = F
+    got = par.convolve()
+    assert "Convolving with Gaussian kernel" in capsys.readouterr().out
+    beam = ob.gaussian_beam(par.rmtf_fwhm, par.cellsize)
+    assert beam.shape[0] % 2 == 1 and abs(beam.sum() - 1) < 1e-12
+    want = np.stack([ob.convolve_beam(F[:, p].astype(np.complex128), beam) for p in range(19)], axis=1)
+    assert got.shape == F.shape and rel(got, want) < 2e-6
+    one = par.convolve(x=F[:, 3], verbose=False)
+    assert one.shape == (len(par.phi),) and rel(one, want[:, 3]) < 2e-6
+    plan = dft.device_plan()
+    planar, _ = dv.pack_planar(F, plan.n, plan.ld2n, plan.device)
+    idx, stats = dv.peak_stats(planar, plan.n)
+    idx, stats = idx.cpu().numpy(), stats.cpu().numpy()
+    for p in range(19):
+        assert idx[p] == np.argmax(np.abs(F[:, p]))
+        phi_pk, pk = ob.peak_parabola(F[:, p].astype(np.complex128), par.cellsize)
+        assert (idx[p] + stats[p, 1] - plan.n / 2) * par.cellsize == pytest.approx(phi_pk, abs=1e-3 * par.cellsize)
+        assert stats[p, 2] == pytest.approx(pk, rel=1e-5)
+    edge = np.abs(par.phi) > par.max_faraday_depth / 1.5
+    noise = dv.edge_noise(planar, plan.n, torch.as_tensor(edge.astype(np.uint8)).cuda(), 1.0).cpu().numpy()
+    for p in range(19):
+        assert noise[p] == pytest.approx(ob.edge_noise(F[:, p].astype(np.complex128), par.phi, par.max_faraday_depth), rel=1e-4)
+
+
+@pytest.mark.parametrize("use_wavelet", [True, False])
+def test_cube_recipe_matches_oracle(use_wavelet):
+    from csromer_b200.cube import estimate_lipschitz, reconstruct_cube
+    rng = np.random.RandomState(77)
+    nu = np.linspace(1.008e9, 2.031e9, 200)
+    Y, X = 3, 4
+    src = cs.FaradayThinSource(nu=nu, s_nu=0.0035 * rng.uniform(0.5, 1.5, size=(Y, X)),
+                               phi_gal=rng.uniform(-300, 300, size=(Y, X)), spectral_idx=0.0)
+    src.simulate()
+    src.apply_noise(0.2 * 0.0035, random_state=rng)
+    cube = np.asarray(src.data)
+    sigma = np.full(200, 0.2 * 0.0035)
+    F, info = reconstruct_cube(cube, nu, sigma=sigma, use_wavelet=use_wavelet, slab=7)
+    assert F.shape == (4, len(info["phi"]), Y, X) and F.dtype == np.complex64
+    assert 2.0 < 1.0 / info["step"] < 3.5  # lambda_max((1/n) E^H E), 2.74 at the 1000-channel JVLA sampling
+    Fo, io = ob.cube_recipe(cube.reshape(200, -1), nu, sigma, wavelet="coif2" if use_wavelet else None, step=info["step"])
+    assert np.isfinite(Fo).all()
+    Fo = Fo.reshape(F.shape)
+    for plane, tol in ((0, TOL_TRANSFORM), (1, TOL_MODEL), (2, TOL_MODEL), (3, TOL_MODEL)):
+        assert rel(F[plane], Fo[plane]) < tol, plane
+    np.testing.assert_allclose(info["noise"].reshape(-1), io["noise"], rtol=1e-4)
+    np.testing.assert_allclose(info["rm_restored"].reshape(-1), io["rm_restored"], atol=1e-9)
+    np.testing.assert_allclose(info["peak_restored"].reshape(-1), io["peak_restored"], rtol=1e-4)
+    assert info["iterations"] == int(np.floor(np.sqrt(400 + np.sqrt(800))))
