@@ -268,7 +268,7 @@ def run_ours(args):
     barrier()
     sampler.stop_flag = True
     launches = int(lib.csr_launch_count(0))
-    ms = (np.zeros(6, dtype=np.float64), np.zeros(6, dtype=np.int64))
+    ms = (np.zeros(8, dtype=np.float64), np.zeros(8, dtype=np.int64))
     import ctypes
     lib.csr_profile(0)
     _lib.check(lib.csr_profile_collect(ms[0].ctypes.data_as(ctypes.POINTER(ctypes.c_double)),
@@ -316,7 +316,7 @@ def run_ours(args):
 
     # ---- roofline of the dominant kernel ---------------------------------------------------------------------
     flops_launch = 8.0 * M_CH * N_PHI * P
-    gemm_ms, gemm_n = float(ms[0].sum()), int(ms[1].sum())
+    gemm_ms, gemm_n = float(ms[0][:6].sum()), int(ms[1][:6].sum())
     achieved = flops_launch * gemm_n / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
     peak = peaks["tf_sustained"]
     per_kind = {}

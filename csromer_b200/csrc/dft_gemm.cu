@@ -444,6 +444,22 @@ struct ProfiledLaunch {
 static bool g_profile = false;
 static std::vector<ProfiledLaunch> g_profiled;
 
+// used by the wavelet launchers (kinds 6 = fused synthesis, 7 = fused analysis + update)
+bool profile_start(cudaStream_t stream, cudaEvent_t* start, cudaEvent_t* stop) {
+    if (!g_profile) return false;
+    if (cudaEventCreate(start) != cudaSuccess || cudaEventCreate(stop) != cudaSuccess) return false;
+    cudaEventRecord(*start, stream);
+    return true;
+}
+void profile_stop(int kind, cudaStream_t stream, cudaEvent_t start, cudaEvent_t stop) {
+    cudaEventRecord(stop, stream);
+    ProfiledLaunch rec;
+    rec.kind = kind;
+    rec.start = start;
+    rec.stop = stop;
+    g_profiled.push_back(rec);
+}
+
 // fp32 row-major [rows, cols] matrix -> map with a {256 x 128} box used only for L2 prefetch of epilogue tiles
 static int make_prefetch_map(CUtensorMap* map, const void* base, int rows, int cols, int ld) {
     EncodeTiledFn enc = get_encode_fn();
@@ -544,7 +560,8 @@ int launch_dft_gemm(const csr_plan* plan, bool adjoint, const __half* a_hi, cons
 
 using namespace csr;
 
-// kinds: 0 plain-forward, 1 plain-adjoint, 2 resid-forward, 3 resid-adjoint, 4 fista-forward, 5 fista-adjoint
+// kinds: 0 plain-forward, 1 plain-adjoint, 2 resid-forward, 3 resid-adjoint, 4 fista-forward, 5 fista-adjoint,
+//        6 fused wavelet synthesis, 7 fused wavelet analysis + update
 extern "C" int csr_profile(int enable) {
     g_profile = enable != 0;
     return CSR_OK;
@@ -552,7 +569,7 @@ extern "C" int csr_profile(int enable) {
 
 extern "C" int csr_profile_collect(double* ms_by_kind, long long* count_by_kind) {
     CSR_REQUIRE(ms_by_kind && count_by_kind, "csr_profile_collect: null pointer");
-    for (int i = 0; i < 6; ++i) {
+    for (int i = 0; i < 8; ++i) {
         ms_by_kind[i] = 0.0;
         count_by_kind[i] = 0;
     }

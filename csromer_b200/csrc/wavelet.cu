@@ -381,6 +381,9 @@ static int set_wavelet_smem(K kernel, int bytes) {
     return CSR_OK;
 }
 
+bool profile_start(cudaStream_t stream, cudaEvent_t* start, cudaEvent_t* stop);
+void profile_stop(int kind, cudaStream_t stream, cudaEvent_t start, cudaEvent_t stop);
+
 int swt_synth_fused(const csr_wavelet* w, const float* coef, int ld_coef, float* sig, int ld_sig, __half* hi,
                     __half* lo, int ld_h, const float* scale, int P, cudaStream_t stream) {
     const FusedTiling t = fused_tiling(w, 3);
@@ -391,10 +394,13 @@ int swt_synth_fused(const csr_wavelet* w, const float* coef, int ld_coef, float*
         if (rc) return rc;
         configured = true;
     }
+    cudaEvent_t ev0, ev1;
+    const bool prof = profile_start(stream, &ev0, &ev1);
     swt_synth_fused_kernel<<<dim3(t.ntiles, P), WAV_THREADS, smem, stream>>>(
         coef, ld_coef, w->N, w->levels, t.H, t.T, t.B, band_offsets(w), make_pair(w->rec_lo, w->rec_hi, w->F), sig, ld_sig,
         hi, lo, ld_h, scale);
     CSR_LAUNCHED();
+    if (prof) profile_stop(6, stream, ev0, ev1);
     return CSR_OK;
 }
 
@@ -411,6 +417,8 @@ int swt_analysis_fused(const csr_wavelet* w, const float* signal, int ld_sig, fl
     }
     const dim3 grid(t.ntiles, P);
     const FilterPair f = make_pair(w->dec_lo, w->dec_hi, w->F);
+    cudaEvent_t ev0, ev1;
+    const bool prof = update && profile_start(stream, &ev0, &ev1);
     if (update) {
         swt_analysis_fused_kernel<true><<<grid, WAV_THREADS, smem, stream>>>(signal, ld_sig, w->N, w->levels, t.H, t.T, t.B,
                                                                             band_offsets(w), f, coef, ld_coef, *update);
@@ -421,6 +429,7 @@ int swt_analysis_fused(const csr_wavelet* w, const float* signal, int ld_sig, fl
                                                                              band_offsets(w), f, coef, ld_coef, none);
     }
     CSR_LAUNCHED();
+    if (prof) profile_stop(7, stream, ev0, ev1);
     return CSR_OK;
 }
 

@@ -145,9 +145,9 @@ int csr_convolve_phi(const float* x, int ld, int n, int P, const float* taps_hos
 int csr_peak(const float* F, int ld, int n, int P, int* argmax, float* stats, void* stream);
 
 /* per-launch timing of the transform GEMMs with CUDA events on the launching stream (measurement aid).
- * csr_profile(1) starts recording; csr_profile_collect sums elapsed ms and launch counts into 6-entry arrays
- * indexed [0 plain-forward, 1 plain-adjoint, 2 resid-forward, 3 resid-adjoint, 4 fista-forward, 5 fista-adjoint]
- * and clears the record. */
+ * csr_profile(1) starts recording; csr_profile_collect sums elapsed ms and launch counts into 8-entry arrays
+ * indexed [0 plain-forward, 1 plain-adjoint, 2 resid-forward, 3 resid-adjoint, 4 fista-forward, 5 fista-adjoint,
+ * 6 fused wavelet synthesis, 7 fused wavelet analysis + update] and clears the record. */
 int csr_profile(int enable);
 int csr_profile_collect(double* ms_by_kind, long long* count_by_kind);
 
