@@ -553,3 +553,33 @@ def test_cube_recipe_matches_oracle(use_wavelet):
     np.testing.assert_allclose(info["rm_restored"].reshape(-1), io["rm_restored"], atol=1e-9)
     np.testing.assert_allclose(info["peak_restored"].reshape(-1), io["peak_restored"], rtol=1e-4)
     assert info["iterations"] == int(np.floor(np.sqrt(400 + np.sqrt(800))))
+
+
+def test_config1_reference_default_schedule_known_answers():
+    """BASELINE configs[0] with the reference's DEFAULT schedule (README.md:157-210): lambda from the sigma heuristic,
+    noise = theo_noise, 1458 iterations.  The numbers below were produced by the reference's own classes
+    ("Reference-derived known answers"; 890 s per line of sight there)."""
+    nu = np.linspace(1.008e9, 2.031e9, 1000)
+    src = cs.FaradayThinSource(nu=nu, s_nu=0.0035, phi_gal=-200, spectral_idx=1.0)
+    src.simulate()
+    src.apply_noise(0.2 * 0.0035, random_state=np.random.RandomState(0))
+    assert src.theo_noise == pytest.approx(2.213594283189171e-05, rel=1e-12)
+    assert src.k == pytest.approx(2123786584.5300963, rel=1e-12)
+    par = cs.Parameter()
+    par.calculate_cellsize(dataset=src, oversampling=8, verbose=False)
+    dft = cs.DFT1D(dataset=src, parameter=par)
+    nufft = cs.NUFFT1D(dataset=src, parameter=par, solve=True)
+    par.data = dft.backward(src.data)
+    par.complex_data_to_real()
+    lam = np.sqrt(src.m + 2 * np.sqrt(src.m)) * np.sqrt(2) * np.mean(src.sigma)
+    assert lam == pytest.approx(0.03227972378805074, rel=1e-12)
+    chi2, l1 = cs.Chi2(dft_obj=nufft), cs.L1(reg=lam)
+    obj, X = cs.FISTA(guess_param=par, F_obj=cs.OFunction([chi2, l1]), fx=chi2, gx=cs.OFunction([l1]), noise=src.theo_noise,
+                      verbose=False).run()
+    X.real_data_to_complex()
+    assert l1.reg == pytest.approx(5.519139152513642e-06, rel=1e-6)
+    assert obj == pytest.approx(644.0708285925691, rel=2e-4)
+    assert par.phi[np.argmax(np.abs(X.data))] == pytest.approx(-201.9582742926516)
+    assert np.abs(X.data).max() == pytest.approx(0.019214807054993312, rel=1e-3)
+    assert abs(np.count_nonzero(X.data) - 2719) <= 30  # the last iterations run at the edge of the unit step's stability
+    assert np.sqrt(np.mean(np.abs(src.residual) ** 2)) == pytest.approx(0.00079447427061831, rel=1e-4)
