@@ -176,7 +176,8 @@ struct BandOffsets {
 
 // Inner loops with the filter length known at compile time: the taps unroll, the coefficients become constant-bank
 // operands of the FMAs and the loads of one output are all issued before its FMAs.  FLEN = 0 is the generic loop.
-template <int FLEN>
+// USE_A / USE_D: an operand whose whole tile is identically zero is not read (its contribution is exactly 0)
+template <int FLEN, bool USE_A, bool USE_D>
 __device__ __forceinline__ void synth_level(const float* __restrict__ a, const float* __restrict__ d,
                                             float* __restrict__ o, int B, int step, const FilterPair& f) {
     const int F = FLEN ? FLEN : f.F;
@@ -188,13 +189,13 @@ __device__ __forceinline__ void synth_level(const float* __restrict__ a, const f
         if (FLEN) {
 #pragma unroll
             for (int t = 0; t < FLEN; ++t) {
-                acc0 = fmaf(f.lo[t], ap[-t * step], acc0);
-                acc1 = fmaf(f.hi[t], dp[-t * step], acc1);
+                if (USE_A) acc0 = fmaf(f.lo[t], ap[-t * step], acc0);
+                if (USE_D) acc1 = fmaf(f.hi[t], dp[-t * step], acc1);
             }
         } else {
             for (int t = 0; t < F; ++t) {
-                acc0 = fmaf(f.lo[t], ap[-t * step], acc0);
-                acc1 = fmaf(f.hi[t], dp[-t * step], acc1);
+                if (USE_A) acc0 = fmaf(f.lo[t], ap[-t * step], acc0);
+                if (USE_D) acc1 = fmaf(f.hi[t], dp[-t * step], acc1);
             }
         }
         o[i] = 0.5f * (acc0 + acc1);
@@ -245,15 +246,37 @@ swt_synth_fused_kernel(const float* __restrict__ coef, int ld_coef, int N, int L
     const int t0 = blockIdx.x * T;
     const int base = t0 - H;
     const float* crow = coef + (size_t)p * ld_coef;
-    for (int i = threadIdx.x; i < B; i += WAV_THREADS) a[i] = crow[bands.off[0] + wrap_index(base + i, N)];
+    // Sparsity shortcut (exact): thresholded coefficient vectors are mostly zero.  A band tile that is identically
+    // zero contributes exactly 0, so it is neither staged nor read; while the running approximation is itself
+    // identically zero the whole level is skipped.
+    int any = 0;
+    for (int i = threadIdx.x; i < B; i += WAV_THREADS) {
+        const float v = crow[bands.off[0] + wrap_index(base + i, N)];
+        a[i] = v;
+        any |= (v != 0.f);
+    }
+    bool a_nz = __syncthreads_or(any) != 0;
     for (int lev = L; lev >= 1; --lev) {
         const int step = 1 << (lev - 1);
         const float* dband = crow + bands.off[L - lev + 1];
-        for (int i = threadIdx.x; i < B; i += WAV_THREADS) d[i] = dband[wrap_index(base + i, N)];
-        __syncthreads();
+        any = 0;
+        for (int i = threadIdx.x; i < B; i += WAV_THREADS) {
+            const float v = dband[wrap_index(base + i, N)];
+            d[i] = v;
+            any |= (v != 0.f);
+        }
+        const bool d_nz = __syncthreads_or(any) != 0;
+        if (!a_nz && !d_nz) continue;  // result identically zero: nothing to compute, `a` stays "zero"
         // only entries whose taps stay inside the buffer are computed (no per-tap clamping); the uncomputed rim
         // grows by step*F/2 per level and is covered by the halo
-        CSR_DISPATCH_FLEN(f.F, synth_level<FL>(a, d, o, B, step, f))
+        if (a_nz && d_nz) {
+            CSR_DISPATCH_FLEN(f.F, (synth_level<FL, true, true>(a, d, o, B, step, f)))
+        } else if (a_nz) {
+            CSR_DISPATCH_FLEN(f.F, (synth_level<FL, true, false>(a, d, o, B, step, f)))
+        } else {
+            CSR_DISPATCH_FLEN(f.F, (synth_level<FL, false, true>(a, d, o, B, step, f)))
+        }
+        a_nz = true;
         __syncthreads();
         float* tmp = a;
         a = o;
@@ -263,7 +286,7 @@ swt_synth_fused_kernel(const float* __restrict__ coef, int ld_coef, int N, int L
     for (int i = H + threadIdx.x; i < H + T; i += WAV_THREADS) {
         const int g = t0 + (i - H);
         if (g >= N) break;
-        const float v = a[i];
+        const float v = a_nz ? a[i] : 0.f;
         if (sig) sig[(size_t)p * ld_sig + g] = v;
         if (hi) {
             __half h, l;
