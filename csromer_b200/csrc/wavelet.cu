@@ -26,9 +26,9 @@ struct FilterPair {
 // ---- undecimated ------------------------------------------------------------------------------------------
 __global__ void swt_level_kernel(const float* __restrict__ a_in, int ld_in, float* __restrict__ a_out, int ld_a,
                                  float* __restrict__ d_out, int ld_d, int N, int step, const FilterPair f) {
-    const int o = blockIdx.x * blockDim.x + threadIdx.x;
+    const int o = blockIdx.y * blockDim.x + threadIdx.x;
     if (o >= N) return;
-    const int p = blockIdx.y;
+    const int p = blockIdx.x;
     const float* src = a_in + (size_t)p * ld_in;
     int idx = (o + (f.F * step) / 2) % N;
     float ca = 0.f, cd = 0.f;
@@ -48,9 +48,9 @@ __global__ void swt_level_kernel(const float* __restrict__ a_in, int ld_in, floa
 __global__ void iswt_level_kernel(const float* __restrict__ a_in, int ld_a, const float* __restrict__ d_in, int ld_d,
                                   float* __restrict__ out, int ld_out, const float* __restrict__ add, int ld_add, int N,
                                   int step, const FilterPair f) {
-    const int o = blockIdx.x * blockDim.x + threadIdx.x;
+    const int o = blockIdx.y * blockDim.x + threadIdx.x;
     if (o >= N) return;
-    const int p = blockIdx.y;
+    const int p = blockIdx.x;
     const float* a = a_in + (size_t)p * ld_a;
     const float* d = d_in + (size_t)p * ld_d;
     // idx(t) = (o + step*(F/2 - 1 - t)) mod N, walked downwards in t
@@ -74,9 +74,9 @@ __global__ void dwt_level_kernel(const float* __restrict__ x_in, int ld_in, int 
                                  float* __restrict__ d_out, int ld_d, const FilterPair f) {
     const int Np = N + (N & 1);
     const int half = Np / 2;
-    const int o = blockIdx.x * blockDim.x + threadIdx.x;
+    const int o = blockIdx.y * blockDim.x + threadIdx.x;
     if (o >= half) return;
-    const int p = blockIdx.y;
+    const int p = blockIdx.x;
     const float* src = x_in + (size_t)p * ld_in;
     int idx = (2 * o + f.F / 2) % Np;
     float ca = 0.f, cd = 0.f;
@@ -96,9 +96,9 @@ __global__ void dwt_level_kernel(const float* __restrict__ x_in, int ld_in, int 
 __global__ void idwt_level_kernel(const float* __restrict__ a_in, int ld_a, const float* __restrict__ d_in, int ld_d,
                                   int half, float* __restrict__ out, int ld_out, int keep,
                                   const float* __restrict__ add, int ld_add, const FilterPair f) {
-    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    const int q = blockIdx.y * blockDim.x + threadIdx.x;
     if (q >= keep) return;
-    const int p = blockIdx.y;
+    const int p = blockIdx.x;
     const int N = 2 * half;
     const float* a = a_in + (size_t)p * ld_a;
     const float* d = d_in + (size_t)p * ld_d;
@@ -117,8 +117,8 @@ __global__ void idwt_level_kernel(const float* __restrict__ a_in, int ld_a, cons
 
 __global__ void copy_rows_kernel(const float* __restrict__ src, int ld_src, float* __restrict__ dst, int ld_dst,
                                  int cols) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c < cols) dst[(size_t)blockIdx.y * ld_dst + c] = src[(size_t)blockIdx.y * ld_src + c];
+    const int c = blockIdx.y * blockDim.x + threadIdx.x;
+    if (c < cols) dst[(size_t)blockIdx.x * ld_dst + c] = src[(size_t)blockIdx.x * ld_src + c];
 }
 
 static FilterPair make_pair(const float* lo, const float* hi, int F) {
@@ -132,7 +132,8 @@ static FilterPair make_pair(const float* lo, const float* hi, int F) {
     return f;
 }
 
-static inline dim3 grid_for(int cols, int P) { return dim3((cols + 255) / 256, P); }
+// lines of sight on grid.x (limit 2^31 - 1), column blocks on grid.y
+static inline dim3 grid_for(int cols, int P) { return dim3(P, (cols + 255) / 256); }
 
 int wavelet_ld(const csr_wavelet* w) { return round_up(w->N, 8); }
 
@@ -242,8 +243,8 @@ swt_synth_fused_kernel(const float* __restrict__ coef, int ld_coef, int N, int L
     float* a = wsm;
     float* o = wsm + B;
     float* d = wsm + 2 * B;
-    const int p = blockIdx.y;
-    const int t0 = blockIdx.x * T;
+    const int p = blockIdx.x;
+    const int t0 = blockIdx.y * T;
     const int base = t0 - H;
     const float* crow = coef + (size_t)p * ld_coef;
     // Sparsity shortcut (exact): thresholded coefficient vectors are mostly zero.  A band tile that is identically
@@ -308,6 +309,41 @@ struct CoefUpdate {  // FISTA update applied to each coefficient as its gradient
     float* delta;
 };
 
+// one analysis level over the whole buffer, filter length fixed at compile time (the dispatch happens once per level,
+// not per element).  d-band results are written (UPDATE = false) or consumed by the FISTA update (UPDATE = true).
+template <int FLEN, bool UPDATE>
+__device__ __forceinline__ void analysis_level(const float* __restrict__ a, float* __restrict__ o, int B, int step, int H,
+                                               int T, int t0, int N, const FilterPair& f, float* __restrict__ cband,
+                                               float* __restrict__ xband, float* __restrict__ zband, float ustep,
+                                               float thr, float beta, float& dsum) {
+    const int F = FLEN ? FLEN : f.F;
+    const int rim = step * (F / 2);
+    const int vlo = H, vhi = min(H + T, H + (N - t0));  // buffer indices whose global sample exists and belongs to the tile
+    for (int i = rim + threadIdx.x; i < B - rim; i += WAV_THREADS) {
+        const bool valid = i >= vlo && i < vhi;
+        const int g = t0 + (i - H);
+        float zo = 0.f, xo = 0.f;
+        if (UPDATE && valid) {  // issue the state loads before the filter loop
+            zo = __ldcg(zband + g);
+            xo = __ldcg(xband + g);
+        }
+        float ca, cd;
+        analysis_taps<FLEN>(a + i + (F * step) / 2, step, f, ca, cd);
+        o[i] = ca;
+        if (valid) {
+            if (UPDATE) {
+                const float u = zo - ustep * cd;
+                const float xn = copysignf(fmaxf(fabsf(u) - thr, 0.f), u);
+                __stcs(xband + g, xn);
+                __stcs(zband + g, xn + beta * (xn - xo));
+                dsum += fabsf(xn - xo);
+            } else {
+                cband[g] = cd;
+            }
+        }
+    }
+}
+
 // signal -> coefficients.  UPDATE = false: write the coefficients (decompose).  UPDATE = true: the signal is the
 // gradient in phi space; every coefficient g of its analysis is consumed on the spot by
 // u = z - step g ; x = soft(u, step lambda) ; z = x + beta (x - x_old)   (fista.py:80-86, l1.py:30-32).
@@ -319,8 +355,8 @@ swt_analysis_fused_kernel(const float* __restrict__ signal, int ld_sig, int N, i
     extern __shared__ float wsm[];
     float* a = wsm;
     float* o = wsm + B;
-    const int p = blockIdx.y;
-    const int t0 = blockIdx.x * T;
+    const int p = blockIdx.x;
+    const int t0 = blockIdx.y * T;
     const int base = t0 - H;
     float thr = 0.f;
     bool active = true;
@@ -339,31 +375,11 @@ swt_analysis_fused_kernel(const float* __restrict__ signal, int ld_sig, int N, i
     for (int lev = 1; lev <= L; ++lev) {
         const int step = 1 << (lev - 1);
         const int band = bands.off[L - lev + 1];
-        const int rim = step * (f.F / 2);
-        for (int i = rim + threadIdx.x; i < B - rim; i += WAV_THREADS) {
-            const int g = t0 + (i - H);
-            const bool valid = i >= H && i < H + T && g < N;
-            float zo = 0.f, xo = 0.f;
-            if (UPDATE && valid) {  // issue the state loads before the filter loop
-                zo = __ldcg(up.z + crow + band + g);
-                xo = __ldcg(up.x + crow + band + g);
-            }
-            const float* ap = a + i + (f.F * step) / 2;
-            float ca, cd;
-            CSR_DISPATCH_FLEN(f.F, analysis_taps<FL>(ap, step, f, ca, cd))
-            o[i] = ca;
-            if (valid) {
-                if (UPDATE) {
-                    const float u = zo - up.step * cd;
-                    const float xn = copysignf(fmaxf(fabsf(u) - thr, 0.f), u);
-                    up.x[crow + band + g] = xn;
-                    up.z[crow + band + g] = xn + up.beta * (xn - xo);
-                    dsum += fabsf(xn - xo);
-                } else {
-                    coef[crow + band + g] = cd;
-                }
-            }
-        }
+        float* cband = UPDATE ? nullptr : coef + crow + band;
+        float* xband = UPDATE ? up.x + crow + band : nullptr;
+        float* zband = UPDATE ? up.z + crow + band : nullptr;
+        CSR_DISPATCH_FLEN(f.F, (analysis_level<FL, UPDATE>(a, o, B, step, H, T, t0, N, f, cband, xband, zband, up.step, thr,
+                                                         up.beta, dsum)))
         __syncthreads();
         float* tmp = a;
         a = o;
@@ -419,7 +435,7 @@ int swt_synth_fused(const csr_wavelet* w, const float* coef, int ld_coef, float*
     }
     cudaEvent_t ev0, ev1;
     const bool prof = profile_start(stream, &ev0, &ev1);
-    swt_synth_fused_kernel<<<dim3(t.ntiles, P), WAV_THREADS, smem, stream>>>(
+    swt_synth_fused_kernel<<<dim3(P, t.ntiles), WAV_THREADS, smem, stream>>>(
         coef, ld_coef, w->N, w->levels, t.H, t.T, t.B, band_offsets(w), make_pair(w->rec_lo, w->rec_hi, w->F), sig, ld_sig,
         hi, lo, ld_h, scale);
     CSR_LAUNCHED();
@@ -438,7 +454,7 @@ int swt_analysis_fused(const csr_wavelet* w, const float* signal, int ld_sig, fl
         if (rc) return rc;
         configured = true;
     }
-    const dim3 grid(t.ntiles, P);
+    const dim3 grid(P, t.ntiles);
     const FilterPair f = make_pair(w->dec_lo, w->dec_hi, w->F);
     cudaEvent_t ev0, ev1;
     const bool prof = update && profile_start(stream, &ev0, &ev1);
