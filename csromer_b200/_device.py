@@ -186,9 +186,11 @@ class DevicePlan:
                    "csr_derotate")
 
     def fista(self, data, w, s, k, x, lambda0, noise, iters, step=1.0, norm_factor=1.0, wavelet=None,
-              use_dirty_as_guess=False, want_dirty=True, want_model=True, want_delta=False, iter_cap=None):
+              use_dirty_as_guess=False, want_dirty=True, want_model=True, want_delta=False, iter_cap=None,
+              want_mma_blocks=False):
         """Run the fused loop.  All tensors are fp32 on the device; ``x`` ([P, ldx]) is updated in place.
-        Returns dict(f_dirty, model, residual, cost[P,2], delta)."""
+        Returns dict(f_dirty, model, residual, cost[P,2], delta[, mma_blocks]).  ``mma_blocks`` (measurement aid) is the
+        number of 128 x 256 x 64 tensor-core blocks the in-loop GEMMs issued (3 per tile and K block when dense)."""
         P = data.shape[0]
         dev = self.device
         out = dict(f_dirty=None, model=None, residual=None, cost=None, delta=None)
@@ -200,10 +202,13 @@ class DevicePlan:
             out["cost"] = torch.empty((P, 2), dtype=torch.float32, device=dev)
         if want_delta:
             out["delta"] = torch.zeros((P,), dtype=torch.float32, device=dev)
+        if want_mma_blocks:
+            out["mma_blocks"] = torch.zeros((1,), dtype=torch.int64, device=dev)
         whandle = wavelet.handle if wavelet is not None else None
         need = self.lib.csr_fista_ws_bytes(self.handle, whandle, P)
         ws = self.ws.get(need, dev)
         a = _lib.FistaArgs()
+        a.mma_blocks = out["mma_blocks"].data_ptr() if want_mma_blocks else None
         a.P, a.iters, a.step, a.norm_factor = P, int(iters), float(step), float(norm_factor)
         a.w_per_pixel = int(w.dim() == 2)
         a.data, a.w, a.s, a.k = data.data_ptr(), w.data_ptr(), s.data_ptr(), k.data_ptr()

@@ -18,7 +18,7 @@ EXPORTS = [
     "csr_wavelet_destroy", "csr_wavelet_ncoef", "csr_wavelet_levels", "csr_wavelet_level_sizes",
     "csr_wavelet_ws_bytes", "csr_wavelet_decompose", "csr_wavelet_reconstruct", "csr_fista_ws_bytes",
     "csr_fista", "csr_launch_count", "csr_profile", "csr_profile_collect", "csr_edge_noise", "csr_convolve_phi",
-    "csr_peak",
+    "csr_peak", "csr_set_option",
 ]
 
 
@@ -33,6 +33,7 @@ class FistaArgs(ctypes.Structure):
         ("data", c_void_p), ("w", c_void_p), ("s", c_void_p), ("k", c_void_p), ("x", c_void_p), ("ldx", c_int),
         ("lambda0", c_void_p), ("noise", c_void_p), ("iter_cap", c_void_p), ("f_dirty", c_void_p), ("model", c_void_p),
         ("residual", c_void_p), ("cost", c_void_p), ("delta", c_void_p), ("use_dirty_as_guess", c_int),
+        ("mma_blocks", c_void_p),
     ]
 
 
@@ -79,6 +80,7 @@ def load():
     lib.csr_edge_noise.argtypes = [c_void_p, c_int, c_int, c_int, c_void_p, c_float, c_void_p, c_void_p]
     lib.csr_convolve_phi.argtypes = [c_void_p, c_int, c_int, c_int, POINTER(c_float), c_int, c_void_p, c_void_p, c_void_p]
     lib.csr_peak.argtypes = [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]
+    lib.csr_set_option.argtypes = [c_char_p, c_int]
     lib.csr_profile.argtypes = [c_int]
     lib.csr_profile_collect.argtypes = [POINTER(c_double), POINTER(c_longlong)]
     lib.csr_launch_count.argtypes = [c_int]
@@ -91,6 +93,11 @@ def check(rc, what):
     if rc != 0:
         msg = load().csr_last_error().decode("utf-8", "replace")
         raise CsrError("%s failed (status %d): %s" % (what, rc, msg))
+
+
+def set_option(name, value):
+    """toggle one of the exact shortcuts (``zero_skip``, ``k_skip``, ``screen``, ``fused_wavelet``); results do not change"""
+    check(load().csr_set_option(name.encode(), int(value)), "csr_set_option")
 
 
 def dptr(arr):

@@ -193,4 +193,14 @@ __host__ __device__ constexpr uint32_t umma_idesc_f16(int M, int N) {
 }
 #endif  // __CUDACC__
 
+// Run-time switches of the exact shortcuts (csr_set_option; defaults come from the environment once):
+//   zero_skip      FISTA epilogue skips loads/stores of (line of sight, 128-column) blocks that are and stay zero
+//   k_skip         forward GEMM skips K blocks whose A tile is identically zero
+//   fused_wavelet  undecimated transforms run as the fused shared-memory kernels
+//   screen         adjoint tiles whose state is zero are screened with one fp16 product before the full kernel
+struct Options {
+    int zero_skip, k_skip, fused_wavelet, screen;
+};
+Options& options();
+
 }  // namespace csr

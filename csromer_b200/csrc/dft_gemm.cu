@@ -38,7 +38,10 @@ constexpr int EPI_WARPS = 8;               // 4 TMEM lane quarters x 2 column ha
 constexpr int EPI_COLS = BN / 2;           // accumulator columns held in registers per epilogue thread
 constexpr int NUM_THREADS = 128 + 32 * EPI_WARPS;  // warpgroup 0: TMA producer, MMA issuer, 2 idle; warpgroups 1-2: epilogue
 constexpr int TMEM_COLS = 512;
-constexpr int SMEM_BYTES = 1024 /*alignment slack*/ + STAGES * STAGE_BYTES + 256;
+constexpr int KMASK_WORDS = 32;             // K-block activity bitmask: 32 x 32 bits, one bit per 128 K columns
+static_assert(KMASK_WORDS * 32 * 128 == kMaxSkipK, "bitmask capacity");
+constexpr int NUM_WARPS_TOTAL = 4 + EPI_WARPS;
+constexpr int SMEM_BYTES = 1024 /*alignment slack*/ + STAGES * STAGE_BYTES + 256 + NUM_WARPS_TOTAL * KMASK_WORDS * 4 + 16;
 constexpr int RASTER_GROUP = 16;  // pixel tiles per rasterisation group (keeps A and B panels L2-resident)
 static_assert(SMEM_BYTES <= 232448, "shared memory budget exceeded");
 
@@ -50,6 +53,31 @@ __device__ __forceinline__ void tile_coords(int t, int MT, int NT, int& mt, int&
     const int local = t - g * per_group;
     mt = first + local % gsize;
     nt = local / gsize;
+}
+
+// ---- K-block skipping (exact) ---------------------------------------------------------------------------------
+// FISTA's soft threshold leaves most of phi space identically zero for every line of sight of a pixel tile, so most
+// K blocks of the forward transform multiply an all-zero A tile.  The producer of the A operand records, per pixel
+// tile and 128 K columns, whether anything non-zero was written (GemmEpilogue::a_kflags); the three roles of this
+// kernel each turn that row of flags into a bitmask in their own shared-memory slot and walk the same list of
+// active K blocks.  Skipped blocks contribute exact zeros, so results are bit-identical to the dense loop.
+// Returns the number of active K blocks of the tile.
+__device__ __forceinline__ int build_kmask(const unsigned int* flags_row, int nwords, int KB, uint32_t* mask, int lane) {
+    int count = 0;
+    for (int w0 = 0; w0 < nwords; w0 += 32) {
+        const int idx = w0 + lane;
+        const unsigned int v = idx < nwords ? __ldcg(flags_row + idx) : 0u;
+        const uint32_t bits = __ballot_sync(0xffffffffu, v != 0u);
+        if (lane == 0) mask[w0 >> 5] = bits;
+        count += 2 * __popc(bits);
+    }
+    __syncwarp();
+    // the last flag word covers a single K block when KB is odd
+    if ((KB & 1) && ((mask[(KB >> 1) >> 5] >> ((KB >> 1) & 31)) & 1u)) count -= 1;
+    return count;
+}
+__device__ __forceinline__ bool kb_active(const uint32_t* mask, int kb) {
+    return (mask[kb >> 6] >> ((kb >> 1) & 31)) & 1u;
 }
 
 // ---- accumulator fragment --------------------------------------------------------------------------------------
@@ -97,6 +125,7 @@ template <int MODE>
 __device__ __forceinline__ void epilogue_tile(const GemmEpilogue& epi, const float (&acc)[EPI_COLS], int lane, int row0,
                                               int col0) {
     const int quad = lane & 3;
+    int tile_nz = 0;  // EPI_FISTA: may any row of this warp hold a non-zero z in these 128 columns afterwards?
 #pragma unroll
     for (int lh = 0; lh < 2; ++lh) {
 #pragma unroll
@@ -175,6 +204,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmEpilogue& epi, const flo
                         const __half2 l = __floats2half2_rn(r0 - hf.x, r1 - hf.y);
                         *reinterpret_cast<__half2*>(epi.out_hi + row_off + col) = h;
                         *reinterpret_cast<__half2*>(epi.out_lo + row_off + col) = l;
+                        dsum += fabsf(hf.x) + fabsf(hf.y);  // S_p of the screening bound
                     } else {  // EPI_FISTA: u = z - step*g ; x = soft(u, step*lambda) ; z = x + beta (x - x_old)
                         const float u0 = in0[jj].x - a0, u1 = in0[jj].y - a1;
                         const float x0 = copysignf(fmaxf(fabsf(u0) - thr, 0.f), u0);
@@ -205,6 +235,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmEpilogue& epi, const flo
                         }
                     }
                     if (flag_ptr != nullptr && quad == 0 && active && nonzero != flag_in) *flag_ptr = (unsigned char)nonzero;
+                    if (flag_ptr != nullptr) tile_nz |= active ? nonzero : flag_in;  // frozen rows keep their state
                 }
             }
             if (MODE == EPI_FISTA && epi.delta != nullptr) {  // kernel-uniform branch
@@ -212,8 +243,63 @@ __device__ __forceinline__ void epilogue_tile(const GemmEpilogue& epi, const flo
                 dsum += __shfl_xor_sync(0xffffffffu, dsum, 2);
                 if (quad == 0 && row_ok && dsum != 0.f) atomicAdd(epi.delta + row, dsum);
             }
+            if (MODE == EPI_RESID && epi.abs_sum_out != nullptr) {  // kernel-uniform branch
+                dsum += __shfl_xor_sync(0xffffffffu, dsum, 1);
+                dsum += __shfl_xor_sync(0xffffffffu, dsum, 2);
+                if (quad == 0 && row_ok && dsum != 0.f) atomicAdd(epi.abs_sum_out + row, dsum);
+            }
         }
     }
+    if (MODE == EPI_FISTA && epi.tile_flags != nullptr && epi.zero_flags != nullptr && col0 < epi.N) {  // warp-uniform
+        const int any_nz = __any_sync(0xffffffffu, tile_nz);
+        if (lane == 0)
+            reinterpret_cast<unsigned char*>(epi.tile_flags)[((size_t)(row0 / BM) * epi.flag_ld + (col0 >> 7)) * 4 + ((row0 >> 5) & 3)] =
+                (unsigned char)any_nz;
+    }
+}
+
+// ---- screening (exact) ----------------------------------------------------------------------------------------
+// A pixel tile x 256-column tile whose x and z are identically zero stays zero through the FISTA update iff
+// |step * g| <= step * lambda for every element.  Far from the sources g is a few noise sigmas and lambda is tens of
+// them, so that decision does not need fp32-class accuracy: the screening kernel computes g1 = A_hi * B_hi only (one
+// third of the tensor work, half of the operand traffic) and bounds what the other two products and the rounding of
+// both evaluations could add:  |g3 - g1| <= (|A_lo| |B_hi| + |A_hi| |B_lo| + rounding) summed over K
+// <= (2 + 2 + K 2^-13) S_p  in accumulator units, with S_p = sum_k |A_hi[p, k]| (|B_hi| <= 2^12, |B_lo| <= 2,
+// |A_lo| <= 2^-11 |A_hi|).  A tile passes when |g1| + kScreenSlack(K) S_p < lambda for all its elements: the full
+// kernel would have produced exact zeros there, so nothing is written.  Any other tile is appended to a list the
+// three-product FISTA kernel then processes.  Results are bit-identical to running the full kernel on every tile.
+__device__ __forceinline__ float screen_slack(int K) { return 8.f + (float)K * (1.f / 2048.f); }
+
+__device__ __forceinline__ bool screen_tile_fails(const GemmEpilogue& epi, const float (&acc)[EPI_COLS], int lane, int row0,
+                                                  int col0, int K) {
+    const int quad = lane & 3;
+    bool fail = false;
+#pragma unroll
+    for (int lh = 0; lh < 2; ++lh) {
+#pragma unroll
+        for (int rh = 0; rh < 2; ++rh) {
+            const int row = row0 + (lane >> 2) + 8 * rh + 16 * lh;
+            if (row >= epi.P) continue;
+            const float l0 = __ldg(epi.lambda0 + row), nz = __ldg(epi.noise + row);
+            const float lam = l0 - (float)epi.iter * nz;
+            const bool active = (nz < l0) && (epi.iter == 0 || lam > 0.f) && (!epi.iter_cap || epi.iter < __ldg(epi.iter_cap + row));
+            if (!active) continue;  // a frozen row keeps its (zero) state whatever g is
+            // accumulator units: g = acc * kTwiddleDescale / a_scale;  pass iff |acc| + slack * S_p < lambda / that factor
+            const float lim = lam * __ldg(epi.a_scale + row) * (1.f / kTwiddleDescale) - screen_slack(K) * __ldg(epi.abs_sum + row);
+            float mx = 0.f;
+            bool bad = !(lim > 0.f);
+#pragma unroll
+            for (int jj = 0; jj < 16; ++jj) {
+                const int col = col0 + 8 * jj + 2 * quad;
+                if (col >= epi.N) continue;
+                const int ai = (((lh * 2 + (jj >> 3)) * 8 + (jj & 7)) * 2 + rh) * 2;
+                mx = fmaxf(mx, fmaxf(fabsf(acc[ai]), fabsf(acc[ai + 1])));
+                bad |= (acc[ai] != acc[ai]) | (acc[ai + 1] != acc[ai + 1]);
+            }
+            fail |= bad | !(mx < lim);
+        }
+    }
+    return fail;
 }
 
 template <int MODE>
@@ -234,8 +320,14 @@ dft_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const int total_tiles = MT * NT;
+    // tiles: all MT * NT of them, or the list a screening launch left behind
+    const int total_tiles = epi.tile_list ? __ldcg(epi.tile_count) : MT * NT;
     const int KB = (K + BK - 1) / BK;
+    constexpr int PRODUCTS = (MODE == EPI_SCREEN) ? 1 : 3;
+    int* last_listed = reinterpret_cast<int*>(smem + STAGES * STAGE_BYTES + 256 + NUM_WARPS_TOTAL * KMASK_WORDS * 4);
+    uint32_t* my_mask = reinterpret_cast<uint32_t*>(smem + STAGES * STAGE_BYTES + 256) + warp * KMASK_WORDS;
+    const bool skip = epi.a_kflags != nullptr;
+    const int kwords = (KB + 1) >> 1;  // one flag word per 128 K columns = 2 K blocks
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&map_a_hi);
@@ -252,6 +344,7 @@ dft_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
             mbar_init(&tmem_full[b], 1);
             mbar_init(&tmem_empty[b], EPI_WARPS);
         }
+        *last_listed = -1;
         mbar_fence_init();
     }
     if (warp == 1) {
@@ -262,6 +355,16 @@ dft_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
+    auto tile_id = [&](int ti) -> int { return epi.tile_list ? __ldcg(epi.tile_list + ti) : ti; };
+    // EPI_SCREEN: is the state (x, z) of this tile identically zero?  (both 128-column blocks of all 128 rows)
+    auto tile_quiet = [&](int t) -> bool {
+        int mt, nt;
+        tile_coords(t, MT, NT, mt, nt);
+        const unsigned int* st = epi.tile_state + (size_t)mt * epi.flag_ld + 2 * nt;
+        unsigned int wd = __ldcg(st);
+        if (2 * nt + 1 < epi.flag_ld) wd |= __ldcg(st + 1);
+        return wd == 0u;
+    };
 
     // register budget: the two single-thread roles need few registers, the epilogue warps hold a 128-register
     // accumulator fragment each -- hand the registers over (64512 = 128*40 + 256*232)
@@ -269,33 +372,43 @@ dft_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
       asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
       if (warp == 0) {
         // ===================== TMA producer =====================
-        if (lane == 0) {
+        {
             int stage = 0;
             uint32_t phase = 0;
-            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+            bool quiet_next = (MODE == EPI_SCREEN && (int)blockIdx.x < total_tiles) ? tile_quiet(blockIdx.x) : true;
+            for (int ti = blockIdx.x; ti < total_tiles; ti += gridDim.x) {
+                const int t = tile_id(ti);
                 int mt, nt;
                 tile_coords(t, MT, NT, mt, nt);
-                // Pull the fp32 tiles the fused epilogue of THIS tile will read (z and x_old, or b) into L2 shortly
-                // before the K loop ends, so the epilogue's loads see L2 latency instead of HBM latency.  Not earlier:
-                // more than an L2's worth of data streams through per tile period and would evict them again.
-                const int pf_kb = max(0, KB - prefetch_lead);
-                for (int kb = 0; kb < KB; ++kb) {
-                    if (kb == pf_kb) {
-                        if (num_prefetch > 0) tma_prefetch_2d(&map_pf0, nt * BN, mt * BM);
-                        if (num_prefetch > 1) tma_prefetch_2d(&map_pf1, nt * BN, mt * BM);
-                    }
-                    mbar_wait(&empty[stage], phase ^ 1);
-                    uint8_t* sb = stage_base + stage * STAGE_BYTES;
-                    mbar_arrive_expect_tx(&full[stage], STAGE_BYTES);
-                    tma_load_2d(sb, &map_a_hi, &full[stage], kb * BK, mt * BM);
-                    tma_load_2d(sb + A_TILE_BYTES, &map_a_lo, &full[stage], kb * BK, mt * BM);
-                    tma_load_2d(sb + 2 * A_TILE_BYTES, &map_b_hi, &full[stage], kb * BK, nt * BN);
-                    tma_load_2d(sb + 2 * A_TILE_BYTES + B_TILE_BYTES, &map_b_lo, &full[stage], kb * BK, nt * BN);
-                    if (++stage == STAGES) {
-                        stage = 0;
-                        phase ^= 1;
+                const bool quiet = quiet_next;  // (the next tile's state is fetched while this one streams)
+                if (MODE == EPI_SCREEN && ti + (int)gridDim.x < total_tiles) quiet_next = tile_quiet(ti + gridDim.x);
+                if (MODE == EPI_SCREEN && !quiet) continue;  // tile with signal: left to the three-product kernel
+                if (skip) build_kmask(epi.a_kflags + (size_t)mt * epi.a_kflag_ld, kwords, KB, my_mask, lane);
+                if (lane == 0) {
+                    // Pull the fp32 tiles the fused epilogue of THIS tile will read (z and x_old, or b) into L2 shortly
+                    // before the K loop ends, so the epilogue's loads see L2 latency instead of HBM latency.  Not
+                    // earlier: more than an L2's worth of data streams through per tile period and would evict them.
+                    const int pf_kb = max(0, KB - prefetch_lead);
+                    for (int kb = 0; kb < KB; ++kb) {
+                        if (kb == pf_kb) {
+                            if (num_prefetch > 0) tma_prefetch_2d(&map_pf0, nt * BN, mt * BM);
+                            if (num_prefetch > 1) tma_prefetch_2d(&map_pf1, nt * BN, mt * BM);
+                        }
+                        if (skip && !kb_active(my_mask, kb)) continue;
+                        mbar_wait(&empty[stage], phase ^ 1);
+                        uint8_t* sb = stage_base + stage * STAGE_BYTES;
+                        mbar_arrive_expect_tx(&full[stage], PRODUCTS == 1 ? A_TILE_BYTES + B_TILE_BYTES : STAGE_BYTES);
+                        tma_load_2d(sb, &map_a_hi, &full[stage], kb * BK, mt * BM);
+                        if (PRODUCTS > 1) tma_load_2d(sb + A_TILE_BYTES, &map_a_lo, &full[stage], kb * BK, mt * BM);
+                        tma_load_2d(sb + 2 * A_TILE_BYTES, &map_b_hi, &full[stage], kb * BK, nt * BN);
+                        if (PRODUCTS > 1) tma_load_2d(sb + 2 * A_TILE_BYTES + B_TILE_BYTES, &map_b_lo, &full[stage], kb * BK, nt * BN);
+                        if (++stage == STAGES) {
+                            stage = 0;
+                            phase ^= 1;
+                        }
                     }
                 }
+                __syncwarp();  // the mask slot is rewritten for the next tile
             }
         }
     } else if (warp == 1) {
@@ -304,19 +417,33 @@ dft_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
         // linearly with K.  The accumulation is therefore cut into chunks of `chunk_kb` K blocks: each chunk
         // starts a fresh TMEM accumulator (two of them, ping-pong) which the epilogue warps add into registers
         // with round-to-nearest while the next chunk is being computed.
-        if (lane == 0) {
+        {
             constexpr uint32_t idesc = umma_idesc_f16(BM, BN);
             int stage = 0;
             uint32_t phase = 0;
             uint32_t chunk = 0;  // running chunk counter -> TMEM buffer = chunk & 1, parity = (chunk >> 1) & 1
-            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-                for (int kb0 = 0; kb0 < KB; kb0 += chunk_kb, ++chunk) {
-                    const int buf = chunk & 1;
-                    mbar_wait(&tmem_empty[buf], ((chunk >> 1) & 1) ^ 1);
-                    tc_fence_after();
-                    const uint32_t d_tmem = tmem_base + (uint32_t)(buf * BN);
-                    const int kb1 = min(KB, kb0 + chunk_kb);
-                    for (int kb = kb0; kb < kb1; ++kb) {
+            unsigned long long issued = 0;  // K blocks x products (executed-work accounting)
+            bool quiet_next = (MODE == EPI_SCREEN && (int)blockIdx.x < total_tiles) ? tile_quiet(blockIdx.x) : true;
+            for (int ti = blockIdx.x; ti < total_tiles; ti += gridDim.x) {
+                const bool quiet = quiet_next;
+                if (MODE == EPI_SCREEN && ti + (int)gridDim.x < total_tiles) quiet_next = tile_quiet(ti + gridDim.x);
+                if (MODE == EPI_SCREEN && !quiet) continue;
+                if (skip) {
+                    int mt, nt;
+                    tile_coords(tile_id(ti), MT, NT, mt, nt);
+                    build_kmask(epi.a_kflags + (size_t)mt * epi.a_kflag_ld, kwords, KB, my_mask, lane);
+                }
+                if (lane == 0) {
+                    int in_chunk = 0;  // active K blocks accumulated into the current chunk so far
+                    uint32_t d_tmem = 0;
+                    for (int kb = 0; kb < KB; ++kb) {
+                        if (skip && !kb_active(my_mask, kb)) continue;
+                        if (in_chunk == 0) {
+                            const int buf = chunk & 1;
+                            mbar_wait(&tmem_empty[buf], ((chunk >> 1) & 1) ^ 1);
+                            tc_fence_after();
+                            d_tmem = tmem_base + (uint32_t)(buf * BN);
+                        }
                         mbar_wait(&full[stage], phase);
                         tc_fence_after();
                         const uint32_t sa_hi = smem_u32(stage_base + stage * STAGE_BYTES);
@@ -329,19 +456,32 @@ dft_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
                             const uint64_t da_lo = umma_desc_sw128(sa_lo + k4 * 32);
                             const uint64_t db_hi = umma_desc_sw128(sb_hi + k4 * 32);
                             const uint64_t db_lo = umma_desc_sw128(sb_lo + k4 * 32);
-                            umma_f16(d_tmem, da_hi, db_hi, idesc, (kb != kb0 || k4 != 0) ? 1u : 0u);
-                            umma_f16(d_tmem, da_lo, db_hi, idesc, 1u);
-                            umma_f16(d_tmem, da_hi, db_lo, idesc, 1u);
+                            umma_f16(d_tmem, da_hi, db_hi, idesc, (in_chunk != 0 || k4 != 0) ? 1u : 0u);
+                            if (PRODUCTS > 1) {
+                                umma_f16(d_tmem, da_lo, db_hi, idesc, 1u);
+                                umma_f16(d_tmem, da_hi, db_lo, idesc, 1u);
+                            }
                         }
+                        issued += PRODUCTS;
                         umma_commit(&empty[stage]);  // smem stage reusable once these MMAs have read it
                         if (++stage == STAGES) {
                             stage = 0;
                             phase ^= 1;
                         }
+                        if (++in_chunk == chunk_kb) {
+                            umma_commit(&tmem_full[chunk & 1]);  // chunk accumulator complete
+                            ++chunk;
+                            in_chunk = 0;
+                        }
                     }
-                    umma_commit(&tmem_full[buf]);  // chunk accumulator complete
+                    if (in_chunk != 0) {
+                        umma_commit(&tmem_full[chunk & 1]);
+                        ++chunk;
+                    }
                 }
+                chunk = __shfl_sync(0xffffffffu, chunk, 0);
             }
+            if (lane == 0 && epi.mma_count != nullptr && issued != 0) atomicAdd(epi.mma_count, issued);
         }
       }
     } else {
@@ -351,13 +491,20 @@ dft_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
         const int sub = warp & 3;        // TMEM lane quarter this warp may read (hardware rule: warp id mod 4)
         const int half = ew >> 2;        // which 128 of the tile's 256 columns
         uint32_t chunk = 0;
-        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        for (int ti = blockIdx.x; ti < total_tiles; ti += gridDim.x) {
+            const int t = tile_id(ti);
             int mt, nt;
             tile_coords(t, MT, NT, mt, nt);
+            if (MODE == EPI_SCREEN && !tile_quiet(t)) {  // hand the tile to the three-product kernel (one warp lists it)
+                if (lane == 0 && atomicMax(last_listed, ti) < ti) epi.out_list[atomicAdd(epi.out_count, 1)] = t;
+                continue;
+            }
             float acc[EPI_COLS];
 #pragma unroll
             for (int j = 0; j < EPI_COLS; ++j) acc[j] = 0.f;
-            for (int kb0 = 0; kb0 < KB; kb0 += chunk_kb, ++chunk) {
+            int active_kb = KB;
+            if (skip) active_kb = build_kmask(epi.a_kflags + (size_t)mt * epi.a_kflag_ld, kwords, KB, my_mask, lane);
+            for (int kb0 = 0; kb0 < active_kb; kb0 += chunk_kb, ++chunk) {
                 const int buf = chunk & 1;
                 mbar_wait(&tmem_full[buf], (chunk >> 1) & 1);
                 tc_fence_after();
@@ -366,7 +513,14 @@ dft_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&tmem_empty[buf]);
             }
-            epilogue_tile<MODE>(epi, acc, lane, mt * BM + sub * 32, nt * BN + half * EPI_COLS);
+            if constexpr (MODE == EPI_SCREEN) {
+                const bool fail = screen_tile_fails(epi, acc, lane, mt * BM + sub * 32, nt * BN + half * EPI_COLS, K);
+                if (__any_sync(0xffffffffu, fail)) {
+                    if (lane == 0 && atomicMax(last_listed, ti) < ti) epi.out_list[atomicAdd(epi.out_count, 1)] = t;
+                }
+            } else {
+                epilogue_tile<MODE>(epi, acc, lane, mt * BM + sub * 32, nt * BN + half * EPI_COLS);
+            }
         }
     }
 
@@ -514,7 +668,7 @@ static int launch_mode(const csr_plan* plan, bool adjoint, const CUtensorMap& a_
     }
     ProfiledLaunch rec;
     if (g_profile) {
-        rec.kind = MODE * 2 + (adjoint ? 1 : 0);
+        rec.kind = MODE == EPI_SCREEN ? 8 : MODE * 2 + (adjoint ? 1 : 0);
         CSR_CUDA(cudaEventCreate(&rec.start));
         CSR_CUDA(cudaEventCreate(&rec.stop));
         CSR_CUDA(cudaEventRecord(rec.start, stream));
@@ -551,6 +705,10 @@ int launch_dft_gemm(const csr_plan* plan, bool adjoint, const __half* a_hi, cons
         case EPI_PLAIN: return launch_mode<EPI_PLAIN>(plan, adjoint, ma_hi, ma_lo, P, epi, stream);
         case EPI_RESID: return launch_mode<EPI_RESID>(plan, adjoint, ma_hi, ma_lo, P, epi, stream);
         case EPI_FISTA: return launch_mode<EPI_FISTA>(plan, adjoint, ma_hi, ma_lo, P, epi, stream);
+        case EPI_SCREEN:
+            CSR_REQUIRE(adjoint && epi.abs_sum && epi.tile_state && epi.out_list && epi.out_count && !epi.tile_list,
+                        "screening launch: missing argument");
+            return launch_mode<EPI_SCREEN>(plan, adjoint, ma_hi, ma_lo, P, epi, stream);
     }
     set_error("unknown epilogue mode %d", epi.mode);
     return CSR_ERR_ARG;
@@ -561,7 +719,7 @@ int launch_dft_gemm(const csr_plan* plan, bool adjoint, const __half* a_hi, cons
 using namespace csr;
 
 // kinds: 0 plain-forward, 1 plain-adjoint, 2 resid-forward, 3 resid-adjoint, 4 fista-forward, 5 fista-adjoint,
-//        6 fused wavelet synthesis, 7 fused wavelet analysis + update
+//        6 fused wavelet synthesis, 7 fused wavelet analysis + update, 8 screening adjoint, 9 reserved
 extern "C" int csr_profile(int enable) {
     g_profile = enable != 0;
     return CSR_OK;
@@ -569,7 +727,7 @@ extern "C" int csr_profile(int enable) {
 
 extern "C" int csr_profile_collect(double* ms_by_kind, long long* count_by_kind) {
     CSR_REQUIRE(ms_by_kind && count_by_kind, "csr_profile_collect: null pointer");
-    for (int i = 0; i < 8; ++i) {
+    for (int i = 0; i < CSR_PROFILE_KINDS; ++i) {
         ms_by_kind[i] = 0.0;
         count_by_kind[i] = 0;
     }

@@ -210,19 +210,26 @@ derotate_kernel(float* __restrict__ data, int ld2m, int m, const double* __restr
 
 // flags[p, blk] = 1 if any of the 128 values z[p, 128*blk .. 128*blk+127] is non-zero (the FISTA epilogue's
 // "all-zero block" shortcut starts from here; x == z at that point)
+// tile_flags (optional, zeroed by the caller): byte (p/32)%4 of word [p/128, blk] is set when the block is non-zero --
+// the forward GEMM skips K blocks whose whole 128-row A tile is zero (dft_gemm.cu, build_kmask)
 __global__ void block_flags_kernel(const float* __restrict__ z, int ld, int cols, unsigned char* __restrict__ flags,
-                                   int flag_ld) {
+                                   int flag_ld, unsigned char* __restrict__ tile_flags) {
     const int p = blockIdx.x;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     for (int blk = warp; blk < flag_ld; blk += EW_THREADS / 32) {
         int nz = 0;
         for (int c = blk * 128 + lane; c < min(cols, blk * 128 + 128); c += 32) nz |= (z[(size_t)p * ld + c] != 0.f);
         nz = __any_sync(0xffffffffu, nz);
-        if (lane == 0) flags[(size_t)p * flag_ld + blk] = (unsigned char)nz;
+        if (lane == 0) {
+            flags[(size_t)p * flag_ld + blk] = (unsigned char)nz;
+            if (nz && tile_flags) tile_flags[((size_t)(p >> 7) * flag_ld + blk) * 4 + ((p >> 5) & 3)] = 1;
+        }
     }
 }
-int launch_block_flags(const float* z, int ld, int cols, int P, unsigned char* flags, int flag_ld, cudaStream_t stream) {
-    block_flags_kernel<<<P, EW_THREADS, 0, stream>>>(z, ld, cols, flags, flag_ld);
+int launch_block_flags(const float* z, int ld, int cols, int P, unsigned char* flags, int flag_ld,
+                       unsigned int* tile_flags, cudaStream_t stream) {
+    if (tile_flags) CSR_CUDA(cudaMemsetAsync(tile_flags, 0, sizeof(unsigned int) * (size_t)((P + 127) / 128) * flag_ld, stream));
+    block_flags_kernel<<<P, EW_THREADS, 0, stream>>>(z, ld, cols, flags, flag_ld, reinterpret_cast<unsigned char*>(tile_flags));
     CSR_LAUNCHED();
     return CSR_OK;
 }

@@ -25,7 +25,8 @@ int launch_coef_update(const float* grad, float* x, float* z, int ld, int ncoef,
                        const float* noise, const int* iter_cap, int iter, float step, float beta, float* delta,
                        cudaStream_t stream);
 int launch_scale_vec(float* v, int n, float f, cudaStream_t stream);
-int launch_block_flags(const float* z, int ld, int cols, int P, unsigned char* flags, int flag_ld, cudaStream_t stream);
+int launch_block_flags(const float* z, int ld, int cols, int P, unsigned char* flags, int flag_ld,
+                       unsigned int* tile_flags, cudaStream_t stream);
 int wavelet_ld(const csr_wavelet* w);
 bool wavelet_fusable(const csr_wavelet* w);
 struct CoefUpdate {
@@ -78,7 +79,12 @@ struct FistaWs {
     float *b, *amask, *fwd_chan, *rscale, *zscale, *z, *f_dirty, *model, *sig, *gcoef, *wav_ws;
     __half *r_hi, *r_lo, *z_hi, *z_lo;
     unsigned char* zero_flags;
+    unsigned int* tile_flags;
     int flag_ld;
+    // safe screening of the adjoint (delta basis): [0] = number of listed tiles, [8 ...) = S_p per line of sight
+    float* screen_hdr;
+    int* tile_list;
+    unsigned long long* mma_count;  // [2]: K blocks x products issued by the in-loop GEMMs, and their dense total
     size_t bytes;
 };
 static FistaWs carve_fista(const csr_plan* plan, const csr_wavelet* wav, int P, void* ws) {
@@ -99,6 +105,10 @@ static FistaWs carve_fista(const csr_plan* plan, const csr_wavelet* wav, int P, 
     f.z_lo = b.take<__half>((size_t)P * plan->ld2n);
     f.flag_ld = (2 * plan->n + 127) / 128;
     f.zero_flags = b.take<unsigned char>((size_t)P * f.flag_ld);
+    f.tile_flags = b.take<unsigned int>((size_t)((P + BM - 1) / BM) * f.flag_ld);
+    f.screen_hdr = b.take<float>((size_t)P + 8);
+    f.tile_list = b.take<int>((size_t)((P + BM - 1) / BM) * ((2 * plan->n + BN - 1) / BN));
+    f.mma_count = b.take<unsigned long long>(2);
     f.sig = f.gcoef = f.wav_ws = nullptr;
     if (wav) {
         f.sig = b.take<float>((size_t)P * plan->ld2n);
@@ -216,13 +226,19 @@ extern "C" int csr_fista(csr_plan* plan, csr_wavelet* wav, const csr_fista_args*
         if ((rc = launch_split_rows(w.z, ld2n, P, 2 * n, nullptr, 0, m, f_dirty, ld2n, w.z_hi, w.z_lo, ld2n, w.zscale, 0, stream)))
             return rc;
     }
-    static const bool zero_skip = getenv("CSR_NO_ZERO_SKIP") == nullptr;
+    const bool zero_skip = options().zero_skip != 0;
+    // forward GEMM skips K blocks whose A tile is identically zero (exact); option k_skip = 0 keeps the dense K loop
+    const bool k_skip = zero_skip && options().k_skip != 0;
+    const bool use_kskip = !wav && k_skip && 2 * n <= kMaxSkipK;
+    // adjoint tiles whose state is zero are screened with one product first (exact); option screen = 0 turns it off
+    const bool use_screen = !wav && zero_skip && options().screen != 0;
     if (!wav && zero_skip) {
-        if ((rc = launch_block_flags(w.z, ld2n, 2 * n, P, w.zero_flags, w.flag_ld, stream))) return rc;
+        if ((rc = launch_block_flags(w.z, ld2n, 2 * n, P, w.zero_flags, w.flag_ld, w.tile_flags, stream))) return rc;
     }
+    CSR_CUDA(cudaMemsetAsync(w.mma_count, 0, 2 * sizeof(unsigned long long), stream));
     if (a.delta) CSR_CUDA(cudaMemsetAsync(a.delta, 0, sizeof(float) * P, stream));
 
-    const bool fused_wavelet = wav && wavelet_fusable(wav) && getenv("CSR_NO_FUSED_WAVELET") == nullptr;
+    const bool fused_wavelet = wav && wavelet_fusable(wav) && options().fused_wavelet != 0;
 
     // 4. iterations
     double t = 1.0;
@@ -250,7 +266,32 @@ extern "C" int csr_fista(csr_plan* plan, csr_wavelet* wav, const csr_fista_args*
             e.out_hi = w.r_hi;
             e.out_lo = w.r_lo;
             e.out_scale = w.rscale;
+            if (use_kskip) {
+                e.a_kflags = w.tile_flags;
+                e.a_kflag_ld = w.flag_ld;
+            }
+            if (use_screen) {
+                CSR_CUDA(cudaMemsetAsync(w.screen_hdr, 0, sizeof(float) * ((size_t)P + 8), stream));
+                e.abs_sum_out = w.screen_hdr + 8;
+            }
+            e.mma_count = w.mma_count;
             if ((rc = launch_dft_gemm(plan, false, w.z_hi, w.z_lo, P, e, stream))) return rc;
+        }
+        if (!wav && use_screen) {
+            GemmEpilogue e = {};
+            e.mode = EPI_SCREEN;
+            e.a_scale = w.rscale;
+            e.lambda0 = a.lambda0;
+            e.noise = a.noise;
+            e.iter_cap = a.iter_cap;
+            e.iter = it;
+            e.abs_sum = w.screen_hdr + 8;
+            e.tile_state = w.tile_flags;
+            e.flag_ld = w.flag_ld;
+            e.out_list = w.tile_list;
+            e.out_count = reinterpret_cast<int*>(w.screen_hdr);
+            e.mma_count = w.mma_count;
+            if ((rc = launch_dft_gemm(plan, true, w.r_hi, w.r_lo, P, e, stream))) return rc;
         }
         if (!wav) {
             GemmEpilogue e = {};
@@ -270,6 +311,12 @@ extern "C" int csr_fista(csr_plan* plan, csr_wavelet* wav, const csr_fista_args*
             e.delta = (last && a.delta) ? a.delta : nullptr;
             e.zero_flags = zero_skip ? w.zero_flags : nullptr;
             e.flag_ld = w.flag_ld;
+            e.tile_flags = zero_skip ? w.tile_flags : nullptr;
+            if (use_screen) {
+                e.tile_list = w.tile_list;
+                e.tile_count = reinterpret_cast<const int*>(w.screen_hdr);
+            }
+            e.mma_count = w.mma_count;
             if ((rc = launch_dft_gemm(plan, true, w.r_hi, w.r_lo, P, e, stream))) return rc;
         } else {
             GemmEpilogue e = {};
@@ -290,6 +337,9 @@ extern "C" int csr_fista(csr_plan* plan, csr_wavelet* wav, const csr_fista_args*
     }
     if (a.delta && a.iters > 0) {
         if ((rc = launch_scale_vec(a.delta, P, 1.0f / (float)ncoef, stream))) return rc;
+    }
+    if (a.mma_blocks) {  // executed-work accounting of the in-loop GEMMs (a measurement aid, two 64-bit counters)
+        CSR_CUDA(cudaMemcpyAsync(a.mma_blocks, w.mma_count, sizeof(unsigned long long), cudaMemcpyDeviceToDevice, stream));
     }
 
     // 5. final evaluate F(x): model_data, residual, chi2 and L1 values (fista.py:107; chi2.py:21-32)

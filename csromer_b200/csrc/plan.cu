@@ -77,7 +77,29 @@ __global__ void twiddle_adj_kernel(const double* __restrict__ lambda2, double l2
 
 }  // namespace csr
 
+namespace csr {
+Options& options() {
+    static Options o = {getenv("CSR_NO_ZERO_SKIP") == nullptr, getenv("CSR_NO_K_SKIP") == nullptr,
+                        getenv("CSR_NO_FUSED_WAVELET") == nullptr, getenv("CSR_NO_SCREEN") == nullptr};
+    return o;
+}
+}  // namespace csr
+
 using namespace csr;
+
+extern "C" int csr_set_option(const char* name, int value) {
+    CSR_REQUIRE(name != nullptr, "csr_set_option: null name");
+    Options& o = options();
+    if (!strcmp(name, "zero_skip")) o.zero_skip = value != 0;
+    else if (!strcmp(name, "k_skip")) o.k_skip = value != 0;
+    else if (!strcmp(name, "fused_wavelet")) o.fused_wavelet = value != 0;
+    else if (!strcmp(name, "screen")) o.screen = value != 0;
+    else {
+        set_error("csr_set_option: unknown option '%s'", name);
+        return CSR_ERR_ARG;
+    }
+    return CSR_OK;
+}
 
 extern "C" const char* csr_last_error(void) { return g_error; }
 extern "C" int csr_version(void) { return 100; }

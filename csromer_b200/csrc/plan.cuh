@@ -35,8 +35,9 @@ namespace csr {
 constexpr int BM = 128;  // lines of sight per tile (UMMA M)
 constexpr int BN = 256;  // output columns per tile (UMMA N)
 constexpr int BK = 64;   // fp16 elements per K block = one 128-byte swizzle row
+constexpr int kMaxSkipK = 32 * 32 * 128;  // longest K the K-block activity bitmask covers (dft_gemm.cu)
 
-enum EpilogueMode { EPI_PLAIN = 0, EPI_RESID = 1, EPI_FISTA = 2 };
+enum EpilogueMode { EPI_PLAIN = 0, EPI_RESID = 1, EPI_FISTA = 2, EPI_SCREEN = 3 };
 
 struct GemmEpilogue {
     // common
@@ -65,6 +66,21 @@ struct GemmEpilogue {
     float* delta;              // [P] sum |x - x_old| (atomicAdd), may be null
     unsigned char* zero_flags; // [P, flag_ld] 1 = block of 128 columns may hold non-zeros; null = no shortcut
     int flag_ld;
+    unsigned int* tile_flags;  // [MT, flag_ld] written by EPI_FISTA: byte q of a word = "rows 32q..32q+31 of pixel tile
+                               // mt may hold non-zeros in this 128-column block"; the next forward GEMM reads it as
+                               // a_kflags and skips K blocks whose A tile is identically zero (exact)
+    // K-block skipping (any mode): word != 0 <=> the A tile (128 rows x 128 K columns) may hold non-zeros; null = dense
+    const unsigned int* a_kflags;
+    int a_kflag_ld;
+    // Safe screening of the FISTA adjoint (exact, see dft_gemm.cu "screening"):
+    float* abs_sum_out;             // EPI_RESID: [P] += sum_c |out_hi[p, c]| (atomicAdd; zeroed by the caller)
+    const float* abs_sum;           // EPI_SCREEN: [P] that sum for the rows of the A operand
+    const unsigned int* tile_state; // EPI_SCREEN: [MT, flag_ld] tile_flags of the current x / z
+    int* out_list;                  // EPI_SCREEN: tiles the full three-product kernel still has to process ...
+    int* out_count;                 //             ... and their number (zeroed by the caller)
+    const int* tile_list;           // any mode: process tiles tile_list[0 .. *tile_count) instead of all MT*NT; null = all
+    const int* tile_count;
+    unsigned long long* mma_count;  // optional: += K blocks x products issued (executed-work accounting)
     int debug;                 // measurement aid (CSR_DEBUG_EPI): bit 0 skips epilogue loads, bit 1 skips stores
 };
 

@@ -475,7 +475,7 @@ int swt_analysis_fused(const csr_wavelet* w, const float* signal, int ld_sig, fl
 // coefficient layout: [signal (N) if append_signal][cA_L][cD_L]...[cD_1]
 int wavelet_decompose(const csr_wavelet* w, const float* signal, int ld_sig, float* coef, int ld_coef, int P,
                       float* ws, cudaStream_t stream) {
-    if (wavelet_fusable(w) && getenv("CSR_NO_FUSED_WAVELET") == nullptr)
+    if (wavelet_fusable(w) && options().fused_wavelet != 0)
         return swt_analysis_fused(w, signal, ld_sig, coef, ld_coef, P, nullptr, stream);
     const int N = w->N, L = w->levels;
     const int ldw = wavelet_ld(w);
@@ -523,7 +523,7 @@ int wavelet_decompose(const csr_wavelet* w, const float* signal, int ld_sig, flo
 
 int wavelet_reconstruct(const csr_wavelet* w, const float* coef, int ld_coef, float* signal, int ld_sig, int P,
                         float* ws, cudaStream_t stream) {
-    if (wavelet_fusable(w) && getenv("CSR_NO_FUSED_WAVELET") == nullptr)
+    if (wavelet_fusable(w) && options().fused_wavelet != 0)
         return swt_synth_fused(w, coef, ld_coef, signal, ld_sig, nullptr, nullptr, 0, nullptr, P, stream);
     const int N = w->N, L = w->levels;
     const int ldw = wavelet_ld(w);

@@ -124,6 +124,9 @@ typedef struct {
     float* cost;
     float* delta;
     int use_dirty_as_guess; /* 1: ignore x on input and start from F_dirty (README.md:186) / its coefficients */
+    unsigned long long* mma_blocks; /* optional [1] (device): K blocks x fp16 products the in-loop GEMMs issued, in units
+                               of one 128 x 256 x 64 tensor-core block; measurement aid for the roofline (a dense
+                               run issues 3 per tile and K block) */
 } csr_fista_args;
 
 size_t csr_fista_ws_bytes(const csr_plan* plan, const csr_wavelet* wav, int P);
@@ -145,11 +148,20 @@ int csr_convolve_phi(const float* x, int ld, int n, int P, const float* taps_hos
 int csr_peak(const float* F, int ld, int n, int P, int* argmax, float* stats, void* stream);
 
 /* per-launch timing of the transform GEMMs with CUDA events on the launching stream (measurement aid).
- * csr_profile(1) starts recording; csr_profile_collect sums elapsed ms and launch counts into 8-entry arrays
- * indexed [0 plain-forward, 1 plain-adjoint, 2 resid-forward, 3 resid-adjoint, 4 fista-forward, 5 fista-adjoint,
- * 6 fused wavelet synthesis, 7 fused wavelet analysis + update] and clears the record. */
+ * csr_profile(1) starts recording; csr_profile_collect sums elapsed ms and launch counts into CSR_PROFILE_KINDS-entry
+ * arrays indexed [0 plain-forward, 1 plain-adjoint, 2 resid-forward, 3 resid-adjoint, 4 fista-forward,
+ * 5 fista-adjoint, 6 fused wavelet synthesis, 7 fused wavelet analysis + update, 8 screening adjoint, 9 reserved]
+ * and clears the record. */
+#define CSR_PROFILE_KINDS 10
 int csr_profile(int enable);
 int csr_profile_collect(double* ms_by_kind, long long* count_by_kind);
+
+/* run-time switches of the exact shortcuts, all default 1 (measurement / test aid; results are bit-identical either
+ * way): "zero_skip" (FISTA epilogue skips blocks that are and stay zero), "k_skip" (forward GEMM skips K blocks whose
+ * A tile is identically zero), "screen" (adjoint tiles whose state is zero are first screened with one fp16 product
+ * and a rigorous error bound; only tiles that may leave zero run the three-product kernel), "fused_wavelet" (fused
+ * shared-memory undecimated transforms). */
+int csr_set_option(const char* name, int value);
 
 /* number of kernels launched by this library on the calling thread since the last reset (bench accounting) */
 long long csr_launch_count(int reset);

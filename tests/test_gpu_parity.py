@@ -215,6 +215,32 @@ def test_fista_delta_basis_batches(nch, P, K, kw):
     check_fista(src, X, cost, l1, ref)
 
 
+@pytest.mark.parametrize("nch,P,K,kw", [(200, 261, 30, dict(mixed=True)), (1000, 300, 20, {}), (203, 129, 25, dict(per_pixel_w=True, flags=0.1))])
+def test_sparsity_shortcuts_are_bit_exact(nch, P, K, kw):
+    """The epilogue's all-zero-block shortcut, the forward GEMM's K-block skipping and the one-product screening of
+    the adjoint must not change a single bit."""
+    from csromer_b200 import _lib
+    src, par = make_batch(nch, P, seed=11 + P, **kw)
+    results = []
+    try:
+        for zero_skip, k_skip, screen in ((1, 1, 1), (1, 1, 0), (1, 0, 1), (1, 0, 0), (0, 0, 0)):
+            _lib.set_option("zero_skip", zero_skip)
+            _lib.set_option("k_skip", k_skip)
+            _lib.set_option("screen", screen)
+            cost, X, l1, lam0, noise = run_fista(src, par, K)
+            results.append((np.array(X.data, copy=True), np.array(cost, copy=True), np.array(src.model_data, copy=True)))
+    finally:
+        _lib.set_option("zero_skip", 1)
+        _lib.set_option("k_skip", 1)
+        _lib.set_option("screen", 1)
+    assert np.count_nonzero(results[0][0]) > 0 and np.count_nonzero(results[0][0]) < 0.2 * results[0][0].size
+    for other in results[1:]:
+        for a, b in zip(results[0], other):
+            np.testing.assert_array_equal(a, b)
+    ref = oracle_fista(src, par, K, lam0, noise)
+    check_fista(src, X, cost, l1, ref)
+
+
 def test_fista_zero_start_and_step_extension():
     src, par = make_batch(200, 37, seed=5)
     cost, X, l1, lam0, noise = run_fista(src, par, 60, lam_mult=5.0, step=1.0 / 2.8, x0="zeros")

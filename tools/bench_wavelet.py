@@ -70,8 +70,8 @@ for _ in range(args.reps):
 e1.record()
 torch.cuda.synchronize()
 lib.csr_profile(0)
-ms = np.zeros(8)
-cnt = np.zeros(8, dtype=np.int64)
+ms = np.zeros(10)
+cnt = np.zeros(10, dtype=np.int64)
 _lib.check(lib.csr_profile_collect(ms.ctypes.data_as(ctypes.POINTER(ctypes.c_double)),
                                    cnt.ctypes.data_as(ctypes.POINTER(ctypes.c_longlong))), "collect")
 total_ms = e0.elapsed_time(e1) / args.reps
