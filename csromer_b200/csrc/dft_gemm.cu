@@ -76,8 +76,16 @@ __device__ __forceinline__ int build_kmask(const unsigned int* flags_row, int nw
     if ((KB & 1) && ((mask[(KB >> 1) >> 5] >> ((KB >> 1) & 31)) & 1u)) count -= 1;
     return count;
 }
-__device__ __forceinline__ bool kb_active(const uint32_t* mask, int kb) {
-    return (mask[kb >> 6] >> ((kb >> 1) & 31)) & 1u;
+// smallest active K block >= kb, or KB when there is none (cost proportional to the number of active blocks, not KB)
+__device__ __forceinline__ int next_active_kb(const uint32_t* mask, int kb, int KB) {
+    while (kb < KB) {
+        const int blk = kb >> 1;
+        const uint32_t bits = mask[blk >> 5] >> (blk & 31);
+        if (bits & 1u) return kb;
+        if (bits) return 2 * (blk + __ffs(bits) - 1);
+        kb = ((blk >> 5) + 1) << 6;
+    }
+    return KB;
 }
 
 // ---- accumulator fragment --------------------------------------------------------------------------------------
@@ -389,12 +397,12 @@ dft_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
                     // before the K loop ends, so the epilogue's loads see L2 latency instead of HBM latency.  Not
                     // earlier: more than an L2's worth of data streams through per tile period and would evict them.
                     const int pf_kb = max(0, KB - prefetch_lead);
-                    for (int kb = 0; kb < KB; ++kb) {
+                    for (int kb = skip ? next_active_kb(my_mask, 0, KB) : 0; kb < KB;
+                         kb = skip ? next_active_kb(my_mask, kb + 1, KB) : kb + 1) {
                         if (kb == pf_kb) {
                             if (num_prefetch > 0) tma_prefetch_2d(&map_pf0, nt * BN, mt * BM);
                             if (num_prefetch > 1) tma_prefetch_2d(&map_pf1, nt * BN, mt * BM);
                         }
-                        if (skip && !kb_active(my_mask, kb)) continue;
                         mbar_wait(&empty[stage], phase ^ 1);
                         uint8_t* sb = stage_base + stage * STAGE_BYTES;
                         mbar_arrive_expect_tx(&full[stage], PRODUCTS == 1 ? A_TILE_BYTES + B_TILE_BYTES : STAGE_BYTES);
@@ -436,8 +444,8 @@ dft_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
                 if (lane == 0) {
                     int in_chunk = 0;  // active K blocks accumulated into the current chunk so far
                     uint32_t d_tmem = 0;
-                    for (int kb = 0; kb < KB; ++kb) {
-                        if (skip && !kb_active(my_mask, kb)) continue;
+                    for (int kb = skip ? next_active_kb(my_mask, 0, KB) : 0; kb < KB;
+                         kb = skip ? next_active_kb(my_mask, kb + 1, KB) : kb + 1) {
                         if (in_chunk == 0) {
                             const int buf = chunk & 1;
                             mbar_wait(&tmem_empty[buf], ((chunk >> 1) & 1) ^ 1);

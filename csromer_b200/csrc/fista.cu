@@ -358,6 +358,10 @@ extern "C" int csr_fista(csr_plan* plan, csr_wavelet* wav, const csr_fista_args*
         e.row_scale = a.k;
         e.chan_scale = w.fwd_chan;
         e.chan_per_pixel = a.w_per_pixel;
+        if (use_kskip) {  // x is zero wherever the loop's tile flags say "x and z are zero"
+            e.a_kflags = w.tile_flags;
+            e.a_kflag_ld = w.flag_ld;
+        }
         if ((rc = launch_dft_gemm(plan, false, w.z_hi, w.z_lo, P, e, stream))) return rc;
         if ((rc = launch_finalize(plan, a, model, a.residual, x, ldc, ncoef, stream))) return rc;
     }

@@ -19,8 +19,10 @@ par = cs.Parameter()
 par.calculate_cellsize(dataset=src, oversampling=8, verbose=False)
 plan = dv.DevicePlan.get(src.lambda2, 0.0, par.phi)
 dev = plan.device
-g = torch.Generator(device=dev).manual_seed(1)
-data = 0.003 * torch.randn((P, plan.ld2m), generator=g, device=dev)
+sys.path.insert(0, ROOT)
+import bench  # noqa: E402  (the bench's own synthetic slab: sources at |phi| < 500 + noise)
+src.sigma = np.full(1000, bench.SIGMA)
+data = dv.pack_planar(bench.make_slab(torch, src, P, 1234, dev), plan.m, plan.ld2m, dev)[0]
 w = torch.full((plan.m,), 1.0 / 0.0007 ** 2, device=dev)
 s = torch.as_tensor(np.ascontiguousarray(src.s), dtype=torch.float32, device=dev)
 k = torch.full((P,), float((w / s).sum()), device=dev)
