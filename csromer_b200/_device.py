@@ -223,6 +223,83 @@ class DevicePlan:
         return out
 
 
+class DeviceStack:
+    """Per-line-of-sight samplings (kernel K4, ``csr_nudft_*`` / ``csr_fista_nu``): lambda2 - l2_ref of every line of
+    sight as an fp64 ``[P, m]`` device matrix (zero padded past ``m_count[p]``) on a uniform phi grid.  No tables."""
+
+    def __init__(self, a, m_count, phi, device=None):
+        require_cuda()
+        self.lib = _lib.load()
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        phi = np.asarray(phi, dtype=np.float64)
+        if phi.ndim != 1 or phi.size < 2:
+            raise ValueError("per-pixel operator needs a 1-D phi grid")
+        dphi = (phi[-1] - phi[0]) / (phi.size - 1)
+        if not np.allclose(np.diff(phi), dphi, rtol=1e-9, atol=0.0):
+            raise ValueError("per-pixel operator needs a uniform phi grid (Parameter.calculate_cellsize builds one)")
+        self.phi0, self.dphi = float(phi[0]), float(dphi)
+        a = np.ascontiguousarray(a, dtype=np.float64)
+        self.P, self.m = int(a.shape[0]), int(a.shape[1])
+        self.n = int(phi.size)
+        self.ld2m, self.ld2n = (2 * self.m + 7) // 8 * 8, (2 * self.n + 7) // 8 * 8
+        self.a = torch.as_tensor(a).to(self.device)
+        self.m_count = torch.as_tensor(np.ascontiguousarray(m_count, dtype=np.int32)).to(self.device)
+        self.ws = Workspace()
+
+    def _sampling(self):
+        s = _lib.NuSampling()
+        s.lambda2, s.ldl, s.m_count = self.a.data_ptr(), self.m, self.m_count.data_ptr()
+        s.m, s.n, s.phi0, s.dphi = self.m, self.n, self.phi0, self.dphi
+        return s
+
+    def forward(self, x, chan_scale=None, row_scale=None):
+        """[P, ld2n] -> [P, ld2m]"""
+        out = torch.zeros((self.P, self.ld2m), dtype=torch.float32, device=self.device)
+        _lib.check(self.lib.csr_nudft_forward(ctypes.byref(self._sampling()), tptr(x), x.shape[1], tptr(chan_scale),
+                                              tptr(row_scale), tptr(out), self.ld2m, self.P, stream_ptr()),
+                   "csr_nudft_forward")
+        return out
+
+    def adjoint(self, b, chan_scale=None, row_scale=None):
+        """[P, ld2m] -> [P, ld2n]"""
+        out = torch.zeros((self.P, self.ld2n), dtype=torch.float32, device=self.device)
+        _lib.check(self.lib.csr_nudft_adjoint(ctypes.byref(self._sampling()), tptr(b), b.shape[1], tptr(chan_scale),
+                                              tptr(row_scale), tptr(out), self.ld2n, self.P, stream_ptr()),
+                   "csr_nudft_adjoint")
+        return out
+
+    def fista(self, data, w, s, k, x, lambda0, noise, iters, step=1.0, norm_factor=1.0, wavelet=None,
+              use_dirty_as_guess=False, want_dirty=True, want_model=True, want_delta=False, iter_cap=None):
+        """same contract as ``DevicePlan.fista``; ``w`` and ``s`` are ``[P, m]``"""
+        P, dev = self.P, self.device
+        out = dict(f_dirty=None, model=None, residual=None, cost=None, delta=None)
+        if want_dirty:
+            out["f_dirty"] = torch.empty((P, self.ld2n), dtype=torch.float32, device=dev)
+        if want_model:
+            out["model"] = torch.empty((P, self.ld2m), dtype=torch.float32, device=dev)
+            out["residual"] = torch.zeros((P, self.ld2m), dtype=torch.float32, device=dev)
+            out["cost"] = torch.empty((P, 2), dtype=torch.float32, device=dev)
+        if want_delta:
+            out["delta"] = torch.zeros((P,), dtype=torch.float32, device=dev)
+        whandle = wavelet.handle if wavelet is not None else None
+        samp = self._sampling()
+        need = self.lib.csr_fista_nu_ws_bytes(ctypes.byref(samp), whandle, P)
+        ws = self.ws.get(need, dev)
+        a = _lib.FistaArgs()
+        a.P, a.iters, a.step, a.norm_factor = P, int(iters), float(step), float(norm_factor)
+        a.w_per_pixel = a.s_per_pixel = 1
+        a.data, a.w, a.s, a.k = data.data_ptr(), w.data_ptr(), s.data_ptr(), k.data_ptr()
+        a.x, a.ldx = x.data_ptr(), x.shape[1]
+        a.lambda0, a.noise = lambda0.data_ptr(), noise.data_ptr()
+        a.iter_cap = iter_cap.data_ptr() if iter_cap is not None else None
+        for key in ("f_dirty", "model", "residual", "cost", "delta"):
+            setattr(a, key, out[key].data_ptr() if out[key] is not None else None)
+        a.use_dirty_as_guess = int(bool(use_dirty_as_guess))
+        _lib.check(self.lib.csr_fista_nu(ctypes.byref(samp), whandle, ctypes.byref(a), tptr(ws), ws.numel(),
+                                         stream_ptr()), "csr_fista_nu")
+        return out
+
+
 class DeviceWavelet:
     """Owns a ``csr_wavelet`` for one (filter bank, level, N) configuration."""
 

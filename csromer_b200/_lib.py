@@ -18,7 +18,7 @@ EXPORTS = [
     "csr_wavelet_destroy", "csr_wavelet_ncoef", "csr_wavelet_levels", "csr_wavelet_level_sizes",
     "csr_wavelet_ws_bytes", "csr_wavelet_decompose", "csr_wavelet_reconstruct", "csr_fista_ws_bytes",
     "csr_fista", "csr_launch_count", "csr_profile", "csr_profile_collect", "csr_edge_noise", "csr_convolve_phi",
-    "csr_peak", "csr_set_option",
+    "csr_peak", "csr_set_option", "csr_nudft_forward", "csr_nudft_adjoint", "csr_fista_nu_ws_bytes", "csr_fista_nu",
 ]
 
 
@@ -33,8 +33,14 @@ class FistaArgs(ctypes.Structure):
         ("data", c_void_p), ("w", c_void_p), ("s", c_void_p), ("k", c_void_p), ("x", c_void_p), ("ldx", c_int),
         ("lambda0", c_void_p), ("noise", c_void_p), ("iter_cap", c_void_p), ("f_dirty", c_void_p), ("model", c_void_p),
         ("residual", c_void_p), ("cost", c_void_p), ("delta", c_void_p), ("use_dirty_as_guess", c_int),
-        ("mma_blocks", c_void_p),
+        ("mma_blocks", c_void_p), ("s_per_pixel", c_int),
     ]
+
+
+class NuSampling(ctypes.Structure):
+    """mirror of ``csr_nu_sampling``"""
+    _fields_ = [("lambda2", c_void_p), ("ldl", c_int), ("m_count", c_void_p), ("m", c_int), ("n", c_int),
+                ("phi0", c_double), ("dphi", c_double)]
 
 
 _lib = None
@@ -81,6 +87,11 @@ def load():
     lib.csr_convolve_phi.argtypes = [c_void_p, c_int, c_int, c_int, POINTER(c_float), c_int, c_void_p, c_void_p, c_void_p]
     lib.csr_peak.argtypes = [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]
     lib.csr_set_option.argtypes = [c_char_p, c_int]
+    for fn in (lib.csr_nudft_forward, lib.csr_nudft_adjoint):
+        fn.argtypes = [POINTER(NuSampling), c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]
+    lib.csr_fista_nu_ws_bytes.argtypes = [POINTER(NuSampling), c_void_p, c_int]
+    lib.csr_fista_nu_ws_bytes.restype = c_size_t
+    lib.csr_fista_nu.argtypes = [POINTER(NuSampling), c_void_p, POINTER(FistaArgs), c_void_p, c_size_t, c_void_p]
     lib.csr_profile.argtypes = [c_int]
     lib.csr_profile_collect.argtypes = [POINTER(c_double), POINTER(c_longlong)]
     lib.csr_launch_count.argtypes = [c_int]

@@ -88,11 +88,12 @@ int launch_split_rows(const float* in, int ld_in, int rows, int cols, const floa
 //   fwd_chan[p?,i] = s norm_factor/(n w) if w>0  forward_normalized's channel factor without k (ndft.py:24-28)
 __global__ void __launch_bounds__(EW_THREADS)
 prepare_kernel(const float* __restrict__ data, int ld2m, int m, int n, const float* __restrict__ w, int w_pp,
-               const float* __restrict__ s, const float* __restrict__ k, float norm_factor, float* __restrict__ b,
-               float* __restrict__ amask, float* __restrict__ fwd_chan) {
+               const float* __restrict__ s_in, int s_pp, const float* __restrict__ k, float norm_factor,
+               float* __restrict__ b, float* __restrict__ amask, float* __restrict__ fwd_chan) {
     const int p = blockIdx.x;
     const float kp = k[p];
     const float* wrow = w + (w_pp ? (size_t)p * m : 0);
+    const float* s = s_in + (s_pp ? (size_t)p * m : 0);
     const float* d = data + (size_t)p * ld2m;
     float* brow = b + (size_t)p * ld2m;
     const float inv_n = norm_factor / (float)n;
@@ -112,7 +113,15 @@ prepare_kernel(const float* __restrict__ data, int ld2m, int m, int n, const flo
 
 int launch_prepare(const csr_plan* plan, const csr_fista_args& a, float* b, float* amask, float* fwd_chan,
                    cudaStream_t stream) {
-    prepare_kernel<<<a.P, EW_THREADS, 0, stream>>>(a.data, plan->ld2m, plan->m, plan->n, a.w, a.w_per_pixel, a.s, a.k,
+    prepare_kernel<<<a.P, EW_THREADS, 0, stream>>>(a.data, plan->ld2m, plan->m, plan->n, a.w, a.w_per_pixel, a.s,
+                                                   a.s_per_pixel, a.k, a.norm_factor, b, amask, fwd_chan);
+    CSR_LAUNCHED();
+    return CSR_OK;
+}
+// same for the per-line-of-sight sampling path (nudft.cu), which has no plan object
+int launch_prepare_nu(const csr_fista_args& a, int m, int n, int ld2m, float* b, float* amask, float* fwd_chan,
+                      cudaStream_t stream) {
+    prepare_kernel<<<a.P, EW_THREADS, 0, stream>>>(a.data, ld2m, m, n, a.w, a.w_per_pixel, a.s, a.s_per_pixel, a.k,
                                                    a.norm_factor, b, amask, fwd_chan);
     CSR_LAUNCHED();
     return CSR_OK;
@@ -148,12 +157,16 @@ finalize_kernel(const float* __restrict__ data, const float* __restrict__ model,
     }
 }
 
-int launch_finalize(const csr_plan* plan, const csr_fista_args& a, const float* model, float* residual,
-                    const float* x, int ldx, int ncoef, cudaStream_t stream) {
-    finalize_kernel<<<a.P, EW_THREADS, 0, stream>>>(a.data, model, plan->ld2m, plan->m, a.w, a.w_per_pixel, residual,
-                                                    x, ldx, ncoef, a.cost);
+int launch_finalize_dims(const csr_fista_args& a, int m, int ld2m, const float* model, float* residual, const float* x,
+                         int ldx, int ncoef, cudaStream_t stream) {
+    finalize_kernel<<<a.P, EW_THREADS, 0, stream>>>(a.data, model, ld2m, m, a.w, a.w_per_pixel, residual, x, ldx, ncoef,
+                                                    a.cost);
     CSR_LAUNCHED();
     return CSR_OK;
+}
+int launch_finalize(const csr_plan* plan, const csr_fista_args& a, const float* model, float* residual,
+                    const float* x, int ldx, int ncoef, cudaStream_t stream) {
+    return launch_finalize_dims(a, plan->m, plan->ld2m, model, residual, x, ldx, ncoef, stream);
 }
 
 // ---- coefficient-space FISTA update (wavelet bases): fista.py:80-86 + l1.py:30-32 on [P, ncoef] ------------

@@ -114,7 +114,8 @@ class FISTA(Optimizer):
         data, pix = dv.pack_planar(ds.data, plan.m, plan.ld2m, dev)
         P = data.shape[0]
         w = op._channel_tensor(ds.w, plan)
-        s = torch.as_tensor(np.asarray(ds.s, dtype=np.float64), dtype=torch.float32).to(dev)
+        s_host = np.asarray(ds.s, dtype=np.float64)
+        s = torch.as_tensor(s_host, dtype=torch.float32).to(dev) if s_host.ndim == 1 else op._channel_tensor(s_host, plan)
         k = dv.per_pixel_vector(ds.k, P, dev, "k")
         engine = None
         if wav is not None:

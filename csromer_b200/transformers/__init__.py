@@ -1,3 +1,3 @@
-from .dfts import DFT1D, FT, NDFT1D, NUFFT1D
+from .dfts import DFT1D, FT, NDFT1D, NUFFT1D, DatasetStack, PerPixelDFT1D
 
-__all__ = ["FT", "NDFT1D", "DFT1D", "NUFFT1D"]
+__all__ = ["FT", "NDFT1D", "DFT1D", "NUFFT1D", "PerPixelDFT1D", "DatasetStack"]

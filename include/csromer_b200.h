@@ -127,11 +127,40 @@ typedef struct {
     unsigned long long* mma_blocks; /* optional [1] (device): K blocks x fp16 products the in-loop GEMMs issued, in units
                                of one 128 x 256 x 64 tensor-core block; measurement aid for the roofline (a dense
                                run issues 3 per tile and K block) */
+    int s_per_pixel;        /* 1: s is [P, m] (per-line-of-sight samplings, csr_fista_nu); 0: [m] */
 } csr_fista_args;
 
 size_t csr_fista_ws_bytes(const csr_plan* plan, const csr_wavelet* wav, int P);
 int csr_fista(csr_plan* plan, csr_wavelet* wav, const csr_fista_args* args, void* ws, size_t ws_bytes,
               void* stream);
+
+/* ---- per-line-of-sight samplings (kernel K4) -----------------------------------------------------------------
+ * When every line of sight has its OWN lambda^2 list (channels deleted per pixel by a flagger,
+ * transformers/flaggers/mean_flagger.py:36-40; one Dataset per pixel in README.md:327-332) no twiddle matrix can be
+ * shared.  These entry points evaluate the same operator (transformers/dfts/ndft.py:17-43, nufft.py:50-77) per line
+ * of sight on the uniform grid phi_j = phi0 + j dphi (reconstruction/parameter.py:105-116) with twiddles generated
+ * on the fly -- no plan, no table.
+ *   lambda2  DEVICE fp64 [P, ldl]: lambda2_i - l2_ref of each line of sight; m_count [P] (or NULL = m) is the number
+ *            of valid leading channels of each row, the rest is padding (output 0 / ignored on input).
+ * csr_nudft_forward: out[p,i] = row_scale[p] chan_scale[p,i] sum_j x[p,j] exp(+2i a_i phi_j)   [P, ldx>=2n] -> [P, ld_out>=2m]
+ * csr_nudft_adjoint: out[p,j] = row_scale[p] sum_i chan_scale[p,i] b[p,i] exp(-2i a_i phi_j)   [P, ldb>=2m] -> [P, ld_out>=2n]
+ * chan_scale is [P, m] or NULL, row_scale [P] or NULL.
+ * csr_fista_nu: csr_fista for such samplings; args->w and args->s must be [P, m] (w_per_pixel = s_per_pixel = 1);
+ *            pitches are ld2m = roundup(2m, 8), ld2n = roundup(2n, 8), ldx = ld2n or roundup(ncoef, 8). */
+typedef struct {
+    const double* lambda2;
+    int ldl;
+    const int* m_count;
+    int m, n;
+    double phi0, dphi;
+} csr_nu_sampling;
+int csr_nudft_forward(const csr_nu_sampling* s, const float* x, int ldx, const float* chan_scale,
+                      const float* row_scale, float* out, int ld_out, int P, void* stream);
+int csr_nudft_adjoint(const csr_nu_sampling* s, const float* b, int ldb, const float* chan_scale,
+                      const float* row_scale, float* out, int ld_out, int P, void* stream);
+size_t csr_fista_nu_ws_bytes(const csr_nu_sampling* s, const csr_wavelet* wav, int P);
+int csr_fista_nu(const csr_nu_sampling* s, csr_wavelet* wav, const csr_fista_args* args, void* ws, size_t ws_bytes,
+                 void* stream);
 
 /* ---- after the loop: the cube recipe's remaining per-line-of-sight steps ("next" rows) ----
  * csr_edge_noise  : noise[p] = eta/2 (std Re F[edges] + std Im F[edges]), numpy.std semantics, over the phi cells whose

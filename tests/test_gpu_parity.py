@@ -314,6 +314,83 @@ def test_fista_iteration_count_semantics():
     assert cost == 0.0 and np.array_equal(X.data, before) and l1b.reg == 1e-6
 
 
+def make_ragged_stack(P, nch, seed, keep=0.8):
+    """P lines of sight that each keep their own random subset of the channels (what a flagger with
+    delete_channels=True leaves behind), one with a non-zero l2_ref, on the shared phi grid of the full band"""
+    rng = np.random.RandomState(seed)
+    nu = np.linspace(1.008e9, 2.031e9, nch)
+    full = cs.Dataset(nu=nu, sigma=np.ones(nch), spectral_idx=1.0)
+    par = cs.Parameter()
+    par.calculate_cellsize(dataset=full, oversampling=8, verbose=False)
+    l2 = np.asarray(full.lambda2)
+    members = []
+    for p in range(P):
+        idx = np.sort(rng.choice(nch, size=max(8, int(keep * nch) - 3 * p), replace=False)) if p else np.arange(nch)
+        lam = l2[idx]
+        sigma = 0.0007 * rng.uniform(0.5, 2.0, size=idx.size)
+        phi0, amp = rng.uniform(-400, 400), 0.0035 * rng.uniform(0.5, 1.5)
+        ds = cs.Dataset(lambda2=lam, sigma=sigma, spectral_idx=1.0, l2_ref=0.03 if p == 1 else None)
+        clean = amp * ds.s * np.exp(2j * phi0 * (lam - ds.l2_ref))
+        ds.data = (clean + rng.normal(0, 0.0007, idx.size) + 1j * rng.normal(0, 0.0007, idx.size)).astype(np.complex64)
+        if p == 2:
+            ds.w[5:15] = 0.0  # in-place flagging on top (k stays, like the reference)
+        members.append(ds)
+    return members, par
+
+
+def test_per_pixel_sampling_transforms_and_fista():
+    """K4: every line of sight has its own lambda^2 list.  Transforms and the FISTA loop against the oracle run
+    line of sight by line of sight (the README's per-pixel loop)."""
+    P, nch, K = 7, 160, 30
+    members, par = make_ragged_stack(P, nch, seed=3)
+    op = cs.PerPixelDFT1D(dataset=members, parameter=par)
+    n = len(par.phi)
+    stack = op.dataset
+    F = op.backward(stack.data)
+    R = op.RMTF()
+    rng = np.random.RandomState(9)
+    x = (rng.normal(size=(n, P)) + 1j * rng.normal(size=(n, P))) * (rng.uniform(size=(n, P)) < 0.03)
+    fw, fn = op.forward(x), op.forward_normalized(x)
+    assert F.shape == (n, P) and fw.shape == (nch, P)
+    for p, ds in enumerate(members):
+        o = ob.ExactDFT(ds.lambda2, par.phi, ds.w, ds.s, ds.k, ds.l2_ref)
+        assert rel(F[:, p], o.backward(np.asarray(ds.data))) < TOL_TRANSFORM
+        assert rel(R[:, p], o.rmtf()) < TOL_TRANSFORM
+        assert rel(fw[:ds.m, p], o.forward(x[:, p])) < TOL_TRANSFORM
+        good = np.asarray(ds.w) > 0
+        assert rel(fn[:ds.m, p][good], o.forward_normalized(x[:, p])[good]) < TOL_TRANSFORM
+        assert np.all(fw[ds.m:, p] == 0) and np.all(fn[:ds.m, p][~good] == 0)
+    for wav_name in (None, "coif2"):
+        for ds in members:
+            ds.model_data = np.zeros_like(ds.data)
+        lam0 = 40.0 * stack.theo_noise
+        noise = lam0 / (2.0 * K)
+        wav = cs.UndecimatedWavelet(wavelet_name=wav_name) if wav_name else None
+        guess = cs.Parameter(phi=par.phi, cellsize=par.cellsize)
+        guess.data = F
+        guess.complex_data_to_real()
+        if wav is not None:
+            guess.data = wav.decompose(guess.data)
+        chi2 = cs.Chi2(dft_obj=op, wavelet=wav)
+        l1 = cs.L1(reg=lam0)
+        step = 1.0 if wav is None else 1.0 / 2.8
+        cost, X = cs.FISTA(guess_param=guess, F_obj=cs.OFunction([chi2, l1]), fx=chi2, gx=cs.OFunction([l1]), noise=noise,
+                           maxiter=K, verbose=False, step=step).run()
+        for p, ds in enumerate(members):
+            o = ob.ExactDFT(ds.lambda2, par.phi, ds.w, ds.s, ds.k, ds.l2_ref)
+            start = ob.complex_to_real(o.backward(np.asarray(ds.data)))
+            owav = None
+            if wav is not None:
+                owav = ob.WaveletDict("coif2", kind="swt")
+                start = owav.decompose(start)
+            ref = ob.fista(o, np.asarray(ds.data), start, lam0[p], noise[p], K, wavelet=owav, step=step)
+            assert np.isfinite(ref["x"]).all()
+            good = np.asarray(ds.w) > 0
+            assert rel(np.asarray(X.data)[:, p], ref["x"]) < TOL_MODEL
+            assert rel(np.asarray(ds.model_data)[good], ref["model"][good]) < TOL_MODEL
+            assert rel(np.asarray(cost)[p], ref["cost"]) < TOL_MODEL
+
+
 def test_galactic_rm_derotation_on_device():
     from csromer_b200 import _device as dv
     src, par = make_batch(200, 90, seed=13)
