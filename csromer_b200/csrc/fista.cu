@@ -40,7 +40,8 @@ struct CoefUpdate {
     float* delta;
 };
 int swt_synth_fused(const csr_wavelet* w, const float* coef, int ld_coef, float* sig, int ld_sig, __half* hi,
-                    __half* lo, int ld_h, const float* scale, int P, cudaStream_t stream);
+                    __half* lo, int ld_h, const float* scale, int P, unsigned int* tile_flags, int flag_ld,
+                    cudaStream_t stream);
 int swt_analysis_fused(const csr_wavelet* w, const float* signal, int ld_sig, float* coef, int ld_coef, int P,
                        const CoefUpdate* update, cudaStream_t stream);
 int wavelet_decompose(const csr_wavelet* w, const float* signal, int ld_sig, float* coef, int ld_coef, int P,
@@ -239,6 +240,7 @@ extern "C" int csr_fista(csr_plan* plan, csr_wavelet* wav, const csr_fista_args*
     if (a.delta) CSR_CUDA(cudaMemsetAsync(a.delta, 0, sizeof(float) * P, stream));
 
     const bool fused_wavelet = wav && wavelet_fusable(wav) && options().fused_wavelet != 0;
+    const bool wav_kskip = fused_wavelet && k_skip && 2 * n <= kMaxSkipK;
 
     // 4. iterations
     double t = 1.0;
@@ -249,7 +251,13 @@ extern "C" int csr_fista(csr_plan* plan, csr_wavelet* wav, const csr_fista_args*
         const bool last = (it == a.iters - 1);
         if (wav && it > 0) {  // (iteration 0 reuses the split made above)
             if (fused_wavelet) {  // synthesis of all levels + operand split in one shared-memory-staged kernel
-                if ((rc = swt_synth_fused(wav, w.z, ldc, nullptr, 0, w.z_hi, w.z_lo, ld2n, w.zscale, P, stream))) return rc;
+                // the synthesis kernel records which (pixel tile, 128-column block)s of the operand hold non-zeros,
+                // so that the forward GEMM can skip the all-zero K blocks (exact)
+                if (wav_kskip)
+                    CSR_CUDA(cudaMemsetAsync(w.tile_flags, 0, sizeof(unsigned int) * (size_t)((P + BM - 1) / BM) * w.flag_ld, stream));
+                if ((rc = swt_synth_fused(wav, w.z, ldc, nullptr, 0, w.z_hi, w.z_lo, ld2n, w.zscale, P,
+                                          wav_kskip ? w.tile_flags : nullptr, w.flag_ld, stream)))
+                    return rc;
             } else {
                 if ((rc = wavelet_reconstruct(wav, w.z, ldc, w.sig, ld2n, P, w.wav_ws, stream))) return rc;
                 if ((rc = launch_split_rows(w.sig, ld2n, P, 2 * n, nullptr, 0, m, nullptr, 0, w.z_hi, w.z_lo, ld2n, w.zscale, 1, stream)))
@@ -266,7 +274,7 @@ extern "C" int csr_fista(csr_plan* plan, csr_wavelet* wav, const csr_fista_args*
             e.out_hi = w.r_hi;
             e.out_lo = w.r_lo;
             e.out_scale = w.rscale;
-            if (use_kskip) {
+            if (use_kskip || (wav_kskip && it > 0)) {
                 e.a_kflags = w.tile_flags;
                 e.a_kflag_ld = w.flag_ld;
             }

@@ -238,7 +238,8 @@ __device__ __forceinline__ void analysis_taps(const float* __restrict__ ap, int 
 __global__ void __launch_bounds__(WAV_THREADS)
 swt_synth_fused_kernel(const float* __restrict__ coef, int ld_coef, int N, int L, int H, int T, int B,
                        const BandOffsets bands, const FilterPair f, float* __restrict__ sig, int ld_sig,
-                       __half* __restrict__ hi, __half* __restrict__ lo, int ld_h, const float* __restrict__ scale) {
+                       __half* __restrict__ hi, __half* __restrict__ lo, int ld_h, const float* __restrict__ scale,
+                       unsigned char* __restrict__ tile_flags, int flag_ld) {
     extern __shared__ float wsm[];
     float* a = wsm;
     float* o = wsm + B;
@@ -294,6 +295,9 @@ swt_synth_fused_kernel(const float* __restrict__ coef, int ld_coef, int N, int L
             split_half(v * sc, h, l);
             hi[(size_t)p * ld_h + g] = h;
             lo[(size_t)p * ld_h + g] = l;
+            // forward GEMM K-block skipping (dft_gemm.cu): mark the (pixel tile, 128-column block) this non-zero
+            // operand value falls in; the caller zeroed the flags, untouched blocks are identically zero
+            if (tile_flags && v != 0.f) tile_flags[((size_t)(p >> 7) * flag_ld + (g >> 7)) * 4 + ((p >> 5) & 3)] = 1;
         }
     }
 }
@@ -424,7 +428,8 @@ bool profile_start(cudaStream_t stream, cudaEvent_t* start, cudaEvent_t* stop);
 void profile_stop(int kind, cudaStream_t stream, cudaEvent_t start, cudaEvent_t stop);
 
 int swt_synth_fused(const csr_wavelet* w, const float* coef, int ld_coef, float* sig, int ld_sig, __half* hi,
-                    __half* lo, int ld_h, const float* scale, int P, cudaStream_t stream) {
+                    __half* lo, int ld_h, const float* scale, int P, unsigned int* tile_flags, int flag_ld,
+                    cudaStream_t stream) {
     const FusedTiling t = fused_tiling(w, 3);
     const int smem = 3 * t.B * 4;
     static bool configured = false;
@@ -437,7 +442,7 @@ int swt_synth_fused(const csr_wavelet* w, const float* coef, int ld_coef, float*
     const bool prof = profile_start(stream, &ev0, &ev1);
     swt_synth_fused_kernel<<<dim3(P, t.ntiles), WAV_THREADS, smem, stream>>>(
         coef, ld_coef, w->N, w->levels, t.H, t.T, t.B, band_offsets(w), make_pair(w->rec_lo, w->rec_hi, w->F), sig, ld_sig,
-        hi, lo, ld_h, scale);
+        hi, lo, ld_h, scale, reinterpret_cast<unsigned char*>(tile_flags), flag_ld);
     CSR_LAUNCHED();
     if (prof) profile_stop(6, stream, ev0, ev1);
     return CSR_OK;
@@ -524,7 +529,7 @@ int wavelet_decompose(const csr_wavelet* w, const float* signal, int ld_sig, flo
 int wavelet_reconstruct(const csr_wavelet* w, const float* coef, int ld_coef, float* signal, int ld_sig, int P,
                         float* ws, cudaStream_t stream) {
     if (wavelet_fusable(w) && options().fused_wavelet != 0)
-        return swt_synth_fused(w, coef, ld_coef, signal, ld_sig, nullptr, nullptr, 0, nullptr, P, stream);
+        return swt_synth_fused(w, coef, ld_coef, signal, ld_sig, nullptr, nullptr, 0, nullptr, P, nullptr, 0, stream);
     const int N = w->N, L = w->levels;
     const int ldw = wavelet_ld(w);
     float* ping = ws;
