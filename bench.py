@@ -40,6 +40,17 @@ if ROOT not in sys.path:
 M_CH, N_PHI = 1000, 7968
 NU = (1.008e9, 2.031e9)
 SIGMA = 0.2 * 0.0035
+WORKLOAD = "c3"
+# --workload c4 (not the driver's line; results under profiles/): BASELINE.json configs[3] at slab scale -- 2000
+# channels (n = 15968), per-pixel weights sigma0 U(0.5, 2) per channel, 10-20 % of each pixel's channels flagged
+# (w = 0), per-pixel Galactic RM ~ N(0, 30) removed on the device inside the step (Dataset.subtract_galacticrm).
+WORKLOADS = {"c3": dict(m=1000, n=7968, slab=16384), "c4": dict(m=2000, n=15968, slab=8192)}
+
+
+def set_workload(name):
+    global M_CH, N_PHI, WORKLOAD
+    WORKLOAD = name
+    M_CH, N_PHI = WORKLOADS[name]["m"], WORKLOADS[name]["n"]
 
 
 def load_peaks():
@@ -124,17 +135,23 @@ def run_reference_arm(args):
 
 
 def ncu_traffic(P):
-    """DRAM bytes per GEMM launch from the committed `ncu --set full` capture (profiles/r1_traffic.json, taken at
-    16384 lines of sight per launch); None if the slab size differs or the file is missing."""
+    """DRAM bytes per launch of the dominant kernel (the screening adjoint GEMM) from the committed `ncu --set full`
+    capture (profiles/r1_traffic.json, taken at 16384 lines of sight per launch); None if the slab size differs or the
+    file is missing."""
     path = os.path.join(ROOT, "profiles", "r1_traffic.json")
-    if P != 16384 or not os.path.exists(path):
+    if P != 16384 or WORKLOAD != "c3" or not os.path.exists(path):
         return None
-    return json.load(open(path)).get("mean")
+    return json.load(open(path)).get("dominant_kernel_bytes")
 
 
 def workload_config(args):
-    return {"workload": "C3: 512x512 px x 1000 ch cube (JVLA 1.008-2.031 GHz), shared lambda^2, n_phi=7968, "
-                        "delta-basis L1 FISTA, exact DFT operator",
+    text = ("C3: 512x512 px x 1000 ch cube (JVLA 1.008-2.031 GHz), shared lambda^2, n_phi=7968, delta-basis L1 FISTA, "
+            "exact DFT operator")
+    if WORKLOAD == "c4":
+        text = ("C4: 1024x1024 px x 2000 ch cube (JVLA 1.008-2.031 GHz), n_phi=15968, per-pixel weights and 10-20 % "
+                "flagged channels per pixel, per-pixel Galactic RM removed on the device inside the step, delta-basis L1 "
+                "FISTA, exact DFT operator")
+    return {"workload": text,
             "fista_iterations": args.iters, "lambda0": "40*theo_noise", "noise": "lambda0/200",
             "los_per_step_per_gpu": args.slab, "transforms_per_los": 2 * args.iters + 2,
             "l2_policy": "inputs larger than L2 (state 2 GB per slab; steps alternate between two slabs)",
@@ -190,8 +207,26 @@ def make_slab(torch, src, P, seed, device):
     thick = torch.rand(P, generator=g, device=device) < 0.3
     fg = 50.0 + 150.0 * torch.rand(P, generator=g, device=device, dtype=torch.float64)
     data = data + thick * (0.0035 * s * torch.exp(2j * l2 * 200.0) * torch.sinc(fg * l2 / np.pi))
+    if WORKLOAD == "c4":
+        return data, g
     noise = torch.randn((2, src.m, P), generator=g, device=device, dtype=torch.float64) * SIGMA
     return (data + torch.complex(noise[0], noise[1])).to(torch.complex64)
+
+
+def make_slab_c4(torch, src, P, seed, device):
+    """C4 on top of the C3 sources: per-pixel sigma and flags, Galactic RM screen.  Returns (complex64 (m, P) data,
+    fp32 [P, m] weights, fp32 [P] phi_gal)."""
+    clean, g = make_slab(torch, src, P, seed, device)
+    m = src.m
+    sigma = SIGMA * (0.5 + 1.5 * torch.rand((m, P), generator=g, device=device, dtype=torch.float64))
+    frac = 0.1 + 0.1 * torch.rand((1, P), generator=g, device=device, dtype=torch.float64)
+    flagged = torch.rand((m, P), generator=g, device=device, dtype=torch.float64) < frac
+    noise = torch.randn((2, m, P), generator=g, device=device, dtype=torch.float64) * sigma
+    phi_gal = 30.0 * torch.randn(P, generator=g, device=device, dtype=torch.float64)
+    l2 = torch.as_tensor(np.ascontiguousarray(src.lambda2), dtype=torch.float64, device=device)[:, None]
+    data = (clean + torch.complex(noise[0], noise[1])) * torch.exp(2j * phi_gal * l2)
+    w = torch.where(flagged, torch.zeros_like(sigma), 1.0 / sigma ** 2)
+    return data.to(torch.complex64), w.t().contiguous().float(), phi_gal.float()
 
 
 def run_ours(args):
@@ -226,12 +261,23 @@ def run_ours(args):
     lam0 = 40.0 * src.theo_noise
     noise = lam0 / (2.0 * K)
 
-    slabs_c = [make_slab(torch, src, P, 1234 + 17 * rank + i, device) for i in range(2)]       # complex (m, P)
-    slabs_dev = [dv.pack_planar(c, plan.m, plan.ld2m, device)[0] for c in slabs_c]              # fp32 [P, 2m]
-    slabs_host = [c.cpu().pin_memory() for c in slabs_c]                                        # e2e inputs
-    del slabs_c
-    w = torch.as_tensor(src.w, dtype=torch.float32, device=device)
     s = torch.as_tensor(src.s, dtype=torch.float32, device=device)
+    if WORKLOAD == "c4":
+        made = [make_slab_c4(torch, src, P, 1235 + 17 * rank + i, device) for i in range(2)]
+        slabs_dev = [dv.pack_planar(c, plan.m, plan.ld2m, device)[0] for c, _, _ in made]
+        w_slabs, gal_slabs = [wt for _, wt, _ in made], [pg for _, _, pg in made]
+        slabs_host = None
+        del made
+        k_slabs = [(wt / s[None, :]).sum(dim=1) for wt in w_slabs]
+        lam_slabs = [40.0 / torch.sqrt(wt.sum(dim=1)) for wt in w_slabs]          # 40 theo_noise per pixel
+        noise_slabs = [lt / (2.0 * K) for lt in lam_slabs]
+        scratch = torch.empty_like(slabs_dev[0])
+    else:
+        slabs_c = [make_slab(torch, src, P, 1234 + 17 * rank + i, device) for i in range(2)]   # complex (m, P)
+        slabs_dev = [dv.pack_planar(c, plan.m, plan.ld2m, device)[0] for c in slabs_c]          # fp32 [P, 2m]
+        slabs_host = [c.cpu().pin_memory() for c in slabs_c]                                    # e2e inputs
+        del slabs_c
+    w = torch.as_tensor(src.w, dtype=torch.float32, device=device)
     k = torch.full((P,), float(src.k), dtype=torch.float32, device=device)
     lam_t = torch.full((P,), lam0, dtype=torch.float32, device=device)
     noise_t = torch.full((P,), noise, dtype=torch.float32, device=device)
@@ -244,8 +290,15 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     def device_step(i):
-        out = plan.fista(slabs_dev[i % 2], w, s, k, x, lam_t, noise_t, K, use_dirty_as_guess=True, want_delta=True,
-                         want_mma_blocks=True)
+        if WORKLOAD == "c4":
+            j = i % 2
+            scratch.copy_(slabs_dev[j])
+            plan.derotate(scratch, gal_slabs[j])        # Dataset.subtract_galacticrm (base/dataset.py:377-381)
+            out = plan.fista(scratch, w_slabs[j], s, k_slabs[j], x, lam_slabs[j], noise_slabs[j], K,
+                             use_dirty_as_guess=True, want_delta=True, want_mma_blocks=True)
+        else:
+            out = plan.fista(slabs_dev[i % 2], w, s, k, x, lam_t, noise_t, K, use_dirty_as_guess=True, want_delta=True,
+                             want_mma_blocks=True)
         # global convergence norm: the only collective on the path (mean |x_new - x_old| over all lines of sight)
         norm_buf[0] = out["delta"].sum()
         norm_buf[1] = float(P)
@@ -283,7 +336,7 @@ def run_ours(args):
     value = world * P * args.steps / (elapsed_ms * 1e-3)
 
     # ---- end to end through the public API with host buffers ----------------------------------------------
-    out_host = torch.empty((2 * N_PHI, P), dtype=torch.float32).pin_memory()
+    out_host = torch.empty((2 * N_PHI, P), dtype=torch.float32).pin_memory() if WORKLOAD == "c3" else None
 
     def e2e_step(i):
         ds = cs.Dataset(lambda2=src.lambda2, data=slabs_host[i % 2], sigma=src.sigma, spectral_idx=1.0)
@@ -302,16 +355,19 @@ def run_ours(args):
         return cost
 
     e2e_steps = max(1, min(args.steps, args.e2e_steps))
-    e2e_step(0)
-    barrier()
-    t0 = time.perf_counter()
-    for i in range(e2e_steps):
-        cost = e2e_step(i)
-    barrier()
-    e2e_wall = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=device)
-    if world > 1:
-        dist.all_reduce(e2e_wall, op=dist.ReduceOp.MAX)
-    e2e_value = world * P * e2e_steps / float(e2e_wall.item())
+    if WORKLOAD == "c3":
+        e2e_step(0)
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(e2e_steps):
+            cost = e2e_step(i)
+        barrier()
+        e2e_wall = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=device)
+        if world > 1:
+            dist.all_reduce(e2e_wall, op=dist.ReduceOp.MAX)
+        e2e_value = world * P * e2e_steps / float(e2e_wall.item())
+    else:  # the optional workloads report the device-resident rate only
+        e2e_value, cost = None, (out["cost"][:, 0] + lam_slabs[0] * 0.5 * out["cost"][:, 1]).cpu().numpy()
     h2d = P * M_CH * 8
     d2h = P * 2 * N_PHI * 4 + P * M_CH * 8 + P * 8
 
@@ -386,12 +442,16 @@ def main():
     ap.add_argument("--steps", type=int, default=4)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--slab", type=int, default=16384, help="lines of sight per step per GPU")
+    ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS), help="c3 = the driver's line (default)")
+    ap.add_argument("--slab", type=int, default=None, help="lines of sight per step per GPU (c3: 16384, c4: 8192)")
     ap.add_argument("--iters", type=int, default=100, help="FISTA iterations (fixed)")
     ap.add_argument("--cpu-iters", type=int, default=4, help="FISTA iterations in the bounded CPU sample")
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
+    set_workload(args.workload)
+    if args.slab is None:
+        args.slab = WORKLOADS[args.workload]["slab"]
     if args.impl == "reference":
         run_reference_arm(args)
     else:
