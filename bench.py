@@ -378,8 +378,8 @@ def run_ours(args):
     # blocks for the in-loop launches, 3 per tile and K block for the dense plain launches).
     flops_launch = 8.0 * M_CH * N_PHI * P
     names = ["plain_forward", "plain_adjoint", "resid_forward", "resid_adjoint", "fista_forward", "fista_adjoint",
-             "swt_synth_fused", "swt_analysis_update_fused", "screen_adjoint"]
-    gemm_kinds = [0, 1, 2, 3, 4, 5, 8]
+             "swt_synth_fused", "swt_analysis_update_fused", "screen_adjoint_fp16", "screen_adjoint_fp8"]
+    gemm_kinds = [0, 1, 2, 3, 4, 5, 8, 9]
     gemm_ms = float(sum(ms[0][i] for i in gemm_kinds))
     transforms = int(sum(ms[1][i] for i in (0, 1, 2, 3, 4, 5)))
     achieved = flops_launch * transforms / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
@@ -396,7 +396,7 @@ def run_ours(args):
     plain_blocks = 3.0 * (ms[1][0] * _tiles(2 * M_CH) * kb_fwd + ms[1][1] * _tiles(2 * N_PHI) * kb_adj)
     loop_blocks = float(out["mma_blocks"].item()) * args.steps   # every step issues the same work (two alike slabs)
     executed = (loop_blocks + plain_blocks) * block_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
-    adj_ms = float(ms[0][5] + ms[0][8])
+    adj_ms = float(ms[0][5] + ms[0][8] + ms[0][9])
     roofline = {"bound": "tensor", "kernel": "dft_gemm_kernel (forward + adjoint, fused epilogues; the adjoint = "
                 "one-product screening launch + three-product launch on the listed tiles)",
                 "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,

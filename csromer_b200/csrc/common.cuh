@@ -43,6 +43,10 @@ static inline size_t align256(size_t v) { return (v + 255) & ~size_t(255); }
 // scale applied to the twiddle tables before the fp16 hi/lo split (exact power of two, undone in epilogues)
 constexpr float kTwiddleScale = 4096.0f;
 constexpr float kTwiddleDescale = 1.0f / 4096.0f;
+// fp8 screening operands: twiddles * 2^8 (|.| <= 256), A operand = fp16-hi operand * 2 (|.| <= 448 or the row is
+// declared unscreenable); accumulator units are therefore 1/8 of the fp16 kernel's
+constexpr float kTwiddleScale8 = 256.0f;
+constexpr float kOperandScale8 = 2.0f;
 // operand rows are scaled so that their reference magnitude lands in (2^5, 2^6]; fp16 overflows at 2^16
 constexpr int kOperandTargetExp = 6;
 
@@ -151,6 +155,17 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64
         ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// same with fp8 (e4m3) inputs: kind::f8f6f4, K = 32 per instruction (the instruction descriptor has the same layout;
+// format code 0 means E4M3 here)
+__device__ __forceinline__ void umma_f8(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                        uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}\n"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
 // arrive on an mbarrier once every previously issued tcgen05.mma of this thread has completed
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
@@ -198,8 +213,9 @@ __host__ __device__ constexpr uint32_t umma_idesc_f16(int M, int N) {
 //   k_skip         forward GEMM skips K blocks whose A tile is identically zero
 //   fused_wavelet  undecimated transforms run as the fused shared-memory kernels
 //   screen         adjoint tiles whose state is zero are screened with one fp16 product before the full kernel
+//   screen8        ... and with an fp8 product before that
 struct Options {
-    int zero_skip, k_skip, fused_wavelet, screen;
+    int zero_skip, k_skip, fused_wavelet, screen, screen8;
 };
 Options& options();
 

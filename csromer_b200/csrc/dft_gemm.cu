@@ -26,6 +26,8 @@
 
 #include <vector>
 
+#include <cuda_fp8.h>
+
 #include "plan.cuh"
 
 namespace csr {
@@ -213,6 +215,12 @@ __device__ __forceinline__ void epilogue_tile(const GemmEpilogue& epi, const flo
                         *reinterpret_cast<__half2*>(epi.out_hi + row_off + col) = h;
                         *reinterpret_cast<__half2*>(epi.out_lo + row_off + col) = l;
                         dsum += fabsf(hf.x) + fabsf(hf.y);  // S_p of the screening bound
+                        if (epi.out8 != nullptr) {
+                            const float2 v8 = make_float2(hf.x * kOperandScale8, hf.y * kOperandScale8);
+                            if (fmaxf(fabsf(v8.x), fabsf(v8.y)) > 448.f) dsum = __int_as_float(0x7f800000);  // unscreenable row
+                            *reinterpret_cast<__nv_fp8x2_storage_t*>(epi.out8 + (size_t)row * epi.ld8 + col) =
+                                __nv_cvt_float2_to_fp8x2(v8, __NV_SATFINITE, __NV_E4M3);
+                        }
                     } else {  // EPI_FISTA: u = z - step*g ; x = soft(u, step*lambda) ; z = x + beta (x - x_old)
                         const float u0 = in0[jj].x - a0, u1 = in0[jj].y - a1;
                         const float x0 = copysignf(fmaxf(fabsf(u0) - thr, 0.f), u0);
@@ -276,8 +284,17 @@ __device__ __forceinline__ void epilogue_tile(const GemmEpilogue& epi, const flo
 // |A_lo| <= 2^-11 |A_hi|).  A tile passes when |g1| + kScreenSlack(K) S_p < lambda for all its elements: the full
 // kernel would have produced exact zeros there, so nothing is written.  Any other tile is appended to a list the
 // three-product FISTA kernel then processes.  Results are bit-identical to running the full kernel on every tile.
+//
+// A first, cheaper pass does the same with fp8 (e4m3) copies of both operands (A8 = rn(2 A_hi), B8 = rn(B_hi / 16),
+// accumulator units 1/8 of the fp16 ones): half the operand bytes and twice the tensor rate.  Its bound, in fp8
+// accumulator units:  sum_k |2 A_hi - A8| |B_hi / 16| + |A8| |B_hi / 16 - B8|
+//   <= sum_k (2^-4 2 |A_hi| + 2^-10) 256 + (2.125 |A_hi| + 2^-10) (16 + 2^-10)  <=  66.1 S_p + 0.27 K,
+// plus the fp16-level terms above (S_p in these units): slack 68 S_p + 0.3 K.  (A row whose 2 A_hi would exceed the
+// e4m3 range poisons its S_p with +inf and is never screened.)  Tiles that fail the fp8 test go to the fp16 test, tiles
+// that fail that one to the three-product kernel.
 __device__ __forceinline__ float screen_slack(int K) { return 8.f + (float)K * (1.f / 2048.f); }
 
+template <bool F8>
 __device__ __forceinline__ bool screen_tile_fails(const GemmEpilogue& epi, const float (&acc)[EPI_COLS], int lane, int row0,
                                                   int col0, int K) {
     const int quad = lane & 3;
@@ -293,7 +310,9 @@ __device__ __forceinline__ bool screen_tile_fails(const GemmEpilogue& epi, const
             const bool active = (nz < l0) && (epi.iter == 0 || lam > 0.f) && (!epi.iter_cap || epi.iter < __ldg(epi.iter_cap + row));
             if (!active) continue;  // a frozen row keeps its (zero) state whatever g is
             // accumulator units: g = acc * kTwiddleDescale / a_scale;  pass iff |acc| + slack * S_p < lambda / that factor
-            const float lim = lam * __ldg(epi.a_scale + row) * (1.f / kTwiddleDescale) - screen_slack(K) * __ldg(epi.abs_sum + row);
+            const float sp = __ldg(epi.abs_sum + row);
+            const float lim = F8 ? lam * __ldg(epi.a_scale + row) * (kTwiddleScale8 * kOperandScale8) - (68.f * sp + 0.3f * (float)K)
+                                 : lam * __ldg(epi.a_scale + row) * (1.f / kTwiddleDescale) - screen_slack(K) * sp;
             float mx = 0.f;
             bool bad = !(lim > 0.f);
 #pragma unroll
@@ -330,8 +349,11 @@ dft_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
     const int lane = threadIdx.x & 31;
     // tiles: all MT * NT of them, or the list a screening launch left behind
     const int total_tiles = epi.tile_list ? __ldcg(epi.tile_count) : MT * NT;
-    const int KB = (K + BK - 1) / BK;
-    constexpr int PRODUCTS = (MODE == EPI_SCREEN) ? 1 : 3;
+    constexpr bool IS_SCREEN = (MODE == EPI_SCREEN || MODE == EPI_SCREEN8);
+    constexpr bool F8 = (MODE == EPI_SCREEN8);
+    constexpr int BKE = F8 ? 2 * BK : BK;  // K elements per block = one 128-byte swizzle row
+    const int KB = (K + BKE - 1) / BKE;
+    constexpr int PRODUCTS = IS_SCREEN ? 1 : 3;
     int* last_listed = reinterpret_cast<int*>(smem + STAGES * STAGE_BYTES + 256 + NUM_WARPS_TOTAL * KMASK_WORDS * 4);
     uint32_t* my_mask = reinterpret_cast<uint32_t*>(smem + STAGES * STAGE_BYTES + 256) + warp * KMASK_WORDS;
     const bool skip = epi.a_kflags != nullptr;
@@ -383,14 +405,14 @@ dft_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
         {
             int stage = 0;
             uint32_t phase = 0;
-            bool quiet_next = (MODE == EPI_SCREEN && (int)blockIdx.x < total_tiles) ? tile_quiet(blockIdx.x) : true;
+            bool quiet_next = (IS_SCREEN && (int)blockIdx.x < total_tiles) ? tile_quiet(tile_id(blockIdx.x)) : true;
             for (int ti = blockIdx.x; ti < total_tiles; ti += gridDim.x) {
                 const int t = tile_id(ti);
                 int mt, nt;
                 tile_coords(t, MT, NT, mt, nt);
                 const bool quiet = quiet_next;  // (the next tile's state is fetched while this one streams)
-                if (MODE == EPI_SCREEN && ti + (int)gridDim.x < total_tiles) quiet_next = tile_quiet(ti + gridDim.x);
-                if (MODE == EPI_SCREEN && !quiet) continue;  // tile with signal: left to the three-product kernel
+                if (IS_SCREEN && ti + (int)gridDim.x < total_tiles) quiet_next = tile_quiet(tile_id(ti + gridDim.x));
+                if (IS_SCREEN && !quiet) continue;  // tile with signal: left to the three-product kernel
                 if (skip) build_kmask(epi.a_kflags + (size_t)mt * epi.a_kflag_ld, kwords, KB, my_mask, lane);
                 if (lane == 0) {
                     // Pull the fp32 tiles the fused epilogue of THIS tile will read (z and x_old, or b) into L2 shortly
@@ -406,10 +428,10 @@ dft_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
                         mbar_wait(&empty[stage], phase ^ 1);
                         uint8_t* sb = stage_base + stage * STAGE_BYTES;
                         mbar_arrive_expect_tx(&full[stage], PRODUCTS == 1 ? A_TILE_BYTES + B_TILE_BYTES : STAGE_BYTES);
-                        tma_load_2d(sb, &map_a_hi, &full[stage], kb * BK, mt * BM);
-                        if (PRODUCTS > 1) tma_load_2d(sb + A_TILE_BYTES, &map_a_lo, &full[stage], kb * BK, mt * BM);
-                        tma_load_2d(sb + 2 * A_TILE_BYTES, &map_b_hi, &full[stage], kb * BK, nt * BN);
-                        if (PRODUCTS > 1) tma_load_2d(sb + 2 * A_TILE_BYTES + B_TILE_BYTES, &map_b_lo, &full[stage], kb * BK, nt * BN);
+                        tma_load_2d(sb, &map_a_hi, &full[stage], kb * BKE, mt * BM);
+                        if (PRODUCTS > 1) tma_load_2d(sb + A_TILE_BYTES, &map_a_lo, &full[stage], kb * BKE, mt * BM);
+                        tma_load_2d(sb + 2 * A_TILE_BYTES, &map_b_hi, &full[stage], kb * BKE, nt * BN);
+                        if (PRODUCTS > 1) tma_load_2d(sb + 2 * A_TILE_BYTES + B_TILE_BYTES, &map_b_lo, &full[stage], kb * BKE, nt * BN);
                         if (++stage == STAGES) {
                             stage = 0;
                             phase ^= 1;
@@ -431,11 +453,11 @@ dft_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
             uint32_t phase = 0;
             uint32_t chunk = 0;  // running chunk counter -> TMEM buffer = chunk & 1, parity = (chunk >> 1) & 1
             unsigned long long issued = 0;  // K blocks x products (executed-work accounting)
-            bool quiet_next = (MODE == EPI_SCREEN && (int)blockIdx.x < total_tiles) ? tile_quiet(blockIdx.x) : true;
+            bool quiet_next = (IS_SCREEN && (int)blockIdx.x < total_tiles) ? tile_quiet(tile_id(blockIdx.x)) : true;
             for (int ti = blockIdx.x; ti < total_tiles; ti += gridDim.x) {
                 const bool quiet = quiet_next;
-                if (MODE == EPI_SCREEN && ti + (int)gridDim.x < total_tiles) quiet_next = tile_quiet(ti + gridDim.x);
-                if (MODE == EPI_SCREEN && !quiet) continue;
+                if (IS_SCREEN && ti + (int)gridDim.x < total_tiles) quiet_next = tile_quiet(tile_id(ti + gridDim.x));
+                if (IS_SCREEN && !quiet) continue;
                 if (skip) {
                     int mt, nt;
                     tile_coords(tile_id(ti), MT, NT, mt, nt);
@@ -464,13 +486,17 @@ dft_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
                             const uint64_t da_lo = umma_desc_sw128(sa_lo + k4 * 32);
                             const uint64_t db_hi = umma_desc_sw128(sb_hi + k4 * 32);
                             const uint64_t db_lo = umma_desc_sw128(sb_lo + k4 * 32);
-                            umma_f16(d_tmem, da_hi, db_hi, idesc, (in_chunk != 0 || k4 != 0) ? 1u : 0u);
+                            if (F8) {
+                                umma_f8(d_tmem, da_hi, db_hi, idesc, (in_chunk != 0 || k4 != 0) ? 1u : 0u);
+                            } else {
+                                umma_f16(d_tmem, da_hi, db_hi, idesc, (in_chunk != 0 || k4 != 0) ? 1u : 0u);
+                            }
                             if (PRODUCTS > 1) {
                                 umma_f16(d_tmem, da_lo, db_hi, idesc, 1u);
                                 umma_f16(d_tmem, da_hi, db_lo, idesc, 1u);
                             }
                         }
-                        issued += PRODUCTS;
+                        issued += F8 ? 2 : PRODUCTS;  // units of one 128 x 256 x 64 block
                         umma_commit(&empty[stage]);  // smem stage reusable once these MMAs have read it
                         if (++stage == STAGES) {
                             stage = 0;
@@ -503,7 +529,7 @@ dft_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
             const int t = tile_id(ti);
             int mt, nt;
             tile_coords(t, MT, NT, mt, nt);
-            if (MODE == EPI_SCREEN && !tile_quiet(t)) {  // hand the tile to the three-product kernel (one warp lists it)
+            if (IS_SCREEN && !tile_quiet(t)) {  // hand the tile on to the next kernel of the cascade (one warp lists it)
                 if (lane == 0 && atomicMax(last_listed, ti) < ti) epi.out_list[atomicAdd(epi.out_count, 1)] = t;
                 continue;
             }
@@ -521,8 +547,8 @@ dft_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&tmem_empty[buf]);
             }
-            if constexpr (MODE == EPI_SCREEN) {
-                const bool fail = screen_tile_fails(epi, acc, lane, mt * BM + sub * 32, nt * BN + half * EPI_COLS, K);
+            if constexpr (IS_SCREEN) {
+                const bool fail = screen_tile_fails<F8>(epi, acc, lane, mt * BM + sub * 32, nt * BN + half * EPI_COLS, K);
                 if (__any_sync(0xffffffffu, fail)) {
                     if (lane == 0 && atomicMax(last_listed, ti) < ti) epi.out_list[atomicAdd(epi.out_count, 1)] = t;
                 }
@@ -559,19 +585,20 @@ static EncodeTiledFn get_encode_fn() {
 
 // fp16 row-major [rows, cols] matrix with pitch ld -> 2-D map with a {64 x box_rows} box, 128B swizzle.
 // Out-of-bounds parts of a box (K tail, ragged last pixel tile) read as zero.
-int make_operand_map(CUtensorMap* map, const void* base, int rows, int cols, int ld, int box_rows) {
+int make_operand_map(CUtensorMap* map, const void* base, int rows, int cols, int ld, int box_rows, int elem_bytes) {
     EncodeTiledFn enc = get_encode_fn();
     if (!enc) {
         set_error("cuTensorMapEncodeTiled is not available from the CUDA driver");
         return CSR_ERR_CUDA;
     }
-    CSR_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0 && ld % 8 == 0,
-                "operand matrix must be 16-byte aligned with a pitch that is a multiple of 8 (ld=%d)", ld);
+    CSR_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0 && (ld * elem_bytes) % 16 == 0,
+                "operand matrix must be 16-byte aligned with a pitch that is a multiple of 16 bytes (ld=%d)", ld);
     cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-    cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
-    cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * elem_bytes};
+    cuuint32_t box[2] = {(cuuint32_t)(BK * 2 / elem_bytes), (cuuint32_t)box_rows};  // one 128-byte swizzle row of K
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+    CUresult r = enc(map, elem_bytes == 1 ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2,
+                     const_cast<void*>(base), dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
@@ -676,13 +703,14 @@ static int launch_mode(const csr_plan* plan, bool adjoint, const CUtensorMap& a_
     }
     ProfiledLaunch rec;
     if (g_profile) {
-        rec.kind = MODE == EPI_SCREEN ? 8 : MODE * 2 + (adjoint ? 1 : 0);
+        rec.kind = MODE == EPI_SCREEN ? 8 : (MODE == EPI_SCREEN8 ? 9 : MODE * 2 + (adjoint ? 1 : 0));
         CSR_CUDA(cudaEventCreate(&rec.start));
         CSR_CUDA(cudaEventCreate(&rec.stop));
         CSR_CUDA(cudaEventRecord(rec.start, stream));
     }
     dft_gemm_kernel<MODE><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(
-        a_hi, a_lo, adjoint ? plan->map_adj_hi : plan->map_fwd_hi, adjoint ? plan->map_adj_lo : plan->map_fwd_lo, pf0,
+        a_hi, a_lo, MODE == EPI_SCREEN8 ? plan->map_adj8 : (adjoint ? plan->map_adj_hi : plan->map_fwd_hi),
+        adjoint ? plan->map_adj_lo : plan->map_fwd_lo, pf0,
         pf1, num_prefetch, prefetch_lead, K, MT, NT, gemm_chunk_kb(adjoint), epi);
     CSR_LAUNCHED();
     if (g_profile) {
@@ -705,17 +733,26 @@ int launch_dft_gemm(const csr_plan* plan, bool adjoint, const __half* a_hi, cons
     epi.ld_out = adjoint ? plan->ld2n : plan->ld2m;
     epi.m = plan->m;
     CUtensorMap ma_hi, ma_lo;
-    int rc = make_operand_map(&ma_hi, a_hi, P, K, ldk, BM);
-    if (rc) return rc;
-    rc = make_operand_map(&ma_lo, a_lo, P, K, ldk, BM);
+    int rc;
+    if (epi.mode == EPI_SCREEN8) {  // a_hi is the fp8 copy of the operand (bytes, pitch ld8); there is no lo part
+        CSR_REQUIRE(adjoint, "fp8 screening exists for the adjoint only");
+        rc = make_operand_map(&ma_hi, a_hi, P, K, plan->ld8, BM, 1);
+        ma_lo = ma_hi;
+    } else {
+        rc = make_operand_map(&ma_hi, a_hi, P, K, ldk, BM);
+        if (rc) return rc;
+        rc = make_operand_map(&ma_lo, a_lo, P, K, ldk, BM);
+    }
     if (rc) return rc;
     switch (epi.mode) {
         case EPI_PLAIN: return launch_mode<EPI_PLAIN>(plan, adjoint, ma_hi, ma_lo, P, epi, stream);
         case EPI_RESID: return launch_mode<EPI_RESID>(plan, adjoint, ma_hi, ma_lo, P, epi, stream);
         case EPI_FISTA: return launch_mode<EPI_FISTA>(plan, adjoint, ma_hi, ma_lo, P, epi, stream);
         case EPI_SCREEN:
-            CSR_REQUIRE(adjoint && epi.abs_sum && epi.tile_state && epi.out_list && epi.out_count && !epi.tile_list,
+        case EPI_SCREEN8:
+            CSR_REQUIRE(adjoint && epi.abs_sum && epi.tile_state && epi.out_list && epi.out_count,
                         "screening launch: missing argument");
+            if (epi.mode == EPI_SCREEN8) return launch_mode<EPI_SCREEN8>(plan, adjoint, ma_hi, ma_lo, P, epi, stream);
             return launch_mode<EPI_SCREEN>(plan, adjoint, ma_hi, ma_lo, P, epi, stream);
     }
     set_error("unknown epilogue mode %d", epi.mode);
@@ -727,7 +764,7 @@ int launch_dft_gemm(const csr_plan* plan, bool adjoint, const __half* a_hi, cons
 using namespace csr;
 
 // kinds: 0 plain-forward, 1 plain-adjoint, 2 resid-forward, 3 resid-adjoint, 4 fista-forward, 5 fista-adjoint,
-//        6 fused wavelet synthesis, 7 fused wavelet analysis + update, 8 screening adjoint, 9 reserved
+//        6 fused wavelet synthesis, 7 fused wavelet analysis + update, 8 fp16 screening adjoint, 9 fp8 screening adjoint
 extern "C" int csr_profile(int enable) {
     g_profile = enable != 0;
     return CSR_OK;

@@ -85,6 +85,8 @@ struct FistaWs {
     // safe screening of the adjoint (delta basis): [0] = number of listed tiles, [8 ...) = S_p per line of sight
     float* screen_hdr;
     int* tile_list;
+    int* tile_list2;
+    unsigned char* r8;  // fp8 copy of the residual operand for the first screening pass
     unsigned long long* mma_count;  // [2]: K blocks x products issued by the in-loop GEMMs, and their dense total
     size_t bytes;
 };
@@ -109,6 +111,8 @@ static FistaWs carve_fista(const csr_plan* plan, const csr_wavelet* wav, int P, 
     f.tile_flags = b.take<unsigned int>((size_t)((P + BM - 1) / BM) * f.flag_ld);
     f.screen_hdr = b.take<float>((size_t)P + 8);
     f.tile_list = b.take<int>((size_t)((P + BM - 1) / BM) * ((2 * plan->n + BN - 1) / BN));
+    f.tile_list2 = b.take<int>((size_t)((P + BM - 1) / BM) * ((2 * plan->n + BN - 1) / BN));
+    f.r8 = b.take<unsigned char>((size_t)P * plan->ld8);
     f.mma_count = b.take<unsigned long long>(2);
     f.sig = f.gcoef = f.wav_ws = nullptr;
     if (wav) {
@@ -233,6 +237,7 @@ extern "C" int csr_fista(csr_plan* plan, csr_wavelet* wav, const csr_fista_args*
     const bool use_kskip = !wav && k_skip && 2 * n <= kMaxSkipK;
     // adjoint tiles whose state is zero are screened with one product first (exact); option screen = 0 turns it off
     const bool use_screen = !wav && zero_skip && options().screen != 0;
+    const bool use_screen8 = use_screen && options().screen8 != 0;  // fp8 pass in front of the fp16 one
     if (!wav && zero_skip) {
         if ((rc = launch_block_flags(w.z, ld2n, 2 * n, P, w.zero_flags, w.flag_ld, w.tile_flags, stream))) return rc;
     }
@@ -281,13 +286,17 @@ extern "C" int csr_fista(csr_plan* plan, csr_wavelet* wav, const csr_fista_args*
             if (use_screen) {
                 CSR_CUDA(cudaMemsetAsync(w.screen_hdr, 0, sizeof(float) * ((size_t)P + 8), stream));
                 e.abs_sum_out = w.screen_hdr + 8;
+                if (use_screen8) {
+                    e.out8 = w.r8;
+                    e.ld8 = plan->ld8;
+                }
             }
             e.mma_count = w.mma_count;
             if ((rc = launch_dft_gemm(plan, false, w.z_hi, w.z_lo, P, e, stream))) return rc;
         }
         if (!wav && use_screen) {
+            // cascade: fp8 screen over all tiles -> list 1 -> fp16 screen -> list 2 -> three-product FISTA kernel
             GemmEpilogue e = {};
-            e.mode = EPI_SCREEN;
             e.a_scale = w.rscale;
             e.lambda0 = a.lambda0;
             e.noise = a.noise;
@@ -296,9 +305,19 @@ extern "C" int csr_fista(csr_plan* plan, csr_wavelet* wav, const csr_fista_args*
             e.abs_sum = w.screen_hdr + 8;
             e.tile_state = w.tile_flags;
             e.flag_ld = w.flag_ld;
-            e.out_list = w.tile_list;
-            e.out_count = reinterpret_cast<int*>(w.screen_hdr);
             e.mma_count = w.mma_count;
+            int* counts = reinterpret_cast<int*>(w.screen_hdr);
+            if (use_screen8) {
+                e.mode = EPI_SCREEN8;
+                e.out_list = w.tile_list2;
+                e.out_count = counts + 1;
+                if ((rc = launch_dft_gemm(plan, true, reinterpret_cast<const __half*>(w.r8), nullptr, P, e, stream))) return rc;
+                e.tile_list = w.tile_list2;
+                e.tile_count = counts + 1;
+            }
+            e.mode = EPI_SCREEN;
+            e.out_list = w.tile_list;
+            e.out_count = counts;
             if ((rc = launch_dft_gemm(plan, true, w.r_hi, w.r_lo, P, e, stream))) return rc;
         }
         if (!wav) {

@@ -8,6 +8,8 @@
 #include <stdarg.h>
 #include <string.h>
 
+#include <cuda_fp8.h>
+
 #include "plan.cuh"
 
 namespace csr {
@@ -52,7 +54,8 @@ __global__ void twiddle_fwd_kernel(const double* __restrict__ lambda2, double l2
 
 // transposed orientation Tt[jj, c] (2n x 2m); i fastest -> coalesced writes.
 __global__ void twiddle_adj_kernel(const double* __restrict__ lambda2, double l2_ref, const double* __restrict__ phi,
-                                   int m, int n, int ld2m, __half* __restrict__ Tt_hi, __half* __restrict__ Tt_lo) {
+                                   int m, int n, int ld2m, __half* __restrict__ Tt_hi, __half* __restrict__ Tt_lo,
+                                   unsigned char* __restrict__ Tt8, int ld8) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int j = blockIdx.y;
     if (i >= m) return;
@@ -73,6 +76,15 @@ __global__ void twiddle_adj_kernel(const double* __restrict__ lambda2, double l2
     Tt_lo[r_im + i] = __hneg(sl);
     Tt_hi[r_im + m + i] = ch;       // Tt[n+j, m+i]   = T[m+i, n+j]   =  cos
     Tt_lo[r_im + m + i] = cl;
+    // e4m3 copy for the first screening pass (round to nearest, |value| <= 256)
+    const unsigned char c8 = __nv_cvt_float_to_fp8((float)(cs * (double)kTwiddleScale8), __NV_SATFINITE, __NV_E4M3);
+    const unsigned char s8 = __nv_cvt_float_to_fp8((float)(sn * (double)kTwiddleScale8), __NV_SATFINITE, __NV_E4M3);
+    const unsigned char ns8 = __nv_cvt_float_to_fp8((float)(-sn * (double)kTwiddleScale8), __NV_SATFINITE, __NV_E4M3);
+    const size_t q_re = (size_t)j * ld8, q_im = (size_t)(n + j) * ld8;
+    Tt8[q_re + i] = c8;
+    Tt8[q_re + m + i] = s8;
+    Tt8[q_im + i] = ns8;
+    Tt8[q_im + m + i] = c8;
 }
 
 }  // namespace csr
@@ -80,7 +92,8 @@ __global__ void twiddle_adj_kernel(const double* __restrict__ lambda2, double l2
 namespace csr {
 Options& options() {
     static Options o = {getenv("CSR_NO_ZERO_SKIP") == nullptr, getenv("CSR_NO_K_SKIP") == nullptr,
-                        getenv("CSR_NO_FUSED_WAVELET") == nullptr, getenv("CSR_NO_SCREEN") == nullptr};
+                        getenv("CSR_NO_FUSED_WAVELET") == nullptr, getenv("CSR_NO_SCREEN") == nullptr,
+                        getenv("CSR_NO_SCREEN8") == nullptr};
     return o;
 }
 }  // namespace csr
@@ -94,6 +107,7 @@ extern "C" int csr_set_option(const char* name, int value) {
     else if (!strcmp(name, "k_skip")) o.k_skip = value != 0;
     else if (!strcmp(name, "fused_wavelet")) o.fused_wavelet = value != 0;
     else if (!strcmp(name, "screen")) o.screen = value != 0;
+    else if (!strcmp(name, "screen8")) o.screen8 = value != 0;
     else {
         set_error("csr_set_option: unknown option '%s'", name);
         return CSR_ERR_ARG;
@@ -118,6 +132,7 @@ extern "C" void csr_plan_destroy(csr_plan* plan) {
     cudaFree(plan->T_lo);
     cudaFree(plan->Tt_hi);
     cudaFree(plan->Tt_lo);
+    cudaFree(plan->Tt8);
     delete plan;
 }
 
@@ -139,7 +154,9 @@ static int plan_build(csr_plan* p, const double* lambda2, const double* phi) {
     CSR_CUDA(cudaMalloc(&p->T_lo, fwd_elems * 2));
     CSR_CUDA(cudaMalloc(&p->Tt_hi, adj_elems * 2));
     CSR_CUDA(cudaMalloc(&p->Tt_lo, adj_elems * 2));
-    p->table_bytes = (fwd_elems + adj_elems) * 4;
+    CSR_CUDA(cudaMalloc(&p->Tt8, (size_t)2 * n * p->ld8));
+    CSR_CUDA(cudaMemset(p->Tt8, 0, (size_t)2 * n * p->ld8));
+    p->table_bytes = (fwd_elems + adj_elems) * 4 + (size_t)2 * n * p->ld8;
     CSR_CUDA(cudaMemset(p->T_hi, 0, fwd_elems * 2));
     CSR_CUDA(cudaMemset(p->T_lo, 0, fwd_elems * 2));
     CSR_CUDA(cudaMemset(p->Tt_hi, 0, adj_elems * 2));
@@ -151,7 +168,7 @@ static int plan_build(csr_plan* p, const double* lambda2, const double* phi) {
     }
     {
         dim3 grid((m + 255) / 256, n);
-        twiddle_adj_kernel<<<grid, 256>>>(p->d_l2, p->l2_ref, p->d_phi, m, n, p->ld2m, p->Tt_hi, p->Tt_lo);
+        twiddle_adj_kernel<<<grid, 256>>>(p->d_l2, p->l2_ref, p->d_phi, m, n, p->ld2m, p->Tt_hi, p->Tt_lo, p->Tt8, p->ld8);
         CSR_LAUNCHED();
     }
     CSR_CUDA(cudaDeviceSynchronize());
@@ -160,6 +177,7 @@ static int plan_build(csr_plan* p, const double* lambda2, const double* phi) {
     if ((rc = make_operand_map(&p->map_fwd_lo, p->T_lo, 2 * m, 2 * n, p->ld2n, BN))) return rc;
     if ((rc = make_operand_map(&p->map_adj_hi, p->Tt_hi, 2 * n, 2 * m, p->ld2m, BN))) return rc;
     if ((rc = make_operand_map(&p->map_adj_lo, p->Tt_lo, 2 * n, 2 * m, p->ld2m, BN))) return rc;
+    if ((rc = make_operand_map(&p->map_adj8, p->Tt8, 2 * n, 2 * m, p->ld8, BN, 1))) return rc;
     return CSR_OK;
 }
 
@@ -177,6 +195,7 @@ extern "C" int csr_plan_create(csr_plan** out, const double* lambda2, int m, dou
     p->n = n;
     p->ld2m = round_up(2 * m, 8);
     p->ld2n = round_up(2 * n, 8);
+    p->ld8 = round_up(2 * m, 16);
     p->l2_ref = l2_ref;
     int rc = plan_build(p, lambda2, phi);
     if (rc != CSR_OK) {

@@ -15,7 +15,10 @@ struct csr_plan {
     __half* T_lo;
     __half* Tt_hi;   // [2n rows, ld2m]  B operand of the adjoint GEMM  (N = 2n, K = 2m)
     __half* Tt_lo;
-    CUtensorMap map_fwd_hi, map_fwd_lo, map_adj_hi, map_adj_lo;
+    // fp8 (e4m3) copy of Tt scaled by kTwiddleScale8, used only by the first screening pass of the adjoint
+    unsigned char* Tt8;  // [2n rows, ld8]
+    int ld8;             // row pitch in bytes of every [*, 2m] fp8 matrix, multiple of 16
+    CUtensorMap map_fwd_hi, map_fwd_lo, map_adj_hi, map_adj_lo, map_adj8;
     size_t table_bytes;
 };
 
@@ -37,12 +40,13 @@ constexpr int BN = 256;  // output columns per tile (UMMA N)
 constexpr int BK = 64;   // fp16 elements per K block = one 128-byte swizzle row
 constexpr int kMaxSkipK = 32 * 32 * 128;  // longest K the K-block activity bitmask covers (dft_gemm.cu)
 
-enum EpilogueMode { EPI_PLAIN = 0, EPI_RESID = 1, EPI_FISTA = 2, EPI_SCREEN = 3 };
+enum EpilogueMode { EPI_PLAIN = 0, EPI_RESID = 1, EPI_FISTA = 2, EPI_SCREEN = 3, EPI_SCREEN8 = 4 };
 
 struct GemmEpilogue {
     // common
     int mode;
     int P, N, ld_out;          // valid rows / columns, output pitch
+    int ld8;                   // pitch of out8 (bytes)
     int m;                     // channels (column -> channel index = c mod m) for chan_scale / a
     const float* a_scale;      // [P] power-of-two scale the A operand rows were multiplied by
     // EPI_PLAIN: out = row_scale[p] * chan_scale[p?, c mod m] * y
@@ -74,6 +78,7 @@ struct GemmEpilogue {
     int a_kflag_ld;
     // Safe screening of the FISTA adjoint (exact, see dft_gemm.cu "screening"):
     float* abs_sum_out;             // EPI_RESID: [P] += sum_c |out_hi[p, c]| (atomicAdd; zeroed by the caller)
+    unsigned char* out8;            // EPI_RESID: optional fp8 e4m3 copy of out_hi * kOperandScale8, pitch ld8
     const float* abs_sum;           // EPI_SCREEN: [P] that sum for the rows of the A operand
     const unsigned int* tile_state; // EPI_SCREEN: [MT, flag_ld] tile_flags of the current x / z
     int* out_list;                  // EPI_SCREEN: tiles the full three-product kernel still has to process ...
@@ -84,7 +89,7 @@ struct GemmEpilogue {
     int debug;                 // measurement aid (CSR_DEBUG_EPI): bit 0 skips epilogue loads, bit 1 skips stores
 };
 
-int make_operand_map(CUtensorMap* map, const void* base, int rows, int cols, int ld, int box_rows);
+int make_operand_map(CUtensorMap* map, const void* base, int rows, int cols, int ld, int box_rows, int elem_bytes = 2);
 int launch_dft_gemm(const csr_plan* plan, bool adjoint, const __half* a_hi, const __half* a_lo, int P,
                     const GemmEpilogue& epi, cudaStream_t stream);
 

@@ -179,7 +179,8 @@ int csr_peak(const float* F, int ld, int n, int P, int* argmax, float* stats, vo
 /* per-launch timing of the transform GEMMs with CUDA events on the launching stream (measurement aid).
  * csr_profile(1) starts recording; csr_profile_collect sums elapsed ms and launch counts into CSR_PROFILE_KINDS-entry
  * arrays indexed [0 plain-forward, 1 plain-adjoint, 2 resid-forward, 3 resid-adjoint, 4 fista-forward,
- * 5 fista-adjoint, 6 fused wavelet synthesis, 7 fused wavelet analysis + update, 8 screening adjoint, 9 reserved]
+ * 5 fista-adjoint, 6 fused wavelet synthesis, 7 fused wavelet analysis + update, 8 fp16 screening adjoint,
+ * 9 fp8 screening adjoint]
  * and clears the record. */
 #define CSR_PROFILE_KINDS 10
 int csr_profile(int enable);
@@ -188,8 +189,8 @@ int csr_profile_collect(double* ms_by_kind, long long* count_by_kind);
 /* run-time switches of the exact shortcuts, all default 1 (measurement / test aid; results are bit-identical either
  * way): "zero_skip" (FISTA epilogue skips blocks that are and stay zero), "k_skip" (forward GEMM skips K blocks whose
  * A tile is identically zero), "screen" (adjoint tiles whose state is zero are first screened with one fp16 product
- * and a rigorous error bound; only tiles that may leave zero run the three-product kernel), "fused_wavelet" (fused
- * shared-memory undecimated transforms). */
+ * and a rigorous error bound; only tiles that may leave zero run the three-product kernel), "screen8" (an fp8 pass in
+ * front of that one), "fused_wavelet" (fused shared-memory undecimated transforms). */
 int csr_set_option(const char* name, int value);
 
 /* number of kernels launched by this library on the calling thread since the last reset (bench accounting) */
