@@ -32,7 +32,8 @@
 
 namespace csr {
 
-constexpr int STAGES = 2;
+constexpr int STAGES = 2;      // three-product modes: 2 stages of 96 KiB (A_hi, A_lo, B_hi, B_lo)
+constexpr int MAX_STAGES = 4;  // one-product (screening) modes: 4 stages of 48 KiB (A, B) in the same shared memory
 constexpr int A_TILE_BYTES = BM * BK * 2;  // 16 KiB
 constexpr int B_TILE_BYTES = BN * BK * 2;  // 32 KiB
 constexpr int STAGE_BYTES = 2 * A_TILE_BYTES + 2 * B_TILE_BYTES;  // A_hi, A_lo, B_hi, B_lo = 96 KiB
@@ -339,11 +340,11 @@ dft_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* stage_base = smem;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
-    uint64_t* full = bars;                     // [STAGES]  TMA -> MMA
-    uint64_t* empty = bars + STAGES;           // [STAGES]  MMA -> TMA
-    uint64_t* tmem_full = bars + 2 * STAGES;   // [2]       MMA -> epilogue (one K chunk accumulated)
-    uint64_t* tmem_empty = bars + 2 * STAGES + 2;  // [2]   epilogue -> MMA (chunk drained to registers)
-    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+    uint64_t* full = bars;                         // [NSTAGES]  TMA -> MMA
+    uint64_t* empty = bars + MAX_STAGES;           // [NSTAGES]  MMA -> TMA
+    uint64_t* tmem_full = bars + 2 * MAX_STAGES;   // [2]       MMA -> epilogue (one K chunk accumulated)
+    uint64_t* tmem_empty = bars + 2 * MAX_STAGES + 2;  // [2]   epilogue -> MMA (chunk drained to registers)
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * MAX_STAGES + 4);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -354,6 +355,11 @@ dft_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
     constexpr int BKE = F8 ? 2 * BK : BK;  // K elements per block = one 128-byte swizzle row
     const int KB = (K + BKE - 1) / BKE;
     constexpr int PRODUCTS = IS_SCREEN ? 1 : 3;
+    // a one-product stage is half the size, so the same shared memory holds a ring twice as deep -- which is what
+    // keeps enough bytes in flight to hide the L2 -> SM latency when a K block is only 4 MMAs long
+    constexpr int NSTAGES = IS_SCREEN ? MAX_STAGES : STAGES;
+    constexpr int STAGE_STRIDE = IS_SCREEN ? A_TILE_BYTES + B_TILE_BYTES : STAGE_BYTES;
+    constexpr int B_OFFSET = IS_SCREEN ? A_TILE_BYTES : 2 * A_TILE_BYTES;
     int* last_listed = reinterpret_cast<int*>(smem + STAGES * STAGE_BYTES + 256 + NUM_WARPS_TOTAL * KMASK_WORDS * 4);
     uint32_t* my_mask = reinterpret_cast<uint32_t*>(smem + STAGES * STAGE_BYTES + 256) + warp * KMASK_WORDS;
     const bool skip = epi.a_kflags != nullptr;
@@ -366,7 +372,7 @@ dft_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
         tma_prefetch_desc(&map_b_lo);
         if (num_prefetch > 0) tma_prefetch_desc(&map_pf0);
         if (num_prefetch > 1) tma_prefetch_desc(&map_pf1);
-        for (int s = 0; s < STAGES; ++s) {
+        for (int s = 0; s < NSTAGES; ++s) {
             mbar_init(&full[s], 1);
             mbar_init(&empty[s], 1);
         }
@@ -426,13 +432,13 @@ dft_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
                             if (num_prefetch > 1) tma_prefetch_2d(&map_pf1, nt * BN, mt * BM);
                         }
                         mbar_wait(&empty[stage], phase ^ 1);
-                        uint8_t* sb = stage_base + stage * STAGE_BYTES;
-                        mbar_arrive_expect_tx(&full[stage], PRODUCTS == 1 ? A_TILE_BYTES + B_TILE_BYTES : STAGE_BYTES);
+                        uint8_t* sb = stage_base + stage * STAGE_STRIDE;
+                        mbar_arrive_expect_tx(&full[stage], STAGE_STRIDE);
                         tma_load_2d(sb, &map_a_hi, &full[stage], kb * BKE, mt * BM);
                         if (PRODUCTS > 1) tma_load_2d(sb + A_TILE_BYTES, &map_a_lo, &full[stage], kb * BKE, mt * BM);
-                        tma_load_2d(sb + 2 * A_TILE_BYTES, &map_b_hi, &full[stage], kb * BKE, nt * BN);
-                        if (PRODUCTS > 1) tma_load_2d(sb + 2 * A_TILE_BYTES + B_TILE_BYTES, &map_b_lo, &full[stage], kb * BKE, nt * BN);
-                        if (++stage == STAGES) {
+                        tma_load_2d(sb + B_OFFSET, &map_b_hi, &full[stage], kb * BKE, nt * BN);
+                        if (PRODUCTS > 1) tma_load_2d(sb + B_OFFSET + B_TILE_BYTES, &map_b_lo, &full[stage], kb * BKE, nt * BN);
+                        if (++stage == NSTAGES) {
                             stage = 0;
                             phase ^= 1;
                         }
@@ -476,9 +482,9 @@ dft_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
                         }
                         mbar_wait(&full[stage], phase);
                         tc_fence_after();
-                        const uint32_t sa_hi = smem_u32(stage_base + stage * STAGE_BYTES);
+                        const uint32_t sa_hi = smem_u32(stage_base + stage * STAGE_STRIDE);
                         const uint32_t sa_lo = sa_hi + A_TILE_BYTES;
-                        const uint32_t sb_hi = sa_hi + 2 * A_TILE_BYTES;
+                        const uint32_t sb_hi = sa_hi + B_OFFSET;
                         const uint32_t sb_lo = sb_hi + B_TILE_BYTES;
 #pragma unroll
                         for (int k4 = 0; k4 < BK / 16; ++k4) {
@@ -498,7 +504,7 @@ dft_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
                         }
                         issued += F8 ? 2 : PRODUCTS;  // units of one 128 x 256 x 64 block
                         umma_commit(&empty[stage]);  // smem stage reusable once these MMAs have read it
-                        if (++stage == STAGES) {
+                        if (++stage == NSTAGES) {
                             stage = 0;
                             phase ^= 1;
                         }
@@ -632,11 +638,21 @@ struct ProfiledLaunch {
 };
 static bool g_profile = false;
 static std::vector<ProfiledLaunch> g_profiled;
+static std::vector<cudaEvent_t> g_event_pool;  // events are reused: creating two per launch costs host time
+
+static cudaError_t pooled_event(cudaEvent_t* ev) {
+    if (!g_event_pool.empty()) {
+        *ev = g_event_pool.back();
+        g_event_pool.pop_back();
+        return cudaSuccess;
+    }
+    return cudaEventCreate(ev);
+}
 
 // used by the wavelet launchers (kinds 6 = fused synthesis, 7 = fused analysis + update)
 bool profile_start(cudaStream_t stream, cudaEvent_t* start, cudaEvent_t* stop) {
     if (!g_profile) return false;
-    if (cudaEventCreate(start) != cudaSuccess || cudaEventCreate(stop) != cudaSuccess) return false;
+    if (pooled_event(start) != cudaSuccess || pooled_event(stop) != cudaSuccess) return false;
     cudaEventRecord(*start, stream);
     return true;
 }
@@ -704,19 +720,52 @@ static int launch_mode(const csr_plan* plan, bool adjoint, const CUtensorMap& a_
     ProfiledLaunch rec;
     if (g_profile) {
         rec.kind = MODE == EPI_SCREEN ? 8 : (MODE == EPI_SCREEN8 ? 9 : MODE * 2 + (adjoint ? 1 : 0));
-        CSR_CUDA(cudaEventCreate(&rec.start));
-        CSR_CUDA(cudaEventCreate(&rec.stop));
+        CSR_CUDA(pooled_event(&rec.start));
+        CSR_CUDA(pooled_event(&rec.stop));
         CSR_CUDA(cudaEventRecord(rec.start, stream));
     }
     dft_gemm_kernel<MODE><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(
         a_hi, a_lo, MODE == EPI_SCREEN8 ? plan->map_adj8 : (adjoint ? plan->map_adj_hi : plan->map_fwd_hi),
         adjoint ? plan->map_adj_lo : plan->map_fwd_lo, pf0,
-        pf1, num_prefetch, prefetch_lead, K, MT, NT, gemm_chunk_kb(adjoint), epi);
+        pf1, num_prefetch, prefetch_lead, K, MT, NT,
+        // screening needs no chunked accumulation: its bound covers the truncation of one long accumulation chain
+        (MODE == EPI_SCREEN || MODE == EPI_SCREEN8) ? (1 << 20) : gemm_chunk_kb(adjoint), epi);
     CSR_LAUNCHED();
     if (g_profile) {
         CSR_CUDA(cudaEventRecord(rec.stop, stream));
         g_profiled.push_back(rec);
     }
+    return CSR_OK;
+}
+
+// The A-operand maps of the FISTA loop are the same every iteration (workspace pointers, P, K, pitch): encoding them
+// costs several microseconds of host time per call, which matters once an iteration is ~1 ms of GPU time.  A map is a
+// pure function of these arguments, so a small per-thread cache is safe.
+static int cached_operand_map(CUtensorMap* map, const void* base, int rows, int cols, int ld, int elem_bytes) {
+    struct Entry {
+        const void* base;
+        int rows, cols, ld, eb;
+        CUtensorMap map;
+    };
+    static thread_local Entry cache[16];
+    static thread_local int next = 0;
+    for (int i = 0; i < 16; ++i) {
+        const Entry& e = cache[i];
+        if (e.base == base && e.rows == rows && e.cols == cols && e.ld == ld && e.eb == elem_bytes) {
+            *map = e.map;
+            return CSR_OK;
+        }
+    }
+    int rc = make_operand_map(map, base, rows, cols, ld, BM, elem_bytes);
+    if (rc) return rc;
+    Entry& e = cache[next];
+    next = (next + 1) % 16;
+    e.base = base;
+    e.rows = rows;
+    e.cols = cols;
+    e.ld = ld;
+    e.eb = elem_bytes;
+    e.map = *map;
     return CSR_OK;
 }
 
@@ -736,12 +785,12 @@ int launch_dft_gemm(const csr_plan* plan, bool adjoint, const __half* a_hi, cons
     int rc;
     if (epi.mode == EPI_SCREEN8) {  // a_hi is the fp8 copy of the operand (bytes, pitch ld8); there is no lo part
         CSR_REQUIRE(adjoint, "fp8 screening exists for the adjoint only");
-        rc = make_operand_map(&ma_hi, a_hi, P, K, plan->ld8, BM, 1);
+        rc = cached_operand_map(&ma_hi, a_hi, P, K, plan->ld8, 1);
         ma_lo = ma_hi;
     } else {
-        rc = make_operand_map(&ma_hi, a_hi, P, K, ldk, BM);
+        rc = cached_operand_map(&ma_hi, a_hi, P, K, ldk, 2);
         if (rc) return rc;
-        rc = make_operand_map(&ma_lo, a_lo, P, K, ldk, BM);
+        rc = cached_operand_map(&ma_lo, a_lo, P, K, ldk, 2);
     }
     if (rc) return rc;
     switch (epi.mode) {
@@ -782,8 +831,8 @@ extern "C" int csr_profile_collect(double* ms_by_kind, long long* count_by_kind)
         CSR_CUDA(cudaEventElapsedTime(&ms, r.start, r.stop));
         ms_by_kind[r.kind] += ms;
         count_by_kind[r.kind] += 1;
-        cudaEventDestroy(r.start);
-        cudaEventDestroy(r.stop);
+        g_event_pool.push_back(r.start);
+        g_event_pool.push_back(r.stop);
     }
     g_profiled.clear();
     return CSR_OK;
