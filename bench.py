@@ -300,8 +300,8 @@ def run_ours(args):
             out = plan.fista(slabs_dev[i % 2], w, s, k, x, lam_t, noise_t, K, use_dirty_as_guess=True, want_delta=True,
                              want_mma_blocks=True)
         # global convergence norm: the only collective on the path (mean |x_new - x_old| over all lines of sight)
-        norm_buf[0] = out["delta"].sum()
-        norm_buf[1] = float(P)
+        torch.sum(out["delta"], dim=0, out=norm_buf[0])
+        norm_buf[1].fill_(float(P))
         if world > 1:
             dist.all_reduce(norm_buf)
         return out

@@ -816,6 +816,13 @@ using namespace csr;
 //        6 fused wavelet synthesis, 7 fused wavelet analysis + update, 8 fp16 screening adjoint, 9 fp8 screening adjoint
 extern "C" int csr_profile(int enable) {
     g_profile = enable != 0;
+    if (g_profile) {  // create the events up front: cudaEventCreate inside a timed region is host time per launch
+        while (g_event_pool.size() < 8192) {
+            cudaEvent_t ev;
+            CSR_CUDA(cudaEventCreate(&ev));
+            g_event_pool.push_back(ev);
+        }
+    }
     return CSR_OK;
 }
 
