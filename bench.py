@@ -24,6 +24,7 @@ cpu_baseline: the oracle's NumPy port of the reference path (twiddles rebuilt wi
          ndft.py:19-34 does), one line of sight per host core like the README's joblib recipe, bounded sample.
 """
 import argparse
+import ctypes
 import json
 import os
 import subprocess
@@ -323,7 +324,6 @@ def run_ours(args):
     sampler.stop_flag = True
     launches = int(lib.csr_launch_count(0))
     ms = (np.zeros(10, dtype=np.float64), np.zeros(10, dtype=np.int64))
-    import ctypes
     lib.csr_profile(0)
     _lib.check(lib.csr_profile_collect(ms[0].ctypes.data_as(ctypes.POINTER(ctypes.c_double)),
                                        ms[1].ctypes.data_as(ctypes.POINTER(ctypes.c_longlong))), "csr_profile_collect")
@@ -371,48 +371,89 @@ def run_ours(args):
     h2d = P * M_CH * 8
     d2h = P * 2 * N_PHI * 4 + P * M_CH * 8 + P * 8
 
-    # ---- roofline of the dominant kernel ---------------------------------------------------------------------
-    # One transform = 8 m n algorithmic flops per line of sight.  A FISTA-adjoint transform is a screening launch
-    # (one fp16 product on tiles whose state is zero) plus a three-product launch on the tiles it lists; together they
-    # count as ONE transform.  `executed` is what the tensor cores really issued (in-kernel counter of 128x256x64
-    # blocks for the in-loop launches, 3 per tile and K block for the dense plain launches).
-    flops_launch = 8.0 * M_CH * N_PHI * P
+    # ---- dense reference leg: the same step with every exact shortcut switched off (bit-identical results) ------
+    def profiled(steps):
+        lib.csr_profile(1)
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0.record()
+        for i in range(steps):
+            o = device_step(i)
+        t1.record()
+        torch.cuda.synchronize()
+        lib.csr_profile(0)
+        pm = (np.zeros(10, dtype=np.float64), np.zeros(10, dtype=np.int64))
+        _lib.check(lib.csr_profile_collect(pm[0].ctypes.data_as(ctypes.POINTER(ctypes.c_double)),
+                                           pm[1].ctypes.data_as(ctypes.POINTER(ctypes.c_longlong))), "csr_profile_collect")
+        return t0.elapsed_time(t1), pm, o
+
+    flops_launch = 8.0 * M_CH * N_PHI * P        # one transform = 8 m n algorithmic flops per line of sight
+    peak = peaks["tf_sustained"]
+    dense = None
+    if not args.no_dense:
+        _lib.set_option("zero_skip", 0)
+        try:
+            device_step(0)
+            d_ms, d_pm, _ = profiled(1)
+        finally:
+            _lib.set_option("zero_skip", 1)
+        d_gemm_ms, d_n = float(d_pm[0][:6].sum()), int(d_pm[1][:6].sum())
+        d_ach = flops_launch * d_n / (d_gemm_ms * 1e-3) / 1e12
+        dense = {"what": "same step, exact shortcuts off (zero_skip=0): every transform is a dense three-product GEMM",
+                 "value": world * P / (d_ms * 1e-3), "unit": "LOS/s", "ms_per_step": d_ms,
+                 "gemm_launches": d_n, "gemm_avg_ms": d_gemm_ms / d_n, "achieved": d_ach, "frac": d_ach / peak,
+                 "executed_tflops": 3.0 * d_ach, "executed_frac": 3.0 * d_ach / peak,
+                 "note": "3 fp16 MMAs per algorithmic product (hi/lo split, fp32-class accuracy): frac <= 1/3"}
+        barrier()
+
+    # ---- roofline ------------------------------------------------------------------------------------------------
+    # A FISTA-adjoint transform is a cascade: fp8 screening launch over the tiles whose state is zero -> fp16
+    # screening of the tiles that fail it -> three-product launch on what is left; together ONE transform.
+    # `executed` is what the tensor cores really issued (in-kernel counters of 128 x 256 x 64 blocks).
     names = ["plain_forward", "plain_adjoint", "resid_forward", "resid_adjoint", "fista_forward", "fista_adjoint",
              "swt_synth_fused", "swt_analysis_update_fused", "screen_adjoint_fp16", "screen_adjoint_fp8"]
     gemm_kinds = [0, 1, 2, 3, 4, 5, 8, 9]
     gemm_ms = float(sum(ms[0][i] for i in gemm_kinds))
     transforms = int(sum(ms[1][i] for i in (0, 1, 2, 3, 4, 5)))
-    achieved = flops_launch * transforms / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
-    peak = peaks["tf_sustained"]
+    path_ach = flops_launch * transforms / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
     per_kind = {}
     for idx in gemm_kinds:
         if ms[1][idx]:
-            per_kind[names[idx]] = {"launches": int(ms[1][idx]), "avg_ms": float(ms[0][idx] / ms[1][idx])}
-    def _tiles(cols):
-        return ((P + 127) // 128) * ((cols + 255) // 256)
-    kb_fwd, kb_adj = (2 * N_PHI + 63) // 64, (2 * M_CH + 63) // 64
+            per_kind[names[idx]] = {"launches": int(ms[1][idx]), "avg_ms": float(ms[0][idx] / ms[1][idx]),
+                                    "share_of_step": float(ms[0][idx] / elapsed_ms)}
     block_flops = 2.0 * 128 * 256 * 64
-    dense_blocks_loop = args.steps * K * 3.0 * (_tiles(2 * M_CH) * kb_fwd + _tiles(2 * N_PHI) * kb_adj)
-    plain_blocks = 3.0 * (ms[1][0] * _tiles(2 * M_CH) * kb_fwd + ms[1][1] * _tiles(2 * N_PHI) * kb_adj)
-    loop_blocks = float(out["mma_blocks"].item()) * args.steps   # every step issues the same work (two alike slabs)
-    executed = (loop_blocks + plain_blocks) * block_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
+    blocks = out["mma_blocks"].double().cpu().numpy()          # per step: [three-product, fp16 screen, fp8 screen, -]
+    dominant = max(per_kind, key=lambda kname: per_kind[kname]["share_of_step"]) if per_kind else None
+    if dominant == "screen_adjoint_fp8":
+        k_ms = ms[0][9] / args.steps
+        k_tf = blocks[2] * block_flops / (k_ms * 1e-3) / 1e12
+        k_peak, k_src = 2.0 * peak, ("2 x MEASURED_PEAKS.json bf16_tflops_sustained (%s): no fp8 figure is measured on this "
+                                     "pool; nominal fp8 dense = 2 x bf16" % peaks["source"])
+        k_name = "dft_gemm_kernel<EPI_SCREEN8>: fp8 (e4m3) screening pass of the adjoint transform, tcgen05 kind::f8f6f4"
+        k_note = ("achieved = fp8 flops the kernel issued (in-kernel counter) / its CUDA-event time; it is L2->SM "
+                  "operand-fabric bound (48 KB of operands per 128x256x128 block: profiles/r1_screen8_gemm_metrics.json, "
+                  "6.9 GB per launch = 12.4 TB/s), not tensor bound")
+    else:  # dense regime: the three-product kernels dominate
+        k_ms = float(sum(ms[0][i] for i in (0, 1, 2, 3, 4, 5))) / args.steps
+        k_tf = (blocks[0] + 3.0 * (ms[1][0] * ((P + 127) // 128) * ((2 * M_CH + 255) // 256) * ((2 * N_PHI + 63) // 64)
+                                   + ms[1][1] * ((P + 127) // 128) * ((2 * N_PHI + 255) // 256) * ((2 * M_CH + 63) // 64))
+                / args.steps) * block_flops / (k_ms * 1e-3) / 1e12
+        k_peak, k_src = peak, "MEASURED_PEAKS.json bf16_tflops_sustained (%s)" % peaks["source"]
+        k_name = "dft_gemm_kernel (three fp16 products per algorithmic product)"
+        k_note = "achieved = fp16 flops issued / CUDA-event time"
     adj_ms = float(ms[0][5] + ms[0][8] + ms[0][9])
-    roofline = {"bound": "tensor", "kernel": "dft_gemm_kernel (forward + adjoint, fused epilogues; the adjoint = "
-                "one-product screening launch + three-product launch on the listed tiles)",
-                "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                "traffic": ncu_traffic(P),
-                "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (%s)" % peaks["source"],
-                "executed_tflops": executed, "executed_frac": executed / peak,
-                "executed_share_of_dense": loop_blocks / dense_blocks_loop if dense_blocks_loop else None,
-                "note": "fp32-class accuracy costs 3 fp16 MMAs per algorithmic product, so a DENSE run is bounded by "
-                        "frac <= 1/3; exact sparsity shortcuts (K-block skipping in the forward transform, safe "
-                        "screening in the adjoint; bit-identical results, tests/test_gpu_parity.py) let the algorithmic "
-                        "rate exceed that. executed_* counts the MMAs really issued. CSR_NO_ZERO_SKIP=1 gives the "
-                        "dense run.",
-                "gemm_share_of_step": gemm_ms / elapsed_ms if elapsed_ms > 0 else None,
-                "adjoint_transform_ms": adj_ms / ms[1][5] if ms[1][5] else None,
-                "adjoint_algorithmic_tflops": flops_launch * ms[1][5] / (adj_ms * 1e-3) / 1e12 if adj_ms > 0 else None,
-                "per_kind": per_kind}
+    roofline = {"bound": "tensor", "kernel": k_name, "achieved": k_tf, "peak": k_peak, "unit": "TFLOP/s",
+                "frac": k_tf / k_peak if k_peak else None, "traffic": ncu_traffic(P), "peak_source": k_src, "note": k_note,
+                "kernel_share_of_step": per_kind[dominant]["share_of_step"] if dominant else None,
+                "path": {"what": "all transform GEMM launches of the step: algorithmic 8 m n flops per line of sight per "
+                                 "transform / their summed CUDA-event time. Exact sparsity shortcuts (forward K-block "
+                                 "skipping, fp8 -> fp16 safe screening of the adjoint; bit-identical results, "
+                                 "tests/test_gpu_parity.py::test_sparsity_shortcuts_are_bit_exact) let this exceed the "
+                                 "dense bound of 1/3 of the tensor peak",
+                         "algorithmic_tflops": path_ach, "frac_of_bf16_peak": path_ach / peak,
+                         "gemm_share_of_step": gemm_ms / elapsed_ms if elapsed_ms > 0 else None,
+                         "adjoint_transform_ms": adj_ms / ms[1][5] if ms[1][5] else None,
+                         "executed_blocks_per_step": {"three_product": blocks[0], "fp16_screen": blocks[1], "fp8_screen": blocks[2]}},
+                "dense": dense, "per_kind": per_kind}
 
     if rank == 0:
         cpu = None
@@ -448,6 +489,7 @@ def main():
     ap.add_argument("--cpu-iters", type=int, default=4, help="FISTA iterations in the bounded CPU sample")
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-dense", action="store_true", help="skip the dense reference leg of the roofline")
     args = ap.parse_args()
     set_workload(args.workload)
     if args.slab is None:

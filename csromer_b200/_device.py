@@ -190,7 +190,8 @@ class DevicePlan:
               want_mma_blocks=False):
         """Run the fused loop.  All tensors are fp32 on the device; ``x`` ([P, ldx]) is updated in place.
         Returns dict(f_dirty, model, residual, cost[P,2], delta[, mma_blocks]).  ``mma_blocks`` (measurement aid) is the
-        number of 128 x 256 x 64 tensor-core blocks the in-loop GEMMs issued (3 per tile and K block when dense)."""
+        number of 128 x 256 x 64 tensor-core blocks the in-loop GEMMs issued, by kind: [three-product, fp16 screening,
+        fp8 screening, unused] (3 per tile and K block when dense)."""
         P = data.shape[0]
         dev = self.device
         out = dict(f_dirty=None, model=None, residual=None, cost=None, delta=None)
@@ -203,7 +204,7 @@ class DevicePlan:
         if want_delta:
             out["delta"] = torch.zeros((P,), dtype=torch.float32, device=dev)
         if want_mma_blocks:
-            out["mma_blocks"] = torch.zeros((1,), dtype=torch.int64, device=dev)
+            out["mma_blocks"] = torch.zeros((4,), dtype=torch.int64, device=dev)
         whandle = wavelet.handle if wavelet is not None else None
         need = self.lib.csr_fista_ws_bytes(self.handle, whandle, P)
         ws = self.ws.get(need, dev)

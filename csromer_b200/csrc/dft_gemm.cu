@@ -521,7 +521,9 @@ dft_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
                 }
                 chunk = __shfl_sync(0xffffffffu, chunk, 0);
             }
-            if (lane == 0 && epi.mma_count != nullptr && issued != 0) atomicAdd(epi.mma_count, issued);
+            // slot 0: three-product launches, 1: fp16 screening, 2: fp8 screening
+            if (lane == 0 && epi.mma_count != nullptr && issued != 0)
+                atomicAdd(epi.mma_count + (MODE == EPI_SCREEN ? 1 : (MODE == EPI_SCREEN8 ? 2 : 0)), issued);
         }
       }
     } else {

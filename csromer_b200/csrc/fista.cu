@@ -87,7 +87,7 @@ struct FistaWs {
     int* tile_list;
     int* tile_list2;
     unsigned char* r8;  // fp8 copy of the residual operand for the first screening pass
-    unsigned long long* mma_count;  // [2]: K blocks x products issued by the in-loop GEMMs, and their dense total
+    unsigned long long* mma_count;  // [4]: tensor-core blocks issued by the in-loop GEMMs (3-product, fp16 screen, fp8 screen)
     size_t bytes;
 };
 static FistaWs carve_fista(const csr_plan* plan, const csr_wavelet* wav, int P, void* ws) {
@@ -113,7 +113,7 @@ static FistaWs carve_fista(const csr_plan* plan, const csr_wavelet* wav, int P, 
     f.tile_list = b.take<int>((size_t)((P + BM - 1) / BM) * ((2 * plan->n + BN - 1) / BN));
     f.tile_list2 = b.take<int>((size_t)((P + BM - 1) / BM) * ((2 * plan->n + BN - 1) / BN));
     f.r8 = b.take<unsigned char>((size_t)P * plan->ld8);
-    f.mma_count = b.take<unsigned long long>(2);
+    f.mma_count = b.take<unsigned long long>(4);
     f.sig = f.gcoef = f.wav_ws = nullptr;
     if (wav) {
         f.sig = b.take<float>((size_t)P * plan->ld2n);
@@ -241,7 +241,7 @@ extern "C" int csr_fista(csr_plan* plan, csr_wavelet* wav, const csr_fista_args*
     if (!wav && zero_skip) {
         if ((rc = launch_block_flags(w.z, ld2n, 2 * n, P, w.zero_flags, w.flag_ld, w.tile_flags, stream))) return rc;
     }
-    CSR_CUDA(cudaMemsetAsync(w.mma_count, 0, 2 * sizeof(unsigned long long), stream));
+    CSR_CUDA(cudaMemsetAsync(w.mma_count, 0, 4 * sizeof(unsigned long long), stream));
     if (a.delta) CSR_CUDA(cudaMemsetAsync(a.delta, 0, sizeof(float) * P, stream));
 
     const bool fused_wavelet = wav && wavelet_fusable(wav) && options().fused_wavelet != 0;
@@ -366,7 +366,7 @@ extern "C" int csr_fista(csr_plan* plan, csr_wavelet* wav, const csr_fista_args*
         if ((rc = launch_scale_vec(a.delta, P, 1.0f / (float)ncoef, stream))) return rc;
     }
     if (a.mma_blocks) {  // executed-work accounting of the in-loop GEMMs (a measurement aid, two 64-bit counters)
-        CSR_CUDA(cudaMemcpyAsync(a.mma_blocks, w.mma_count, sizeof(unsigned long long), cudaMemcpyDeviceToDevice, stream));
+        CSR_CUDA(cudaMemcpyAsync(a.mma_blocks, w.mma_count, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToDevice, stream));
     }
 
     // 5. final evaluate F(x): model_data, residual, chi2 and L1 values (fista.py:107; chi2.py:21-32)
