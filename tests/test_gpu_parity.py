@@ -245,21 +245,25 @@ def test_sparsity_shortcuts_are_bit_exact(nch, P, K, kw):
 
 def test_wavelet_forward_k_skipping_is_bit_exact():
     """undecimated basis: the fused synthesis kernel flags the non-zero operand blocks and the forward GEMM skips the
-    rest -- same bits as the dense K loop"""
+    rest; coefficient-state flags let the update kernel skip state traffic of blocks that are and stay zero -- same
+    bits as the dense loops"""
     from csromer_b200 import _lib
     src, par = make_batch(300, 200, seed=77, mixed=True)
     results = []
     try:
-        for k_skip in (1, 0):
+        for k_skip, zero_skip in ((1, 1), (0, 1), (0, 0)):
             _lib.set_option("k_skip", k_skip)
+            _lib.set_option("zero_skip", zero_skip)
             wav = cs.UndecimatedWavelet(wavelet_name="coif2")
             cost, X, l1, lam0, noise = run_fista(src, par, 25, wav=wav, step=1.0 / 2.8)
             results.append((np.array(X.data, copy=True), np.array(cost, copy=True), np.array(src.model_data, copy=True)))
     finally:
         _lib.set_option("k_skip", 1)
+        _lib.set_option("zero_skip", 1)
     assert 0 < np.count_nonzero(results[0][0]) < 0.2 * results[0][0].size
-    for a, b in zip(*results):
-        np.testing.assert_array_equal(a, b)
+    for other in results[1:]:
+        for a, b in zip(results[0], other):
+            np.testing.assert_array_equal(a, b)
 
 
 def test_fista_zero_start_and_step_extension():
