@@ -12,11 +12,15 @@ from .objectivefunction import L1, Chi2, Fi, OFunction
 from .optimization import FISTA, Optimizer
 from .reconstruction import Parameter
 from .simulation import FaradaySource, FaradayThickSource, FaradayThinSource
-from .transformers import DFT1D, FT, NDFT1D, NUFFT1D, DatasetStack, PerPixelDFT1D
+from .io import DeviceCube, Reader, Writer, filter_cubes
+from .transformers import (DFT1D, FT, NDFT1D, NUFFT1D, DatasetStack, Flagger, HampelFlagger, ManualFlagger, MeanFlagger,
+                           PerPixelDFT1D)
+from .utils import calculate_noise
 
 __version__ = "0.1.0"
 __all__ = [
     "Dataset", "Parameter", "FT", "NDFT1D", "DFT1D", "NUFFT1D", "PerPixelDFT1D", "DatasetStack", "Wavelet", "DiscreteWavelet", "UndecimatedWavelet",
     "Fi", "Chi2", "L1", "OFunction", "Optimizer", "FISTA", "FaradaySource", "FaradayThinSource",
-    "FaradayThickSource", "reconstruct_cube", "estimate_lipschitz",
+    "FaradayThickSource", "reconstruct_cube", "estimate_lipschitz", "Flagger", "MeanFlagger", "HampelFlagger",
+    "ManualFlagger", "Reader", "Writer", "filter_cubes", "DeviceCube", "calculate_noise",
 ]

@@ -177,6 +177,21 @@ int csr_convolve_phi(const float* x, int ld, int n, int P, const float* taps_hos
                      float* out, void* stream);
 int csr_peak(const float* F, int ld, int n, int P, int* argmax, float* stats, void* stream);
 
+/* ---- cube layouts either side of the path ----------------------------------------
+ * csr_pack_slab    : Stokes Q, U planes [m, npix] (frequency first: README.md:288-297, io/io_functions.py:58-84) ->
+ *                    data [P, ld_out] planar rows of pixels p0 .. p0+P-1; non-finite samples become 0 and are reported
+ *                    in valid[P, m] (optional; 1 = finite) for the per-pixel weights
+ * csr_unpack_slab  : F [P, ld] planar -> re, im [n, npix] columns p0 .. p0+P-1, the (2, n_phi, Y, X) layout of
+ *                    io/io_functions.py:151-203
+ * csr_channel_stats: stats[m, 2] = {nansum, nanstd} of every channel image [Y, X] over the window [y0,yn) x [x0,xn):
+ *                    utils/utilities.py:68-110 (calculate_noise, no sigma clipping); io_functions.py:15-33 drops the
+ *                    channels whose nansum is 0 */
+int csr_pack_slab(const float* q, const float* u, long long npix, int m, long long p0, int P, float* out, int ld_out,
+                  unsigned char* valid, void* stream);
+int csr_unpack_slab(const float* in, int ld, int n, long long npix, long long p0, int P, float* re, float* im,
+                    void* stream);
+int csr_channel_stats(const float* img, int m, int Y, int X, int x0, int xn, int y0, int yn, float* stats, void* stream);
+
 /* per-launch timing of the transform GEMMs with CUDA events on the launching stream (measurement aid).
  * csr_profile(1) starts recording; csr_profile_collect sums elapsed ms and launch counts into CSR_PROFILE_KINDS-entry
  * arrays indexed [0 plain-forward, 1 plain-adjoint, 2 resid-forward, 3 resid-adjoint, 4 fista-forward,

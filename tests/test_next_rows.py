@@ -1,0 +1,163 @@
+"""Rows next to the hot path: flaggers, calculate_noise, filter_cubes, cube I/O layouts.
+
+CPU part: this package's host mirrors against tests/golden/next_rows.npz, frozen from the reference's own classes by
+oracle/make_golden_next.py; the FITS codec against the standard's layout and a round trip.
+GPU part: the cube transposes and channel statistics of csrc/cubeio.cu against NumPy on the same inputs (bit exact for
+the transposes, 1e-6 relative for the fp64-accumulated statistics)."""
+import os
+
+import numpy as np
+import pytest
+from conftest import golden
+
+import csromer_b200 as cs
+from csromer_b200.io import fits_lite
+from csromer_b200.transformers.flaggers import hampel, median_absolute_deviation
+
+
+@pytest.fixture(scope="module")
+def g():
+    return golden("next_rows")
+
+
+def fresh(g):
+    return cs.Dataset(nu=g["nu"], sigma=g["sigma"].copy(), data=g["data"].copy(), spectral_idx=0.7)
+
+
+@pytest.mark.parametrize("tag,nsigma,delete", [("mean_ns0_w", 0.0, False), ("mean_ns5_w", 5.0, False), ("mean_ns5_del", 5.0, True)])
+def test_mean_flagger_matches_reference(g, tag, nsigma, delete, capsys):
+    ds = fresh(g)
+    idxs, outliers = cs.MeanFlagger(dataset=ds, nsigma=nsigma, delete_channels=delete).run()
+    np.testing.assert_array_equal(idxs, g[tag + "_idxs"])
+    np.testing.assert_array_equal(outliers, g[tag + "_outliers"])
+    np.testing.assert_array_equal(ds.w, g[tag + "_w"])
+    np.testing.assert_array_equal(ds.lambda2, g[tag + "_lambda2"])
+    np.testing.assert_allclose(ds.sigma, g[tag + "_sigma"], rtol=1e-14)
+    np.testing.assert_array_equal(ds.data, g[tag + "_data"])
+    assert ds.k == pytest.approx(float(g[tag + "_k"]), rel=1e-14)
+    assert "Flagging" in capsys.readouterr().out
+
+
+def test_hampel_and_manual_flaggers_match_reference(g):
+    keep, outliers = hampel(g["sigma"], 9, 3.0, False)
+    np.testing.assert_array_equal(keep, g["hampel_keep"])
+    np.testing.assert_array_equal(outliers, g["hampel_outliers"])
+    imputed, _, _ = hampel(g["sigma"], 9, 3.0, True)
+    np.testing.assert_allclose(imputed, g["hampel_imputed"], rtol=1e-15)
+    assert median_absolute_deviation(g["sigma"]) == pytest.approx(float(g["mad"]), rel=1e-15)
+    # the class (the reference's run() cannot execute: it passes dataset.w as the window)
+    ds = fresh(g)
+    k_before = ds.k
+    keep2, out2 = cs.HampelFlagger(dataset=ds, nsigma=3.0, w=9).run()
+    np.testing.assert_array_equal(out2, g["hampel_outliers"])
+    assert np.all(ds.w[out2] == 0) and ds.k == k_before          # in-place flagging leaves k stale, like the reference
+    ds = fresh(g)
+    idxs, _ = cs.ManualFlagger(dataset=ds, delete_channels=True, outlier_idxs=[3, 4, 50]).run()
+    np.testing.assert_array_equal(idxs, g["manual_idxs"])
+    np.testing.assert_array_equal(ds.lambda2, g["manual_lambda2"])
+    np.testing.assert_allclose(ds.sigma, g["manual_sigma"], rtol=1e-14)
+    np.testing.assert_array_equal(ds.data, g["manual_data"])
+
+
+def test_per_pixel_mean_flagging_extension():
+    rng = np.random.RandomState(0)
+    m, P = 50, 7
+    sigma = 1e-3 * (1 + 0.1 * rng.uniform(size=(m, P)))
+    sigma[5, 2] *= 10
+    sigma[9, 6] *= 10
+    ds = cs.Dataset(nu=np.linspace(1e9, 2e9, m), sigma=sigma, data=np.zeros((m, P), np.complex64))
+    keep, mask = cs.MeanFlagger(dataset=ds, nsigma=5.0).run()
+    assert mask.shape == (m, P) and mask[5, 2] and mask[9, 6]
+    from csromer_b200.transformers.flaggers import normal_flagging
+    for p in range(P):          # every pixel gets exactly the single-line-of-sight decision
+        _, outl = normal_flagging(sigma[:, p], None, 5.0)
+        np.testing.assert_array_equal(np.where(mask[:, p])[0], outl)
+    np.testing.assert_array_equal(ds.w == 0, mask)
+    with pytest.raises(ValueError):
+        cs.MeanFlagger(dataset=ds, nsigma=5.0, delete_channels=True).run()
+
+
+def test_calculate_noise_and_filter_cubes_match_reference(g):
+    cube = g["cube"]
+    np.testing.assert_allclose(cs.calculate_noise(image=cube), g["noise_full"], rtol=1e-6)
+    np.testing.assert_allclose(cs.calculate_noise(image=cube, x0=2, xn=20, y0=1, yn=15), g["noise_window"], rtol=1e-6)
+    assert cs.calculate_noise(image=cube[1]) == pytest.approx(float(g["noise_image"]), rel=1e-6)
+    with pytest.raises(NotImplementedError):
+        cs.calculate_noise(image=cube, use_sigma_clipped_stats=True)
+    header = {"CRVAL3": 1.0e9, "NAXIS3": 6, "CDELT3": 1.0e6}
+    _, fQ, _, fnu = cs.filter_cubes(np.zeros_like(cube), cube, cube * 0.5, header)
+    np.testing.assert_array_equal(fQ, g["filter_Q"])
+    np.testing.assert_array_equal(fnu, g["filter_nu"])
+
+
+def test_fits_codec_layout_and_round_trip(tmp_path):
+    rng = np.random.RandomState(1)
+    cube = (rng.normal(size=(5, 4, 6)) + 1j * rng.normal(size=(5, 4, 6))).astype(np.complex64)
+    phi = np.linspace(-100.0, 100.0, 5)
+    header = fits_lite.Header({"CRVAL1": 12.5, "CTYPE1": "RA---SIN", "BUNIT": "Jy/beam", "EQUINOX": 2000.0})
+    path = str(tmp_path / "fd_cube.fits")
+    cs.Writer(output=path).writeFITSCube(cube, header, 5, phi, phi[1] - phi[0])
+    raw = open(path, "rb").read()
+    assert len(raw) % 2880 == 0 and raw[:30] == b"SIMPLE  =                    T"
+    hdr, data = cs.Reader().readCube(file=path, memmap=True)
+    assert data.shape == (2, 5, 4, 6) and hdr["NAXIS"] == 4 and hdr["NAXIS4"] == 2 and hdr["NAXIS3"] == 5
+    assert hdr["CTYPE3"] == "Phi" and hdr["CUNIT3"] == "rad/m/m" and hdr["CRVAL3"] == -100.0 and hdr["CDELT3"] == 50.0
+    assert hdr["CTYPE1"] == "RA---SIN" and hdr["BUNIT"] == "Jy/beam" and hdr["CRVAL1"] == 12.5
+    np.testing.assert_array_equal(np.asarray(data[0]), cube.real)
+    np.testing.assert_array_equal(np.asarray(data[1]), cube.imag)
+    # big-endian float32 right after the header block(s)
+    first = np.frombuffer(raw[2880:2884] if raw[2880:2881] != b" " else raw[5760:5764], dtype=">f4")[0]
+    assert first == cube.real[0, 0, 0]
+    # plain image, integer type, non-memmap
+    img = np.arange(12, dtype=np.int16).reshape(3, 4)
+    p2 = str(tmp_path / "img.fits")
+    cs.Writer().writeFITS(data=img, header={"OBJECT": "test"}, output=p2)
+    h2, d2 = cs.Reader().readImage(name=p2)
+    assert h2["BITPIX"] == 16 and h2["OBJECT"] == "test"
+    np.testing.assert_array_equal(d2, img)
+    assert cs.Reader(Q_cube_name=p2).readHeader()["NAXIS1"] == 4
+    # numpy side of the reader / writer
+    npy = str(tmp_path / "qu.npy")
+    cs.Writer(output=npy).writeNPCube(np.stack([img, 2 * img], axis=-1))
+    Q, U = cs.Reader(numpy_file=npy).readNumpyFile()
+    np.testing.assert_array_equal(U, 2 * Q)
+
+
+@pytest.mark.gpu
+def test_device_cube_transposes_and_channel_statistics():
+    import torch
+    rng = np.random.RandomState(5)
+    m, Y, X = 70, 37, 45          # nothing is a multiple of the 32 x 32 tile
+    Q = rng.normal(size=(m, Y, X)).astype(np.float32)
+    U = rng.normal(size=(m, Y, X)).astype(np.float32)
+    Q[3, 5, 7] = np.nan
+    U[10, 0, 0] = np.inf
+    Q[20] = np.nan
+    cube = cs.DeviceCube(Q, U)
+    npix = Y * X
+    for p0, P in ((0, 33), (100, 257), (npix - 50, 50)):
+        planar, valid = cube.slab(p0, P)
+        qf, uf = Q.reshape(m, -1)[:, p0:p0 + P].T, U.reshape(m, -1)[:, p0:p0 + P].T
+        ok = np.isfinite(qf) & np.isfinite(uf)
+        np.testing.assert_array_equal(valid.cpu().numpy().astype(bool), ok)
+        np.testing.assert_array_equal(planar[:, :m].cpu().numpy(), np.where(ok, qf, 0))
+        np.testing.assert_array_equal(planar[:, m:2 * m].cpu().numpy(), np.where(ok, uf, 0))
+        assert planar.shape[1] % 8 == 0 and float(planar[:, 2 * m:].abs().sum()) == 0
+    s_sum, s_std = cube.channel_stats("Q", x0=2, xn=40, y0=1, yn=30)
+    want_sum, want_std = np.nansum(Q[:, 1:30, 2:40], axis=(1, 2)), np.nanstd(Q[:, 1:30, 2:40].astype(np.float64), axis=(1, 2))
+    fin = np.isfinite(want_std)
+    np.testing.assert_allclose(s_sum.cpu().numpy()[fin], want_sum[fin], rtol=1e-5, atol=1e-4)
+    np.testing.assert_allclose(s_std.cpu().numpy()[fin], want_std[fin], rtol=1e-6)
+    assert np.isnan(s_std.cpu().numpy()[20]) and not fin[20]
+    np.testing.assert_allclose(cs.calculate_noise(image=torch.as_tensor(U[:, :, :]).cuda()).cpu().numpy()[1:10],
+                               np.nanstd(U[1:10].astype(np.float64), axis=(1, 2)), rtol=1e-6)
+    # Faraday-depth side: planar rows -> (2, n, Y, X)
+    n = 53
+    out = cube.new_output(n)
+    F = rng.normal(size=(npix, 2 * n + 2)).astype(np.float32)
+    for p0 in range(0, npix, 400):
+        P = min(400, npix - p0)
+        cube.store(torch.as_tensor(F[p0:p0 + P]).cuda(), n, p0, out)
+    got = out.cpu().numpy()
+    np.testing.assert_array_equal(got[0].reshape(n, -1), F[:, :n].T)
+    np.testing.assert_array_equal(got[1].reshape(n, -1), F[:, n:2 * n].T)
