@@ -90,25 +90,31 @@ channel_stats_kernel(const float* __restrict__ img, int Y, int X, int x0, int xn
                      float* __restrict__ stats) {
     __shared__ double red[32];
     const float* plane = img + (size_t)blockIdx.x * Y * X;
-    const int wx = xn - x0, wy = yn - y0;
-    const long long total = (long long)wx * wy;
+    // a warp per image row, lanes along x: coalesced and free of index divisions
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
     double sum = 0.0, cnt = 0.0;
-    for (long long t = threadIdx.x; t < total; t += blockDim.x) {
-        const float v = plane[(size_t)(y0 + t / wx) * X + x0 + t % wx];
-        if (!isnan(v)) {
-            sum += v;
-            cnt += 1.0;
+    for (int y = y0 + warp; y < yn; y += nwarps) {
+        const float* row = plane + (size_t)y * X;
+        for (int x = x0 + lane; x < xn; x += 32) {
+            const float v = row[x];
+            if (!isnan(v)) {
+                sum += v;
+                cnt += 1.0;
+            }
         }
     }
     sum = block_sum(sum, red);
     cnt = block_sum(cnt, red);
     const double mean = cnt > 0.0 ? sum / cnt : 0.0;
     double ss = 0.0;
-    for (long long t = threadIdx.x; t < total; t += blockDim.x) {
-        const float v = plane[(size_t)(y0 + t / wx) * X + x0 + t % wx];
-        if (!isnan(v)) {
-            const double d = (double)v - mean;
-            ss += d * d;
+    for (int y = y0 + warp; y < yn; y += nwarps) {
+        const float* row = plane + (size_t)y * X;
+        for (int x = x0 + lane; x < xn; x += 32) {
+            const float v = row[x];
+            if (!isnan(v)) {
+                const double d = (double)v - mean;
+                ss += d * d;
+            }
         }
     }
     ss = block_sum(ss, red);
