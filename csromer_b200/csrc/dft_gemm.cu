@@ -574,6 +574,188 @@ dft_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
     }
 }
 
+
+// ---- fp8 screening on CTA pairs (cta_group::2) ---------------------------------------------------------------------
+// The one-CTA fp8 screening kernel is bound by operand delivery into the SM: 48 KB (A 16 + B 32) per 128 x 256 x 128
+// block.  Here two CTAs of a cluster (the two SMs of a TPC) screen two pixel tiles of the same column tile with ONE
+// M = 256 MMA: each CTA stages its own A tile and only HALF of the B tile (32 KB per block and SM), the tensor core
+// reads both halves, and each CTA's TMEM receives its 128 rows.  Six 32 KB stages per CTA; the leader CTA (rank 0)
+// issues the MMAs and owns the full / accumulator-empty barriers, MMA commits are multicast to both CTAs.
+// Same test, same bound, same lists as dft_gemm_kernel<EPI_SCREEN8>; a pair runs when at least one of its two
+// pixel tiles is quiet (the other CTA then just passes its tile on).
+constexpr int P2_STAGES = 6;
+constexpr int P2_STAGE_BYTES = 2 * A_TILE_BYTES;  // A (128 rows x 128 B) + half of B (128 rows x 128 B)
+constexpr int P2_SMEM_BYTES = 1024 + P2_STAGES * P2_STAGE_BYTES + 256;
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
+screen8_pair_kernel(const __grid_constant__ CUtensorMap map_a8, const __grid_constant__ CUtensorMap map_b8, int K, int MT,
+                    int NT, const GemmEpilogue epi) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* stage_base = smem;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + P2_STAGES * P2_STAGE_BYTES);
+    uint64_t* full = bars;                              // [P2_STAGES]  both CTAs' TMA -> leader's MMA thread
+    uint64_t* empty = bars + P2_STAGES;                 // [P2_STAGES]  MMA -> each CTA's producer (multicast commit)
+    uint64_t* tmem_full = bars + 2 * P2_STAGES;         // [2]  MMA -> each CTA's epilogue warps (multicast commit)
+    uint64_t* tmem_empty = bars + 2 * P2_STAGES + 2;    // [2]  epilogue warps of BOTH CTAs -> leader's MMA thread
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * P2_STAGES + 4);
+    int* last_listed = reinterpret_cast<int*>(bars + 2 * P2_STAGES + 5);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const int cluster_id = blockIdx.x >> 1, nclusters = gridDim.x >> 1;
+    const int MTP = (MT + 1) / 2;
+    const int total = MTP * NT;
+    const int KB = (K + 2 * BK - 1) / (2 * BK);  // 128 fp8 elements per K block
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&map_a8);
+        tma_prefetch_desc(&map_b8);
+        for (int s = 0; s < P2_STAGES; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], 1);
+        }
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(&tmem_full[b], 1);
+            mbar_init(&tmem_empty[b], 2 * EPI_WARPS);
+        }
+        *last_listed = -1;
+        mbar_fence_init();
+    }
+    if (warp == 1) {
+        tmem_alloc_pair(tmem_ptr, TMEM_COLS);
+        tmem_relinquish_pair();
+    }
+    tc_fence_before();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    auto quiet = [&](int mt, int nt) -> bool {  // does pixel tile mt exist and is its state zero in this column tile?
+        if (mt >= MT) return false;
+        const unsigned int* st = epi.tile_state + (size_t)mt * epi.flag_ld + 2 * nt;
+        unsigned int wd = __ldcg(st);
+        if (2 * nt + 1 < epi.flag_ld) wd |= __ldcg(st + 1);
+        return wd == 0u;
+    };
+
+    if (warp < 4) {
+      asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+      if (warp == 0) {
+        // ===================== TMA producer (both CTAs) =====================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tp = cluster_id; tp < total; tp += nclusters) {
+                int mtp, nt;
+                tile_coords(tp, MTP, NT, mtp, nt);
+                if (!quiet(2 * mtp, nt) && !quiet(2 * mtp + 1, nt)) continue;
+                const int mt = 2 * mtp + (int)rank;
+                for (int kb = 0; kb < KB; ++kb) {
+                    mbar_wait(&empty[stage], phase ^ 1);
+                    uint8_t* sb = stage_base + stage * P2_STAGE_BYTES;
+                    if (rank == 0) mbar_arrive_expect_tx(&full[stage], 2 * P2_STAGE_BYTES);
+                    tma_load_2d_pair(sb, &map_a8, &full[stage], kb * 2 * BK, mt * BM);
+                    tma_load_2d_pair(sb + A_TILE_BYTES, &map_b8, &full[stage], kb * 2 * BK, nt * BN + (int)rank * (BN / 2));
+                    if (++stage == P2_STAGES) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+            }
+        }
+      } else if (warp == 1 && rank == 0) {
+        // ===================== MMA issuer (leader CTA only) =====================
+        if (lane == 0) {
+            constexpr uint32_t idesc = umma_idesc_f16(2 * BM, BN);  // M = 256 over the pair; format code 0 = e4m3 here
+            int stage = 0;
+            uint32_t phase = 0, use = 0;
+            unsigned long long issued = 0;
+            for (int tp = cluster_id; tp < total; tp += nclusters) {
+                int mtp, nt;
+                tile_coords(tp, MTP, NT, mtp, nt);
+                if (!quiet(2 * mtp, nt) && !quiet(2 * mtp + 1, nt)) continue;
+                const int buf = use & 1;
+                mbar_wait(&tmem_empty[buf], ((use >> 1) & 1) ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(buf * BN);
+                for (int kb = 0; kb < KB; ++kb) {
+                    mbar_wait(&full[stage], phase);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(stage_base + stage * P2_STAGE_BYTES);
+                    const uint32_t sb = sa + A_TILE_BYTES;
+#pragma unroll
+                    for (int k4 = 0; k4 < 4; ++k4)
+                        umma_f8_pair(d_tmem, umma_desc_sw128(sa + k4 * 32), umma_desc_sw128(sb + k4 * 32), idesc,
+                                     (kb != 0 || k4 != 0) ? 1u : 0u);
+                    umma_commit_pair(&empty[stage]);
+                    if (++stage == P2_STAGES) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                    issued += 4;  // two CTAs x one 128-element fp8 K block = 4 units of 128 x 256 x 64
+                }
+                umma_commit_pair(&tmem_full[buf]);
+                ++use;
+            }
+            if (epi.mma_count != nullptr && issued != 0) atomicAdd(epi.mma_count + 2, issued);
+        }
+      }
+    } else {
+        // ===================== epilogue warps (both CTAs) =====================
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
+        const int ew = warp - 4;
+        const int sub = warp & 3;
+        const int half = ew >> 2;
+        uint32_t use = 0;
+        int ti = 0;  // running index of this CTA's tiles (for the one-lister-per-tile rule)
+        for (int tp = cluster_id; tp < total; tp += nclusters, ++ti) {
+            int mtp, nt;
+            tile_coords(tp, MTP, NT, mtp, nt);
+            const int mt = 2 * mtp + (int)rank;
+            const bool q_own = quiet(mt, nt), q_other = quiet(2 * mtp + 1 - (int)rank, nt);
+            const bool exists = mt < MT;
+            const int t = mt + nt * 0;  // (tile id in the full kernel's numbering is computed below)
+            (void)t;
+            bool list_it = exists && !q_own;
+            if (q_own || q_other) {
+                const int buf = use & 1;
+                mbar_wait(&tmem_full[buf], (use >> 1) & 1);
+                tc_fence_after();
+                if (q_own) {
+                    float acc[EPI_COLS];
+#pragma unroll
+                    for (int j = 0; j < EPI_COLS; ++j) acc[j] = 0.f;
+                    drain_chunk(tmem_base + ((uint32_t)(sub * 32) << 16) + (uint32_t)(buf * BN + half * EPI_COLS), acc);
+                    const bool fail = screen_tile_fails<true>(epi, acc, lane, mt * BM + sub * 32, nt * BN + half * EPI_COLS, K);
+                    list_it = __any_sync(0xffffffffu, fail) != 0;
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) {
+                    if (rank == 0) mbar_arrive(&tmem_empty[buf]);
+                    else mbar_arrive_leader(&tmem_empty[buf]);
+                }
+                ++use;
+            }
+            if (list_it && lane == 0 && atomicMax(last_listed, ti) < ti) {
+                // tile id in the numbering of dft_gemm_kernel's tile_coords(t, MT, NT): invert it
+                const int g = mt / RASTER_GROUP, first = g * RASTER_GROUP;
+                const int gsize = min(RASTER_GROUP, MT - first);
+                epi.out_list[atomicAdd(epi.out_count, 1)] = g * RASTER_GROUP * NT + nt * gsize + (mt - first);
+            }
+        }
+    }
+
+    tc_fence_before();
+    cluster_sync_all();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc_pair(tmem_base, TMEM_COLS);
+    }
+}
+
 // ---- host side --------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -808,6 +990,59 @@ int launch_dft_gemm(const csr_plan* plan, bool adjoint, const __half* a_hi, cons
     }
     set_error("unknown epilogue mode %d", epi.mode);
     return CSR_ERR_ARG;
+}
+
+
+// fp8 screening on CTA pairs; `a8` is the fp8 copy of the residual operand ([P, ld8] bytes)
+int launch_screen8_pair(const csr_plan* plan, const unsigned char* a8, int P, const GemmEpilogue& epi_in, cudaStream_t stream) {
+    GemmEpilogue epi = epi_in;
+    epi.P = P;
+    epi.N = 2 * plan->n;
+    epi.ld_out = plan->ld2n;
+    epi.m = plan->m;
+    CSR_REQUIRE(epi.abs_sum && epi.tile_state && epi.out_list && epi.out_count && !epi.tile_list, "pair screening: missing argument");
+    const int K = 2 * plan->m;
+    const int MT = (P + BM - 1) / BM, NT = (2 * plan->n + BN - 1) / BN;
+    CUtensorMap ma;
+    int rc = cached_operand_map(&ma, a8, P, K, plan->ld8, 1);
+    if (rc) return rc;
+    static int max_clusters = 0;
+    if (max_clusters == 0) {
+        CSR_CUDA(cudaFuncSetAttribute(screen8_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, P2_SMEM_BYTES));
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(2 * plan->num_sms);
+        cfg.blockDim = dim3(NUM_THREADS);
+        cfg.dynamicSmemBytes = P2_SMEM_BYTES;
+        cudaLaunchAttribute attr;
+        attr.id = cudaLaunchAttributeClusterDimension;
+        attr.val.clusterDim.x = 2;
+        attr.val.clusterDim.y = 1;
+        attr.val.clusterDim.z = 1;
+        cfg.attrs = &attr;
+        cfg.numAttrs = 1;
+        int n = 0;
+        if (cudaOccupancyMaxActiveClusters(&n, screen8_pair_kernel, &cfg) != cudaSuccess || n <= 0) {
+            cudaGetLastError();
+            n = plan->num_sms / 2;
+        }
+        max_clusters = n;
+    }
+    const int pairs = ((MT + 1) / 2) * NT;
+    const int clusters = min(pairs, max_clusters);
+    ProfiledLaunch rec;
+    if (g_profile) {
+        rec.kind = 9;
+        CSR_CUDA(pooled_event(&rec.start));
+        CSR_CUDA(pooled_event(&rec.stop));
+        CSR_CUDA(cudaEventRecord(rec.start, stream));
+    }
+    screen8_pair_kernel<<<2 * clusters, NUM_THREADS, P2_SMEM_BYTES, stream>>>(ma, plan->map_adj8_half, K, MT, NT, epi);
+    CSR_LAUNCHED();
+    if (g_profile) {
+        CSR_CUDA(cudaEventRecord(rec.stop, stream));
+        g_profiled.push_back(rec);
+    }
+    return CSR_OK;
 }
 
 }  // namespace csr

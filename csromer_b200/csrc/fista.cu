@@ -311,7 +311,11 @@ extern "C" int csr_fista(csr_plan* plan, csr_wavelet* wav, const csr_fista_args*
                 e.mode = EPI_SCREEN8;
                 e.out_list = w.tile_list2;
                 e.out_count = counts + 1;
-                if ((rc = launch_dft_gemm(plan, true, reinterpret_cast<const __half*>(w.r8), nullptr, P, e, stream))) return rc;
+                if (options().pair != 0 && P > BM) {
+                    if ((rc = launch_screen8_pair(plan, w.r8, P, e, stream))) return rc;
+                } else {
+                    if ((rc = launch_dft_gemm(plan, true, reinterpret_cast<const __half*>(w.r8), nullptr, P, e, stream))) return rc;
+                }
                 e.tile_list = w.tile_list2;
                 e.tile_count = counts + 1;
             }

@@ -93,7 +93,7 @@ namespace csr {
 Options& options() {
     static Options o = {getenv("CSR_NO_ZERO_SKIP") == nullptr, getenv("CSR_NO_K_SKIP") == nullptr,
                         getenv("CSR_NO_FUSED_WAVELET") == nullptr, getenv("CSR_NO_SCREEN") == nullptr,
-                        getenv("CSR_NO_SCREEN8") == nullptr};
+                        getenv("CSR_NO_SCREEN8") == nullptr, getenv("CSR_NO_PAIR") == nullptr};
     return o;
 }
 }  // namespace csr
@@ -108,6 +108,7 @@ extern "C" int csr_set_option(const char* name, int value) {
     else if (!strcmp(name, "fused_wavelet")) o.fused_wavelet = value != 0;
     else if (!strcmp(name, "screen")) o.screen = value != 0;
     else if (!strcmp(name, "screen8")) o.screen8 = value != 0;
+    else if (!strcmp(name, "pair")) o.pair = value != 0;
     else {
         set_error("csr_set_option: unknown option '%s'", name);
         return CSR_ERR_ARG;
@@ -178,6 +179,7 @@ static int plan_build(csr_plan* p, const double* lambda2, const double* phi) {
     if ((rc = make_operand_map(&p->map_adj_hi, p->Tt_hi, 2 * n, 2 * m, p->ld2m, BN))) return rc;
     if ((rc = make_operand_map(&p->map_adj_lo, p->Tt_lo, 2 * n, 2 * m, p->ld2m, BN))) return rc;
     if ((rc = make_operand_map(&p->map_adj8, p->Tt8, 2 * n, 2 * m, p->ld8, BN, 1))) return rc;
+    if ((rc = make_operand_map(&p->map_adj8_half, p->Tt8, 2 * n, 2 * m, p->ld8, BN / 2, 1))) return rc;
     return CSR_OK;
 }
 

@@ -19,6 +19,7 @@ struct csr_plan {
     unsigned char* Tt8;  // [2n rows, ld8]
     int ld8;             // row pitch in bytes of every [*, 2m] fp8 matrix, multiple of 16
     CUtensorMap map_fwd_hi, map_fwd_lo, map_adj_hi, map_adj_lo, map_adj8;
+    CUtensorMap map_adj8_half;  // Tt8 with a 128-row box: half a B tile per CTA of a cta_group::2 pair
     size_t table_bytes;
 };
 
@@ -92,5 +93,6 @@ struct GemmEpilogue {
 int make_operand_map(CUtensorMap* map, const void* base, int rows, int cols, int ld, int box_rows, int elem_bytes = 2);
 int launch_dft_gemm(const csr_plan* plan, bool adjoint, const __half* a_hi, const __half* a_lo, int P,
                     const GemmEpilogue& epi, cudaStream_t stream);
+int launch_screen8_pair(const csr_plan* plan, const unsigned char* a8, int P, const GemmEpilogue& epi, cudaStream_t stream);
 
 }  // namespace csr
