@@ -13,14 +13,21 @@
 // products  A_hi*B_hi + A_lo*B_hi + A_hi*B_lo  into one fp32 accumulator: fp32-class accuracy at one third
 // of the fp16 tensor rate (the dropped A_lo*B_lo term is ~2^-22 relative).
 //
-// Structure (one CTA per SM, persistent over tiles):
-//   warp 0   : TMA producer   (cp.async.bulk.tensor -> 128B-swizzled smem ring, mbarrier complete_tx)
-//   warp 1   : MMA issuer     (one thread issues tcgen05.mma; tcgen05.commit frees smem stages / publishes
-//                              the accumulator); also owns the TMEM allocation
-//   warps 2-9: epilogue       (tcgen05.ld 16x256b -> register accumulators -> float2 / half2 global I/O)
+// Structure (one CTA per SM, persistent over tiles, 384 threads):
+//   warp 0    : TMA producer   (cp.async.bulk.tensor -> 128B-swizzled smem ring, mbarrier complete_tx)
+//   warp 1    : MMA issuer     (one thread issues tcgen05.mma; tcgen05.commit frees smem stages / publishes
+//                               the accumulator); also owns the TMEM allocation
+//   warps 4-11: epilogue       (tcgen05.ld 16x256b -> register accumulators -> float2 / half2 global I/O)
 // TMEM holds two 128x256 fp32 accumulators used ping-pong per K CHUNK: the tensor core's fp32 accumulate
 // truncates, so partial sums are moved to registers (round-to-nearest adds) every `chunk_kb` K blocks while the
 // next chunk runs; the fused epilogue of tile t overlaps the first chunks of tile t+1 the same way.
+//
+// Kernels in this file:
+//   dft_gemm_kernel<EPI_PLAIN | EPI_RESID | EPI_FISTA>   three-product GEMM with the fused epilogues above; the forward
+//                                                        direction can skip K blocks whose A tile is zero (build_kmask)
+//   dft_gemm_kernel<EPI_SCREEN | EPI_SCREEN8>            one-product (fp16 / fp8) safe screening of adjoint tiles
+//   screen8_pair_kernel                                  the fp8 screening pass on CTA pairs (cta_group::2)
+// and the host-side launchers with their tensor-map cache and per-launch CUDA-event profiling.
 #include <stdlib.h>
 #include <string.h>
 
@@ -716,9 +723,7 @@ screen8_pair_kernel(const __grid_constant__ CUtensorMap map_a8, const __grid_con
             const int mt = 2 * mtp + (int)rank;
             const bool q_own = quiet(mt, nt), q_other = quiet(2 * mtp + 1 - (int)rank, nt);
             const bool exists = mt < MT;
-            const int t = mt + nt * 0;  // (tile id in the full kernel's numbering is computed below)
-            (void)t;
-            bool list_it = exists && !q_own;
+            bool list_it = exists && !q_own;  // a tile with signal goes straight to the next pass of the cascade
             if (q_own || q_other) {
                 const int buf = use & 1;
                 mbar_wait(&tmem_full[buf], (use >> 1) & 1);
