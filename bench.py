@@ -445,10 +445,11 @@ def run_ours(args):
         k_tf = blocks[2] * block_flops / (k_ms * 1e-3) / 1e12
         k_peak, k_src = 2.0 * peak, ("2 x MEASURED_PEAKS.json bf16_tflops_sustained (%s): no fp8 figure is measured on this "
                                      "pool; nominal fp8 dense = 2 x bf16" % peaks["source"])
-        k_name = "dft_gemm_kernel<EPI_SCREEN8>: fp8 (e4m3) screening pass of the adjoint transform, tcgen05 kind::f8f6f4"
-        k_note = ("achieved = fp8 flops the kernel issued (in-kernel counter) / its CUDA-event time; it is L2->SM "
-                  "operand-fabric bound (48 KB of operands per 128x256x128 block: profiles/r1_screen8_gemm_metrics.json, "
-                  "6.9 GB per launch = 12.4 TB/s), not tensor bound")
+        k_name = ("screen8_pair_kernel: fp8 (e4m3) screening pass of the adjoint transform on CTA pairs, tcgen05 "
+                  "cta_group::2 kind::f8f6f4")
+        k_note = ("achieved = fp8 flops the kernel issued (in-kernel counter) / its CUDA-event time; ncu: tensor pipe "
+                  "active 70 %, L2->SM operand traffic 4.6 GB per launch = 11.4 TB/s (the fabric is the bound), DRAM 69 MB "
+                  "(profiles/r1_final_gemm_metrics.json)")
     else:  # dense regime: the three-product kernels dominate
         k_ms = float(sum(ms[0][i] for i in (0, 1, 2, 3, 4, 5))) / args.steps
         k_tf = (blocks[0] + 3.0 * (ms[1][0] * ((P + 127) // 128) * ((2 * M_CH + 255) // 256) * ((2 * N_PHI + 63) // 64)

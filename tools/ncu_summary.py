@@ -6,6 +6,7 @@ import subprocess
 import sys
 
 launch_csv, rep, out = sys.argv[1:4]
+what = sys.argv[4] if len(sys.argv) > 4 else "python tools/prof_target.py 16384 6 (one fused FISTA call: C3 sampling, 16384 LOS, 6 iterations, bench slab)"
 rows = list(csv.reader(l for l in open(launch_csv) if l.startswith('"')))
 hdr = rows[0]
 ki, vi = hdr.index("Kernel Name"), hdr.index("Metric Value")
@@ -21,8 +22,8 @@ for r in rows[1:]:
     a[0] += 1
     a[1] += ns
 with open(out + "_launches.txt", "w") as f:
-    f.write("# ncu --metrics gpu__time_duration.sum --clock-control none  python tools/prof_target.py 16384 6\n")
-    f.write("# (one fused FISTA call: C3 sampling m=1000 n=7968, 16384 LOS, 6 iterations, bench slab; cold-cache serialised times)\n")
+    f.write("# ncu --metrics gpu__time_duration.sum --clock-control none  %s\n" % what)
+    f.write("# (cold-cache, serialised times: compare SHARES)\n")
     f.write("%-60s %6s %12s %7s\n" % ("kernel", "count", "total_us", "share"))
     for name, (c, ns) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
         f.write("%-60s %6d %12.1f %6.1f%%\n" % (name[:60], c, ns / 1e3, 100 * ns / total))
