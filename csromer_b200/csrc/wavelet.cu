@@ -249,25 +249,37 @@ swt_synth_fused_kernel(const float* __restrict__ coef, int ld_coef, int N, int L
     const int base = t0 - H;
     const float* crow = coef + (size_t)p * ld_coef;
     // Sparsity shortcut (exact): thresholded coefficient vectors are mostly zero.  A band tile that is identically
-    // zero contributes exactly 0, so it is neither staged nor read; while the running approximation is itself
-    // identically zero the whole level is skipped.
-    int any = 0;
-    for (int i = threadIdx.x; i < B; i += WAV_THREADS) {
-        const float v = crow[bands.off[0] + wrap_index(base + i, N)];
-        a[i] = v;
-        any |= (v != 0.f);
+    // zero contributes exactly 0, so it is not staged; while the running approximation is itself identically zero
+    // the whole level is skipped.  Which band tiles hold anything is found in ONE pass: every thread tests its
+    // samples of all L + 1 bands with independent loads (one memory latency instead of L + 1 dependent load / vote
+    // phases -- most tiles are zero in every band, and they are done after this pass), then the non-zero bands
+    // are staged (their second read hits L2).
+    __shared__ unsigned int band_nz_s;
+    if (threadIdx.x == 0) band_nz_s = 0u;
+    __syncthreads();
+    {
+        unsigned int mine = 0u;
+        for (int i = threadIdx.x; i < B; i += WAV_THREADS) {
+            const int gi = wrap_index(base + i, N);
+            for (int b = 0; b <= L; ++b) mine |= (crow[bands.off[b] + gi] != 0.f) ? (1u << b) : 0u;
+        }
+        mine = __reduce_or_sync(0xffffffffu, mine);
+        if ((threadIdx.x & 31) == 0 && mine) atomicOr(&band_nz_s, mine);
     }
-    bool a_nz = __syncthreads_or(any) != 0;
+    __syncthreads();
+    const unsigned int band_nz = band_nz_s;
+    bool a_nz = (band_nz & 1u) != 0;
+    if (a_nz) {
+        for (int i = threadIdx.x; i < B; i += WAV_THREADS) a[i] = crow[bands.off[0] + wrap_index(base + i, N)];
+    }
     for (int lev = L; lev >= 1; --lev) {
         const int step = 1 << (lev - 1);
         const float* dband = crow + bands.off[L - lev + 1];
-        any = 0;
-        for (int i = threadIdx.x; i < B; i += WAV_THREADS) {
-            const float v = dband[wrap_index(base + i, N)];
-            d[i] = v;
-            any |= (v != 0.f);
+        const bool d_nz = ((band_nz >> (L - lev + 1)) & 1u) != 0;
+        if (d_nz) {
+            for (int i = threadIdx.x; i < B; i += WAV_THREADS) d[i] = dband[wrap_index(base + i, N)];
         }
-        const bool d_nz = __syncthreads_or(any) != 0;
+        if (a_nz || d_nz) __syncthreads();  // staged operands visible (uniform branch)
         if (!a_nz && !d_nz) continue;  // result identically zero: nothing to compute, `a` stays "zero"
         // only entries whose taps stay inside the buffer are computed (no per-tap clamping); the uncomputed rim
         // grows by step*F/2 per level and is covered by the halo
