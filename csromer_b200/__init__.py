@@ -16,11 +16,12 @@ from .io import DeviceCube, Reader, Writer, filter_cubes
 from .transformers import (DFT1D, FT, NDFT1D, NUFFT1D, DatasetStack, Flagger, HampelFlagger, ManualFlagger, MeanFlagger,
                            PerPixelDFT1D)
 from .utils import calculate_noise
+from .wrappers import CSROMERReconstructorWrapper, FaradayReconstructorWrapper
 
 __version__ = "0.1.0"
 __all__ = [
     "Dataset", "Parameter", "FT", "NDFT1D", "DFT1D", "NUFFT1D", "PerPixelDFT1D", "DatasetStack", "Wavelet", "DiscreteWavelet", "UndecimatedWavelet",
     "Fi", "Chi2", "L1", "OFunction", "Optimizer", "FISTA", "FaradaySource", "FaradayThinSource",
     "FaradayThickSource", "reconstruct_cube", "estimate_lipschitz", "Flagger", "MeanFlagger", "HampelFlagger",
-    "ManualFlagger", "Reader", "Writer", "filter_cubes", "DeviceCube", "calculate_noise",
+    "ManualFlagger", "CSROMERReconstructorWrapper", "FaradayReconstructorWrapper", "Reader", "Writer", "filter_cubes", "DeviceCube", "calculate_noise",
 ]

@@ -123,6 +123,74 @@ def test_fits_codec_layout_and_round_trip(tmp_path):
     np.testing.assert_array_equal(U, 2 * Q)
 
 
+def test_reconstructor_wrapper_static_helpers():
+    W = cs.CSROMERReconstructorWrapper
+    # 3-point parabola: exact for a sampled parabola
+    n, cell = 64, 2.5
+    j = np.arange(n)
+    true_pos, true_peak = 40.3, 7.0
+    f = (true_peak - 0.5 * (j - true_pos) ** 2).clip(min=0.0) * np.exp(1j * 0.3)
+    pos, peak = W.estimate_peak_quadratic_interpolation(f, cell)
+    assert pos == pytest.approx((true_pos - n / 2) * cell, abs=1e-9) and peak == pytest.approx(true_peak, abs=1e-9)
+    pos2, peak2 = W.estimate_peak_quadratic_interpolation(np.stack([f, np.roll(f, 3)], axis=1), cell)   # batched
+    assert pos2[0] == pytest.approx(pos) and pos2[1] == pytest.approx(pos + 3 * cell) and peak2[1] == pytest.approx(peak)
+    assert W.calculate_ricean_peak(5.0, 1.0) == pytest.approx(np.sqrt(25 - 2.3))
+    assert W.calculate_sigma_phi_peak(50.0, 10.0, 0.5) == pytest.approx(50.0 / (2 * 10.0 / 0.5))
+    # sigma clipping as documented by astropy: outliers beyond sigma * mad_std around the mean are dropped iteratively
+    from csromer_b200.wrappers.reconstructors import sigma_clipped_std
+    rng = np.random.RandomState(0)
+    x = rng.normal(0, 1.0, 4000)
+    x[:20] = 50.0
+    assert sigma_clipped_std(x, sigma=3.0) == pytest.approx(np.std(x[20:][np.abs(x[20:]) < 3.05]), rel=0.02)
+    assert sigma_clipped_std(x, mask=np.arange(4000) >= 20, sigma=3.0) == 0.0          # only the 20 equal outliers are left
+    # the reference's default threshold = 0 masks everything but phi = 0 -> noise 0 (csromer_reconstructor.py:86-102)
+    phi = np.linspace(-10, 10, 21)
+    assert W.calculate_fd_signal_noise(rng.normal(size=21) + 1j * rng.normal(size=21), phi, 10.0) == 0.0
+    assert W.calculate_fd_signal_noise(rng.normal(size=21) + 1j * rng.normal(size=21), phi, 10.0, threshold=2.0, sigma=3.0) > 0
+
+
+@pytest.mark.gpu
+def test_reconstructor_wrapper_matches_oracle_pipeline(capsys):
+    """the reference's one-call wrapper (default lambda / noise schedule, flagger first) on the GPU path against the
+    oracle run with the same schedule; step = 1 / lambda_max on both sides (the unit step is unstable at the end of
+    this schedule)"""
+    from oracle import restatement as ob
+    rng = np.random.RandomState(4)
+    m = 160
+    nu = np.linspace(1.008e9, 2.031e9, m)
+    src = cs.FaradayThinSource(nu=nu, s_nu=0.0035, phi_gal=-150.0, spectral_idx=1.0)
+    src.simulate()
+    src.apply_noise(0.2 * 0.0035, random_state=rng)
+    sig = np.asarray(src.sigma).copy()
+    sig[[11, 70]] *= 8.0
+    src.sigma = sig
+    flagger = cs.MeanFlagger(dataset=src, nsigma=5.0, delete_channels=True)
+    rec = cs.CSROMERReconstructorWrapper(dataset=src, flagger=flagger, oversampling=8.0, step="auto")
+    rec.reconstruct()
+    capsys.readouterr()
+    assert src.m == m - 2 and rec.fd_model.shape == (len(rec.parameter.phi),)
+    par = rec.parameter
+    op = ob.ExactDFT(src.lambda2, par.phi, src.w, src.s, src.k, src.l2_ref)
+    dirty = op.backward(np.asarray(src.data))
+    lam0 = np.sqrt(src.m + 2 * np.sqrt(src.m)) * np.sqrt(2) * np.mean(src.sigma)
+    assert rec.lambda_l_norm == pytest.approx(lam0, rel=1e-12)
+    step = 1.0 / cs.estimate_lipschitz(rec.dft)
+    ref = ob.fista(op, np.asarray(src.data), ob.complex_to_real(dirty), lam0, src.theo_noise, None, step=step)
+    model = ob.real_to_complex(ref["x"])
+    scale = np.abs(model).max()
+    assert np.abs(rec.fd_dirty - dirty).max() / np.abs(dirty).max() < 1e-5
+    assert np.abs(rec.fd_model - model).max() / scale < 2e-4
+    assert rec.rm_model == par.phi[np.argmax(np.abs(model))] and abs(rec.rm_model + 150.0) < 2 * par.cellsize
+    mag = np.abs(model)
+    first = np.sum(par.phi * mag) / mag.sum()
+    assert rec.second_moment == pytest.approx(np.sum(mag * (par.phi - first) ** 2) / mag.sum(), rel=2e-3)
+    resid_fd = op.backward(np.asarray(src.data) - ref["model"])
+    assert np.abs(rec.fd_residual - resid_fd).max() / np.abs(dirty).max() < 2e-4
+    restored = ob.convolve_beam(model, ob.gaussian_beam(par.rmtf_fwhm, par.cellsize)) + resid_fd
+    assert np.abs(rec.fd_restored - restored).max() / np.abs(restored).max() < 2e-4
+    assert abs(rec.rm_restored_quadratic_interpolation + 150.0) < par.cellsize
+
+
 @pytest.mark.gpu
 def test_device_cube_transposes_and_channel_statistics():
     import torch
