@@ -477,15 +477,24 @@ dft_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
                     build_kmask(epi.a_kflags + (size_t)mt * epi.a_kflag_ld, kwords, KB, my_mask, lane);
                 }
                 if (lane == 0) {
-                    int in_chunk = 0;  // active K blocks accumulated into the current chunk so far
+                    // A chunk is the set of (active) K blocks inside one aligned window of `chunk_kb` blocks, so skipping
+                    // zero blocks never changes how the others are grouped: bit-identical to the dense loop.
+                    int in_chunk = 0, cur_win = -1;  // K blocks accumulated into the current chunk so far / its window
                     uint32_t d_tmem = 0;
                     for (int kb = skip ? next_active_kb(my_mask, 0, KB) : 0; kb < KB;
                          kb = skip ? next_active_kb(my_mask, kb + 1, KB) : kb + 1) {
+                        const int win = kb / chunk_kb;
+                        if (in_chunk != 0 && win != cur_win) {
+                            umma_commit(&tmem_full[chunk & 1]);  // chunk accumulator complete
+                            ++chunk;
+                            in_chunk = 0;
+                        }
                         if (in_chunk == 0) {
                             const int buf = chunk & 1;
                             mbar_wait(&tmem_empty[buf], ((chunk >> 1) & 1) ^ 1);
                             tc_fence_after();
                             d_tmem = tmem_base + (uint32_t)(buf * BN);
+                            cur_win = win;
                         }
                         mbar_wait(&full[stage], phase);
                         tc_fence_after();
@@ -515,11 +524,7 @@ dft_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
                             stage = 0;
                             phase ^= 1;
                         }
-                        if (++in_chunk == chunk_kb) {
-                            umma_commit(&tmem_full[chunk & 1]);  // chunk accumulator complete
-                            ++chunk;
-                            in_chunk = 0;
-                        }
+                        ++in_chunk;
                     }
                     if (in_chunk != 0) {
                         umma_commit(&tmem_full[chunk & 1]);
@@ -551,9 +556,21 @@ dft_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
             float acc[EPI_COLS];
 #pragma unroll
             for (int j = 0; j < EPI_COLS; ++j) acc[j] = 0.f;
-            int active_kb = KB;
-            if (skip) active_kb = build_kmask(epi.a_kflags + (size_t)mt * epi.a_kflag_ld, kwords, KB, my_mask, lane);
-            for (int kb0 = 0; kb0 < active_kb; kb0 += chunk_kb, ++chunk) {
+            int nchunks = (KB + chunk_kb - 1) / chunk_kb;
+            if (skip) {  // count the windows that hold an active K block, exactly as the MMA thread walks them
+                build_kmask(epi.a_kflags + (size_t)mt * epi.a_kflag_ld, kwords, KB, my_mask, lane);
+                int c = 0;
+                if (lane == 0) {
+                    int cur_win = -1;
+                    for (int kb = next_active_kb(my_mask, 0, KB); kb < KB; kb = next_active_kb(my_mask, kb + 1, KB)) {
+                        const int win = kb / chunk_kb;
+                        c += (win != cur_win);
+                        cur_win = win;
+                    }
+                }
+                nchunks = __shfl_sync(0xffffffffu, c, 0);
+            }
+            for (int c = 0; c < nchunks; ++c, ++chunk) {
                 const int buf = chunk & 1;
                 mbar_wait(&tmem_full[buf], (chunk >> 1) & 1);
                 tc_fence_after();
