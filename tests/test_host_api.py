@@ -203,3 +203,36 @@ def test_no_gpu_means_loud_failure():
     par.calculate_cellsize(dataset=src, verbose=False)
     with pytest.raises(CsrError):
         cs.NDFT1D(dataset=src, parameter=par).backward(src.data)
+
+
+def test_dataset_stack_presents_ragged_datasets_as_one_batch():
+    """host logic of the per-line-of-sight sampling path (PerPixelDFT1D): zero padding, fan-out of model_data"""
+    from csromer_b200.transformers.dfts import DatasetStack
+    rng = np.random.RandomState(0)
+    nu = np.linspace(1.0e9, 2.0e9, 40)
+    full = cs.Dataset(nu=nu, sigma=np.ones(40))
+    members = []
+    for p, keep in enumerate((40, 31, 25)):
+        idx = np.sort(rng.choice(40, size=keep, replace=False))
+        ds = cs.Dataset(lambda2=np.asarray(full.lambda2)[idx], sigma=0.1 * (1 + rng.uniform(size=keep)),
+                        data=(rng.normal(size=keep) + 1j * rng.normal(size=keep)).astype(np.complex64),
+                        spectral_idx=0.5, l2_ref=0.01 * p)
+        members.append(ds)
+    st = DatasetStack(members)
+    assert (st.m, st.P) == (40, 3) and list(st.m_count) == [40, 31, 25]
+    assert st.data.shape == (40, 3) and np.all(st.data[31:, 1] == 0) and np.all(st.w[25:, 2] == 0)
+    np.testing.assert_array_equal(st.data[:25, 2], members[2].data)
+    np.testing.assert_allclose(st.lambda2_minus_ref[:31, 1], np.asarray(members[1].lambda2) - 0.01)
+    np.testing.assert_allclose(st.k, [float(d.k) for d in members])
+    np.testing.assert_allclose(st.theo_noise, [d.theo_noise for d in members])
+    assert np.all(st.s[31:, 1] == 1.0)
+    model = (rng.normal(size=(40, 3)) + 1j * rng.normal(size=(40, 3)))
+    st.model_data = model
+    for p, ds in enumerate(members):
+        np.testing.assert_allclose(ds.model_data, model[:ds.m, p].astype(np.complex64))
+        np.testing.assert_allclose(ds.residual, ds.data - ds.model_data)
+    np.testing.assert_allclose(st.residual[:25, 2], members[2].residual)
+    with pytest.raises(ValueError):
+        DatasetStack([])
+    with pytest.raises(ValueError):
+        DatasetStack([cs.Dataset(nu=nu, sigma=np.ones(40), data=np.zeros((40, 2), np.complex64))])
