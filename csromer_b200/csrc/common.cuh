@@ -271,6 +271,7 @@ __host__ __device__ constexpr uint32_t umma_idesc_f16(int M, int N) {
 struct Options {
     int zero_skip, k_skip, fused_wavelet, screen, screen8;
     int pair;  // the fp8 screening pass runs on CTA pairs (cta_group::2)
+    int wavelet_vec4;  // fused wavelet kernels with four samples per thread (bit-identical to the scalar ones)
 };
 Options& options();
 

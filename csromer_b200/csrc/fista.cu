@@ -29,21 +29,15 @@ int launch_block_flags(const float* z, int ld, int cols, int P, unsigned char* f
                        unsigned int* tile_flags, cudaStream_t stream);
 int wavelet_ld(const csr_wavelet* w);
 bool wavelet_fusable(const csr_wavelet* w);
-struct CoefUpdate {
-    float* x;
-    float* z;
-    const float* lambda0;
-    const float* noise;
-    const int* iter_cap;
-    int iter;
-    float step, beta;
-    float* delta;
-};
 int swt_synth_fused(const csr_wavelet* w, const float* coef, int ld_coef, float* sig, int ld_sig, __half* hi,
                     __half* lo, int ld_h, const float* scale, int P, unsigned int* tile_flags, int flag_ld,
-                    cudaStream_t stream);
+                    const unsigned char* coef_flags, int coef_flag_ld, cudaStream_t stream);
 int swt_analysis_fused(const csr_wavelet* w, const float* signal, int ld_sig, float* coef, int ld_coef, int P,
                        const CoefUpdate* update, cudaStream_t stream);
+int coef_flag_ld(const csr_wavelet* w);
+bool coef_flags_usable(const csr_wavelet* w, const float* x, const float* z, int ld_coef);
+int launch_coef_flags(const csr_wavelet* w, const float* z, int ld_coef, int P, unsigned char* flags, int flag_ld,
+                      cudaStream_t stream);
 int wavelet_decompose(const csr_wavelet* w, const float* signal, int ld_sig, float* coef, int ld_coef, int P,
                       float* ws, cudaStream_t stream);
 int wavelet_reconstruct(const csr_wavelet* w, const float* coef, int ld_coef, float* signal, int ld_sig, int P,
@@ -88,6 +82,7 @@ struct FistaWs {
     int* tile_list2;
     unsigned char* r8;  // fp8 copy of the residual operand for the first screening pass
     unsigned long long* mma_count;  // [4]: tensor-core blocks issued by the in-loop GEMMs (3-product, fp16 screen, fp8 screen)
+    unsigned char* coef_flags[2];   // wavelet bases: coefficient-state flags (ping-pong), pitch coef_flag_ld(wav)
     size_t bytes;
 };
 static FistaWs carve_fista(const csr_plan* plan, const csr_wavelet* wav, int P, void* ws) {
@@ -115,10 +110,13 @@ static FistaWs carve_fista(const csr_plan* plan, const csr_wavelet* wav, int P, 
     f.r8 = b.take<unsigned char>((size_t)P * plan->ld8);
     f.mma_count = b.take<unsigned long long>(4);
     f.sig = f.gcoef = f.wav_ws = nullptr;
+    f.coef_flags[0] = f.coef_flags[1] = nullptr;
     if (wav) {
         f.sig = b.take<float>((size_t)P * plan->ld2n);
         f.gcoef = b.take<float>((size_t)P * ldc);
         f.wav_ws = b.take<float>((size_t)2 * P * wavelet_ld(wav));
+        f.coef_flags[0] = b.take<unsigned char>((size_t)P * coef_flag_ld(wav));
+        f.coef_flags[1] = b.take<unsigned char>((size_t)P * coef_flag_ld(wav));
     }
     f.bytes = b.off;
     return f;
@@ -246,6 +244,12 @@ extern "C" int csr_fista(csr_plan* plan, csr_wavelet* wav, const csr_fista_args*
 
     const bool fused_wavelet = wav && wavelet_fusable(wav) && options().fused_wavelet != 0;
     const bool wav_kskip = fused_wavelet && k_skip && 2 * n <= kMaxSkipK;
+    // coefficient-state flags: blocks of 512 coefficients whose x and z are identically zero need no state traffic in
+    // the update kernel and no scan in the synthesis kernel (exact)
+    const bool wav_flags = fused_wavelet && zero_skip && coef_flags_usable(wav, x, w.z, ldc);
+    const int cfl_ld = wav ? coef_flag_ld(wav) : 0;
+    int cfl_cur = 0;
+    if (wav_flags && (rc = launch_coef_flags(wav, w.z, ldc, P, w.coef_flags[0], cfl_ld, stream))) return rc;
 
     // 4. iterations
     double t = 1.0;
@@ -261,7 +265,8 @@ extern "C" int csr_fista(csr_plan* plan, csr_wavelet* wav, const csr_fista_args*
                 if (wav_kskip)
                     CSR_CUDA(cudaMemsetAsync(w.tile_flags, 0, sizeof(unsigned int) * (size_t)((P + BM - 1) / BM) * w.flag_ld, stream));
                 if ((rc = swt_synth_fused(wav, w.z, ldc, nullptr, 0, w.z_hi, w.z_lo, ld2n, w.zscale, P,
-                                          wav_kskip ? w.tile_flags : nullptr, w.flag_ld, stream)))
+                                          wav_kskip ? w.tile_flags : nullptr, w.flag_ld,
+                                          wav_flags ? w.coef_flags[cfl_cur] : nullptr, cfl_ld, stream)))
                     return rc;
             } else {
                 if ((rc = wavelet_reconstruct(wav, w.z, ldc, w.sig, ld2n, P, w.wav_ws, stream))) return rc;
@@ -356,7 +361,15 @@ extern "C" int csr_fista(csr_plan* plan, csr_wavelet* wav, const csr_fista_args*
             e.out = w.sig;  // gradient in phi space
             if ((rc = launch_dft_gemm(plan, true, w.r_hi, w.r_lo, P, e, stream))) return rc;
             if (fused_wavelet) {  // analysis of all levels + threshold + momentum in one kernel
-                CoefUpdate up = {x, w.z, a.lambda0, a.noise, a.iter_cap, it, a.step, beta, (last && a.delta) ? a.delta : nullptr};
+                CoefUpdate up = {x, w.z, a.lambda0, a.noise, a.iter_cap, it, a.step, beta, (last && a.delta) ? a.delta : nullptr,
+                                 nullptr, nullptr, 0};
+                if (wav_flags) {
+                    CSR_CUDA(cudaMemsetAsync(w.coef_flags[cfl_cur ^ 1], 0, (size_t)P * cfl_ld, stream));
+                    up.flags_in = w.coef_flags[cfl_cur];
+                    up.flags_out = w.coef_flags[cfl_cur ^ 1];
+                    up.flag_ld = cfl_ld;
+                    cfl_cur ^= 1;
+                }
                 if ((rc = swt_analysis_fused(wav, w.sig, ld2n, nullptr, ldc, P, &up, stream))) return rc;
             } else {
                 if ((rc = wavelet_decompose(wav, w.sig, ld2n, w.gcoef, ldc, P, w.wav_ws, stream))) return rc;

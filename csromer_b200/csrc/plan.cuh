@@ -90,6 +90,25 @@ struct GemmEpilogue {
     int debug;                 // measurement aid (CSR_DEBUG_EPI): bit 0 skips epilogue loads, bit 1 skips stores
 };
 
+// FISTA update applied to each wavelet coefficient as its gradient value is produced (wavelet.cu; may be disabled)
+struct CoefUpdate {
+    float* x;
+    float* z;
+    const float* lambda0;
+    const float* noise;
+    const int* iter_cap;
+    int iter;
+    float step, beta;
+    float* delta;
+    // coefficient-state flags (exact shortcut): byte [p, band * nb + (sample >> kCoefBlockShift)] = 0 means "x and z are
+    // identically zero in this block" -- no state loads, and no stores while the new values are zero again
+    const unsigned char* flags_in;
+    unsigned char* flags_out;  // zeroed by the caller; set to 1 where non-zero values were written
+    int flag_ld;
+};
+constexpr int kCoefBlockShift = 9;  // 512 coefficients per flag
+constexpr int kCoefFlagBands = 16;  // fused kernels keep the flags of at most this many bands in shared memory
+
 int make_operand_map(CUtensorMap* map, const void* base, int rows, int cols, int ld, int box_rows, int elem_bytes = 2);
 int launch_dft_gemm(const csr_plan* plan, bool adjoint, const __half* a_hi, const __half* a_lo, int P,
                     const GemmEpilogue& epi, cudaStream_t stream);

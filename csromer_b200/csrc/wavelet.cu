@@ -314,17 +314,6 @@ swt_synth_fused_kernel(const float* __restrict__ coef, int ld_coef, int N, int L
     }
 }
 
-struct CoefUpdate {  // FISTA update applied to each coefficient as its gradient value is produced (may be disabled)
-    float* x;
-    float* z;
-    const float* lambda0;
-    const float* noise;
-    const int* iter_cap;
-    int iter;
-    float step, beta;
-    float* delta;
-};
-
 // one analysis level over the whole buffer, filter length fixed at compile time (the dispatch happens once per level,
 // not per element).  d-band results are written (UPDATE = false) or consumed by the FISTA update (UPDATE = true).
 template <int FLEN, bool UPDATE>
@@ -423,6 +412,365 @@ swt_analysis_fused_kernel(const float* __restrict__ signal, int ld_sig, int N, i
     }
 }
 
+// ---- the same two kernels, four consecutive samples per thread ------------------------------------------------
+// The one-sample-per-thread kernels above are bound by shared-memory load issue (F loads per output and level) and
+// by memory-level parallelism (two 4-byte state loads in flight per thread).  Here a thread owns four consecutive
+// samples: an a-trous level with step % 4 == 0 needs one 16-byte shared load per tap for all four outputs, steps 1
+// and 2 read one aligned register window (5 / 7 vectors for F = 12) that covers every tap of the four outputs, and the
+// coefficient state moves as 16-byte global accesses.  Every output is still accumulated tap by tap in ascending t,
+// so results are bit-identical to the scalar kernels.  Requirements: N % 4 == 0, pitches % 4 == 0, 16-byte aligned
+// bases, F in the unrolled set; anything else runs the scalar kernels.  All rims are rounded up to multiples of four
+// (halo H4 = sum over levels of round_up(step F/2, 4)).
+constexpr int WAV4_THREADS = 256;
+
+__host__ __device__ constexpr int round_up4(int v) { return (v + 3) & ~3; }
+
+static int fused_halo4(const csr_wavelet* w) {
+    int h = 0;
+    for (int lev = 1; lev <= w->levels; ++lev) h += round_up4((w->F / 2) << (lev - 1));
+    return h;
+}
+static FusedTiling fused_tiling4(const csr_wavelet* w, int nbuf) {
+    FusedTiling t;
+    t.H = fused_halo4(w);
+    const int bmax = WAV_SMEM_BUDGET / (4 * nbuf);
+    const int tmax = bmax - 2 * t.H;
+    if (tmax < 256) {
+        t.T = t.B = t.ntiles = 0;
+        return t;
+    }
+    t.ntiles = (w->N + tmax - 1) / tmax;
+    t.T = round_up((w->N + t.ntiles - 1) / t.ntiles, 32);
+    t.B = t.T + 2 * t.H;
+    return t;
+}
+static bool vec4_filter(int F) { return F == 2 || F == 4 || F == 6 || F == 8 || F == 12; }
+static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+// taps of four consecutive outputs i .. i+3.  OFF = (tap 0 position - output position) / step: F/2 for the analysis,
+// F/2 - 1 for the synthesis; tap t sits at  i + j + (OFF - t) step.  SMALL = step (1 or 2) or 0 for step % 4 == 0.
+template <int FLEN, int OFF, int SMALL, bool TWO>
+__device__ __forceinline__ void taps4(const float* __restrict__ a, int i, int step, const float (&f0)[64],
+                                      const float (&f1)[64], float (&c0)[4], float (&c1)[4]) {
+    if (SMALL == 0) {
+        const float* ap = a + i + OFF * step;
+#pragma unroll
+        for (int t = 0; t < FLEN; ++t) {
+            const float4 v = *reinterpret_cast<const float4*>(ap - t * step);
+            c0[0] = fmaf(f0[t], v.x, c0[0]);
+            c0[1] = fmaf(f0[t], v.y, c0[1]);
+            c0[2] = fmaf(f0[t], v.z, c0[2]);
+            c0[3] = fmaf(f0[t], v.w, c0[3]);
+            if (TWO) {
+                c1[0] = fmaf(f1[t], v.x, c1[0]);
+                c1[1] = fmaf(f1[t], v.y, c1[1]);
+                c1[2] = fmaf(f1[t], v.z, c1[2]);
+                c1[3] = fmaf(f1[t], v.w, c1[3]);
+            }
+        }
+    } else {
+        constexpr int LEFT = round_up4((FLEN - 1 - OFF) * SMALL);  // lowest tap: i + (OFF - (FLEN-1)) step
+        constexpr int RIGHT = round_up4(OFF * SMALL);              // highest tap: i + 3 + OFF step
+        constexpr int CNT = (LEFT + 4 + RIGHT) / 4;
+        float w[4 * CNT];
+#pragma unroll
+        for (int c = 0; c < CNT; ++c) {
+            const float4 v = *reinterpret_cast<const float4*>(a + i - LEFT + 4 * c);
+            w[4 * c] = v.x;
+            w[4 * c + 1] = v.y;
+            w[4 * c + 2] = v.z;
+            w[4 * c + 3] = v.w;
+        }
+#pragma unroll
+        for (int t = 0; t < FLEN; ++t) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float v = w[j + (OFF - t) * SMALL + LEFT];
+                c0[j] = fmaf(f0[t], v, c0[j]);
+                if (TWO) c1[j] = fmaf(f1[t], v, c1[j]);
+            }
+        }
+    }
+}
+
+__device__ __forceinline__ bool nonzero4(const float4& v) { return v.x != 0.f || v.y != 0.f || v.z != 0.f || v.w != 0.f; }
+
+__device__ __forceinline__ float soft_update(float zo, float xo, float g, float ustep, float thr, float beta, float& znew,
+                                             float& dsum) {
+    const float u = zo - ustep * g;
+    const float xn = copysignf(fmaxf(fabsf(u) - thr, 0.f), u);
+    znew = xn + beta * (xn - xo);
+    dsum += fabsf(xn - xo);
+    return xn;
+}
+
+// sfl: this band's state flags of the tile's blocks in shared memory (index (g >> kCoefBlockShift) - blk0), or null;
+// fout: this band's row of the flags being written, or null
+template <int FLEN, bool UPDATE, int SMALL>
+__device__ __forceinline__ void analysis_level4(const float* __restrict__ a, float* __restrict__ o, int B, int step, int H,
+                                                int T, int t0, int N, const FilterPair& f, float* __restrict__ cband,
+                                                float* __restrict__ xband, float* __restrict__ zband, float ustep,
+                                                float thr, float beta, float& dsum, const unsigned char* sfl, int blk0,
+                                                unsigned char* __restrict__ fout) {
+    const int rim = round_up4(step * (FLEN / 2));
+    const int vlo = H, vhi = min(H + T, H + (N - t0));
+    for (int i = rim + 4 * threadIdx.x; i < B - rim; i += 4 * WAV4_THREADS) {
+        const bool valid = i >= vlo && i < vhi;
+        const int g = t0 + (i - H);
+        float4 zo = make_float4(0.f, 0.f, 0.f, 0.f), xo = zo;
+        bool st = true;  // "the state may hold non-zeros here"
+        if (UPDATE && valid) {  // state loads in flight while the filters run
+            if (sfl) st = sfl[(g >> kCoefBlockShift) - blk0] != 0;
+            if (st) {
+                zo = __ldcg(reinterpret_cast<const float4*>(zband + g));
+                xo = __ldcg(reinterpret_cast<const float4*>(xband + g));
+            }
+        }
+        float ca[4] = {0.f, 0.f, 0.f, 0.f}, cd[4] = {0.f, 0.f, 0.f, 0.f};
+        taps4<FLEN, FLEN / 2, SMALL, true>(a, i, step, f.lo, f.hi, ca, cd);
+        *reinterpret_cast<float4*>(o + i) = make_float4(ca[0], ca[1], ca[2], ca[3]);
+        if (valid) {
+            if (UPDATE) {
+                float4 xn, zn;
+                xn.x = soft_update(zo.x, xo.x, cd[0], ustep, thr, beta, zn.x, dsum);
+                xn.y = soft_update(zo.y, xo.y, cd[1], ustep, thr, beta, zn.y, dsum);
+                xn.z = soft_update(zo.z, xo.z, cd[2], ustep, thr, beta, zn.z, dsum);
+                xn.w = soft_update(zo.w, xo.w, cd[3], ustep, thr, beta, zn.w, dsum);
+                const bool nzr = nonzero4(xn) || nonzero4(zn);
+                if (st || nzr) {  // a zero block whose new values are zero again keeps its (zero) memory
+                    __stcs(reinterpret_cast<float4*>(xband + g), xn);
+                    __stcs(reinterpret_cast<float4*>(zband + g), zn);
+                }
+                if (nzr && fout) fout[g >> kCoefBlockShift] = 1;
+            } else {
+                *reinterpret_cast<float4*>(cband + g) = make_float4(cd[0], cd[1], cd[2], cd[3]);
+            }
+        }
+    }
+}
+
+template <int FLEN, bool UPDATE>
+__global__ void __launch_bounds__(WAV4_THREADS, 3)
+swt_analysis_fused4_kernel(const float* __restrict__ signal, int ld_sig, int N, int L, int H, int T, int B,
+                           const BandOffsets bands, const FilterPair f, float* __restrict__ coef, int ld_coef,
+                           const CoefUpdate up) {
+    extern __shared__ __align__(16) float wsm4[];
+    constexpr int MAXBLK = WAV_SMEM_BUDGET / 8 / (1 << kCoefBlockShift) + 3;  // flag blocks a tile can touch
+    __shared__ unsigned char sflags[UPDATE ? kCoefFlagBands * MAXBLK : 1];
+    float* a = wsm4;
+    float* o = wsm4 + B;
+    const int p = blockIdx.x;
+    const int t0 = blockIdx.y * T;
+    const int base = t0 - H;
+    const int NB = (N + (1 << kCoefBlockShift) - 1) >> kCoefBlockShift;
+    const int blk0 = t0 >> kCoefBlockShift;
+    const int nblk = min(NB - 1, (t0 + T - 1) >> kCoefBlockShift) - blk0 + 1;
+    const bool use_flags = UPDATE && up.flags_in != nullptr;
+    float thr = 0.f;
+    if (UPDATE) {
+        const float l0 = up.lambda0[p], nz = up.noise[p];
+        const float lam = l0 - (float)up.iter * nz;
+        const bool active = (nz < l0) && (up.iter == 0 || lam > 0.f) && (!up.iter_cap || up.iter < up.iter_cap[p]);
+        thr = up.step * lam;
+        if (!active) {  // whole CTA: this line of sight is frozen; its state flags carry over
+            if (use_flags) {
+                for (int idx = threadIdx.x; idx < (L + 1) * nblk; idx += WAV4_THREADS) {
+                    const size_t at = (size_t)p * up.flag_ld + (idx / nblk) * NB + blk0 + idx % nblk;
+                    if (up.flags_in[at]) up.flags_out[at] = 1;
+                }
+            }
+            return;
+        }
+        if (use_flags) {
+            for (int idx = threadIdx.x; idx < (L + 1) * nblk; idx += WAV4_THREADS)
+                sflags[(idx / nblk) * MAXBLK + idx % nblk] = up.flags_in[(size_t)p * up.flag_ld + (idx / nblk) * NB + blk0 + idx % nblk];
+        }
+    }
+    const float* srow = signal + (size_t)p * ld_sig;
+    for (int i = 4 * threadIdx.x; i < B; i += 4 * WAV4_THREADS)
+        *reinterpret_cast<float4*>(a + i) = *reinterpret_cast<const float4*>(srow + wrap_index(base + i, N));
+    __syncthreads();
+    const size_t crow = (size_t)p * ld_coef;
+    float dsum = 0.f;
+    for (int lev = 1; lev <= L; ++lev) {
+        const int step = 1 << (lev - 1);
+        const int bi = L - lev + 1;
+        const int band = bands.off[bi];
+        float* cband = UPDATE ? nullptr : coef + crow + band;
+        float* xband = UPDATE ? up.x + crow + band : nullptr;
+        float* zband = UPDATE ? up.z + crow + band : nullptr;
+        const unsigned char* sfl = use_flags ? sflags + bi * MAXBLK : nullptr;
+        unsigned char* fout = use_flags ? up.flags_out + (size_t)p * up.flag_ld + bi * NB : nullptr;
+        if (lev == 1)
+            analysis_level4<FLEN, UPDATE, 1>(a, o, B, step, H, T, t0, N, f, cband, xband, zband, up.step, thr, up.beta, dsum, sfl, blk0, fout);
+        else if (lev == 2)
+            analysis_level4<FLEN, UPDATE, 2>(a, o, B, step, H, T, t0, N, f, cband, xband, zband, up.step, thr, up.beta, dsum, sfl, blk0, fout);
+        else
+            analysis_level4<FLEN, UPDATE, 0>(a, o, B, step, H, T, t0, N, f, cband, xband, zband, up.step, thr, up.beta, dsum, sfl, blk0, fout);
+        __syncthreads();
+        float* tmp = a;
+        a = o;
+        o = tmp;
+    }
+    const int vhi = min(H + T, H + (N - t0));
+    for (int i = H + 4 * threadIdx.x; i < vhi; i += 4 * WAV4_THREADS) {  // approximation band cA_L
+        const int g = t0 + (i - H);
+        const float4 ca = *reinterpret_cast<const float4*>(a + i);
+        if (UPDATE) {
+            float* zb = up.z + crow + bands.off[0] + g;
+            float* xb = up.x + crow + bands.off[0] + g;
+            const bool st = use_flags ? sflags[(g >> kCoefBlockShift) - blk0] != 0 : true;
+            float4 zo = make_float4(0.f, 0.f, 0.f, 0.f), xo = zo;
+            if (st) {
+                zo = __ldcg(reinterpret_cast<const float4*>(zb));
+                xo = __ldcg(reinterpret_cast<const float4*>(xb));
+            }
+            float4 xn, zn;
+            xn.x = soft_update(zo.x, xo.x, ca.x, up.step, thr, up.beta, zn.x, dsum);
+            xn.y = soft_update(zo.y, xo.y, ca.y, up.step, thr, up.beta, zn.y, dsum);
+            xn.z = soft_update(zo.z, xo.z, ca.z, up.step, thr, up.beta, zn.z, dsum);
+            xn.w = soft_update(zo.w, xo.w, ca.w, up.step, thr, up.beta, zn.w, dsum);
+            const bool nzr = nonzero4(xn) || nonzero4(zn);
+            if (st || nzr) {
+                __stcs(reinterpret_cast<float4*>(xb), xn);
+                __stcs(reinterpret_cast<float4*>(zb), zn);
+            }
+            if (nzr && use_flags) up.flags_out[(size_t)p * up.flag_ld + (g >> kCoefBlockShift)] = 1;
+        } else {
+            *reinterpret_cast<float4*>(coef + crow + bands.off[0] + g) = ca;
+        }
+    }
+    if (UPDATE && up.delta != nullptr) {
+#pragma unroll
+        for (int sft = 16; sft > 0; sft >>= 1) dsum += __shfl_xor_sync(0xffffffffu, dsum, sft);
+        if ((threadIdx.x & 31) == 0 && dsum != 0.f) atomicAdd(up.delta + p, dsum);
+    }
+}
+
+// state flags of a coefficient matrix: byte [p, band * NB + k] = "block k of band `band` holds a non-zero"
+__global__ void coef_flags_kernel(const float* __restrict__ z, int ld_coef, int N, int NB, const BandOffsets bands,
+                                  unsigned char* __restrict__ flags, int flag_ld) {
+    const int p = blockIdx.x, band = blockIdx.y / NB, k = blockIdx.y % NB;
+    const int s0 = k << kCoefBlockShift, s1 = min(N, s0 + (1 << kCoefBlockShift));
+    const float* row = z + (size_t)p * ld_coef + bands.off[band];
+    int nz = 0;
+    for (int i = s0 + 4 * threadIdx.x; i < s1; i += 4 * blockDim.x) nz |= nonzero4(*reinterpret_cast<const float4*>(row + i));
+    nz = __syncthreads_or(nz);
+    if (threadIdx.x == 0) flags[(size_t)p * flag_ld + band * NB + k] = nz ? 1 : 0;
+}
+
+template <int FLEN, int SMALL, bool USE_A, bool USE_D>
+__device__ __forceinline__ void synth_level4(const float* __restrict__ a, const float* __restrict__ d,
+                                             float* __restrict__ o, int B, int step, const FilterPair& f) {
+    const int rim = round_up4(step * (FLEN / 2));
+    for (int i = rim + 4 * threadIdx.x; i < B - rim; i += 4 * WAV4_THREADS) {
+        float acc0[4] = {0.f, 0.f, 0.f, 0.f}, acc1[4] = {0.f, 0.f, 0.f, 0.f};
+        if (USE_A) taps4<FLEN, FLEN / 2 - 1, SMALL, false>(a, i, step, f.lo, f.lo, acc0, acc0);
+        if (USE_D) taps4<FLEN, FLEN / 2 - 1, SMALL, false>(d, i, step, f.hi, f.hi, acc1, acc1);
+        *reinterpret_cast<float4*>(o + i) = make_float4(0.5f * (acc0[0] + acc1[0]), 0.5f * (acc0[1] + acc1[1]),
+                                                        0.5f * (acc0[2] + acc1[2]), 0.5f * (acc0[3] + acc1[3]));
+    }
+}
+
+template <int FLEN, int SMALL>
+__device__ __forceinline__ void synth_level4_any(const float* a, const float* d, float* o, int B, int step,
+                                                 const FilterPair& f, bool a_nz, bool d_nz) {
+    if (a_nz && d_nz) synth_level4<FLEN, SMALL, true, true>(a, d, o, B, step, f);
+    else if (a_nz) synth_level4<FLEN, SMALL, true, false>(a, d, o, B, step, f);
+    else synth_level4<FLEN, SMALL, false, true>(a, d, o, B, step, f);
+}
+
+template <int FLEN>
+__global__ void __launch_bounds__(WAV4_THREADS, 3)
+swt_synth_fused4_kernel(const float* __restrict__ coef, int ld_coef, int N, int L, int H, int T, int B,
+                        const BandOffsets bands, const FilterPair f, float* __restrict__ sig, int ld_sig,
+                        __half* __restrict__ hi, __half* __restrict__ lo, int ld_h, const float* __restrict__ scale,
+                        unsigned char* __restrict__ tile_flags, int flag_ld, const unsigned char* __restrict__ cflags,
+                        int cflag_ld) {
+    extern __shared__ __align__(16) float wsm4[];
+    float* a = wsm4;
+    float* o = wsm4 + B;
+    float* d = wsm4 + 2 * B;
+    const int p = blockIdx.x;
+    const int t0 = blockIdx.y * T;
+    const int base = t0 - H;
+    const float* crow = coef + (size_t)p * ld_coef;
+    // which band tiles hold anything: from the coefficient-state flags when the caller maintains them (a zero flag
+    // guarantees zeros; a set flag over zeros only costs work), else by one pass of independent 16-byte loads
+    __shared__ unsigned int band_nz_s;
+    if (threadIdx.x == 0) band_nz_s = 0u;
+    __syncthreads();
+    if (cflags != nullptr) {
+        const int NB = (N + (1 << kCoefBlockShift) - 1) >> kCoefBlockShift;
+        const int ws = wrap_index(base, N);  // the buffer covers [ws, ws + B) modulo N
+        unsigned int mine = 0u;
+        for (int idx = threadIdx.x; idx < (L + 1) * NB; idx += WAV4_THREADS) {
+            const int b = idx / NB, k = idx - b * NB;
+            const int bs = k << kCoefBlockShift, be = min(N, bs + (1 << kCoefBlockShift));
+            const bool ov = B >= N || (ws + B <= N ? (bs < ws + B && be > ws) : (be > ws || bs < ws + B - N));
+            if (ov && cflags[(size_t)p * cflag_ld + idx]) mine |= 1u << b;
+        }
+        mine = __reduce_or_sync(0xffffffffu, mine);
+        if ((threadIdx.x & 31) == 0 && mine) atomicOr(&band_nz_s, mine);
+    } else {
+        unsigned int mine = 0u;
+        for (int i = 4 * threadIdx.x; i < B; i += 4 * WAV4_THREADS) {
+            const int gi = wrap_index(base + i, N);
+            for (int b = 0; b <= L; ++b) {
+                const float4 v = __ldg(reinterpret_cast<const float4*>(crow + bands.off[b] + gi));
+                mine |= nonzero4(v) ? (1u << b) : 0u;
+            }
+        }
+        mine = __reduce_or_sync(0xffffffffu, mine);
+        if ((threadIdx.x & 31) == 0 && mine) atomicOr(&band_nz_s, mine);
+    }
+    __syncthreads();
+    const unsigned int band_nz = band_nz_s;
+    bool a_nz = (band_nz & 1u) != 0;
+    if (a_nz) {
+        for (int i = 4 * threadIdx.x; i < B; i += 4 * WAV4_THREADS)
+            *reinterpret_cast<float4*>(a + i) = __ldg(reinterpret_cast<const float4*>(crow + bands.off[0] + wrap_index(base + i, N)));
+    }
+    for (int lev = L; lev >= 1; --lev) {
+        const int step = 1 << (lev - 1);
+        const float* dband = crow + bands.off[L - lev + 1];
+        const bool d_nz = ((band_nz >> (L - lev + 1)) & 1u) != 0;
+        if (d_nz) {
+            for (int i = 4 * threadIdx.x; i < B; i += 4 * WAV4_THREADS)
+                *reinterpret_cast<float4*>(d + i) = __ldg(reinterpret_cast<const float4*>(dband + wrap_index(base + i, N)));
+        }
+        if (a_nz || d_nz) __syncthreads();
+        if (!a_nz && !d_nz) continue;
+        if (lev == 1) synth_level4_any<FLEN, 1>(a, d, o, B, step, f, a_nz, d_nz);
+        else if (lev == 2) synth_level4_any<FLEN, 2>(a, d, o, B, step, f, a_nz, d_nz);
+        else synth_level4_any<FLEN, 0>(a, d, o, B, step, f, a_nz, d_nz);
+        a_nz = true;
+        __syncthreads();
+        float* tmp = a;
+        a = o;
+        o = tmp;
+    }
+    const float sc = scale ? scale[p] : 1.f;
+    const int vhi = min(H + T, H + (N - t0));
+    for (int i = H + 4 * threadIdx.x; i < vhi; i += 4 * WAV4_THREADS) {
+        const int g = t0 + (i - H);
+        const float4 v = a_nz ? *reinterpret_cast<const float4*>(a + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+        if (sig) *reinterpret_cast<float4*>(sig + (size_t)p * ld_sig + g) = v;
+        if (hi) {
+            __align__(8) __half h[4];
+            __align__(8) __half l[4];
+            split_half(v.x * sc, h[0], l[0]);
+            split_half(v.y * sc, h[1], l[1]);
+            split_half(v.z * sc, h[2], l[2]);
+            split_half(v.w * sc, h[3], l[3]);
+            *reinterpret_cast<uint2*>(hi + (size_t)p * ld_h + g) = *reinterpret_cast<const uint2*>(h);
+            *reinterpret_cast<uint2*>(lo + (size_t)p * ld_h + g) = *reinterpret_cast<const uint2*>(l);
+            if (tile_flags && (v.x != 0.f || v.y != 0.f || v.z != 0.f || v.w != 0.f))
+                tile_flags[((size_t)(p >> 7) * flag_ld + (g >> 7)) * 4 + ((p >> 5) & 3)] = 1;
+        }
+    }
+}
+
 static BandOffsets band_offsets(const csr_wavelet* w) {
     BandOffsets b;
     memset(&b, 0, sizeof(b));
@@ -439,22 +787,65 @@ static int set_wavelet_smem(K kernel, int bytes) {
 bool profile_start(cudaStream_t stream, cudaEvent_t* start, cudaEvent_t* stop);
 void profile_stop(int kind, cudaStream_t stream, cudaEvent_t start, cudaEvent_t stop);
 
+int coef_flag_ld(const csr_wavelet* w) {
+    const int NB = (w->N + (1 << kCoefBlockShift) - 1) >> kCoefBlockShift;
+    return round_up((w->levels + 1) * NB, 16);
+}
+// the fused loop may keep coefficient-state flags iff both fused kernels will run their four-sample versions
+bool coef_flags_usable(const csr_wavelet* w, const float* x, const float* z, int ld_coef) {
+    return options().wavelet_vec4 != 0 && wavelet_fusable(w) && vec4_filter(w->F) && fused_tiling4(w, 3).T > 0 &&
+           fused_tiling4(w, 2).T > 0 && w->N % 4 == 0 && ld_coef % 4 == 0 && aligned16(x) && aligned16(z) &&
+           w->levels + 1 <= kCoefFlagBands;
+}
+int launch_coef_flags(const csr_wavelet* w, const float* z, int ld_coef, int P, unsigned char* flags, int flag_ld,
+                      cudaStream_t stream) {
+    const int NB = (w->N + (1 << kCoefBlockShift) - 1) >> kCoefBlockShift;
+    coef_flags_kernel<<<dim3(P, (w->levels + 1) * NB), 128, 0, stream>>>(z, ld_coef, w->N, NB, band_offsets(w), flags, flag_ld);
+    CSR_LAUNCHED();
+    return CSR_OK;
+}
+
+#define CSR_DISPATCH_FLEN4(FVAL, CALL) \
+    switch (FVAL) {                    \
+        case 2: { constexpr int FL = 2; CALL; } break;   \
+        case 4: { constexpr int FL = 4; CALL; } break;   \
+        case 6: { constexpr int FL = 6; CALL; } break;   \
+        case 8: { constexpr int FL = 8; CALL; } break;   \
+        default: { constexpr int FL = 12; CALL; } break; \
+    }
+
 int swt_synth_fused(const csr_wavelet* w, const float* coef, int ld_coef, float* sig, int ld_sig, __half* hi,
                     __half* lo, int ld_h, const float* scale, int P, unsigned int* tile_flags, int flag_ld,
-                    cudaStream_t stream) {
-    const FusedTiling t = fused_tiling(w, 3);
+                    const unsigned char* coef_flags, int coef_flag_ld, cudaStream_t stream) {
+    const FusedTiling t4 = fused_tiling4(w, 3);
+    const bool vec4 = options().wavelet_vec4 != 0 && vec4_filter(w->F) && t4.T > 0 && w->N % 4 == 0 && ld_coef % 4 == 0 &&
+                      aligned16(coef) && (!sig || (ld_sig % 4 == 0 && aligned16(sig))) &&
+                      (!hi || (ld_h % 4 == 0 && ((uintptr_t)hi & 7) == 0 && ((uintptr_t)lo & 7) == 0));
+    const FusedTiling t = vec4 ? t4 : fused_tiling(w, 3);
     const int smem = 3 * t.B * 4;
+    CSR_REQUIRE(vec4 || coef_flags == nullptr, "swt_synth_fused: coefficient flags need the four-sample kernels");
     static bool configured = false;
     if (!configured) {
         int rc = set_wavelet_smem(swt_synth_fused_kernel, WAV_SMEM_BUDGET + 1024);
+        CSR_DISPATCH_FLEN4(2, if (!rc) rc = set_wavelet_smem(swt_synth_fused4_kernel<FL>, WAV_SMEM_BUDGET + 1024))
+        CSR_DISPATCH_FLEN4(4, if (!rc) rc = set_wavelet_smem(swt_synth_fused4_kernel<FL>, WAV_SMEM_BUDGET + 1024))
+        CSR_DISPATCH_FLEN4(6, if (!rc) rc = set_wavelet_smem(swt_synth_fused4_kernel<FL>, WAV_SMEM_BUDGET + 1024))
+        CSR_DISPATCH_FLEN4(8, if (!rc) rc = set_wavelet_smem(swt_synth_fused4_kernel<FL>, WAV_SMEM_BUDGET + 1024))
+        CSR_DISPATCH_FLEN4(12, if (!rc) rc = set_wavelet_smem(swt_synth_fused4_kernel<FL>, WAV_SMEM_BUDGET + 1024))
         if (rc) return rc;
         configured = true;
     }
     cudaEvent_t ev0, ev1;
     const bool prof = profile_start(stream, &ev0, &ev1);
-    swt_synth_fused_kernel<<<dim3(P, t.ntiles), WAV_THREADS, smem, stream>>>(
-        coef, ld_coef, w->N, w->levels, t.H, t.T, t.B, band_offsets(w), make_pair(w->rec_lo, w->rec_hi, w->F), sig, ld_sig,
-        hi, lo, ld_h, scale, reinterpret_cast<unsigned char*>(tile_flags), flag_ld);
+    if (vec4) {
+        CSR_DISPATCH_FLEN4(w->F, (swt_synth_fused4_kernel<FL><<<dim3(P, t.ntiles), WAV4_THREADS, smem, stream>>>(
+            coef, ld_coef, w->N, w->levels, t.H, t.T, t.B, band_offsets(w), make_pair(w->rec_lo, w->rec_hi, w->F), sig, ld_sig,
+            hi, lo, ld_h, scale, reinterpret_cast<unsigned char*>(tile_flags), flag_ld, coef_flags, coef_flag_ld)))
+    } else {
+        swt_synth_fused_kernel<<<dim3(P, t.ntiles), WAV_THREADS, smem, stream>>>(
+            coef, ld_coef, w->N, w->levels, t.H, t.T, t.B, band_offsets(w), make_pair(w->rec_lo, w->rec_hi, w->F), sig, ld_sig,
+            hi, lo, ld_h, scale, reinterpret_cast<unsigned char*>(tile_flags), flag_ld);
+    }
     CSR_LAUNCHED();
     if (prof) profile_stop(6, stream, ev0, ev1);
     return CSR_OK;
@@ -462,12 +853,22 @@ int swt_synth_fused(const csr_wavelet* w, const float* coef, int ld_coef, float*
 
 int swt_analysis_fused(const csr_wavelet* w, const float* signal, int ld_sig, float* coef, int ld_coef, int P,
                        const CoefUpdate* update, cudaStream_t stream) {
-    const FusedTiling t = fused_tiling(w, 2);
+    const FusedTiling t4 = fused_tiling4(w, 2);
+    const bool vec4 = options().wavelet_vec4 != 0 && vec4_filter(w->F) && t4.T > 0 && w->N % 4 == 0 && ld_coef % 4 == 0 &&
+                      ld_sig % 4 == 0 && aligned16(signal) &&
+                      (update ? (aligned16(update->x) && aligned16(update->z)) : aligned16(coef));
+    const FusedTiling t = vec4 ? t4 : fused_tiling(w, 2);
     const int smem = 2 * t.B * 4;
+    CSR_REQUIRE(vec4 || !update || update->flags_in == nullptr, "swt_analysis_fused: coefficient flags need the four-sample kernels");
     static bool configured = false;
     if (!configured) {
         int rc = set_wavelet_smem(swt_analysis_fused_kernel<true>, WAV_SMEM_BUDGET + 1024);
         if (!rc) rc = set_wavelet_smem(swt_analysis_fused_kernel<false>, WAV_SMEM_BUDGET + 1024);
+#define CSR_SET4(FV)                                                                                                   \
+    CSR_DISPATCH_FLEN4(FV, if (!rc) rc = set_wavelet_smem(swt_analysis_fused4_kernel<FL, true>, WAV_SMEM_BUDGET + 1024);  \
+                       if (!rc) rc = set_wavelet_smem(swt_analysis_fused4_kernel<FL, false>, WAV_SMEM_BUDGET + 1024))
+        CSR_SET4(2) CSR_SET4(4) CSR_SET4(6) CSR_SET4(8) CSR_SET4(12)
+#undef CSR_SET4
         if (rc) return rc;
         configured = true;
     }
@@ -475,12 +876,20 @@ int swt_analysis_fused(const csr_wavelet* w, const float* signal, int ld_sig, fl
     const FilterPair f = make_pair(w->dec_lo, w->dec_hi, w->F);
     cudaEvent_t ev0, ev1;
     const bool prof = update && profile_start(stream, &ev0, &ev1);
-    if (update) {
+    CoefUpdate none;
+    memset(&none, 0, sizeof(none));
+    if (vec4) {
+        if (update) {
+            CSR_DISPATCH_FLEN4(w->F, (swt_analysis_fused4_kernel<FL, true><<<grid, WAV4_THREADS, smem, stream>>>(
+                signal, ld_sig, w->N, w->levels, t.H, t.T, t.B, band_offsets(w), f, coef, ld_coef, *update)))
+        } else {
+            CSR_DISPATCH_FLEN4(w->F, (swt_analysis_fused4_kernel<FL, false><<<grid, WAV4_THREADS, smem, stream>>>(
+                signal, ld_sig, w->N, w->levels, t.H, t.T, t.B, band_offsets(w), f, coef, ld_coef, none)))
+        }
+    } else if (update) {
         swt_analysis_fused_kernel<true><<<grid, WAV_THREADS, smem, stream>>>(signal, ld_sig, w->N, w->levels, t.H, t.T, t.B,
                                                                             band_offsets(w), f, coef, ld_coef, *update);
     } else {
-        CoefUpdate none;
-        memset(&none, 0, sizeof(none));
         swt_analysis_fused_kernel<false><<<grid, WAV_THREADS, smem, stream>>>(signal, ld_sig, w->N, w->levels, t.H, t.T, t.B,
                                                                              band_offsets(w), f, coef, ld_coef, none);
     }
@@ -541,7 +950,7 @@ int wavelet_decompose(const csr_wavelet* w, const float* signal, int ld_sig, flo
 int wavelet_reconstruct(const csr_wavelet* w, const float* coef, int ld_coef, float* signal, int ld_sig, int P,
                         float* ws, cudaStream_t stream) {
     if (wavelet_fusable(w) && options().fused_wavelet != 0)
-        return swt_synth_fused(w, coef, ld_coef, signal, ld_sig, nullptr, nullptr, 0, nullptr, P, nullptr, 0, stream);
+        return swt_synth_fused(w, coef, ld_coef, signal, ld_sig, nullptr, nullptr, 0, nullptr, P, nullptr, 0, nullptr, 0, stream);
     const int N = w->N, L = w->levels;
     const int ldw = wavelet_ld(w);
     float* ping = ws;

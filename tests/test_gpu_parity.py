@@ -475,6 +475,48 @@ def test_wavelet_transforms(name, kind, N, level, norm, app):
         w.reconstruct(c[:-1])
 
 
+@pytest.mark.parametrize("name,N,level", [("db1", 4096, None), ("sym2", 3136, None), ("coif1", 3136, 4), ("db4", 15936, None),
+                                          ("coif2", 15936, None), ("coif2", 63936, None), ("coif2", 1032, 3)])
+def test_wavelet_vec4_kernels_are_bit_exact(name, N, level):
+    """the fused undecimated kernels with four samples per thread (16-byte shared / global accesses) accumulate every
+    output tap by tap like the one-sample kernels: same bits out, for the transforms and for a FISTA run"""
+    from csromer_b200 import _lib
+    rng = np.random.RandomState(11)
+    x = rng.normal(size=(N, 5)).astype(np.float32)
+    x[N // 3: N // 3 + N // 4, 1] = 0.0
+    out = []
+    try:
+        for vec4 in (1, 0):
+            _lib.set_option("wavelet_vec4", vec4)
+            w = cs.UndecimatedWavelet(wavelet_name=name, wavelet_level=level)
+            c = w.decompose(x)
+            c_sparse = np.where(np.abs(c) > 2.0, c, 0).astype(np.float32)  # mostly-zero band tiles (the skip paths)
+            out.append((np.array(c, copy=True), np.array(w.reconstruct(c), copy=True), np.array(w.reconstruct(c_sparse), copy=True)))
+    finally:
+        _lib.set_option("wavelet_vec4", 1)
+    for a, b in zip(out[0], out[1]):
+        np.testing.assert_array_equal(a, b)
+    o = ob.WaveletDict(name, kind="swt", level=level)
+    assert rel(out[0][0], o.decompose(x.astype(np.float64))) < 2e-6
+
+
+def test_wavelet_vec4_fista_is_bit_exact():
+    from csromer_b200 import _lib
+    src, par = make_batch(300, 70, seed=78, mixed=True)
+    results = []
+    try:
+        for vec4 in (1, 0):
+            _lib.set_option("wavelet_vec4", vec4)
+            wav = cs.UndecimatedWavelet(wavelet_name="coif2")
+            cost, X, l1, lam0, noise = run_fista(src, par, 25, wav=wav, step=1.0 / 2.8)
+            results.append((np.array(X.data, copy=True), np.array(cost, copy=True), np.array(src.model_data, copy=True)))
+    finally:
+        _lib.set_option("wavelet_vec4", 1)
+    assert 0 < np.count_nonzero(results[0][0]) < 0.2 * results[0][0].size
+    for a, b in zip(results[0], results[1]):
+        np.testing.assert_array_equal(a, b)
+
+
 def test_wavelet_complex_variants_and_errors():
     rng = np.random.RandomState(4)
     z = (rng.normal(size=256) + 1j * rng.normal(size=256)).astype(np.complex64)
