@@ -325,7 +325,7 @@ def run_ours(args):
     barrier()
     sampler.stop_flag = True
     launches = int(lib.csr_launch_count(0))
-    ms = (np.zeros(10, dtype=np.float64), np.zeros(10, dtype=np.int64))
+    ms = (np.zeros(12, dtype=np.float64), np.zeros(12, dtype=np.int64))
     lib.csr_profile(0)
     _lib.check(lib.csr_profile_collect(ms[0].ctypes.data_as(ctypes.POINTER(ctypes.c_double)),
                                        ms[1].ctypes.data_as(ctypes.POINTER(ctypes.c_longlong))), "csr_profile_collect")
@@ -398,7 +398,7 @@ def run_ours(args):
         t1.record()
         torch.cuda.synchronize()
         lib.csr_profile(0)
-        pm = (np.zeros(10, dtype=np.float64), np.zeros(10, dtype=np.int64))
+        pm = (np.zeros(12, dtype=np.float64), np.zeros(12, dtype=np.int64))
         _lib.check(lib.csr_profile_collect(pm[0].ctypes.data_as(ctypes.POINTER(ctypes.c_double)),
                                            pm[1].ctypes.data_as(ctypes.POINTER(ctypes.c_longlong))), "csr_profile_collect")
         return t0.elapsed_time(t1), pm, o

@@ -272,6 +272,7 @@ struct Options {
     int zero_skip, k_skip, fused_wavelet, screen, screen8;
     int pair;  // the fp8 screening pass runs on CTA pairs (cta_group::2)
     int wavelet_vec4;  // fused wavelet kernels with four samples per thread (bit-identical to the scalar ones)
+    int wavelet_screen;  // wavelet bases: one-product gradient + rigorous bound away from the active coefficients
 };
 Options& options();
 

@@ -361,12 +361,13 @@ dft_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
     constexpr bool F8 = (MODE == EPI_SCREEN8);
     constexpr int BKE = F8 ? 2 * BK : BK;  // K elements per block = one 128-byte swizzle row
     const int KB = (K + BKE - 1) / BKE;
-    constexpr int PRODUCTS = IS_SCREEN ? 1 : 3;
+    constexpr bool ONE = IS_SCREEN || MODE == EPI_PLAIN1;  // one product per K block
+    constexpr int PRODUCTS = ONE ? 1 : 3;
     // a one-product stage is half the size, so the same shared memory holds a ring twice as deep -- which is what
     // keeps enough bytes in flight to hide the L2 -> SM latency when a K block is only 4 MMAs long
-    constexpr int NSTAGES = IS_SCREEN ? MAX_STAGES : STAGES;
-    constexpr int STAGE_STRIDE = IS_SCREEN ? A_TILE_BYTES + B_TILE_BYTES : STAGE_BYTES;
-    constexpr int B_OFFSET = IS_SCREEN ? A_TILE_BYTES : 2 * A_TILE_BYTES;
+    constexpr int NSTAGES = ONE ? MAX_STAGES : STAGES;
+    constexpr int STAGE_STRIDE = ONE ? A_TILE_BYTES + B_TILE_BYTES : STAGE_BYTES;
+    constexpr int B_OFFSET = ONE ? A_TILE_BYTES : 2 * A_TILE_BYTES;
     int* last_listed = reinterpret_cast<int*>(smem + STAGES * STAGE_BYTES + 256 + NUM_WARPS_TOTAL * KMASK_WORDS * 4);
     uint32_t* my_mask = reinterpret_cast<uint32_t*>(smem + STAGES * STAGE_BYTES + 256) + warp * KMASK_WORDS;
     const bool skip = epi.a_kflags != nullptr;
@@ -535,7 +536,7 @@ dft_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
             }
             // slot 0: three-product launches, 1: fp16 screening, 2: fp8 screening
             if (lane == 0 && epi.mma_count != nullptr && issued != 0)
-                atomicAdd(epi.mma_count + (MODE == EPI_SCREEN ? 1 : (MODE == EPI_SCREEN8 ? 2 : 0)), issued);
+                atomicAdd(epi.mma_count + ((MODE == EPI_SCREEN || MODE == EPI_PLAIN1) ? 1 : (MODE == EPI_SCREEN8 ? 2 : 0)), issued);
         }
       }
     } else {
@@ -585,7 +586,7 @@ dft_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
                     if (lane == 0 && atomicMax(last_listed, ti) < ti) epi.out_list[atomicAdd(epi.out_count, 1)] = t;
                 }
             } else {
-                epilogue_tile<MODE>(epi, acc, lane, mt * BM + sub * 32, nt * BN + half * EPI_COLS);
+                epilogue_tile<MODE == EPI_PLAIN1 ? EPI_PLAIN : MODE>(epi, acc, lane, mt * BM + sub * 32, nt * BN + half * EPI_COLS);
             }
         }
     }
@@ -925,7 +926,7 @@ static int launch_mode(const csr_plan* plan, bool adjoint, const CUtensorMap& a_
     }
     ProfiledLaunch rec;
     if (g_profile) {
-        rec.kind = MODE == EPI_SCREEN ? 8 : (MODE == EPI_SCREEN8 ? 9 : MODE * 2 + (adjoint ? 1 : 0));
+        rec.kind = MODE == EPI_SCREEN ? 8 : (MODE == EPI_SCREEN8 ? 9 : (MODE == EPI_PLAIN1 ? 10 : MODE * 2 + (adjoint ? 1 : 0)));
         CSR_CUDA(pooled_event(&rec.start));
         CSR_CUDA(pooled_event(&rec.stop));
         CSR_CUDA(cudaEventRecord(rec.start, stream));
@@ -935,7 +936,7 @@ static int launch_mode(const csr_plan* plan, bool adjoint, const CUtensorMap& a_
         adjoint ? plan->map_adj_lo : plan->map_fwd_lo, pf0,
         pf1, num_prefetch, prefetch_lead, K, MT, NT,
         // screening needs no chunked accumulation: its bound covers the truncation of one long accumulation chain
-        (MODE == EPI_SCREEN || MODE == EPI_SCREEN8) ? (1 << 20) : gemm_chunk_kb(adjoint), epi);
+        (MODE == EPI_SCREEN || MODE == EPI_SCREEN8 || MODE == EPI_PLAIN1) ? (1 << 20) : gemm_chunk_kb(adjoint), epi);
     CSR_LAUNCHED();
     if (g_profile) {
         CSR_CUDA(cudaEventRecord(rec.stop, stream));
@@ -1001,6 +1002,9 @@ int launch_dft_gemm(const csr_plan* plan, bool adjoint, const __half* a_hi, cons
     if (rc) return rc;
     switch (epi.mode) {
         case EPI_PLAIN: return launch_mode<EPI_PLAIN>(plan, adjoint, ma_hi, ma_lo, P, epi, stream);
+        case EPI_PLAIN1:
+            CSR_REQUIRE(adjoint, "the one-product plain transform exists for the adjoint only");
+            return launch_mode<EPI_PLAIN1>(plan, adjoint, ma_hi, ma_lo, P, epi, stream);
         case EPI_RESID: return launch_mode<EPI_RESID>(plan, adjoint, ma_hi, ma_lo, P, epi, stream);
         case EPI_FISTA: return launch_mode<EPI_FISTA>(plan, adjoint, ma_hi, ma_lo, P, epi, stream);
         case EPI_SCREEN:
@@ -1014,6 +1018,74 @@ int launch_dft_gemm(const csr_plan* plan, bool adjoint, const __half* a_hi, cons
     return CSR_ERR_ARG;
 }
 
+
+// ---- helpers of the wavelet-domain screening (fista.cu) ------------------------------------------------------------
+// eps[p]: everything the two dropped products and the rounding of both evaluations can add to one output element of
+// row p (the bound of the fp16 screening above, + 0.1 S_p for the fp32 arithmetic downstream), in output units
+__global__ void screen_eps_kernel(const float* __restrict__ abs_sum, const float* __restrict__ a_scale, int K,
+                                  float* __restrict__ eps, int P) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p < P) eps[p] = (screen_slack(K) + 0.1f) * abs_sum[p] * (kTwiddleDescale / a_scale[p]) * 1.00001f;
+}
+int launch_screen_eps(const float* abs_sum, const float* a_scale, int K, float* eps, int P, cudaStream_t stream) {
+    screen_eps_kernel<<<(P + 255) / 256, 256, 0, stream>>>(abs_sum, a_scale, K, eps, P);
+    CSR_LAUNCHED();
+    return CSR_OK;
+}
+
+// one CTA walks the tiles in rasterised order and appends each to one of two lists (ordered compaction)
+__global__ void __launch_bounds__(1024)
+split_tile_lists_kernel(const unsigned char* __restrict__ need, const unsigned char* __restrict__ exclude, int MT, int NT,
+                        int* __restrict__ list_a, int* __restrict__ count_a, int* __restrict__ list_b,
+                        int* __restrict__ count_b) {
+    __shared__ int warp_a[32], warp_b[32];
+    __shared__ int base_a, base_b;
+    if (threadIdx.x == 0) base_a = base_b = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int t0 = 0; t0 < MT * NT; t0 += 1024) {
+        const int t = t0 + threadIdx.x;
+        bool a = false, b = false;
+        if (t < MT * NT) {
+            int mt, nt;
+            tile_coords(t, MT, NT, mt, nt);
+            a = need[(size_t)mt * NT + nt] != 0 && (exclude == nullptr || exclude[(size_t)mt * NT + nt] == 0);
+            b = !a && list_b != nullptr && (exclude == nullptr);
+        }
+        const unsigned ba = __ballot_sync(0xffffffffu, a), bb = __ballot_sync(0xffffffffu, b);
+        if (lane == 0) {
+            warp_a[warp] = __popc(ba);
+            warp_b[warp] = __popc(bb);
+        }
+        __syncthreads();
+        int oa = base_a, ob = base_b;
+        for (int w = 0; w < warp; ++w) {
+            oa += warp_a[w];
+            ob += warp_b[w];
+        }
+        if (a) list_a[oa + __popc(ba & ((1u << lane) - 1))] = t;
+        if (b) list_b[ob + __popc(bb & ((1u << lane) - 1))] = t;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            for (int w = 0; w < 32; ++w) {
+                base_a += warp_a[w];
+                base_b += warp_b[w];
+            }
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        *count_a = base_a;
+        if (count_b) *count_b = base_b;
+    }
+}
+int launch_split_tile_lists(const unsigned char* need, const unsigned char* exclude, int P, int N, int* list_a, int* count_a,
+                            int* list_b, int* count_b, cudaStream_t stream) {
+    const int MT = (P + BM - 1) / BM, NT = (N + BN - 1) / BN;
+    split_tile_lists_kernel<<<1, 1024, 0, stream>>>(need, exclude, MT, NT, list_a, count_a, list_b, count_b);
+    CSR_LAUNCHED();
+    return CSR_OK;
+}
 
 // fp8 screening on CTA pairs; `a8` is the fp8 copy of the residual operand ([P, ld8] bytes)
 int launch_screen8_pair(const csr_plan* plan, const unsigned char* a8, int P, const GemmEpilogue& epi_in, cudaStream_t stream) {
@@ -1072,7 +1144,8 @@ int launch_screen8_pair(const csr_plan* plan, const unsigned char* a8, int P, co
 using namespace csr;
 
 // kinds: 0 plain-forward, 1 plain-adjoint, 2 resid-forward, 3 resid-adjoint, 4 fista-forward, 5 fista-adjoint,
-//        6 fused wavelet synthesis, 7 fused wavelet analysis + update, 8 fp16 screening adjoint, 9 fp8 screening adjoint
+//        6 fused wavelet synthesis, 7 fused wavelet analysis + update, 8 fp16 screening adjoint, 9 fp8 screening adjoint,
+//        10 one-product plain adjoint (wavelet-domain screening), 11 wavelet analysis + update, redo pass
 extern "C" int csr_profile(int enable) {
     g_profile = enable != 0;
     if (g_profile) {  // create the events up front: cudaEventCreate inside a timed region is host time per launch

@@ -36,6 +36,9 @@ int swt_analysis_fused(const csr_wavelet* w, const float* signal, int ld_sig, fl
                        const CoefUpdate* update, cudaStream_t stream);
 int coef_flag_ld(const csr_wavelet* w);
 bool coef_flags_usable(const csr_wavelet* w, const float* x, const float* z, int ld_coef);
+int launch_need_from_flags(const csr_wavelet* w, const unsigned char* flags, int flag_ld, int P, unsigned char* need,
+                           int need_ld, cudaStream_t stream);
+void wavelet_band_l1(const csr_wavelet* w, float* l1);
 int launch_coef_flags(const csr_wavelet* w, const float* z, int ld_coef, int P, unsigned char* flags, int flag_ld,
                       cudaStream_t stream);
 int wavelet_decompose(const csr_wavelet* w, const float* signal, int ld_sig, float* coef, int ld_coef, int P,
@@ -83,6 +86,10 @@ struct FistaWs {
     unsigned char* r8;  // fp8 copy of the residual operand for the first screening pass
     unsigned long long* mma_count;  // [4]: tensor-core blocks issued by the in-loop GEMMs (3-product, fp16 screen, fp8 screen)
     unsigned char* coef_flags[2];   // wavelet bases: coefficient-state flags (ping-pong), pitch coef_flag_ld(wav)
+    unsigned char* redo_flags;      // wavelet-domain screening: blocks that failed the test in the speculative pass
+    unsigned char* need[2];         // adjoint tiles [MT, NT] that need the exact gradient (predicted / after the test)
+    int* tile_list3;
+    float* eps;                     // [P] error bound of the one-product gradient
     size_t bytes;
 };
 static FistaWs carve_fista(const csr_plan* plan, const csr_wavelet* wav, int P, void* ws) {
@@ -110,13 +117,21 @@ static FistaWs carve_fista(const csr_plan* plan, const csr_wavelet* wav, int P, 
     f.r8 = b.take<unsigned char>((size_t)P * plan->ld8);
     f.mma_count = b.take<unsigned long long>(4);
     f.sig = f.gcoef = f.wav_ws = nullptr;
-    f.coef_flags[0] = f.coef_flags[1] = nullptr;
+    f.coef_flags[0] = f.coef_flags[1] = f.redo_flags = f.need[0] = f.need[1] = nullptr;
+    f.tile_list3 = nullptr;
+    f.eps = nullptr;
     if (wav) {
         f.sig = b.take<float>((size_t)P * plan->ld2n);
         f.gcoef = b.take<float>((size_t)P * ldc);
         f.wav_ws = b.take<float>((size_t)2 * P * wavelet_ld(wav));
         f.coef_flags[0] = b.take<unsigned char>((size_t)P * coef_flag_ld(wav));
         f.coef_flags[1] = b.take<unsigned char>((size_t)P * coef_flag_ld(wav));
+        f.redo_flags = b.take<unsigned char>((size_t)P * coef_flag_ld(wav));
+        const size_t tiles = (size_t)((P + BM - 1) / BM) * ((2 * plan->n + BN - 1) / BN);
+        f.need[0] = b.take<unsigned char>(tiles);
+        f.need[1] = b.take<unsigned char>(tiles);
+        f.tile_list3 = b.take<int>(tiles);
+        f.eps = b.take<float>(P);
     }
     f.bytes = b.off;
     return f;
@@ -250,6 +265,14 @@ extern "C" int csr_fista(csr_plan* plan, csr_wavelet* wav, const csr_fista_args*
     const int cfl_ld = wav ? coef_flag_ld(wav) : 0;
     int cfl_cur = 0;
     if (wav_flags && (rc = launch_coef_flags(wav, w.z, ldc, P, w.coef_flags[0], cfl_ld, stream))) return rc;
+    // wavelet-domain screening of the adjoint (exact): the three-product gradient is computed only on the tiles that
+    // coefficients with non-zero state can see; elsewhere ONE product and the bound |c| + ||h_band||_1 eps < lambda
+    // prove that a coefficient stays zero, and the few blocks that fail are redone with the exact gradient
+    const bool wav_screen = wav_flags && options().screen != 0 && options().wavelet_screen != 0;
+    float band_l1[kCoefFlagBands] = {};
+    if (wav_screen) wavelet_band_l1(wav, band_l1);
+    const size_t n_tiles = (size_t)((P + BM - 1) / BM) * ((2 * n + BN - 1) / BN);
+    const int NTc = (2 * n + BN - 1) / BN;
 
     // 4. iterations
     double t = 1.0;
@@ -288,7 +311,7 @@ extern "C" int csr_fista(csr_plan* plan, csr_wavelet* wav, const csr_fista_args*
                 e.a_kflags = w.tile_flags;
                 e.a_kflag_ld = w.flag_ld;
             }
-            if (use_screen) {
+            if (use_screen || wav_screen) {
                 CSR_CUDA(cudaMemsetAsync(w.screen_hdr, 0, sizeof(float) * ((size_t)P + 8), stream));
                 e.abs_sum_out = w.screen_hdr + 8;
                 if (use_screen8) {
@@ -359,10 +382,34 @@ extern "C" int csr_fista(csr_plan* plan, csr_wavelet* wav, const csr_fista_args*
             e.mode = EPI_PLAIN;
             e.a_scale = w.rscale;
             e.out = w.sig;  // gradient in phi space
+            e.mma_count = w.mma_count;
+            int* counts = reinterpret_cast<int*>(w.screen_hdr);  // [0] exact tiles, [1] one-product tiles, [2] redo tiles
+            if (wav_screen) {
+                if ((rc = launch_screen_eps(w.screen_hdr + 8, w.rscale, 2 * m, w.eps, P, stream))) return rc;
+                CSR_CUDA(cudaMemsetAsync(w.need[0], 0, n_tiles, stream));
+                if ((rc = launch_need_from_flags(wav, w.coef_flags[cfl_cur], cfl_ld, P, w.need[0], NTc, stream))) return rc;
+                if ((rc = launch_split_tile_lists(w.need[0], nullptr, P, 2 * n, w.tile_list, counts, w.tile_list2, counts + 1, stream)))
+                    return rc;
+                GemmEpilogue e1 = e;
+                e1.mode = EPI_PLAIN1;
+                e1.tile_list = w.tile_list2;
+                e1.tile_count = counts + 1;
+                if ((rc = launch_dft_gemm(plan, true, w.r_hi, w.r_lo, P, e1, stream))) return rc;
+                e.tile_list = w.tile_list;
+                e.tile_count = counts;
+            }
             if ((rc = launch_dft_gemm(plan, true, w.r_hi, w.r_lo, P, e, stream))) return rc;
             if (fused_wavelet) {  // analysis of all levels + threshold + momentum in one kernel
-                CoefUpdate up = {x, w.z, a.lambda0, a.noise, a.iter_cap, it, a.step, beta, (last && a.delta) ? a.delta : nullptr,
-                                 nullptr, nullptr, 0};
+                CoefUpdate up = {};
+                up.x = x;
+                up.z = w.z;
+                up.lambda0 = a.lambda0;
+                up.noise = a.noise;
+                up.iter_cap = a.iter_cap;
+                up.iter = it;
+                up.step = a.step;
+                up.beta = beta;
+                up.delta = (last && a.delta) ? a.delta : nullptr;
                 if (wav_flags) {
                     CSR_CUDA(cudaMemsetAsync(w.coef_flags[cfl_cur ^ 1], 0, (size_t)P * cfl_ld, stream));
                     up.flags_in = w.coef_flags[cfl_cur];
@@ -370,7 +417,25 @@ extern "C" int csr_fista(csr_plan* plan, csr_wavelet* wav, const csr_fista_args*
                     up.flag_ld = cfl_ld;
                     cfl_cur ^= 1;
                 }
+                if (wav_screen) {
+                    CSR_CUDA(cudaMemsetAsync(w.redo_flags, 0, (size_t)P * cfl_ld, stream));
+                    up.screen_mode = 1;
+                    up.eps = w.eps;
+                    for (int b = 0; b < kCoefFlagBands; ++b) up.band_l1[b] = band_l1[b];
+                    up.redo = w.redo_flags;
+                }
                 if ((rc = swt_analysis_fused(wav, w.sig, ld2n, nullptr, ldc, P, &up, stream))) return rc;
+                if (wav_screen) {  // exact gradient where a block failed the test, then those blocks only
+                    CSR_CUDA(cudaMemsetAsync(w.need[1], 0, n_tiles, stream));
+                    if ((rc = launch_need_from_flags(wav, w.redo_flags, cfl_ld, P, w.need[1], NTc, stream))) return rc;
+                    if ((rc = launch_split_tile_lists(w.need[1], w.need[0], P, 2 * n, w.tile_list3, counts + 2, nullptr, nullptr, stream)))
+                        return rc;
+                    e.tile_list = w.tile_list3;
+                    e.tile_count = counts + 2;
+                    if ((rc = launch_dft_gemm(plan, true, w.r_hi, w.r_lo, P, e, stream))) return rc;
+                    up.screen_mode = 2;
+                    if ((rc = swt_analysis_fused(wav, w.sig, ld2n, nullptr, ldc, P, &up, stream))) return rc;
+                }
             } else {
                 if ((rc = wavelet_decompose(wav, w.sig, ld2n, w.gcoef, ldc, P, w.wav_ws, stream))) return rc;
                 if ((rc = launch_coef_update(w.gcoef, x, w.z, ldc, ncoef, P, a.lambda0, a.noise, a.iter_cap, it, a.step, beta,

@@ -41,7 +41,9 @@ constexpr int BN = 256;  // output columns per tile (UMMA N)
 constexpr int BK = 64;   // fp16 elements per K block = one 128-byte swizzle row
 constexpr int kMaxSkipK = 32 * 32 * 128;  // longest K the K-block activity bitmask covers (dft_gemm.cu)
 
-enum EpilogueMode { EPI_PLAIN = 0, EPI_RESID = 1, EPI_FISTA = 2, EPI_SCREEN = 3, EPI_SCREEN8 = 4 };
+// EPI_PLAIN1: the plain epilogue on ONE fp16 product (A_hi B_hi, one accumulation chain) -- the cheap gradient of the
+// wavelet-domain screening; |EPI_PLAIN - EPI_PLAIN1| <= screen_eps per element (dft_gemm.cu)
+enum EpilogueMode { EPI_PLAIN = 0, EPI_RESID = 1, EPI_FISTA = 2, EPI_SCREEN = 3, EPI_SCREEN8 = 4, EPI_PLAIN1 = 5 };
 
 struct GemmEpilogue {
     // common
@@ -90,6 +92,9 @@ struct GemmEpilogue {
     int debug;                 // measurement aid (CSR_DEBUG_EPI): bit 0 skips epilogue loads, bit 1 skips stores
 };
 
+constexpr int kCoefBlockShift = 9;  // 512 coefficients per flag
+constexpr int kCoefFlagBands = 16;  // fused kernels keep the flags of at most this many bands in shared memory
+
 // FISTA update applied to each wavelet coefficient as its gradient value is produced (wavelet.cu; may be disabled)
 struct CoefUpdate {
     float* x;
@@ -105,13 +110,24 @@ struct CoefUpdate {
     const unsigned char* flags_in;
     unsigned char* flags_out;  // zeroed by the caller; set to 1 where non-zero values were written
     int flag_ld;
+    // wavelet-domain screening of the adjoint (fista.cu, needs the flags).  screen_mode 0: the gradient is exact
+    // everywhere.  1: it is exact only where a set state flag can see it; a zero-state group whose coefficients provably
+    // stay below the threshold -- |c| + band_l1 * eps[p] < lambda -- is done, any other marks its block in `redo` and is
+    // left untouched.  2: only groups of blocks marked in `redo` are updated (their support is exact by now).
+    int screen_mode;
+    const float* eps;                 // [P] bound on the error of an inexact gradient element
+    float band_l1[kCoefFlagBands];    // l1 norm of the cascaded analysis filter of each band [cA_L, cD_L, ..., cD_1]
+    unsigned char* redo;              // [P, flag_ld] like the flags; zeroed by the caller before the mode-1 pass
 };
-constexpr int kCoefBlockShift = 9;  // 512 coefficients per flag
-constexpr int kCoefFlagBands = 16;  // fused kernels keep the flags of at most this many bands in shared memory
 
 int make_operand_map(CUtensorMap* map, const void* base, int rows, int cols, int ld, int box_rows, int elem_bytes = 2);
 int launch_dft_gemm(const csr_plan* plan, bool adjoint, const __half* a_hi, const __half* a_lo, int P,
                     const GemmEpilogue& epi, cudaStream_t stream);
+// eps[p] = bound on |three-product - one-product| adjoint output of line of sight p, in output units
+int launch_screen_eps(const float* abs_sum, const float* a_scale, int K, float* eps, int P, cudaStream_t stream);
+// need: [MT, NT] bytes.  Tiles with need != 0 (and exclude == 0, if given) -> list_a; with both_lists the others -> list_b
+int launch_split_tile_lists(const unsigned char* need, const unsigned char* exclude, int P, int N, int* list_a, int* count_a,
+                            int* list_b, int* count_b, cudaStream_t stream);
 int launch_screen8_pair(const csr_plan* plan, const unsigned char* a8, int P, const GemmEpilogue& epi, cudaStream_t stream);
 
 }  // namespace csr

@@ -10,8 +10,11 @@
 //   dwt (periodization): c[o] = sum_t f[t] x'[(2o + F/2 - t) mod N'],  x' = x with its last sample repeated
 //       once when N is odd;   idwt: x[(2o + t - F/2 + 1) mod N] += cA[o] rec_lo[t] + cD[o] rec_hi[t]
 // Every level is one gather kernel over [P, band] (grid.y = line of sight), memory-bound and coalesced.
+#include <math.h>
 #include <stdlib.h>
 #include <string.h>
+
+#include <vector>
 
 #include "plan.cuh"
 
@@ -314,6 +317,18 @@ swt_synth_fused_kernel(const float* __restrict__ coef, int ld_coef, int N, int L
     }
 }
 
+// u = z - step g ; x = soft(u, step lambda) ; z = x + beta (x - x_old)   (fista.py:80-86, l1.py:30-32).  The roundings
+// are spelled out so that every kernel of this file produces the same bits whatever the compiler would contract.
+__device__ __forceinline__ float soft_update(float zo, float xo, float g, float ustep, float thr, float beta, float& znew,
+                                             float& dsum) {
+    const float u = __fmaf_rn(-ustep, g, zo);
+    const float xn = copysignf(fmaxf(fabsf(u) - thr, 0.f), u);
+    const float dx = __fsub_rn(xn, xo);
+    znew = __fmaf_rn(beta, dx, xn);
+    dsum += fabsf(dx);
+    return xn;
+}
+
 // one analysis level over the whole buffer, filter length fixed at compile time (the dispatch happens once per level,
 // not per element).  d-band results are written (UPDATE = false) or consumed by the FISTA update (UPDATE = true).
 template <int FLEN, bool UPDATE>
@@ -337,11 +352,10 @@ __device__ __forceinline__ void analysis_level(const float* __restrict__ a, floa
         o[i] = ca;
         if (valid) {
             if (UPDATE) {
-                const float u = zo - ustep * cd;
-                const float xn = copysignf(fmaxf(fabsf(u) - thr, 0.f), u);
+                float zn;
+                const float xn = soft_update(zo, xo, cd, ustep, thr, beta, zn, dsum);
                 __stcs(xband + g, xn);
-                __stcs(zband + g, xn + beta * (xn - xo));
-                dsum += fabsf(xn - xo);
+                __stcs(zband + g, zn);
             } else {
                 cband[g] = cd;
             }
@@ -367,9 +381,9 @@ swt_analysis_fused_kernel(const float* __restrict__ signal, int ld_sig, int N, i
     bool active = true;
     if (UPDATE) {
         const float l0 = up.lambda0[p], nz = up.noise[p];
-        const float lam = l0 - (float)up.iter * nz;
+        const float lam = __fmaf_rn(-(float)up.iter, nz, l0);
         active = (nz < l0) && (up.iter == 0 || lam > 0.f) && (!up.iter_cap || up.iter < up.iter_cap[p]);
-        thr = up.step * lam;
+        thr = __fmul_rn(up.step, lam);  // (explicit rounding: the compiler would contract this product into |u| - thr)
         if (!active) return;  // whole CTA: this line of sight is frozen
     }
     const float* srow = signal + (size_t)p * ld_sig;
@@ -396,11 +410,10 @@ swt_analysis_fused_kernel(const float* __restrict__ signal, int ld_sig, int N, i
         const float ca = a[i];
         if (UPDATE) {
             const float zo = up.z[crow + bands.off[0] + g], xo = up.x[crow + bands.off[0] + g];
-            const float u = zo - up.step * ca;
-            const float xn = copysignf(fmaxf(fabsf(u) - thr, 0.f), u);
+            float zn;
+            const float xn = soft_update(zo, xo, ca, up.step, thr, up.beta, zn, dsum);
             up.x[crow + bands.off[0] + g] = xn;
-            up.z[crow + bands.off[0] + g] = xn + up.beta * (xn - xo);
-            dsum += fabsf(xn - xo);
+            up.z[crow + bands.off[0] + g] = zn;
         } else {
             coef[crow + bands.off[0] + g] = ca;
         }
@@ -495,23 +508,16 @@ __device__ __forceinline__ void taps4(const float* __restrict__ a, int i, int st
 
 __device__ __forceinline__ bool nonzero4(const float4& v) { return v.x != 0.f || v.y != 0.f || v.z != 0.f || v.w != 0.f; }
 
-__device__ __forceinline__ float soft_update(float zo, float xo, float g, float ustep, float thr, float beta, float& znew,
-                                             float& dsum) {
-    const float u = zo - ustep * g;
-    const float xn = copysignf(fmaxf(fabsf(u) - thr, 0.f), u);
-    znew = xn + beta * (xn - xo);
-    dsum += fabsf(xn - xo);
-    return xn;
-}
-
 // sfl: this band's state flags of the tile's blocks in shared memory (index (g >> kCoefBlockShift) - blk0), or null;
-// fout: this band's row of the flags being written, or null
+// fout: this band's row of the flags being written, or null.  mode / el1 / rfl / rout: wavelet-domain screening
+// (CoefUpdate::screen_mode; el1 = band_l1 * eps[p]; rfl = redo marks in shared memory; rout = redo marks being written)
 template <int FLEN, bool UPDATE, int SMALL>
 __device__ __forceinline__ void analysis_level4(const float* __restrict__ a, float* __restrict__ o, int B, int step, int H,
                                                 int T, int t0, int N, const FilterPair& f, float* __restrict__ cband,
                                                 float* __restrict__ xband, float* __restrict__ zband, float ustep,
                                                 float thr, float beta, float& dsum, const unsigned char* sfl, int blk0,
-                                                unsigned char* __restrict__ fout) {
+                                                unsigned char* __restrict__ fout, int mode, float el1,
+                                                const unsigned char* rfl, unsigned char* __restrict__ rout) {
     const int rim = round_up4(step * (FLEN / 2));
     const int vlo = H, vhi = min(H + T, H + (N - t0));
     for (int i = rim + 4 * threadIdx.x; i < B - rim; i += 4 * WAV4_THREADS) {
@@ -519,8 +525,13 @@ __device__ __forceinline__ void analysis_level4(const float* __restrict__ a, flo
         const int g = t0 + (i - H);
         float4 zo = make_float4(0.f, 0.f, 0.f, 0.f), xo = zo;
         bool st = true;  // "the state may hold non-zeros here"
+        bool update = UPDATE && valid;
         if (UPDATE && valid) {  // state loads in flight while the filters run
             if (sfl) st = sfl[(g >> kCoefBlockShift) - blk0] != 0;
+            if (mode == 2) {  // redo pass: only zero-state blocks that failed the screening test
+                update = rfl[(g >> kCoefBlockShift) - blk0] != 0;
+                st = false;
+            }
             if (st) {
                 zo = __ldcg(reinterpret_cast<const float4*>(zband + g));
                 xo = __ldcg(reinterpret_cast<const float4*>(xband + g));
@@ -531,17 +542,24 @@ __device__ __forceinline__ void analysis_level4(const float* __restrict__ a, flo
         *reinterpret_cast<float4*>(o + i) = make_float4(ca[0], ca[1], ca[2], ca[3]);
         if (valid) {
             if (UPDATE) {
-                float4 xn, zn;
-                xn.x = soft_update(zo.x, xo.x, cd[0], ustep, thr, beta, zn.x, dsum);
-                xn.y = soft_update(zo.y, xo.y, cd[1], ustep, thr, beta, zn.y, dsum);
-                xn.z = soft_update(zo.z, xo.z, cd[2], ustep, thr, beta, zn.z, dsum);
-                xn.w = soft_update(zo.w, xo.w, cd[3], ustep, thr, beta, zn.w, dsum);
-                const bool nzr = nonzero4(xn) || nonzero4(zn);
-                if (st || nzr) {  // a zero block whose new values are zero again keeps its (zero) memory
-                    __stcs(reinterpret_cast<float4*>(xband + g), xn);
-                    __stcs(reinterpret_cast<float4*>(zband + g), zn);
+                if (mode == 1 && !st) {  // zero state, gradient possibly inexact: provably below the threshold?
+                    const float mx = fmaxf(fmaxf(fabsf(cd[0]), fabsf(cd[1])), fmaxf(fabsf(cd[2]), fabsf(cd[3])));
+                    if (!(ustep * (mx + el1) * 1.000001f < thr)) rout[g >> kCoefBlockShift] = 1;
+                    update = false;
                 }
-                if (nzr && fout) fout[g >> kCoefBlockShift] = 1;
+                if (update) {
+                    float4 xn, zn;
+                    xn.x = soft_update(zo.x, xo.x, cd[0], ustep, thr, beta, zn.x, dsum);
+                    xn.y = soft_update(zo.y, xo.y, cd[1], ustep, thr, beta, zn.y, dsum);
+                    xn.z = soft_update(zo.z, xo.z, cd[2], ustep, thr, beta, zn.z, dsum);
+                    xn.w = soft_update(zo.w, xo.w, cd[3], ustep, thr, beta, zn.w, dsum);
+                    const bool nzr = nonzero4(xn) || nonzero4(zn);
+                    if (st || nzr) {  // a zero block whose new values are zero again keeps its (zero) memory
+                        __stcs(reinterpret_cast<float4*>(xband + g), xn);
+                        __stcs(reinterpret_cast<float4*>(zband + g), zn);
+                    }
+                    if (nzr && fout) fout[g >> kCoefBlockShift] = 1;
+                }
             } else {
                 *reinterpret_cast<float4*>(cband + g) = make_float4(cd[0], cd[1], cd[2], cd[3]);
             }
@@ -557,6 +575,7 @@ swt_analysis_fused4_kernel(const float* __restrict__ signal, int ld_sig, int N, 
     extern __shared__ __align__(16) float wsm4[];
     constexpr int MAXBLK = WAV_SMEM_BUDGET / 8 / (1 << kCoefBlockShift) + 3;  // flag blocks a tile can touch
     __shared__ unsigned char sflags[UPDATE ? kCoefFlagBands * MAXBLK : 1];
+    __shared__ unsigned char rflags[UPDATE ? kCoefFlagBands * MAXBLK : 1];
     float* a = wsm4;
     float* o = wsm4 + B;
     const int p = blockIdx.x;
@@ -566,14 +585,15 @@ swt_analysis_fused4_kernel(const float* __restrict__ signal, int ld_sig, int N, 
     const int blk0 = t0 >> kCoefBlockShift;
     const int nblk = min(NB - 1, (t0 + T - 1) >> kCoefBlockShift) - blk0 + 1;
     const bool use_flags = UPDATE && up.flags_in != nullptr;
-    float thr = 0.f;
+    const int mode = UPDATE ? up.screen_mode : 0;
+    float thr = 0.f, eps = 0.f;
     if (UPDATE) {
         const float l0 = up.lambda0[p], nz = up.noise[p];
-        const float lam = l0 - (float)up.iter * nz;
+        const float lam = __fmaf_rn(-(float)up.iter, nz, l0);
         const bool active = (nz < l0) && (up.iter == 0 || lam > 0.f) && (!up.iter_cap || up.iter < up.iter_cap[p]);
-        thr = up.step * lam;
+        thr = __fmul_rn(up.step, lam);  // (explicit rounding: the compiler would contract this product into |u| - thr)
         if (!active) {  // whole CTA: this line of sight is frozen; its state flags carry over
-            if (use_flags) {
+            if (use_flags && mode != 2) {
                 for (int idx = threadIdx.x; idx < (L + 1) * nblk; idx += WAV4_THREADS) {
                     const size_t at = (size_t)p * up.flag_ld + (idx / nblk) * NB + blk0 + idx % nblk;
                     if (up.flags_in[at]) up.flags_out[at] = 1;
@@ -582,9 +602,15 @@ swt_analysis_fused4_kernel(const float* __restrict__ signal, int ld_sig, int N, 
             return;
         }
         if (use_flags) {
-            for (int idx = threadIdx.x; idx < (L + 1) * nblk; idx += WAV4_THREADS)
-                sflags[(idx / nblk) * MAXBLK + idx % nblk] = up.flags_in[(size_t)p * up.flag_ld + (idx / nblk) * NB + blk0 + idx % nblk];
+            int any = 0;
+            for (int idx = threadIdx.x; idx < (L + 1) * nblk; idx += WAV4_THREADS) {
+                const size_t at = (size_t)p * up.flag_ld + (idx / nblk) * NB + blk0 + idx % nblk;
+                sflags[(idx / nblk) * MAXBLK + idx % nblk] = up.flags_in[at];
+                if (mode == 2) any |= (rflags[(idx / nblk) * MAXBLK + idx % nblk] = up.redo[at]);
+            }
+            if (mode == 2 && !__syncthreads_or(any)) return;  // nothing of this tile failed the screening test
         }
+        if (mode == 1) eps = up.eps[p];
     }
     const float* srow = signal + (size_t)p * ld_sig;
     for (int i = 4 * threadIdx.x; i < B; i += 4 * WAV4_THREADS)
@@ -600,13 +626,16 @@ swt_analysis_fused4_kernel(const float* __restrict__ signal, int ld_sig, int N, 
         float* xband = UPDATE ? up.x + crow + band : nullptr;
         float* zband = UPDATE ? up.z + crow + band : nullptr;
         const unsigned char* sfl = use_flags ? sflags + bi * MAXBLK : nullptr;
+        const unsigned char* rfl = use_flags ? rflags + bi * MAXBLK : nullptr;
         unsigned char* fout = use_flags ? up.flags_out + (size_t)p * up.flag_ld + bi * NB : nullptr;
+        unsigned char* rout = (use_flags && mode == 1) ? up.redo + (size_t)p * up.flag_ld + bi * NB : nullptr;
+        const float el1 = mode == 1 ? up.band_l1[bi] * eps : 0.f;
         if (lev == 1)
-            analysis_level4<FLEN, UPDATE, 1>(a, o, B, step, H, T, t0, N, f, cband, xband, zband, up.step, thr, up.beta, dsum, sfl, blk0, fout);
+            analysis_level4<FLEN, UPDATE, 1>(a, o, B, step, H, T, t0, N, f, cband, xband, zband, up.step, thr, up.beta, dsum, sfl, blk0, fout, mode, el1, rfl, rout);
         else if (lev == 2)
-            analysis_level4<FLEN, UPDATE, 2>(a, o, B, step, H, T, t0, N, f, cband, xband, zband, up.step, thr, up.beta, dsum, sfl, blk0, fout);
+            analysis_level4<FLEN, UPDATE, 2>(a, o, B, step, H, T, t0, N, f, cband, xband, zband, up.step, thr, up.beta, dsum, sfl, blk0, fout, mode, el1, rfl, rout);
         else
-            analysis_level4<FLEN, UPDATE, 0>(a, o, B, step, H, T, t0, N, f, cband, xband, zband, up.step, thr, up.beta, dsum, sfl, blk0, fout);
+            analysis_level4<FLEN, UPDATE, 0>(a, o, B, step, H, T, t0, N, f, cband, xband, zband, up.step, thr, up.beta, dsum, sfl, blk0, fout, mode, el1, rfl, rout);
         __syncthreads();
         float* tmp = a;
         a = o;
@@ -619,7 +648,19 @@ swt_analysis_fused4_kernel(const float* __restrict__ signal, int ld_sig, int N, 
         if (UPDATE) {
             float* zb = up.z + crow + bands.off[0] + g;
             float* xb = up.x + crow + bands.off[0] + g;
-            const bool st = use_flags ? sflags[(g >> kCoefBlockShift) - blk0] != 0 : true;
+            const int blk = (g >> kCoefBlockShift) - blk0;
+            bool st = use_flags ? sflags[blk] != 0 : true;
+            bool update = true;
+            if (mode == 2) {
+                update = rflags[blk] != 0;
+                st = false;
+            }
+            if (mode == 1 && !st) {
+                const float mx = fmaxf(fmaxf(fabsf(ca.x), fabsf(ca.y)), fmaxf(fabsf(ca.z), fabsf(ca.w)));
+                if (!(up.step * (mx + up.band_l1[0] * eps) * 1.000001f < thr)) up.redo[(size_t)p * up.flag_ld + (g >> kCoefBlockShift)] = 1;
+                update = false;
+            }
+            if (!update) continue;
             float4 zo = make_float4(0.f, 0.f, 0.f, 0.f), xo = zo;
             if (st) {
                 zo = __ldcg(reinterpret_cast<const float4*>(zb));
@@ -644,6 +685,28 @@ swt_analysis_fused4_kernel(const float* __restrict__ signal, int ld_sig, int N, 
 #pragma unroll
         for (int sft = 16; sft > 0; sft >>= 1) dsum += __shfl_xor_sync(0xffffffffu, dsum, sft);
         if ((threadIdx.x & 31) == 0 && dsum != 0.f) atomicAdd(up.delta + p, dsum);
+    }
+}
+
+// adjoint tiles (128 lines of sight x 256 phi columns) whose gradient a set coefficient flag can see: every coefficient
+// of block [bs, be) of any band depends on the signal inside [bs - H, be + H) only, H = (F/2)(2^L - 1)
+__global__ void need_from_flags_kernel(const unsigned char* __restrict__ flags, int flag_ld, int N, int NB, int L, int H,
+                                       unsigned char* __restrict__ need, int need_ld) {
+    const int p = blockIdx.x;
+    unsigned char* row = need + (size_t)(p >> 7) * need_ld;
+    for (int idx = threadIdx.x; idx < (L + 1) * NB; idx += blockDim.x) {
+        if (!flags[(size_t)p * flag_ld + idx]) continue;
+        const int k = idx % NB;
+        const int bs = k << kCoefBlockShift, be = min(N, bs + (1 << kCoefBlockShift));
+        const int len = be - bs + 2 * H;
+        if (len >= N) {
+            for (int t = 0; t <= (N - 1) >> 8; ++t) row[t] = 1;
+        } else {
+            const int lo = wrap_index(bs - H, N), hi = lo + len;
+            for (int t = lo >> 8; t <= (min(hi, N) - 1) >> 8; ++t) row[t] = 1;
+            if (hi > N)
+                for (int t = 0; t <= (hi - N - 1) >> 8; ++t) row[t] = 1;
+        }
     }
 }
 
@@ -805,6 +868,36 @@ int launch_coef_flags(const csr_wavelet* w, const float* z, int ld_coef, int P, 
     return CSR_OK;
 }
 
+// tiles of the adjoint GEMM that the set flags depend on (need: [ceil(P/128), need_ld] bytes, zeroed by the caller)
+int launch_need_from_flags(const csr_wavelet* w, const unsigned char* flags, int flag_ld, int P, unsigned char* need,
+                           int need_ld, cudaStream_t stream) {
+    const int NB = (w->N + (1 << kCoefBlockShift) - 1) >> kCoefBlockShift;
+    const int H = (w->F / 2) * ((1 << w->levels) - 1);
+    need_from_flags_kernel<<<P, 128, 0, stream>>>(flags, flag_ld, w->N, NB, w->levels, H, need, need_ld);
+    CSR_LAUNCHED();
+    return CSR_OK;
+}
+// l1 norms of the cascaded analysis filters, band order [cA_L, cD_L, ..., cD_1], rounded up
+void wavelet_band_l1(const csr_wavelet* w, float* l1) {
+    const int F = w->F, L = w->levels;
+    std::vector<double> lo(1, 1.0);
+    for (int lev = 1; lev <= L; ++lev) {
+        const int step = 1 << (lev - 1);
+        std::vector<double> a(lo.size() + (size_t)(F - 1) * step, 0.0), d(a.size(), 0.0);
+        for (size_t i = 0; i < lo.size(); ++i)
+            for (int t = 0; t < F; ++t) {
+                a[i + (size_t)t * step] += lo[i] * (double)w->dec_lo[t];
+                d[i + (size_t)t * step] += lo[i] * (double)w->dec_hi[t];
+            }
+        double sd = 0.0, sa = 0.0;
+        for (double v : d) sd += fabs(v);
+        for (double v : a) sa += fabs(v);
+        l1[L - lev + 1] = (float)(sd * 1.0001);
+        if (lev == L) l1[0] = (float)(sa * 1.0001);
+        lo.swap(a);
+    }
+}
+
 #define CSR_DISPATCH_FLEN4(FVAL, CALL) \
     switch (FVAL) {                    \
         case 2: { constexpr int FL = 2; CALL; } break;   \
@@ -894,7 +987,7 @@ int swt_analysis_fused(const csr_wavelet* w, const float* signal, int ld_sig, fl
                                                                              band_offsets(w), f, coef, ld_coef, none);
     }
     CSR_LAUNCHED();
-    if (prof) profile_stop(7, stream, ev0, ev1);
+    if (prof) profile_stop(update->screen_mode == 2 ? 11 : 7, stream, ev0, ev1);
     return CSR_OK;
 }
 

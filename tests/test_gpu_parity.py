@@ -517,6 +517,32 @@ def test_wavelet_vec4_fista_is_bit_exact():
         np.testing.assert_array_equal(a, b)
 
 
+@pytest.mark.parametrize("nch,P,K,name,kw", [(300, 70, 25, "coif2", dict(mixed=True)), (1000, 261, 12, "coif2", dict(mixed=True)),
+                                              (203, 300, 30, "sym2", dict(per_pixel_w=True, flags=0.1)), (400, 129, 40, "db4", {})])
+def test_wavelet_domain_screening_is_bit_exact(nch, P, K, name, kw):
+    """undecimated basis: away from the coefficients with non-zero state the gradient is computed with ONE fp16 product
+    and a rigorous bound proves that the coefficients there stay zero; blocks that fail are redone with the exact
+    gradient.  Same bits as the dense three-product loop, and parity with the oracle."""
+    from csromer_b200 import _lib
+    src, par = make_batch(nch, P, seed=79, **kw)
+    results = []
+    try:
+        for screen in (1, 0):
+            _lib.set_option("wavelet_screen", screen)
+            wav = cs.UndecimatedWavelet(wavelet_name=name)
+            cost, X, l1, lam0, noise = run_fista(src, par, K, wav=wav, step=1.0 / 2.8)
+            results.append((np.array(X.data, copy=True), np.array(cost, copy=True), np.array(src.model_data, copy=True)))
+    finally:
+        _lib.set_option("wavelet_screen", 1)
+    assert 0 < np.count_nonzero(results[0][0]) < 0.3 * results[0][0].size
+    for a, b in zip(results[0], results[1]):
+        np.testing.assert_array_equal(a, b)
+    if nch <= 400:
+        owav = ob.WaveletDict(name, kind="swt")
+        ref = oracle_fista(src, par, K, lam0, noise, owav=owav, step=1.0 / 2.8)
+        check_fista(src, X, cost, l1, ref)
+
+
 def test_wavelet_complex_variants_and_errors():
     rng = np.random.RandomState(4)
     z = (rng.normal(size=256) + 1j * rng.normal(size=256)).astype(np.complex64)

@@ -70,8 +70,8 @@ for _ in range(args.reps):
 e1.record()
 torch.cuda.synchronize()
 lib.csr_profile(0)
-ms = np.zeros(10)
-cnt = np.zeros(10, dtype=np.int64)
+ms = np.zeros(12)
+cnt = np.zeros(12, dtype=np.int64)
 _lib.check(lib.csr_profile_collect(ms.ctypes.data_as(ctypes.POINTER(ctypes.c_double)),
                                    cnt.ctypes.data_as(ctypes.POINTER(ctypes.c_longlong))), "collect")
 total_ms = e0.elapsed_time(e1) / args.reps
@@ -80,14 +80,18 @@ peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.ex
 C, N = eng.ncoef, eng.N
 flops = 8.0 * m * n * P
 names = ["plain_forward", "plain_adjoint", "resid_forward", "resid_adjoint", "fista_forward", "fista_adjoint",
-         "swt_synth_fused", "swt_analysis_update_fused"]
+         "swt_synth_fused", "swt_analysis_update_fused", "screen_adjoint_fp16", "screen_adjoint_fp8",
+         "plain_adjoint_one_product", "swt_analysis_update_redo"]
+screened = cnt[10] > 0  # wavelet-domain screening: the adjoint launches process tile lists, not the whole matrix
 kern = {}
 for i, name in enumerate(names):
     if cnt[i] == 0:
         continue
     avg = ms[i] / cnt[i]
     d = {"launches": int(cnt[i]), "avg_ms": float(avg), "share_of_run": float(ms[i] / (total_ms * args.reps))}
-    if i < 6:
+    if i >= 8 or (screened and i == 1):
+        pass
+    elif i < 6:
         d["algorithmic_tflops"] = flops / avg / 1e9
         d["frac_of_sustained_bf16_peak"] = d["algorithmic_tflops"] / peaks["bf16_tflops_sustained"]
         d["executed_frac"] = 3 * d["frac_of_sustained_bf16_peak"]
