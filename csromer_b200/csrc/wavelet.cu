@@ -465,20 +465,21 @@ static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 
 template <int FLEN, int OFF, int SMALL, bool TWO>
 __device__ __forceinline__ void taps4(const float* __restrict__ a, int i, int step, const float (&f0)[64],
                                       const float (&f1)[64], float (&c0)[4], float (&c1)[4]) {
+    // packed fp32 FMAs (FFMA2, sm_100): two independent round-to-nearest FMAs per issue slot -- same bits as two FFMAs
+    float2 p0[2] = {make_float2(c0[0], c0[1]), make_float2(c0[2], c0[3])};
+    float2 p1[2] = {make_float2(c1[0], c1[1]), make_float2(c1[2], c1[3])};
     if (SMALL == 0) {
         const float* ap = a + i + OFF * step;
 #pragma unroll
         for (int t = 0; t < FLEN; ++t) {
             const float4 v = *reinterpret_cast<const float4*>(ap - t * step);
-            c0[0] = fmaf(f0[t], v.x, c0[0]);
-            c0[1] = fmaf(f0[t], v.y, c0[1]);
-            c0[2] = fmaf(f0[t], v.z, c0[2]);
-            c0[3] = fmaf(f0[t], v.w, c0[3]);
+            const float2 g0 = make_float2(f0[t], f0[t]);
+            p0[0] = __ffma2_rn(g0, make_float2(v.x, v.y), p0[0]);
+            p0[1] = __ffma2_rn(g0, make_float2(v.z, v.w), p0[1]);
             if (TWO) {
-                c1[0] = fmaf(f1[t], v.x, c1[0]);
-                c1[1] = fmaf(f1[t], v.y, c1[1]);
-                c1[2] = fmaf(f1[t], v.z, c1[2]);
-                c1[3] = fmaf(f1[t], v.w, c1[3]);
+                const float2 g1 = make_float2(f1[t], f1[t]);
+                p1[0] = __ffma2_rn(g1, make_float2(v.x, v.y), p1[0]);
+                p1[1] = __ffma2_rn(g1, make_float2(v.z, v.w), p1[1]);
             }
         }
     } else {
@@ -496,13 +497,24 @@ __device__ __forceinline__ void taps4(const float* __restrict__ a, int i, int st
         }
 #pragma unroll
         for (int t = 0; t < FLEN; ++t) {
+            const float2 g0 = make_float2(f0[t], f0[t]), g1 = make_float2(f1[t], f1[t]);
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const float v = w[j + (OFF - t) * SMALL + LEFT];
-                c0[j] = fmaf(f0[t], v, c0[j]);
-                if (TWO) c1[j] = fmaf(f1[t], v, c1[j]);
+            for (int j = 0; j < 2; ++j) {
+                const float2 v = make_float2(w[2 * j + (OFF - t) * SMALL + LEFT], w[2 * j + 1 + (OFF - t) * SMALL + LEFT]);
+                p0[j] = __ffma2_rn(g0, v, p0[j]);
+                if (TWO) p1[j] = __ffma2_rn(g1, v, p1[j]);
             }
         }
+    }
+    c0[0] = p0[0].x;
+    c0[1] = p0[0].y;
+    c0[2] = p0[1].x;
+    c0[3] = p0[1].y;
+    if (TWO) {
+        c1[0] = p1[0].x;
+        c1[1] = p1[0].y;
+        c1[2] = p1[1].x;
+        c1[3] = p1[1].y;
     }
 }
 
