@@ -612,9 +612,14 @@ constexpr int P2_STAGES = 6;
 constexpr int P2_STAGE_BYTES = 2 * A_TILE_BYTES;  // A (128 rows x 128 B) + half of B (128 rows x 128 B)
 constexpr int P2_SMEM_BYTES = 1024 + P2_STAGES * P2_STAGE_BYTES + 256;
 
+// PMODE 0: the fp8 screening pass.  PMODE 1: the one-product fp16 plain adjoint (EPI_PLAIN1) -- same staging (a 128-byte
+// row holds 64 fp16 instead of 128 fp8), kind::f16 MMAs, the plain epilogue, every listed pair computed by both CTAs.
+template <int PMODE>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
 screen8_pair_kernel(const __grid_constant__ CUtensorMap map_a8, const __grid_constant__ CUtensorMap map_b8, int K, int MT,
                     int NT, const GemmEpilogue epi) {
+    constexpr bool PLAIN = PMODE == 1;
+    constexpr int BKE = PLAIN ? BK : 2 * BK;  // K elements per 128-byte row
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* stage_base = smem;
@@ -631,8 +636,9 @@ screen8_pair_kernel(const __grid_constant__ CUtensorMap map_a8, const __grid_con
     const uint32_t rank = cluster_ctarank();
     const int cluster_id = blockIdx.x >> 1, nclusters = gridDim.x >> 1;
     const int MTP = (MT + 1) / 2;
-    const int total = MTP * NT;
-    const int KB = (K + 2 * BK - 1) / (2 * BK);  // 128 fp8 elements per K block
+    const int total = (PLAIN && epi.tile_list) ? __ldcg(epi.tile_count) : MTP * NT;
+    const int KB = (K + BKE - 1) / BKE;
+    auto pair_id = [&](int ti) -> int { return (PLAIN && epi.tile_list) ? __ldcg(epi.tile_list + ti) : ti; };
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&map_a8);
@@ -658,6 +664,7 @@ screen8_pair_kernel(const __grid_constant__ CUtensorMap map_a8, const __grid_con
     const uint32_t tmem_base = *tmem_ptr;
 
     auto quiet = [&](int mt, int nt) -> bool {  // does pixel tile mt exist and is its state zero in this column tile?
+        if (PLAIN) return mt < MT;  // (plain mode: every existing tile of a listed pair is computed)
         if (mt >= MT) return false;
         const unsigned int* st = epi.tile_state + (size_t)mt * epi.flag_ld + 2 * nt;
         unsigned int wd = __ldcg(st);
@@ -672,17 +679,17 @@ screen8_pair_kernel(const __grid_constant__ CUtensorMap map_a8, const __grid_con
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int tp = cluster_id; tp < total; tp += nclusters) {
+            for (int ti = cluster_id; ti < total; ti += nclusters) {
                 int mtp, nt;
-                tile_coords(tp, MTP, NT, mtp, nt);
+                tile_coords(pair_id(ti), MTP, NT, mtp, nt);
                 if (!quiet(2 * mtp, nt) && !quiet(2 * mtp + 1, nt)) continue;
                 const int mt = 2 * mtp + (int)rank;
                 for (int kb = 0; kb < KB; ++kb) {
                     mbar_wait(&empty[stage], phase ^ 1);
                     uint8_t* sb = stage_base + stage * P2_STAGE_BYTES;
                     if (rank == 0) mbar_arrive_expect_tx(&full[stage], 2 * P2_STAGE_BYTES);
-                    tma_load_2d_pair(sb, &map_a8, &full[stage], kb * 2 * BK, mt * BM);
-                    tma_load_2d_pair(sb + A_TILE_BYTES, &map_b8, &full[stage], kb * 2 * BK, nt * BN + (int)rank * (BN / 2));
+                    tma_load_2d_pair(sb, &map_a8, &full[stage], kb * BKE, mt * BM);
+                    tma_load_2d_pair(sb + A_TILE_BYTES, &map_b8, &full[stage], kb * BKE, nt * BN + (int)rank * (BN / 2));
                     if (++stage == P2_STAGES) {
                         stage = 0;
                         phase ^= 1;
@@ -697,9 +704,9 @@ screen8_pair_kernel(const __grid_constant__ CUtensorMap map_a8, const __grid_con
             int stage = 0;
             uint32_t phase = 0, use = 0;
             unsigned long long issued = 0;
-            for (int tp = cluster_id; tp < total; tp += nclusters) {
+            for (int ti = cluster_id; ti < total; ti += nclusters) {
                 int mtp, nt;
-                tile_coords(tp, MTP, NT, mtp, nt);
+                tile_coords(pair_id(ti), MTP, NT, mtp, nt);
                 if (!quiet(2 * mtp, nt) && !quiet(2 * mtp + 1, nt)) continue;
                 const int buf = use & 1;
                 mbar_wait(&tmem_empty[buf], ((use >> 1) & 1) ^ 1);
@@ -711,20 +718,25 @@ screen8_pair_kernel(const __grid_constant__ CUtensorMap map_a8, const __grid_con
                     const uint32_t sa = smem_u32(stage_base + stage * P2_STAGE_BYTES);
                     const uint32_t sb = sa + A_TILE_BYTES;
 #pragma unroll
-                    for (int k4 = 0; k4 < 4; ++k4)
-                        umma_f8_pair(d_tmem, umma_desc_sw128(sa + k4 * 32), umma_desc_sw128(sb + k4 * 32), idesc,
-                                     (kb != 0 || k4 != 0) ? 1u : 0u);
+                    for (int k4 = 0; k4 < 4; ++k4) {
+                        if (PLAIN)
+                            umma_f16_pair(d_tmem, umma_desc_sw128(sa + k4 * 32), umma_desc_sw128(sb + k4 * 32), idesc,
+                                          (kb != 0 || k4 != 0) ? 1u : 0u);
+                        else
+                            umma_f8_pair(d_tmem, umma_desc_sw128(sa + k4 * 32), umma_desc_sw128(sb + k4 * 32), idesc,
+                                         (kb != 0 || k4 != 0) ? 1u : 0u);
+                    }
                     umma_commit_pair(&empty[stage]);
                     if (++stage == P2_STAGES) {
                         stage = 0;
                         phase ^= 1;
                     }
-                    issued += 4;  // two CTAs x one 128-element fp8 K block = 4 units of 128 x 256 x 64
+                    issued += PLAIN ? 2 : 4;  // two CTAs x one 128-element fp8 K block = 4 units of 128 x 256 x 64
                 }
                 umma_commit_pair(&tmem_full[buf]);
                 ++use;
             }
-            if (epi.mma_count != nullptr && issued != 0) atomicAdd(epi.mma_count + 2, issued);
+            if (epi.mma_count != nullptr && issued != 0) atomicAdd(epi.mma_count + (PLAIN ? 1 : 2), issued);
         }
       }
     } else {
@@ -735,9 +747,9 @@ screen8_pair_kernel(const __grid_constant__ CUtensorMap map_a8, const __grid_con
         const int half = ew >> 2;
         uint32_t use = 0;
         int ti = 0;  // running index of this CTA's tiles (for the one-lister-per-tile rule)
-        for (int tp = cluster_id; tp < total; tp += nclusters, ++ti) {
+        for (int tq = cluster_id; tq < total; tq += nclusters, ++ti) {
             int mtp, nt;
-            tile_coords(tp, MTP, NT, mtp, nt);
+            tile_coords(pair_id(tq), MTP, NT, mtp, nt);
             const int mt = 2 * mtp + (int)rank;
             const bool q_own = quiet(mt, nt), q_other = quiet(2 * mtp + 1 - (int)rank, nt);
             const bool exists = mt < MT;
@@ -751,17 +763,30 @@ screen8_pair_kernel(const __grid_constant__ CUtensorMap map_a8, const __grid_con
 #pragma unroll
                     for (int j = 0; j < EPI_COLS; ++j) acc[j] = 0.f;
                     drain_chunk(tmem_base + ((uint32_t)(sub * 32) << 16) + (uint32_t)(buf * BN + half * EPI_COLS), acc);
-                    const bool fail = screen_tile_fails<true>(epi, acc, lane, mt * BM + sub * 32, nt * BN + half * EPI_COLS, K);
-                    list_it = __any_sync(0xffffffffu, fail) != 0;
+                    if (PLAIN) {  // the accumulator is in registers: hand the TMEM buffer back before the global stores
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) {
+                            if (rank == 0) mbar_arrive(&tmem_empty[buf]);
+                            else mbar_arrive_leader(&tmem_empty[buf]);
+                        }
+                        epilogue_tile<EPI_PLAIN>(epi, acc, lane, mt * BM + sub * 32, nt * BN + half * EPI_COLS);
+                    } else {
+                        const bool fail = screen_tile_fails<true>(epi, acc, lane, mt * BM + sub * 32, nt * BN + half * EPI_COLS, K);
+                        list_it = __any_sync(0xffffffffu, fail) != 0;
+                    }
                 }
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) {
-                    if (rank == 0) mbar_arrive(&tmem_empty[buf]);
-                    else mbar_arrive_leader(&tmem_empty[buf]);
+                if (!(PLAIN && q_own)) {
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) {
+                        if (rank == 0) mbar_arrive(&tmem_empty[buf]);
+                        else mbar_arrive_leader(&tmem_empty[buf]);
+                    }
                 }
                 ++use;
             }
+            if (PLAIN) continue;
             if (list_it && lane == 0 && atomicMax(last_listed, ti) < ti) {
                 // tile id in the numbering of dft_gemm_kernel's tile_coords(t, MT, NT): invert it
                 const int g = mt / RASTER_GROUP, first = g * RASTER_GROUP;
@@ -1087,22 +1112,15 @@ int launch_split_tile_lists(const unsigned char* need, const unsigned char* excl
     return CSR_OK;
 }
 
-// fp8 screening on CTA pairs; `a8` is the fp8 copy of the residual operand ([P, ld8] bytes)
-int launch_screen8_pair(const csr_plan* plan, const unsigned char* a8, int P, const GemmEpilogue& epi_in, cudaStream_t stream) {
-    GemmEpilogue epi = epi_in;
-    epi.P = P;
-    epi.N = 2 * plan->n;
-    epi.ld_out = plan->ld2n;
-    epi.m = plan->m;
-    CSR_REQUIRE(epi.abs_sum && epi.tile_state && epi.out_list && epi.out_count && !epi.tile_list, "pair screening: missing argument");
+template <int PMODE>
+static int launch_pair_kernel(const csr_plan* plan, const CUtensorMap& ma, const CUtensorMap& mb, int P, const GemmEpilogue& epi,
+                              cudaStream_t stream) {
     const int K = 2 * plan->m;
-    const int MT = (P + BM - 1) / BM, NT = (2 * plan->n + BN - 1) / BN;
-    CUtensorMap ma;
-    int rc = cached_operand_map(&ma, a8, P, K, plan->ld8, 1);
-    if (rc) return rc;
+    const int MT = (P + BM - 1) / BM;
+    const int NT = (epi.N + BN - 1) / BN;
     static int max_clusters = 0;
     if (max_clusters == 0) {
-        CSR_CUDA(cudaFuncSetAttribute(screen8_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, P2_SMEM_BYTES));
+        CSR_CUDA(cudaFuncSetAttribute(screen8_pair_kernel<PMODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, P2_SMEM_BYTES));
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(2 * plan->num_sms);
         cfg.blockDim = dim3(NUM_THREADS);
@@ -1115,7 +1133,7 @@ int launch_screen8_pair(const csr_plan* plan, const unsigned char* a8, int P, co
         cfg.attrs = &attr;
         cfg.numAttrs = 1;
         int n = 0;
-        if (cudaOccupancyMaxActiveClusters(&n, screen8_pair_kernel, &cfg) != cudaSuccess || n <= 0) {
+        if (cudaOccupancyMaxActiveClusters(&n, screen8_pair_kernel<PMODE>, &cfg) != cudaSuccess || n <= 0) {
             cudaGetLastError();
             n = plan->num_sms / 2;
         }
@@ -1125,17 +1143,84 @@ int launch_screen8_pair(const csr_plan* plan, const unsigned char* a8, int P, co
     const int clusters = min(pairs, max_clusters);
     ProfiledLaunch rec;
     if (g_profile) {
-        rec.kind = 9;
+        rec.kind = PMODE == 1 ? 10 : 9;
         CSR_CUDA(pooled_event(&rec.start));
         CSR_CUDA(pooled_event(&rec.stop));
         CSR_CUDA(cudaEventRecord(rec.start, stream));
     }
-    screen8_pair_kernel<<<2 * clusters, NUM_THREADS, P2_SMEM_BYTES, stream>>>(ma, plan->map_adj8_half, K, MT, NT, epi);
+    screen8_pair_kernel<PMODE><<<2 * clusters, NUM_THREADS, P2_SMEM_BYTES, stream>>>(ma, mb, K, MT, NT, epi);
     CSR_LAUNCHED();
     if (g_profile) {
         CSR_CUDA(cudaEventRecord(rec.stop, stream));
         g_profiled.push_back(rec);
     }
+    return CSR_OK;
+}
+
+// fp8 screening on CTA pairs; `a8` is the fp8 copy of the residual operand ([P, ld8] bytes)
+int launch_screen8_pair(const csr_plan* plan, const unsigned char* a8, int P, const GemmEpilogue& epi_in, cudaStream_t stream) {
+    CSR_REQUIRE(P > 0, "P must be positive");
+    GemmEpilogue epi = epi_in;
+    epi.P = P;
+    epi.N = 2 * plan->n;
+    epi.ld_out = plan->ld2n;
+    epi.m = plan->m;
+    CSR_REQUIRE(epi.abs_sum && epi.tile_state && epi.out_list && epi.out_count, "screening launch: missing argument");
+    CUtensorMap ma;
+    int rc = cached_operand_map(&ma, a8, P, 2 * plan->m, plan->ld8, 1);
+    if (rc) return rc;
+    return launch_pair_kernel<0>(plan, ma, plan->map_adj8_half, P, epi, stream);
+}
+
+// the one-product plain adjoint (EPI_PLAIN1) on CTA pairs
+int launch_plain1_pair(const csr_plan* plan, const __half* a_hi, int P, const GemmEpilogue& epi_in, cudaStream_t stream) {
+    CSR_REQUIRE(P > 0 && epi_in.out != nullptr, "launch_plain1_pair: bad argument");
+    GemmEpilogue epi = epi_in;
+    epi.mode = EPI_PLAIN;
+    epi.P = P;
+    epi.N = 2 * plan->n;
+    epi.ld_out = plan->ld2n;
+    epi.m = plan->m;
+    epi.debug = 0;
+    CUtensorMap ma;
+    int rc = cached_operand_map(&ma, a_hi, P, 2 * plan->m, plan->ld2m, 2);
+    if (rc) return rc;
+    return launch_pair_kernel<1>(plan, ma, plan->map_adj_hi_half, P, epi, stream);
+}
+
+// pairs of pixel tiles (numbering of tile_coords(tp, ceil(MT/2), NT)) with an existing member whose need byte is 0
+__global__ void __launch_bounds__(1024)
+pair_list_kernel(const unsigned char* __restrict__ need, int MT, int NT, int* __restrict__ list, int* __restrict__ count) {
+    __shared__ int warp_n[32];
+    __shared__ int base;
+    if (threadIdx.x == 0) base = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int MTP = (MT + 1) / 2;
+    for (int t0 = 0; t0 < MTP * NT; t0 += 1024) {
+        const int t = t0 + threadIdx.x;
+        bool a = false;
+        if (t < MTP * NT) {
+            int mtp, nt;
+            tile_coords(t, MTP, NT, mtp, nt);
+            a = need[(size_t)(2 * mtp) * NT + nt] == 0 || (2 * mtp + 1 < MT && need[(size_t)(2 * mtp + 1) * NT + nt] == 0);
+        }
+        const unsigned ba = __ballot_sync(0xffffffffu, a);
+        if (lane == 0) warp_n[warp] = __popc(ba);
+        __syncthreads();
+        int oa = base;
+        for (int w = 0; w < warp; ++w) oa += warp_n[w];
+        if (a) list[oa + __popc(ba & ((1u << lane) - 1))] = t;
+        __syncthreads();
+        if (threadIdx.x == 0)
+            for (int w = 0; w < 32; ++w) base += warp_n[w];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *count = base;
+}
+int launch_pair_list(const unsigned char* need, int P, int N, int* list, int* count, cudaStream_t stream) {
+    pair_list_kernel<<<1, 1024, 0, stream>>>(need, (P + BM - 1) / BM, (N + BN - 1) / BN, list, count);
+    CSR_LAUNCHED();
     return CSR_OK;
 }
 

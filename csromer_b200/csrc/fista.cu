@@ -394,7 +394,12 @@ extern "C" int csr_fista(csr_plan* plan, csr_wavelet* wav, const csr_fista_args*
                 e1.mode = EPI_PLAIN1;
                 e1.tile_list = w.tile_list2;
                 e1.tile_count = counts + 1;
-                if ((rc = launch_dft_gemm(plan, true, w.r_hi, w.r_lo, P, e1, stream))) return rc;
+                if (options().pair != 0 && P > BM) {  // on CTA pairs: every pair with a tile outside the exact list
+                    if ((rc = launch_pair_list(w.need[0], P, 2 * n, w.tile_list2, counts + 1, stream))) return rc;
+                    if ((rc = launch_plain1_pair(plan, w.r_hi, P, e1, stream))) return rc;
+                } else {
+                    if ((rc = launch_dft_gemm(plan, true, w.r_hi, w.r_lo, P, e1, stream))) return rc;
+                }
                 e.tile_list = w.tile_list;
                 e.tile_count = counts;
             }

@@ -183,6 +183,7 @@ static int plan_build(csr_plan* p, const double* lambda2, const double* phi) {
     if ((rc = make_operand_map(&p->map_adj_lo, p->Tt_lo, 2 * n, 2 * m, p->ld2m, BN))) return rc;
     if ((rc = make_operand_map(&p->map_adj8, p->Tt8, 2 * n, 2 * m, p->ld8, BN, 1))) return rc;
     if ((rc = make_operand_map(&p->map_adj8_half, p->Tt8, 2 * n, 2 * m, p->ld8, BN / 2, 1))) return rc;
+    if ((rc = make_operand_map(&p->map_adj_hi_half, p->Tt_hi, 2 * n, 2 * m, p->ld2m, BN / 2))) return rc;
     return CSR_OK;
 }
 

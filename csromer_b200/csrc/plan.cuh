@@ -20,6 +20,7 @@ struct csr_plan {
     int ld8;             // row pitch in bytes of every [*, 2m] fp8 matrix, multiple of 16
     CUtensorMap map_fwd_hi, map_fwd_lo, map_adj_hi, map_adj_lo, map_adj8;
     CUtensorMap map_adj8_half;  // Tt8 with a 128-row box: half a B tile per CTA of a cta_group::2 pair
+    CUtensorMap map_adj_hi_half;  // Tt_hi with a 128-row box (the one-product plain adjoint on CTA pairs)
     size_t table_bytes;
 };
 
@@ -129,5 +130,9 @@ int launch_screen_eps(const float* abs_sum, const float* a_scale, int K, float* 
 int launch_split_tile_lists(const unsigned char* need, const unsigned char* exclude, int P, int N, int* list_a, int* count_a,
                             int* list_b, int* count_b, cudaStream_t stream);
 int launch_screen8_pair(const csr_plan* plan, const unsigned char* a8, int P, const GemmEpilogue& epi, cudaStream_t stream);
+// EPI_PLAIN1 on CTA pairs; epi.tile_list / tile_count name PAIRS of pixel tiles (launch_pair_list), null = all
+int launch_plain1_pair(const csr_plan* plan, const __half* a_hi, int P, const GemmEpilogue& epi, cudaStream_t stream);
+// pairs (two pixel tiles x one column tile) with at least one existing tile whose need byte is 0
+int launch_pair_list(const unsigned char* need, int P, int N, int* list, int* count, cudaStream_t stream);
 
 }  // namespace csr

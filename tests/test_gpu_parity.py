@@ -527,16 +527,19 @@ def test_wavelet_domain_screening_is_bit_exact(nch, P, K, name, kw):
     src, par = make_batch(nch, P, seed=79, **kw)
     results = []
     try:
-        for screen in (1, 0):
+        for screen, pair in ((1, 1), (1, 0), (0, 1)):  # (pair: the one-product gradient runs on cta_group::2 CTA pairs)
             _lib.set_option("wavelet_screen", screen)
+            _lib.set_option("pair", pair)
             wav = cs.UndecimatedWavelet(wavelet_name=name)
             cost, X, l1, lam0, noise = run_fista(src, par, K, wav=wav, step=1.0 / 2.8)
             results.append((np.array(X.data, copy=True), np.array(cost, copy=True), np.array(src.model_data, copy=True)))
     finally:
         _lib.set_option("wavelet_screen", 1)
+        _lib.set_option("pair", 1)
     assert 0 < np.count_nonzero(results[0][0]) < 0.3 * results[0][0].size
-    for a, b in zip(results[0], results[1]):
-        np.testing.assert_array_equal(a, b)
+    for other in results[1:]:
+        for a, b in zip(results[0], other):
+            np.testing.assert_array_equal(a, b)
     if nch <= 400:
         owav = ob.WaveletDict(name, kind="swt")
         ref = oracle_fista(src, par, K, lam0, noise, owav=owav, step=1.0 / 2.8)
