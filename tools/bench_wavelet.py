@@ -3,6 +3,8 @@ n = 31968, undecimated coif2, L = 6; or the C3 sampling with --nch 1000), device
 CUDA events (csr_profile).  Not the driver's bench line (bench.py measures configs[2]); results go to profiles/.
 
     python tools/bench_wavelet.py [--nch 4000] [--los 4096] [--iters 20] [--reps 3]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29511 \
+        tools/bench_wavelet.py --iters 100 --reps 2        # pixel-sharded: every rank its own slab, max over ranks
 """
 import argparse
 import ctypes
@@ -26,6 +28,11 @@ ap.add_argument("--los", type=int, default=4096)
 ap.add_argument("--iters", type=int, default=20)
 ap.add_argument("--reps", type=int, default=3)
 args = ap.parse_args()
+world, rank, local = (int(os.environ.get(k, d)) for k, d in (("WORLD_SIZE", "1"), ("RANK", "0"), ("LOCAL_RANK", "0")))
+torch.cuda.set_device(local)
+if world > 1:
+    import torch.distributed as dist
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
 band = (0.9e9, 1.67e9) if args.nch != 1000 else (1.008e9, 2.031e9)
 nu = np.linspace(band[0], band[1], args.nch)
@@ -40,7 +47,7 @@ dev = plan.device
 m, n, P, K = plan.m, plan.n, args.los, args.iters
 step = 1.0 / estimate_lipschitz(dft)
 eng = cs.UndecimatedWavelet(wavelet_name="coif2").prepare(2 * n)
-g = torch.Generator(device=dev).manual_seed(1236)
+g = torch.Generator(device=dev).manual_seed(1236 + 17 * rank)
 l2 = torch.as_tensor(np.ascontiguousarray(src.lambda2), dtype=torch.float64, device=dev)[None, :]
 phi = (torch.rand(P, generator=g, device=dev, dtype=torch.float64) - 0.5)[:, None] * 1000.0
 amp = 0.0035 * (0.5 + torch.rand(P, generator=g, device=dev, dtype=torch.float64))[:, None]
@@ -60,21 +67,31 @@ def run():
     return plan.fista(data, w, s, k, x, lam, nz, K, step=step, use_dirty_as_guess=True, wavelet=eng)
 
 
+def barrier():
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+
+
 run()
-torch.cuda.synchronize()
+barrier()
 lib.csr_profile(1)
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 e0.record()
 for _ in range(args.reps):
     run()
 e1.record()
-torch.cuda.synchronize()
+barrier()
 lib.csr_profile(0)
 ms = np.zeros(12)
 cnt = np.zeros(12, dtype=np.int64)
 _lib.check(lib.csr_profile_collect(ms.ctypes.data_as(ctypes.POINTER(ctypes.c_double)),
                                    cnt.ctypes.data_as(ctypes.POINTER(ctypes.c_longlong))), "collect")
 total_ms = e0.elapsed_time(e1) / args.reps
+if world > 1:  # the slowest rank defines the step
+    tmax = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    total_ms = float(tmax.item())
 peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else \
     {"hbm_gbs": 6650.0, "bf16_tflops_sustained": 1400.0}
 C, N = eng.ncoef, eng.N
@@ -103,7 +120,12 @@ for i, name in enumerate(names):
     kern[name] = d
 line = {"workload": "%d ch (%.3f-%.3f GHz), n_phi=%d, SWT coif2 L=%d (ncoef=%d), %d LOS, K=%d FISTA iterations, "
                     "step=1/lambda_max=%.3f, lambda0=40 theo_noise" % (m, band[0] / 1e9, band[1] / 1e9, n, eng.levels, C, P, K, step),
-        "ms_per_run": total_ms, "ms_per_iteration": total_ms / K, "los_per_s_at_K": P / total_ms * 1e3,
-        "los_per_s_at_K100_extrapolated": P / (total_ms / K * 100) * 1e3, "finite": bool(torch.isfinite(x).all()),
-        "kernels": kern}
-print(json.dumps(line))
+        "n_gpus": world, "los_per_gpu": P, "scaling": "weak (pixel-sharded, no data-path collective)",
+        "ms_per_run": total_ms, "ms_per_iteration": total_ms / K, "los_per_s_at_K": world * P / total_ms * 1e3,
+        "los_per_s_at_K100_extrapolated": world * P / (total_ms / K * 100) * 1e3,
+        "full_c5_cube_seconds_at_this_rate": 2048 * 2048 / (world * P / (total_ms / K * 100) * 1e3),
+        "finite": bool(torch.isfinite(x).all()), "kernels_rank0": kern}
+if rank == 0:
+    print(json.dumps(line))
+if world > 1:
+    dist.destroy_process_group()
