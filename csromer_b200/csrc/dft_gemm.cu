@@ -619,7 +619,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
 screen8_pair_kernel(const __grid_constant__ CUtensorMap map_a8, const __grid_constant__ CUtensorMap map_b8, int K, int MT,
                     int NT, const GemmEpilogue epi) {
     constexpr bool PLAIN = PMODE == 1;
-    constexpr int BKE = PLAIN ? BK : 2 * BK;  // K elements per 128-byte row
+    constexpr bool F16 = PMODE != 0;          // PMODE 2: the fp16 screening test (EPI_SCREEN) over all quiet tiles
+    constexpr int BKE = F16 ? BK : 2 * BK;    // K elements per 128-byte row
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* stage_base = smem;
@@ -719,7 +720,7 @@ screen8_pair_kernel(const __grid_constant__ CUtensorMap map_a8, const __grid_con
                     const uint32_t sb = sa + A_TILE_BYTES;
 #pragma unroll
                     for (int k4 = 0; k4 < 4; ++k4) {
-                        if (PLAIN)
+                        if (F16)
                             umma_f16_pair(d_tmem, umma_desc_sw128(sa + k4 * 32), umma_desc_sw128(sb + k4 * 32), idesc,
                                           (kb != 0 || k4 != 0) ? 1u : 0u);
                         else
@@ -731,12 +732,12 @@ screen8_pair_kernel(const __grid_constant__ CUtensorMap map_a8, const __grid_con
                         stage = 0;
                         phase ^= 1;
                     }
-                    issued += PLAIN ? 2 : 4;  // two CTAs x one 128-element fp8 K block = 4 units of 128 x 256 x 64
+                    issued += F16 ? 2 : 4;  // two CTAs x one 128-element fp8 K block = 4 units of 128 x 256 x 64
                 }
                 umma_commit_pair(&tmem_full[buf]);
                 ++use;
             }
-            if (epi.mma_count != nullptr && issued != 0) atomicAdd(epi.mma_count + (PLAIN ? 1 : 2), issued);
+            if (epi.mma_count != nullptr && issued != 0) atomicAdd(epi.mma_count + (F16 ? 1 : 2), issued);
         }
       }
     } else {
@@ -772,7 +773,7 @@ screen8_pair_kernel(const __grid_constant__ CUtensorMap map_a8, const __grid_con
                         }
                         epilogue_tile<EPI_PLAIN>(epi, acc, lane, mt * BM + sub * 32, nt * BN + half * EPI_COLS);
                     } else {
-                        const bool fail = screen_tile_fails<true>(epi, acc, lane, mt * BM + sub * 32, nt * BN + half * EPI_COLS, K);
+                        const bool fail = screen_tile_fails<!F16>(epi, acc, lane, mt * BM + sub * 32, nt * BN + half * EPI_COLS, K);
                         list_it = __any_sync(0xffffffffu, fail) != 0;
                     }
                 }
@@ -1143,7 +1144,7 @@ static int launch_pair_kernel(const csr_plan* plan, const CUtensorMap& ma, const
     const int clusters = min(pairs, max_clusters);
     ProfiledLaunch rec;
     if (g_profile) {
-        rec.kind = PMODE == 1 ? 10 : 9;
+        rec.kind = PMODE == 1 ? 10 : (PMODE == 2 ? 8 : 9);
         CSR_CUDA(pooled_event(&rec.start));
         CSR_CUDA(pooled_event(&rec.stop));
         CSR_CUDA(cudaEventRecord(rec.start, stream));
@@ -1170,6 +1171,22 @@ int launch_screen8_pair(const csr_plan* plan, const unsigned char* a8, int P, co
     int rc = cached_operand_map(&ma, a8, P, 2 * plan->m, plan->ld8, 1);
     if (rc) return rc;
     return launch_pair_kernel<0>(plan, ma, plan->map_adj8_half, P, epi, stream);
+}
+
+// the fp16 screening test on CTA pairs over every quiet tile (no fp8 pass in front): for residuals whose l1 norm makes
+// the fp8 bound useless (per-pixel weights: the weighted residual stays signal-sized)
+int launch_screen16_pair(const csr_plan* plan, const __half* a_hi, int P, const GemmEpilogue& epi_in, cudaStream_t stream) {
+    CSR_REQUIRE(P > 0, "P must be positive");
+    GemmEpilogue epi = epi_in;
+    epi.P = P;
+    epi.N = 2 * plan->n;
+    epi.ld_out = plan->ld2n;
+    epi.m = plan->m;
+    CSR_REQUIRE(epi.abs_sum && epi.tile_state && epi.out_list && epi.out_count && !epi.tile_list, "pair screening: missing argument");
+    CUtensorMap ma;
+    int rc = cached_operand_map(&ma, a_hi, P, 2 * plan->m, plan->ld2m, 2);
+    if (rc) return rc;
+    return launch_pair_kernel<2>(plan, ma, plan->map_adj_hi_half, P, epi, stream);
 }
 
 // the one-product plain adjoint (EPI_PLAIN1) on CTA pairs

@@ -130,6 +130,7 @@ int launch_screen_eps(const float* abs_sum, const float* a_scale, int K, float* 
 int launch_split_tile_lists(const unsigned char* need, const unsigned char* exclude, int P, int N, int* list_a, int* count_a,
                             int* list_b, int* count_b, cudaStream_t stream);
 int launch_screen8_pair(const csr_plan* plan, const unsigned char* a8, int P, const GemmEpilogue& epi, cudaStream_t stream);
+int launch_screen16_pair(const csr_plan* plan, const __half* a_hi, int P, const GemmEpilogue& epi, cudaStream_t stream);
 // EPI_PLAIN1 on CTA pairs; epi.tile_list / tile_count name PAIRS of pixel tiles (launch_pair_list), null = all
 int launch_plain1_pair(const csr_plan* plan, const __half* a_hi, int P, const GemmEpilogue& epi, cudaStream_t stream);
 // pairs (two pixel tiles x one column tile) with at least one existing tile whose need byte is 0
