@@ -226,8 +226,16 @@ __device__ __forceinline__ void epilogue_tile(const GemmEpilogue& epi, const flo
                         if (epi.out8 != nullptr) {
                             const float2 v8 = make_float2(hf.x * kOperandScale8, hf.y * kOperandScale8);
                             if (fmaxf(fabsf(v8.x), fabsf(v8.y)) > 448.f) dsum = __int_as_float(0x7f800000);  // unscreenable row
-                            *reinterpret_cast<__nv_fp8x2_storage_t*>(epi.out8 + (size_t)row * epi.ld8 + col) =
-                                __nv_cvt_float2_to_fp8x2(v8, __NV_SATFINITE, __NV_E4M3);
+                            // (fp8 rows are [first half | pad | second half | pad], halves ld8/2 apart: plan.cu)
+                            const __nv_fp8x2_storage_t pk = __nv_cvt_float2_to_fp8x2(v8, __NV_SATFINITE, __NV_E4M3);
+                            unsigned char* o8 = epi.out8 + (size_t)row * epi.ld8;
+                            const int h8 = epi.ld8 >> 1;
+                            if (epi.m & 1) {  // odd m: the pair may straddle the halves and the second half sits at odd offsets
+                                o8[col < epi.m ? col : col - epi.m + h8] = (unsigned char)(pk & 0xff);
+                                o8[col + 1 < epi.m ? col + 1 : col + 1 - epi.m + h8] = (unsigned char)(pk >> 8);
+                            } else {
+                                *reinterpret_cast<__nv_fp8x2_storage_t*>(o8 + (col < epi.m ? col : col - epi.m + h8)) = pk;
+                            }
                         }
                     } else {  // EPI_FISTA: u = z - step*g ; x = soft(u, step*lambda) ; z = x + beta (x - x_old)
                         const float u0 = in0[jj].x - a0, u1 = in0[jj].y - a1;
@@ -608,6 +616,99 @@ dft_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
 // issues the MMAs and owns the full / accumulator-empty barriers, MMA commits are multicast to both CTAs.
 // Same test, same bound, same lists as dft_gemm_kernel<EPI_SCREEN8>; a pair runs when at least one of its two
 // pixel tiles is quiet (the other CTA then just passes its tile on).
+// ---- mirror-symmetric screening ------------------------------------------------------------------------------------
+// phi_j = -phi_{n-j}: with b = alpha + i beta and theta = 2 (lambda2 - l2_ref) phi_j, j >= n/2,
+//   Re F(+-phi_j) = C_alpha +- S_beta,   Im F(+-phi_j) = C_beta -+ S_alpha,   C_x = sum_i x_i cos theta_i, S_x = sum_i x_i sin theta_i
+// so four real sums of length m bound the gradient at BOTH +phi_j and -phi_j: the GEMM [2P, m] (rows alpha_p, beta_p: the
+// half rows of the residual operand) x [m, n] (the half rows cos / sin of the table rows j >= n/2) has half the K of the
+// plain one for the same outputs.  |C| < L/2 and |S| < L/2 for every entry imply |C +- S| < L, with L = the plain test's
+// limit (its slack covers both partial sums: S_p = S_alpha + S_beta, K = 2 m).  The one cell without a mirror (j = 0) is an
+// extra column tile.  Original column ranges [lo, hi) of the real representation that symmetric column tile nt decides:
+__device__ __forceinline__ int sym_ranges(int nt, int NT, int n, int (&lo)[4], int (&hi)[4]) {
+    if (nt == NT - 1) {  // phi_0 alone
+        lo[0] = 0;
+        hi[0] = 1;
+        lo[1] = n;
+        hi[1] = n + 1;
+        return 2;
+    }
+    const int j0 = n / 2 + (BN / 2) * nt, j1 = min(j0 + BN / 2, n);
+    lo[0] = j0;  // Re F(+phi)
+    hi[0] = j1;
+    lo[1] = n - j1 + 1;  // Re F(-phi): j' = n - j
+    hi[1] = n - j0 + 1;
+    lo[2] = n + lo[0];   // Im
+    hi[2] = n + hi[0];
+    lo[3] = n + lo[1];
+    hi[3] = n + hi[1];
+    return 4;
+}
+
+// rows of the half-row view: row = 2 p + h; `ncols` valid columns from col0 (each phi is a (cos, sin) column pair).
+// The thread that holds (C_alpha, S_alpha) of a (line of sight, phi) and the one that holds (C_beta, S_beta) are four lanes
+// apart (consecutive rows of the fragment): one exchange gives each of them one of the two sums |C_x| + |S_y|.
+// Returns bit 0: a bound on Re F failed (the alpha rows test |C_alpha| + |S_beta|), bit 1: one on Im F (beta rows).
+template <bool F8>
+__device__ __forceinline__ int screen_tile_fails_sym(const GemmEpilogue& epi, const float (&acc)[EPI_COLS], int lane, int row0,
+                                                     int col0, int ncols, int Khalf) {
+    const int quad = lane & 3;
+    const int part = 1 << ((lane >> 2) & 1);  // (row0 and the row offsets 8 rh + 16 lh are even)
+    int fail = 0;
+#pragma unroll
+    for (int lh = 0; lh < 2; ++lh) {
+#pragma unroll
+        for (int rh = 0; rh < 2; ++rh) {
+            const int p = (row0 + (lane >> 2) + 8 * rh + 16 * lh) >> 1;  // (both lanes of an exchange share p)
+            const bool row_ok = p < epi.P;
+            float lim = 0.f;
+            bool active = false;
+            if (row_ok) {
+                const float l0 = __ldg(epi.lambda0 + p), nz = __ldg(epi.noise + p);
+                const float lam = l0 - (float)epi.iter * nz;
+                active = (nz < l0) && (epi.iter == 0 || lam > 0.f) && (!epi.iter_cap || epi.iter < __ldg(epi.iter_cap + p));
+                const float sp = __ldg(epi.abs_sum + p);
+                lim = F8 ? lam * __ldg(epi.a_scale + p) * (kTwiddleScale8 * kOperandScale8) - (68.f * sp + 0.6f * (float)Khalf)
+                         : lam * __ldg(epi.a_scale + p) * (1.f / kTwiddleDescale) - screen_slack(2 * Khalf) * sp;
+            }
+            float mx = 0.f;
+            bool bad = false;
+#pragma unroll
+            for (int jj = 0; jj < 16; ++jj) {
+                const int col = col0 + 8 * jj + 2 * quad;
+                const int ai = (((lh * 2 + (jj >> 3)) * 8 + (jj & 7)) * 2 + rh) * 2;
+                // own (C, S); the partner row's S (all lanes take part in the exchange)
+                const float s_other = __shfl_xor_sync(0xffffffffu, acc[ai + 1], 4);
+                if (col >= ncols) continue;
+                mx = fmaxf(mx, fabsf(acc[ai]) + fabsf(s_other));
+                bad |= (acc[ai] != acc[ai]) | (s_other != s_other);
+            }
+            if (row_ok && active && (bad | !(lim > 0.f) | !(mx < lim))) fail |= part;
+        }
+    }
+    return fail;
+}
+
+// per (group of 64 lines of sight, symmetric column tile): 1 = some original tile this symmetric tile overlaps is quiet
+// (its state is identically zero), i.e. there is something to decide; the three roles of the pair kernel read this byte
+__global__ void sym_quiet_kernel(const unsigned int* __restrict__ tile_state, int flag_ld, int MTg, int NTs, int nphi,
+                                 unsigned char* __restrict__ symq) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= MTg * NTs) return;
+    const int mt = idx / NTs, nt = idx - mt * NTs;
+    const unsigned int mask = (mt & 1) ? 0xFFFF0000u : 0x0000FFFFu;
+    const unsigned int* row = tile_state + (size_t)(mt >> 1) * flag_ld;
+    int lo[4], hi[4];
+    const int nr = sym_ranges(nt, NTs, nphi, lo, hi);
+    unsigned char any_quiet = 0;
+    for (int r = 0; r < nr; ++r)
+        for (int t = lo[r] >> 8; t <= (hi[r] - 1) >> 8; ++t) {
+            unsigned int wd = row[2 * t];
+            if (2 * t + 1 < flag_ld) wd |= row[2 * t + 1];
+            if (!(wd & mask)) any_quiet = 1;
+        }
+    symq[idx] = any_quiet;
+}
+
 constexpr int P2_STAGES = 6;
 constexpr int P2_STAGE_BYTES = 2 * A_TILE_BYTES;  // A (128 rows x 128 B) + half of B (128 rows x 128 B)
 constexpr int P2_SMEM_BYTES = 1024 + P2_STAGES * P2_STAGE_BYTES + 256;
@@ -619,8 +720,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
 screen8_pair_kernel(const __grid_constant__ CUtensorMap map_a8, const __grid_constant__ CUtensorMap map_b8, int K, int MT,
                     int NT, const GemmEpilogue epi) {
     constexpr bool PLAIN = PMODE == 1;
-    constexpr bool F16 = PMODE != 0;          // PMODE 2: the fp16 screening test (EPI_SCREEN) over all quiet tiles
+    constexpr bool F16 = PMODE == 1 || PMODE == 2 || PMODE == 4;  // PMODE 2: the fp16 screening test over all quiet tiles
+    constexpr bool SYM = PMODE >= 3;          // PMODE 3 / 4: mirror-symmetric fp8 / fp16 screening (MT counts 64-LOS groups)
     constexpr int BKE = F16 ? BK : 2 * BK;    // K elements per 128-byte row
+    const int nphi = epi.N >> 1;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* stage_base = smem;
@@ -667,6 +770,7 @@ screen8_pair_kernel(const __grid_constant__ CUtensorMap map_a8, const __grid_con
     auto quiet = [&](int mt, int nt) -> bool {  // does pixel tile mt exist and is its state zero in this column tile?
         if (PLAIN) return mt < MT;  // (plain mode: every existing tile of a listed pair is computed)
         if (mt >= MT) return false;
+        if (SYM) return __ldcg(epi.symq + (size_t)mt * NT + nt) != 0;  // is any original tile it overlaps quiet?
         const unsigned int* st = epi.tile_state + (size_t)mt * epi.flag_ld + 2 * nt;
         unsigned int wd = __ldcg(st);
         if (2 * nt + 1 < epi.flag_ld) wd |= __ldcg(st + 1);
@@ -690,7 +794,8 @@ screen8_pair_kernel(const __grid_constant__ CUtensorMap map_a8, const __grid_con
                     uint8_t* sb = stage_base + stage * P2_STAGE_BYTES;
                     if (rank == 0) mbar_arrive_expect_tx(&full[stage], 2 * P2_STAGE_BYTES);
                     tma_load_2d_pair(sb, &map_a8, &full[stage], kb * BKE, mt * BM);
-                    tma_load_2d_pair(sb + A_TILE_BYTES, &map_b8, &full[stage], kb * BKE, nt * BN + (int)rank * (BN / 2));
+                    const int brow = SYM ? (nt == NT - 1 ? 0 : nphi + nt * BN) : nt * BN;  // (half-row view: rows of j >= n/2)
+                    tma_load_2d_pair(sb + A_TILE_BYTES, &map_b8, &full[stage], kb * BKE, brow + (int)rank * (BN / 2));
                     if (++stage == P2_STAGES) {
                         stage = 0;
                         phase ^= 1;
@@ -755,6 +860,7 @@ screen8_pair_kernel(const __grid_constant__ CUtensorMap map_a8, const __grid_con
             const bool q_own = quiet(mt, nt), q_other = quiet(2 * mtp + 1 - (int)rank, nt);
             const bool exists = mt < MT;
             bool list_it = exists && !q_own;  // a tile with signal goes straight to the next pass of the cascade
+            int sym_fail = 0;
             if (q_own || q_other) {
                 const int buf = use & 1;
                 mbar_wait(&tmem_full[buf], (use >> 1) & 1);
@@ -772,6 +878,11 @@ screen8_pair_kernel(const __grid_constant__ CUtensorMap map_a8, const __grid_con
                             else mbar_arrive_leader(&tmem_empty[buf]);
                         }
                         epilogue_tile<EPI_PLAIN>(epi, acc, lane, mt * BM + sub * 32, nt * BN + half * EPI_COLS);
+                    } else if (SYM) {
+                        const int fail = screen_tile_fails_sym<!F16>(epi, acc, lane, mt * BM + sub * 32, half * EPI_COLS,
+                                                                     nt == NT - 1 ? 2 : nphi - nt * BN, K);
+                        sym_fail = (int)__reduce_or_sync(0xffffffffu, (unsigned)fail);
+                        list_it = sym_fail != 0;
                     } else {
                         const bool fail = screen_tile_fails<!F16>(epi, acc, lane, mt * BM + sub * 32, nt * BN + half * EPI_COLS, K);
                         list_it = __any_sync(0xffffffffu, fail) != 0;
@@ -788,6 +899,48 @@ screen8_pair_kernel(const __grid_constant__ CUtensorMap map_a8, const __grid_con
                 ++use;
             }
             if (PLAIN) continue;
+            if (SYM) {  // original tiles that go on: (a) those with state, (b) those a failed bound of this warp touches
+                if (exists && lane == 0) {
+                    unsigned char* row = epi.need + (size_t)(mt >> 1) * epi.need_ld;
+                    int lo[4], hi[4];
+                    if (ew == 0) {  // (a) once per tile, per original tile (the ranges do not align with them)
+                        const unsigned int mask = (mt & 1) ? 0xFFFF0000u : 0x0000FFFFu;
+                        const unsigned int* st = epi.tile_state + (size_t)(mt >> 1) * epi.flag_ld;
+                        const int nr = sym_ranges(nt, NT, nphi, lo, hi);
+                        for (int r = 0; r < nr; ++r)
+                            for (int t = lo[r] >> 8; t <= (hi[r] - 1) >> 8; ++t) {
+                                unsigned int wd = __ldcg(st + 2 * t);
+                                if (2 * t + 1 < epi.flag_ld) wd |= __ldcg(st + 2 * t + 1);
+                                if (wd & mask) row[t] = 1;
+                            }
+                    }
+                    if (sym_fail) {  // (b) the 64 phi of this warp's 128 columns, both signs, the part (Re / Im) that failed
+                        int nr = 0;
+                        if (nt == NT - 1) {
+                            nr = sym_ranges(nt, NT, nphi, lo, hi);
+                        } else {
+                            const int j0 = nphi / 2 + (BN / 2) * nt + (EPI_COLS / 2) * half, j1 = min(j0 + EPI_COLS / 2, nphi);
+                            if (j0 < j1) {
+                                lo[0] = j0;
+                                hi[0] = j1;
+                                lo[1] = nphi - j1 + 1;
+                                hi[1] = nphi - j0 + 1;
+                                lo[2] = nphi + lo[0];
+                                hi[2] = nphi + hi[0];
+                                lo[3] = nphi + lo[1];
+                                hi[3] = nphi + hi[1];
+                                nr = 4;
+                            }
+                        }
+                        for (int r = 0; r < nr; ++r) {
+                            const int partbit = nr == 2 ? (1 << r) : (1 << (r >> 1));
+                            if (sym_fail & partbit)
+                                for (int t = lo[r] >> 8; t <= (hi[r] - 1) >> 8; ++t) row[t] = 1;
+                        }
+                    }
+                }
+                continue;
+            }
             if (list_it && lane == 0 && atomicMax(last_listed, ti) < ti) {
                 // tile id in the numbering of dft_gemm_kernel's tile_coords(t, MT, NT): invert it
                 const int g = mt / RASTER_GROUP, first = g * RASTER_GROUP;
@@ -927,7 +1080,7 @@ static int launch_mode(const csr_plan* plan, bool adjoint, const CUtensorMap& a_
         CSR_CUDA(cudaFuncSetAttribute(dft_gemm_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
         configured = true;
     }
-    const int K = adjoint ? 2 * plan->m : 2 * plan->n;
+    const int K = MODE == EPI_SCREEN8 ? plan->ld8 : (adjoint ? 2 * plan->m : 2 * plan->n);  // (fp8 rows are padded)
     const int N = adjoint ? 2 * plan->n : 2 * plan->m;
     const int MT = (P + BM - 1) / BM;
     const int NT = (N + BN - 1) / BN;
@@ -1018,7 +1171,7 @@ int launch_dft_gemm(const csr_plan* plan, bool adjoint, const __half* a_hi, cons
     int rc;
     if (epi.mode == EPI_SCREEN8) {  // a_hi is the fp8 copy of the operand (bytes, pitch ld8); there is no lo part
         CSR_REQUIRE(adjoint, "fp8 screening exists for the adjoint only");
-        rc = cached_operand_map(&ma_hi, a_hi, P, K, plan->ld8, 1);
+        rc = cached_operand_map(&ma_hi, a_hi, P, plan->ld8, plan->ld8, 1);
         ma_lo = ma_hi;
     } else {
         rc = cached_operand_map(&ma_hi, a_hi, P, K, ldk, 2);
@@ -1116,9 +1269,12 @@ int launch_split_tile_lists(const unsigned char* need, const unsigned char* excl
 template <int PMODE>
 static int launch_pair_kernel(const csr_plan* plan, const CUtensorMap& ma, const CUtensorMap& mb, int P, const GemmEpilogue& epi,
                               cudaStream_t stream) {
-    const int K = 2 * plan->m;
-    const int MT = (P + BM - 1) / BM;
-    const int NT = (epi.N + BN - 1) / BN;
+    const bool sym = PMODE >= 3;
+    // symmetric modes: K = one half row, MT counts groups of 64 lines of sight (128 half rows), NT the tiles of 128
+    // non-negative phi (256 half rows of the table) plus the tile of the one cell without a mirror
+    const int K = sym ? (PMODE == 3 ? plan->ld8 / 2 : plan->m) : (PMODE == 0 ? plan->ld8 : 2 * plan->m);  // (fp8 rows are padded)
+    const int MT = sym ? (P + BM / 2 - 1) / (BM / 2) : (P + BM - 1) / BM;
+    const int NT = sym ? (plan->n + BN - 1) / BN + 1 : (epi.N + BN - 1) / BN;
     static int max_clusters = 0;
     if (max_clusters == 0) {
         CSR_CUDA(cudaFuncSetAttribute(screen8_pair_kernel<PMODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, P2_SMEM_BYTES));
@@ -1144,7 +1300,7 @@ static int launch_pair_kernel(const csr_plan* plan, const CUtensorMap& ma, const
     const int clusters = min(pairs, max_clusters);
     ProfiledLaunch rec;
     if (g_profile) {
-        rec.kind = PMODE == 1 ? 10 : (PMODE == 2 ? 8 : 9);
+        rec.kind = PMODE == 1 ? 10 : ((PMODE == 2 || PMODE == 4) ? 8 : 9);
         CSR_CUDA(pooled_event(&rec.start));
         CSR_CUDA(pooled_event(&rec.stop));
         CSR_CUDA(cudaEventRecord(rec.start, stream));
@@ -1168,9 +1324,41 @@ int launch_screen8_pair(const csr_plan* plan, const unsigned char* a8, int P, co
     epi.m = plan->m;
     CSR_REQUIRE(epi.abs_sum && epi.tile_state && epi.out_list && epi.out_count, "screening launch: missing argument");
     CUtensorMap ma;
-    int rc = cached_operand_map(&ma, a8, P, 2 * plan->m, plan->ld8, 1);
+    int rc = cached_operand_map(&ma, a8, P, plan->ld8, plan->ld8, 1);
     if (rc) return rc;
     return launch_pair_kernel<0>(plan, ma, plan->map_adj8_half, P, epi, stream);
+}
+
+size_t sym_scratch_bytes(const csr_plan* plan, int P) {
+    const size_t MTo = (P + BM - 1) / BM, NTo = (2 * plan->n + BN - 1) / BN;
+    const size_t MTg = (P + BM / 2 - 1) / (BM / 2), NTs = (plan->n + BN - 1) / BN + 1;
+    return align256(MTo * NTo) + align256(MTg * NTs);
+}
+
+int launch_screen_sym_pair(const csr_plan* plan, const void* a, bool fp8, int P, const GemmEpilogue& epi_in, unsigned char* need,
+                           cudaStream_t stream) {
+    CSR_REQUIRE(P > 0 && plan->sym_ok && (fp8 || plan->sym16_ok) && need, "symmetric screening: not available for this plan");
+    GemmEpilogue epi = epi_in;
+    epi.P = P;
+    epi.N = 2 * plan->n;
+    epi.ld_out = plan->ld2n;
+    epi.m = plan->m;
+    CSR_REQUIRE(epi.abs_sum && epi.tile_state && epi.out_list && epi.out_count && !epi.tile_list, "pair screening: missing argument");
+    const int MTo = (P + BM - 1) / BM, NTo = (2 * plan->n + BN - 1) / BN;
+    epi.need = need;
+    epi.need_ld = NTo;
+    CSR_CUDA(cudaMemsetAsync(need, 0, (size_t)MTo * NTo, stream));
+    const int MTg = (P + BM / 2 - 1) / (BM / 2), NTs = (plan->n + BN - 1) / BN + 1;
+    unsigned char* symq = need + align256((size_t)MTo * NTo);  // (the scratch holds both maps: sym_scratch_bytes)
+    epi.symq = symq;
+    sym_quiet_kernel<<<(MTg * NTs + 255) / 256, 256, 0, stream>>>(epi.tile_state, epi.flag_ld, MTg, NTs, plan->n, symq);
+    CSR_LAUNCHED();
+    CUtensorMap ma;
+    int rc = fp8 ? cached_operand_map(&ma, a, 2 * P, plan->m, plan->ld8 / 2, 1) : cached_operand_map(&ma, a, 2 * P, plan->m, plan->m, 2);
+    if (rc) return rc;
+    rc = fp8 ? launch_pair_kernel<3>(plan, ma, plan->map_sym8, P, epi, stream) : launch_pair_kernel<4>(plan, ma, plan->map_sym16, P, epi, stream);
+    if (rc) return rc;
+    return launch_split_tile_lists(need, nullptr, P, 2 * plan->n, epi.out_list, epi.out_count, nullptr, nullptr, stream);
 }
 
 // the fp16 screening test on CTA pairs over every quiet tile (no fp8 pass in front): for residuals whose l1 norm makes

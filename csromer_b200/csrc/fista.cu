@@ -116,8 +116,9 @@ static FistaWs carve_fista(const csr_plan* plan, const csr_wavelet* wav, int P, 
     f.tile_list2 = b.take<int>((size_t)((P + BM - 1) / BM) * ((2 * plan->n + BN - 1) / BN));
     f.r8 = b.take<unsigned char>((size_t)P * plan->ld8);
     f.mma_count = b.take<unsigned long long>(4);
+    f.need[0] = b.take<unsigned char>(sym_scratch_bytes(plan, P));
     f.sig = f.gcoef = f.wav_ws = nullptr;
-    f.coef_flags[0] = f.coef_flags[1] = f.redo_flags = f.need[0] = f.need[1] = nullptr;
+    f.coef_flags[0] = f.coef_flags[1] = f.redo_flags = f.need[1] = nullptr;
     f.tile_list3 = nullptr;
     f.eps = nullptr;
     if (wav) {
@@ -128,7 +129,6 @@ static FistaWs carve_fista(const csr_plan* plan, const csr_wavelet* wav, int P, 
         f.coef_flags[1] = b.take<unsigned char>((size_t)P * coef_flag_ld(wav));
         f.redo_flags = b.take<unsigned char>((size_t)P * coef_flag_ld(wav));
         const size_t tiles = (size_t)((P + BM - 1) / BM) * ((2 * plan->n + BN - 1) / BN);
-        f.need[0] = b.take<unsigned char>(tiles);
         f.need[1] = b.take<unsigned char>(tiles);
         f.tile_list3 = b.take<int>(tiles);
         f.eps = b.take<float>(P);
@@ -259,6 +259,7 @@ extern "C" int csr_fista(csr_plan* plan, csr_wavelet* wav, const csr_fista_args*
         if ((rc = launch_block_flags(w.z, ld2n, 2 * n, P, w.zero_flags, w.flag_ld, w.tile_flags, stream))) return rc;
     }
     CSR_CUDA(cudaMemsetAsync(w.mma_count, 0, 4 * sizeof(unsigned long long), stream));
+    if (use_screen8) CSR_CUDA(cudaMemsetAsync(w.r8, 0, (size_t)P * plan->ld8, stream));  // (the padding of the fp8 rows stays zero)
     if (a.delta) CSR_CUDA(cudaMemsetAsync(a.delta, 0, sizeof(float) * P, stream));
 
     const bool fused_wavelet = wav && wavelet_fusable(wav) && options().fused_wavelet != 0;
@@ -339,17 +340,24 @@ extern "C" int csr_fista(csr_plan* plan, csr_wavelet* wav, const csr_fista_args*
             e.flag_ld = w.flag_ld;
             e.mma_count = w.mma_count;
             int* counts = reinterpret_cast<int*>(w.screen_hdr);
+            const bool sym = options().pair != 0 && options().sym != 0 && plan->sym_ok;  // mirror-symmetric screening
             if (screen16_pair) {  // one fp16 pass on CTA pairs over every quiet tile
                 e.mode = EPI_SCREEN;
                 e.out_list = w.tile_list;
                 e.out_count = counts;
-                if ((rc = launch_screen16_pair(plan, w.r_hi, P, e, stream))) return rc;
+                if (sym && plan->sym16_ok) {
+                    if ((rc = launch_screen_sym_pair(plan, w.r_hi, false, P, e, w.need[0], stream))) return rc;
+                } else {
+                    if ((rc = launch_screen16_pair(plan, w.r_hi, P, e, stream))) return rc;
+                }
             } else {
                 if (use_screen8) {
                     e.mode = EPI_SCREEN8;
                     e.out_list = w.tile_list2;
                     e.out_count = counts + 1;
-                    if (options().pair != 0 && P > BM) {
+                    if (sym) {
+                        if ((rc = launch_screen_sym_pair(plan, w.r8, true, P, e, w.need[0], stream))) return rc;
+                    } else if (options().pair != 0 && P > BM) {
                         if ((rc = launch_screen8_pair(plan, w.r8, P, e, stream))) return rc;
                     } else {
                         if ((rc = launch_dft_gemm(plan, true, reinterpret_cast<const __half*>(w.r8), nullptr, P, e, stream))) return rc;

@@ -81,10 +81,11 @@ __global__ void twiddle_adj_kernel(const double* __restrict__ lambda2, double l2
     const unsigned char s8 = __nv_cvt_float_to_fp8((float)(sn * (double)kTwiddleScale8), __NV_SATFINITE, __NV_E4M3);
     const unsigned char ns8 = __nv_cvt_float_to_fp8((float)(-sn * (double)kTwiddleScale8), __NV_SATFINITE, __NV_E4M3);
     const size_t q_re = (size_t)j * ld8, q_im = (size_t)(n + j) * ld8;
+    const int h8 = ld8 / 2;  // the second half of an fp8 row starts at ld8/2 (a multiple of 16): half-row views exist
     Tt8[q_re + i] = c8;
-    Tt8[q_re + m + i] = s8;
+    Tt8[q_re + h8 + i] = s8;
     Tt8[q_im + i] = ns8;
-    Tt8[q_im + m + i] = c8;
+    Tt8[q_im + h8 + i] = c8;
 }
 
 }  // namespace csr
@@ -94,7 +95,8 @@ Options& options() {
     static Options o = {getenv("CSR_NO_ZERO_SKIP") == nullptr, getenv("CSR_NO_K_SKIP") == nullptr,
                         getenv("CSR_NO_FUSED_WAVELET") == nullptr, getenv("CSR_NO_SCREEN") == nullptr,
                         getenv("CSR_NO_SCREEN8") == nullptr, getenv("CSR_NO_PAIR") == nullptr,
-                        getenv("CSR_NO_WAVELET_VEC4") == nullptr, getenv("CSR_NO_SCREEN16_PAIR") == nullptr,
+                        getenv("CSR_NO_WAVELET_VEC4") == nullptr, getenv("CSR_NO_SYM") == nullptr,
+                        getenv("CSR_NO_SCREEN16_PAIR") == nullptr,
                         getenv("CSR_NO_WAVELET_SCREEN") == nullptr};
     return o;
 }
@@ -114,6 +116,7 @@ extern "C" int csr_set_option(const char* name, int value) {
     else if (!strcmp(name, "wavelet_vec4")) o.wavelet_vec4 = value != 0;
     else if (!strcmp(name, "wavelet_screen")) o.wavelet_screen = value != 0;
     else if (!strcmp(name, "screen16_pair")) o.screen16_pair = value != 0;
+    else if (!strcmp(name, "sym")) o.sym = value != 0;
     else {
         set_error("csr_set_option: unknown option '%s'", name);
         return CSR_ERR_ARG;
@@ -183,8 +186,17 @@ static int plan_build(csr_plan* p, const double* lambda2, const double* phi) {
     if ((rc = make_operand_map(&p->map_fwd_lo, p->T_lo, 2 * m, 2 * n, p->ld2n, BN))) return rc;
     if ((rc = make_operand_map(&p->map_adj_hi, p->Tt_hi, 2 * n, 2 * m, p->ld2m, BN))) return rc;
     if ((rc = make_operand_map(&p->map_adj_lo, p->Tt_lo, 2 * n, 2 * m, p->ld2m, BN))) return rc;
-    if ((rc = make_operand_map(&p->map_adj8, p->Tt8, 2 * n, 2 * m, p->ld8, BN, 1))) return rc;
-    if ((rc = make_operand_map(&p->map_adj8_half, p->Tt8, 2 * n, 2 * m, p->ld8, BN / 2, 1))) return rc;
+    if ((rc = make_operand_map(&p->map_adj8, p->Tt8, 2 * n, p->ld8, p->ld8, BN, 1))) return rc;
+    if ((rc = make_operand_map(&p->map_adj8_half, p->Tt8, 2 * n, p->ld8, p->ld8, BN / 2, 1))) return rc;
+    // mirror symmetry of the phi grid (exact in fp64: sincos is odd / even, so the tables mirror exactly)
+    p->sym_ok = (n % 2 == 0 && n >= 4) ? 1 : 0;
+    for (int j = 1; j < n && p->sym_ok; ++j)
+        if (phi[j] != -phi[n - j]) p->sym_ok = 0;
+    p->sym16_ok = p->sym_ok && p->ld2m == 2 * m && m % 8 == 0;
+    if (p->sym_ok) {
+        if ((rc = make_operand_map(&p->map_sym8, p->Tt8, 2 * n, m, p->ld8 / 2, BN / 2, 1))) return rc;
+        if (p->sym16_ok && (rc = make_operand_map(&p->map_sym16, p->Tt_hi, 2 * n, m, m, BN / 2))) return rc;
+    }
     if ((rc = make_operand_map(&p->map_adj_hi_half, p->Tt_hi, 2 * n, 2 * m, p->ld2m, BN / 2))) return rc;
     return CSR_OK;
 }
@@ -203,7 +215,7 @@ extern "C" int csr_plan_create(csr_plan** out, const double* lambda2, int m, dou
     p->n = n;
     p->ld2m = round_up(2 * m, 8);
     p->ld2n = round_up(2 * n, 8);
-    p->ld8 = round_up(2 * m, 16);
+    p->ld8 = 2 * round_up(m, 16);  // [first half | zero padding | second half | zero padding]
     p->l2_ref = l2_ref;
     int rc = plan_build(p, lambda2, phi);
     if (rc != CSR_OK) {

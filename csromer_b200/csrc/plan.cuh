@@ -21,6 +21,12 @@ struct csr_plan {
     CUtensorMap map_fwd_hi, map_fwd_lo, map_adj_hi, map_adj_lo, map_adj8;
     CUtensorMap map_adj8_half;  // Tt8 with a 128-row box: half a B tile per CTA of a cta_group::2 pair
     CUtensorMap map_adj_hi_half;  // Tt_hi with a 128-row box (the one-product plain adjoint on CTA pairs)
+    // Mirror-symmetric screening (dft_gemm.cu): when phi_j = -phi_{n-j} the tables of +phi and -phi differ only in the
+    // sign of the sines, so the rows (cos theta_{.,j}, sin theta_{.,j}), j >= n/2, of Tt -- read as a [4n, m] matrix of
+    // half rows -- bound the gradient at both +phi_j and -phi_j with half the K and half the operand bytes
+    int sym_ok;                   // the phi grid is exactly antisymmetric about index n/2 (and n is even)
+    int sym16_ok;                 // ... and the fp16 table can be read as half rows (ld2m == 2m, m % 8 == 0)
+    CUtensorMap map_sym8, map_sym16;  // half-row views [2n rows, m], pitch ld8/2 bytes / m halves, 128-row box
     size_t table_bytes;
 };
 
@@ -89,6 +95,9 @@ struct GemmEpilogue {
     int* out_count;                 //             ... and their number (zeroed by the caller)
     const int* tile_list;           // any mode: process tiles tile_list[0 .. *tile_count) instead of all MT*NT; null = all
     const int* tile_count;
+    const unsigned char* symq;      // mirror-symmetric screening: per (64-LOS group, symmetric tile) bits of the ranges with state
+    unsigned char* need;            // mirror-symmetric screening: [MT, need_ld] bytes, 1 = tile must go on (zeroed by the caller)
+    int need_ld;
     unsigned long long* mma_count;  // optional: += K blocks x products issued (executed-work accounting)
     int debug;                 // measurement aid (CSR_DEBUG_EPI): bit 0 skips epilogue loads, bit 1 skips stores
 };
@@ -130,6 +139,11 @@ int launch_screen_eps(const float* abs_sum, const float* a_scale, int K, float* 
 int launch_split_tile_lists(const unsigned char* need, const unsigned char* exclude, int P, int N, int* list_a, int* count_a,
                             int* list_b, int* count_b, cudaStream_t stream);
 int launch_screen8_pair(const csr_plan* plan, const unsigned char* a8, int P, const GemmEpilogue& epi, cudaStream_t stream);
+// mirror-symmetric screening on CTA pairs (plan->sym_ok): fp8 (a = fp8 residual copy) or fp16 (a = r_hi, plan->sym16_ok);
+// tiles that are not quiet or fail the test end up in epi.out_list / out_count; `need` is scratch of sym_scratch_bytes()
+size_t sym_scratch_bytes(const csr_plan* plan, int P);
+int launch_screen_sym_pair(const csr_plan* plan, const void* a, bool fp8, int P, const GemmEpilogue& epi, unsigned char* need,
+                           cudaStream_t stream);
 int launch_screen16_pair(const csr_plan* plan, const __half* a_hi, int P, const GemmEpilogue& epi, cudaStream_t stream);
 // EPI_PLAIN1 on CTA pairs; epi.tile_list / tile_count name PAIRS of pixel tiles (launch_pair_list), null = all
 int launch_plain1_pair(const csr_plan* plan, const __half* a_hi, int P, const GemmEpilogue& epi, cudaStream_t stream);

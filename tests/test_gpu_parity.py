@@ -223,13 +223,16 @@ def test_sparsity_shortcuts_are_bit_exact(nch, P, K, kw):
     src, par = make_batch(nch, P, seed=11 + P, **kw)
     results = []
     try:
-        for zero_skip, k_skip, screen, screen8, pair in ((1, 1, 1, 1, 1), (1, 1, 1, 1, 0), (1, 1, 1, 0, 0), (1, 1, 0, 0, 0),
-                                                        (1, 0, 1, 1, 1), (1, 0, 0, 0, 0), (0, 0, 0, 0, 0)):
+        # (sym: the pair kernels screen +phi and -phi together, half the K; pair = 1, sym = 0 is the plain pair kernel)
+        for zero_skip, k_skip, screen, screen8, pair, sym in ((1, 1, 1, 1, 1, 1), (1, 1, 1, 1, 1, 0), (1, 1, 1, 1, 0, 0),
+                                                             (1, 1, 1, 0, 0, 0), (1, 1, 0, 0, 0, 0), (1, 0, 1, 1, 1, 1),
+                                                             (1, 0, 0, 0, 0, 0), (0, 0, 0, 0, 0, 0)):
             _lib.set_option("zero_skip", zero_skip)
             _lib.set_option("k_skip", k_skip)
             _lib.set_option("screen", screen)
             _lib.set_option("screen8", screen8)
             _lib.set_option("pair", pair)
+            _lib.set_option("sym", sym)
             cost, X, l1, lam0, noise = run_fista(src, par, K)
             results.append((np.array(X.data, copy=True), np.array(cost, copy=True), np.array(src.model_data, copy=True)))
     finally:
@@ -238,6 +241,7 @@ def test_sparsity_shortcuts_are_bit_exact(nch, P, K, kw):
         _lib.set_option("screen", 1)
         _lib.set_option("screen8", 1)
         _lib.set_option("pair", 1)
+        _lib.set_option("sym", 1)
     assert np.count_nonzero(results[0][0]) > 0 and np.count_nonzero(results[0][0]) < 0.2 * results[0][0].size
     for other in results[1:]:
         for a, b in zip(results[0], other):
