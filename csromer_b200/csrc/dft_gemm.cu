@@ -647,12 +647,20 @@ __device__ __forceinline__ int sym_ranges(int nt, int NT, int n, int (&lo)[4], i
 // rows of the half-row view: row = 2 p + h; `ncols` valid columns from col0 (each phi is a (cos, sin) column pair).
 // The thread that holds (C_alpha, S_alpha) of a (line of sight, phi) and the one that holds (C_beta, S_beta) are four lanes
 // apart (consecutive rows of the fragment): one exchange gives each of them one of the two sums |C_x| + |S_y|.
-// Returns bit 0: a bound on Re F failed (the alpha rows test |C_alpha| + |S_beta|), bit 1: one on Im F (beta rows).
+// Returns which bounds failed, attributed to the ORIGINAL column tiles they belong to: bit 4 part + k, part 0 = Re F (the
+// alpha rows test |C_alpha| + |S_beta|), 1 = Im F (beta rows); k = 0 / 1: the first / second original tile of the +phi
+// columns of this warp's 64 phi, k = 2 / 3: of its -phi columns (a run of 64 columns meets at most two tiles of 256).
+// jw = phi index of the warp's first column pair (regular tiles), -1 for the tile of the cell without a mirror.
 template <bool F8>
 __device__ __forceinline__ int screen_tile_fails_sym(const GemmEpilogue& epi, const float (&acc)[EPI_COLS], int lane, int row0,
-                                                     int col0, int ncols, int Khalf) {
+                                                     int col0, int ncols, int Khalf, int jw) {
     const int quad = lane & 3;
-    const int part = 1 << ((lane >> 2) & 1);  // (row0 and the row offsets 8 rh + 16 lh are even)
+    const int part = (lane >> 2) & 1;  // (row0 and the row offsets 8 rh + 16 lh are even)
+    const int nphi = epi.N >> 1;
+    // columns of this lane's part: + side  base_p + j  (Re: j, Im: n + j),  - side  base_m - j  (Re: n - j, Im: 2n - j);
+    // kk = phi offset inside the warp's run; the original tile changes at kk = split
+    const int split_p = jw < 0 ? 64 : 256 - (((part ? nphi : 0) + jw) & 255);
+    const int split_m = jw < 0 ? 64 : (((part ? 2 * nphi : nphi) - jw) & 255) + 1;
     int fail = 0;
 #pragma unroll
     for (int lh = 0; lh < 2; ++lh) {
@@ -670,19 +678,40 @@ __device__ __forceinline__ int screen_tile_fails_sym(const GemmEpilogue& epi, co
                 lim = F8 ? lam * __ldg(epi.a_scale + p) * (kTwiddleScale8 * kOperandScale8) - (68.f * sp + 0.6f * (float)Khalf)
                          : lam * __ldg(epi.a_scale + p) * (1.f / kTwiddleDescale) - screen_slack(2 * Khalf) * sp;
             }
-            float mx = 0.f;
-            bool bad = false;
+            // fast path: one maximum over the thread's 16 column pairs.  |C| + |S'| >= 0 or NaN: as unsigned bit patterns
+            // they order like the floats with NaN on top, so an integer max carries a NaN through to the comparison
+            unsigned int mxi = 0u;
 #pragma unroll
             for (int jj = 0; jj < 16; ++jj) {
                 const int col = col0 + 8 * jj + 2 * quad;
                 const int ai = (((lh * 2 + (jj >> 3)) * 8 + (jj & 7)) * 2 + rh) * 2;
                 // own (C, S); the partner row's S (all lanes take part in the exchange)
                 const float s_other = __shfl_xor_sync(0xffffffffu, acc[ai + 1], 4);
-                if (col >= ncols) continue;
-                mx = fmaxf(mx, fabsf(acc[ai]) + fabsf(s_other));
-                bad |= (acc[ai] != acc[ai]) | (s_other != s_other);
+                if (col < ncols) mxi = max(mxi, __float_as_uint(fabsf(acc[ai]) + fabsf(s_other)));
             }
-            if (row_ok && active && (bad | !(lim > 0.f) | !(mx < lim))) fail |= part;
+            const bool ok = !(row_ok && active) || ((lim > 0.f) && (__uint_as_float(mxi) < lim));
+            if (__all_sync(0xffffffffu, ok)) continue;  // (warp-uniform: the slow path exchanges again)
+            // slow path (tiles near the sources): which original tile do the failing columns belong to?
+            float mp0 = 0.f, mp1 = 0.f, mm0 = 0.f, mm1 = 0.f;  // maxima over the + / - columns in their first / second tile
+            bool bad = false;
+#pragma unroll
+            for (int jj = 0; jj < 16; ++jj) {
+                const int col = col0 + 8 * jj + 2 * quad;
+                const int ai = (((lh * 2 + (jj >> 3)) * 8 + (jj & 7)) * 2 + rh) * 2;
+                const float s_other = __shfl_xor_sync(0xffffffffu, acc[ai + 1], 4);
+                if (col >= ncols) continue;
+                const float v = fabsf(acc[ai]) + fabsf(s_other);
+                bad |= (v != v);
+                const int kk = 4 * jj + quad;
+                if (kk < split_p) mp0 = fmaxf(mp0, v); else mp1 = fmaxf(mp1, v);
+                if (kk < split_m) mm0 = fmaxf(mm0, v); else mm1 = fmaxf(mm1, v);
+            }
+            if (row_ok && active) {
+                if (bad | !(lim > 0.f))
+                    fail |= 15 << (4 * part);
+                else
+                    fail |= ((!(mp0 < lim)) | ((!(mp1 < lim)) << 1) | ((!(mm0 < lim)) << 2) | ((!(mm1 < lim)) << 3)) << (4 * part);
+            }
         }
     }
     return fail;
@@ -776,6 +805,16 @@ screen8_pair_kernel(const __grid_constant__ CUtensorMap map_a8, const __grid_con
         if (2 * nt + 1 < epi.flag_ld) wd |= __ldcg(st + 1);
         return wd == 0u;
     };
+    // symmetric modes: the quiet bytes of both groups of pair tile ti (bits 0-7: CTA 0's group, 8-15: CTA 1's), fetched one
+    // tile ahead so that no role waits for an L2 round trip at the top of a tile
+    auto qraw = [&](int ti) -> unsigned int {
+        if (!SYM || ti >= total) return 0u;
+        int mtp, nt;
+        tile_coords(pair_id(ti), MTP, NT, mtp, nt);
+        const unsigned int a = 2 * mtp < MT ? __ldcg(epi.symq + (size_t)(2 * mtp) * NT + nt) : 0u;
+        const unsigned int b = 2 * mtp + 1 < MT ? __ldcg(epi.symq + (size_t)(2 * mtp + 1) * NT + nt) : 0u;
+        return a | (b << 8);
+    };
 
     if (warp < 4) {
       asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
@@ -784,10 +823,13 @@ screen8_pair_kernel(const __grid_constant__ CUtensorMap map_a8, const __grid_con
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
+            unsigned int qn = qraw(cluster_id);
             for (int ti = cluster_id; ti < total; ti += nclusters) {
                 int mtp, nt;
                 tile_coords(pair_id(ti), MTP, NT, mtp, nt);
-                if (!quiet(2 * mtp, nt) && !quiet(2 * mtp + 1, nt)) continue;
+                const unsigned int qc = qn;
+                qn = qraw(ti + nclusters);
+                if (SYM ? qc == 0u : (!quiet(2 * mtp, nt) && !quiet(2 * mtp + 1, nt))) continue;
                 const int mt = 2 * mtp + (int)rank;
                 for (int kb = 0; kb < KB; ++kb) {
                     mbar_wait(&empty[stage], phase ^ 1);
@@ -810,10 +852,13 @@ screen8_pair_kernel(const __grid_constant__ CUtensorMap map_a8, const __grid_con
             int stage = 0;
             uint32_t phase = 0, use = 0;
             unsigned long long issued = 0;
+            unsigned int qn = qraw(cluster_id);
             for (int ti = cluster_id; ti < total; ti += nclusters) {
                 int mtp, nt;
                 tile_coords(pair_id(ti), MTP, NT, mtp, nt);
-                if (!quiet(2 * mtp, nt) && !quiet(2 * mtp + 1, nt)) continue;
+                const unsigned int qc = qn;
+                qn = qraw(ti + nclusters);
+                if (SYM ? qc == 0u : (!quiet(2 * mtp, nt) && !quiet(2 * mtp + 1, nt))) continue;
                 const int buf = use & 1;
                 mbar_wait(&tmem_empty[buf], ((use >> 1) & 1) ^ 1);
                 tc_fence_after();
@@ -853,11 +898,15 @@ screen8_pair_kernel(const __grid_constant__ CUtensorMap map_a8, const __grid_con
         const int half = ew >> 2;
         uint32_t use = 0;
         int ti = 0;  // running index of this CTA's tiles (for the one-lister-per-tile rule)
+        unsigned int qn = qraw(cluster_id);
         for (int tq = cluster_id; tq < total; tq += nclusters, ++ti) {
             int mtp, nt;
             tile_coords(pair_id(tq), MTP, NT, mtp, nt);
             const int mt = 2 * mtp + (int)rank;
-            const bool q_own = quiet(mt, nt), q_other = quiet(2 * mtp + 1 - (int)rank, nt);
+            const unsigned int qc = qn;
+            qn = qraw(tq + nclusters);
+            const bool q_own = SYM ? ((qc >> (8 * rank)) & 0xffu) != 0u : quiet(mt, nt);
+            const bool q_other = SYM ? ((qc >> (8 * (1 - rank))) & 0xffu) != 0u : quiet(2 * mtp + 1 - (int)rank, nt);
             const bool exists = mt < MT;
             bool list_it = exists && !q_own;  // a tile with signal goes straight to the next pass of the cascade
             int sym_fail = 0;
@@ -880,7 +929,8 @@ screen8_pair_kernel(const __grid_constant__ CUtensorMap map_a8, const __grid_con
                         epilogue_tile<EPI_PLAIN>(epi, acc, lane, mt * BM + sub * 32, nt * BN + half * EPI_COLS);
                     } else if (SYM) {
                         const int fail = screen_tile_fails_sym<!F16>(epi, acc, lane, mt * BM + sub * 32, half * EPI_COLS,
-                                                                     nt == NT - 1 ? 2 : nphi - nt * BN, K);
+                                                                     nt == NT - 1 ? 2 : nphi - nt * BN, K,
+                                                                     nt == NT - 1 ? -1 : nphi / 2 + (BN / 2) * nt + (EPI_COLS / 2) * half);
                         sym_fail = (int)__reduce_or_sync(0xffffffffu, (unsigned)fail);
                         list_it = sym_fail != 0;
                     } else {
@@ -914,28 +964,21 @@ screen8_pair_kernel(const __grid_constant__ CUtensorMap map_a8, const __grid_con
                                 if (wd & mask) row[t] = 1;
                             }
                     }
-                    if (sym_fail) {  // (b) the 64 phi of this warp's 128 columns, both signs, the part (Re / Im) that failed
-                        int nr = 0;
-                        if (nt == NT - 1) {
-                            nr = sym_ranges(nt, NT, nphi, lo, hi);
+                    if (sym_fail) {  // (b) the original tiles the failed bounds of this warp belong to
+                        if (nt == NT - 1) {  // the cell without a mirror: columns 0 (Re) and n (Im)
+                            if (sym_fail & 0x0f) row[0] = 1;
+                            if (sym_fail & 0xf0) row[nphi >> 8] = 1;
                         } else {
-                            const int j0 = nphi / 2 + (BN / 2) * nt + (EPI_COLS / 2) * half, j1 = min(j0 + EPI_COLS / 2, nphi);
-                            if (j0 < j1) {
-                                lo[0] = j0;
-                                hi[0] = j1;
-                                lo[1] = nphi - j1 + 1;
-                                hi[1] = nphi - j0 + 1;
-                                lo[2] = nphi + lo[0];
-                                hi[2] = nphi + hi[0];
-                                lo[3] = nphi + lo[1];
-                                hi[3] = nphi + hi[1];
-                                nr = 4;
+                            const int jw = nphi / 2 + (BN / 2) * nt + (EPI_COLS / 2) * half;
+                            for (int part = 0; part < 2; ++part) {
+                                const int bits = (sym_fail >> (4 * part)) & 15;
+                                const int tp = ((part ? nphi : 0) + jw) >> 8;             // + side: tiles tp, tp + 1
+                                const int tm = ((part ? 2 * nphi : nphi) - jw) >> 8;      // - side: tiles tm, tm - 1
+                                if (bits & 1) row[tp] = 1;
+                                if ((bits & 2) && tp + 1 < epi.need_ld) row[tp + 1] = 1;
+                                if (bits & 4) row[tm] = 1;
+                                if ((bits & 8) && tm > 0) row[tm - 1] = 1;
                             }
-                        }
-                        for (int r = 0; r < nr; ++r) {
-                            const int partbit = nr == 2 ? (1 << r) : (1 << (r >> 1));
-                            if (sym_fail & partbit)
-                                for (int t = lo[r] >> 8; t <= (hi[r] - 1) >> 8; ++t) row[t] = 1;
                         }
                     }
                 }
