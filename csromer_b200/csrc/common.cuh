@@ -188,6 +188,14 @@ __device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const CUtensorM
           "r"(c1)
         : "memory");
 }
+__device__ __forceinline__ void tma_load_4d_pair(void* smem_dst, const CUtensorMap* map, uint64_t* leader_bar, int c0, int c1,
+                                                 int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(leader_bar) & kPeerBitMask), "r"(c0),
+          "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
 // arrive on the leader CTA's copy of a barrier (from either CTA)
 __device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
     asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & kPeerBitMask) : "memory");

@@ -136,6 +136,32 @@ __device__ __forceinline__ void drain_chunk(uint32_t taddr, float (&acc)[EPI_COL
     }
 }
 
+// acc = the accumulator in TMEM (single-chain kernels: nothing to add to): the four loads are issued back to back and
+// waited for once, instead of four load / wait round trips
+__device__ __forceinline__ void tmem_ld_16x256b_x8_nowait(uint32_t taddr, uint32_t* r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.16x256b.x8.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void load_chunk(uint32_t taddr, float (&acc)[EPI_COLS]) {
+    uint32_t r[EPI_COLS];
+#pragma unroll
+    for (int lh = 0; lh < 2; ++lh)
+#pragma unroll
+        for (int ch = 0; ch < 2; ++ch)
+            tmem_ld_16x256b_x8_nowait(taddr + ((uint32_t)(16 * lh) << 16) + (uint32_t)(64 * ch), r + (lh * 2 + ch) * 32);
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int j = 0; j < EPI_COLS; ++j) acc[j] = __uint_as_float(r[j]);
+}
+
 // Fused epilogue on the register fragment of one thread.  row0 / col0: first row of the warp's 32 rows and first
 // of its 128 columns.  Every (row, 8-column block) costs one float2 access per array; the loads of 8 blocks of a row
 // are issued together before their results are used (x / z alias, the compiler cannot hoist them itself).
@@ -717,6 +743,69 @@ __device__ __forceinline__ int screen_tile_fails_sym(const GemmEpilogue& epi, co
     return fail;
 }
 
+// The same test when the A tile was loaded through the 4-D map (GemmEpilogue::sym_rows8): rows 16 G + 8 h + l of the tile
+// are row h (alpha / beta) of line of sight 8 G + l, so a thread's rows rh = 0 / 1 are the alpha and the beta row of ONE
+// line of sight and no exchange is needed.  row0: first row of the warp (a multiple of 32).
+template <bool F8>
+__device__ __forceinline__ int screen_tile_fails_sym8(const GemmEpilogue& epi, const float (&acc)[EPI_COLS], int lane, int row0,
+                                                      int col0, int ncols, int Khalf, int jw) {
+    const int quad = lane & 3;
+    const int nphi = epi.N >> 1;
+    int fail = 0;
+#pragma unroll
+    for (int lh = 0; lh < 2; ++lh) {
+        const int p = (row0 >> 1) + 8 * lh + (lane >> 2);
+        const bool row_ok = p < epi.P;
+        float lim = 0.f;
+        bool active = false;
+        if (row_ok) {
+            const float l0 = __ldg(epi.lambda0 + p), nz = __ldg(epi.noise + p);
+            const float lam = l0 - (float)epi.iter * nz;
+            active = (nz < l0) && (epi.iter == 0 || lam > 0.f) && (!epi.iter_cap || epi.iter < __ldg(epi.iter_cap + p));
+            const float sp = __ldg(epi.abs_sum + p);
+            lim = F8 ? lam * __ldg(epi.a_scale + p) * (kTwiddleScale8 * kOperandScale8) - (68.f * sp + 0.6f * (float)Khalf)
+                     : lam * __ldg(epi.a_scale + p) * (1.f / kTwiddleDescale) - screen_slack(2 * Khalf) * sp;
+        }
+        unsigned int mre = 0u, mim = 0u;  // (integer max of non-negative floats: a NaN ends up on top)
+#pragma unroll
+        for (int jj = 0; jj < 16; ++jj) {
+            const int col = col0 + 8 * jj + 2 * quad;
+            const int aa = (((lh * 2 + (jj >> 3)) * 8 + (jj & 7)) * 2 + 0) * 2, ab = aa + 2;  // alpha row (rh = 0), beta row (rh = 1)
+            if (col < ncols) {
+                mre = max(mre, __float_as_uint(fabsf(acc[aa]) + fabsf(acc[ab + 1])));      // |C_alpha| + |S_beta|
+                mim = max(mim, __float_as_uint(fabsf(acc[ab]) + fabsf(acc[aa + 1])));      // |C_beta| + |S_alpha|
+            }
+        }
+        if (!(row_ok && active)) continue;
+        const bool limok = lim > 0.f;
+        if (limok && __uint_as_float(mre) < lim && __uint_as_float(mim) < lim) continue;
+        // slow path (tiles near the sources): which original tiles do the failing columns belong to?
+#pragma unroll
+        for (int part = 0; part < 2; ++part) {
+            const int split_p = jw < 0 ? 64 : 256 - (((part ? nphi : 0) + jw) & 255);
+            const int split_m = jw < 0 ? 64 : (((part ? 2 * nphi : nphi) - jw) & 255) + 1;
+            float mp0 = 0.f, mp1 = 0.f, mm0 = 0.f, mm1 = 0.f;
+            bool bad = !limok;
+#pragma unroll
+            for (int jj = 0; jj < 16; ++jj) {
+                const int col = col0 + 8 * jj + 2 * quad;
+                if (col >= ncols) continue;
+                const int aa = (((lh * 2 + (jj >> 3)) * 8 + (jj & 7)) * 2 + 0) * 2, ab = aa + 2;
+                const float v = part ? fabsf(acc[ab]) + fabsf(acc[aa + 1]) : fabsf(acc[aa]) + fabsf(acc[ab + 1]);
+                bad |= (v != v);
+                const int kk = 4 * jj + quad;
+                if (kk < split_p) mp0 = fmaxf(mp0, v); else mp1 = fmaxf(mp1, v);
+                if (kk < split_m) mm0 = fmaxf(mm0, v); else mm1 = fmaxf(mm1, v);
+            }
+            if (bad)
+                fail |= 15 << (4 * part);
+            else
+                fail |= ((!(mp0 < lim)) | ((!(mp1 < lim)) << 1) | ((!(mm0 < lim)) << 2) | ((!(mm1 < lim)) << 3)) << (4 * part);
+        }
+    }
+    return fail;
+}
+
 // per (group of 64 lines of sight, symmetric column tile): 1 = some original tile this symmetric tile overlaps is quiet
 // (its state is identically zero), i.e. there is something to decide; the three roles of the pair kernel read this byte
 __global__ void sym_quiet_kernel(const unsigned int* __restrict__ tile_state, int flag_ld, int MTg, int NTs, int nphi,
@@ -835,7 +924,10 @@ screen8_pair_kernel(const __grid_constant__ CUtensorMap map_a8, const __grid_con
                     mbar_wait(&empty[stage], phase ^ 1);
                     uint8_t* sb = stage_base + stage * P2_STAGE_BYTES;
                     if (rank == 0) mbar_arrive_expect_tx(&full[stage], 2 * P2_STAGE_BYTES);
-                    tma_load_2d_pair(sb, &map_a8, &full[stage], kb * BKE, mt * BM);
+                    if (SYM && epi.sym_rows8)  // rows regrouped by the 4-D map: 8 groups of (alpha rows | beta rows) of 8 LOS
+                        tma_load_4d_pair(sb, &map_a8, &full[stage], kb * BKE, 0, 0, mt * 8);
+                    else
+                        tma_load_2d_pair(sb, &map_a8, &full[stage], kb * BKE, mt * BM);
                     const int brow = SYM ? (nt == NT - 1 ? 0 : nphi + nt * BN) : nt * BN;  // (half-row view: rows of j >= n/2)
                     tma_load_2d_pair(sb + A_TILE_BYTES, &map_b8, &full[stage], kb * BKE, brow + (int)rank * (BN / 2));
                     if (++stage == P2_STAGES) {
@@ -916,9 +1008,7 @@ screen8_pair_kernel(const __grid_constant__ CUtensorMap map_a8, const __grid_con
                 tc_fence_after();
                 if (q_own) {
                     float acc[EPI_COLS];
-#pragma unroll
-                    for (int j = 0; j < EPI_COLS; ++j) acc[j] = 0.f;
-                    drain_chunk(tmem_base + ((uint32_t)(sub * 32) << 16) + (uint32_t)(buf * BN + half * EPI_COLS), acc);
+                    load_chunk(tmem_base + ((uint32_t)(sub * 32) << 16) + (uint32_t)(buf * BN + half * EPI_COLS), acc);
                     if (PLAIN) {  // the accumulator is in registers: hand the TMEM buffer back before the global stores
                         tc_fence_before();
                         __syncwarp();
@@ -928,9 +1018,11 @@ screen8_pair_kernel(const __grid_constant__ CUtensorMap map_a8, const __grid_con
                         }
                         epilogue_tile<EPI_PLAIN>(epi, acc, lane, mt * BM + sub * 32, nt * BN + half * EPI_COLS);
                     } else if (SYM) {
-                        const int fail = screen_tile_fails_sym<!F16>(epi, acc, lane, mt * BM + sub * 32, half * EPI_COLS,
-                                                                     nt == NT - 1 ? 2 : nphi - nt * BN, K,
-                                                                     nt == NT - 1 ? -1 : nphi / 2 + (BN / 2) * nt + (EPI_COLS / 2) * half);
+                        const int jw = nt == NT - 1 ? -1 : nphi / 2 + (BN / 2) * nt + (EPI_COLS / 2) * half;
+                        const int ncv = nt == NT - 1 ? 2 : nphi - nt * BN;
+                        const int fail = epi.sym_rows8
+                                             ? screen_tile_fails_sym8<!F16>(epi, acc, lane, mt * BM + sub * 32, half * EPI_COLS, ncv, K, jw)
+                                             : screen_tile_fails_sym<!F16>(epi, acc, lane, mt * BM + sub * 32, half * EPI_COLS, ncv, K, jw);
                         sym_fail = (int)__reduce_or_sync(0xffffffffu, (unsigned)fail);
                         list_it = sym_fail != 0;
                     } else {
@@ -1378,6 +1470,47 @@ size_t sym_scratch_bytes(const csr_plan* plan, int P) {
     return align256(MTo * NTo) + align256(MTg * NTs);
 }
 
+// 4-D view of a [P, 2 halves] operand for the symmetric kernels: (k, line of sight within a group of 8, half, group), box
+// {one 128-byte row, 8, 2, 8} = 128 tile rows ordered [group][half][line of sight]
+static int cached_sym_map(CUtensorMap* map, const void* base, int P, int m, size_t row_bytes, size_t half_bytes, int elem_bytes) {
+    struct Entry {
+        const void* base;
+        int P, m, eb;
+        size_t rb, hb;
+        CUtensorMap map;
+    };
+    static thread_local Entry cache[8];
+    static thread_local int next = 0;
+    for (int i = 0; i < 8; ++i) {
+        const Entry& e = cache[i];
+        if (e.base == base && e.P == P && e.m == m && e.eb == elem_bytes && e.rb == row_bytes && e.hb == half_bytes) {
+            *map = e.map;
+            return CSR_OK;
+        }
+    }
+    EncodeTiledFn enc = get_encode_fn();
+    if (!enc) return CSR_ERR_CUDA;
+    if ((reinterpret_cast<uintptr_t>(base) & 15) || row_bytes % 16 || half_bytes % 16) return CSR_ERR_ARG;
+    cuuint64_t dims[4] = {(cuuint64_t)m, 8, 2, (cuuint64_t)((P + 7) / 8)};
+    cuuint64_t strides[3] = {(cuuint64_t)row_bytes, (cuuint64_t)half_bytes, (cuuint64_t)(8 * row_bytes)};
+    cuuint32_t box[4] = {(cuuint32_t)(BK * 2 / elem_bytes), 8, 2, 8};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = enc(map, elem_bytes == 1 ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4,
+                     const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return CSR_ERR_CUDA;  // (the caller falls back to the 2-D view)
+    Entry& e = cache[next];
+    next = (next + 1) % 8;
+    e.base = base;
+    e.P = P;
+    e.m = m;
+    e.eb = elem_bytes;
+    e.rb = row_bytes;
+    e.hb = half_bytes;
+    e.map = *map;
+    return CSR_OK;
+}
+
 int launch_screen_sym_pair(const csr_plan* plan, const void* a, bool fp8, int P, const GemmEpilogue& epi_in, unsigned char* need,
                            cudaStream_t stream) {
     CSR_REQUIRE(P > 0 && plan->sym_ok && (fp8 || plan->sym16_ok) && need, "symmetric screening: not available for this plan");
@@ -1397,7 +1530,16 @@ int launch_screen_sym_pair(const csr_plan* plan, const void* a, bool fp8, int P,
     sym_quiet_kernel<<<(MTg * NTs + 255) / 256, 256, 0, stream>>>(epi.tile_state, epi.flag_ld, MTg, NTs, plan->n, symq);
     CSR_LAUNCHED();
     CUtensorMap ma;
-    int rc = fp8 ? cached_operand_map(&ma, a, 2 * P, plan->m, plan->ld8 / 2, 1) : cached_operand_map(&ma, a, 2 * P, plan->m, plan->m, 2);
+    // rows regrouped so that a thread holds both rows of a line of sight (needs the operand allocated with its row count
+    // rounded up to 8: fista.cu); 2-D half-row view otherwise
+    static const bool rows8 = getenv("CSR_NO_SYM_ROWS8") == nullptr;
+    int rc = CSR_ERR_ARG;
+    if (rows8)
+        rc = fp8 ? cached_sym_map(&ma, a, P, plan->m, (size_t)plan->ld8, (size_t)plan->ld8 / 2, 1)
+                 : cached_sym_map(&ma, a, P, plan->m, (size_t)plan->ld2m * 2, (size_t)plan->m * 2, 2);
+    epi.sym_rows8 = rc == CSR_OK ? 1 : 0;
+    if (rc != CSR_OK)
+        rc = fp8 ? cached_operand_map(&ma, a, 2 * P, plan->m, plan->ld8 / 2, 1) : cached_operand_map(&ma, a, 2 * P, plan->m, plan->m, 2);
     if (rc) return rc;
     rc = fp8 ? launch_pair_kernel<3>(plan, ma, plan->map_sym8, P, epi, stream) : launch_pair_kernel<4>(plan, ma, plan->map_sym16, P, epi, stream);
     if (rc) return rc;

@@ -104,8 +104,8 @@ static FistaWs carve_fista(const csr_plan* plan, const csr_wavelet* wav, int P, 
     f.z = b.take<float>((size_t)P * ldc);
     f.f_dirty = b.take<float>((size_t)P * plan->ld2n);
     f.model = b.take<float>((size_t)P * plan->ld2m);
-    f.r_hi = b.take<__half>((size_t)P * plan->ld2m);
-    f.r_lo = b.take<__half>((size_t)P * plan->ld2m);
+    f.r_hi = b.take<__half>((size_t)round_up(P, 8) * plan->ld2m);  // (rows rounded up: the 4-D operand view reads groups of 8)
+    f.r_lo = b.take<__half>((size_t)round_up(P, 8) * plan->ld2m);
     f.z_hi = b.take<__half>((size_t)P * plan->ld2n);
     f.z_lo = b.take<__half>((size_t)P * plan->ld2n);
     f.flag_ld = (2 * plan->n + 127) / 128;
@@ -114,7 +114,7 @@ static FistaWs carve_fista(const csr_plan* plan, const csr_wavelet* wav, int P, 
     f.screen_hdr = b.take<float>((size_t)P + 8);
     f.tile_list = b.take<int>((size_t)((P + BM - 1) / BM) * ((2 * plan->n + BN - 1) / BN));
     f.tile_list2 = b.take<int>((size_t)((P + BM - 1) / BM) * ((2 * plan->n + BN - 1) / BN));
-    f.r8 = b.take<unsigned char>((size_t)P * plan->ld8);
+    f.r8 = b.take<unsigned char>((size_t)round_up(P, 8) * plan->ld8);
     f.mma_count = b.take<unsigned long long>(4);
     f.need[0] = b.take<unsigned char>(sym_scratch_bytes(plan, P));
     f.sig = f.gcoef = f.wav_ws = nullptr;
@@ -259,7 +259,7 @@ extern "C" int csr_fista(csr_plan* plan, csr_wavelet* wav, const csr_fista_args*
         if ((rc = launch_block_flags(w.z, ld2n, 2 * n, P, w.zero_flags, w.flag_ld, w.tile_flags, stream))) return rc;
     }
     CSR_CUDA(cudaMemsetAsync(w.mma_count, 0, 4 * sizeof(unsigned long long), stream));
-    if (use_screen8) CSR_CUDA(cudaMemsetAsync(w.r8, 0, (size_t)P * plan->ld8, stream));  // (the padding of the fp8 rows stays zero)
+    if (use_screen8) CSR_CUDA(cudaMemsetAsync(w.r8, 0, (size_t)round_up(P, 8) * plan->ld8, stream));  // (the padding of the fp8 rows stays zero)
     if (a.delta) CSR_CUDA(cudaMemsetAsync(a.delta, 0, sizeof(float) * P, stream));
 
     const bool fused_wavelet = wav && wavelet_fusable(wav) && options().fused_wavelet != 0;

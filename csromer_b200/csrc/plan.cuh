@@ -95,6 +95,8 @@ struct GemmEpilogue {
     int* out_count;                 //             ... and their number (zeroed by the caller)
     const int* tile_list;           // any mode: process tiles tile_list[0 .. *tile_count) instead of all MT*NT; null = all
     const int* tile_count;
+    int sym_rows8;                  // mirror-symmetric screening: the A tile arrives as [8 groups][alpha rows of 8 LOS | beta rows of
+                                    // the same 8 LOS] (4-D tensor map), so one thread holds both rows of a line of sight
     const unsigned char* symq;      // mirror-symmetric screening: per (64-LOS group, symmetric tile) bits of the ranges with state
     unsigned char* need;            // mirror-symmetric screening: [MT, need_ld] bytes, 1 = tile must go on (zeroed by the caller)
     int need_ld;
