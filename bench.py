@@ -445,11 +445,12 @@ def run_ours(args):
         k_tf = blocks[2] * block_flops / (k_ms * 1e-3) / 1e12
         k_peak, k_src = 2.0 * peak, ("2 x MEASURED_PEAKS.json bf16_tflops_sustained (%s): no fp8 figure is measured on this "
                                      "pool; nominal fp8 dense = 2 x bf16" % peaks["source"])
-        k_name = ("screen8_pair_kernel: fp8 (e4m3) screening pass of the adjoint transform on CTA pairs, tcgen05 "
-                  "cta_group::2 kind::f8f6f4")
-        k_note = ("achieved = fp8 flops the kernel issued (in-kernel counter) / its CUDA-event time; ncu: tensor pipe "
-                  "active 70 %, L2->SM operand traffic 4.6 GB per launch = 11.4 TB/s (the fabric is the bound), DRAM 69 MB "
-                  "(profiles/r1_final_gemm_metrics.json)")
+        k_name = ("screen8_pair_kernel<3>: mirror-symmetric fp8 (e4m3) screening pass of the adjoint transform on CTA pairs "
+                  "(+phi and -phi decided by one product with half the K), tcgen05 cta_group::2 kind::f8f6f4")
+        k_note = ("achieved = fp8 flops the kernel issued (in-kernel counter) / its CUDA-event time; the kernel is bound by the "
+                  "L2->SM operand fabric, not by the tensor pipe: ncu (profiles/r1_sym8_metrics.json) tensor pipe active 42 %, "
+                  "2.54 GB of operands per launch = 7.4-8.5 TB/s, DRAM 42 MB; the symmetric formulation halves both the flops "
+                  "and the operand bytes of the plain pair kernel (0.37 -> 0.30 ms per launch)")
     else:  # dense regime: the three-product kernels dominate
         k_ms = float(sum(ms[0][i] for i in (0, 1, 2, 3, 4, 5))) / args.steps
         k_tf = (blocks[0] + 3.0 * (ms[1][0] * ((P + 127) // 128) * ((2 * M_CH + 255) // 256) * ((2 * N_PHI + 63) // 64)
@@ -464,7 +465,7 @@ def run_ours(args):
                 "kernel_share_of_step": per_kind[dominant]["share_of_step"] if dominant else None,
                 "path": {"what": "all transform GEMM launches of the step: algorithmic 8 m n flops per line of sight per "
                                  "transform / their summed CUDA-event time. Exact sparsity shortcuts (forward K-block "
-                                 "skipping, fp8 -> fp16 safe screening of the adjoint; bit-identical results, "
+                                 "skipping, mirror-symmetric fp8 -> fp16 safe screening of the adjoint; bit-identical results, "
                                  "tests/test_gpu_parity.py::test_sparsity_shortcuts_are_bit_exact) let this exceed the "
                                  "dense bound of 1/3 of the tensor peak",
                          "algorithmic_tflops": path_ach, "frac_of_bf16_peak": path_ach / peak,
