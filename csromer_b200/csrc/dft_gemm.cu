@@ -196,6 +196,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmEpilogue& epi, const flo
             const size_t row_off = (size_t)row * epi.ld_out;
             const float* cs_row = nullptr;
             if (MODE != EPI_FISTA && epi.chan_scale) cs_row = epi.chan_scale + (epi.chan_per_pixel ? (size_t)row * epi.m : 0);
+            const bool cs_even = (epi.m & 1) == 0 && (reinterpret_cast<uintptr_t>(epi.chan_scale) & 7) == 0;
             float dsum = 0.f;
             // Sparsity shortcut (exact): FISTA's soft threshold leaves most of phi space identically zero.  A byte per
             // (row, 128-column block) records "x and z are all zero here"; such a block needs no loads, and if its new
@@ -227,8 +228,12 @@ __device__ __forceinline__ void epilogue_tile(const GemmEpilogue& epi, const flo
                             if (MODE == EPI_RESID) in0[jj] = __ldcg(reinterpret_cast<const float2*>(epi.b + row_off + col));
                             if (cs_row) {
                                 const int c0 = col >= epi.m ? col - epi.m : col;
-                                const int c1 = col + 1 >= epi.m ? col + 1 - epi.m : col + 1;
-                                in1[jj] = make_float2(__ldg(cs_row + c0), __ldg(cs_row + c1));
+                                if (cs_even) {  // even m: the pair never straddles the halves and stays 8-byte aligned
+                                    in1[jj] = __ldg(reinterpret_cast<const float2*>(cs_row + c0));
+                                } else {
+                                    const int c1 = col + 1 >= epi.m ? col + 1 - epi.m : col + 1;
+                                    in1[jj] = make_float2(__ldg(cs_row + c0), __ldg(cs_row + c1));
+                                }
                             }
                         }
                     }
@@ -806,6 +811,39 @@ __device__ __forceinline__ int screen_tile_fails_sym8(const GemmEpilogue& epi, c
     return fail;
 }
 
+// The plain adjoint from the four partial sums (rows regrouped by the 4-D map: a thread holds the alpha and the beta row
+// of one line of sight): out[p, j] = C_a + S_b, out[p, n - j] = C_a - S_b, out[p, n + j] = C_b - S_a, out[p, 2n - j] =
+// C_b + S_a, times the operand descale.  jw: phi index of the warp's first column pair, -1 for the cell without a mirror.
+__device__ __forceinline__ void epilogue_plain_sym8(const GemmEpilogue& epi, const float (&acc)[EPI_COLS], int lane, int row0,
+                                                    int col0, int ncols, int jw) {
+    const int quad = lane & 3;
+    const int nphi = epi.N >> 1;
+#pragma unroll
+    for (int lh = 0; lh < 2; ++lh) {
+        const int p = (row0 >> 1) + 8 * lh + (lane >> 2);
+        if (p >= epi.P) continue;
+        const float descale = kTwiddleDescale / __ldg(epi.a_scale + p);
+        float* o = epi.out + (size_t)p * epi.ld_out;
+#pragma unroll
+        for (int jj = 0; jj < 16; ++jj) {
+            const int col = col0 + 8 * jj + 2 * quad;
+            if (col >= ncols) continue;
+            const int aa = (((lh * 2 + (jj >> 3)) * 8 + (jj & 7)) * 2 + 0) * 2, ab = aa + 2;
+            const float ca = acc[aa], sa = acc[aa + 1], cb = acc[ab], sb = acc[ab + 1];
+            if (jw < 0) {  // phi_0 itself (its own table row)
+                __stcs(o, (ca + sb) * descale);
+                __stcs(o + nphi, (cb - sa) * descale);
+            } else {
+                const int j = jw + 4 * jj + quad;
+                __stcs(o + j, (ca + sb) * descale);
+                __stcs(o + nphi - j, (ca - sb) * descale);
+                __stcs(o + nphi + j, (cb - sa) * descale);
+                __stcs(o + 2 * nphi - j, (cb + sa) * descale);
+            }
+        }
+    }
+}
+
 // per (group of 64 lines of sight, symmetric column tile): 1 = some original tile this symmetric tile overlaps is quiet
 // (its state is identically zero), i.e. there is something to decide; the three roles of the pair kernel read this byte
 __global__ void sym_quiet_kernel(const unsigned int* __restrict__ tile_state, int flag_ld, int MTg, int NTs, int nphi,
@@ -837,8 +875,8 @@ template <int PMODE>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
 screen8_pair_kernel(const __grid_constant__ CUtensorMap map_a8, const __grid_constant__ CUtensorMap map_b8, int K, int MT,
                     int NT, const GemmEpilogue epi) {
-    constexpr bool PLAIN = PMODE == 1;
-    constexpr bool F16 = PMODE == 1 || PMODE == 2 || PMODE == 4;  // PMODE 2: the fp16 screening test over all quiet tiles
+    constexpr bool PLAIN = PMODE == 1 || PMODE == 5;  // PMODE 5: the one-product plain adjoint, mirror-symmetric (rows8 map)
+    constexpr bool F16 = PMODE == 1 || PMODE == 2 || PMODE == 4 || PMODE == 5;  // PMODE 2: the fp16 screening test over all quiet tiles
     constexpr bool SYM = PMODE >= 3;          // PMODE 3 / 4: mirror-symmetric fp8 / fp16 screening (MT counts 64-LOS groups)
     constexpr int BKE = F16 ? BK : 2 * BK;    // K elements per 128-byte row
     const int nphi = epi.N >> 1;
@@ -898,6 +936,11 @@ screen8_pair_kernel(const __grid_constant__ CUtensorMap map_a8, const __grid_con
     // tile ahead so that no role waits for an L2 round trip at the top of a tile
     auto qraw = [&](int ti) -> unsigned int {
         if (!SYM || ti >= total) return 0u;
+        if (PLAIN) {  // every existing group of a listed pair is computed
+            int mtp, nt;
+            tile_coords(pair_id(ti), MTP, NT, mtp, nt);
+            return (2 * mtp < MT ? 1u : 0u) | (2 * mtp + 1 < MT ? 0x100u : 0u);
+        }
         int mtp, nt;
         tile_coords(pair_id(ti), MTP, NT, mtp, nt);
         const unsigned int a = 2 * mtp < MT ? __ldcg(epi.symq + (size_t)(2 * mtp) * NT + nt) : 0u;
@@ -1016,7 +1059,11 @@ screen8_pair_kernel(const __grid_constant__ CUtensorMap map_a8, const __grid_con
                             if (rank == 0) mbar_arrive(&tmem_empty[buf]);
                             else mbar_arrive_leader(&tmem_empty[buf]);
                         }
-                        epilogue_tile<EPI_PLAIN>(epi, acc, lane, mt * BM + sub * 32, nt * BN + half * EPI_COLS);
+                        if (SYM)
+                            epilogue_plain_sym8(epi, acc, lane, mt * BM + sub * 32, half * EPI_COLS, nt == NT - 1 ? 2 : nphi - nt * BN,
+                                                nt == NT - 1 ? -1 : nphi / 2 + (BN / 2) * nt + (EPI_COLS / 2) * half);
+                        else
+                            epilogue_tile<EPI_PLAIN>(epi, acc, lane, mt * BM + sub * 32, nt * BN + half * EPI_COLS);
                     } else if (SYM) {
                         const int jw = nt == NT - 1 ? -1 : nphi / 2 + (BN / 2) * nt + (EPI_COLS / 2) * half;
                         const int ncv = nt == NT - 1 ? 2 : nphi - nt * BN;
@@ -1435,7 +1482,7 @@ static int launch_pair_kernel(const csr_plan* plan, const CUtensorMap& ma, const
     const int clusters = min(pairs, max_clusters);
     ProfiledLaunch rec;
     if (g_profile) {
-        rec.kind = PMODE == 1 ? 10 : ((PMODE == 2 || PMODE == 4) ? 8 : 9);
+        rec.kind = (PMODE == 1 || PMODE == 5) ? 10 : ((PMODE == 2 || PMODE == 4) ? 8 : 9);
         CSR_CUDA(pooled_event(&rec.start));
         CSR_CUDA(pooled_event(&rec.stop));
         CSR_CUDA(cudaEventRecord(rec.start, stream));
@@ -1576,6 +1623,69 @@ int launch_plain1_pair(const csr_plan* plan, const __half* a_hi, int P, const Ge
     int rc = cached_operand_map(&ma, a_hi, P, 2 * plan->m, plan->ld2m, 2);
     if (rc) return rc;
     return launch_pair_kernel<1>(plan, ma, plan->map_adj_hi_half, P, epi, stream);
+}
+
+// the one-product plain adjoint, mirror-symmetric (needs plan->sym16_ok and the 4-D operand view); epi.tile_list names
+// (pixel tile, symmetric column tile) pairs: launch_sym_pair_list
+int launch_plain1_sym_pair(const csr_plan* plan, const __half* a_hi, int P, const GemmEpilogue& epi_in, cudaStream_t stream) {
+    CSR_REQUIRE(P > 0 && epi_in.out != nullptr && plan->sym16_ok, "launch_plain1_sym_pair: bad argument");
+    GemmEpilogue epi = epi_in;
+    epi.mode = EPI_PLAIN;
+    epi.P = P;
+    epi.N = 2 * plan->n;
+    epi.ld_out = plan->ld2n;
+    epi.m = plan->m;
+    epi.debug = 0;
+    epi.sym_rows8 = 1;
+    CUtensorMap ma;
+    int rc = cached_sym_map(&ma, a_hi, P, plan->m, (size_t)plan->ld2m * 2, (size_t)plan->m * 2, 2);
+    if (rc) return rc;
+    return launch_pair_kernel<5>(plan, ma, plan->map_sym16, P, epi, stream);
+}
+bool plain1_sym_available(const csr_plan* plan, const __half* a_hi, int P) {
+    static const bool on = getenv("CSR_NO_SYM_PLAIN1") == nullptr;
+    CUtensorMap ma;
+    return on && plan->sym16_ok && cached_sym_map(&ma, a_hi, P, plan->m, (size_t)plan->ld2m * 2, (size_t)plan->m * 2, 2) == CSR_OK;
+}
+
+// (pixel tile, symmetric column tile) pairs that overlap an original tile whose need byte is 0
+__global__ void __launch_bounds__(1024)
+sym_pair_list_kernel(const unsigned char* __restrict__ need, int MTo, int NTo, int NTs, int nphi, int* __restrict__ list,
+                     int* __restrict__ count) {
+    __shared__ int warp_n[32];
+    __shared__ int base;
+    if (threadIdx.x == 0) base = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int t0 = 0; t0 < MTo * NTs; t0 += 1024) {
+        const int t = t0 + threadIdx.x;
+        bool a = false;
+        if (t < MTo * NTs) {
+            int mtp, nt;
+            tile_coords(t, MTo, NTs, mtp, nt);
+            int lo[4], hi[4];
+            const int nr = sym_ranges(nt, NTs, nphi, lo, hi);
+            for (int r = 0; r < nr; ++r)
+                for (int c = lo[r] >> 8; c <= (hi[r] - 1) >> 8; ++c) a |= need[(size_t)mtp * NTo + c] == 0;
+        }
+        const unsigned ba = __ballot_sync(0xffffffffu, a);
+        if (lane == 0) warp_n[warp] = __popc(ba);
+        __syncthreads();
+        int oa = base;
+        for (int w = 0; w < warp; ++w) oa += warp_n[w];
+        if (a) list[oa + __popc(ba & ((1u << lane) - 1))] = t;
+        __syncthreads();
+        if (threadIdx.x == 0)
+            for (int w = 0; w < 32; ++w) base += warp_n[w];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *count = base;
+}
+int launch_sym_pair_list(const csr_plan* plan, const unsigned char* need, int P, int* list, int* count, cudaStream_t stream) {
+    sym_pair_list_kernel<<<1, 1024, 0, stream>>>(need, (P + BM - 1) / BM, (2 * plan->n + BN - 1) / BN, (plan->n + BN - 1) / BN + 1,
+                                                plan->n, list, count);
+    CSR_LAUNCHED();
+    return CSR_OK;
 }
 
 // pairs of pixel tiles (numbering of tile_coords(tp, ceil(MT/2), NT)) with an existing member whose need byte is 0

@@ -413,7 +413,11 @@ extern "C" int csr_fista(csr_plan* plan, csr_wavelet* wav, const csr_fista_args*
                 e1.mode = EPI_PLAIN1;
                 e1.tile_list = w.tile_list2;
                 e1.tile_count = counts + 1;
-                if (options().pair != 0 && P > BM) {  // on CTA pairs: every pair with a tile outside the exact list
+                if (options().pair != 0 && options().sym != 0 && plain1_sym_available(plan, w.r_hi, P)) {
+                    // mirror-symmetric on CTA pairs: +phi and -phi from one product with half the K
+                    if ((rc = launch_sym_pair_list(plan, w.need[0], P, w.tile_list2, counts + 1, stream))) return rc;
+                    if ((rc = launch_plain1_sym_pair(plan, w.r_hi, P, e1, stream))) return rc;
+                } else if (options().pair != 0 && P > BM) {  // on CTA pairs: every pair with a tile outside the exact list
                     if ((rc = launch_pair_list(w.need[0], P, 2 * n, w.tile_list2, counts + 1, stream))) return rc;
                     if ((rc = launch_plain1_pair(plan, w.r_hi, P, e1, stream))) return rc;
                 } else {

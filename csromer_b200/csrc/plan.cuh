@@ -149,6 +149,9 @@ int launch_screen_sym_pair(const csr_plan* plan, const void* a, bool fp8, int P,
 int launch_screen16_pair(const csr_plan* plan, const __half* a_hi, int P, const GemmEpilogue& epi, cudaStream_t stream);
 // EPI_PLAIN1 on CTA pairs; epi.tile_list / tile_count name PAIRS of pixel tiles (launch_pair_list), null = all
 int launch_plain1_pair(const csr_plan* plan, const __half* a_hi, int P, const GemmEpilogue& epi, cudaStream_t stream);
+int launch_plain1_sym_pair(const csr_plan* plan, const __half* a_hi, int P, const GemmEpilogue& epi, cudaStream_t stream);
+bool plain1_sym_available(const csr_plan* plan, const __half* a_hi, int P);
+int launch_sym_pair_list(const csr_plan* plan, const unsigned char* need, int P, int* list, int* count, cudaStream_t stream);
 // pairs (two pixel tiles x one column tile) with at least one existing tile whose need byte is 0
 int launch_pair_list(const unsigned char* need, int P, int N, int* list, int* count, cudaStream_t stream);
 
