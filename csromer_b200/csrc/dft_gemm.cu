@@ -1394,17 +1394,17 @@ int launch_screen_eps(const float* abs_sum, const float* a_scale, int K, float* 
     return CSR_OK;
 }
 
-// one CTA walks the tiles in rasterised order and appends each to one of two lists (ordered compaction)
+// one CTA walks the tiles in rasterised order and appends each to one of two lists (ordered compaction): per chunk of
+// 1024 tiles one ballot per warp, the 32 warp counts scanned by every warp with shuffles, one barrier
 __global__ void __launch_bounds__(1024)
 split_tile_lists_kernel(const unsigned char* __restrict__ need, const unsigned char* __restrict__ exclude, int MT, int NT,
                         int* __restrict__ list_a, int* __restrict__ count_a, int* __restrict__ list_b,
                         int* __restrict__ count_b) {
-    __shared__ int warp_a[32], warp_b[32];
-    __shared__ int base_a, base_b;
-    if (threadIdx.x == 0) base_a = base_b = 0;
-    __syncthreads();
+    __shared__ int warp_a[2][32], warp_b[2][32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int t0 = 0; t0 < MT * NT; t0 += 1024) {
+    int base_a = 0, base_b = 0;  // (every thread carries the running totals)
+    int buf = 0;
+    for (int t0 = 0; t0 < MT * NT; t0 += 1024, buf ^= 1) {
         const int t = t0 + threadIdx.x;
         bool a = false, b = false;
         if (t < MT * NT) {
@@ -1415,25 +1415,23 @@ split_tile_lists_kernel(const unsigned char* __restrict__ need, const unsigned c
         }
         const unsigned ba = __ballot_sync(0xffffffffu, a), bb = __ballot_sync(0xffffffffu, b);
         if (lane == 0) {
-            warp_a[warp] = __popc(ba);
-            warp_b[warp] = __popc(bb);
+            warp_a[buf][warp] = __popc(ba);
+            warp_b[buf][warp] = __popc(bb);
         }
-        __syncthreads();
-        int oa = base_a, ob = base_b;
-        for (int w = 0; w < warp; ++w) {
-            oa += warp_a[w];
-            ob += warp_b[w];
+        __syncthreads();  // (double-buffered counts: one barrier per chunk)
+        const int ca = warp_a[buf][lane], cb = warp_b[buf][lane];
+        int pa = lane < warp ? ca : 0, pb = lane < warp ? cb : 0, ta = ca, tb = cb;
+#pragma unroll
+        for (int sft = 16; sft > 0; sft >>= 1) {
+            pa += __shfl_xor_sync(0xffffffffu, pa, sft);
+            pb += __shfl_xor_sync(0xffffffffu, pb, sft);
+            ta += __shfl_xor_sync(0xffffffffu, ta, sft);
+            tb += __shfl_xor_sync(0xffffffffu, tb, sft);
         }
-        if (a) list_a[oa + __popc(ba & ((1u << lane) - 1))] = t;
-        if (b) list_b[ob + __popc(bb & ((1u << lane) - 1))] = t;
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            for (int w = 0; w < 32; ++w) {
-                base_a += warp_a[w];
-                base_b += warp_b[w];
-            }
-        }
-        __syncthreads();
+        if (a) list_a[base_a + pa + __popc(ba & ((1u << lane) - 1))] = t;
+        if (b) list_b[base_b + pb + __popc(bb & ((1u << lane) - 1))] = t;
+        base_a += ta;
+        base_b += tb;
     }
     if (threadIdx.x == 0) {
         *count_a = base_a;
