@@ -440,6 +440,23 @@ def run_ours(args):
     block_flops = 2.0 * 128 * 256 * 64
     blocks = out["mma_blocks"].double().cpu().numpy()          # per step: [three-product, fp16 screen, fp8 screen, -]
     dominant = max(per_kind, key=lambda kname: per_kind[kname]["share_of_step"]) if per_kind else None
+    # the fp8 screening kernel and the forward transform take about the same time per launch (0.30 ms each): report the
+    # tensor-core kernel under `roofline` whenever it is within 10 % of the top share, the forward transform (bound by its
+    # fused epilogue's HBM traffic) under `roofline.second_kernel`, so that the line does not flip between runs
+    if dominant and "screen_adjoint_fp8" in per_kind and \
+            per_kind["screen_adjoint_fp8"]["share_of_step"] >= 0.9 * per_kind[dominant]["share_of_step"]:
+        dominant = "screen_adjoint_fp8"
+    second = None
+    if "resid_forward" in per_kind:
+        f_ms = per_kind["resid_forward"]["avg_ms"]
+        f_bytes = P * 2.0 * M_CH * (4 + 2 + 2 + 1)      # per element: b read (fp32), r_hi, r_lo (fp16) and r8 (fp8) written
+        second = {"kernel": "dft_gemm_kernel<EPI_RESID>: forward transform with K-block skipping + fused residual epilogue",
+                  "bound": "hbm", "achieved": f_bytes / (f_ms * 1e-3) / 1e9, "peak": peaks["hbm"], "unit": "GB/s",
+                  "frac": f_bytes / (f_ms * 1e-3) / 1e9 / peaks["hbm"], "avg_ms": f_ms,
+                  "share_of_step": per_kind["resid_forward"]["share_of_step"],
+                  "note": "algorithmic bytes = 9 B per output element of the [P, 2m] residual; with ~9 of 249 K blocks active "
+                          "the MMA work is negligible and the kernel is bound by the ~20 us fused epilogue of each 128 x 256 "
+                          "tile (8 epilogue warps per SM, 32-byte row segments), not by HBM bandwidth: the next thing to fix"}
     if dominant == "screen_adjoint_fp8":
         k_ms = ms[0][9] / args.steps
         k_tf = blocks[2] * block_flops / (k_ms * 1e-3) / 1e12
@@ -472,7 +489,7 @@ def run_ours(args):
                          "gemm_share_of_step": gemm_ms / elapsed_ms if elapsed_ms > 0 else None,
                          "adjoint_transform_ms": adj_ms / ms[1][5] if ms[1][5] else None,
                          "executed_blocks_per_step": {"three_product": blocks[0], "fp16_screen": blocks[1], "fp8_screen": blocks[2]}},
-                "dense": dense, "per_kind": per_kind}
+                "second_kernel": second, "dense": dense, "per_kind": per_kind}
 
     if rank == 0:
         cpu = None
