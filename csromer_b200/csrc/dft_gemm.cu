@@ -847,8 +847,9 @@ __device__ __forceinline__ void epilogue_plain_sym8(const GemmEpilogue& epi, con
 // per (group of 64 lines of sight, symmetric column tile): 1 = some original tile this symmetric tile overlaps is quiet
 // (its state is identically zero), i.e. there is something to decide; the three roles of the pair kernel read this byte
 __global__ void sym_quiet_kernel(const unsigned int* __restrict__ tile_state, int flag_ld, int MTg, int NTs, int nphi,
-                                 unsigned char* __restrict__ symq) {
+                                 unsigned char* __restrict__ symq, unsigned char* __restrict__ need, int need_bytes) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx < need_bytes) need[idx] = 0;  // (also clears the map the pair kernel marks: one launch less per iteration)
     if (idx >= MTg * NTs) return;
     const int mt = idx / NTs, nt = idx - mt * NTs;
     const unsigned int mask = (mt & 1) ? 0xFFFF0000u : 0x0000FFFFu;
@@ -1568,11 +1569,11 @@ int launch_screen_sym_pair(const csr_plan* plan, const void* a, bool fp8, int P,
     const int MTo = (P + BM - 1) / BM, NTo = (2 * plan->n + BN - 1) / BN;
     epi.need = need;
     epi.need_ld = NTo;
-    CSR_CUDA(cudaMemsetAsync(need, 0, (size_t)MTo * NTo, stream));
     const int MTg = (P + BM / 2 - 1) / (BM / 2), NTs = (plan->n + BN - 1) / BN + 1;
     unsigned char* symq = need + align256((size_t)MTo * NTo);  // (the scratch holds both maps: sym_scratch_bytes)
     epi.symq = symq;
-    sym_quiet_kernel<<<(MTg * NTs + 255) / 256, 256, 0, stream>>>(epi.tile_state, epi.flag_ld, MTg, NTs, plan->n, symq);
+    const int cover = max(MTg * NTs, MTo * NTo);
+    sym_quiet_kernel<<<(cover + 255) / 256, 256, 0, stream>>>(epi.tile_state, epi.flag_ld, MTg, NTs, plan->n, symq, need, MTo * NTo);
     CSR_LAUNCHED();
     CUtensorMap ma;
     // rows regrouped so that a thread holds both rows of a line of sight (needs the operand allocated with its row count
