@@ -250,6 +250,28 @@ def test_sparsity_shortcuts_are_bit_exact(nch, P, K, kw):
     check_fista(src, X, cost, l1, ref)
 
 
+def test_fista_on_a_phi_grid_without_mirror_symmetry():
+    """the mirror-symmetric screening kernels need phi_j = -phi_{n-j}; any other grid must take the plain kernels (and a
+    grid that is symmetric must give the same answer with the shortcut off)"""
+    from csromer_b200 import _lib
+    src, par = make_batch(200, 140, seed=31, mixed=True)
+    par.phi = par.phi + 0.37 * par.cellsize          # shifted grid: no cell mirrors another
+    cost, X, l1, lam0, noise = run_fista(src, par, 30)
+    ref = oracle_fista(src, par, 30, lam0, noise)
+    check_fista(src, X, cost, l1, ref)
+    assert np.count_nonzero(X.data) < 0.2 * X.data.size
+    src2, par2 = make_batch(200, 140, seed=31, mixed=True)
+    res = []
+    try:
+        for sym in (1, 0):
+            _lib.set_option("sym", sym)
+            cost2, X2, _, _, _ = run_fista(src2, par2, 30)
+            res.append(np.array(X2.data, copy=True))
+    finally:
+        _lib.set_option("sym", 1)
+    np.testing.assert_array_equal(res[0], res[1])
+
+
 def test_wavelet_forward_k_skipping_is_bit_exact():
     """undecimated basis: the fused synthesis kernel flags the non-zero operand blocks and the forward GEMM skips the
     rest; coefficient-state flags let the update kernel skip state traffic of blocks that are and stay zero -- same
