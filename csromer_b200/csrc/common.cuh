@@ -289,6 +289,7 @@ struct Options {
     int zero_skip, k_skip, fused_wavelet, screen, screen8;
     int pair;  // the fp8 screening pass runs on CTA pairs (cta_group::2)
     int wavelet_vec4;  // fused wavelet kernels with four samples per thread (bit-identical to the scalar ones)
+    int resid_fast;  // lean residual epilogue of the forward transform on interior column runs (same bits)
     int sym;  // mirror-symmetric screening (phi_j = -phi_{n-j}): half the K for the same decisions
     int screen16_pair;  // per-pixel weights: one fp16 screening pass on CTA pairs instead of the fp8 -> fp16 cascade
     int wavelet_screen;  // wavelet bases: one-product gradient + rigorous bound away from the active coefficients

@@ -247,7 +247,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmEpilogue& epi, const flo
                     if (MODE == EPI_PLAIN) {
                         __stcs(reinterpret_cast<float2*>(epi.out + row_off + col), make_float2(a0 * rs * in1[jj].x, a1 * rs * in1[jj].y));
                     } else if (MODE == EPI_RESID) {
-                        const float r0 = (in1[jj].x * a0 - in0[jj].x) * oscale, r1 = (in1[jj].y * a1 - in0[jj].y) * oscale;
+                        const float r0 = __fmaf_rn(in1[jj].x, a0, -in0[jj].x) * oscale, r1 = __fmaf_rn(in1[jj].y, a1, -in0[jj].y) * oscale;  // (explicit: same bits in both residual epilogues)
                         const __half2 h = __floats2half2_rn(r0, r1);
                         const float2 hf = __half22float2(h);
                         const __half2 l = __floats2half2_rn(r0 - hf.x, r1 - hf.y);
@@ -318,6 +318,67 @@ __device__ __forceinline__ void epilogue_tile(const GemmEpilogue& epi, const flo
         if (lane == 0)
             reinterpret_cast<unsigned char*>(epi.tile_flags)[((size_t)(row0 / BM) * epi.flag_ld + (col0 >> 7)) * 4 + ((row0 >> 5) & 3)] =
                 (unsigned char)any_nz;
+    }
+}
+
+// EPI_RESID for a warp whose 128 columns lie inside one half of the row ([0, m) or [m, 2m)) and inside the matrix, m even:
+// no per-element bounds, one base pointer per array and row with compile-time offsets.  Same arithmetic, same bits as
+// epilogue_tile<EPI_RESID>; the general function keeps the straddling and ragged runs.  (ncu: the general epilogue spends
+// ~60 % of its ~125 instructions per element on predicates, branches and 64-bit address arithmetic.)
+__device__ __forceinline__ void epilogue_resid_fast(const GemmEpilogue& epi, const float (&acc)[EPI_COLS], int lane, int row0,
+                                                    int col0) {
+    const int quad = lane & 3;
+    const int cbase = col0 + 2 * quad;                                  // first column pair of this thread
+    const int chan0 = cbase >= epi.m ? cbase - epi.m : cbase;           // ... as a channel index
+    const int c8 = cbase >= epi.m ? cbase - epi.m + (epi.ld8 >> 1) : cbase;  // ... in the half-row fp8 layout
+#pragma unroll
+    for (int lh = 0; lh < 2; ++lh) {
+#pragma unroll
+        for (int rh = 0; rh < 2; ++rh) {
+            const int row = row0 + (lane >> 2) + 8 * rh + 16 * lh;
+            const bool row_ok = row < epi.P;
+            float dsum = 0.f;
+            if (row_ok) {
+                const float descale = kTwiddleDescale / __ldg(epi.a_scale + row);
+                const float oscale = __ldg(epi.out_scale + row);
+                const size_t row_off = (size_t)row * epi.ld_out;
+                const float2* bp = reinterpret_cast<const float2*>(epi.b + row_off + cbase);
+                const float2* cp = epi.chan_scale
+                                       ? reinterpret_cast<const float2*>(epi.chan_scale + (epi.chan_per_pixel ? (size_t)row * epi.m : 0) + chan0)
+                                       : nullptr;
+                __half2* hp = reinterpret_cast<__half2*>(epi.out_hi + row_off + cbase);
+                __half2* lp = reinterpret_cast<__half2*>(epi.out_lo + row_off + cbase);
+                __nv_fp8x2_storage_t* p8 = epi.out8 ? reinterpret_cast<__nv_fp8x2_storage_t*>(epi.out8 + (size_t)row * epi.ld8 + c8) : nullptr;
+                float2 in0[16], in1[16];
+#pragma unroll
+                for (int jj = 0; jj < 16; ++jj) {  // the row's 32 loads in flight before any result is stored
+                    in0[jj] = __ldcg(bp + 4 * jj);
+                    in1[jj] = cp ? __ldg(cp + 4 * jj) : make_float2(1.f, 1.f);
+                }
+#pragma unroll
+                for (int jj = 0; jj < 16; ++jj) {
+                    const int ai = (((lh * 2 + (jj >> 3)) * 8 + (jj & 7)) * 2 + rh) * 2;
+                    const float a0 = acc[ai] * descale, a1 = acc[ai + 1] * descale;
+                    const float r0 = __fmaf_rn(in1[jj].x, a0, -in0[jj].x) * oscale, r1 = __fmaf_rn(in1[jj].y, a1, -in0[jj].y) * oscale;  // (explicit: same bits in both residual epilogues)
+                    const __half2 h = __floats2half2_rn(r0, r1);
+                    const float2 hf = __half22float2(h);
+                    const __half2 l = __floats2half2_rn(r0 - hf.x, r1 - hf.y);
+                    hp[4 * jj] = h;
+                    lp[4 * jj] = l;
+                    dsum += fabsf(hf.x) + fabsf(hf.y);
+                    if (p8 != nullptr) {  // kernel-uniform
+                        const float2 v8 = make_float2(hf.x * kOperandScale8, hf.y * kOperandScale8);
+                        if (fmaxf(fabsf(v8.x), fabsf(v8.y)) > 448.f) dsum = __int_as_float(0x7f800000);  // unscreenable row
+                        p8[4 * jj] = __nv_cvt_float2_to_fp8x2(v8, __NV_SATFINITE, __NV_E4M3);
+                    }
+                }
+            }
+            if (epi.abs_sum_out != nullptr) {  // kernel-uniform
+                dsum += __shfl_xor_sync(0xffffffffu, dsum, 1);
+                dsum += __shfl_xor_sync(0xffffffffu, dsum, 2);
+                if (quad == 0 && row_ok && dsum != 0.f) atomicAdd(epi.abs_sum_out + row, dsum);
+            }
+        }
     }
 }
 
@@ -583,6 +644,12 @@ dft_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
         asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
         const int ew = warp - 4;
         const int sub = warp & 3;        // TMEM lane quarter this warp may read (hardware rule: warp id mod 4)
+        // the lean residual epilogue needs: m even, 8-byte aligned float2 / half2 views, no measurement switches
+        const bool resid_fast = MODE == EPI_RESID && (epi.m & 1) == 0 && epi.debug == 0 && epi.no_fast == 0 && (epi.ld_out & 1) == 0 &&
+                                ((reinterpret_cast<uintptr_t>(epi.b) | reinterpret_cast<uintptr_t>(epi.chan_scale)) & 7) == 0 &&
+                                ((reinterpret_cast<uintptr_t>(epi.out_hi) | reinterpret_cast<uintptr_t>(epi.out_lo)) & 3) == 0 &&
+                                (epi.out8 == nullptr || ((reinterpret_cast<uintptr_t>(epi.out8) | (uintptr_t)epi.ld8) & 1) == 0) &&
+                                true;
         const int half = ew >> 2;        // which 128 of the tile's 256 columns
         uint32_t chunk = 0;
         for (int ti = blockIdx.x; ti < total_tiles; ti += gridDim.x) {
@@ -625,7 +692,11 @@ dft_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
                     if (lane == 0 && atomicMax(last_listed, ti) < ti) epi.out_list[atomicAdd(epi.out_count, 1)] = t;
                 }
             } else {
-                epilogue_tile<MODE == EPI_PLAIN1 ? EPI_PLAIN : MODE>(epi, acc, lane, mt * BM + sub * 32, nt * BN + half * EPI_COLS);
+                const int ecol0 = nt * BN + half * EPI_COLS;
+                if (MODE == EPI_RESID && resid_fast && ecol0 + EPI_COLS <= epi.N && (ecol0 + EPI_COLS <= epi.m || ecol0 >= epi.m))
+                    epilogue_resid_fast(epi, acc, lane, mt * BM + sub * 32, ecol0);  // (warp-uniform choice)
+                else
+                    epilogue_tile<MODE == EPI_PLAIN1 ? EPI_PLAIN : MODE>(epi, acc, lane, mt * BM + sub * 32, ecol0);
             }
         }
     }
@@ -1344,6 +1415,7 @@ int launch_dft_gemm(const csr_plan* plan, bool adjoint, const __half* a_hi, cons
     GemmEpilogue epi = epi_in;
     static const int debug_flags = getenv("CSR_DEBUG_EPI") ? atoi(getenv("CSR_DEBUG_EPI")) : 0;  // measurement aid only
     epi.debug = debug_flags;
+    epi.no_fast = options().resid_fast == 0;
     const int K = adjoint ? 2 * plan->m : 2 * plan->n;
     const int ldk = adjoint ? plan->ld2m : plan->ld2n;
     epi.P = P;

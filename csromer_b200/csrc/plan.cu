@@ -95,7 +95,8 @@ Options& options() {
     static Options o = {getenv("CSR_NO_ZERO_SKIP") == nullptr, getenv("CSR_NO_K_SKIP") == nullptr,
                         getenv("CSR_NO_FUSED_WAVELET") == nullptr, getenv("CSR_NO_SCREEN") == nullptr,
                         getenv("CSR_NO_SCREEN8") == nullptr, getenv("CSR_NO_PAIR") == nullptr,
-                        getenv("CSR_NO_WAVELET_VEC4") == nullptr, getenv("CSR_NO_SYM") == nullptr,
+                        getenv("CSR_NO_WAVELET_VEC4") == nullptr, getenv("CSR_NO_RESID_FAST") == nullptr,
+                        getenv("CSR_NO_SYM") == nullptr,
                         getenv("CSR_NO_SCREEN16_PAIR") == nullptr,
                         getenv("CSR_NO_WAVELET_SCREEN") == nullptr};
     return o;
@@ -117,6 +118,7 @@ extern "C" int csr_set_option(const char* name, int value) {
     else if (!strcmp(name, "wavelet_screen")) o.wavelet_screen = value != 0;
     else if (!strcmp(name, "screen16_pair")) o.screen16_pair = value != 0;
     else if (!strcmp(name, "sym")) o.sym = value != 0;
+    else if (!strcmp(name, "resid_fast")) o.resid_fast = value != 0;
     else {
         set_error("csr_set_option: unknown option '%s'", name);
         return CSR_ERR_ARG;

@@ -102,6 +102,7 @@ struct GemmEpilogue {
     int need_ld;
     unsigned long long* mma_count;  // optional: += K blocks x products issued (executed-work accounting)
     int debug;                 // measurement aid (CSR_DEBUG_EPI): bit 0 skips epilogue loads, bit 1 skips stores
+    int no_fast;               // 1 = keep the general residual epilogue everywhere (option resid_fast = 0; same bits)
 };
 
 constexpr int kCoefBlockShift = 9;  // 512 coefficients per flag

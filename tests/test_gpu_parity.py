@@ -233,6 +233,7 @@ def test_sparsity_shortcuts_are_bit_exact(nch, P, K, kw):
             _lib.set_option("screen8", screen8)
             _lib.set_option("pair", pair)
             _lib.set_option("sym", sym)
+            _lib.set_option("resid_fast", zero_skip and screen8)   # (the lean residual epilogue: off in the plainer combinations)
             cost, X, l1, lam0, noise = run_fista(src, par, K)
             results.append((np.array(X.data, copy=True), np.array(cost, copy=True), np.array(src.model_data, copy=True)))
     finally:
@@ -242,6 +243,7 @@ def test_sparsity_shortcuts_are_bit_exact(nch, P, K, kw):
         _lib.set_option("screen8", 1)
         _lib.set_option("pair", 1)
         _lib.set_option("sym", 1)
+        _lib.set_option("resid_fast", 1)
     assert np.count_nonzero(results[0][0]) > 0 and np.count_nonzero(results[0][0]) < 0.2 * results[0][0].size
     for other in results[1:]:
         for a, b in zip(results[0], other):
