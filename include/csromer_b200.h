@@ -207,7 +207,8 @@ int csr_profile_collect(double* ms_by_kind, long long* count_by_kind);
  * A tile is identically zero), "screen" (adjoint tiles whose state is zero are first screened with one fp16 product
  * and a rigorous error bound; only tiles that may leave zero run the three-product kernel), "screen8" (an fp8 pass in
  * front of that one), "pair" (that fp8 pass on cta_group::2 CTA pairs), "fused_wavelet" (fused shared-memory undecimated transforms),
- * "wavelet_vec4" (their four-samples-per-thread versions and the coefficient-state flags), "sym" (the pair screening kernels decide +phi and -phi together when the phi grid is antisymmetric:
+ * "wavelet_vec4" (their four-samples-per-thread versions and the coefficient-state flags), "resid_fast" (lean residual epilogue of the forward transform on interior column
+ * runs), "sym" (the pair screening kernels decide +phi and -phi together when the phi grid is antisymmetric:
  * half the K), "screen16_pair" (per-pixel weights: one fp16 screening pass on CTA pairs instead of the
  * fp8 -> fp16 cascade), "wavelet_screen" (wavelet
  * bases: one-product gradient plus a rigorous bound away from the active coefficients, exact redo of what fails). */
