@@ -324,7 +324,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmEpilogue& epi, const flo
 // EPI_RESID for a warp whose 128 columns lie inside one half of the row ([0, m) or [m, 2m)) and inside the matrix, m even:
 // no per-element bounds, one base pointer per array and row with compile-time offsets.  Same arithmetic, same bits as
 // epilogue_tile<EPI_RESID>; the general function keeps the straddling and ragged runs.  (ncu: the general epilogue spends
-// ~60 % of its ~125 instructions per element on predicates, branches and 64-bit address arithmetic.)
+// more than half of its ~60 instructions per element on predicates, branches and 64-bit address arithmetic.)
 __device__ __forceinline__ void epilogue_resid_fast(const GemmEpilogue& epi, const float (&acc)[EPI_COLS], int lane, int row0,
                                                     int col0) {
     const int quad = lane & 3;
