@@ -701,14 +701,16 @@ swt_analysis_fused4_kernel(const float* __restrict__ signal, int ld_sig, int N, 
 }
 
 // adjoint tiles (128 lines of sight x 256 phi columns) whose gradient a set coefficient flag can see: every coefficient
-// of block [bs, be) of any band depends on the signal inside [bs - H, be + H) only, H = (F/2)(2^L - 1)
-__global__ void need_from_flags_kernel(const unsigned char* __restrict__ flags, int flag_ld, int N, int NB, int L, int H,
+// of block [bs, be) of the level-l band depends on the signal inside [bs - H_l, be + H_l) only, H_l = (F/2)(2^l - 1)
+__global__ void need_from_flags_kernel(const unsigned char* __restrict__ flags, int flag_ld, int N, int NB, int L, int halfF,
                                        unsigned char* __restrict__ need, int need_ld) {
     const int p = blockIdx.x;
     unsigned char* row = need + (size_t)(p >> 7) * need_ld;
     for (int idx = threadIdx.x; idx < (L + 1) * NB; idx += blockDim.x) {
         if (!flags[(size_t)p * flag_ld + idx]) continue;
-        const int k = idx % NB;
+        const int k = idx % NB, band = idx / NB;
+        const int lev = band == 0 ? L : L - band + 1;   // bands [cA_L, cD_L, ..., cD_1]
+        const int H = halfF * ((1 << lev) - 1);         // a level-l coefficient sees the signal within (F/2)(2^l - 1) of it
         const int bs = k << kCoefBlockShift, be = min(N, bs + (1 << kCoefBlockShift));
         const int len = be - bs + 2 * H;
         if (len >= N) {
@@ -884,8 +886,7 @@ int launch_coef_flags(const csr_wavelet* w, const float* z, int ld_coef, int P, 
 int launch_need_from_flags(const csr_wavelet* w, const unsigned char* flags, int flag_ld, int P, unsigned char* need,
                            int need_ld, cudaStream_t stream) {
     const int NB = (w->N + (1 << kCoefBlockShift) - 1) >> kCoefBlockShift;
-    const int H = (w->F / 2) * ((1 << w->levels) - 1);
-    need_from_flags_kernel<<<P, 128, 0, stream>>>(flags, flag_ld, w->N, NB, w->levels, H, need, need_ld);
+    need_from_flags_kernel<<<P, 128, 0, stream>>>(flags, flag_ld, w->N, NB, w->levels, w->F / 2, need, need_ld);
     CSR_LAUNCHED();
     return CSR_OK;
 }
