@@ -56,6 +56,25 @@ def test_error_paths_without_device(built_library):
     assert rc == -1
 
 
+def test_documented_options_are_accepted(built_library):
+    """every run-time switch the header documents is a name csr_set_option knows (and unknown names are refused)"""
+    lib = built_library
+    header = open(os.path.join(ROOT, "include", "csromer_b200.h")).read()
+    doc = header[header.index("run-time switches of the exact shortcuts"):header.index("int csr_set_option")]
+    names = re.findall(r'"(\w+)"', doc)
+    assert {"zero_skip", "k_skip", "screen", "screen8", "pair", "sym", "resid_fast", "screen16_pair", "fused_wavelet",
+            "wavelet_vec4", "wavelet_screen"} <= set(names)
+    for name in names:
+        assert lib.csr_set_option(name.encode(), 1) == 0, name
+    assert lib.csr_set_option(b"no_such_option", 1) != 0 and b"unknown option" in lib.csr_last_error()
+
+
+def test_sass_contains_cta_pair_and_packed_fma_instructions(built_library):
+    sass = subprocess.run(["cuobjdump", "-sass", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    assert "FFMA2" in sass, "packed fp32 FMAs (fused wavelet kernels) missing from SASS"
+    assert "UTCHMMA.2CTA" in sass and "UTCQMMA.2CTA" in sass, "cta_group::2 MMAs (fp16 / fp8 pair kernels) missing from SASS"
+
+
 def test_sass_contains_blackwell_tensor_and_tma_instructions(built_library):
     sass = subprocess.run(["cuobjdump", "-sass", _lib.LIB_PATH], capture_output=True, text=True).stdout
     assert "UTCHMMA" in sass, "tcgen05.mma missing from SASS"
