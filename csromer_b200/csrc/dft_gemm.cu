@@ -25,8 +25,14 @@
 // Kernels in this file:
 //   dft_gemm_kernel<EPI_PLAIN | EPI_RESID | EPI_FISTA>   three-product GEMM with the fused epilogues above; the forward
 //                                                        direction can skip K blocks whose A tile is zero (build_kmask)
-//   dft_gemm_kernel<EPI_SCREEN | EPI_SCREEN8>            one-product (fp16 / fp8) safe screening of adjoint tiles
-//   screen8_pair_kernel                                  the fp8 screening pass on CTA pairs (cta_group::2)
+//   dft_gemm_kernel<EPI_SCREEN | EPI_SCREEN8 | EPI_PLAIN1>  one-product (fp16 / fp8) safe screening of adjoint tiles; one-product
+//                                                        plain adjoint (wavelet-domain screening)
+//   screen8_pair_kernel<PMODE>                           the one-product kernels on CTA pairs (cta_group::2, M = 256):
+//        0  fp8 screening                     3  fp8 screening, mirror-symmetric (+phi and -phi from half the K)
+//        1  fp16 plain adjoint (EPI_PLAIN1)   4  fp16 screening, mirror-symmetric
+//        2  fp16 screening                    5  fp16 plain adjoint, mirror-symmetric
+//   epilogue_resid_fast                                  the lean residual epilogue of interior column runs
+//   sym_quiet_kernel, split_tile_lists_kernel, pair_list_kernel, sym_pair_list_kernel, screen_eps_kernel   small helpers
 // and the host-side launchers with their tensor-map cache and per-launch CUDA-event profiling.
 #include <stdlib.h>
 #include <string.h>
@@ -943,6 +949,8 @@ constexpr int P2_SMEM_BYTES = 1024 + P2_STAGES * P2_STAGE_BYTES + 256;
 
 // PMODE 0: the fp8 screening pass.  PMODE 1: the one-product fp16 plain adjoint (EPI_PLAIN1) -- same staging (a 128-byte
 // row holds 64 fp16 instead of 128 fp8), kind::f16 MMAs, the plain epilogue, every listed pair computed by both CTAs.
+// PMODE 2: the fp16 screening test over all quiet tiles.  PMODE 3 / 4 / 5: modes 0 / 2 / 1 in the mirror-symmetric
+// formulation (see "mirror-symmetric screening" above): MT counts groups of 64 lines of sight, NT tiles of 128 phi >= 0.
 template <int PMODE>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
 screen8_pair_kernel(const __grid_constant__ CUtensorMap map_a8, const __grid_constant__ CUtensorMap map_b8, int K, int MT,
