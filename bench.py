@@ -2,26 +2,39 @@
 """bench.py -- lines of sight per second for fixed-iteration FISTA (BASELINE.json metric) on N B200s.
 
     python bench.py --gpus N --steps K --warmup W            (N > 1: launched by torch.distributed.run)
-    python bench.py --impl reference ...                     (the reference's CPU algorithm on the host cores)
+    python bench.py --impl reference ...                     (the reference's own CPU classes on the host cores)
 
-Workload (config.workload): BASELINE.json configs[2] -- a 512 x 512-pixel cube x 1000 channels (JVLA band
-1.008-2.031 GHz, n = 7968 Faraday-depth cells at oversampling 8), shared lambda^2 sampling, delta-basis L1 FISTA
-with K_fista = 100 iterations, lambda0 = 40 theo_noise, noise = lambda0 / 200.  One STEP =
-one pass of the whole hot path (dirty spectrum + 100 iterations + final evaluate = 2*100+2 transforms per line of
-sight) over one slab of `--slab` lines of sight (default 16384 = 32 image rows); the cube is 16 such slabs.  With N
-GPUs every rank runs its own slab per step (pixels shard with no data-path communication; weak scaling); the only
-collective is the all-reduce of the convergence norm after each step.
+ONE JSON line.  The headline (`value`, `e2e`, `roofline`, `cpu_baseline`) is BASELINE.json configs[2] (C3), so that
+rounds compare; `configs.c4` and `configs.c5` are sub-records of the same run for configs[3] and configs[4] (the
+north-star target: wavelet-regularised FISTA at the 4000-channel sampling), each with its own value, ms_per_step,
+per-kernel roofline and clocks; `parity` holds the in-run correctness checks of every workload AT BENCH SCALE.
 
-value  : whole-job LOS/s with the slab resident in HBM (x, z state = 2 GB per slab >> 126 MB L2, so no L2 flush is
-         needed between steps; steps alternate between two different slabs).
-e2e    : the same metric through the public API (Dataset / NDFT1D / Chi2 / L1 / FISTA.run) with HOST buffers: the
-         slab's data comes from pinned host memory every step and the solution cube and cost are read back.
-roofline: the transform GEMM kernel (dft_gemm_kernel, both directions), algorithmic 8*m*n flops per line of sight
-         per launch over CUDA-event launch durations recorded inside the timed region (csr_profile), against the
-         measured dense bf16 tensor peak.  The kernel executes 3 fp16 products per algorithmic product (hi/lo
-         split for fp32-class accuracy), so frac <= 1/3 by construction; `executed_tflops` is 3x achieved.
-cpu_baseline: the oracle's NumPy port of the reference path (twiddles rebuilt with np.exp in every transform, as
-         ndft.py:19-34 does), one line of sight per host core like the README's joblib recipe, bounded sample.
+Workloads (K_fista = 100 iterations, lambda0 = 40 theo_noise, noise = lambda0 / 200):
+  c3  512 x 512 px x 1000 ch (JVLA 1.008-2.031 GHz), n_phi = 7968, shared lambda^2, delta-basis L1, slabs of 16384 LOS
+  c4  1024 x 1024 px x 2000 ch, n_phi = 15968, per-pixel weights + 10-20 % flagged channels per pixel, per-pixel Galactic
+      RM removed on the device inside the step, delta-basis L1, slabs of 8192 LOS
+  c5  2048 x 2048 px x 4000 ch (MeerKAT 0.9-1.67 GHz), n_phi = 31968, undecimated coif2 wavelet basis (L = 6, 447 552
+      coefficients per LOS), step = 1 / lambda_max, slabs of 4096 LOS
+One STEP = one pass of the whole hot path (dirty spectrum + K iterations + final evaluate = 2 K + 2 transforms per line
+of sight) over one slab.  With N GPUs every rank runs its own slab per step (pixels shard with no data-path
+communication; weak scaling); the only collective is the all-reduce of the convergence norm after each step.
+
+value  : whole-job LOS/s with the slab resident in HBM (state of a slab is GBs >> 126 MB L2, and steps alternate between
+         two slabs, so no L2 flush is needed), CUDA events, max over ranks.
+e2e    : the same metric through the public API (Dataset / NDFT1D / Chi2 / L1 / FISTA.run) with HOST buffers: the slab's
+         data comes from pinned host memory every step and the solution and cost are read back, all inside the timed
+         region.
+roofline: per kernel, `algorithmic` (SURVEY.md section 8d work / CUDA-event time) and `executed` (in-kernel MMA counters,
+         or the ncu DRAM bytes of the committed capture of this build) are reported SEPARATELY; the exact sparsity
+         shortcuts skip provably-zero work, so an algorithmic figure above the peak carries the word "skipped".
+         Tensor peaks are measured in this run (torch.matmul bf16 and torch._scaled_mm e4m3, 8192^3, burst and sustained);
+         the HBM peak is MEASURED_PEAKS.json's.
+parity : (i) the solution of the bench slab with every exact shortcut on equals the dense run bit for bit;
+         (ii) sampled lines of sight of the bench slab against oracle.restatement.fista, max-norm relative < 1e-4
+         (the oracle is the checker here, never the thing measured).
+cpu_baseline / --impl reference: the reference's own classes (oracle/_ref, a byte-for-byte run-time copy of
+         /root/reference/src/csromer made by oracle/build_ref.py) fanned out one line of sight per core with joblib's
+         multiprocessing backend like README.md:309-315, bounded sample, extrapolated linearly in the transform count.
 """
 import argparse
 import ctypes
@@ -38,20 +51,36 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-M_CH, N_PHI = 1000, 7968
-NU = (1.008e9, 2.031e9)
 SIGMA = 0.2 * 0.0035
-WORKLOAD = "c3"
-# --workload c4 (not the driver's line; results under profiles/): BASELINE.json configs[3] at slab scale -- 2000
-# channels (n = 15968), per-pixel weights sigma0 U(0.5, 2) per channel, 10-20 % of each pixel's channels flagged
-# (w = 0), per-pixel Galactic RM ~ N(0, 30) removed on the device inside the step (Dataset.subtract_galacticrm).
-WORKLOADS = {"c3": dict(m=1000, n=7968, slab=16384), "c4": dict(m=2000, n=15968, slab=8192)}
-
-
-def set_workload(name):
-    global M_CH, N_PHI, WORKLOAD
-    WORKLOAD = name
-    M_CH, N_PHI = WORKLOADS[name]["m"], WORKLOADS[name]["n"]
+JVLA, MEERKAT = (1.008e9, 2.031e9), (0.9e9, 1.67e9)
+WORKLOADS = {
+    "c3": dict(m=1000, n=7968, slab=16384, band=JVLA, basis="delta", seed=1234,
+               text="C3: 512x512 px x 1000 ch cube (JVLA 1.008-2.031 GHz), shared lambda^2, n_phi=7968, delta-basis L1 FISTA, "
+                    "exact DFT operator"),
+    "c4": dict(m=2000, n=15968, slab=8192, band=JVLA, basis="delta", seed=1235,
+               text="C4: 1024x1024 px x 2000 ch cube (JVLA 1.008-2.031 GHz), n_phi=15968, per-pixel weights and 10-20 % "
+                    "flagged channels per pixel, per-pixel Galactic RM removed on the device inside the step, delta-basis "
+                    "L1 FISTA, exact DFT operator"),
+    "c5": dict(m=4000, n=31968, slab=4096, band=MEERKAT, basis="swt-coif2", seed=1236,
+               text="C5: 2048x2048 px x 4000 ch cube (MeerKAT 0.9-1.67 GHz), shared lambda^2, n_phi=31968, undecimated coif2 "
+                    "wavelet basis (L=6, 447552 coefficients per LOS), L1 FISTA with step 1/lambda_max, exact DFT operator"),
+}
+KIND_NAMES = ["plain_forward", "plain_adjoint", "resid_forward", "resid_adjoint", "fista_forward", "fista_adjoint",
+              "swt_synth_fused", "swt_analysis_update_fused", "screen_adjoint_fp16", "screen_adjoint_fp8",
+              "plain_adjoint_one_product", "swt_analysis_update_redo"]
+KERNEL_OF_KIND = {
+    0: "dft_gemm_kernel<EPI_PLAIN> forward (three fp16 products, tcgen05 kind::f16)",
+    1: "dft_gemm_kernel<EPI_PLAIN> adjoint (three fp16 products)",
+    2: "dft_gemm_kernel<EPI_RESID> forward + fused residual epilogue (K-block skipping)",
+    5: "dft_gemm_kernel<EPI_FISTA> adjoint + fused threshold / momentum epilogue on the listed tiles",
+    6: "swt_synth_fused4_kernel (all synthesis levels + operand split, shared-memory staged)",
+    7: "swt_analysis_fused4_kernel<UPDATE> (all analysis levels + threshold + momentum)",
+    8: "screen8_pair_kernel<4> / dft_gemm_kernel<EPI_SCREEN>: one-product fp16 screening of the adjoint",
+    9: "screen8_pair_kernel<3>: mirror-symmetric fp8 (e4m3) screening of the adjoint on CTA pairs (cta_group::2, kind::f8f6f4)",
+    10: "screen8_pair_kernel<5>: one-product fp16 plain adjoint, mirror-symmetric, on CTA pairs (wavelet-domain screening)",
+    11: "swt_analysis_fused4_kernel<UPDATE>, redo pass on the blocks that failed the bound",
+}
+BLOCK_FLOPS = 2.0 * 128 * 256 * 64      # one counted tensor-core block
 
 
 def load_peaks():
@@ -59,15 +88,48 @@ def load_peaks():
     if os.path.exists(path):
         d = json.load(open(path))
         return dict(hbm=d.get("hbm_gbs", 6650.0), tf_burst=d.get("bf16_tflops", 1590.0),
-                    tf_sustained=d.get("bf16_tflops_sustained", 1400.0), source="measured")
-    return dict(hbm=6650.0, tf_burst=1590.0, tf_sustained=1400.0, source="fallback")
+                    tf_sustained=d.get("bf16_tflops_sustained", 1400.0), source="MEASURED_PEAKS.json (driver-measured)")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sustained=1400.0, source="fallback of B200_PROFILING.md (no MEASURED_PEAKS.json)")
 
 
 # ---------------------------------------------------------------------------------------------------------
-# CPU baseline / reference arm: the oracle port of the reference algorithm on the host cores
+# CPU baseline / reference arm
 # ---------------------------------------------------------------------------------------------------------
-def _cpu_one_los(args):
-    seed, k_sample = args
+def _ref_one_los(seed, k_sample, m_ch, band):
+    """one line of sight through the REFERENCE'S classes (README.md:157-214 recipe), returns seconds"""
+    os.environ["OMP_NUM_THREADS"] = "1"
+    try:
+        from threadpoolctl import threadpool_limits
+        limiter = threadpool_limits(limits=1)
+    except Exception:  # pragma: no cover
+        limiter = None
+    from oracle import ref_shim
+    R = ref_shim.load()
+    rng = np.random.RandomState(seed)
+    nu = np.linspace(band[0], band[1], m_ch)
+    src = R.FaradayThinSource(nu=nu, s_nu=0.0035 * rng.uniform(0.5, 1.5), phi_gal=rng.uniform(-500, 500), spectral_idx=1.0)
+    src.simulate()
+    src.apply_noise(SIGMA, random_state=rng)
+    par = R.Parameter()
+    par.calculate_cellsize(dataset=src, oversampling=8, verbose=False)
+    t0 = time.perf_counter()
+    dft = R.NDFT1DFixed(dataset=src, parameter=par)
+    f_dirty = dft.backward(src.data)
+    par.data = f_dirty
+    par.complex_data_to_real()
+    lam0 = 40.0 * src.theo_noise
+    chi2 = R.Chi2(dft_obj=dft, wavelet=None)          # (caches F_dirty: one more adjoint, chi2.py:15-19)
+    l1 = R.L1(reg=lam0)
+    opt = R.FISTA(guess_param=par, F_obj=R.OFunction(F=[chi2, l1]), fx=chi2, gx=R.OFunction(F=[l1]), noise=lam0 / 200.0,
+                  maxiter=k_sample, verbose=False)
+    opt.run()
+    dt = time.perf_counter() - t0
+    del limiter
+    return dt
+
+
+def _port_one_los(seed, k_sample, m_ch, band):
+    """the oracle's NumPy port with twiddles rebuilt in every transform (the reference's cost profile)"""
     try:
         from threadpoolctl import threadpool_limits
         limiter = threadpool_limits(limits=1)
@@ -75,12 +137,12 @@ def _cpu_one_los(args):
         limiter = None
     from oracle import restatement as ob
     rng = np.random.RandomState(seed)
-    nu = np.linspace(NU[0], NU[1], M_CH)
+    nu = np.linspace(band[0], band[1], m_ch)
     l2 = ob.lambda2_from_nu(nu)
-    sc = ob.dataset_scalars(l2, np.full(M_CH, SIGMA), 1.0)
+    sc = ob.dataset_scalars(l2, np.full(m_ch, SIGMA), 1.0)
     grid = ob.phi_grid(l2, sc["w"], 8.0)
     data = ob.thin_source(l2, 0.0035 * rng.uniform(0.5, 1.5), rng.uniform(-500, 500), 1.0)
-    data = data + rng.normal(0, SIGMA, M_CH) + 1j * rng.normal(0, SIGMA, M_CH)
+    data = data + rng.normal(0, SIGMA, m_ch) + 1j * rng.normal(0, SIGMA, m_ch)
     op = ob.ExactDFT(l2, grid["phi"], sc["w"], sc["s"], sc["k"], rebuild_twiddles=True)
     t0 = time.perf_counter()
     x0 = ob.complex_to_real(op.backward(data))
@@ -91,71 +153,63 @@ def _cpu_one_los(args):
     return dt
 
 
-def cpu_sample(k_sample, k_full, cores):
-    """one line of sight per core, k_sample iterations each; returns (LOS/s extrapolated to k_full, wall, text)"""
-    import multiprocessing as mp
-    ctx = mp.get_context("fork")
+def cpu_sample(k_sample, k_full, cores, wl):
+    """one line of sight per core, k_sample iterations each -> dict(value = LOS/s extrapolated to k_full, kind, sample)"""
+    from joblib import Parallel, delayed
+    from oracle import ref_shim
+    kind = "reference" if ref_shim.available() else "port"
+    fn = _ref_one_los if kind == "reference" else _port_one_los
     t0 = time.perf_counter()
-    with ctx.Pool(cores) as pool:
-        per_los = pool.map(_cpu_one_los, [(1000 + i, k_sample) for i in range(cores)])
+    per_los = Parallel(n_jobs=cores, backend="multiprocessing")(
+        delayed(fn)(1000 + i, k_sample, wl["m"], wl["band"]) for i in range(cores))
     wall = time.perf_counter() - t0
-    transforms_sample, transforms_full = 2 * k_sample + 2, 2 * k_full + 2
+    # transforms per run of the reference's classes: K x (forward + adjoint) + dirty + Chi2's cached F_dirty + final F(x)
+    extra = 3 if kind == "reference" else 2
+    t_sample, t_full = 2 * k_sample + extra, 2 * k_full + extra
     busy = max(per_los)
-    los_per_s = cores / (busy * transforms_full / transforms_sample)
-    text = ("%d LOS (one per core, m=%d n=%d), %d of %d FISTA iterations each = %d of %d transforms, slowest worker "
-            "%.2f s, extrapolated linearly in the transform count" %
-            (cores, M_CH, N_PHI, k_sample, k_full, transforms_sample, transforms_full, busy))
-    return los_per_s, wall, text
+    value = cores / (busy * t_full / t_sample)
+    what = ("the reference's own Dataset / Parameter / NDFT1D(+k) / Chi2 / L1 / OFunction / FISTA (unmodified files under %s)"
+            % ref_shim.source_dir() if kind == "reference" else "oracle.restatement port (oracle/_ref missing), twiddles rebuilt per transform")
+    text = ("%s; %d LOS (one per core, joblib multiprocessing, OMP_NUM_THREADS=1; m=%d n=%d), %d of %d FISTA iterations each = "
+            "%d of %d transforms, slowest worker %.2f s, extrapolated linearly in the transform count" %
+            (what, cores, wl["m"], wl["n"], k_sample, k_full, t_sample, t_full, busy))
+    return {"value": value, "unit": "LOS/s", "cores": cores, "kind": kind, "sample": text, "wall_s": wall}
 
 
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    wl = WORKLOADS[args.workload]
     cores = os.cpu_count() or 1
     for _ in range(args.warmup):
-        cpu_sample(1, args.iters, cores)
+        cpu_sample(1, args.iters, cores, wl)
     t0 = time.perf_counter()
-    vals = []
-    text = ""
+    vals, rec = [], None
     for _ in range(args.steps):
-        v, _, text = cpu_sample(args.cpu_iters, args.iters, cores)
-        vals.append(v)
+        rec = cpu_sample(args.cpu_iters, args.iters, cores, wl)
+        vals.append(rec["value"])
     wall = time.perf_counter() - t0
     value = float(np.mean(vals))
+    rec = dict(rec, value=value)
     line = {
         "impl": "reference", "metric": "lines-of-sight/sec (fixed-iter FISTA)", "value": value, "unit": "LOS/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * wall / max(args.steps, 1),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": workload_config(args),
-        "cpu_baseline": {"value": value, "unit": "LOS/s", "cores": cores, "kind": "port", "sample": text},
+        "config": workload_config(args, args.workload, wl["slab"]),
+        "cpu_baseline": rec,
         "e2e": {"value": value, "unit": "LOS/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line))
 
 
-def ncu_traffic(P):
-    """DRAM bytes per launch of the dominant kernel (the screening adjoint GEMM) from the committed `ncu --set full`
-    capture (profiles/r1_traffic.json, taken at 16384 lines of sight per launch); None if the slab size differs or the
-    file is missing."""
-    path = os.path.join(ROOT, "profiles", "r1_traffic.json")
-    if P != 16384 or WORKLOAD != "c3" or not os.path.exists(path):
-        return None
-    return json.load(open(path)).get("dominant_kernel_bytes")
-
-
-def workload_config(args):
-    text = ("C3: 512x512 px x 1000 ch cube (JVLA 1.008-2.031 GHz), shared lambda^2, n_phi=7968, delta-basis L1 FISTA, "
-            "exact DFT operator")
-    if WORKLOAD == "c4":
-        text = ("C4: 1024x1024 px x 2000 ch cube (JVLA 1.008-2.031 GHz), n_phi=15968, per-pixel weights and 10-20 % "
-                "flagged channels per pixel, per-pixel Galactic RM removed on the device inside the step, delta-basis L1 "
-                "FISTA, exact DFT operator")
-    return {"workload": text,
+def workload_config(args, name, slab):
+    wl = WORKLOADS[name]
+    return {"workload": wl["text"],
             "fista_iterations": args.iters, "lambda0": "40*theo_noise", "noise": "lambda0/200",
-            "los_per_step_per_gpu": args.slab, "transforms_per_los": 2 * args.iters + 2,
-            "l2_policy": "inputs larger than L2 (state 2 GB per slab; steps alternate between two slabs)",
+            "los_per_step_per_gpu": slab, "transforms_per_los": 2 * args.iters + 2,
+            "l2_policy": "inputs larger than L2 (the state of a slab is GBs; steps alternate between two slabs)",
             "e2e_pipeline": "public API per slab; the D2H of step i's solution overlaps step i+1's compute (second stream, "
                             "two pinned buffers); all copies inside the timed region",
             "parallelism": "pixel-sharded, no data-path collective"}
@@ -196,11 +250,65 @@ class ClockSampler(threading.Thread):
 
 
 # ---------------------------------------------------------------------------------------------------------
-# synthetic slab: generated on the device, outside every timed region
+# run context, tensor peaks measured in the run
 # ---------------------------------------------------------------------------------------------------------
-def make_slab(torch, src, P, seed, device):
+class Ctx:
+    pass
+
+
+def measure_tensor_peaks(ctx):
+    """dense 8192^3 matmul, bf16 (torch.matmul) and fp8 e4m3 (torch._scaled_mm): best of 10 (burst) and back to back for
+    ~1.5 s (sustained) -- the library figures the hand-written kernels are held against"""
+    torch = ctx.torch
+    n = 8192
+    out = {}
+
+    def timed(fn):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        best = 1e9
+        for _ in range(10):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            e1.synchronize()
+            best = min(best, e0.elapsed_time(e1))
+        reps = max(10, int(1500.0 / best))
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        e1.synchronize()
+        flop = 2.0 * n ** 3
+        return flop / best / 1e9, flop * reps / e0.elapsed_time(e1) / 1e9
+
+    try:
+        a = torch.randn((n, n), device=ctx.device, dtype=torch.bfloat16)
+        b = torch.randn((n, n), device=ctx.device, dtype=torch.bfloat16)
+        c = torch.empty((n, n), device=ctx.device, dtype=torch.bfloat16)
+        out["bf16_burst"], out["bf16_sustained"] = timed(lambda: torch.matmul(a, b, out=c))
+    except Exception as exc:  # pragma: no cover
+        out["bf16_error"] = repr(exc)[:200]
+    try:
+        a8 = (torch.randn((n, n), device=ctx.device) * 0.5).to(torch.float8_e4m3fn)
+        b8 = (torch.randn((n, n), device=ctx.device) * 0.5).to(torch.float8_e4m3fn).t()   # column-major operand
+        one = torch.ones((), device=ctx.device, dtype=torch.float32)
+        out["fp8_burst"], out["fp8_sustained"] = timed(
+            lambda: torch._scaled_mm(a8, b8, scale_a=one, scale_b=one, out_dtype=torch.bfloat16))
+    except Exception as exc:  # pragma: no cover
+        out["fp8_error"] = repr(exc)[:200]
+    return out
+
+
+# ---------------------------------------------------------------------------------------------------------
+# synthetic slabs (SURVEY.md section 8d): generated on the device, outside every timed region
+# ---------------------------------------------------------------------------------------------------------
+def make_sources(torch, src, P, seed, device):
     """thin source per pixel (phi ~ U(-500, 500), amplitude 0.0035 U(0.5, 1.5)), 30 % of pixels + a thick slab
-    (phi_fg ~ U(50, 200) centred on 200), alpha = 1, Gaussian noise sigma = 0.2 * 0.0035.  Returns complex64 (m, P)."""
+    (phi_fg ~ U(50, 200) centred on 200), alpha = 1.  Returns (noise-free complex128 (m, P), generator)."""
     g = torch.Generator(device=device).manual_seed(seed)
     l2 = torch.as_tensor(np.ascontiguousarray(src.lambda2), dtype=torch.float64, device=device)[:, None]
     s = torch.as_tensor(np.ascontiguousarray(src.s), dtype=torch.float64, device=device)[:, None]
@@ -210,16 +318,20 @@ def make_slab(torch, src, P, seed, device):
     thick = torch.rand(P, generator=g, device=device) < 0.3
     fg = 50.0 + 150.0 * torch.rand(P, generator=g, device=device, dtype=torch.float64)
     data = data + thick * (0.0035 * s * torch.exp(2j * l2 * 200.0) * torch.sinc(fg * l2 / np.pi))
-    if WORKLOAD == "c4":
-        return data, g
+    return data, g
+
+
+def make_slab(torch, src, P, seed, device):
+    """sources + Gaussian noise sigma = 0.2 * 0.0035 per channel.  complex64 (m, P)"""
+    data, g = make_sources(torch, src, P, seed, device)
     noise = torch.randn((2, src.m, P), generator=g, device=device, dtype=torch.float64) * SIGMA
     return (data + torch.complex(noise[0], noise[1])).to(torch.complex64)
 
 
 def make_slab_c4(torch, src, P, seed, device):
-    """C4 on top of the C3 sources: per-pixel sigma and flags, Galactic RM screen.  Returns (complex64 (m, P) data,
+    """C4 on top of the same sources: per-pixel sigma and flags, Galactic RM screen.  Returns (complex64 (m, P) data,
     fp32 [P, m] weights, fp32 [P] phi_gal)."""
-    clean, g = make_slab(torch, src, P, seed, device)
+    clean, g = make_sources(torch, src, P, seed, device)
     m = src.m
     sigma = SIGMA * (0.5 + 1.5 * torch.rand((m, P), generator=g, device=device, dtype=torch.float64))
     frac = 0.1 + 0.1 * torch.rand((1, P), generator=g, device=device, dtype=torch.float64)
@@ -232,129 +344,316 @@ def make_slab_c4(torch, src, P, seed, device):
     return data.to(torch.complex64), w.t().contiguous().float(), phi_gal.float()
 
 
-def run_ours(args):
-    import torch
-    import torch.distributed as dist
+class Workload:
+    """one BASELINE config at slab scale: two input slabs resident in HBM, one state slab, `step(i)` = the whole hot path"""
 
-    import __graft_entry__ as ge
-    ge.build()
-    import csromer_b200 as cs
-    from csromer_b200 import _device as dv
-    from csromer_b200 import _lib
-
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    device = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=device)
-    lib = _lib.load()
-    peaks = load_peaks()
-
-    nu = np.linspace(NU[0], NU[1], M_CH)
-    src = cs.FaradayThinSource(nu=nu, s_nu=0.0035, phi_gal=-200.0, spectral_idx=1.0)
-    src.simulate()
-    src.sigma = np.full(M_CH, SIGMA)
-    par = cs.Parameter()
-    par.calculate_cellsize(dataset=src, oversampling=8, verbose=False)
-    assert (src.m, len(par.phi)) == (M_CH, N_PHI)
-    plan = dv.DevicePlan.get(src.lambda2, src.l2_ref, par.phi, device)
-    P, K = args.slab, args.iters
-    lam0 = 40.0 * src.theo_noise
-    noise = lam0 / (2.0 * K)
-
-    s = torch.as_tensor(src.s, dtype=torch.float32, device=device)
-    if WORKLOAD == "c4":
-        made = [make_slab_c4(torch, src, P, 1235 + 17 * rank + i, device) for i in range(2)]
-        slabs_dev = [dv.pack_planar(c, plan.m, plan.ld2m, device)[0] for c, _, _ in made]
-        w_slabs, gal_slabs = [wt for _, wt, _ in made], [pg for _, _, pg in made]
-        slabs_host = None
-        del made
-        k_slabs = [(wt / s[None, :]).sum(dim=1) for wt in w_slabs]
-        lam_slabs = [40.0 / torch.sqrt(wt.sum(dim=1)) for wt in w_slabs]          # 40 theo_noise per pixel
-        noise_slabs = [lt / (2.0 * K) for lt in lam_slabs]
-        scratch = torch.empty_like(slabs_dev[0])
-    else:
-        slabs_c = [make_slab(torch, src, P, 1234 + 17 * rank + i, device) for i in range(2)]   # complex (m, P)
-        slabs_dev = [dv.pack_planar(c, plan.m, plan.ld2m, device)[0] for c in slabs_c]          # fp32 [P, 2m]
-        slabs_host = [c.cpu().pin_memory() for c in slabs_c]                                    # e2e inputs
-        del slabs_c
-    w = torch.as_tensor(src.w, dtype=torch.float32, device=device)
-    k = torch.full((P,), float(src.k), dtype=torch.float32, device=device)
-    lam_t = torch.full((P,), lam0, dtype=torch.float32, device=device)
-    noise_t = torch.full((P,), noise, dtype=torch.float32, device=device)
-    x = torch.zeros((P, plan.ld2n), dtype=torch.float32, device=device)
-    norm_buf = torch.zeros(2, dtype=torch.float32, device=device)
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def device_step(i):
-        if WORKLOAD == "c4":
-            j = i % 2
-            scratch.copy_(slabs_dev[j])
-            plan.derotate(scratch, gal_slabs[j])        # Dataset.subtract_galacticrm (base/dataset.py:377-381)
-            out = plan.fista(scratch, w_slabs[j], s, k_slabs[j], x, lam_slabs[j], noise_slabs[j], K,
-                             use_dirty_as_guess=True, want_delta=True, want_mma_blocks=True)
+    def __init__(self, ctx, name, slab, iters):
+        import csromer_b200 as cs
+        from csromer_b200 import _device as dv
+        torch = ctx.torch
+        self.ctx, self.name, self.wl, self.P, self.K = ctx, name, WORKLOADS[name], slab, iters
+        wl, dev, P, K = self.wl, ctx.device, slab, iters
+        nu = np.linspace(wl["band"][0], wl["band"][1], wl["m"])
+        src = cs.FaradayThinSource(nu=nu, s_nu=0.0035, phi_gal=-200.0, spectral_idx=1.0)
+        src.simulate()
+        src.sigma = np.full(wl["m"], SIGMA)
+        par = cs.Parameter()
+        par.calculate_cellsize(dataset=src, oversampling=8, verbose=False)
+        assert (src.m, len(par.phi)) == (wl["m"], wl["n"]), (src.m, len(par.phi))
+        self.src, self.par = src, par
+        self.plan = plan = dv.DevicePlan.get(src.lambda2, src.l2_ref, par.phi, dev)
+        self.m, self.n = plan.m, plan.n
+        self.lam0 = 40.0 * src.theo_noise
+        self.noise = self.lam0 / (2.0 * K)
+        self.s = torch.as_tensor(src.s, dtype=torch.float32, device=dev)
+        self.step_size, self.engine, self.slabs_host = 1.0, None, None
+        seeds = [wl["seed"] + 17 * ctx.rank + i for i in range(2)]
+        if name == "c4":
+            made = [make_slab_c4(torch, src, P, sd, dev) for sd in seeds]
+            self.slabs_dev = [dv.pack_planar(c, plan.m, plan.ld2m, dev)[0] for c, _, _ in made]
+            self.w_slabs, self.gal_slabs = [wt for _, wt, _ in made], [pg for _, _, pg in made]
+            del made
+            self.k_slabs = [(wt / self.s[None, :]).sum(dim=1) for wt in self.w_slabs]
+            self.lam_slabs = [40.0 / torch.sqrt(wt.sum(dim=1)) for wt in self.w_slabs]          # 40 theo_noise per pixel
+            self.noise_slabs = [lt / (2.0 * K) for lt in self.lam_slabs]
+            self.scratch = torch.empty_like(self.slabs_dev[0])
         else:
-            out = plan.fista(slabs_dev[i % 2], w, s, k, x, lam_t, noise_t, K, use_dirty_as_guess=True, want_delta=True,
+            slabs_c = [make_slab(torch, src, P, sd, dev) for sd in seeds]                  # complex (m, P)
+            self.slabs_dev = [dv.pack_planar(c, plan.m, plan.ld2m, dev)[0] for c in slabs_c]  # fp32 [P, 2m]
+            if name == "c3":
+                self.slabs_host = [c.cpu().pin_memory() for c in slabs_c]                  # e2e inputs
+            del slabs_c
+            self.w = torch.as_tensor(src.w, dtype=torch.float32, device=dev)
+            self.k = torch.full((P,), float(src.k), dtype=torch.float32, device=dev)
+            self.lam_t = torch.full((P,), self.lam0, dtype=torch.float32, device=dev)
+            self.noise_t = torch.full((P,), self.noise, dtype=torch.float32, device=dev)
+        if name == "c5":
+            from csromer_b200.cube import estimate_lipschitz
+            self.dft = cs.NDFT1D(dataset=src, parameter=par)
+            self.step_size = 1.0 / estimate_lipschitz(self.dft)
+            self.engine = cs.UndecimatedWavelet(wavelet_name="coif2").prepare(2 * plan.n)
+            self.x = torch.zeros((P, self.engine.ldc), dtype=torch.float32, device=dev)
+        else:
+            self.x = torch.zeros((P, plan.ld2n), dtype=torch.float32, device=dev)
+        self.norm_buf = torch.zeros(2, dtype=torch.float32, device=dev)
+
+    def step(self, i, collective=True):
+        torch, plan, K, j = self.ctx.torch, self.plan, self.K, i % 2
+        if self.name == "c4":
+            self.scratch.copy_(self.slabs_dev[j])
+            plan.derotate(self.scratch, self.gal_slabs[j])      # Dataset.subtract_galacticrm (base/dataset.py:377-381)
+            out = plan.fista(self.scratch, self.w_slabs[j], self.s, self.k_slabs[j], self.x, self.lam_slabs[j],
+                             self.noise_slabs[j], K, use_dirty_as_guess=True, want_delta=True, want_mma_blocks=True)
+        else:
+            out = plan.fista(self.slabs_dev[j], self.w, self.s, self.k, self.x, self.lam_t, self.noise_t, K,
+                             step=self.step_size, wavelet=self.engine, use_dirty_as_guess=True, want_delta=True,
                              want_mma_blocks=True)
-        # global convergence norm: the only collective on the path (mean |x_new - x_old| over all lines of sight)
-        torch.sum(out["delta"], dim=0, out=norm_buf[0])
-        norm_buf[1].fill_(float(P))
-        if world > 1:
-            dist.all_reduce(norm_buf)
+        if collective:
+            # global convergence norm: the only collective on the path (mean |x_new - x_old| over all lines of sight)
+            torch.sum(out["delta"], dim=0, out=self.norm_buf[0])
+            self.norm_buf[1].fill_(float(self.P))
+            if self.ctx.world > 1:
+                self.ctx.dist.all_reduce(self.norm_buf)
         return out
 
-    # ---- device-resident timing -------------------------------------------------------------------------
-    for i in range(args.warmup):
-        device_step(i)
-    barrier()
-    sampler = ClockSampler(local)
+    # ---- host copies of a few lines of sight of slab j, for the oracle ------------------------------------------
+    def oracle_solution(self, j, idx):
+        """oracle.restatement.fista on lines of sight `idx` of slab j -> dict(x (ncoef, len(idx)), model)"""
+        from oracle import restatement as ob
+        torch, m = self.ctx.torch, self.m
+        sel = torch.as_tensor(np.asarray(idx), device=self.ctx.device)
+        rows = self.slabs_dev[j].index_select(0, sel).double().cpu().numpy()           # [len(idx), ld2m] planar
+        data = (rows[:, :m] + 1j * rows[:, m:2 * m]).T                                   # (m, len(idx))
+        l2, phi = np.asarray(self.src.lambda2, dtype=np.float64), np.asarray(self.par.phi, dtype=np.float64)
+        s = np.asarray(self.src.s, dtype=np.float64)
+        big = self.m * self.n > 2.0e7
+        if self.name == "c4":
+            w = self.w_slabs[j].index_select(0, sel).double().cpu().numpy().T            # (m, len(idx))
+            gal = self.gal_slabs[j].index_select(0, sel).double().cpu().numpy()
+            data = ob.subtract_galactic_rm(data, l2, gal)
+            op = ob.ExactDFT(l2, phi, w, s, cache_adjoint=big)
+            lam = 40.0 / np.sqrt(w.sum(axis=0))
+            noise = lam / (2.0 * self.K)
+        else:
+            op = ob.ExactDFT(l2, phi, np.asarray(self.src.w, dtype=np.float64), s, float(self.src.k), cache_adjoint=big)
+            lam, noise = self.lam0, self.noise
+        x0 = ob.complex_to_real(op.backward(data))
+        wav = None
+        if self.name == "c5":
+            wav = ob.WaveletDict("coif2", kind="swt", fast_iswt=True)
+            x0 = wav.decompose(x0)
+        return ob.fista(op, data, x0, lam, noise, self.K, wavelet=wav, step=self.step_size)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# measurement of one workload
+# ---------------------------------------------------------------------------------------------------------
+def collect_profile(lib):
+    from csromer_b200 import _lib
+    ms, cnt = np.zeros(12, dtype=np.float64), np.zeros(12, dtype=np.int64)
+    lib.csr_profile(0)
+    _lib.check(lib.csr_profile_collect(ms.ctypes.data_as(ctypes.POINTER(ctypes.c_double)),
+                                       cnt.ctypes.data_as(ctypes.POINTER(ctypes.c_longlong))), "csr_profile_collect")
+    return ms, cnt
+
+
+def timed_steps(ctx, w, steps, warmup, first=0):
+    """W untimed + K timed steps (barrier + synchronize on both sides, CUDA events, max over ranks)"""
+    torch, lib = ctx.torch, ctx.lib
+    for i in range(warmup):
+        w.step(first + i)
+    ctx.barrier()
+    sampler = ClockSampler(ctx.local)
     sampler.start()
     lib.csr_launch_count(1)
     lib.csr_profile(1)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for i in range(args.steps):
-        out = device_step(i)
+    out = None
+    for i in range(steps):
+        out = w.step(first + warmup + i)
     e1.record()
-    barrier()
+    ctx.barrier()
     sampler.stop_flag = True
     launches = int(lib.csr_launch_count(0))
-    ms = (np.zeros(12, dtype=np.float64), np.zeros(12, dtype=np.int64))
-    lib.csr_profile(0)
-    _lib.check(lib.csr_profile_collect(ms[0].ctypes.data_as(ctypes.POINTER(ctypes.c_double)),
-                                       ms[1].ctypes.data_as(ctypes.POINTER(ctypes.c_longlong))), "csr_profile_collect")
-    elapsed = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=device)
-    if world > 1:
-        dist.all_reduce(elapsed, op=dist.ReduceOp.MAX)
-    elapsed_ms = float(elapsed.item())
-    finite = bool(torch.isfinite(x).all())
-    conv_norm = float(norm_buf[0] / norm_buf[1])
-    value = world * P * args.steps / (elapsed_ms * 1e-3)
+    ms, cnt = collect_profile(lib)
+    elapsed = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=ctx.device)
+    if ctx.world > 1:
+        ctx.dist.all_reduce(elapsed, op=ctx.dist.ReduceOp.MAX)
+    return dict(elapsed_ms=float(elapsed.item()), launches=launches, ms=ms, cnt=cnt, out=out, clocks=sampler.summary(),
+                blocks=out["mma_blocks"].double().cpu().numpy())      # blocks: per step, per kind
 
-    # ---- end to end through the public API with host buffers ----------------------------------------------
-    # Streaming pipeline, as a cube run would do it: the device->host copy of step i's solution slab runs on a second
-    # stream into one of two pinned buffers while step i+1 computes; every step's H2D and D2H stay inside the timed
-    # region (the last copy is waited for before the clock stops).
-    out_host = [torch.empty((2 * N_PHI, P), dtype=torch.float32).pin_memory() for _ in range(2)] if WORKLOAD == "c3" else None
-    copy_stream = torch.cuda.Stream(device=device)
+
+def ncu_capture(name):
+    """per-kernel DRAM bytes per launch from the committed `ncu --set full` capture of THIS build (profiles/r2_traffic.json,
+    taken at the bench slab sizes); {} when missing"""
+    path = os.path.join(ROOT, "profiles", "r2_traffic.json")
+    if not os.path.exists(path):
+        return {}
+    return json.load(open(path)).get(name, {})
+
+
+def kernel_table(w, res, steps, peaks):
+    """per kernel kind: launches, avg ms, share of the step, algorithmic and executed rates against the bounding peak"""
+    ms, cnt, blocks, elapsed_ms = res["ms"], res["cnt"], res["blocks"], res["elapsed_ms"]
+    P, m, n = w.P, w.m, w.n
+    flops_transform = 8.0 * m * n * P                     # one transform of the slab, algorithmic (SURVEY.md 8d)
+    traffic = ncu_capture(w.name) if P == w.wl["slab"] else {}
+    table = {}
+    C = w.engine.ncoef if w.engine is not None else 0
+    for kind in range(12):
+        if cnt[kind] == 0:
+            continue
+        avg_ms = float(ms[kind] / cnt[kind])
+        per_step = cnt[kind] / steps
+        rec = {"kernel": KERNEL_OF_KIND.get(kind, KIND_NAMES[kind]), "launches": int(cnt[kind]), "avg_ms": avg_ms,
+               "share_of_step": float(ms[kind] / elapsed_ms)}
+        dram = traffic.get(KIND_NAMES[kind])
+        if kind in (0, 1, 2, 5, 8, 9, 10):
+            fp8 = kind == 9
+            peak = peaks["fp8_sustained"] if fp8 else peaks["bf16_sustained"]
+            ex = blocks[kind] / per_step * BLOCK_FLOPS / (avg_ms * 1e-3) / 1e12        # issued by the tensor cores
+            burst = peaks["measured_in_run"].get("fp8_burst" if fp8 else "bf16_burst")
+            rec.update({"bound": "tensor", "peak": peak, "unit": "TFLOP/s",
+                        "peak_source": peaks["fp8_source"] if fp8 else peaks["bf16_source"],
+                        "executed": ex, "executed_frac": ex / peak if peak else None,
+                        "executed_frac_of_burst_peak": ex / burst if burst else None})
+            if kind in (0, 1, 2):   # a launch of these kinds stands for one whole transform of the slab
+                alg = flops_transform / (avg_ms * 1e-3) / 1e12
+                rec["algorithmic"] = alg
+                rec["algorithmic_frac"] = alg / peak
+                if alg > peak / 3.0:
+                    rec["algorithmic_note"] = ("above 1/3 of the peak (three fp16 products per algorithmic product) only "
+                                               "because provably-zero K blocks / tiles are skipped")
+        if kind == 2:   # the forward transform in the sparse regime is bound by its fused epilogue's HBM traffic
+            nbytes = P * 2.0 * m * (4 + 2 + 2 + 1)       # b read (fp32); r_hi, r_lo (fp16), r8 (fp8) written
+            rec["hbm"] = {"bound": "hbm", "algorithmic_bytes": nbytes, "algorithmic": nbytes / (avg_ms * 1e-3) / 1e9,
+                          "peak": peaks["hbm"], "unit": "GB/s", "algorithmic_frac": nbytes / (avg_ms * 1e-3) / 1e9 / peaks["hbm"]}
+        if kind == 11:
+            rec.update({"bound": "hbm", "note": "redo pass over the few blocks that failed the bound; nearly all blocks are "
+                                                "skipped, so no algorithmic rate is quoted"})
+        if kind in (6, 7):
+            nbytes = (C + 2 * n) * 4.0 * P if kind == 6 else (2 * n + 4 * C) * 4.0 * P     # SURVEY.md 8d: ~24 C per LOS-iteration
+            alg = nbytes / (avg_ms * 1e-3) / 1e9
+            rec.update({"bound": "hbm", "peak": peaks["hbm"], "unit": "GB/s", "peak_source": peaks["source"],
+                        "algorithmic_bytes": nbytes, "algorithmic": alg, "algorithmic_frac": alg / peaks["hbm"]})
+            if alg > peaks["hbm"]:
+                rec["algorithmic_note"] = ("above the HBM peak only because blocks whose coefficient state is and stays zero "
+                                           "are skipped (coefficient-state flags); see `executed`")
+        if dram is not None:
+            rec["traffic"] = dram
+            rec["executed_gbs"] = dram / (avg_ms * 1e-3) / 1e9
+            rec["executed_hbm_frac"] = rec["executed_gbs"] / peaks["hbm"]
+            rec["traffic_source"] = "ncu dram__bytes_read.sum + dram__bytes_write.sum per launch, profiles/r2_traffic.json"
+        table[KIND_NAMES[kind]] = rec
+    return table
+
+
+def headline_roofline(w, res, table, steps, peaks):
+    """the base contract's `roofline` object: the kernel with the largest share of the step"""
+    if not table:
+        return None
+    dom = max(table, key=lambda k: table[k]["share_of_step"])
+    rec = table[dom]
+    K = w.K
+    transforms = float(sum(res["cnt"][i] for i in (0, 1, 2, 5))) / steps
+    gemm_ms = float(sum(res["ms"][i] for i in (0, 1, 2, 5, 8, 9, 10)))
+    path_alg = 8.0 * w.m * w.n * w.P * (2 * K + 2) * steps / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else None
+    if rec.get("bound") == "tensor":
+        achieved, peak, frac, unit = rec["executed"], rec["peak"], rec["executed_frac"], "TFLOP/s"
+        what = "achieved = tensor-core flops the kernel ISSUED (in-kernel MMA counter) / its CUDA-event time"
+        if dom == "resid_forward":    # its bound is the epilogue's HBM traffic
+            h = rec["hbm"]
+            achieved, peak, frac, unit = h["algorithmic"], h["peak"], h["algorithmic_frac"], "GB/s"
+            what = ("achieved = algorithmic bytes of the fused residual epilogue (9 B per element of the [P, 2m] residual) / "
+                    "CUDA-event time; the MMA work of the ~9 active K blocks is minor")
+    else:
+        achieved, peak, frac, unit = rec.get("algorithmic"), rec.get("peak"), rec.get("algorithmic_frac"), "GB/s"
+        if "executed_gbs" in rec:   # the ncu DRAM bytes of this build's capture are the honest numerator
+            achieved, frac = rec["executed_gbs"], rec["executed_hbm_frac"]
+        what = ("achieved = ncu DRAM bytes per launch (committed capture of this build) / CUDA-event time" if "executed_gbs" in rec
+                else "achieved = algorithmic bytes (SURVEY.md 8d) / CUDA-event time; blocks skipped by the exact zero-state "
+                     "flags are counted as moved, so a fraction above 1 means skipped work, not bandwidth")
+    return {"bound": "hbm" if unit == "GB/s" else "tensor", "kernel": rec["kernel"], "kind": dom, "achieved": achieved,
+            "peak": peak, "unit": unit, "frac": frac, "traffic": rec.get("traffic"), "what": what,
+            "peak_source": rec.get("peak_source", peaks["source"]), "kernel_share_of_step": rec["share_of_step"],
+            "path": {"what": "all transform launches of the step: algorithmic 8 m n flops per line of sight per transform / "
+                             "their summed CUDA-event time; exact shortcuts (K-block skipping, safe screening) skip "
+                             "provably-zero work, so this is NOT a hardware utilisation",
+                     "algorithmic_tflops_with_skipped_work": path_alg,
+                     "gemm_share_of_step": gemm_ms / res["elapsed_ms"], "transform_launch_groups_per_step": transforms},
+            "per_kernel": table}
+
+
+def parity_check(ctx, w, sample):
+    """(i) shortcuts on vs dense: bit equality of the solution slab; (ii) sampled LOS against the oracle"""
+    from csromer_b200 import _lib
+    torch = ctx.torch
+    rec = {"slab": w.P, "iterations": w.K}
+    w.step(0, collective=False)
+    torch.cuda.synchronize()
+    x_fast = w.x.clone()
+    t0 = time.perf_counter()
+    _lib.set_option("zero_skip", 0)          # switches off every exact shortcut downstream of it (fista.cu)
+    try:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        w.step(0, collective=False)
+        e1.record()
+        torch.cuda.synchronize()
+    finally:
+        _lib.set_option("zero_skip", 1)
+    dense_ms = e0.elapsed_time(e1)
+    diff = (w.x != x_fast)
+    rec["shortcuts_vs_dense"] = {"bit_equal": not bool(diff.any()), "mismatches": int(diff.sum()),
+                                 "elements": int(x_fast.numel()), "dense_step_ms": dense_ms,
+                                 "dense_los_per_s": w.P / (dense_ms * 1e-3),
+                                 "what": "x of the bench slab, all exact shortcuts on vs zero_skip=0 (dense three-product "
+                                         "GEMMs, no screening, no state flags)"}
+    del diff
+    rec["finite"] = bool(torch.isfinite(x_fast).all())
+    if sample > 0 and ctx.rank == 0 and (ctx.world == 1 or os.environ.get("CSR_BENCH_ORACLE_ALL_N")):  # (like cpu_baseline: N = 1 only)
+        idx = np.linspace(0, w.P - 1, sample).astype(np.int64)
+        t0 = time.perf_counter()
+        ref = w.oracle_solution(0, idx)
+        ncoef = ref["x"].shape[0]
+        got = x_fast.index_select(0, torch.as_tensor(idx, device=ctx.device))[:, :ncoef].double().cpu().numpy().T
+        scale = np.abs(ref["x"]).max()
+        err = float(np.abs(got - ref["x"]).max() / scale)
+        support_ref = np.abs(ref["x"]) > 1e-6 * scale
+        support_got = got != 0.0
+        rec["oracle"] = {"los": [int(i) for i in idx], "parity_max_rel": err, "tolerance": 1e-4,
+                         "ok": bool(np.isfinite(err) and err < 1e-4),
+                         "nonzeros_ref": int(support_ref.sum()), "nonzeros_gpu": int(support_got.sum()),
+                         "oracle_finite": bool(np.isfinite(ref["x"]).all() and scale < 10.0),
+                         "seconds": time.perf_counter() - t0,
+                         "what": "max |x_gpu - x_oracle| / max |x_oracle| over the sampled lines of sight of the bench slab, "
+                                 "oracle = oracle.restatement.fista in float64 (same inputs read back from the device)"}
+    rec["ok"] = rec["shortcuts_vs_dense"]["bit_equal"] and rec["finite"] and rec.get("oracle", {}).get("ok", True)
+    return rec, x_fast
+
+
+def e2e_c3(ctx, w, args):
+    """C3 end to end through the public API with HOST buffers.  Streaming pipeline, as a cube run would do it: the
+    device->host copy of step i's solution runs on a second stream into one of two pinned buffers while step i+1
+    computes; every step's H2D and D2H stay inside the timed region (the last copy is waited for before the clock stops)."""
+    import csromer_b200 as cs
+    torch = ctx.torch
+    P, K, n = w.P, w.K, w.n
+    out_host = [torch.empty((2 * n, P), dtype=torch.float32).pin_memory() for _ in range(2)]
+    copy_stream = torch.cuda.Stream(device=ctx.device)
     copy_done = [None, None]
 
     def e2e_step(i):
-        ds = cs.Dataset(lambda2=src.lambda2, data=slabs_host[i % 2], sigma=src.sigma, spectral_idx=1.0)
-        dft = cs.NDFT1D(dataset=ds, parameter=par)
+        ds = cs.Dataset(lambda2=w.src.lambda2, data=w.slabs_host[i % 2], sigma=w.src.sigma, spectral_idx=1.0)
+        dft = cs.NDFT1D(dataset=ds, parameter=w.par)
         f_dirty = dft.backward(ds.data)                      # H2D of the slab + dirty spectrum
-        guess = cs.Parameter(phi=par.phi, cellsize=par.cellsize)
+        guess = cs.Parameter(phi=w.par.phi, cellsize=w.par.cellsize)
         guess.data = f_dirty
         guess.complex_data_to_real()
         chi2 = cs.Chi2(dft_obj=dft, F_dirty=f_dirty)
-        l1 = cs.L1(reg=lam0)
-        opt = cs.FISTA(guess_param=guess, F_obj=cs.OFunction([chi2, l1]), fx=chi2, gx=cs.OFunction([l1]), noise=noise,
+        l1 = cs.L1(reg=w.lam0)
+        opt = cs.FISTA(guess_param=guess, F_obj=cs.OFunction([chi2, l1]), fx=chi2, gx=cs.OFunction([l1]), noise=w.noise,
                        maxiter=K, verbose=False)
         cost, X = opt.run()                                  # (returns after the D2H of the per-pixel cost)
         ready = torch.cuda.Event()
@@ -369,148 +668,128 @@ def run_ours(args):
             copy_done[i % 2].record(copy_stream)
         return cost
 
-    e2e_steps = max(1, min(args.steps, args.e2e_steps))
-    if WORKLOAD == "c3":
-        e2e_step(0)
-        copy_stream.synchronize()
-        barrier()
-        t0 = time.perf_counter()
-        for i in range(e2e_steps):
-            cost = e2e_step(i)
-        copy_stream.synchronize()
-        barrier()
-        e2e_wall = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=device)
-        if world > 1:
-            dist.all_reduce(e2e_wall, op=dist.ReduceOp.MAX)
-        e2e_value = world * P * e2e_steps / float(e2e_wall.item())
-    else:  # the optional workloads report the device-resident rate only
-        e2e_value, cost = None, (out["cost"][:, 0] + lam_slabs[0] * 0.5 * out["cost"][:, 1]).cpu().numpy()
-    h2d = P * M_CH * 8
-    d2h = P * 2 * N_PHI * 4 + P * 8      # solution slab (fp32 planar) + per-pixel (chi2, l1) values
+    steps = max(1, min(args.steps, args.e2e_steps))
+    e2e_step(0)
+    copy_stream.synchronize()
+    ctx.barrier()
+    t0 = time.perf_counter()
+    for i in range(steps):
+        cost = e2e_step(i)
+    copy_stream.synchronize()
+    ctx.barrier()
+    wall = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=ctx.device)
+    if ctx.world > 1:
+        ctx.dist.all_reduce(wall, op=ctx.dist.ReduceOp.MAX)
+    return {"value": ctx.world * P * steps / float(wall.item()), "unit": "LOS/s", "h2d_bytes_per_step": P * w.m * 8,
+            "d2h_bytes_per_step": P * 2 * n * 4 + P * 8, "steps": steps,
+            "what": "solution slab shipped dense (fp32 planar) + per-pixel (chi2, l1) values"}, float(np.mean(np.asarray(cost)))
 
-    # ---- dense reference leg: the same step with every exact shortcut switched off (bit-identical results) ------
-    def profiled(steps):
-        lib.csr_profile(1)
-        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        t0.record()
-        for i in range(steps):
-            o = device_step(i)
-        t1.record()
+
+def run_workload(ctx, name, args, steps, warmup, peaks, headline):
+    torch = ctx.torch
+    slab = args.slab if (headline and args.slab) else WORKLOADS[name]["slab"]
+    w = Workload(ctx, name, slab, args.iters)
+    res = timed_steps(ctx, w, steps, warmup)
+    value = ctx.world * w.P * steps / (res["elapsed_ms"] * 1e-3)
+    table = kernel_table(w, res, steps, peaks)
+    roof = headline_roofline(w, res, table, steps, peaks)
+    conv = float(w.norm_buf[0] / w.norm_buf[1])
+    rec = {"metric": "lines-of-sight/sec (fixed-iter FISTA)", "value": value, "unit": "LOS/s", "n_gpus": ctx.world,
+           "steps": steps, "warmup": warmup, "ms_per_step": res["elapsed_ms"] / steps,
+           "ms_per_iteration": res["elapsed_ms"] / steps / max(w.K, 1),
+           "config": workload_config(args, name, w.P), "gpu_launches": res["launches"], "roofline": roof,
+           "clocks": res["clocks"], "convergence_norm": conv,
+           "algorithmic_tflops_with_skipped_work": value * 8.0 * w.m * w.n * (2 * w.K + 2) / 1e12}
+    if name == "c5":
+        rec["step_size"] = w.step_size
+        rec["full_cube_seconds_at_this_rate"] = 2048.0 * 2048.0 / value
+    parity = None
+    if not args.no_parity:
+        parity, _ = parity_check(ctx, w, args.parity_los if name != "c5" else min(args.parity_los, 4))
+        ctx.barrier()
+    extra = {}
+    if name == "c3" and headline:
+        extra["e2e"], extra["final_cost_mean"] = e2e_c3(ctx, w, args)
+    # free the slab, the plan tables and the workspace before the next workload
+    from csromer_b200 import _device as dv
+    for plan in list(dv.DevicePlan._cache.values()):
+        plan.ws.buf = None
+        plan.close()
+    dv.DevicePlan._cache.clear()
+    del w
+    torch.cuda.empty_cache()
+    return rec, parity, extra
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    import __graft_entry__ as ge
+    ge.build()
+    from csromer_b200 import _lib
+
+    ctx = Ctx()
+    ctx.torch, ctx.dist = torch, dist
+    ctx.world = int(os.environ.get("WORLD_SIZE", "1"))
+    ctx.rank = int(os.environ.get("RANK", "0"))
+    ctx.local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(ctx.local)
+    ctx.device = torch.device("cuda", ctx.local)
+    if ctx.world > 1:
+        dist.init_process_group("nccl", device_id=ctx.device)
+    ctx.lib = _lib.load()
+
+    def barrier():
+        if ctx.world > 1:
+            dist.barrier()
         torch.cuda.synchronize()
-        lib.csr_profile(0)
-        pm = (np.zeros(12, dtype=np.float64), np.zeros(12, dtype=np.int64))
-        _lib.check(lib.csr_profile_collect(pm[0].ctypes.data_as(ctypes.POINTER(ctypes.c_double)),
-                                           pm[1].ctypes.data_as(ctypes.POINTER(ctypes.c_longlong))), "csr_profile_collect")
-        return t0.elapsed_time(t1), pm, o
+    ctx.barrier = barrier
 
-    flops_launch = 8.0 * M_CH * N_PHI * P        # one transform = 8 m n algorithmic flops per line of sight
-    peak = peaks["tf_sustained"]
-    dense = None
-    if not args.no_dense:
-        _lib.set_option("zero_skip", 0)
-        try:
-            device_step(0)
-            d_ms, d_pm, _ = profiled(1)
-        finally:
-            _lib.set_option("zero_skip", 1)
-        d_gemm_ms, d_n = float(d_pm[0][:6].sum()), int(d_pm[1][:6].sum())
-        d_ach = flops_launch * d_n / (d_gemm_ms * 1e-3) / 1e12
-        dense = {"what": "same step, exact shortcuts off (zero_skip=0): every transform is a dense three-product GEMM",
-                 "value": world * P / (d_ms * 1e-3), "unit": "LOS/s", "ms_per_step": d_ms,
-                 "gemm_launches": d_n, "gemm_avg_ms": d_gemm_ms / d_n, "achieved": d_ach, "frac": d_ach / peak,
-                 "executed_tflops": 3.0 * d_ach, "executed_frac": 3.0 * d_ach / peak,
-                 "note": "3 fp16 MMAs per algorithmic product (hi/lo split, fp32-class accuracy): frac <= 1/3"}
-        barrier()
+    base = load_peaks()
+    measured = measure_tensor_peaks(ctx) if not args.no_peaks else {}
+    peaks = {"hbm": base["hbm"], "source": base["source"], "measured_in_run": measured,
+             "driver_bf16_sustained": base["tf_sustained"], "driver_bf16_burst": base["tf_burst"]}
+    if "bf16_sustained" in measured:
+        peaks["bf16_sustained"], peaks["bf16_source"] = measured["bf16_sustained"], \
+            "measured in this run: torch.matmul bf16 8192^3 back to back (sustained); burst %.0f" % measured["bf16_burst"]
+    else:
+        peaks["bf16_sustained"], peaks["bf16_source"] = base["tf_sustained"], base["source"]
+    if "fp8_sustained" in measured:
+        peaks["fp8_sustained"], peaks["fp8_source"] = measured["fp8_sustained"], \
+            "measured in this run: torch._scaled_mm e4m3 8192^3 back to back (sustained); burst %.0f" % measured["fp8_burst"]
+    else:
+        peaks["fp8_sustained"], peaks["fp8_source"] = 2.0 * peaks["bf16_sustained"], \
+            "DERIVED, not measured: 2 x the bf16 figure (torch._scaled_mm unavailable: %s)" % measured.get("fp8_error", "skipped")
+    barrier()
 
-    # ---- roofline ------------------------------------------------------------------------------------------------
-    # A FISTA-adjoint transform is a cascade: fp8 screening launch over the tiles whose state is zero -> fp16
-    # screening of the tiles that fail it -> three-product launch on what is left; together ONE transform.
-    # `executed` is what the tensor cores really issued (in-kernel counters of 128 x 256 x 64 blocks).
-    names = ["plain_forward", "plain_adjoint", "resid_forward", "resid_adjoint", "fista_forward", "fista_adjoint",
-             "swt_synth_fused", "swt_analysis_update_fused", "screen_adjoint_fp16", "screen_adjoint_fp8"]
-    gemm_kinds = [0, 1, 2, 3, 4, 5, 8, 9]
-    gemm_ms = float(sum(ms[0][i] for i in gemm_kinds))
-    transforms = int(sum(ms[1][i] for i in (0, 1, 2, 3, 4, 5)))
-    path_ach = flops_launch * transforms / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
-    per_kind = {}
-    for idx in gemm_kinds:
-        if ms[1][idx]:
-            per_kind[names[idx]] = {"launches": int(ms[1][idx]), "avg_ms": float(ms[0][idx] / ms[1][idx]),
-                                    "share_of_step": float(ms[0][idx] / elapsed_ms)}
-    block_flops = 2.0 * 128 * 256 * 64
-    blocks = out["mma_blocks"].double().cpu().numpy()          # per step: [three-product, fp16 screen, fp8 screen, -]
-    dominant = max(per_kind, key=lambda kname: per_kind[kname]["share_of_step"]) if per_kind else None
-    # the fp8 screening kernel and the forward transform take about the same time per launch (0.30 ms each): report the
-    # tensor-core kernel under `roofline` whenever it is within 10 % of the top share, the forward transform (bound by its
-    # fused epilogue's HBM traffic) under `roofline.second_kernel`, so that the line does not flip between runs
-    if dominant and "screen_adjoint_fp8" in per_kind and \
-            per_kind["screen_adjoint_fp8"]["share_of_step"] >= 0.9 * per_kind[dominant]["share_of_step"]:
-        dominant = "screen_adjoint_fp8"
-    second = None
-    if "resid_forward" in per_kind:
-        f_ms = per_kind["resid_forward"]["avg_ms"]
-        f_bytes = P * 2.0 * M_CH * (4 + 2 + 2 + 1)      # per element: b read (fp32), r_hi, r_lo (fp16) and r8 (fp8) written
-        second = {"kernel": "dft_gemm_kernel<EPI_RESID>: forward transform with K-block skipping + fused residual epilogue",
-                  "bound": "hbm", "achieved": f_bytes / (f_ms * 1e-3) / 1e9, "peak": peaks["hbm"], "unit": "GB/s",
-                  "frac": f_bytes / (f_ms * 1e-3) / 1e9 / peaks["hbm"], "avg_ms": f_ms,
-                  "share_of_step": per_kind["resid_forward"]["share_of_step"],
-                  "note": "algorithmic bytes = 9 B per output element of the [P, 2m] residual; with ~9 of 249 K blocks active "
-                          "the MMA work is negligible and the kernel is bound by the ~20 us fused epilogue of each 128 x 256 "
-                          "tile (8 epilogue warps per SM, 32-byte row segments), not by HBM bandwidth: the next thing to fix"}
-    if dominant == "screen_adjoint_fp8":
-        k_ms = ms[0][9] / args.steps
-        k_tf = blocks[2] * block_flops / (k_ms * 1e-3) / 1e12
-        k_peak, k_src = 2.0 * peak, ("2 x MEASURED_PEAKS.json bf16_tflops_sustained (%s): no fp8 figure is measured on this "
-                                     "pool; nominal fp8 dense = 2 x bf16" % peaks["source"])
-        k_name = ("screen8_pair_kernel<3>: mirror-symmetric fp8 (e4m3) screening pass of the adjoint transform on CTA pairs "
-                  "(+phi and -phi decided by one product with half the K), tcgen05 cta_group::2 kind::f8f6f4")
-        k_note = ("achieved = fp8 flops the kernel issued (in-kernel counter) / its CUDA-event time; the kernel is bound by the "
-                  "L2->SM operand fabric, not by the tensor pipe: ncu (profiles/r1_sym8_metrics.json) tensor pipe active 42 %, "
-                  "2.54 GB of operands per launch = 7.4-8.5 TB/s, DRAM 42 MB; the symmetric formulation halves both the flops "
-                  "and the operand bytes of the plain pair kernel (0.37 -> 0.30 ms per launch)")
-    else:  # dense regime: the three-product kernels dominate
-        k_ms = float(sum(ms[0][i] for i in (0, 1, 2, 3, 4, 5))) / args.steps
-        k_tf = (blocks[0] + 3.0 * (ms[1][0] * ((P + 127) // 128) * ((2 * M_CH + 255) // 256) * ((2 * N_PHI + 63) // 64)
-                                   + ms[1][1] * ((P + 127) // 128) * ((2 * N_PHI + 255) // 256) * ((2 * M_CH + 63) // 64))
-                / args.steps) * block_flops / (k_ms * 1e-3) / 1e12
-        k_peak, k_src = peak, "MEASURED_PEAKS.json bf16_tflops_sustained (%s)" % peaks["source"]
-        k_name = "dft_gemm_kernel (three fp16 products per algorithmic product)"
-        k_note = "achieved = fp16 flops issued / CUDA-event time"
-    adj_ms = float(ms[0][5] + ms[0][8] + ms[0][9])
-    roofline = {"bound": "tensor", "kernel": k_name, "achieved": k_tf, "peak": k_peak, "unit": "TFLOP/s",
-                "frac": k_tf / k_peak if k_peak else None, "traffic": ncu_traffic(P), "peak_source": k_src, "note": k_note,
-                "kernel_share_of_step": per_kind[dominant]["share_of_step"] if dominant else None,
-                "path": {"what": "all transform GEMM launches of the step: algorithmic 8 m n flops per line of sight per "
-                                 "transform / their summed CUDA-event time. Exact sparsity shortcuts (forward K-block "
-                                 "skipping, mirror-symmetric fp8 -> fp16 safe screening of the adjoint; bit-identical results, "
-                                 "tests/test_gpu_parity.py::test_sparsity_shortcuts_are_bit_exact) let this exceed the "
-                                 "dense bound of 1/3 of the tensor peak",
-                         "algorithmic_tflops": path_ach, "frac_of_bf16_peak": path_ach / peak,
-                         "gemm_share_of_step": gemm_ms / elapsed_ms if elapsed_ms > 0 else None,
-                         "adjoint_transform_ms": adj_ms / ms[1][5] if ms[1][5] else None,
-                         "executed_blocks_per_step": {"three_product": blocks[0], "fp16_screen": blocks[1], "fp8_screen": blocks[2]}},
-                "second_kernel": second, "dense": dense, "per_kind": per_kind}
+    head = args.workload
+    rec, parity, extra = run_workload(ctx, head, args, args.steps, args.warmup, peaks, True)
+    parities = {head: parity}
+    configs = {}
+    for name in [n for n in args.also.split(",") if n and n != head]:
+        sub_steps = max(1, min(args.steps, args.sub_steps))
+        sub, par, _ = run_workload(ctx, name, args, sub_steps, max(3, min(args.warmup, 3)), peaks, False)
+        configs[name] = sub
+        parities[name] = par
 
-    if rank == 0:
+    if ctx.rank == 0:
         cpu = None
-        if world == 1 and not args.no_cpu:
-            cores = os.cpu_count() or 1
-            v, wall, text = cpu_sample(args.cpu_iters, K, cores)
-            cpu = {"value": v, "unit": "LOS/s", "cores": cores, "kind": "port", "sample": text, "wall_s": wall}
-        line = {
-            "metric": "lines-of-sight/sec (fixed-iter FISTA)", "value": value, "unit": "LOS/s", "n_gpus": world,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 (split-fp16 tensor-core "
-            "products, fp32 accumulate)", "data": "synthetic", "config": workload_config(args),
-            "e2e": {"value": e2e_value, "unit": "LOS/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "steps": e2e_steps},
-            "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "clocks": sampler.summary(),
-            "algorithmic_tflops": value * 8.0 * M_CH * N_PHI * (2 * K + 2) / 1e12,
-            "finite": finite, "convergence_norm": conv_norm, "final_cost_mean": float(np.mean(np.asarray(cost))),
-        }
+        if ctx.world == 1 and not args.no_cpu:
+            cpu = cpu_sample(args.cpu_iters, args.iters, os.cpu_count() or 1, WORKLOADS[head])
+        line = dict(rec)
+        line.update({"higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                     "dtype": "f32 (split-fp16 tensor-core products, fp32 accumulate)", "data": "synthetic",
+                     "e2e": extra.get("e2e"), "cpu_baseline": cpu, "peaks": peaks, "configs": configs,
+                     "parity": parities, "final_cost_mean": extra.get("final_cost_mean"),
+                     "finite": all(p["finite"] for p in parities.values() if p)})
         print(json.dumps(line))
-    if world > 1:
+    if ctx.world > 1:
         dist.destroy_process_group()
+    bad = [k for k, p in parities.items() if p and not p["ok"]]
+    if bad:
+        print("PARITY FAILED at bench scale: %s" % bad, file=sys.stderr)
+        sys.exit(3)
 
 
 def main():
@@ -519,17 +798,18 @@ def main():
     ap.add_argument("--steps", type=int, default=4)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS), help="c3 = the driver's line (default)")
-    ap.add_argument("--slab", type=int, default=None, help="lines of sight per step per GPU (c3: 16384, c4: 8192)")
+    ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS), help="the headline workload (default c3)")
+    ap.add_argument("--also", default="c4,c5", help="workloads reported as sub-records under `configs` ('' = none)")
+    ap.add_argument("--sub-steps", type=int, default=3, help="timed steps of each sub-record workload")
+    ap.add_argument("--slab", type=int, default=None, help="lines of sight per step per GPU of the headline workload")
     ap.add_argument("--iters", type=int, default=100, help="FISTA iterations (fixed)")
     ap.add_argument("--cpu-iters", type=int, default=4, help="FISTA iterations in the bounded CPU sample")
     ap.add_argument("--e2e-steps", type=int, default=4)
+    ap.add_argument("--parity-los", type=int, default=8, help="lines of sight of the bench slab checked against the oracle")
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--no-dense", action="store_true", help="skip the dense reference leg of the roofline")
+    ap.add_argument("--no-parity", action="store_true", help="skip the in-run parity block (profiling runs)")
+    ap.add_argument("--no-peaks", action="store_true", help="skip the in-run tensor-peak measurement (profiling runs)")
     args = ap.parse_args()
-    set_workload(args.workload)
-    if args.slab is None:
-        args.slab = WORKLOADS[args.workload]["slab"]
     if args.impl == "reference":
         run_reference_arm(args)
     else:

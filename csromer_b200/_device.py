@@ -204,7 +204,7 @@ class DevicePlan:
         if want_delta:
             out["delta"] = torch.zeros((P,), dtype=torch.float32, device=dev)
         if want_mma_blocks:
-            out["mma_blocks"] = torch.zeros((4,), dtype=torch.int64, device=dev)
+            out["mma_blocks"] = torch.zeros((12,), dtype=torch.int64, device=dev)
         whandle = wavelet.handle if wavelet is not None else None
         need = self.lib.csr_fista_ws_bytes(self.handle, whandle, P)
         ws = self.ws.get(need, dev)

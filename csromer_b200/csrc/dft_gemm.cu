@@ -640,9 +640,8 @@ dft_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
                 }
                 chunk = __shfl_sync(0xffffffffu, chunk, 0);
             }
-            // slot 0: three-product launches, 1: fp16 screening, 2: fp8 screening
-            if (lane == 0 && epi.mma_count != nullptr && issued != 0)
-                atomicAdd(epi.mma_count + ((MODE == EPI_SCREEN || MODE == EPI_PLAIN1) ? 1 : (MODE == EPI_SCREEN8 ? 2 : 0)), issued);
+            // one counter per profile kind (csr_profile_collect's numbering), set by the launcher
+            if (lane == 0 && epi.mma_count != nullptr && issued != 0) atomicAdd(epi.mma_count + epi.count_slot, issued);
         }
       }
     } else {
@@ -1102,7 +1101,7 @@ screen8_pair_kernel(const __grid_constant__ CUtensorMap map_a8, const __grid_con
                 umma_commit_pair(&tmem_full[buf]);
                 ++use;
             }
-            if (epi.mma_count != nullptr && issued != 0) atomicAdd(epi.mma_count + (F16 ? 1 : 2), issued);
+            if (epi.mma_count != nullptr && issued != 0) atomicAdd(epi.mma_count + epi.count_slot, issued);
         }
       }
     } else {
@@ -1336,7 +1335,7 @@ static int make_prefetch_map(CUtensorMap* map, const void* base, int rows, int c
 
 template <int MODE>
 static int launch_mode(const csr_plan* plan, bool adjoint, const CUtensorMap& a_hi, const CUtensorMap& a_lo, int P,
-                       const GemmEpilogue& epi, cudaStream_t stream) {
+                       const GemmEpilogue& epi_in, cudaStream_t stream) {
     static bool configured = false;
     if (!configured) {
         CSR_CUDA(cudaFuncSetAttribute(dft_gemm_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
@@ -1353,21 +1352,23 @@ static int launch_mode(const csr_plan* plan, bool adjoint, const CUtensorMap& a_
     int num_prefetch = 0;
     static const bool use_prefetch = getenv("CSR_PREFETCH") != nullptr;  // measured: no gain on B200, off by default
     static const int prefetch_lead = getenv("CSR_PREFETCH_LEAD") ? atoi(getenv("CSR_PREFETCH_LEAD")) : 8;
-    if (use_prefetch && (reinterpret_cast<uintptr_t>(MODE == EPI_FISTA ? (const void*)epi.z : (const void*)epi.b) & 15) == 0) {
+    if (use_prefetch && (reinterpret_cast<uintptr_t>(MODE == EPI_FISTA ? (const void*)epi_in.z : (const void*)epi_in.b) & 15) == 0) {
         int rc = CSR_OK;
         if (MODE == EPI_FISTA) {
-            rc = make_prefetch_map(&pf0, epi.z, P, N, epi.ld_out);
-            if (!rc) rc = make_prefetch_map(&pf1, epi.x, P, N, epi.ld_out);
+            rc = make_prefetch_map(&pf0, epi_in.z, P, N, epi_in.ld_out);
+            if (!rc) rc = make_prefetch_map(&pf1, epi_in.x, P, N, epi_in.ld_out);
             num_prefetch = 2;
         } else if (MODE == EPI_RESID) {
-            rc = make_prefetch_map(&pf0, epi.b, P, N, epi.ld_out);
+            rc = make_prefetch_map(&pf0, epi_in.b, P, N, epi_in.ld_out);
             num_prefetch = 1;
         }
         if (rc) return rc;
     }
     ProfiledLaunch rec;
+    rec.kind = MODE == EPI_SCREEN ? 8 : (MODE == EPI_SCREEN8 ? 9 : (MODE == EPI_PLAIN1 ? 10 : MODE * 2 + (adjoint ? 1 : 0)));
+    GemmEpilogue epi = epi_in;
+    epi.count_slot = rec.kind;
     if (g_profile) {
-        rec.kind = MODE == EPI_SCREEN ? 8 : (MODE == EPI_SCREEN8 ? 9 : (MODE == EPI_PLAIN1 ? 10 : MODE * 2 + (adjoint ? 1 : 0)));
         CSR_CUDA(pooled_event(&rec.start));
         CSR_CUDA(pooled_event(&rec.stop));
         CSR_CUDA(cudaEventRecord(rec.start, stream));
@@ -1528,8 +1529,10 @@ int launch_split_tile_lists(const unsigned char* need, const unsigned char* excl
 }
 
 template <int PMODE>
-static int launch_pair_kernel(const csr_plan* plan, const CUtensorMap& ma, const CUtensorMap& mb, int P, const GemmEpilogue& epi,
+static int launch_pair_kernel(const csr_plan* plan, const CUtensorMap& ma, const CUtensorMap& mb, int P, const GemmEpilogue& epi_in,
                               cudaStream_t stream) {
+    GemmEpilogue epi = epi_in;
+    epi.count_slot = (PMODE == 1 || PMODE == 5) ? 10 : ((PMODE == 2 || PMODE == 4) ? 8 : 9);
     const bool sym = PMODE >= 3;
     // symmetric modes: K = one half row, MT counts groups of 64 lines of sight (128 half rows), NT the tiles of 128
     // non-negative phi (256 half rows of the table) plus the tile of the one cell without a mirror

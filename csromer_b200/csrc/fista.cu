@@ -84,7 +84,7 @@ struct FistaWs {
     int* tile_list;
     int* tile_list2;
     unsigned char* r8;  // fp8 copy of the residual operand for the first screening pass
-    unsigned long long* mma_count;  // [4]: tensor-core blocks issued by the in-loop GEMMs (3-product, fp16 screen, fp8 screen)
+    unsigned long long* mma_count;  // [CSR_PROFILE_KINDS]: tensor-core blocks issued by the in-loop GEMMs, per profile kind
     unsigned char* coef_flags[2];   // wavelet bases: coefficient-state flags (ping-pong), pitch coef_flag_ld(wav)
     unsigned char* redo_flags;      // wavelet-domain screening: blocks that failed the test in the speculative pass
     unsigned char* need[2];         // adjoint tiles [MT, NT] that need the exact gradient (predicted / after the test)
@@ -115,7 +115,7 @@ static FistaWs carve_fista(const csr_plan* plan, const csr_wavelet* wav, int P, 
     f.tile_list = b.take<int>((size_t)((P + BM - 1) / BM) * ((2 * plan->n + BN - 1) / BN));
     f.tile_list2 = b.take<int>((size_t)((P + BM - 1) / BM) * ((2 * plan->n + BN - 1) / BN));
     f.r8 = b.take<unsigned char>((size_t)round_up(P, 8) * plan->ld8);
-    f.mma_count = b.take<unsigned long long>(4);
+    f.mma_count = b.take<unsigned long long>(CSR_PROFILE_KINDS);
     f.need[0] = b.take<unsigned char>(sym_scratch_bytes(plan, P));
     f.sig = f.gcoef = f.wav_ws = nullptr;
     f.coef_flags[0] = f.coef_flags[1] = f.redo_flags = f.need[1] = nullptr;
@@ -211,6 +211,7 @@ extern "C" int csr_fista(csr_plan* plan, csr_wavelet* wav, const csr_fista_args*
     float* f_dirty = a.f_dirty ? a.f_dirty : w.f_dirty;
     float* model = a.model ? a.model : w.model;
 
+    CSR_CUDA(cudaMemsetAsync(w.mma_count, 0, CSR_PROFILE_KINDS * sizeof(unsigned long long), stream));
     // 1. diagonals and the data term b = (w/(s k)) d; its scale drives every residual operand
     if ((rc = launch_prepare(plan, a, w.b, w.amask, w.fwd_chan, stream))) return rc;
     if ((rc = launch_split_rows(w.b, ld2m, P, 2 * m, nullptr, 0, m, nullptr, 0, w.r_hi, w.r_lo, ld2m, w.rscale, 0, stream)))
@@ -222,6 +223,7 @@ extern "C" int csr_fista(csr_plan* plan, csr_wavelet* wav, const csr_fista_args*
         e.mode = EPI_PLAIN;
         e.a_scale = w.rscale;
         e.out = f_dirty;
+        e.mma_count = w.mma_count;
         if ((rc = launch_dft_gemm(plan, true, w.r_hi, w.r_lo, P, e, stream))) return rc;
     }
 
@@ -258,7 +260,6 @@ extern "C" int csr_fista(csr_plan* plan, csr_wavelet* wav, const csr_fista_args*
     if (!wav && zero_skip) {
         if ((rc = launch_block_flags(w.z, ld2n, 2 * n, P, w.zero_flags, w.flag_ld, w.tile_flags, stream))) return rc;
     }
-    CSR_CUDA(cudaMemsetAsync(w.mma_count, 0, 4 * sizeof(unsigned long long), stream));
     if (use_screen8) CSR_CUDA(cudaMemsetAsync(w.r8, 0, (size_t)round_up(P, 8) * plan->ld8, stream));  // (the padding of the fp8 rows stays zero)
     if (a.delta) CSR_CUDA(cudaMemsetAsync(a.delta, 0, sizeof(float) * P, stream));
 
@@ -475,9 +476,6 @@ extern "C" int csr_fista(csr_plan* plan, csr_wavelet* wav, const csr_fista_args*
     if (a.delta && a.iters > 0) {
         if ((rc = launch_scale_vec(a.delta, P, 1.0f / (float)ncoef, stream))) return rc;
     }
-    if (a.mma_blocks) {  // executed-work accounting of the in-loop GEMMs (a measurement aid, two 64-bit counters)
-        CSR_CUDA(cudaMemcpyAsync(a.mma_blocks, w.mma_count, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToDevice, stream));
-    }
 
     // 5. final evaluate F(x): model_data, residual, chi2 and L1 values (fista.py:107; chi2.py:21-32)
     if (a.model || a.residual || a.cost) {
@@ -499,8 +497,12 @@ extern "C" int csr_fista(csr_plan* plan, csr_wavelet* wav, const csr_fista_args*
             e.a_kflags = w.tile_flags;
             e.a_kflag_ld = w.flag_ld;
         }
+        e.mma_count = w.mma_count;
         if ((rc = launch_dft_gemm(plan, false, w.z_hi, w.z_lo, P, e, stream))) return rc;
         if ((rc = launch_finalize(plan, a, model, a.residual, x, ldc, ncoef, stream))) return rc;
+    }
+    if (a.mma_blocks) {  // executed-work accounting of every GEMM launch of this call (a measurement aid)
+        CSR_CUDA(cudaMemcpyAsync(a.mma_blocks, w.mma_count, CSR_PROFILE_KINDS * sizeof(unsigned long long), cudaMemcpyDeviceToDevice, stream));
     }
     return CSR_OK;
 }

@@ -100,7 +100,8 @@ struct GemmEpilogue {
     const unsigned char* symq;      // mirror-symmetric screening: per (64-LOS group, symmetric tile) bits of the ranges with state
     unsigned char* need;            // mirror-symmetric screening: [MT, need_ld] bytes, 1 = tile must go on (zeroed by the caller)
     int need_ld;
-    unsigned long long* mma_count;  // optional: += K blocks x products issued (executed-work accounting)
+    unsigned long long* mma_count;  // optional: [CSR_PROFILE_KINDS], slot count_slot += K blocks x products issued
+    int count_slot;                 // profile kind of this launch (set by the launchers)
     int debug;                 // measurement aid (CSR_DEBUG_EPI): bit 0 skips epilogue loads, bit 1 skips stores
     int no_fast;               // 1 = keep the general residual epilogue everywhere (option resid_fast = 0; same bits)
 };

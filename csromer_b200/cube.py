@@ -61,10 +61,31 @@ def reconstruct_cube(data, nu, sigma=None, spectral_idx=None, eta=1.0, use_wavel
                 rm_restored_interpolated=np.zeros(P_total), step=None, iterations=None, phi=par.phi)
     edge_dev = None
     step_value = None
+    info["blanked_samples"] = 0
+    info["dead_pixels"] = np.zeros(P_total, dtype=bool)
     for lo in range(0, P_total, slab):
         hi = min(P_total, lo + slab)
-        ds = Dataset(nu=nu, sigma=sigma, data=np.ascontiguousarray(flat[:, lo:hi]) if isinstance(flat, np.ndarray) else flat[:, lo:hi],
-                     spectral_idx=spectral_idx)
+        block = np.ascontiguousarray(flat[:, lo:hi]) if isinstance(flat, np.ndarray) else flat[:, lo:hi]
+        ds = Dataset(nu=nu, sigma=sigma, data=block, spectral_idx=spectral_idx)
+        # Blanked samples (NaN / inf: real Q/U cubes almost always carry some).  The reference's recipe never feeds such
+        # pixels in (it selects pixels with utils.make_mask_faraday, README.md:298-307); here a non-finite SAMPLE becomes
+        # 0 with weight 0 -- a flagged channel of that pixel only -- and a pixel without a single finite sample ("dead")
+        # keeps the shared weights on all-zero data: its dirty spectrum, noise and lambda are 0, the loop freezes it
+        # (noise >= lambda, fista.py:74-77) and its output planes are written as NaN.
+        finite = torch.isfinite(block) if dv.is_torch(block) else np.isfinite(block)
+        dead = None
+        if not bool(finite.all()):
+            if dv.is_torch(block):
+                finite = finite.cpu().numpy()
+                block = torch.where(torch.as_tensor(finite, device=block.device), block, torch.zeros_like(block))
+            else:
+                block = np.where(finite, block, 0)
+            dead = ~finite.any(axis=0)
+            info["blanked_samples"] += int(finite.size - finite.sum())
+            info["dead_pixels"][lo:hi] = dead
+            w_pp = np.asarray(probe.w, dtype=np.float64)[:, None] * (finite | dead[None, :])
+            ds = Dataset(nu=nu, sigma=sigma, data=block, spectral_idx=spectral_idx)
+            ds.w = w_pp                                                              # per-pixel flags: refreshes k, theo_noise
         dft = NDFT1D(dataset=ds, parameter=par)
         nufft = NUFFT1D(dataset=ds, parameter=par, solve=True)
         plan = dft.device_plan()
@@ -73,7 +94,7 @@ def reconstruct_cube(data, nu, sigma=None, spectral_idx=None, eta=1.0, use_wavel
             edge_dev = torch.as_tensor(edge.astype(np.uint8)).to(plan.device)
         d_planar, _ = dv.pack_planar(ds.data, m, plan.ld2m, plan.device)
         w = np.asarray(ds.w)
-        chan = torch.as_tensor(w / ds.s, dtype=torch.float32).to(plan.device)
+        chan = dft._channel_tensor(w / (ds.s if w.ndim == 1 else np.asarray(ds.s)[:, None]), plan)   # [m] or [P, m]
         row = dv.per_pixel_vector(1.0 / np.asarray(ds.k), hi - lo, plan.device, "k")
         dirty = plan.adjoint(d_planar, chan, row)                                  # F_dirty = dft.backward(data)
         noise = dv.edge_noise(dirty, n, edge_dev, eta)                              # README.md:336-338
@@ -97,6 +118,8 @@ def reconstruct_cube(data, nu, sigma=None, spectral_idx=None, eta=1.0, use_wavel
         restored = dv.convolve_phi(model_planar, n, taps, add=f_resid)             # X.convolve() + F_residual
         for plane, t in enumerate((dirty, model_planar, restored, f_resid)):
             F_flat[plane, :, lo:hi] = dv.unpack_complex(t, n, (hi - lo,))
+        if dead is not None and dead.any():
+            F_flat[:, :, lo + np.nonzero(dead)[0]] = np.nan
         idx_m, _ = dv.peak_stats(model_planar, n)
         idx_r, st_r = dv.peak_stats(restored, n)
         idx_m, idx_r, st_r = idx_m.cpu().numpy(), idx_r.cpu().numpy(), st_r.cpu().numpy()
@@ -106,6 +129,6 @@ def reconstruct_cube(data, nu, sigma=None, spectral_idx=None, eta=1.0, use_wavel
         info["peak_restored"][lo:hi] = st_r[:, 2]
         info["rm_restored_interpolated"][lo:hi] = (idx_r + st_r[:, 1] - n / 2) * par.cellsize
     info["step"] = step_value
-    for key in ("noise", "lambda_l1", "rm_model", "rm_restored", "peak_restored", "rm_restored_interpolated"):
+    for key in ("noise", "lambda_l1", "rm_model", "rm_restored", "peak_restored", "rm_restored_interpolated", "dead_pixels"):
         info[key] = info[key].reshape(pix) if pix else info[key]
     return F, info

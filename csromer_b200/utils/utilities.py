@@ -30,6 +30,27 @@ def complex_to_real(z):
     return np.concatenate([z.real, z.imag], axis=0)
 
 
+def make_mask(I=None, sigma=0.0):
+    """(indices where ``I >= sigma``, indices where ``I < sigma``) as ``np.where`` tuples (utils/utilities.py:35-38)"""
+    I = np.asarray(I)
+    keep = I >= sigma
+    return np.where(keep), np.where(I < sigma)
+
+
+def make_mask_faraday(I=None, P=None, cube_Q=None, cube_U=None, spectral_idx=None, sigma_I=0.0, sigma_P=0.0):
+    """Pixels worth reconstructing: total intensity and polarised intensity above their thresholds and not a single NaN
+    along the frequency axis of Q or U (nor in the spectral-index map when one is given).  Returns ``(kept, masked)`` as
+    ``np.where`` tuples like the reference (utils/utilities.py:41-65); the cube recipe loops over ``kept``
+    (README.md:298-307)."""
+    keep = (np.asarray(I) >= sigma_I) & (np.asarray(P) >= sigma_P)
+    for cube in (cube_Q, cube_U):
+        if cube is not None:
+            keep &= ~np.isnan(np.asarray(cube)).any(axis=0)
+    if spectral_idx is not None:
+        keep &= ~np.isnan(np.asarray(spectral_idx))
+    return np.where(keep), np.where(~keep)
+
+
 def calculate_noise(image=None, x0=None, xn=None, y0=None, yn=None, nsigma=3, cenfunc="mean", stdfunc="mad_std",
                     use_sigma_clipped_stats=False):
     """Noise of an image ``(Y, X)`` or of every channel of a cube ``(m, Y, X)`` over the window ``[y0:yn, x0:xn]``:

@@ -124,10 +124,10 @@ typedef struct {
     float* cost;
     float* delta;
     int use_dirty_as_guess; /* 1: ignore x on input and start from F_dirty (README.md:186) / its coefficients */
-    unsigned long long* mma_blocks; /* optional [4] (device): tensor-core work the in-loop GEMMs issued, in units of one
-                               128 x 256 x 64 multiply-accumulate block: [0] three-product launches, [1] fp16 screening,
-                               [2] fp8 screening (an fp8 K block of 128 counts 2), [3] unused; measurement aid for the
-                               roofline (a dense run issues 3 per tile and K block of 64) */
+    unsigned long long* mma_blocks; /* optional [CSR_PROFILE_KINDS] (device): tensor-core work the in-loop GEMMs issued, in
+                               units of one 128 x 256 x 64 multiply-accumulate block, per launch kind in
+                               csr_profile_collect's numbering (three-product kinds issue 3 per tile and K block of 64
+                               when dense, an fp8 K block of 128 counts 2); the executed-work side of the roofline */
     int s_per_pixel;        /* 1: s is [P, m] (per-line-of-sight samplings, csr_fista_nu); 0: [m] */
 } csr_fista_args;
 

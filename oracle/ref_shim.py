@@ -2,8 +2,9 @@
 
 TEST INFRASTRUCTURE ONLY.  Nothing under ``csromer_b200/`` may import this file.  It exists so that
 ``oracle/make_golden.py`` can run the reference's own classes in the build container and freeze their
-outputs under ``tests/golden/``; ``/root/reference`` does not exist on the GPU box, so no test, smoke() or
-bench imports this at run time (``available()`` is False there).
+outputs under ``tests/golden/``; ``/root/reference`` does not exist on the GPU box; there the shim
+imports the byte-for-byte copy ``oracle/build_ref.py`` leaves under ``oracle/_ref/`` (git-ignored, shipped with the
+built artefacts), which is what bench.py's ``--impl reference`` arm and ``cpu_baseline`` time.
 
 Why stubs are needed: ``astropy``, ``pywt``, ``pynufft`` and ``prox_tv`` are not
 installed and there is no network.  The exact-DFT path (``Dataset``, ``Parameter``, ``NDFT1D``, ``Chi2``,
@@ -17,10 +18,20 @@ import sys
 import types
 
 REFERENCE_SRC = os.environ.get("CSROMER_REFERENCE_SRC", "/root/reference/src")
+# the byte-for-byte run-time copy oracle/build_ref.py makes (git-ignored; travels to the GPU box)
+REF_COPY = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
+
+
+def source_dir():
+    """directory that holds the reference's ``csromer`` package: the reference tree itself, else its copy"""
+    for d in (REFERENCE_SRC, REF_COPY):
+        if os.path.isdir(os.path.join(d, "csromer")):
+            return d
+    return None
 
 
 def available():
-    return os.path.isdir(os.path.join(REFERENCE_SRC, "csromer"))
+    return source_dir() is not None
 
 
 def _stub(name, **attrs):
@@ -62,7 +73,7 @@ def load():
 
     # bare package object: skips src/csromer/__init__.py (setuptools_scm version lookup)
     pkg = types.ModuleType("csromer")
-    pkg.__path__ = [os.path.join(REFERENCE_SRC, "csromer")]
+    pkg.__path__ = [os.path.join(source_dir(), "csromer")]
     sys.modules["csromer"] = pkg
     # tv.py / tsv.py use an ndarray dataclass default, which python >= 3.11 rejects (tv.py:11, tsv.py:11)
     _stub("csromer.objectivefunction.priors.tv", TV=_Anything)

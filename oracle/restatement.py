@@ -94,10 +94,14 @@ class ExactDFT:
     ``k`` may also be passed explicitly because in-place flagging leaves it stale in the reference
     (transformers/flaggers/mean_flagger.py:42)."""
 
-    def __init__(self, lambda2, phi, w=None, s=None, k=None, l2_ref=0.0, rebuild_twiddles=False):
+    def __init__(self, lambda2, phi, w=None, s=None, k=None, l2_ref=0.0, rebuild_twiddles=False, cache_adjoint=False):
         # rebuild_twiddles=True reproduces the reference's COST profile as well as its values: ndft.py:19,25,34,42
         # call np.exp on the full m x n matrix inside every transform.  Used only by bench.py's CPU baseline.
         self.rebuild_twiddles = rebuild_twiddles
+        # cache_adjoint=True also keeps conj(E).T (bench.py's in-run parity sample at the large samplings: the
+        # conjugate copy of a 2 GB matrix per call would dominate the check); values are identical
+        self.cache_adjoint = cache_adjoint and not rebuild_twiddles
+        self._Eh = None
         self.lambda2 = np.asarray(lambda2, dtype=np.float64)
         self.phi = np.asarray(phi, dtype=np.float64)
         self.m, self.n = self.lambda2.shape[0], self.phi.shape[0]
@@ -134,6 +138,10 @@ class ExactDFT:
         wt = self._col(self.w, b) / self._col(self.s, b)
         if self.rebuild_twiddles:  # the reference builds the conjugate matrix directly (ndft.py:34)
             return (np.exp(-2.0j * self.phi[:, None] * self._l2[None, :]) @ (wt * b)) / self.k
+        if self.cache_adjoint:
+            if self._Eh is None:
+                self._Eh = np.ascontiguousarray(self.E.conj().T)
+            return (self._Eh @ (wt * b)) / self.k
         return (self.E.conj().T @ (wt * b)) / self.k
 
     def rmtf(self):
@@ -267,6 +275,31 @@ def iswt(coeffs, bank, norm=False):
     return out
 
 
+def iswt_fast(coeffs, bank, norm=False):
+    """``iswt`` in closed form: pywt's average of the even- and odd-phase periodization IDWTs of one a-trous level
+    collapses to ONE gather, a'[o] = 1/2 sum_t (rec_lo[t] a[.] + rec_hi[t] d[.]) at (o + step (F/2 - 1 - t)) mod N.
+    Same values as ``iswt`` (the pywt-literal double loop; tests/test_oracle_wavelets.py holds them together) at a
+    fraction of the cost -- used where the literal form would take minutes (bench.py's in-run parity sample)."""
+    rec_lo, rec_hi = bank[2], bank[3]
+    if norm:
+        rec_lo, rec_hi = rec_lo * np.sqrt(2), rec_hi * np.sqrt(2)
+    out = np.array(coeffs[0], dtype=np.float64, copy=True)
+    L = len(coeffs) - 1
+    F = rec_lo.shape[0]
+    for j in range(L, 0, -1):
+        step = 1 << (j - 1)
+        cD = coeffs[L - j + 1]
+        acc = np.zeros_like(out)
+        for t in range(F):
+            sh = step * (F // 2 - 1 - t)
+            if rec_lo[t] != 0.0:
+                acc += rec_lo[t] * np.roll(out, -sh, axis=0)
+            if rec_hi[t] != 0.0:
+                acc += rec_hi[t] * np.roll(cD, -sh, axis=0)
+        out = 0.5 * acc
+    return out
+
+
 def _dwt_per(x, f_lo, f_hi):
     """single-level periodization DWT along axis 0; odd lengths repeat the last sample once."""
     N = x.shape[0]
@@ -312,9 +345,10 @@ class WaveletDict:
     chi2.py:44-55), coefficients flattened like pywt.ravel_coeffs, optional ``append_signal``
     (dictionaries/undecimated.py:84-85,143-169; discrete.py:42-43,71-82)."""
 
-    def __init__(self, name, kind="swt", level=None, norm=False, append_signal=False):
+    def __init__(self, name, kind="swt", level=None, norm=False, append_signal=False, fast_iswt=False):
         self.bank = filter_bank(name)
         self.kind, self.level, self.norm, self.append_signal = kind, level, norm, append_signal
+        self.fast_iswt = fast_iswt  # closed-form iswt (same values; see iswt_fast)
         self.shapes = None
         self.N = None
 
@@ -333,7 +367,10 @@ class WaveletDict:
         for ln in self.shapes:
             cs.append(c[o:o + ln])
             o += ln
-        out = iswt(cs, self.bank, self.norm) if self.kind == "swt" else waverec_per(cs, self.bank)
+        if self.kind == "swt":
+            out = iswt_fast(cs, self.bank, self.norm) if self.fast_iswt else iswt(cs, self.bank, self.norm)
+        else:
+            out = waverec_per(cs, self.bank)
         return sig + out if sig is not None else out
 
 

@@ -785,6 +785,56 @@ def test_cube_recipe_matches_oracle(use_wavelet):
     assert info["iterations"] == int(np.floor(np.sqrt(400 + np.sqrt(800))))
 
 
+def test_cube_recipe_with_blanked_samples():
+    """a NaN-blanked pixel must not poison its slab.  One dead pixel (all NaN), one pixel with a few blanked
+    channels, one with an inf: the dead pixel comes back as NaN planes, the partly blanked ones as the reconstruction
+    with those channels flagged (w = 0) -- checked against the oracle run with those weights -- and every other
+    pixel stays within tolerance of the clean run."""
+    from csromer_b200.cube import reconstruct_cube
+    rng = np.random.RandomState(78)
+    nu = np.linspace(1.008e9, 2.031e9, 200)
+    Y, X = 2, 4
+    src = cs.FaradayThinSource(nu=nu, s_nu=0.0035 * rng.uniform(0.5, 1.5, size=(Y, X)),
+                               phi_gal=rng.uniform(-300, 300, size=(Y, X)), spectral_idx=0.0)
+    src.simulate()
+    src.apply_noise(0.2 * 0.0035, random_state=rng)
+    clean = np.asarray(src.data).astype(np.complex128)
+    sigma = np.full(200, 0.2 * 0.0035)
+    cube = clean.copy()
+    cube[:, 0, 1] = np.nan                      # dead pixel
+    cube[[5, 17, 18, 150], 1, 2] = np.nan       # four blanked channels
+    cube[60, 0, 3] = np.inf                     # one inf
+    F0, info0 = reconstruct_cube(clean, nu, sigma=sigma, use_wavelet=False, slab=8)
+    F, info = reconstruct_cube(cube, nu, sigma=sigma, use_wavelet=False, slab=8, step=info0["step"])
+    assert info["blanked_samples"] == 200 + 4 + 1 and info["dead_pixels"].sum() == 1 and info["dead_pixels"][0, 1]
+    assert np.isnan(F[:, :, 0, 1]).all()
+    good = np.ones((Y, X), dtype=bool)
+    good[0, 1] = False
+    assert np.isfinite(F[:, :, good]).all()
+    untouched = good.copy()
+    untouched[1, 2] = untouched[0, 3] = False
+    assert rel(F[:, :, untouched], F0[:, :, untouched]) < TOL_MODEL
+    # the partly blanked pixel against the oracle with those channels at weight 0 (same phi grid as the cube run)
+    l2 = ob.lambda2_from_nu(nu)
+    order = np.argsort(-nu)                     # lambda2 is stored ascending; data stays in caller order (SURVEY 7.4)
+    sc = ob.dataset_scalars(l2, sigma, 0.0)
+    wp = sc["w"].copy()
+    d = cube[:, 1, 2].copy()
+    bad = ~np.isfinite(d)
+    d[bad] = 0.0
+    wp[bad] = 0.0
+    op = ob.ExactDFT(l2, info["phi"], wp, sc["s"])
+    dirty = op.backward(d)
+    assert rel(F[0, :, 1, 2], dirty) < TOL_TRANSFORM
+    grid = ob.phi_grid(l2, sc["w"], 8.0)
+    noise = ob.edge_noise(dirty, info["phi"], grid["max_faraday_depth"], 1.0)
+    assert info["noise"][1, 2] == pytest.approx(noise, rel=1e-4)
+    lam = np.sqrt(2 * 200 + np.sqrt(4 * 200)) * noise
+    r = ob.fista(op, d, ob.complex_to_real(dirty), lam, noise, None, step=info0["step"])
+    assert rel(F[1, :, 1, 2], ob.real_to_complex(r["x"])) < TOL_MODEL
+    del order
+
+
 def test_config1_reference_default_schedule_known_answers():
     """BASELINE configs[0] with the reference's DEFAULT schedule (README.md:157-210): lambda from the sigma heuristic,
     noise = theo_noise, 1458 iterations.  The numbers below were produced by the reference's own classes

@@ -236,3 +236,22 @@ def test_dataset_stack_presents_ragged_datasets_as_one_batch():
         DatasetStack([])
     with pytest.raises(ValueError):
         DatasetStack([cs.Dataset(nu=nu, sigma=np.ones(40), data=np.zeros((40, 2), np.complex64))])
+
+
+def test_make_mask_helpers_follow_the_reference():
+    """utils/utilities.py:35-65 of the reference: np.where tuples of kept / masked pixels"""
+    from csromer_b200.utils import make_mask, make_mask_faraday
+    rng = np.random.RandomState(3)
+    I, P = rng.uniform(0, 1, (5, 6)), rng.uniform(0, 1, (5, 6))
+    Q, U = rng.normal(size=(7, 5, 6)), rng.normal(size=(7, 5, 6))
+    Q[3, 1, 2] = np.nan
+    U[0, 4, 5] = np.nan
+    alpha = rng.normal(size=(5, 6))
+    alpha[2, 2] = np.nan
+    kept, masked = make_mask(I, 0.4)
+    assert set(zip(*kept)) == set(zip(*np.where(I >= 0.4))) and len(kept[0]) + len(masked[0]) == I.size
+    kept, masked = make_mask_faraday(I, P, Q, U, None, 0.3, 0.2)
+    expect = (I >= 0.3) & (P >= 0.2) & ~np.isnan(Q).any(axis=0) & ~np.isnan(U).any(axis=0)
+    assert set(zip(*kept)) == set(zip(*np.where(expect))) and (1, 2) not in set(zip(*kept)) and (4, 5) in set(zip(*masked))
+    kept2, _ = make_mask_faraday(I, P, Q, U, alpha, 0.3, 0.2)
+    assert set(zip(*kept2)) == set(zip(*np.where(expect & ~np.isnan(alpha))))

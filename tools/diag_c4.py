@@ -37,6 +37,7 @@ for name in ("c4", "no_flags", "const_sigma"):
         nz = lam / 200.0
         out = plan.fista(data0.clone(), w, s, k, x, lam, nz, K, use_dirty_as_guess=True, want_mma_blocks=True)
         b = out["mma_blocks"].double().cpu().numpy()
+        b = np.array([b[[0, 1, 2, 5]].sum(), b[8] + b[10], b[9], 0.0])  # three-product, fp16 one-product, fp8
         print(name, "K=%3d" % K, "blocks 3prod %.3g fp16 %.3g fp8 %.3g | last-range per-iter: 3prod %.3g fp16 %.3g fp8 %.3g" % (
             b[0], b[1], b[2], *(b[:3] - prev[:3])), "nnz", int((x != 0).sum()) // P)
         prev = b

@@ -30,5 +30,6 @@ for sym in (1, 0):
         nz = torch.full((P,), lam0 / (2 * K), dtype=torch.float32, device=dev)
         out = plan.fista(data, w, s, k, x, lam, nz, kk, use_dirty_as_guess=True, want_mma_blocks=True)
         b = out["mma_blocks"].double().cpu().numpy()
+        b = np.array([b[[0, 1, 2, 5]].sum(), b[8] + b[10], b[9], 0.0])  # three-product, fp16 one-product, fp8
         print("sym=%d K=%3d per-iteration in the last range: 3prod %.3g fp16 %.3g fp8 %.3g" % (sym, kk, *((b[:3] - prev[:3]) / (kk - (0 if prev[0] == 0 else kprev)))))
         prev, kprev = b, kk
