@@ -67,7 +67,7 @@ WORKLOADS = {
 }
 KIND_NAMES = ["plain_forward", "plain_adjoint", "resid_forward", "resid_adjoint", "fista_forward", "fista_adjoint",
               "swt_synth_fused", "swt_analysis_update_fused", "screen_adjoint_fp16", "screen_adjoint_fp8",
-              "plain_adjoint_one_product", "swt_analysis_update_redo"]
+              "plain_adjoint_one_product", "swt_analysis_update_redo", "tile_selection_and_lists", "row_update", "kind14", "kind15"]
 KERNEL_OF_KIND = {
     0: "dft_gemm_kernel<EPI_PLAIN> forward (three fp16 products, tcgen05 kind::f16)",
     1: "dft_gemm_kernel<EPI_PLAIN> adjoint (three fp16 products)",
@@ -79,6 +79,8 @@ KERNEL_OF_KIND = {
     9: "screen8_pair_kernel<3>: mirror-symmetric fp8 (e4m3) screening of the adjoint on CTA pairs (cta_group::2, kind::f8f6f4)",
     10: "screen8_pair_kernel<5>: one-product fp16 plain adjoint, mirror-symmetric, on CTA pairs (wavelet-domain screening)",
     11: "swt_analysis_fused4_kernel<UPDATE>, redo pass on the blocks that failed the bound",
+    12: "sym_select_kernel / split_tile_lists_kernel (+ their memsets): which tiles the screening and the exact kernels process",
+    13: "row_update_kernel: row clocks of the incremental screening, operand scales",
 }
 BLOCK_FLOPS = 2.0 * 128 * 256 * 64      # one counted tensor-core block
 
@@ -450,7 +452,7 @@ class Workload:
 # ---------------------------------------------------------------------------------------------------------
 def collect_profile(lib):
     from csromer_b200 import _lib
-    ms, cnt = np.zeros(12, dtype=np.float64), np.zeros(12, dtype=np.int64)
+    ms, cnt = np.zeros(16, dtype=np.float64), np.zeros(16, dtype=np.int64)
     lib.csr_profile(0)
     _lib.check(lib.csr_profile_collect(ms.ctypes.data_as(ctypes.POINTER(ctypes.c_double)),
                                        cnt.ctypes.data_as(ctypes.POINTER(ctypes.c_longlong))), "csr_profile_collect")
@@ -501,7 +503,7 @@ def kernel_table(w, res, steps, peaks):
     traffic = ncu_capture(w.name) if P == w.wl["slab"] else {}
     table = {}
     C = w.engine.ncoef if w.engine is not None else 0
-    for kind in range(12):
+    for kind in range(16):
         if cnt[kind] == 0:
             continue
         avg_ms = float(ms[kind] / cnt[kind])

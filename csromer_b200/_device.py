@@ -204,14 +204,21 @@ class DevicePlan:
         if want_delta:
             out["delta"] = torch.zeros((P,), dtype=torch.float32, device=dev)
         if want_mma_blocks:
-            out["mma_blocks"] = torch.zeros((12,), dtype=torch.int64, device=dev)
+            out["mma_blocks"] = torch.zeros((16,), dtype=torch.int64, device=dev)
         whandle = wavelet.handle if wavelet is not None else None
         need = self.lib.csr_fista_ws_bytes(self.handle, whandle, P)
         ws = self.ws.get(need, dev)
         a = _lib.FistaArgs()
         a.mma_blocks = out["mma_blocks"].data_ptr() if want_mma_blocks else None
         a.P, a.iters, a.step, a.norm_factor = P, int(iters), float(step), float(norm_factor)
+        if s.dim() == 2 and w.dim() == 1:       # per-pixel spectral factors need the per-pixel channel diagonals
+            w = w[None, :].expand(P, self.m).contiguous()
         a.w_per_pixel = int(w.dim() == 2)
+        a.s_per_pixel = int(s.dim() == 2)       # per-pixel spectral factors [P, m] (prepare_kernel reads the row of p)
+        for name, t, pp in (("w", w, a.w_per_pixel), ("s", s, a.s_per_pixel)):
+            want = (P, self.m) if pp else (self.m,)
+            if tuple(t.shape) != want:
+                raise ValueError("%s has shape %s, expected %s" % (name, tuple(t.shape), want))
         a.data, a.w, a.s, a.k = data.data_ptr(), w.data_ptr(), s.data_ptr(), k.data_ptr()
         a.x, a.ldx = x.data_ptr(), x.shape[1]
         a.lambda0, a.noise = lambda0.data_ptr(), noise.data_ptr()

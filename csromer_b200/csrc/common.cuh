@@ -293,6 +293,8 @@ struct Options {
     int sym;  // mirror-symmetric screening (phi_j = -phi_{n-j}): half the K for the same decisions
     int screen16_pair;  // per-pixel weights: one fp16 screening pass on CTA pairs instead of the fp8 -> fp16 cascade
     int wavelet_screen;  // wavelet bases: one-product gradient + rigorous bound away from the active coefficients
+    int screen_incr;  // incremental safe screening: a screened tile is re-screened only when its margin is used up
+    int rescale;      // operand scales of z and r follow the row maxima (fp16 headroom in diverging runs)
 };
 Options& options();
 

@@ -204,6 +204,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmEpilogue& epi, const flo
             if (MODE != EPI_FISTA && epi.chan_scale) cs_row = epi.chan_scale + (epi.chan_per_pixel ? (size_t)row * epi.m : 0);
             const bool cs_even = (epi.m & 1) == 0 && (reinterpret_cast<uintptr_t>(epi.chan_scale) & 7) == 0;
             float dsum = 0.f;
+            float st_dz = 0.f, st_zabs = 0.f, st_max = 0.f;  // row statistics (GemmEpilogue::row_stat)
             // Sparsity shortcut (exact): FISTA's soft threshold leaves most of phi space identically zero.  A byte per
             // (row, 128-column block) records "x and z are all zero here"; such a block needs no loads, and if its new
             // values are zero again it needs no stores either.
@@ -260,6 +261,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmEpilogue& epi, const flo
                         *reinterpret_cast<__half2*>(epi.out_hi + row_off + col) = h;
                         *reinterpret_cast<__half2*>(epi.out_lo + row_off + col) = l;
                         dsum += fabsf(hf.x) + fabsf(hf.y);  // S_p of the screening bound
+                        st_max = fmaxf(st_max, fmaxf(fabsf(r0), fabsf(r1)));
                         if (epi.out8 != nullptr) {
                             const float2 v8 = make_float2(hf.x * kOperandScale8, hf.y * kOperandScale8);
                             if (fmaxf(fabsf(v8.x), fabsf(v8.y)) > 448.f) dsum = __int_as_float(0x7f800000);  // unscreenable row
@@ -280,6 +282,9 @@ __device__ __forceinline__ void epilogue_tile(const GemmEpilogue& epi, const flo
                         const float x1 = copysignf(fmaxf(fabsf(u1) - thr, 0.f), u1);
                         const float z0 = x0 + epi.beta * (x0 - in1[jj].x), z1 = x1 + epi.beta * (x1 - in1[jj].y);
                         dsum += fabsf(x0 - in1[jj].x) + fabsf(x1 - in1[jj].y);
+                        st_dz += fabsf(z0 - in0[jj].x) + fabsf(z1 - in0[jj].y);
+                        st_zabs += fabsf(z0) + fabsf(z1);
+                        st_max = fmaxf(st_max, fmaxf(fabsf(z0), fabsf(z1)));
                         in1[jj] = make_float2(x0, x1);  // keep the results; whether they are stored is decided below
                         in0[jj] = make_float2(z0, z1);
                         nonzero |= (x0 != 0.f) | (x1 != 0.f) | (z0 != 0.f) | (z1 != 0.f);
@@ -317,6 +322,26 @@ __device__ __forceinline__ void epilogue_tile(const GemmEpilogue& epi, const flo
                 dsum += __shfl_xor_sync(0xffffffffu, dsum, 2);
                 if (quad == 0 && row_ok && dsum != 0.f) atomicAdd(epi.abs_sum_out + row, dsum);
             }
+            if ((MODE == EPI_FISTA || MODE == EPI_RESID) && epi.row_stat != nullptr) {  // kernel-uniform branch
+                st_max = fmaxf(st_max, __shfl_xor_sync(0xffffffffu, st_max, 1));
+                st_max = fmaxf(st_max, __shfl_xor_sync(0xffffffffu, st_max, 2));
+                if (MODE == EPI_FISTA) {
+                    st_dz += __shfl_xor_sync(0xffffffffu, st_dz, 1);
+                    st_dz += __shfl_xor_sync(0xffffffffu, st_dz, 2);
+                    st_zabs += __shfl_xor_sync(0xffffffffu, st_zabs, 1);
+                    st_zabs += __shfl_xor_sync(0xffffffffu, st_zabs, 2);
+                }
+                if (quad == 0 && row_ok) {  // (|.| >= 0 or NaN: as unsigned bit patterns they order like the floats, NaN on top)
+                    float* rs = epi.row_stat + 4 * (size_t)row;
+                    if (MODE == EPI_FISTA) {
+                        if (st_dz != 0.f) atomicAdd(rs, st_dz);
+                        if (st_zabs != 0.f) atomicAdd(rs + 1, st_zabs);
+                        if (st_max != 0.f) atomicMax(reinterpret_cast<unsigned int*>(rs + 2), __float_as_uint(st_max));
+                    } else if (st_max != 0.f) {
+                        atomicMax(reinterpret_cast<unsigned int*>(rs + 3), __float_as_uint(st_max));
+                    }
+                }
+            }
         }
     }
     if (MODE == EPI_FISTA && epi.tile_flags != nullptr && epi.zero_flags != nullptr && col0 < epi.N) {  // warp-uniform
@@ -343,7 +368,7 @@ __device__ __forceinline__ void epilogue_resid_fast(const GemmEpilogue& epi, con
         for (int rh = 0; rh < 2; ++rh) {
             const int row = row0 + (lane >> 2) + 8 * rh + 16 * lh;
             const bool row_ok = row < epi.P;
-            float dsum = 0.f;
+            float dsum = 0.f, rmax = 0.f;
             if (row_ok) {
                 const float descale = kTwiddleDescale / __ldg(epi.a_scale + row);
                 const float oscale = __ldg(epi.out_scale + row);
@@ -372,6 +397,7 @@ __device__ __forceinline__ void epilogue_resid_fast(const GemmEpilogue& epi, con
                     hp[4 * jj] = h;
                     lp[4 * jj] = l;
                     dsum += fabsf(hf.x) + fabsf(hf.y);
+                    rmax = fmaxf(rmax, fmaxf(fabsf(r0), fabsf(r1)));
                     if (p8 != nullptr) {  // kernel-uniform
                         const float2 v8 = make_float2(hf.x * kOperandScale8, hf.y * kOperandScale8);
                         if (fmaxf(fabsf(v8.x), fabsf(v8.y)) > 448.f) dsum = __int_as_float(0x7f800000);  // unscreenable row
@@ -383,6 +409,12 @@ __device__ __forceinline__ void epilogue_resid_fast(const GemmEpilogue& epi, con
                 dsum += __shfl_xor_sync(0xffffffffu, dsum, 1);
                 dsum += __shfl_xor_sync(0xffffffffu, dsum, 2);
                 if (quad == 0 && row_ok && dsum != 0.f) atomicAdd(epi.abs_sum_out + row, dsum);
+            }
+            if (epi.row_stat != nullptr) {  // kernel-uniform
+                rmax = fmaxf(rmax, __shfl_xor_sync(0xffffffffu, rmax, 1));
+                rmax = fmaxf(rmax, __shfl_xor_sync(0xffffffffu, rmax, 2));
+                if (quad == 0 && row_ok && rmax != 0.f)
+                    atomicMax(reinterpret_cast<unsigned int*>(epi.row_stat + 4 * (size_t)row + 3), __float_as_uint(rmax));
             }
         }
     }
@@ -827,9 +859,25 @@ __device__ __forceinline__ int screen_tile_fails_sym(const GemmEpilogue& epi, co
 // The same test when the A tile was loaded through the 4-D map (GemmEpilogue::sym_rows8): rows 16 G + 8 h + l of the tile
 // are row h (alpha / beta) of line of sight 8 G + l, so a thread's rows rh = 0 / 1 are the alpha and the beta row of ONE
 // line of sight and no exchange is needed.  row0: first row of the warp (a multiple of 32).
+// Incremental screening (exact).  A tile that passes has a MARGIN per row: (lim - max |g1|) in real units of the gradient.
+// Between two tests the gradient of row p at a phi cell that lies D cells away from every cell whose state changed moves
+// by at most  coef(D) ||path of z_p||_1:  delta g = (nf / n) sum_{i live} exp(-2i (l2_i - l2_ref) d) delta z  cell by cell,
+// i.e. |delta g| <= coef(D) |delta z| with coef(D) = (|nf| / n) (m_base env[D] + dead_p), env the suffix maximum of the
+// normalised |RMTF| of the base channel set (far from a source ~0.03 instead of the trivial 1) and dead_p the channels
+// pixel p flags on top of it.  lambda decays by noise_p per iteration, and the rounding of both evaluations is covered
+// by an allowance R_p (forward GEMM error <= 2^-12 ||z||_1 per output, operand storage 2^-19 ||r||_1), kept as a running
+// maximum rhat_p.  row_update_kernel maintains per row the path length L_p, the additive clock Q_p = it noise_p + rhat_p
+// and the union [lo_p, hi_p] of the phi cells that held state since iteration 1.  The test below records per (tile, row)
+//     X = 0.999 margin - 2 rhat_p + Q_p,   L0 = L_p        (as of the test)
+// and the tile stays provably zero -- neither screened nor listed -- while for all its rows
+//     X - Q_p(now) > coef(D(tile, [lo_p, hi_p] now)) (L_p(now) - L0)          (sym_quiet_kernel).
+// [margin(it0) > coef dL + (it - it0) noise + R(it) + R(it0) follows: Q(now) - Q(it0) + 2 rhat(it0) >= the last three
+// terms; the union of extents only grows, so D(now) <= every earlier distance and env is non-increasing.]  A row that
+// fails or has no positive margin records X = 0: screened again next iteration.  Inactive rows and rows beyond P put no
+// constraint (+inf from the initialisation).  exp_tile: the 64 entries of this (group, symmetric tile), or null.
 template <bool F8>
 __device__ __forceinline__ int screen_tile_fails_sym8(const GemmEpilogue& epi, const float (&acc)[EPI_COLS], int lane, int row0,
-                                                      int col0, int ncols, int Khalf, int jw) {
+                                                      int col0, int ncols, int Khalf, int jw, float2* exp_tile) {
     const int quad = lane & 3;
     const int nphi = epi.N >> 1;
     int fail = 0;
@@ -839,6 +887,7 @@ __device__ __forceinline__ int screen_tile_fails_sym8(const GemmEpilogue& epi, c
         const bool row_ok = p < epi.P;
         float lim = 0.f;
         bool active = false;
+        unsigned int exp_bits = 0x7f800000u;  // this thread's bound on the row's expiry (+inf = no constraint)
         if (row_ok) {
             const float l0 = __ldg(epi.lambda0 + p), nz = __ldg(epi.noise + p);
             const float lam = l0 - (float)epi.iter * nz;
@@ -857,9 +906,23 @@ __device__ __forceinline__ int screen_tile_fails_sym8(const GemmEpilogue& epi, c
                 mim = max(mim, __float_as_uint(fabsf(acc[ab]) + fabsf(acc[aa + 1])));      // |C_beta| + |S_alpha|
             }
         }
-        if (!(row_ok && active)) continue;
         const bool limok = lim > 0.f;
-        if (limok && __uint_as_float(mre) < lim && __uint_as_float(mim) < lim) continue;
+        const bool pass = !(row_ok && active) || (limok && __uint_as_float(mre) < lim && __uint_as_float(mim) < lim);
+        if (exp_tile != nullptr) {  // kernel-uniform; the four lanes of a row agree on one value, one of them records it
+            if (row_ok && active) {
+                exp_bits = 0u;
+                if (pass) {
+                    const float unit = F8 ? 1.f / (__ldg(epi.a_scale + p) * (kTwiddleScale8 * kOperandScale8))
+                                          : kTwiddleDescale / __ldg(epi.a_scale + p);
+                    const float margin = (lim - fmaxf(__uint_as_float(mre), __uint_as_float(mim))) * unit * 0.999f;
+                    exp_bits = __float_as_uint(fmaxf(margin - 2.f * __ldg(epi.rhat + p) + __ldg(epi.qclock + p), 0.f));
+                }
+            }
+            exp_bits = min(exp_bits, __shfl_xor_sync(0xffffffffu, exp_bits, 1));
+            exp_bits = min(exp_bits, __shfl_xor_sync(0xffffffffu, exp_bits, 2));
+            if (quad == 0 && exp_bits != 0x7f800000u) atomicMin(reinterpret_cast<unsigned int*>(exp_tile + (p & 63)), exp_bits);
+        }
+        if (pass) continue;
         // slow path (tiles near the sources): which original tiles do the failing columns belong to?
 #pragma unroll
         for (int part = 0; part < 2; ++part) {
@@ -920,26 +983,85 @@ __device__ __forceinline__ void epilogue_plain_sym8(const GemmEpilogue& epi, con
     }
 }
 
-// per (group of 64 lines of sight, symmetric column tile): 1 = some original tile this symmetric tile overlaps is quiet
-// (its state is identically zero), i.e. there is something to decide; the three roles of the pair kernel read this byte
-__global__ void sym_quiet_kernel(const unsigned int* __restrict__ tile_state, int flag_ld, int MTg, int NTs, int nphi,
-                                 unsigned char* __restrict__ symq, unsigned char* __restrict__ need, int need_bytes) {
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx < need_bytes) need[idx] = 0;  // (also clears the map the pair kernel marks: one launch less per iteration)
-    if (idx >= MTg * NTs) return;
-    const int mt = idx / NTs, nt = idx - mt * NTs;
-    const unsigned int mask = (mt & 1) ? 0xFFFF0000u : 0x0000FFFFu;
-    const unsigned int* row = tile_state + (size_t)(mt >> 1) * flag_ld;
+// One warp per PAIR tile (two groups of 64 lines of sight x one symmetric column tile) decides what the pair kernel has to
+// do.  Per group: symq = 1 when some original tile this symmetric tile overlaps is quiet (its state is identically zero)
+// -- there is something to decide -- AND the margins of the last test no longer cover what happened since (incremental
+// screening, see above).  A tile that is going to be tested gets its entries reset to {+inf, L_p} (the test takes minima
+// of the first), one without a quiet original tile gets {0, .} (nothing is proven for it).  Pair tiles with work are
+// appended to `list` (numbering of tile_coords(t, MTP, NTs)); original tiles that hold state are marked in `need` (zeroed
+// by the caller): they go on to the next pass whatever the test says.
+__global__ void sym_select_kernel(const unsigned int* __restrict__ tile_state, int flag_ld, int MTg, int NTs, int nphi,
+                                  unsigned char* __restrict__ symq, unsigned char* __restrict__ need, int need_ld,
+                                  int* __restrict__ list, int* __restrict__ count, float2* __restrict__ expiry, IncrState st,
+                                  int P, int record) {
+    const int idx = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    const int MTP = (MTg + 1) / 2;
+    if (idx >= MTP * NTs) return;
+    const int mtp = idx / NTs, nt = idx - mtp * NTs;
     int lo[4], hi[4];
     const int nr = sym_ranges(nt, NTs, nphi, lo, hi);
-    unsigned char any_quiet = 0;
-    for (int r = 0; r < nr; ++r)
-        for (int t = lo[r] >> 8; t <= (hi[r] - 1) >> 8; ++t) {
-            unsigned int wd = row[2 * t];
-            if (2 * t + 1 < flag_ld) wd |= row[2 * t + 1];
-            if (!(wd & mask)) any_quiet = 1;
+    // phi cells this symmetric tile decides: [a0, a1] and its mirror [b0, b1] (the cell without a mirror: [0, 0])
+    const int a0 = nt == NTs - 1 ? 0 : lo[0], a1 = nt == NTs - 1 ? 0 : hi[0] - 1;
+    const int b0 = nt == NTs - 1 ? 0 : lo[1], b1 = nt == NTs - 1 ? 0 : hi[1] - 1;
+    int work = 0;
+    for (int g = 0; g < 2; ++g) {
+        const int mt = 2 * mtp + g;
+        if (mt >= MTg) break;
+        const unsigned int mask = (mt & 1) ? 0xFFFF0000u : 0x0000FFFFu;
+        const unsigned int* row = tile_state + (size_t)(mt >> 1) * flag_ld;
+        unsigned char* need_row = need + (size_t)(mt >> 1) * need_ld;
+        int any_quiet = 0;
+        for (int r = 0; r < nr; ++r)
+            for (int t = (lo[r] >> 8) + lane; t <= (hi[r] - 1) >> 8; t += 32) {
+                unsigned int wd = row[2 * t];
+                if (2 * t + 1 < flag_ld) wd |= row[2 * t + 1];
+                if (wd & mask) need_row[t] = 1;  // an original tile with state
+                else any_quiet = 1;
+            }
+        any_quiet = __any_sync(0xffffffffu, any_quiet);
+        int screen = any_quiet;
+        if (expiry != nullptr) {
+            float2* e = expiry + ((size_t)mt * NTs + nt) * 64;
+            bool valid = any_quiet != 0;
+            float len[2] = {0.f, 0.f};
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int p = mt * 64 + lane + 32 * h;
+                if (p >= P) continue;
+                len[h] = st.pathlen[p];
+                if (!valid) continue;
+                const float2 rec = e[lane + 32 * h];
+                if (!(rec.x > 0.f)) {
+                    valid = false;
+                } else if (rec.x != __int_as_float(0x7f800000)) {
+                    const int2 ex = st.ext[p];
+                    int dist = nphi - 1;
+                    if (ex.x <= ex.y) {
+                        const int da = max(0, max(a0 - ex.y, ex.x - a1)), db = max(0, max(b0 - ex.y, ex.x - b1));
+                        dist = min(min(da, db), nphi - 1);
+                    }
+                    const float2 c = st.crow[p];
+                    const float coef = c.x * st.env[dist] + c.y;
+                    if (!(rec.x - st.qclock[p] > coef * (len[h] - rec.y) * 1.001f)) valid = false;
+                }
+            }
+            valid = __all_sync(0xffffffffu, valid);
+            if (valid) {
+                screen = 0;  // still provably zero: neither tested nor listed
+            } else {
+                const float v = (any_quiet && record) ? __int_as_float(0x7f800000) : 0.f;
+                e[lane] = make_float2(v, len[0]);
+                e[lane + 32] = make_float2(v, len[1]);
+            }
         }
-    symq[idx] = any_quiet;
+        if (lane == 0) symq[(size_t)mt * NTs + nt] = (unsigned char)screen;
+        work |= screen;
+    }
+    if (work && lane == 0) {  // (tile id in the numbering of tile_coords(t, MTP, NTs): invert it)
+        const int g = mtp / RASTER_GROUP, first = g * RASTER_GROUP;
+        const int gsize = min(RASTER_GROUP, MTP - first);
+        list[atomicAdd(count, 1)] = g * RASTER_GROUP * NTs + nt * gsize + (mtp - first);
+    }
 }
 
 constexpr int P2_STAGES = 6;
@@ -975,9 +1097,10 @@ screen8_pair_kernel(const __grid_constant__ CUtensorMap map_a8, const __grid_con
     const uint32_t rank = cluster_ctarank();
     const int cluster_id = blockIdx.x >> 1, nclusters = gridDim.x >> 1;
     const int MTP = (MT + 1) / 2;
-    const int total = (PLAIN && epi.tile_list) ? __ldcg(epi.tile_count) : MTP * NT;
+    const bool listed = (PLAIN || SYM) && epi.tile_list != nullptr;  // pair tiles to process (sym_select_kernel / pair lists)
+    const int total = listed ? __ldcg(epi.tile_count) : MTP * NT;
     const int KB = (K + BKE - 1) / BKE;
-    auto pair_id = [&](int ti) -> int { return (PLAIN && epi.tile_list) ? __ldcg(epi.tile_list + ti) : ti; };
+    auto pair_id = [&](int ti) -> int { return listed ? __ldcg(epi.tile_list + ti) : ti; };
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&map_a8);
@@ -1146,8 +1269,9 @@ screen8_pair_kernel(const __grid_constant__ CUtensorMap map_a8, const __grid_con
                     } else if (SYM) {
                         const int jw = nt == NT - 1 ? -1 : nphi / 2 + (BN / 2) * nt + (EPI_COLS / 2) * half;
                         const int ncv = nt == NT - 1 ? 2 : nphi - nt * BN;
+                        float2* exp_tile = epi.expiry ? epi.expiry + ((size_t)mt * NT + nt) * 64 : nullptr;
                         const int fail = epi.sym_rows8
-                                             ? screen_tile_fails_sym8<!F16>(epi, acc, lane, mt * BM + sub * 32, half * EPI_COLS, ncv, K, jw)
+                                             ? screen_tile_fails_sym8<!F16>(epi, acc, lane, mt * BM + sub * 32, half * EPI_COLS, ncv, K, jw, exp_tile)
                                              : screen_tile_fails_sym<!F16>(epi, acc, lane, mt * BM + sub * 32, half * EPI_COLS, ncv, K, jw);
                         sym_fail = (int)__reduce_or_sync(0xffffffffu, (unsigned)fail);
                         list_it = sym_fail != 0;
@@ -1167,22 +1291,10 @@ screen8_pair_kernel(const __grid_constant__ CUtensorMap map_a8, const __grid_con
                 ++use;
             }
             if (PLAIN) continue;
-            if (SYM) {  // original tiles that go on: (a) those with state, (b) those a failed bound of this warp touches
+            if (SYM) {  // original tiles that go on: those with state (marked by sym_select_kernel) and those a failed bound touches
                 if (exists && lane == 0) {
                     unsigned char* row = epi.need + (size_t)(mt >> 1) * epi.need_ld;
-                    int lo[4], hi[4];
-                    if (ew == 0) {  // (a) once per tile, per original tile (the ranges do not align with them)
-                        const unsigned int mask = (mt & 1) ? 0xFFFF0000u : 0x0000FFFFu;
-                        const unsigned int* st = epi.tile_state + (size_t)(mt >> 1) * epi.flag_ld;
-                        const int nr = sym_ranges(nt, NT, nphi, lo, hi);
-                        for (int r = 0; r < nr; ++r)
-                            for (int t = lo[r] >> 8; t <= (hi[r] - 1) >> 8; ++t) {
-                                unsigned int wd = __ldcg(st + 2 * t);
-                                if (2 * t + 1 < epi.flag_ld) wd |= __ldcg(st + 2 * t + 1);
-                                if (wd & mask) row[t] = 1;
-                            }
-                    }
-                    if (sym_fail) {  // (b) the original tiles the failed bounds of this warp belong to
+                    if (sym_fail) {  // the original tiles the failed bounds of this warp belong to
                         if (nt == NT - 1) {  // the cell without a mirror: columns 0 (Re) and n (Im)
                             if (sym_fail & 0x0f) row[0] = 1;
                             if (sym_fail & 0xf0) row[nphi >> 8] = 1;
@@ -1476,6 +1588,118 @@ int launch_screen_eps(const float* abs_sum, const float* a_scale, int K, float* 
     return CSR_OK;
 }
 
+// ---- end of an iteration: row clocks of the incremental screening, operand scales that follow the row maxima ----------
+// (see "Incremental screening" above.)  One warp per line of sight.  dz = ||z(it+1) - z(it)||_1 and ||z(it+1)||_1 were
+// accumulated by EPI_FISTA, S_p = sum |r_hi(it)| by EPI_RESID; the state flags give the phi cells that hold state now.
+// Scales: an operand row is rescaled (power of two, target magnitude 2^6) when its maximum came within 2^4 of the fp16
+// range -- diverging runs (unit step below the stability limit) grow by less than that per iteration, so nothing
+// saturates; runs that stay in range never change a scale and keep their bits.
+__global__ void row_update_kernel(RowUpdate u, int P) {
+    const int p = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (p >= P) return;
+    float* rs = u.row_stat + 4 * (size_t)p;
+    const float dz = rs[0], zabs = rs[1];
+    const float zmax = rs[2], rmax_scaled = rs[3];   // (bit patterns of non-negative floats)
+    __syncwarp();
+    if (lane < 4) rs[lane] = 0.f;
+    if (u.incr.pathlen != nullptr) {
+        // phi cells with state: block b of the flags covers columns [128 b, 128 b + 127] of [Re (n) | Im (n)]
+        int lo = 0x7fffffff, hi = -1;
+        if (u.zero_flags != nullptr) {
+            const unsigned char* fl = u.zero_flags + (size_t)p * u.flag_ld;
+            for (int b = lane; b < u.flag_ld; b += 32) {
+                if (!fl[b]) continue;
+                const int c0 = 128 * b, c1 = min(128 * b + 127, 2 * u.n - 1);
+                if (c1 < u.n) {
+                    lo = min(lo, c0), hi = max(hi, c1);
+                } else if (c0 >= u.n) {
+                    lo = min(lo, c0 - u.n), hi = max(hi, c1 - u.n);
+                } else {  // the block that straddles the two halves: the last cells of Re and the first of Im
+                    lo = 0, hi = u.n - 1;
+                }
+            }
+        } else {
+            lo = 0, hi = u.n - 1;
+        }
+#pragma unroll
+        for (int sft = 16; sft > 0; sft >>= 1) {
+            lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, sft));
+            hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, sft));
+        }
+        if (lane == 0) {
+            const float2 c = u.incr.crow[p];
+            const float a = 2.f * (c.x + c.y);                                                    // trivial coefficient
+            const float r_l1 = u.abs_sum ? u.abs_sum[p] / u.rscale[p] * 1.001f + a * dz : 0.f;   // >= ||r(it+1)||_1
+            const float rr = fmaxf(u.incr.rhat[p], a * zabs * (1.f / 4096.f) + r_l1 * (1.f / 524288.f));
+            u.incr.rhat[p] = rr;
+            u.incr.pathlen[p] += dz * 1.001f;
+            u.incr.qclock[p] = ((float)(u.iter + 1) * u.noise[p] + rr) * 1.0001f;
+            int2 ex = u.incr.ext[p];
+            if (u.iter == 0) ex = make_int2(0x7fffffff, -1);   // (the dense starting point does not count: nothing is
+            if (lo <= hi) {                                     //  recorded before iteration 1)
+                ex.x = min(ex.x, lo);
+                ex.y = max(ex.y, hi);
+            }
+            u.incr.ext[p] = ex;
+        }
+    }
+    if (u.rescale && lane == 0) {
+        const float zs = u.zscale_write[p];
+        u.zscale_read[p] = zs;                       // the operand EPI_FISTA just stored carries this scale
+        if (zmax * zs >= 4096.f) u.zscale_write[p] = operand_scale(zmax);
+        if (rmax_scaled >= 4096.f) u.rscale[p] = operand_scale(rmax_scaled / u.rscale[p]);
+    }
+}
+int launch_row_update(const RowUpdate& u, int P, cudaStream_t stream) {
+    cudaEvent_t ev0, ev1;
+    const bool prof = profile_start(stream, &ev0, &ev1);
+    row_update_kernel<<<(P * 32 + 255) / 256, 256, 0, stream>>>(u, P);
+    CSR_LAUNCHED();
+    if (prof) profile_stop(13, stream, ev0, ev1);
+    return CSR_OK;
+}
+
+// |RMTF| of the base channel set at the offsets k cell, k = 0 .. n-1 (fp64 phases like the tables), then its suffix maximum
+__global__ void rmtf_abs_kernel(const double* __restrict__ l2, double l2_ref, int m, const float* __restrict__ w, double cell,
+                                int n, float* __restrict__ out) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const double d = 2.0 * cell * (double)k;
+    double re = 0.0, im = 0.0;
+    int base = 0;
+    for (int i = 0; i < m; ++i) {
+        if (w != nullptr && !(w[i] > 0.f)) continue;
+        double sn, cs;
+        sincos((l2[i] - l2_ref) * d, &sn, &cs);
+        re += cs;
+        im += sn;
+        ++base;
+    }
+    out[k] = base > 0 ? (float)(sqrt(re * re + im * im) / (double)base * 1.001 + 1e-6) : 0.f;
+}
+__global__ void __launch_bounds__(1024) suffix_max_kernel(const float* __restrict__ in, int n, float* __restrict__ out) {
+    __shared__ float part[1024];
+    // thread t owns the contiguous chunk [t c, (t + 1) c): chunk maxima, then a suffix maximum over the chunks
+    const int c = (n + 1023) / 1024, t = threadIdx.x;
+    float mx = 0.f;
+    for (int k = min(n, (t + 1) * c) - 1; k >= t * c; --k) mx = fmaxf(mx, in[k]);
+    part[t] = mx;
+    __syncthreads();
+    float tail = 0.f;  // maximum over the chunks after mine
+    for (int q = t + 1; q < 1024; ++q) tail = fmaxf(tail, part[q]);
+    for (int k = min(n, (t + 1) * c) - 1; k >= t * c; --k) {
+        tail = fmaxf(tail, in[k]);
+        out[k] = tail;
+    }
+}
+int launch_rmtf_envelope(const csr_plan* plan, const float* w, float* env, float* scratch, cudaStream_t stream) {
+    rmtf_abs_kernel<<<(plan->n + 127) / 128, 128, 0, stream>>>(plan->d_l2, plan->l2_ref, plan->m, w, plan->cell, plan->n, scratch);
+    CSR_LAUNCHED();
+    suffix_max_kernel<<<1, 1024, 0, stream>>>(scratch, plan->n, env);
+    CSR_LAUNCHED();
+    return CSR_OK;
+}
+
 // one CTA walks the tiles in rasterised order and appends each to one of two lists (ordered compaction): per chunk of
 // 1024 tiles one ballot per warp, the 32 warp counts scanned by every warp with shuffles, one barrier
 __global__ void __launch_bounds__(1024)
@@ -1523,8 +1747,11 @@ split_tile_lists_kernel(const unsigned char* __restrict__ need, const unsigned c
 int launch_split_tile_lists(const unsigned char* need, const unsigned char* exclude, int P, int N, int* list_a, int* count_a,
                             int* list_b, int* count_b, cudaStream_t stream) {
     const int MT = (P + BM - 1) / BM, NT = (N + BN - 1) / BN;
+    cudaEvent_t ev0, ev1;
+    const bool prof = profile_start(stream, &ev0, &ev1);
     split_tile_lists_kernel<<<1, 1024, 0, stream>>>(need, exclude, MT, NT, list_a, count_a, list_b, count_b);
     CSR_LAUNCHED();
+    if (prof) profile_stop(12, stream, ev0, ev1);
     return CSR_OK;
 }
 
@@ -1641,8 +1868,9 @@ static int cached_sym_map(CUtensorMap* map, const void* base, int P, int m, size
 }
 
 int launch_screen_sym_pair(const csr_plan* plan, const void* a, bool fp8, int P, const GemmEpilogue& epi_in, unsigned char* need,
-                           cudaStream_t stream) {
-    CSR_REQUIRE(P > 0 && plan->sym_ok && (fp8 || plan->sym16_ok) && need, "symmetric screening: not available for this plan");
+                           int* pair_list, int* pair_count, const IncrState* incr, bool record, cudaStream_t stream) {
+    CSR_REQUIRE(P > 0 && plan->sym_ok && (fp8 || plan->sym16_ok) && need && pair_list && pair_count,
+                "symmetric screening: not available for this plan");
     GemmEpilogue epi = epi_in;
     epi.P = P;
     epi.N = 2 * plan->n;
@@ -1655,9 +1883,6 @@ int launch_screen_sym_pair(const csr_plan* plan, const void* a, bool fp8, int P,
     const int MTg = (P + BM / 2 - 1) / (BM / 2), NTs = (plan->n + BN - 1) / BN + 1;
     unsigned char* symq = need + align256((size_t)MTo * NTo);  // (the scratch holds both maps: sym_scratch_bytes)
     epi.symq = symq;
-    const int cover = max(MTg * NTs, MTo * NTo);
-    sym_quiet_kernel<<<(cover + 255) / 256, 256, 0, stream>>>(epi.tile_state, epi.flag_ld, MTg, NTs, plan->n, symq, need, MTo * NTo);
-    CSR_LAUNCHED();
     CUtensorMap ma;
     // rows regrouped so that a thread holds both rows of a line of sight (needs the operand allocated with its row count
     // rounded up to 8: fista.cu); 2-D half-row view otherwise
@@ -1670,6 +1895,22 @@ int launch_screen_sym_pair(const csr_plan* plan, const void* a, bool fp8, int P,
     if (rc != CSR_OK)
         rc = fp8 ? cached_operand_map(&ma, a, 2 * P, plan->m, plan->ld8 / 2, 1) : cached_operand_map(&ma, a, 2 * P, plan->m, plan->m, 2);
     if (rc) return rc;
+    // incremental screening needs the per-row test of the regrouped operand view, the row clocks and the bound's inputs
+    IncrState st = {};
+    if (incr) st = *incr;
+    if (!epi.sym_rows8 || !st.pathlen || !st.env || !epi.qclock || !epi.rhat) epi.expiry = nullptr;
+    cudaEvent_t ev0, ev1;
+    const bool prof = profile_start(stream, &ev0, &ev1);
+    CSR_CUDA(cudaMemsetAsync(need, 0, (size_t)MTo * NTo, stream));
+    CSR_CUDA(cudaMemsetAsync(pair_count, 0, sizeof(int), stream));
+    const int MTP = (MTg + 1) / 2;
+    sym_select_kernel<<<(MTP * NTs * 32 + 255) / 256, 256, 0, stream>>>(epi.tile_state, epi.flag_ld, MTg, NTs, plan->n, symq, need,
+                                                                       NTo, pair_list, pair_count, epi.expiry, st, P, record ? 1 : 0);
+    CSR_LAUNCHED();
+    if (prof) profile_stop(12, stream, ev0, ev1);
+    if (!record) epi.expiry = nullptr;  // (first iteration: the rounding allowance of the starting point is not known yet)
+    epi.tile_list = pair_list;
+    epi.tile_count = pair_count;
     rc = fp8 ? launch_pair_kernel<3>(plan, ma, plan->map_sym8, P, epi, stream) : launch_pair_kernel<4>(plan, ma, plan->map_sym16, P, epi, stream);
     if (rc) return rc;
     return launch_split_tile_lists(need, nullptr, P, 2 * plan->n, epi.out_list, epi.out_count, nullptr, nullptr, stream);

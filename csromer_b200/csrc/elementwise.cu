@@ -89,7 +89,7 @@ int launch_split_rows(const float* in, int ld_in, int rows, int cols, const floa
 __global__ void __launch_bounds__(EW_THREADS)
 prepare_kernel(const float* __restrict__ data, int ld2m, int m, int n, const float* __restrict__ w, int w_pp,
                const float* __restrict__ s_in, int s_pp, const float* __restrict__ k, float norm_factor,
-               float* __restrict__ b, float* __restrict__ amask, float* __restrict__ fwd_chan) {
+               float* __restrict__ b, float* __restrict__ amask, float* __restrict__ fwd_chan, float2* __restrict__ crow) {
     const int p = blockIdx.x;
     const float kp = k[p];
     const float* wrow = w + (w_pp ? (size_t)p * m : 0);
@@ -97,8 +97,10 @@ prepare_kernel(const float* __restrict__ data, int ld2m, int m, int n, const flo
     const float* d = data + (size_t)p * ld2m;
     float* brow = b + (size_t)p * ld2m;
     const float inv_n = norm_factor / (float)n;
+    float live = 0.f;  // channels with w > 0
     for (int i = threadIdx.x; i < m; i += EW_THREADS) {
         const float wi = wrow[i], si = s[i];
+        live += wi > 0.f ? 1.f : 0.f;
         const float sk = wi / (si * kp);
         brow[i] = sk * d[i];
         brow[m + i] = sk * d[m + i];
@@ -109,12 +111,18 @@ prepare_kernel(const float* __restrict__ data, int ld2m, int m, int n, const flo
         }
     }
     for (int c = 2 * m + threadIdx.x; c < ld2m; c += EW_THREADS) brow[c] = 0.f;
+    if (crow != nullptr) {  // (kernel-uniform) coefficients of the incremental-screening bound (plan.cuh, IncrState)
+        live = block_reduce(live, false);
+        if (threadIdx.x == 0)
+            crow[p] = w_pp ? make_float2(fabsf(inv_n) * (float)m * 1.0001f, fabsf(inv_n) * ((float)m - live) * 1.0001f)
+                           : make_float2(fabsf(inv_n) * live * 1.0001f, 0.f);
+    }
 }
 
-int launch_prepare(const csr_plan* plan, const csr_fista_args& a, float* b, float* amask, float* fwd_chan,
+int launch_prepare(const csr_plan* plan, const csr_fista_args& a, float* b, float* amask, float* fwd_chan, float2* crow,
                    cudaStream_t stream) {
     prepare_kernel<<<a.P, EW_THREADS, 0, stream>>>(a.data, plan->ld2m, plan->m, plan->n, a.w, a.w_per_pixel, a.s,
-                                                   a.s_per_pixel, a.k, a.norm_factor, b, amask, fwd_chan);
+                                                   a.s_per_pixel, a.k, a.norm_factor, b, amask, fwd_chan, crow);
     CSR_LAUNCHED();
     return CSR_OK;
 }
@@ -122,7 +130,7 @@ int launch_prepare(const csr_plan* plan, const csr_fista_args& a, float* b, floa
 int launch_prepare_nu(const csr_fista_args& a, int m, int n, int ld2m, float* b, float* amask, float* fwd_chan,
                       cudaStream_t stream) {
     prepare_kernel<<<a.P, EW_THREADS, 0, stream>>>(a.data, ld2m, m, n, a.w, a.w_per_pixel, a.s, a.s_per_pixel, a.k,
-                                                   a.norm_factor, b, amask, fwd_chan);
+                                                   a.norm_factor, b, amask, fwd_chan, nullptr);
     CSR_LAUNCHED();
     return CSR_OK;
 }

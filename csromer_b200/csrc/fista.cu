@@ -17,7 +17,7 @@ namespace csr {
 int launch_split_rows(const float* in, int ld_in, int rows, int cols, const float* chan_scale, int chan_pp, int m,
                       const float* ref2, int ld_ref2, __half* hi, __half* lo, int ld_out, float* scale,
                       int fixed_scale, cudaStream_t stream);
-int launch_prepare(const csr_plan* plan, const csr_fista_args& a, float* b, float* amask, float* fwd_chan,
+int launch_prepare(const csr_plan* plan, const csr_fista_args& a, float* b, float* amask, float* fwd_chan, float2* crow,
                    cudaStream_t stream);
 int launch_finalize(const csr_plan* plan, const csr_fista_args& a, const float* model, float* residual,
                     const float* x, int ldx, int ncoef, cudaStream_t stream);
@@ -90,6 +90,12 @@ struct FistaWs {
     unsigned char* need[2];         // adjoint tiles [MT, NT] that need the exact gradient (predicted / after the test)
     int* tile_list3;
     float* eps;                     // [P] error bound of the one-product gradient
+    // row statistics, operand-scale tracking and the clocks of the incremental screening (dft_gemm.cu, row_update_kernel)
+    float *row_stat, *pathlen, *qclock, *rhat, *zscale_w, *env, *env_scratch;
+    float2 *crow, *expiry;
+    int2* ext;
+    int* sym_list;                  // pair tiles the mirror-symmetric screening kernel has to process, [0] = their number
+    size_t expiry_count;
     size_t bytes;
 };
 static FistaWs carve_fista(const csr_plan* plan, const csr_wavelet* wav, int P, void* ws) {
@@ -117,6 +123,18 @@ static FistaWs carve_fista(const csr_plan* plan, const csr_wavelet* wav, int P, 
     f.r8 = b.take<unsigned char>((size_t)round_up(P, 8) * plan->ld8);
     f.mma_count = b.take<unsigned long long>(CSR_PROFILE_KINDS);
     f.need[0] = b.take<unsigned char>(sym_scratch_bytes(plan, P));
+    f.row_stat = b.take<float>((size_t)4 * P);
+    f.crow = b.take<float2>(P);
+    f.pathlen = b.take<float>(P);
+    f.qclock = b.take<float>(P);
+    f.rhat = b.take<float>(P);
+    f.ext = b.take<int2>(P);
+    f.zscale_w = b.take<float>(P);
+    f.env = b.take<float>(plan->n);
+    f.env_scratch = b.take<float>(plan->n);
+    f.expiry_count = wav ? 0 : (size_t)((P + BM / 2 - 1) / (BM / 2)) * ((plan->n + BN - 1) / BN + 1) * 64;
+    f.expiry = b.take<float2>(f.expiry_count);
+    f.sym_list = b.take<int>((size_t)(((P + BM / 2 - 1) / (BM / 2) + 1) / 2) * ((plan->n + BN - 1) / BN + 1) + 8);
     f.sig = f.gcoef = f.wav_ws = nullptr;
     f.coef_flags[0] = f.coef_flags[1] = f.redo_flags = f.need[1] = nullptr;
     f.tile_list3 = nullptr;
@@ -213,7 +231,7 @@ extern "C" int csr_fista(csr_plan* plan, csr_wavelet* wav, const csr_fista_args*
 
     CSR_CUDA(cudaMemsetAsync(w.mma_count, 0, CSR_PROFILE_KINDS * sizeof(unsigned long long), stream));
     // 1. diagonals and the data term b = (w/(s k)) d; its scale drives every residual operand
-    if ((rc = launch_prepare(plan, a, w.b, w.amask, w.fwd_chan, stream))) return rc;
+    if ((rc = launch_prepare(plan, a, w.b, w.amask, w.fwd_chan, w.crow, stream))) return rc;
     if ((rc = launch_split_rows(w.b, ld2m, P, 2 * m, nullptr, 0, m, nullptr, 0, w.r_hi, w.r_lo, ld2m, w.rscale, 0, stream)))
         return rc;
 
@@ -259,6 +277,33 @@ extern "C" int csr_fista(csr_plan* plan, csr_wavelet* wav, const csr_fista_args*
     const bool use_screen8 = use_screen && !screen16_pair && options().screen8 != 0;  // fp8 pass in front of the fp16 one
     if (!wav && zero_skip) {
         if ((rc = launch_block_flags(w.z, ld2n, 2 * n, P, w.zero_flags, w.flag_ld, w.tile_flags, stream))) return rc;
+    }
+    // mirror-symmetric screening on CTA pairs (+phi and -phi decided together: half the K)
+    const bool sym = use_screen && options().pair != 0 && options().sym != 0 && plan->sym_ok && (!screen16_pair || plan->sym16_ok);
+    // incremental screening (exact): a tile that passed is tested again only when its margin may have been used up
+    const bool incr = sym && (screen16_pair || use_screen8) && options().screen_incr != 0 && w.expiry_count > 0 && plan->uniform_ok;
+    // the operand scales of z and r follow the row maxima (nothing changes while a run stays within the fp16 range)
+    const bool rescale = options().rescale != 0;
+    const bool row_stats = incr || rescale;
+    if (row_stats) {
+        CSR_CUDA(cudaMemsetAsync(w.row_stat, 0, sizeof(float) * 4 * (size_t)P, stream));
+        CSR_CUDA(cudaMemcpyAsync(w.zscale_w, w.zscale, sizeof(float) * P, cudaMemcpyDeviceToDevice, stream));
+    }
+    IncrState incr_state = {};
+    if (incr) {
+        CSR_CUDA(cudaMemsetAsync(w.pathlen, 0, sizeof(float) * P, stream));
+        CSR_CUDA(cudaMemsetAsync(w.qclock, 0, sizeof(float) * P, stream));
+        CSR_CUDA(cudaMemsetAsync(w.rhat, 0, sizeof(float) * P, stream));
+        CSR_CUDA(cudaMemsetAsync(w.ext, 0, sizeof(int2) * P, stream));
+        CSR_CUDA(cudaMemsetAsync(w.expiry, 0, sizeof(float2) * w.expiry_count, stream));
+        // |RMTF| envelope of the base channel set: the shared weights' live channels, or all channels when pixels flag their own
+        if ((rc = launch_rmtf_envelope(plan, a.w_per_pixel ? nullptr : a.w, w.env, w.env_scratch, stream))) return rc;
+        incr_state.pathlen = w.pathlen;
+        incr_state.qclock = w.qclock;
+        incr_state.rhat = w.rhat;
+        incr_state.ext = w.ext;
+        incr_state.crow = w.crow;
+        incr_state.env = w.env;
     }
     if (use_screen8) CSR_CUDA(cudaMemsetAsync(w.r8, 0, (size_t)round_up(P, 8) * plan->ld8, stream));  // (the padding of the fp8 rows stays zero)
     if (a.delta) CSR_CUDA(cudaMemsetAsync(a.delta, 0, sizeof(float) * P, stream));
@@ -326,6 +371,7 @@ extern "C" int csr_fista(csr_plan* plan, csr_wavelet* wav, const csr_fista_args*
                 }
             }
             e.mma_count = w.mma_count;
+            if (row_stats) e.row_stat = w.row_stat;
             if ((rc = launch_dft_gemm(plan, false, w.z_hi, w.z_lo, P, e, stream))) return rc;
         }
         if (!wav && use_screen) {
@@ -341,13 +387,17 @@ extern "C" int csr_fista(csr_plan* plan, csr_wavelet* wav, const csr_fista_args*
             e.flag_ld = w.flag_ld;
             e.mma_count = w.mma_count;
             int* counts = reinterpret_cast<int*>(w.screen_hdr);
-            const bool sym = options().pair != 0 && options().sym != 0 && plan->sym_ok;  // mirror-symmetric screening
+            if (incr) {
+                e.qclock = w.qclock;
+                e.rhat = w.rhat;
+                e.expiry = w.expiry;
+            }
             if (screen16_pair) {  // one fp16 pass on CTA pairs over every quiet tile
                 e.mode = EPI_SCREEN;
                 e.out_list = w.tile_list;
                 e.out_count = counts;
-                if (sym && plan->sym16_ok) {
-                    if ((rc = launch_screen_sym_pair(plan, w.r_hi, false, P, e, w.need[0], stream))) return rc;
+                if (sym) {
+                    if ((rc = launch_screen_sym_pair(plan, w.r_hi, false, P, e, w.need[0], w.sym_list + 8, w.sym_list, incr ? &incr_state : nullptr, it > 0, stream))) return rc;
                 } else {
                     if ((rc = launch_screen16_pair(plan, w.r_hi, P, e, stream))) return rc;
                 }
@@ -357,7 +407,7 @@ extern "C" int csr_fista(csr_plan* plan, csr_wavelet* wav, const csr_fista_args*
                     e.out_list = w.tile_list2;
                     e.out_count = counts + 1;
                     if (sym) {
-                        if ((rc = launch_screen_sym_pair(plan, w.r8, true, P, e, w.need[0], stream))) return rc;
+                        if ((rc = launch_screen_sym_pair(plan, w.r8, true, P, e, w.need[0], w.sym_list + 8, w.sym_list, incr ? &incr_state : nullptr, it > 0, stream))) return rc;
                     } else if (options().pair != 0 && P > BM) {
                         if ((rc = launch_screen8_pair(plan, w.r8, P, e, stream))) return rc;
                     } else {
@@ -366,6 +416,7 @@ extern "C" int csr_fista(csr_plan* plan, csr_wavelet* wav, const csr_fista_args*
                     e.tile_list = w.tile_list2;
                     e.tile_count = counts + 1;
                 }
+                e.expiry = nullptr;  // (the second, fp16 pass of the cascade tests every tile it is handed)
                 e.mode = EPI_SCREEN;
                 e.out_list = w.tile_list;
                 e.out_count = counts;
@@ -380,7 +431,8 @@ extern "C" int csr_fista(csr_plan* plan, csr_wavelet* wav, const csr_fista_args*
             e.z = w.z;
             e.out_hi = w.z_hi;
             e.out_lo = w.z_lo;
-            e.out_scale = w.zscale;
+            e.out_scale = row_stats ? w.zscale_w : w.zscale;
+            if (row_stats) e.row_stat = w.row_stat;
             e.lambda0 = a.lambda0;
             e.noise = a.noise;
             e.iter_cap = a.iter_cap;
@@ -471,6 +523,22 @@ extern "C" int csr_fista(csr_plan* plan, csr_wavelet* wav, const csr_fista_args*
                                              (last && a.delta) ? a.delta : nullptr, stream)))
                     return rc;
             }
+        }
+        if (row_stats && !last) {  // row clocks of the incremental screening; operand scales follow the row maxima
+            RowUpdate u = {};
+            u.row_stat = w.row_stat;
+            u.noise = a.noise;
+            u.abs_sum = (use_screen || wav_screen) ? w.screen_hdr + 8 : nullptr;
+            u.rscale = w.rscale;
+            u.zscale_read = wav ? w.zscale_w : w.zscale;   // (wavelet bases: the synthesis kernel keeps its fixed scale)
+            u.zscale_write = w.zscale_w;
+            if (incr) u.incr = incr_state;
+            u.zero_flags = (!wav && zero_skip) ? w.zero_flags : nullptr;
+            u.flag_ld = w.flag_ld;
+            u.n = n;
+            u.iter = it;
+            u.rescale = rescale ? 1 : 0;
+            if ((rc = launch_row_update(u, P, stream))) return rc;
         }
     }
     if (a.delta && a.iters > 0) {

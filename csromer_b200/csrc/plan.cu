@@ -10,6 +10,8 @@
 
 #include <cuda_fp8.h>
 
+#include <math.h>
+
 #include "plan.cuh"
 
 namespace csr {
@@ -98,7 +100,8 @@ Options& options() {
                         getenv("CSR_NO_WAVELET_VEC4") == nullptr, getenv("CSR_NO_RESID_FAST") == nullptr,
                         getenv("CSR_NO_SYM") == nullptr,
                         getenv("CSR_NO_SCREEN16_PAIR") == nullptr,
-                        getenv("CSR_NO_WAVELET_SCREEN") == nullptr};
+                        getenv("CSR_NO_WAVELET_SCREEN") == nullptr, getenv("CSR_NO_SCREEN_INCR") == nullptr,
+                        getenv("CSR_NO_RESCALE") == nullptr};
     return o;
 }
 }  // namespace csr
@@ -119,6 +122,8 @@ extern "C" int csr_set_option(const char* name, int value) {
     else if (!strcmp(name, "screen16_pair")) o.screen16_pair = value != 0;
     else if (!strcmp(name, "sym")) o.sym = value != 0;
     else if (!strcmp(name, "resid_fast")) o.resid_fast = value != 0;
+    else if (!strcmp(name, "screen_incr")) o.screen_incr = value != 0;
+    else if (!strcmp(name, "rescale")) o.rescale = value != 0;
     else {
         set_error("csr_set_option: unknown option '%s'", name);
         return CSR_ERR_ARG;
@@ -195,6 +200,10 @@ static int plan_build(csr_plan* p, const double* lambda2, const double* phi) {
     for (int j = 1; j < n && p->sym_ok; ++j)
         if (phi[j] != -phi[n - j]) p->sym_ok = 0;
     p->sym16_ok = p->sym_ok && p->ld2m == 2 * m && m % 8 == 0;
+    p->cell = n > 1 ? (phi[n - 1] - phi[0]) / (double)(n - 1) : 0.0;
+    p->uniform_ok = (n > 1 && p->cell > 0.0) ? 1 : 0;
+    for (int j = 0; j < n && p->uniform_ok; ++j)
+        if (fabs(phi[j] - (phi[0] + j * p->cell)) > 1e-9 * p->cell) p->uniform_ok = 0;
     if (p->sym_ok) {
         if ((rc = make_operand_map(&p->map_sym8, p->Tt8, 2 * n, m, p->ld8 / 2, BN / 2, 1))) return rc;
         if (p->sym16_ok && (rc = make_operand_map(&p->map_sym16, p->Tt_hi, 2 * n, m, m, BN / 2))) return rc;

@@ -26,6 +26,8 @@ struct csr_plan {
     // half rows -- bound the gradient at both +phi_j and -phi_j with half the K and half the operand bytes
     int sym_ok;                   // the phi grid is exactly antisymmetric about index n/2 (and n is even)
     int sym16_ok;                 // ... and the fp16 table can be read as half rows (ld2m == 2m, m % 8 == 0)
+    int uniform_ok;               // phi_j = phi_0 + j cell to rounding (Parameter.calculate_cellsize builds such grids)
+    double cell;
     CUtensorMap map_sym8, map_sym16;  // half-row views [2n rows, m], pitch ld8/2 bytes / m halves, 128-row box
     size_t table_bytes;
 };
@@ -100,6 +102,13 @@ struct GemmEpilogue {
     const unsigned char* symq;      // mirror-symmetric screening: per (64-LOS group, symmetric tile) bits of the ranges with state
     unsigned char* need;            // mirror-symmetric screening: [MT, need_ld] bytes, 1 = tile must go on (zeroed by the caller)
     int need_ld;
+    // Row statistics of the running iteration (zeroed by row_update_kernel): [p][0] += sum |z_new - z_old|, [1] += sum |z_new|,
+    // [2] = max |z_new| (bits, atomicMax) -- written by EPI_FISTA; [3] = max |r * out_scale| (bits) -- written by EPI_RESID.
+    float* row_stat;
+    // Incremental safe screening (mirror-symmetric pair kernels; see "incremental screening" in dft_gemm.cu):
+    const float* qclock;            // [P] additive row clock Q_p = it * noise_p + rhat_p (monotone)
+    const float* rhat;              // [P] running maximum of the rounding allowance
+    float2* expiry;                 // [MTg * NTs][64] per (tile, row): {X = margin - 2 rhat + Q as of the test, path length L0 then}
     unsigned long long* mma_count;  // optional: [CSR_PROFILE_KINDS], slot count_slot += K blocks x products issued
     int count_slot;                 // profile kind of this launch (set by the launchers)
     int debug;                 // measurement aid (CSR_DEBUG_EPI): bit 0 skips epilogue loads, bit 1 skips stores
@@ -138,6 +147,32 @@ int make_operand_map(CUtensorMap* map, const void* base, int rows, int cols, int
 int launch_dft_gemm(const csr_plan* plan, bool adjoint, const __half* a_hi, const __half* a_lo, int P,
                     const GemmEpilogue& epi, cudaStream_t stream);
 // eps[p] = bound on |three-product - one-product| adjoint output of line of sight p, in output units
+// Row clocks of the incremental screening.  The gradient of row p at a phi cell D cells away from every cell whose state
+// changed moves by at most  coef(D) * (path length of z_p),  coef(D) = crow.x * env[D] + crow.y  (env = suffix maximum of
+// the normalised |RMTF| of the base channel set, crow.x = |norm_factor| m_base / n, crow.y = |norm_factor| dead_p / n for
+// the channels a pixel flags on top of the base set).
+struct IncrState {
+    float* pathlen;         // [P] L_p = sum over iterations of ||z(s+1) - z(s)||_1 (rounded up)
+    float* qclock;          // [P] Q_p = it * noise_p + rhat_p
+    float* rhat;            // [P]
+    int2* ext;              // [P] union since iteration 1 of the phi-cell ranges [lo, hi] that held state (lo > hi: none)
+    const float2* crow;     // [P]
+    const float* env;       // [n]
+};
+// end of an iteration: consume row_stat into the row clocks of the incremental screening and follow the operand scales
+struct RowUpdate {
+    float* row_stat;        // [P, 4]
+    const float* noise;     // [P] lambda's decrement per iteration
+    const float* abs_sum;   // [P] sum |r_hi| of this iteration (scaled units), may be null
+    float* rscale;          // [P] scale of the residual operand (may be lowered for the next forward transform)
+    float* zscale_read;     // [P] scale the stored z operand was written with (read by the next forward transform)
+    float* zscale_write;    // [P] scale EPI_FISTA writes the next z operand with
+    IncrState incr;         // pathlen == nullptr: no incremental screening
+    const unsigned char* zero_flags;  // [P, flag_ld] state flags per 128 columns of the [Re | Im] row
+    int flag_ld, n, iter;
+    int rescale;            // follow the row maxima with the operand scales
+};
+int launch_row_update(const RowUpdate& u, int P, cudaStream_t stream);
 int launch_screen_eps(const float* abs_sum, const float* a_scale, int K, float* eps, int P, cudaStream_t stream);
 // need: [MT, NT] bytes.  Tiles with need != 0 (and exclude == 0, if given) -> list_a; with both_lists the others -> list_b
 int launch_split_tile_lists(const unsigned char* need, const unsigned char* exclude, int P, int N, int* list_a, int* count_a,
@@ -146,8 +181,14 @@ int launch_screen8_pair(const csr_plan* plan, const unsigned char* a8, int P, co
 // mirror-symmetric screening on CTA pairs (plan->sym_ok): fp8 (a = fp8 residual copy) or fp16 (a = r_hi, plan->sym16_ok);
 // tiles that are not quiet or fail the test end up in epi.out_list / out_count; `need` is scratch of sym_scratch_bytes()
 size_t sym_scratch_bytes(const csr_plan* plan, int P);
+// incr / record: incremental screening (incr->pathlen set; epi.expiry its per-tile store): tiles whose margins still hold
+// are skipped; record = this test writes its margins
+// pair_list / pair_count: scratch for the pair tiles that have work ((ceil(P/64)+1)/2 * (ceil(n/256)+1) ints, one int)
 int launch_screen_sym_pair(const csr_plan* plan, const void* a, bool fp8, int P, const GemmEpilogue& epi, unsigned char* need,
-                           cudaStream_t stream);
+                           int* pair_list, int* pair_count, const IncrState* incr, bool record, cudaStream_t stream);
+// env[k] = 1.001 * max over k' >= k of |sum_{i in base} exp(-2i (lambda2_i - l2_ref) k' cell)| / |base|  (k = 0 .. n-1);
+// base = channels with w[i] > 0 (w = shared weights [m]) or all channels (w = nullptr); scratch: [n] floats
+int launch_rmtf_envelope(const csr_plan* plan, const float* w, float* env, float* scratch, cudaStream_t stream);
 int launch_screen16_pair(const csr_plan* plan, const __half* a_hi, int P, const GemmEpilogue& epi, cudaStream_t stream);
 // EPI_PLAIN1 on CTA pairs; epi.tile_list / tile_count name PAIRS of pixel tiles (launch_pair_list), null = all
 int launch_plain1_pair(const csr_plan* plan, const __half* a_hi, int P, const GemmEpilogue& epi, cudaStream_t stream);

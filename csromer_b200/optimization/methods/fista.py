@@ -59,6 +59,10 @@ class FISTA(Optimizer):
         ok = (isinstance(self.fx, Chi2) and isinstance(getattr(self.fx, "dft_obj", None), FT)
               and hasattr(self.gx, "F") and self.gx.F is not None and len(self.gx.F) == 1
               and isinstance(self.gx.F[0], L1) and self.guess_param is not None and self.guess_param.data is not None)
+        # the fused loop hard-codes backward = (1/k) E^H (w/s): an operator configured otherwise (NUFFT1D(normalize=False)
+        # scales by 1/n, nufft.py:68-69) must go through the generic loop, which calls the operator's own methods
+        if ok and getattr(self.fx.dft_obj, "normalize", True) is False:
+            ok = False
         if self.fused and not ok:
             raise ValueError("fused=True needs fx=Chi2(dft_obj=<NDFT1D|NUFFT1D>) and gx=OFunction([L1])")
         return ok
@@ -149,12 +153,27 @@ class FISTA(Optimizer):
         cost_t = out["cost"].double().cpu().numpy()
         chi_v = cost_t[:, 0].reshape(pix) if pix else float(cost_t[0, 0])
         l1_v = cost_t[:, 1].reshape(pix) if pix else float(cost_t[0, 1])
-        cost = chi2.reg * chi_v + lam_final * l1_v
-        if hasattr(self.F_obj, "values") and self.F_obj is not None:
-            try:
-                self.F_obj.values[0], self.F_obj.values[1] = chi_v, l1_v
-            except (IndexError, TypeError):
-                pass
+        # F_obj.evaluate(x) of the reference (fista.py:107, ofunction.py:40-46): every term with ITS OWN reg -- the L1 term
+        # F_obj holds is usually the very object gx decayed, but it need not be
+        cost = None
+        terms = getattr(self.F_obj, "F", None)
+        if terms:
+            cost = 0.0
+            for i, term in enumerate(terms):
+                if isinstance(term, Chi2) and term.dft_obj is op and term.wavelet is wav:
+                    value = chi_v
+                elif isinstance(term, L1):
+                    value = l1_v
+                else:
+                    cost = None     # a term the fused loop did not evaluate: leave it to the objects below
+                    break
+                cost = cost + term.reg * value
+                try:
+                    self.F_obj.values[i] = value
+                except (AttributeError, IndexError, TypeError):
+                    pass
+        if cost is None:
+            cost = chi2.reg * chi_v + lam_final * l1_v
         # deep copy of the guess like the reference (fista.py:37-38), minus its (about to be replaced) data array
         held, self.guess_param._data = self.guess_param._data, None
         try:

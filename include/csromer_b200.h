@@ -196,9 +196,10 @@ int csr_channel_stats(const float* img, int m, int Y, int X, int x0, int xn, int
  * csr_profile(1) starts recording; csr_profile_collect sums elapsed ms and launch counts into CSR_PROFILE_KINDS-entry
  * arrays indexed [0 plain-forward, 1 plain-adjoint, 2 resid-forward, 3 resid-adjoint, 4 fista-forward,
  * 5 fista-adjoint, 6 fused wavelet synthesis, 7 fused wavelet analysis + update, 8 fp16 screening adjoint,
- * 9 fp8 screening adjoint, 10 one-product plain adjoint (wavelet-domain screening), 11 wavelet analysis + update redo pass]
- * and clears the record. */
-#define CSR_PROFILE_KINDS 12
+ * 9 fp8 screening adjoint, 10 one-product plain adjoint (wavelet-domain screening), 11 wavelet analysis + update redo pass,
+ * 12 tile selection / tile-list kernels of the screening, 13 end-of-iteration row update (incremental-screening clocks,
+ * operand scales), 14 and 15 reserved] and clears the record. */
+#define CSR_PROFILE_KINDS 16
 int csr_profile(int enable);
 int csr_profile_collect(double* ms_by_kind, long long* count_by_kind);
 

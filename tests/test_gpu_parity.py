@@ -224,9 +224,12 @@ def test_sparsity_shortcuts_are_bit_exact(nch, P, K, kw):
     results = []
     try:
         # (sym: the pair kernels screen +phi and -phi together, half the K; pair = 1, sym = 0 is the plain pair kernel)
-        for zero_skip, k_skip, screen, screen8, pair, sym in ((1, 1, 1, 1, 1, 1), (1, 1, 1, 1, 1, 0), (1, 1, 1, 1, 0, 0),
-                                                             (1, 1, 1, 0, 0, 0), (1, 1, 0, 0, 0, 0), (1, 0, 1, 1, 1, 1),
-                                                             (1, 0, 0, 0, 0, 0), (0, 0, 0, 0, 0, 0)):
+        # (incr: incremental screening -- a tile that passed is tested again only when its margin may be used up)
+        for zero_skip, k_skip, screen, screen8, pair, sym, incr in (
+                (1, 1, 1, 1, 1, 1, 1), (1, 1, 1, 1, 1, 1, 0), (1, 1, 1, 1, 1, 0, 0), (1, 1, 1, 1, 0, 0, 0), (1, 1, 1, 0, 0, 0, 0),
+                (1, 1, 0, 0, 0, 0, 0), (1, 0, 1, 1, 1, 1, 1), (1, 0, 0, 0, 0, 0, 0), (0, 0, 0, 0, 0, 0, 0)):
+            _lib.set_option("screen_incr", incr)
+            _lib.set_option("rescale", incr)
             _lib.set_option("zero_skip", zero_skip)
             _lib.set_option("k_skip", k_skip)
             _lib.set_option("screen", screen)
@@ -244,12 +247,96 @@ def test_sparsity_shortcuts_are_bit_exact(nch, P, K, kw):
         _lib.set_option("pair", 1)
         _lib.set_option("sym", 1)
         _lib.set_option("resid_fast", 1)
+        _lib.set_option("screen_incr", 1)
+        _lib.set_option("rescale", 1)
     assert np.count_nonzero(results[0][0]) > 0 and np.count_nonzero(results[0][0]) < 0.2 * results[0][0].size
     for other in results[1:]:
         for a, b in zip(results[0], other):
             np.testing.assert_array_equal(a, b)
     ref = oracle_fista(src, par, K, lam0, noise)
     check_fista(src, X, cost, l1, ref)
+
+
+@pytest.mark.parametrize("per_pixel", [False, True])
+def test_incremental_screening_skips_work_and_keeps_the_bits(per_pixel):
+    """incremental screening on a slab large enough for the pair kernels (P > 128): the screening GEMMs issue fewer
+    tensor-core blocks than with the switch off, and the solution is the same bit for bit.  Shared weights take the fp8
+    cascade, per-pixel weights the one-pass fp16 screening."""
+    from csromer_b200 import _device as dv
+    from csromer_b200 import _lib
+    K, P = 60, 300
+    src, par = make_batch(400, P, seed=5, mixed=True, per_pixel_w=per_pixel, flags=0.1 if per_pixel else 0.0)
+    dft = cs.NDFT1D(dataset=src, parameter=par)
+    plan = dft.device_plan()
+    dev = plan.device
+    data, _ = dv.pack_planar(src.data, plan.m, plan.ld2m, dev)
+    w = dft._channel_tensor(src.w, plan)
+    s = torch.as_tensor(np.asarray(src.s), dtype=torch.float32, device=dev)
+    k = dv.per_pixel_vector(src.k, P, dev, "k")
+    lam0 = 40.0 * np.asarray(src.theo_noise, dtype=np.float64)
+    lam = dv.per_pixel_vector(lam0, P, dev, "lambda")
+    noise = dv.per_pixel_vector(lam0 / (2.0 * K), P, dev, "noise")
+    got = {}
+    try:
+        for incr in (1, 0):
+            _lib.set_option("screen_incr", incr)
+            x = torch.zeros((P, plan.ld2n), dtype=torch.float32, device=dev)
+            out = plan.fista(data, w, s, k, x, lam, noise, K, use_dirty_as_guess=True, want_mma_blocks=True)
+            got[incr] = (x.cpu().numpy(), out["mma_blocks"].cpu().numpy().astype(np.float64))
+    finally:
+        _lib.set_option("screen_incr", 1)
+    np.testing.assert_array_equal(got[1][0], got[0][0])
+    assert 0 < np.count_nonzero(got[1][0]) < 0.2 * got[1][0].size
+    kind = 8 if per_pixel else 9        # fp16 / fp8 screening launches (csr_profile_collect's numbering)
+    assert got[0][1][kind] > 0 and got[1][1][kind] < 0.6 * got[0][1][kind], (got[1][1], got[0][1])
+
+
+def test_per_pixel_spectral_factor_in_the_shared_sampling_path():
+    """a [P, m] spectral factor used to be read as a shared [m] vector.  Every line of sight its own
+    spectral index, shared weights: GPU loop against the oracle with the same s."""
+    from csromer_b200 import _device as dv
+    K, P = 25, 37
+    src, par = make_batch(200, P, seed=21)
+    rng = np.random.RandomState(4)
+    alpha = rng.normal(1.0, 0.3, size=P)
+    nu_of_l2 = ob.C_LIGHT / np.sqrt(src.lambda2)
+    s_pp = (nu_of_l2[:, None] / src.nu_0) ** alpha[None, :]                       # (m, P)
+    k_pp = np.sum(np.asarray(src.w)[:, None] / s_pp, axis=0)
+    dft = cs.NDFT1D(dataset=src, parameter=par)
+    plan = dft.device_plan()
+    dev = plan.device
+    data, _ = dv.pack_planar(src.data, plan.m, plan.ld2m, dev)
+    w = torch.as_tensor(np.asarray(src.w), dtype=torch.float32, device=dev)
+    s = torch.as_tensor(s_pp.T.copy(), dtype=torch.float32, device=dev)           # [P, m]
+    k = dv.per_pixel_vector(k_pp, P, dev, "k")
+    lam0 = 40.0 * float(src.theo_noise)
+    lam = dv.per_pixel_vector(lam0, P, dev, "lambda")
+    noise = dv.per_pixel_vector(lam0 / (2.0 * K), P, dev, "noise")
+    x = torch.zeros((P, plan.ld2n), dtype=torch.float32, device=dev)
+    out = plan.fista(data, w, s, k, x, lam, noise, K, use_dirty_as_guess=True)
+    op = ob.ExactDFT(src.lambda2, par.phi, src.w, s_pp, k_pp, src.l2_ref)
+    d = np.asarray(src.data)
+    ref = ob.fista(op, d, ob.complex_to_real(op.backward(d)), lam0, lam0 / (2.0 * K), K)
+    got = x[:, :2 * plan.n].double().cpu().numpy().T
+    assert rel(got, ref["x"]) < TOL_MODEL
+    model = out["model"].double().cpu().numpy()
+    assert rel((model[:, :plan.m] + 1j * model[:, plan.m:2 * plan.m]).T, ref["model"]) < TOL_MODEL
+
+
+def test_operand_scales_follow_a_diverging_run():
+    """unit step below the stability limit (lambda0 = 5 theo_noise) diverges -- in the
+    reference too.  The fp16 operand scales must follow the growth instead of saturating: the GPU run stays finite and
+    tracks the float64 oracle while the iterate grows by orders of magnitude."""
+    src, par = make_batch(200, 40, seed=3, mixed=True)
+    K = 20
+    cost, X, l1, lam0, noise = run_fista(src, par, K, lam_mult=5.0)
+    op = oracle_operator(src, par)
+    start = ob.complex_to_real(op.backward(np.asarray(src.data)))
+    ref = ob.fista(op, np.asarray(src.data), start, lam0, noise, K)
+    growth = np.abs(ref["x"]).max() / np.abs(start).max()
+    assert 1e6 < growth < 1e20, growth     # far beyond the 2^10 headroom of the initial fp16 operand scales
+    assert np.isfinite(X.data).all()
+    assert rel(X.data, ref["x"]) < 5e-3
 
 
 def test_fista_on_a_phi_grid_without_mirror_symmetry():

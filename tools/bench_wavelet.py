@@ -83,8 +83,8 @@ for _ in range(args.reps):
 e1.record()
 barrier()
 lib.csr_profile(0)
-ms = np.zeros(12)
-cnt = np.zeros(12, dtype=np.int64)
+ms = np.zeros(16)
+cnt = np.zeros(16, dtype=np.int64)
 _lib.check(lib.csr_profile_collect(ms.ctypes.data_as(ctypes.POINTER(ctypes.c_double)),
                                    cnt.ctypes.data_as(ctypes.POINTER(ctypes.c_longlong))), "collect")
 total_ms = e0.elapsed_time(e1) / args.reps

@@ -52,7 +52,7 @@ for prof in (0, 1, 0):
     dev_ms, host_ms = run(3)
     print("profile=%d: device %.1f ms/step, host enqueue %.1f ms/step" % (prof, dev_ms, host_ms))
     if prof:
-        ms, cnt = np.zeros(12), np.zeros(12, dtype=np.int64)
+        ms, cnt = np.zeros(16), np.zeros(16, dtype=np.int64)
         import ctypes
         lib.csr_profile_collect(ms.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), cnt.ctypes.data_as(ctypes.POINTER(ctypes.c_longlong)))
         print("  kernel ms per step by kind:", np.round(ms / 3, 2), "sum %.1f" % (ms.sum() / 3))
