@@ -130,6 +130,21 @@ __device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* map, int c0, 
                  : "memory");
 }
 
+// 2-D tiled store shared -> global (bulk async group); out-of-bounds parts of the box are clipped
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* smem_src, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                 ::"l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// wait until all but the N most recent bulk groups of this thread have finished READING their shared-memory source
+template <int N>
+__device__ __forceinline__ void tma_store_wait_read() {
+    asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+// order generic-proxy accesses to shared memory (st.shared / ld.shared) against the async proxy (TMA) that follows
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
 // ---- tcgen05 / TMEM ------------------------------------------------------------------------------------
 __device__ __forceinline__ void tmem_alloc(uint32_t* smem_result, uint32_t ncols) {  // whole warp
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_result)),
@@ -295,6 +310,8 @@ struct Options {
     int wavelet_screen;  // wavelet bases: one-product gradient + rigorous bound away from the active coefficients
     int screen_incr;  // incremental safe screening: a screened tile is re-screened only when its margin is used up
     int rescale;      // operand scales of z and r follow the row maxima (fp16 headroom in diverging runs)
+    int pair3;        // three-product transforms on CTA pairs (cta_group::2, M = 256; each SM stages half of the B tile)
+    int tma_epi;      // ... with the residual epilogue staged through shared memory (TMA loads of b, TMA stores of r)
 };
 Options& options();
 

@@ -1331,6 +1331,379 @@ screen8_pair_kernel(const __grid_constant__ CUtensorMap map_a8, const __grid_con
     }
 }
 
+// ---- three-product transforms on CTA pairs (cta_group::2) -----------------------------------------------------------
+// dft_gemm_kernel's arithmetic -- the same three fp16 products per K block, the same window-aligned accumulation chunks
+// drained into registers, the same K-block skipping -- issued as M = 256 MMAs over the two SMs of a TPC: each CTA stages its
+// own A tile (hi, lo) and only HALF of the B tile (hi, lo), 64 KiB per K block and SM instead of 96.  In the sparse regime
+// the forward transform is bound by operand delivery (L2 -> SM) and by its epilogue, not by the tensor pipe: the pair moves
+// a third less per tile, and the shared memory it frees stages the residual epilogue's global traffic through TMA -- the b
+// tile arrives by bulk tensor loads issued before the K loop ends (two 4 KiB passes in flight per warp), the fp16 hi / lo
+// operand of the adjoint leaves by bulk tensor stores from a swizzled staging tile -- instead of 8-row x 32-byte accesses
+// per warp instruction.  A pair tile skips the K blocks that are zero for BOTH of its pixel tiles; a block that is zero for
+// one of them adds exact zeros there, so the results equal the one-CTA kernel's bit for bit.
+constexpr int P3_STAGES = 2;
+constexpr int P3_STAGE_BYTES = 4 * A_TILE_BYTES;      // A_hi, A_lo, half of B_hi, half of B_lo: 4 x (128 rows x 128 B) = 64 KiB
+constexpr int P3_EPI_WARP_BYTES = 12 * 1024;          // per epilogue warp: two 4 KiB passes of b + 4 KiB of output staging
+constexpr int P3_BAR_BYTES = 512;
+constexpr int P3_SMEM_BYTES = 1024 + P3_STAGES * P3_STAGE_BYTES + EPI_WARPS * P3_EPI_WARP_BYTES + P3_BAR_BYTES + NUM_WARPS_TOTAL * KMASK_WORDS * 4;
+static_assert(P3_SMEM_BYTES <= 232448, "shared memory budget exceeded");
+
+// K-block activity of a pair tile: the union of its two pixel tiles' flag rows (row1 may be null)
+__device__ __forceinline__ int build_kmask2(const unsigned int* row0, const unsigned int* row1, int nwords, int KB, uint32_t* mask,
+                                            int lane) {
+    int count = 0;
+    for (int w0 = 0; w0 < nwords; w0 += 32) {
+        const int idx = w0 + lane;
+        unsigned int v = idx < nwords ? __ldcg(row0 + idx) : 0u;
+        if (row1 != nullptr && idx < nwords) v |= __ldcg(row1 + idx);
+        const uint32_t bits = __ballot_sync(0xffffffffu, v != 0u);
+        if (lane == 0) mask[w0 >> 5] = bits;
+        count += 2 * __popc(bits);
+    }
+    __syncwarp();
+    if ((KB & 1) && ((mask[(KB >> 1) >> 5] >> ((KB >> 1) & 31)) & 1u)) count -= 1;
+    return count;
+}
+
+// EPI_RESID with its global traffic staged through shared memory (see above).  One warp, its 32 rows x 128 columns, in four
+// passes of 32 columns.  bbuf: two 4 KiB pass buffers (128-byte-swizzled boxes of 32 fp32 x 32 rows), bbar their barriers,
+// bphase their parities; passes 0 and 1 of this tile were requested by resid_tma_request before the K loop ended.  obuf:
+// 2 KiB hi + 2 KiB lo (64-byte-swizzled boxes of 32 fp16 x 32 rows).  Same arithmetic, same bits as epilogue_tile<EPI_RESID>;
+// the fp8 copy (1 byte per element) keeps its direct stores.  Columns / rows beyond the matrix are clipped by the TMA unit.
+__device__ __forceinline__ void resid_tma_request(const GemmEpilogue& epi, const CUtensorMap* map_b, uint8_t* bbuf, uint64_t* bbar,
+                                                  int pass, int row0, int col0) {
+    mbar_arrive_expect_tx(&bbar[pass & 1], 4096);
+    tma_load_2d(bbuf + (pass & 1) * 4096, map_b, &bbar[pass & 1], col0 + 32 * pass, row0);
+}
+__device__ __forceinline__ void epilogue_resid_tma(const GemmEpilogue& epi, const float (&acc)[EPI_COLS], int lane, int row0, int col0,
+                                                   const CUtensorMap* map_b, const CUtensorMap* map_hi, const CUtensorMap* map_lo,
+                                                   uint8_t* bbuf, uint8_t* obuf, uint64_t* bbar, uint32_t (&bphase)[2]) {
+    const int quad = lane & 3, r8 = lane >> 2;
+    float descale[4], oscale[4], dsum[4], rmax[4];
+    const float* cs_row[4];
+    bool row_ok[4];
+    const bool cs_even = (epi.m & 1) == 0 && (reinterpret_cast<uintptr_t>(epi.chan_scale) & 7) == 0;
+#pragma unroll
+    for (int ri = 0; ri < 4; ++ri) {  // ri = 2 lh + rh
+        const int row = row0 + r8 + 8 * (ri & 1) + 16 * (ri >> 1);
+        row_ok[ri] = row < epi.P;
+        descale[ri] = row_ok[ri] ? kTwiddleDescale / __ldg(epi.a_scale + row) : 0.f;
+        oscale[ri] = row_ok[ri] ? __ldg(epi.out_scale + row) : 0.f;
+        cs_row[ri] = (epi.chan_scale && row_ok[ri]) ? epi.chan_scale + (epi.chan_per_pixel ? (size_t)row * epi.m : 0) : nullptr;
+        dsum[ri] = 0.f;
+        rmax[ri] = 0.f;
+    }
+#pragma unroll
+    for (int pass = 0; pass < 4; ++pass) {
+        const int pc0 = col0 + 32 * pass;
+        const uint8_t* bsrc = bbuf + (pass & 1) * 4096;
+        mbar_wait(&bbar[pass & 1], bphase[pass & 1]);
+        bphase[pass & 1] ^= 1;
+        if (lane == 0) tma_store_wait_read<0>();  // the previous pass's stores have read the staging tile
+        __syncwarp();
+#pragma unroll
+        for (int ri = 0; ri < 4; ++ri) {
+            const int rin = r8 + 8 * (ri & 1) + 16 * (ri >> 1);
+            const int row = row0 + rin;
+#pragma unroll
+            for (int jl = 0; jl < 4; ++jl) {
+                const int col = pc0 + 8 * jl + 2 * quad;
+                const int ai = ((((ri >> 1) * 2 + (pass >> 1)) * 8 + (4 * (pass & 1) + jl)) * 2 + (ri & 1)) * 2;
+                const bool ok = row_ok[ri] && col < epi.N;
+                float2 cs = make_float2(1.f, 1.f);
+                if (cs_row[ri] != nullptr && ok) {
+                    const int c0 = col >= epi.m ? col - epi.m : col;
+                    if (cs_even) {
+                        cs = __ldg(reinterpret_cast<const float2*>(cs_row[ri] + c0));
+                    } else {
+                        const int c1 = col + 1 >= epi.m ? col + 1 - epi.m : col + 1;
+                        cs = make_float2(__ldg(cs_row[ri] + c0), __ldg(cs_row[ri] + c1));
+                    }
+                }
+                const int bb = (8 * jl + 2 * quad) * 4;  // byte offset of the column pair within the 128-byte row of b
+                const float2 bv = *reinterpret_cast<const float2*>(bsrc + rin * 128 + ((((bb >> 4) ^ (rin & 7)) << 4) | (bb & 15)));
+                const float a0 = acc[ai] * descale[ri], a1 = acc[ai + 1] * descale[ri];
+                const float r0 = __fmaf_rn(cs.x, a0, -bv.x) * oscale[ri], r1 = __fmaf_rn(cs.y, a1, -bv.y) * oscale[ri];
+                const __half2 h = __floats2half2_rn(r0, r1);
+                const float2 hf = __half22float2(h);
+                const __half2 l = __floats2half2_rn(r0 - hf.x, r1 - hf.y);
+                const int ob = (8 * jl + 2 * quad) * 2;  // byte offset within the 64-byte row of the staging boxes
+                const int so = rin * 64 + ((((ob >> 4) ^ ((rin >> 1) & 3)) << 4) | (ob & 15));
+                *reinterpret_cast<__half2*>(obuf + so) = h;
+                *reinterpret_cast<__half2*>(obuf + 2048 + so) = l;
+                if (ok) {
+                    dsum[ri] += fabsf(hf.x) + fabsf(hf.y);
+                    rmax[ri] = fmaxf(rmax[ri], fmaxf(fabsf(r0), fabsf(r1)));
+                    if (epi.out8 != nullptr) {
+                        const float2 v8 = make_float2(hf.x * kOperandScale8, hf.y * kOperandScale8);
+                        if (fmaxf(fabsf(v8.x), fabsf(v8.y)) > 448.f) dsum[ri] = __int_as_float(0x7f800000);  // unscreenable row
+                        const __nv_fp8x2_storage_t pk = __nv_cvt_float2_to_fp8x2(v8, __NV_SATFINITE, __NV_E4M3);
+                        unsigned char* o8 = epi.out8 + (size_t)row * epi.ld8;
+                        const int h8 = epi.ld8 >> 1;
+                        if (epi.m & 1) {
+                            o8[col < epi.m ? col : col - epi.m + h8] = (unsigned char)(pk & 0xff);
+                            o8[col + 1 < epi.m ? col + 1 : col + 1 - epi.m + h8] = (unsigned char)(pk >> 8);
+                        } else {
+                            *reinterpret_cast<__nv_fp8x2_storage_t*>(o8 + (col < epi.m ? col : col - epi.m + h8)) = pk;
+                        }
+                    }
+                }
+            }
+        }
+        fence_proxy_async();  // the staging tile is complete for the async proxy; the reads of b precede its refill
+        __syncwarp();
+        if (lane == 0) {
+            if (pass + 2 < 4) resid_tma_request(epi, map_b, bbuf, bbar, pass + 2, row0, col0);
+            if (pc0 < epi.N) {
+                tma_store_2d(map_hi, obuf, pc0, row0);
+                tma_store_2d(map_lo, obuf + 2048, pc0, row0);
+                tma_store_commit();
+            }
+        }
+    }
+#pragma unroll
+    for (int ri = 0; ri < 4; ++ri) {
+        const int row = row0 + r8 + 8 * (ri & 1) + 16 * (ri >> 1);
+        if (epi.abs_sum_out != nullptr) {  // kernel-uniform
+            float d = dsum[ri];
+            d += __shfl_xor_sync(0xffffffffu, d, 1);
+            d += __shfl_xor_sync(0xffffffffu, d, 2);
+            if (quad == 0 && row_ok[ri] && d != 0.f) atomicAdd(epi.abs_sum_out + row, d);
+        }
+        if (epi.row_stat != nullptr) {  // kernel-uniform
+            float v = rmax[ri];
+            v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 1));
+            v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 2));
+            if (quad == 0 && row_ok[ri] && v != 0.f)
+                atomicMax(reinterpret_cast<unsigned int*>(epi.row_stat + 4 * (size_t)row + 3), __float_as_uint(v));
+        }
+    }
+}
+
+template <int MODE, bool TMA_EPI>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
+dft_gemm_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
+                     const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
+                     const __grid_constant__ CUtensorMap map_e_in, const __grid_constant__ CUtensorMap map_e_hi,
+                     const __grid_constant__ CUtensorMap map_e_lo, int K, int MT, int NT, int chunk_kb, const GemmEpilogue epi) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* stage_base = smem;
+    uint8_t* epi_base = smem + P3_STAGES * P3_STAGE_BYTES;                       // (1024-byte aligned)
+    uint64_t* bars = reinterpret_cast<uint64_t*>(epi_base + EPI_WARPS * P3_EPI_WARP_BYTES);
+    uint64_t* full = bars;                              // [P3_STAGES]  both CTAs' TMA -> leader's MMA thread
+    uint64_t* empty = bars + P3_STAGES;                 // [P3_STAGES]  MMA -> each CTA's producer (multicast commit)
+    uint64_t* tmem_full = bars + 2 * P3_STAGES;         // [2]  MMA -> each CTA's epilogue warps (multicast commit)
+    uint64_t* tmem_empty = bars + 2 * P3_STAGES + 2;    // [2]  epilogue warps of BOTH CTAs -> leader's MMA thread
+    uint64_t* bbar_all = bars + 2 * P3_STAGES + 4;      // [EPI_WARPS][2]  b passes of the staged epilogue
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * P3_STAGES + 4 + 2 * EPI_WARPS);
+    uint32_t* masks = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(bars) + P3_BAR_BYTES);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const int cluster_id = blockIdx.x >> 1, nclusters = gridDim.x >> 1;
+    const int MTP = (MT + 1) / 2;
+    const int total = MTP * NT;
+    const int KB = (K + BK - 1) / BK;
+    uint32_t* my_mask = masks + warp * KMASK_WORDS;
+    const bool skip = epi.a_kflags != nullptr;
+    const int kwords = (KB + 1) >> 1;
+    auto pair_mask = [&](int mtp) {  // union of the K-block activity of the pair's two pixel tiles
+        const unsigned int* r0 = epi.a_kflags + (size_t)(2 * mtp) * epi.a_kflag_ld;
+        build_kmask2(r0, 2 * mtp + 1 < MT ? r0 + epi.a_kflag_ld : nullptr, kwords, KB, my_mask, lane);
+    };
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&map_a_hi);
+        tma_prefetch_desc(&map_a_lo);
+        tma_prefetch_desc(&map_b_hi);
+        tma_prefetch_desc(&map_b_lo);
+        if (TMA_EPI) {
+            tma_prefetch_desc(&map_e_in);
+            tma_prefetch_desc(&map_e_hi);
+            tma_prefetch_desc(&map_e_lo);
+        }
+        for (int s = 0; s < P3_STAGES; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], 1);
+        }
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(&tmem_full[b], 1);
+            mbar_init(&tmem_empty[b], 2 * EPI_WARPS);
+        }
+        for (int b = 0; b < 2 * EPI_WARPS; ++b) mbar_init(&bbar_all[b], 1);
+        mbar_fence_init();
+    }
+    if (warp == 1) {
+        tmem_alloc_pair(tmem_ptr, TMEM_COLS);
+        tmem_relinquish_pair();
+    }
+    tc_fence_before();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    if (warp < 4) {
+      asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+      if (warp == 0) {
+        // ===================== TMA producer (both CTAs) =====================
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int ti = cluster_id; ti < total; ti += nclusters) {
+            int mtp, nt;
+            tile_coords(ti, MTP, NT, mtp, nt);
+            if (skip) pair_mask(mtp);
+            if (lane == 0) {
+                const int mt = 2 * mtp + (int)rank;
+                for (int kb = skip ? next_active_kb(my_mask, 0, KB) : 0; kb < KB; kb = skip ? next_active_kb(my_mask, kb + 1, KB) : kb + 1) {
+                    mbar_wait(&empty[stage], phase ^ 1);
+                    uint8_t* sb = stage_base + stage * P3_STAGE_BYTES;
+                    if (rank == 0) mbar_arrive_expect_tx(&full[stage], 2 * P3_STAGE_BYTES);
+                    tma_load_2d_pair(sb, &map_a_hi, &full[stage], kb * BK, mt * BM);
+                    tma_load_2d_pair(sb + A_TILE_BYTES, &map_a_lo, &full[stage], kb * BK, mt * BM);
+                    tma_load_2d_pair(sb + 2 * A_TILE_BYTES, &map_b_hi, &full[stage], kb * BK, nt * BN + (int)rank * (BN / 2));
+                    tma_load_2d_pair(sb + 3 * A_TILE_BYTES, &map_b_lo, &full[stage], kb * BK, nt * BN + (int)rank * (BN / 2));
+                    if (++stage == P3_STAGES) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+            }
+            __syncwarp();  // the mask slot is rewritten for the next tile
+        }
+      } else if (warp == 1 && rank == 0) {
+        // ===================== MMA issuer (leader CTA only) =====================
+        constexpr uint32_t idesc = umma_idesc_f16(2 * BM, BN);  // M = 256 over the pair
+        int stage = 0;
+        uint32_t phase = 0;
+        uint32_t chunk = 0;
+        unsigned long long issued = 0;
+        for (int ti = cluster_id; ti < total; ti += nclusters) {
+            int mtp, nt;
+            tile_coords(ti, MTP, NT, mtp, nt);
+            if (skip) pair_mask(mtp);
+            if (lane == 0) {
+                int in_chunk = 0, cur_win = -1;
+                uint32_t d_tmem = 0;
+                for (int kb = skip ? next_active_kb(my_mask, 0, KB) : 0; kb < KB; kb = skip ? next_active_kb(my_mask, kb + 1, KB) : kb + 1) {
+                    const int win = kb / chunk_kb;
+                    if (in_chunk != 0 && win != cur_win) {
+                        umma_commit_pair(&tmem_full[chunk & 1]);
+                        ++chunk;
+                        in_chunk = 0;
+                    }
+                    if (in_chunk == 0) {
+                        const int buf = chunk & 1;
+                        mbar_wait(&tmem_empty[buf], ((chunk >> 1) & 1) ^ 1);
+                        tc_fence_after();
+                        d_tmem = tmem_base + (uint32_t)(buf * BN);
+                        cur_win = win;
+                    }
+                    mbar_wait(&full[stage], phase);
+                    tc_fence_after();
+                    const uint32_t sa_hi = smem_u32(stage_base + stage * P3_STAGE_BYTES);
+                    const uint32_t sa_lo = sa_hi + A_TILE_BYTES, sb_hi = sa_hi + 2 * A_TILE_BYTES, sb_lo = sa_hi + 3 * A_TILE_BYTES;
+#pragma unroll
+                    for (int k4 = 0; k4 < BK / 16; ++k4) {
+                        const uint64_t da_hi = umma_desc_sw128(sa_hi + k4 * 32), da_lo = umma_desc_sw128(sa_lo + k4 * 32);
+                        const uint64_t db_hi = umma_desc_sw128(sb_hi + k4 * 32), db_lo = umma_desc_sw128(sb_lo + k4 * 32);
+                        umma_f16_pair(d_tmem, da_hi, db_hi, idesc, (in_chunk != 0 || k4 != 0) ? 1u : 0u);
+                        umma_f16_pair(d_tmem, da_lo, db_hi, idesc, 1u);
+                        umma_f16_pair(d_tmem, da_hi, db_lo, idesc, 1u);
+                    }
+                    issued += 6;  // two CTAs x three products, units of one 128 x 256 x 64 block
+                    umma_commit_pair(&empty[stage]);
+                    if (++stage == P3_STAGES) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                    ++in_chunk;
+                }
+                if (in_chunk != 0) {
+                    umma_commit_pair(&tmem_full[chunk & 1]);
+                    ++chunk;
+                }
+            }
+            chunk = __shfl_sync(0xffffffffu, chunk, 0);
+        }
+        if (lane == 0 && epi.mma_count != nullptr && issued != 0) atomicAdd(epi.mma_count + epi.count_slot, issued);
+      }
+    } else {
+        // ===================== epilogue warps (both CTAs) =====================
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
+        const int ew = warp - 4;
+        const int sub = warp & 3;
+        const int half = ew >> 2;
+        uint8_t* bbuf = epi_base + ew * P3_EPI_WARP_BYTES;
+        uint8_t* obuf = bbuf + 8192;
+        uint64_t* bbar = bbar_all + 2 * ew;
+        uint32_t bphase[2] = {0u, 0u};
+        uint32_t chunk = 0;
+        const bool resid_fast = MODE == EPI_RESID && (epi.m & 1) == 0 && epi.debug == 0 && epi.no_fast == 0 && (epi.ld_out & 1) == 0 &&
+                                ((reinterpret_cast<uintptr_t>(epi.b) | reinterpret_cast<uintptr_t>(epi.chan_scale)) & 7) == 0 &&
+                                ((reinterpret_cast<uintptr_t>(epi.out_hi) | reinterpret_cast<uintptr_t>(epi.out_lo)) & 3) == 0 &&
+                                (epi.out8 == nullptr || ((reinterpret_cast<uintptr_t>(epi.out8) | (uintptr_t)epi.ld8) & 1) == 0);
+        for (int ti = cluster_id; ti < total; ti += nclusters) {
+            int mtp, nt;
+            tile_coords(ti, MTP, NT, mtp, nt);
+            const int mt = 2 * mtp + (int)rank;
+            const bool exists = mt < MT;
+            const int erow0 = mt * BM + sub * 32, ecol0 = nt * BN + half * EPI_COLS;
+            const bool staged = TMA_EPI && MODE == EPI_RESID && exists && ecol0 < epi.N;
+            if (staged && lane == 0) {  // the first two passes of b arrive while the K loop runs
+                resid_tma_request(epi, &map_e_in, bbuf, bbar, 0, erow0, ecol0);
+                resid_tma_request(epi, &map_e_in, bbuf, bbar, 1, erow0, ecol0);
+            }
+            float acc[EPI_COLS];
+#pragma unroll
+            for (int j = 0; j < EPI_COLS; ++j) acc[j] = 0.f;
+            int nchunks = (KB + chunk_kb - 1) / chunk_kb;
+            if (skip) {  // count the windows that hold an active K block, exactly as the MMA thread walks them
+                pair_mask(mtp);
+                int c = 0;
+                if (lane == 0) {
+                    int cur_win = -1;
+                    for (int kb = next_active_kb(my_mask, 0, KB); kb < KB; kb = next_active_kb(my_mask, kb + 1, KB)) {
+                        const int win = kb / chunk_kb;
+                        c += (win != cur_win);
+                        cur_win = win;
+                    }
+                }
+                nchunks = __shfl_sync(0xffffffffu, c, 0);
+            }
+            for (int c = 0; c < nchunks; ++c, ++chunk) {
+                const int buf = chunk & 1;
+                mbar_wait(&tmem_full[buf], (chunk >> 1) & 1);
+                tc_fence_after();
+                if (exists) drain_chunk(tmem_base + ((uint32_t)(sub * 32) << 16) + (uint32_t)(buf * BN + half * EPI_COLS), acc);
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) {
+                    if (rank == 0) mbar_arrive(&tmem_empty[buf]);
+                    else mbar_arrive_leader(&tmem_empty[buf]);
+                }
+            }
+            if (!exists) continue;
+            if (staged) {
+                epilogue_resid_tma(epi, acc, lane, erow0, ecol0, &map_e_in, &map_e_hi, &map_e_lo, bbuf, obuf, bbar, bphase);
+            } else if (MODE == EPI_RESID && resid_fast && ecol0 + EPI_COLS <= epi.N && (ecol0 + EPI_COLS <= epi.m || ecol0 >= epi.m)) {
+                epilogue_resid_fast(epi, acc, lane, erow0, ecol0);
+            } else {
+                epilogue_tile<MODE>(epi, acc, lane, erow0, ecol0);
+            }
+        }
+        if (TMA_EPI && lane == 0) tma_store_wait_read<0>();  // the staging tiles stay valid until the last stores have read them
+    }
+
+    tc_fence_before();
+    cluster_sync_all();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc_pair(tmem_base, TMEM_COLS);
+    }
+}
+
 // ---- host side --------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -1530,6 +1903,97 @@ static int cached_operand_map(CUtensorMap* map, const void* base, int rows, int 
     return CSR_OK;
 }
 
+// [rows, cols] row-major matrix with pitch ld -> 2-D map with a {box_cols x box_rows} box whose rows span 64 or 128 bytes
+// (swizzled accordingly): the staging tiles of the pair kernel's residual epilogue.  Cached like the operand maps.
+static int cached_tile_map(CUtensorMap* map, const void* base, int rows, int cols, int ld, int elem_bytes, int box_cols, int box_rows) {
+    struct Entry {
+        const void* base;
+        int rows, cols, ld, eb, bc, br;
+        CUtensorMap map;
+    };
+    static thread_local Entry cache[8];
+    static thread_local int next = 0;
+    for (int i = 0; i < 8; ++i) {
+        const Entry& e = cache[i];
+        if (e.base == base && e.rows == rows && e.cols == cols && e.ld == ld && e.eb == elem_bytes && e.bc == box_cols && e.br == box_rows) {
+            *map = e.map;
+            return CSR_OK;
+        }
+    }
+    EncodeTiledFn enc = get_encode_fn();
+    if (!enc) return CSR_ERR_CUDA;
+    const int row_bytes = box_cols * elem_bytes;
+    if ((reinterpret_cast<uintptr_t>(base) & 15) || ((size_t)ld * elem_bytes) % 16 || (row_bytes != 64 && row_bytes != 128)) return CSR_ERR_ARG;
+    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * elem_bytes};
+    cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(map, elem_bytes == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base),
+                     dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return CSR_ERR_CUDA;
+    Entry& e = cache[next];
+    next = (next + 1) % 8;
+    e.base = base;
+    e.rows = rows;
+    e.cols = cols;
+    e.ld = ld;
+    e.eb = elem_bytes;
+    e.bc = box_cols;
+    e.br = box_rows;
+    e.map = *map;
+    return CSR_OK;
+}
+
+template <int MODE, bool TMA_EPI>
+static int launch_pair3(const csr_plan* plan, bool adjoint, const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& e_in,
+                        const CUtensorMap& e_hi, const CUtensorMap& e_lo, int P, const GemmEpilogue& epi_in, cudaStream_t stream) {
+    static int max_clusters = 0;
+    if (max_clusters == 0) {
+        CSR_CUDA(cudaFuncSetAttribute(dft_gemm_pair_kernel<MODE, TMA_EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, P3_SMEM_BYTES));
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(2 * plan->num_sms);
+        cfg.blockDim = dim3(NUM_THREADS);
+        cfg.dynamicSmemBytes = P3_SMEM_BYTES;
+        cudaLaunchAttribute attr;
+        attr.id = cudaLaunchAttributeClusterDimension;
+        attr.val.clusterDim.x = 2;
+        attr.val.clusterDim.y = 1;
+        attr.val.clusterDim.z = 1;
+        cfg.attrs = &attr;
+        cfg.numAttrs = 1;
+        int n = 0;
+        if (cudaOccupancyMaxActiveClusters(&n, dft_gemm_pair_kernel<MODE, TMA_EPI>, &cfg) != cudaSuccess || n <= 0) {
+            cudaGetLastError();
+            n = plan->num_sms / 2;
+        }
+        max_clusters = n;
+    }
+    const int K = adjoint ? 2 * plan->m : 2 * plan->n;
+    const int N = adjoint ? 2 * plan->n : 2 * plan->m;
+    const int MT = (P + BM - 1) / BM, NT = (N + BN - 1) / BN;
+    const int clusters = min(((MT + 1) / 2) * NT, max_clusters);
+    GemmEpilogue epi = epi_in;
+    ProfiledLaunch rec;
+    rec.kind = MODE * 2 + (adjoint ? 1 : 0);
+    epi.count_slot = rec.kind;
+    if (g_profile) {
+        CSR_CUDA(pooled_event(&rec.start));
+        CSR_CUDA(pooled_event(&rec.stop));
+        CSR_CUDA(cudaEventRecord(rec.start, stream));
+    }
+    dft_gemm_pair_kernel<MODE, TMA_EPI><<<2 * clusters, NUM_THREADS, P3_SMEM_BYTES, stream>>>(
+        a_hi, a_lo, adjoint ? plan->map_adj_hi_half : plan->map_fwd_hi_half, adjoint ? plan->map_adj_lo_half : plan->map_fwd_lo_half, e_in,
+        e_hi, e_lo, K, MT, NT, gemm_chunk_kb(adjoint), epi);
+    CSR_LAUNCHED();
+    if (g_profile) {
+        CSR_CUDA(cudaEventRecord(rec.stop, stream));
+        g_profiled.push_back(rec);
+    }
+    return CSR_OK;
+}
+
 int launch_dft_gemm(const csr_plan* plan, bool adjoint, const __half* a_hi, const __half* a_lo, int P,
                     const GemmEpilogue& epi_in, cudaStream_t stream) {
     CSR_REQUIRE(P > 0, "P must be positive");
@@ -1555,6 +2019,24 @@ int launch_dft_gemm(const csr_plan* plan, bool adjoint, const __half* a_hi, cons
         rc = cached_operand_map(&ma_lo, a_lo, P, K, ldk, 2);
     }
     if (rc) return rc;
+    // Three-product transforms of whole matrices on CTA pairs (a tile list names single tiles: those stay on one CTA each).
+    // Measured on B200 (profiles/README.md, round 2): the dense transforms gain 8 % (operand delivery: 64 KiB per K block
+    // and SM instead of 96); the K-block-skipping forward transform LOSES (0.27 -> 0.31 ms, 0.39 ms with the TMA-staged
+    // epilogue: every 2-block accumulation chunk costs a cross-SM hand-shake, and a warp's four 4 KiB passes of dependent
+    // bulk copies are latency bound), so the residual transform takes the pair kernel only in the dense regime or on request
+    // (option pair3 = 2).
+    const bool pair_resid = options().pair3 >= 2 || epi.a_kflags == nullptr;
+    if (options().pair3 != 0 && options().pair != 0 && P > BM && epi.tile_list == nullptr && epi.debug == 0 &&
+        (epi.mode == EPI_PLAIN || (epi.mode == EPI_RESID && pair_resid))) {
+        if (epi.mode == EPI_PLAIN) return launch_pair3<EPI_PLAIN, false>(plan, adjoint, ma_hi, ma_lo, ma_hi, ma_hi, ma_hi, P, epi, stream);
+        CUtensorMap e_in, e_hi, e_lo;
+        const bool staged = options().tma_epi != 0 && options().pair3 >= 2 && epi.b != nullptr && epi.out_hi != nullptr && epi.out_lo != nullptr &&
+                            cached_tile_map(&e_in, epi.b, P, epi.N, epi.ld_out, 4, 32, 32) == CSR_OK &&
+                            cached_tile_map(&e_hi, epi.out_hi, P, epi.N, epi.ld_out, 2, 32, 32) == CSR_OK &&
+                            cached_tile_map(&e_lo, epi.out_lo, P, epi.N, epi.ld_out, 2, 32, 32) == CSR_OK;
+        if (staged) return launch_pair3<EPI_RESID, true>(plan, adjoint, ma_hi, ma_lo, e_in, e_hi, e_lo, P, epi, stream);
+        return launch_pair3<EPI_RESID, false>(plan, adjoint, ma_hi, ma_lo, ma_hi, ma_hi, ma_hi, P, epi, stream);
+    }
     switch (epi.mode) {
         case EPI_PLAIN: return launch_mode<EPI_PLAIN>(plan, adjoint, ma_hi, ma_lo, P, epi, stream);
         case EPI_PLAIN1:

@@ -101,7 +101,9 @@ Options& options() {
                         getenv("CSR_NO_SYM") == nullptr,
                         getenv("CSR_NO_SCREEN16_PAIR") == nullptr,
                         getenv("CSR_NO_WAVELET_SCREEN") == nullptr, getenv("CSR_NO_SCREEN_INCR") == nullptr,
-                        getenv("CSR_NO_RESCALE") == nullptr};
+                        getenv("CSR_NO_RESCALE") == nullptr,
+                        getenv("CSR_NO_PAIR3") != nullptr ? 0 : (getenv("CSR_PAIR3") != nullptr ? atoi(getenv("CSR_PAIR3")) : 1),
+                        getenv("CSR_NO_TMA_EPI") == nullptr};
     return o;
 }
 }  // namespace csr
@@ -124,6 +126,8 @@ extern "C" int csr_set_option(const char* name, int value) {
     else if (!strcmp(name, "resid_fast")) o.resid_fast = value != 0;
     else if (!strcmp(name, "screen_incr")) o.screen_incr = value != 0;
     else if (!strcmp(name, "rescale")) o.rescale = value != 0;
+    else if (!strcmp(name, "pair3")) o.pair3 = value;   // 0 off, 1 dense transforms only (default), 2 every whole-matrix transform
+    else if (!strcmp(name, "tma_epi")) o.tma_epi = value != 0;
     else {
         set_error("csr_set_option: unknown option '%s'", name);
         return CSR_ERR_ARG;
@@ -209,6 +213,9 @@ static int plan_build(csr_plan* p, const double* lambda2, const double* phi) {
         if (p->sym16_ok && (rc = make_operand_map(&p->map_sym16, p->Tt_hi, 2 * n, m, m, BN / 2))) return rc;
     }
     if ((rc = make_operand_map(&p->map_adj_hi_half, p->Tt_hi, 2 * n, 2 * m, p->ld2m, BN / 2))) return rc;
+    if ((rc = make_operand_map(&p->map_adj_lo_half, p->Tt_lo, 2 * n, 2 * m, p->ld2m, BN / 2))) return rc;
+    if ((rc = make_operand_map(&p->map_fwd_hi_half, p->T_hi, 2 * m, 2 * n, p->ld2n, BN / 2))) return rc;
+    if ((rc = make_operand_map(&p->map_fwd_lo_half, p->T_lo, 2 * m, 2 * n, p->ld2n, BN / 2))) return rc;
     return CSR_OK;
 }
 

@@ -21,6 +21,7 @@ struct csr_plan {
     CUtensorMap map_fwd_hi, map_fwd_lo, map_adj_hi, map_adj_lo, map_adj8;
     CUtensorMap map_adj8_half;  // Tt8 with a 128-row box: half a B tile per CTA of a cta_group::2 pair
     CUtensorMap map_adj_hi_half;  // Tt_hi with a 128-row box (the one-product plain adjoint on CTA pairs)
+    CUtensorMap map_adj_lo_half, map_fwd_hi_half, map_fwd_lo_half;  // the other tables with 128-row boxes (three-product pair kernel)
     // Mirror-symmetric screening (dft_gemm.cu): when phi_j = -phi_{n-j} the tables of +phi and -phi differ only in the
     // sign of the sines, so the rows (cos theta_{.,j}, sin theta_{.,j}), j >= n/2, of Tt -- read as a [4n, m] matrix of
     // half rows -- bound the gradient at both +phi_j and -phi_j with half the K and half the operand bytes

@@ -225,11 +225,15 @@ def test_sparsity_shortcuts_are_bit_exact(nch, P, K, kw):
     try:
         # (sym: the pair kernels screen +phi and -phi together, half the K; pair = 1, sym = 0 is the plain pair kernel)
         # (incr: incremental screening -- a tile that passed is tested again only when its margin may be used up)
-        for zero_skip, k_skip, screen, screen8, pair, sym, incr in (
-                (1, 1, 1, 1, 1, 1, 1), (1, 1, 1, 1, 1, 1, 0), (1, 1, 1, 1, 1, 0, 0), (1, 1, 1, 1, 0, 0, 0), (1, 1, 1, 0, 0, 0, 0),
-                (1, 1, 0, 0, 0, 0, 0), (1, 0, 1, 1, 1, 1, 1), (1, 0, 0, 0, 0, 0, 0), (0, 0, 0, 0, 0, 0, 0)):
+        # (pair3 / tma: the three-product transforms on CTA pairs, with the residual epilogue staged through shared memory)
+        for zero_skip, k_skip, screen, screen8, pair, sym, incr, pair3, tma in (
+                (1, 1, 1, 1, 1, 1, 1, 1, 1), (1, 1, 1, 1, 1, 1, 1, 2, 1), (1, 1, 1, 1, 1, 1, 1, 2, 0), (1, 1, 1, 1, 1, 1, 0, 0, 0),
+                (1, 1, 1, 1, 1, 0, 0, 2, 1), (1, 1, 1, 1, 0, 0, 0, 0, 0), (1, 1, 1, 0, 0, 0, 0, 0, 0), (1, 1, 0, 0, 0, 0, 0, 0, 0),
+                (1, 0, 1, 1, 1, 1, 1, 1, 1), (1, 0, 0, 0, 0, 0, 0, 0, 0), (0, 0, 0, 0, 1, 0, 0, 2, 1), (0, 0, 0, 0, 0, 0, 0, 0, 0)):
             _lib.set_option("screen_incr", incr)
             _lib.set_option("rescale", incr)
+            _lib.set_option("pair3", pair3)
+            _lib.set_option("tma_epi", tma)
             _lib.set_option("zero_skip", zero_skip)
             _lib.set_option("k_skip", k_skip)
             _lib.set_option("screen", screen)
@@ -249,6 +253,8 @@ def test_sparsity_shortcuts_are_bit_exact(nch, P, K, kw):
         _lib.set_option("resid_fast", 1)
         _lib.set_option("screen_incr", 1)
         _lib.set_option("rescale", 1)
+        _lib.set_option("pair3", 1)
+        _lib.set_option("tma_epi", 1)
     assert np.count_nonzero(results[0][0]) > 0 and np.count_nonzero(results[0][0]) < 0.2 * results[0][0].size
     for other in results[1:]:
         for a, b in zip(results[0], other):
