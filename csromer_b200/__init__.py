@@ -5,6 +5,7 @@ Same public classes as the reference (``Dataset``, ``Parameter``, ``NDFT1D``/``D
 lambda^2 <-> phi transforms, the Chi2 gradient, the L1 / wavelet proximal steps and the FISTA loop running on
 sm_100a CUDA kernels for every line of sight of a cube at once.  See DESIGN.md.
 """
+from ._device import SparseRows
 from .base import Dataset
 from .cube import estimate_lipschitz, reconstruct_cube
 from .dictionaries import DiscreteWavelet, UndecimatedWavelet, Wavelet

@@ -32,6 +32,18 @@ def is_torch(a):
     return isinstance(a, torch.Tensor)
 
 
+_side_streams = {}
+
+
+def side_stream(device=None):
+    """one extra stream per device for transfers that overlap the compute stream (Dataset.prefetch)"""
+    require_cuda()
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    if dev not in _side_streams:
+        _side_streams[dev] = torch.cuda.Stream(device=dev)
+    return _side_streams[dev]
+
+
 def pixel_shape(arr, lead):
     """(pixel shape tuple, P) of an array whose axis 0 has length ``lead``."""
     if arr.shape[0] != lead:
@@ -51,19 +63,32 @@ def to_device(a, dtype=None, device=None):
     return t if dtype is None else t.to(dtype)
 
 
+def _offset_ptr(t, byte_offset):
+    return ctypes.c_void_p(t.data_ptr() + int(byte_offset))
+
+
 def pack_planar(a, length, ld, device=None):
-    """complex ``(length, *pix)`` or real ``(2*length, *pix)`` -> fp32 ``[P, ld]`` planar on the device."""
+    """complex ``(length, *pix)`` or real ``(2*length, *pix)`` -> fp32 ``[P, ld]`` planar on the device.  The transpose
+    is ``csr_pack_planar`` (32 x 32 shared-memory tiles), torch only moves the bytes to the device."""
     t = to_device(a, device=device)
+    lib = _lib.load()
     if t.is_complex():
         pix, P = pixel_shape(t, length)
-        t = t.reshape(length, P)
-        out = torch.zeros((P, ld), dtype=torch.float32, device=t.device)
-        out[:, :length] = t.real.t()
-        out[:, length:2 * length] = t.imag.t()
+        t = t.reshape(length, P).to(torch.complex64).contiguous()
+        flat = torch.view_as_real(t)                                   # [length, P, 2] fp32, interleaved
+        out = torch.empty((P, ld), dtype=torch.float32, device=t.device)
+        if ld > 2 * length:
+            out[:, 2 * length:] = 0.0
+        _lib.check(lib.csr_pack_planar(tptr(flat), _offset_ptr(flat, 4), 2 * P, 2, length, P, tptr(out), ld, stream_ptr()),
+                   "csr_pack_planar")
     else:
         pix, P = pixel_shape(t, 2 * length)
-        out = torch.zeros((P, ld), dtype=torch.float32, device=t.device)
-        out[:, :2 * length] = t.reshape(2 * length, P).t()
+        t = t.reshape(2 * length, P).to(torch.float32).contiguous()
+        out = torch.empty((P, ld), dtype=torch.float32, device=t.device)
+        if ld > 2 * length:
+            out[:, 2 * length:] = 0.0
+        _lib.check(lib.csr_pack_planar(tptr(t), _offset_ptr(t, 4 * length * P), P, 1, length, P, tptr(out), ld, stream_ptr()),
+                   "csr_pack_planar")
     return out, pix
 
 
@@ -71,14 +96,22 @@ def pack_real(a, length, ld, device=None):
     """real ``(length, *pix)`` -> fp32 ``[P, ld]``."""
     t = to_device(a, device=device)
     pix, P = pixel_shape(t, length)
-    out = torch.zeros((P, ld), dtype=torch.float32, device=t.device)
-    out[:, :length] = t.reshape(length, P).t()
+    t = t.reshape(length, P).to(torch.float32).contiguous()
+    out = torch.empty((P, ld), dtype=torch.float32, device=t.device)
+    if ld > length:
+        out[:, length:] = 0.0
+    _lib.check(_lib.load().csr_pack_planar(tptr(t), None, P, 1, length, P, tptr(out), ld, stream_ptr()), "csr_pack_planar")
     return out, pix
 
 
 def unpack_complex(t, length, pix, like_torch=False):
     """fp32 ``[P, ld]`` planar -> complex64 ``(length, *pix)`` (numpy unless ``like_torch``)."""
-    c = torch.complex(t[:, :length], t[:, length:2 * length]).t().contiguous().reshape((length,) + tuple(pix))
+    P = t.shape[0]
+    c = torch.empty((length, P), dtype=torch.complex64, device=t.device)
+    flat = torch.view_as_real(c)
+    _lib.check(_lib.load().csr_unpack_planar(tptr(t), t.shape[1], length, P, tptr(flat), _offset_ptr(flat, 4), 2 * P, 2,
+                                             stream_ptr()), "csr_unpack_planar")
+    c = c.reshape((length,) + tuple(pix))
     return c if like_torch else c.cpu().numpy()
 
 
@@ -91,8 +124,88 @@ def unpack_complex_like(t, length, pix, like):
 
 
 def unpack_real(t, length, pix, like_torch=False):
-    r = t[:, :length].t().contiguous().reshape((length,) + tuple(pix))
+    P = t.shape[0]
+    r = torch.empty((length, P), dtype=torch.float32, device=t.device)
+    _lib.check(_lib.load().csr_unpack_planar(tptr(t), t.shape[1], length, P, tptr(r), None, P, 1, stream_ptr()),
+               "csr_unpack_planar")
+    r = r.reshape((length,) + tuple(pix))
     return r if like_torch else r.cpu().numpy()
+
+
+class SparseRows:
+    """Compressed rows of a solution slab: for every line of sight the indices and values of its non-zero entries
+    (``csr_sparse_count`` / ``csr_sparse_fill``).  Behaves like the ``(ncoef, *pix)`` array it stands for as far as
+    ``len()``, ``shape`` and ``todense()`` go; ``offsets`` (P + 1, int64), ``indices`` (int32) and ``values`` (fp32) are
+    torch tensors on the device the solution lives on, or NumPy arrays after ``cpu()``."""
+
+    def __init__(self, offsets, indices, values, ncoef, pix):
+        self.offsets, self.indices, self.values = offsets, indices, values
+        self.ncoef, self.pix = int(ncoef), tuple(pix)
+
+    @classmethod
+    def from_planar(cls, x, ncoef, pix, capacity=None):
+        """``x``: fp32 ``[P, ld]`` on the device.  ``capacity`` = None sizes the lists exactly (one 8-byte read-back, i.e. a
+        synchronisation); an integer allocates that many entries without waiting for the device -- ``trim()`` later
+        checks that the solution fitted."""
+        lib = _lib.load()
+        P = x.shape[0]
+        counts = torch.empty((P,), dtype=torch.int32, device=x.device)
+        _lib.check(lib.csr_sparse_count(tptr(x), x.shape[1], int(ncoef), P, tptr(counts), stream_ptr()), "csr_sparse_count")
+        offsets = torch.zeros((P + 1,), dtype=torch.int64, device=x.device)
+        torch.cumsum(counts, dim=0, out=offsets[1:])
+        total = int(offsets[-1].item()) if capacity is None else int(capacity)
+        indices = torch.empty((max(total, 1),), dtype=torch.int32, device=x.device)
+        values = torch.empty((max(total, 1),), dtype=torch.float32, device=x.device)
+        _lib.check(lib.csr_sparse_fill(tptr(x), x.shape[1], int(ncoef), P, tptr(offsets), tptr(indices), tptr(values), total,
+                                       stream_ptr()), "csr_sparse_fill")
+        rows = cls(offsets, indices[:total], values[:total], ncoef, pix)
+        rows.lazy = capacity is not None
+        return rows
+
+    lazy = False
+
+    def trim(self):
+        """lists allocated with a ``capacity``: wait for the count, cut them to it (raises if they were too short)"""
+        if self.lazy:
+            total = int(self.offsets[-1])
+            if total > self.values.shape[0]:
+                raise CsrError("SparseRows: %d non-zeros do not fit the capacity of %d entries" % (total, self.values.shape[0]))
+            self.indices, self.values, self.lazy = self.indices[:total], self.values[:total], False
+        return self
+
+    def __len__(self):
+        return self.ncoef
+
+    @property
+    def shape(self):
+        return (self.ncoef,) + self.pix
+
+    @property
+    def nnz(self):
+        return int(self.trim().values.shape[0])
+
+    @property
+    def nbytes(self):
+        return int(self.offsets.numel()) * 8 + self.nnz * 8
+
+    def cpu(self):
+        if not is_torch(self.offsets):
+            return self
+        self.trim()
+        return SparseRows(self.offsets.cpu().numpy(), self.indices.cpu().numpy(), self.values.cpu().numpy(), self.ncoef, self.pix)
+
+    def row(self, p):
+        lo, hi = int(self.offsets[p]), int(self.offsets[p + 1])
+        return self.indices[lo:hi], self.values[lo:hi]
+
+    def todense(self):
+        """NumPy ``(ncoef, *pix)`` fp32"""
+        h = self.cpu()
+        P = h.offsets.shape[0] - 1
+        out = np.zeros((P, self.ncoef), dtype=np.float32)
+        rows = np.repeat(np.arange(P), np.diff(h.offsets))
+        out[rows, h.indices] = h.values
+        return np.ascontiguousarray(out.T).reshape(self.shape)
 
 
 def per_pixel_vector(v, P, device, name):

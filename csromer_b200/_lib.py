@@ -19,7 +19,8 @@ EXPORTS = [
     "csr_wavelet_ws_bytes", "csr_wavelet_decompose", "csr_wavelet_reconstruct", "csr_fista_ws_bytes",
     "csr_fista", "csr_launch_count", "csr_profile", "csr_profile_collect", "csr_edge_noise", "csr_convolve_phi",
     "csr_peak", "csr_set_option", "csr_nudft_forward", "csr_nudft_adjoint", "csr_fista_nu_ws_bytes", "csr_fista_nu",
-    "csr_pack_slab", "csr_unpack_slab", "csr_channel_stats",
+    "csr_pack_slab", "csr_unpack_slab", "csr_channel_stats", "csr_pack_planar", "csr_unpack_planar", "csr_sparse_count",
+    "csr_sparse_fill",
 ]
 
 
@@ -91,6 +92,10 @@ def load():
     lib.csr_pack_slab.argtypes = [c_void_p, c_void_p, c_longlong, c_int, c_longlong, c_int, c_void_p, c_int, c_void_p, c_void_p]
     lib.csr_unpack_slab.argtypes = [c_void_p, c_int, c_int, c_longlong, c_longlong, c_int, c_void_p, c_void_p, c_void_p]
     lib.csr_channel_stats.argtypes = [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]
+    lib.csr_pack_planar.argtypes = [c_void_p, c_void_p, c_longlong, c_int, c_int, c_int, c_void_p, c_int, c_void_p]
+    lib.csr_unpack_planar.argtypes = [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_longlong, c_int, c_void_p]
+    lib.csr_sparse_count.argtypes = [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]
+    lib.csr_sparse_fill.argtypes = [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_longlong, c_void_p]
     for fn in (lib.csr_nudft_forward, lib.csr_nudft_adjoint):
         fn.argtypes = [POINTER(NuSampling), c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]
     lib.csr_fista_nu_ws_bytes.argtypes = [POINTER(NuSampling), c_void_p, c_int]

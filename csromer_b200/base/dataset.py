@@ -186,6 +186,44 @@ class Dataset:
         if self._model_data is None:
             self._model_data = np.zeros_like(np.asarray(val)) if isinstance(val, np.ndarray) else None
 
+    def __getstate__(self):  # (copies and pickles do not carry the device-side copy of the data)
+        state = self.__dict__.copy()
+        state.pop("_packed", None)
+        return state
+
+    # ---- device copy of the data (GPU path) -----------------------------------------------------------------
+    def _data_key(self):
+        d = self._data
+        return (id(d), getattr(d, "_version", None), tuple(np.shape(d)))
+
+    def device_data(self, device=None):
+        """``data`` as the fp32 planar ``[P, ld2m]`` device matrix the kernels read, plus the pixel shape.  The copy is kept
+        on this object, so the dirty spectrum and the FISTA run of one dataset share one host-to-device transfer; it is
+        refreshed when ``data`` is re-assigned or (torch tensors) modified in place."""
+        from .. import _device as dv
+        held = getattr(self, "_packed", None)
+        if held is not None and held[0] == self._data_key() and (device is None or held[1].device == dv.torch.device(device)):
+            if held[3] is not None:
+                dv.torch.cuda.current_stream().wait_event(held[3])     # uploaded by prefetch() on its own stream
+            return held[1], held[2]
+        planar, pix = dv.pack_planar(self._data, self._m, (2 * self._m + 7) // 8 * 8, device)
+        if isinstance(self._data, np.ndarray) is False:                # NumPy arrays can change unnoticed: not cached
+            self._packed = (self._data_key(), planar, pix, None)
+        return planar, pix
+
+    def prefetch(self, device=None):
+        """Start the host-to-device transfer of ``data`` (pinned host tensor) on a side stream, so that it overlaps the
+        reconstruction of the previous slab; ``device_data`` then waits for it instead of copying."""
+        from .. import _device as dv
+        torch = dv.torch
+        stream = dv.side_stream(device)
+        with torch.cuda.stream(stream):
+            planar, pix = dv.pack_planar(self._data, self._m, (2 * self._m + 7) // 8 * 8, device)
+            done = torch.cuda.Event()
+            done.record(stream)
+        self._packed = (self._data_key(), planar, pix, done)
+        return self
+
     def defer_model(self, model_thunk, residual_thunk):
         """Used by the fused FISTA loop: ``model_data`` / ``residual`` of the final evaluation stay on the GPU until
         somebody reads them (for a cube they are large and often never read); the thunks convert to the type and

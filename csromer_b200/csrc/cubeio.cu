@@ -48,6 +48,57 @@ __global__ void pack_slab_kernel(const float* __restrict__ q, const float* __res
     }
 }
 
+// The same transpose for any frequency-first array the Python layer holds: `a` / `b` are the two planes (Re / Im of a
+// complex (L, P) array: b = a + 1 with pix_stride = 2 and chan_stride = 2 P; the two halves of a real (2L, P) array:
+// b = a + L * P), element (c, p) at plane[c * chan_stride + p * pix_stride].  No NaN handling: values pass unchanged.
+__global__ void pack_planar_kernel(const float* __restrict__ a, const float* __restrict__ b, long long chan_stride,
+                                   int pix_stride, int L, int P, float* __restrict__ out, int ld) {
+    __shared__ float ta[TP][TP + 1], tb[TP][TP + 1];
+    const int pb = blockIdx.x * TP, cb = blockIdx.y * TP;
+    for (int r = threadIdx.y; r < TP; r += 8) {
+        const int c = cb + r, p = pb + threadIdx.x;
+        float va = 0.f, vb = 0.f;
+        if (c < L && p < P) {
+            va = a[(size_t)c * chan_stride + (size_t)p * pix_stride];
+            if (b) vb = b[(size_t)c * chan_stride + (size_t)p * pix_stride];
+        }
+        ta[r][threadIdx.x] = va;
+        tb[r][threadIdx.x] = vb;
+    }
+    __syncthreads();
+    for (int r = threadIdx.y; r < TP; r += 8) {
+        const int p = pb + r, c = cb + threadIdx.x;
+        if (p < P && c < L) {
+            out[(size_t)p * ld + c] = ta[threadIdx.x][r];
+            if (b) out[(size_t)p * ld + L + c] = tb[threadIdx.x][r];
+        }
+    }
+}
+// ... and back: planar rows [P, ld] -> the two planes
+__global__ void unpack_planar_kernel(const float* __restrict__ in, int ld, int L, int P, float* __restrict__ a,
+                                     float* __restrict__ b, long long chan_stride, int pix_stride) {
+    __shared__ float ta[TP][TP + 1], tb[TP][TP + 1];
+    const int pb = blockIdx.x * TP, jb = blockIdx.y * TP;
+    for (int r = threadIdx.y; r < TP; r += 8) {
+        const int p = pb + r, j = jb + threadIdx.x;
+        float va = 0.f, vb = 0.f;
+        if (p < P && j < L) {
+            va = in[(size_t)p * ld + j];
+            if (b) vb = in[(size_t)p * ld + L + j];
+        }
+        ta[r][threadIdx.x] = va;
+        tb[r][threadIdx.x] = vb;
+    }
+    __syncthreads();
+    for (int r = threadIdx.y; r < TP; r += 8) {
+        const int j = jb + r, p = pb + threadIdx.x;
+        if (j < L && p < P) {
+            a[(size_t)j * chan_stride + (size_t)p * pix_stride] = ta[threadIdx.x][r];
+            if (b) b[(size_t)j * chan_stride + (size_t)p * pix_stride] = tb[threadIdx.x][r];
+        }
+    }
+}
+
 // grid: (ceil(P / 32), ceil(n / 32)), block (32, 8)
 __global__ void unpack_slab_kernel(const float* __restrict__ in, int ld, int n, long long npix, long long p0, int P,
                                    float* __restrict__ re, float* __restrict__ im) {
@@ -151,6 +202,24 @@ extern "C" int csr_channel_stats(const float* img, int m, int Y, int X, int x0, 
     CSR_REQUIRE(img && stats && m > 0 && Y > 0 && X > 0, "csr_channel_stats: bad argument");
     CSR_REQUIRE(0 <= x0 && x0 < xn && xn <= X && 0 <= y0 && y0 < yn && yn <= Y, "csr_channel_stats: bad window");
     channel_stats_kernel<<<m, 1024, 0, (cudaStream_t)stream>>>(img, Y, X, x0, xn, y0, yn, stats);
+    CSR_LAUNCHED();
+    return CSR_OK;
+}
+
+extern "C" int csr_pack_planar(const float* a, const float* b, long long chan_stride, int pix_stride, int L, int P, float* out,
+                               int ld_out, void* stream) {
+    CSR_REQUIRE(a && out && L > 0 && P > 0 && pix_stride > 0 && ld_out >= (b ? 2 * L : L), "csr_pack_planar: bad argument");
+    dim3 grid((P + TP - 1) / TP, (L + TP - 1) / TP), block(TP, 8);
+    pack_planar_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(a, b, chan_stride, pix_stride, L, P, out, ld_out);
+    CSR_LAUNCHED();
+    return CSR_OK;
+}
+
+extern "C" int csr_unpack_planar(const float* in, int ld, int L, int P, float* a, float* b, long long chan_stride, int pix_stride,
+                                 void* stream) {
+    CSR_REQUIRE(in && a && L > 0 && P > 0 && pix_stride > 0 && ld >= (b ? 2 * L : L), "csr_unpack_planar: bad argument");
+    dim3 grid((P + TP - 1) / TP, (L + TP - 1) / TP), block(TP, 8);
+    unpack_planar_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(in, ld, L, P, a, b, chan_stride, pix_stride);
     CSR_LAUNCHED();
     return CSR_OK;
 }

@@ -11,7 +11,8 @@ Two execution paths with the same semantics:
   * generic: the reference's Python loop over ``fx`` / ``g_prox`` callables, for any other objective objects.
 
 Extensions (not in the reference): ``step`` (gradient step, default 1.0 = reference; SURVEY.md section 0 fact 11 explains
-why 1/lambda_max may be wanted), per-pixel ``lambda`` / ``noise`` arrays for batches.
+why 1/lambda_max may be wanted), per-pixel ``lambda`` / ``noise`` arrays for batches, ``sparse_out`` (the solution comes
+back as compressed rows -- indices and values of its non-zeros -- instead of a dense slab).
 """
 import copy
 from dataclasses import dataclass
@@ -51,6 +52,9 @@ class FISTA(Optimizer):
     noise: float = None
     step: float = 1.0
     fused: bool = None  # None = automatic
+    sparse_out: bool = False  # fused path: return the solution as compressed rows (``SparseRows``) instead of a dense array
+    sparse_capacity: int = None  # ... with lists of this many entries allocated up front (no wait for the count)
+    async_cost: bool = False  # torch inputs: return the cost as a device tensor instead of waiting for it (streaming runs)
 
     # ------------------------------------------------------------------------------------------------------
     def _can_fuse(self):
@@ -115,7 +119,7 @@ class FISTA(Optimizer):
             param = copy.deepcopy(self.guess_param)
             return 0.0, param
 
-        data, pix = dv.pack_planar(ds.data, plan.m, plan.ld2m, dev)
+        data, pix = ds.device_data(dev) if hasattr(ds, "device_data") else dv.pack_planar(ds.data, plan.m, plan.ld2m, dev)
         P = data.shape[0]
         w = op._channel_tensor(ds.w, plan)
         s_host = np.asarray(ds.s, dtype=np.float64)
@@ -150,9 +154,18 @@ class FISTA(Optimizer):
                        lambda: dv.unpack_complex_like(resid_dev, plan.m, pix, like))
         lam_final = _decayed_lambda(lam0, noise, iters if cap is None else np.minimum(cap, iters))
         l1.reg = lam_final
-        cost_t = out["cost"].double().cpu().numpy()
-        chi_v = cost_t[:, 0].reshape(pix) if pix else float(cost_t[0, 0])
-        l1_v = cost_t[:, 1].reshape(pix) if pix else float(cost_t[0, 1])
+        if self.async_cost and like_torch:   # no host synchronisation: values stay on the device
+            cost_t = out["cost"].double()
+            chi_v, l1_v = cost_t[:, 0].reshape(pix), cost_t[:, 1].reshape(pix)
+            if np.ndim(lam_final):
+                lam_final_dev = torch.as_tensor(np.asarray(lam_final, dtype=np.float64).reshape(pix)).to(dev)
+            else:
+                lam_final_dev = float(lam_final)
+        else:
+            cost_t = out["cost"].double().cpu().numpy()
+            chi_v = cost_t[:, 0].reshape(pix) if pix else float(cost_t[0, 0])
+            l1_v = cost_t[:, 1].reshape(pix) if pix else float(cost_t[0, 1])
+            lam_final_dev = None
         # F_obj.evaluate(x) of the reference (fista.py:107, ofunction.py:40-46): every term with ITS OWN reg -- the L1 term
         # F_obj holds is usually the very object gx decayed, but it need not be
         cost = None
@@ -167,21 +180,26 @@ class FISTA(Optimizer):
                 else:
                     cost = None     # a term the fused loop did not evaluate: leave it to the objects below
                     break
-                cost = cost + term.reg * value
+                reg = lam_final_dev if (lam_final_dev is not None and term is l1) else term.reg
+                cost = cost + reg * value
                 try:
                     self.F_obj.values[i] = value
                 except (AttributeError, IndexError, TypeError):
                     pass
         if cost is None:
-            cost = chi2.reg * chi_v + lam_final * l1_v
+            cost = chi2.reg * chi_v + (lam_final if lam_final_dev is None else lam_final_dev) * l1_v
         # deep copy of the guess like the reference (fista.py:37-38), minus its (about to be replaced) data array
         held, self.guess_param._data = self.guess_param._data, None
         try:
             param = copy.deepcopy(self.guess_param)
         finally:
             self.guess_param._data = held
-        xr = dv.unpack_real(x, ncoef, pix, like_torch)
-        param.data = xr if like_torch else xr.astype(x0.dtype if np.asarray(x0).dtype.kind == "f" else np.float32)
+        if self.sparse_out:  # > 99 % of an L1 solution is zero: indices and values of the rest (csrc/sparse.cu)
+            rows = dv.SparseRows.from_planar(x, ncoef, pix, capacity=self.sparse_capacity if like_torch else None)
+            param.data = rows if like_torch else rows.cpu()
+        else:
+            xr = dv.unpack_real(x, ncoef, pix, like_torch)
+            param.data = xr if like_torch else xr.astype(x0.dtype if np.asarray(x0).dtype.kind == "f" else np.float32)
         self.F_dirty = out["f_dirty"]
         self.device_outputs = out  # planar device tensors of the run: f_dirty, model, residual, cost
         self._device_plan, self._pixel_shape = plan, pix

@@ -75,7 +75,10 @@ class FT(metaclass=ABCMeta):
     def _adjoint(self, b, row_scale_value):
         """row_scale * E^H ((w/s) b) for ``b`` complex ``(m, *pix)``"""
         plan = self.device_plan()
-        bt, pix = dv.pack_planar(b, plan.m, plan.ld2m, plan.device)
+        if b is self.dataset.data and not isinstance(b, np.ndarray):    # one upload per dataset (Dataset.device_data)
+            bt, pix = self.dataset.device_data(plan.device)
+        else:
+            bt, pix = dv.pack_planar(b, plan.m, plan.ld2m, plan.device)
         w, s = self._weights()
         s_col = s if w.ndim == 1 else s.reshape((-1,) + (1,) * (w.ndim - 1))
         chan = self._channel_tensor(w / s_col, plan)

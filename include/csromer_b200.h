@@ -192,6 +192,26 @@ int csr_unpack_slab(const float* in, int ld, int n, long long npix, long long p0
                     void* stream);
 int csr_channel_stats(const float* img, int m, int Y, int X, int x0, int xn, int y0, int yn, float* stats, void* stream);
 
+/* The same transposes for the arrays the Python classes hold (frequency / phi FIRST, pixels last: Dataset.data (m, P)
+ * complex, Parameter.data (n, P) complex or (2n, P) real -- the batch extension of base/dataset.py and
+ * reconstruction/parameter.py:127-137) <-> planar pixel-major rows.  a / b are the two planes, element (c, p) at
+ * plane[c * chan_stride + p * pix_stride]: Re / Im of an interleaved complex64 array (b = a + 1, pix_stride = 2,
+ * chan_stride = 2 P), or the two halves of a real (2L, P) array (b = a + L P); b = NULL moves a single [L, P] plane. */
+int csr_pack_planar(const float* a, const float* b, long long chan_stride, int pix_stride, int L, int P, float* out,
+                    int ld_out, void* stream);
+int csr_unpack_planar(const float* in, int ld, int L, int P, float* a, float* b, long long chan_stride, int pix_stride,
+                      void* stream);
+
+/* ---- compressed-row read-back of the L1 solution (README.md:374-384 writes it into dense planes; > 99 % of it is
+ * zero after the soft threshold of objectivefunction/priors/l1.py:30-32) -------------------------------------------
+ * csr_sparse_count: counts[p] = number of non-zeros among x[p, 0 .. ncols)
+ * csr_sparse_fill : idx / val [offsets[p], offsets[p+1]) = columns and values of the non-zeros of row p, ascending;
+ *                   offsets [P + 1] = exclusive prefix sum of counts (64-bit); entries at or beyond `capacity` are not
+ *                   written (lists sized before offsets[P] was read back: compare the two afterwards) */
+int csr_sparse_count(const float* x, int ld, int ncols, int P, int* counts, void* stream);
+int csr_sparse_fill(const float* x, int ld, int ncols, int P, const long long* offsets, int* idx, float* val,
+                    long long capacity, void* stream);
+
 /* per-launch timing of the transform GEMMs with CUDA events on the launching stream (measurement aid).
  * csr_profile(1) starts recording; csr_profile_collect sums elapsed ms and launch counts into CSR_PROFILE_KINDS-entry
  * arrays indexed [0 plain-forward, 1 plain-adjoint, 2 resid-forward, 3 resid-adjoint, 4 fista-forward,

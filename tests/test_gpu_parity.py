@@ -329,6 +329,46 @@ def test_per_pixel_spectral_factor_in_the_shared_sampling_path():
     assert rel((model[:, :plan.m] + 1j * model[:, plan.m:2 * plan.m]).T, ref["model"]) < TOL_MODEL
 
 
+def test_sparse_output_equals_dense_output():
+    """FISTA(sparse_out=True): the compressed rows hold exactly the non-zeros of the dense solution (NumPy in -> host
+    arrays, torch in -> device tensors); a prefetched dataset gives the same answer as a lazily uploaded one."""
+    src, par = make_batch(200, 77, seed=13, mixed=True)
+    K = 30
+    cost, X, l1, lam0, noise = run_fista(src, par, K)
+    dense = np.asarray(X.data)
+    dft = cs.NDFT1D(dataset=src, parameter=par)
+    guess = cs.Parameter(phi=par.phi, cellsize=par.cellsize)
+    guess.data = dft.backward(src.data)
+    guess.complex_data_to_real()
+    chi2, l1b = cs.Chi2(dft_obj=dft), cs.L1(reg=lam0)
+    cost2, Xs = cs.FISTA(guess_param=guess, F_obj=cs.OFunction([chi2, l1b]), fx=chi2, gx=cs.OFunction([l1b]), noise=noise, maxiter=K,
+                         verbose=False, sparse_out=True).run()
+    rows = Xs.data
+    assert isinstance(rows, cs.SparseRows) and isinstance(rows.values, np.ndarray) and len(rows) == dense.shape[0]
+    assert rows.shape == dense.shape and rows.nnz == np.count_nonzero(dense) and 0 < rows.nnz < 0.2 * dense.size
+    np.testing.assert_array_equal(rows.todense(), dense)
+    np.testing.assert_array_equal(cost2, cost)
+    idx, val = rows.row(5)
+    np.testing.assert_array_equal(idx, np.nonzero(dense[:, 5])[0])
+    np.testing.assert_array_equal(val, dense[idx, 5])
+    # torch host tensor in (pinned), prefetched on the side stream: device-resident compressed rows out
+    data_t = torch.as_tensor(np.asarray(src.data).astype(np.complex64)).pin_memory()
+    ds = cs.Dataset(lambda2=src.lambda2, data=data_t, sigma=src.sigma, spectral_idx=1.0).prefetch()
+    dft2 = cs.NDFT1D(dataset=ds, parameter=par)
+    g2 = cs.Parameter(phi=par.phi, cellsize=par.cellsize)
+    g2.data = dft2.backward(ds.data)
+    g2.complex_data_to_real()
+    chi2c, l1c = cs.Chi2(dft_obj=dft2), cs.L1(reg=lam0)
+    _, Xt = cs.FISTA(guess_param=g2, F_obj=cs.OFunction([chi2c, l1c]), fx=chi2c, gx=cs.OFunction([l1c]), noise=noise, maxiter=K,
+                     verbose=False, sparse_out=True).run()
+    assert dv_is_cuda(Xt.data.values)
+    assert rel(Xt.data.todense(), dense) < 1e-6            # (complex64 input instead of complex128: not the same bits)
+
+
+def dv_is_cuda(t):
+    return isinstance(t, torch.Tensor) and t.is_cuda
+
+
 def test_operand_scales_follow_a_diverging_run():
     """unit step below the stability limit (lambda0 = 5 theo_noise) diverges -- in the
     reference too.  The fp16 operand scales must follow the growth instead of saturating: the GPU run stays finite and
