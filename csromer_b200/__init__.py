@@ -8,6 +8,7 @@ sm_100a CUDA kernels for every line of sight of a cube at once.  See DESIGN.md.
 from ._device import SparseRows
 from .base import Dataset
 from .cube import estimate_lipschitz, reconstruct_cube
+from .faraday_sky import FaradaySky
 from .dictionaries import DiscreteWavelet, UndecimatedWavelet, Wavelet
 from .objectivefunction import L1, Chi2, Fi, OFunction
 from .optimization import FISTA, Optimizer
@@ -24,5 +25,5 @@ __all__ = [
     "Dataset", "Parameter", "FT", "NDFT1D", "DFT1D", "NUFFT1D", "PerPixelDFT1D", "DatasetStack", "Wavelet", "DiscreteWavelet", "UndecimatedWavelet",
     "Fi", "Chi2", "L1", "OFunction", "Optimizer", "FISTA", "FaradaySource", "FaradayThinSource",
     "FaradayThickSource", "reconstruct_cube", "estimate_lipschitz", "Flagger", "MeanFlagger", "HampelFlagger",
-    "ManualFlagger", "CSROMERReconstructorWrapper", "FaradayReconstructorWrapper", "Reader", "Writer", "filter_cubes", "DeviceCube", "calculate_noise",
+    "ManualFlagger", "FaradaySky", "SparseRows", "CSROMERReconstructorWrapper", "FaradayReconstructorWrapper", "Reader", "Writer", "filter_cubes", "DeviceCube", "calculate_noise",
 ]

@@ -58,7 +58,8 @@ def to_device(a, dtype=None, device=None):
     if is_torch(a):
         t = a.to(device=device or "cuda", non_blocking=True)
     else:
-        h = torch.from_numpy(np.ascontiguousarray(a))
+        arr = np.ascontiguousarray(a)
+        h = torch.from_numpy(arr if arr.flags.writeable else arr.copy())
         t = h.pin_memory().to(device or "cuda", non_blocking=True)
     return t if dtype is None else t.to(dtype)
 

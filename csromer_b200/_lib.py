@@ -20,7 +20,7 @@ EXPORTS = [
     "csr_fista", "csr_launch_count", "csr_profile", "csr_profile_collect", "csr_edge_noise", "csr_convolve_phi",
     "csr_peak", "csr_set_option", "csr_nudft_forward", "csr_nudft_adjoint", "csr_fista_nu_ws_bytes", "csr_fista_nu",
     "csr_pack_slab", "csr_unpack_slab", "csr_channel_stats", "csr_pack_planar", "csr_unpack_planar", "csr_sparse_count",
-    "csr_sparse_fill",
+    "csr_sparse_fill", "csr_flag_mean", "csr_flag_hampel", "csr_galactic_rm_image", "csr_healpix_lookup",
 ]
 
 
@@ -37,6 +37,12 @@ class FistaArgs(ctypes.Structure):
         ("residual", c_void_p), ("cost", c_void_p), ("delta", c_void_p), ("use_dirty_as_guess", c_int),
         ("mma_blocks", c_void_p), ("s_per_pixel", c_int),
     ]
+
+
+class Wcs(ctypes.Structure):
+    """mirror of ``csr_wcs``"""
+    _fields_ = [("crval1", c_double), ("crval2", c_double), ("crpix1", c_double), ("crpix2", c_double), ("cd11", c_double),
+                ("cd12", c_double), ("cd21", c_double), ("cd22", c_double), ("lonpole", c_double), ("proj", c_int)]
 
 
 class NuSampling(ctypes.Structure):
@@ -96,6 +102,12 @@ def load():
     lib.csr_unpack_planar.argtypes = [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_longlong, c_int, c_void_p]
     lib.csr_sparse_count.argtypes = [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]
     lib.csr_sparse_fill.argtypes = [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_longlong, c_void_p]
+    lib.csr_flag_mean.argtypes = [c_void_p, c_int, c_int, c_void_p, c_float, c_void_p, c_void_p, c_void_p]
+    lib.csr_flag_hampel.argtypes = [c_void_p, c_int, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p]
+    lib.csr_galactic_rm_image.argtypes = [c_void_p, c_void_p, c_int, c_int, POINTER(Wcs), c_int, c_int, c_int, c_int, c_void_p,
+                                          c_void_p, c_void_p]
+    lib.csr_healpix_lookup.argtypes = [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p,
+                                       c_void_p, c_void_p]
     for fn in (lib.csr_nudft_forward, lib.csr_nudft_adjoint):
         fn.argtypes = [POINTER(NuSampling), c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]
     lib.csr_fista_nu_ws_bytes.argtypes = [POINTER(NuSampling), c_void_p, c_int]

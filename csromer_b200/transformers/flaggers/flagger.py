@@ -63,3 +63,37 @@ class Flagger(metaclass=ABCMeta):
         else:
             ds.w[outliers] = 0.0
         print("Flagging {0:.2f}% of the data".format(100.0 * flagged / total))
+
+
+def device_flag(sigma, weights, kind, nsigma, mean_sigma=None, window=None):
+    """Per-pixel flagging on the GPU (csrc/flag.cu).  ``sigma`` ``(m, *pix)`` host array or CUDA tensor, ``weights`` like it
+    (or ``(m,)``, broadcast); returns (new weights as a float32 array / tensor of sigma's shape, boolean outlier mask of the
+    same type).  ``kind``: "mean" (MeanFlagger) or "hampel" (HampelFlagger, ``window`` channels)."""
+    import torch
+
+    from ... import _device as dv
+    from ... import _lib
+    lib = _lib.load()
+    on_device = dv.is_torch(sigma) and sigma.is_cuda
+    m = sigma.shape[0]
+    pix = tuple(sigma.shape[1:])
+    sig, _ = dv.pack_real(sigma, m, m)                                           # [P, m]
+    P = sig.shape[0]
+    marks = torch.ones_like(sig)                                                 # the kernel zeroes the outlier channels
+    if kind == "mean":
+        center = None if mean_sigma is None else dv.per_pixel_vector(mean_sigma, P, sig.device, "mean_sigma")
+        _lib.check(lib.csr_flag_mean(dv.tptr(sig), P, m, dv.tptr(center), float(nsigma), dv.tptr(marks), None, dv.stream_ptr()),
+                   "csr_flag_mean")
+    elif kind == "hampel":
+        _lib.check(lib.csr_flag_hampel(dv.tptr(sig), P, m, int(window), float(nsigma), dv.tptr(marks), None, dv.stream_ptr()),
+                   "csr_flag_hampel")
+    else:
+        raise ValueError("kind must be 'mean' or 'hampel'")
+    out_mask = dv.unpack_real(marks, m, pix, like_torch=True) == 0
+    w_t = dv.to_device(weights).to(torch.float32)
+    if w_t.dim() == 1:
+        w_t = w_t.reshape((m,) + (1,) * len(pix)).expand((m,) + pix)
+    new_w = torch.where(out_mask, torch.zeros((), device=w_t.device), w_t.reshape((m,) + pix))
+    if on_device:
+        return new_w, out_mask
+    return new_w.cpu().numpy(), out_mask.cpu().numpy()

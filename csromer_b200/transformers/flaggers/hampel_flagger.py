@@ -40,8 +40,21 @@ class HampelFlagger(Flagger):
         if self.w is None:
             raise ValueError("HampelFlagger needs the window length w")
         sigma = np.array(self.dataset.sigma, dtype=np.float64, copy=True)
-        if sigma.ndim != 1:
-            raise ValueError("HampelFlagger works on a single line of sight (shared sigma)")
+        if sigma.ndim != 1:  # batch extension: every pixel its own decision, weights zeroed (csr_flag_hampel / NumPy)
+            if self.imputation:
+                raise ValueError("imputation works on a single line of sight (shared sigma)")
+            import torch
+            if torch.cuda.is_available():
+                from .flagger import device_flag
+                mask = device_flag(sigma, np.ones(sigma.shape[0]), "hampel", nsigma, window=self.w)[1]
+            else:
+                flat = sigma.reshape(sigma.shape[0], -1)
+                mask = np.zeros(flat.shape, dtype=bool)
+                for p in range(flat.shape[1]):
+                    mask[hampel(flat[:, p], self.w, nsigma, False)[1], p] = True
+                mask = mask.reshape(sigma.shape)
+            self._apply(None, mask, sigma)
+            return ~mask, mask
         if self.imputation:
             new_sigma, keep, outliers = hampel(sigma, self.w, nsigma, True)
             self.dataset.sigma = new_sigma

@@ -29,7 +29,15 @@ class MeanFlagger(Flagger):
             keep, outliers = normal_flagging(sigma, mean_sigma, nsigma)
             self._apply(keep, outliers, sigma)
             return keep, outliers
-        center = sigma.mean(axis=0) if mean_sigma is None else np.asarray(mean_sigma)
-        mask = sigma > center + nsigma * sigma.std(axis=0) / np.sqrt(sigma.shape[0])
+        mask = self._per_pixel_mask(sigma, mean_sigma, nsigma)
         self._apply(None, mask, sigma)
         return ~mask, mask
+
+    def _per_pixel_mask(self, sigma, mean_sigma, nsigma):
+        """outlier mask of a per-pixel sigma ``(m, *pix)``: on the GPU when there is one (csr_flag_mean), NumPy otherwise"""
+        import torch
+        if torch.cuda.is_available():
+            from .flagger import device_flag
+            return device_flag(sigma, np.ones(sigma.shape[0]), "mean", nsigma, mean_sigma=mean_sigma)[1]
+        center = sigma.mean(axis=0) if mean_sigma is None else np.asarray(mean_sigma)
+        return sigma > center + nsigma * sigma.std(axis=0) / np.sqrt(sigma.shape[0])

@@ -202,6 +202,32 @@ int csr_pack_planar(const float* a, const float* b, long long chan_stride, int p
 int csr_unpack_planar(const float* in, int ld, int L, int P, float* a, float* b, long long chan_stride, int pix_stride,
                       void* stream);
 
+/* ---- per-pixel channel flagging: sigma [P, m] -> the weights w [P, m] of the outlier channels
+ * are zeroed in place (the per-pixel masks csr_fista consumes with w_per_pixel = 1); flagged [P] (optional) counts them.
+ * csr_flag_mean  : transformers/flaggers/mean_flagger.py:10-46 -- outlier <=> sigma > center + nsigma std / sqrt(m), center =
+ *                  mean(sigma) of the line of sight or mean_sigma[p] when given
+ * csr_flag_hampel: transformers/flaggers/hampel_flagger.py:9-21 -- |sigma - median(smooth)| > nsigma 1.4826 MAD(smooth),
+ *                  smooth = moving average over `window` channels ("valid" part); m - window + 1 <= 8192 */
+int csr_flag_mean(const float* sigma, int P, int m, const float* mean_sigma, float nsigma, float* w, int* flagged, void* stream);
+int csr_flag_hampel(const float* sigma, int P, int m, int window, float nsigma, float* w, int* flagged, void* stream);
+
+/* ---- Galactic rotation-measure foreground of an image (faraday_sky/faraday_sky.py:62-141):
+ * pixel -> sky (zenithal TAN / SIN WCS) -> Galactic -> HEALPix (RING or NESTED) -> Faraday-sky map value (nearest pixel).
+ * rm_mean / rm_std [ny, nx] are the per-pixel phi_gal csr_derotate removes.  wcs: degrees, FITS 1-based CRPIX, CD matrix
+ * (= CDELT x PC); proj 0 = TAN, 1 = SIN; lonpole normally 180.  swap_axes = 1 reproduces the reference's argument order
+ * (array_index_to_world(xx, yy): element [r, c] is evaluated at pixel x = r, y = c); galactic_frame = 1: the WCS is
+ * already in Galactic coordinates (GLON / GLAT).
+ * csr_healpix_lookup: the same gather for n explicit positions (radians; icrs = 1: right ascension / declination,
+ * 0: Galactic l / b) -- FaradaySky.galactic_rm (faraday_sky.py:62-97); out_pix (optional) receives the HEALPix indices. */
+typedef struct {
+    double crval1, crval2, crpix1, crpix2, cd11, cd12, cd21, cd22, lonpole;
+    int proj;
+} csr_wcs;
+int csr_galactic_rm_image(const float* map_mean, const float* map_std, int nside, int nested, const csr_wcs* wcs, int nx, int ny,
+                          int swap_axes, int galactic_frame, float* rm_mean, float* rm_std, void* stream);
+int csr_healpix_lookup(const float* map_mean, const float* map_std, int nside, int nested, const double* lon, const double* lat,
+                       int icrs, int n, float* out_mean, float* out_std, long long* out_pix, void* stream);
+
 /* ---- compressed-row read-back of the L1 solution (README.md:374-384 writes it into dense planes; > 99 % of it is
  * zero after the soft threshold of objectivefunction/priors/l1.py:30-32) -------------------------------------------
  * csr_sparse_count: counts[p] = number of non-zeros among x[p, 0 .. ncols)

@@ -530,3 +530,99 @@ def cube_recipe(data, nu, sigma, spectral_idx=0.0, eta=1.0, wavelet="coif2", ove
         info["rm_restored"][p] = phi[np.argmax(np.abs(restored))]
         info["rm_restored_interpolated"][p], info["peak_restored"][p] = peak_parabola(restored, grid["cellsize"])
     return F, info
+
+
+# ----------------------------------------------------------------------------------------------------------
+# Galactic RM foreground of an image (faraday_sky/faraday_sky.py:62-141).  astropy.wcs, astropy.coordinates and
+# astropy_healpix are third-party packages absent here: PARITY UNPINNED against them; the chain below restates the
+# published algorithms (FITS WCS papers I / II; IAU 1958 Galactic pole in J2000; Gorski et al. 2005 HEALPix) and is
+# pinned by HEALPix known answers and the pix2ang round trip (tests/test_oracle_sky.py).
+# ----------------------------------------------------------------------------------------------------------
+def healpix_ang2pix_ring(nside, theta, phi):
+    """HEALPix RING index of colatitude theta / longitude phi (radians)"""
+    theta, phi = np.asarray(theta, dtype=np.float64), np.asarray(phi, dtype=np.float64)
+    z = np.cos(theta)
+    za = np.abs(z)
+    tt = np.mod(phi, 2 * np.pi) / (0.5 * np.pi)
+    ns = int(nside)
+    npix = 12 * ns * ns
+    # equatorial belt
+    t1, t2 = ns * (0.5 + tt), ns * z * 0.75
+    jp, jm = np.floor(t1 - t2).astype(np.int64), np.floor(t1 + t2).astype(np.int64)
+    ir = ns + 1 + jp - jm
+    kshift = 1 - (ir & 1)
+    ip = np.mod((jp + jm - ns + kshift + 1) // 2, 4 * ns)
+    eq = 2 * ns * (ns - 1) + (ir - 1) * 4 * ns + ip
+    # polar caps
+    tp = tt - np.floor(tt)
+    tmp = ns * np.sqrt(3.0 * (1.0 - za))
+    jp2, jm2 = np.floor(tp * tmp).astype(np.int64), np.floor((1.0 - tp) * tmp).astype(np.int64)
+    ir2 = jp2 + jm2 + 1
+    ip2 = np.mod(np.floor(tt * ir2).astype(np.int64), 4 * ir2)
+    cap = np.where(z > 0, 2 * ir2 * (ir2 - 1) + ip2, npix - 2 * ir2 * (ir2 + 1) + ip2)
+    return np.where(za <= 2.0 / 3.0, eq, cap)
+
+
+def healpix_pix2ang_ring(nside, pix):
+    """centre (theta, phi) of RING pixel `pix` -- the independent inverse used to pin ang2pix"""
+    ns = int(nside)
+    pix = np.asarray(pix, dtype=np.int64)
+    npix, ncap = 12 * ns * ns, 2 * ns * (ns - 1)
+    theta, phi = np.zeros(pix.shape), np.zeros(pix.shape)
+    north = pix < ncap
+    iring = ((1 + np.sqrt(1 + 2 * pix[north].astype(np.float64))) / 2).astype(np.int64)   # counted from the north pole
+    iphi = pix[north] + 1 - 2 * iring * (iring - 1)
+    theta[north] = np.arccos(1.0 - iring ** 2 / (3.0 * ns * ns))
+    phi[north] = (iphi - 0.5) * np.pi / (2.0 * iring)
+    eq = (pix >= ncap) & (pix < npix - ncap)
+    ip = pix[eq] - ncap
+    iring = ip // (4 * ns) + ns
+    iphi = ip % (4 * ns) + 1
+    fodd = 0.5 * (1 + ((iring + ns) & 1))
+    theta[eq] = np.arccos((2 * ns - iring) * 2.0 / (3.0 * ns))
+    phi[eq] = (iphi - fodd) * np.pi / (2.0 * ns)
+    south = pix >= npix - ncap
+    ip = npix - pix[south]
+    iring = ((1 + np.sqrt(2 * ip.astype(np.float64) - 1)) / 2).astype(np.int64)            # counted from the south pole
+    iphi = 4 * iring + 1 - (ip - 2 * iring * (iring - 1))
+    theta[south] = np.arccos(-1.0 + iring ** 2 / (3.0 * ns * ns))
+    phi[south] = (iphi - 0.5) * np.pi / (2.0 * iring)
+    return theta, phi
+
+
+def icrs_to_galactic(ra, dec):
+    """(l, b) in radians from right ascension / declination (J2000 pole 192.85948, 27.12825 deg; l_NCP = 122.93192 deg)"""
+    ra_ngp, dec_ngp, l_ncp = np.radians(192.85948), np.radians(27.12825), np.radians(122.93192)
+    b = np.arcsin(np.clip(np.sin(dec) * np.sin(dec_ngp) + np.cos(dec) * np.cos(dec_ngp) * np.cos(ra - ra_ngp), -1, 1))
+    l = l_ncp - np.arctan2(np.cos(dec) * np.sin(ra - ra_ngp),
+                           np.sin(dec) * np.cos(dec_ngp) - np.cos(dec) * np.sin(dec_ngp) * np.cos(ra - ra_ngp))
+    return np.mod(l, 2 * np.pi), b
+
+
+def wcs_pixel_to_sky(x, y, crval, crpix, cd, proj="TAN", lonpole=180.0):
+    """0-based pixel (x, y) -> (ra, dec) radians for a zenithal TAN / SIN WCS (FITS WCS paper II, eqs. 2, 54-59)"""
+    px, py = np.asarray(x, dtype=np.float64) + 1.0 - crpix[0], np.asarray(y, dtype=np.float64) + 1.0 - crpix[1]
+    xi = np.radians(cd[0][0] * px + cd[0][1] * py)
+    eta = np.radians(cd[1][0] * px + cd[1][1] * py)
+    rr = np.hypot(xi, eta)
+    phi = np.where(rr > 0, np.arctan2(xi, -eta), 0.0)
+    theta = np.arccos(np.minimum(rr, 1.0)) if proj == "SIN" else np.arctan2(1.0, rr)
+    a0, d0, dp = np.radians(crval[0]), np.radians(crval[1]), phi - np.radians(lonpole)
+    dec = np.arcsin(np.clip(np.sin(theta) * np.sin(d0) + np.cos(theta) * np.cos(d0) * np.cos(dp), -1, 1))
+    ra = a0 + np.arctan2(-np.cos(theta) * np.sin(dp), np.sin(theta) * np.cos(d0) - np.cos(theta) * np.sin(d0) * np.cos(dp))
+    return ra, dec
+
+
+def galactic_rm_image(sky_mean, sky_std, nside, header, swap_axes=False):
+    """faraday_sky.py:99-141 (nearest HEALPix pixel, RING): -> (rm_mean [NAXIS2, NAXIS1], rm_std)"""
+    nx, ny = int(header["NAXIS1"]), int(header["NAXIS2"])
+    cd = [[header.get("CD1_1", header.get("CDELT1", 1.0)), header.get("CD1_2", 0.0)],
+          [header.get("CD2_1", 0.0), header.get("CD2_2", header.get("CDELT2", 1.0))]]
+    proj = "SIN" if str(header.get("CTYPE1", "RA---TAN")).endswith("SIN") else "TAN"
+    cc, rr = np.meshgrid(np.arange(nx), np.arange(ny))
+    x, y = (rr, cc) if swap_axes else (cc, rr)
+    ra, dec = wcs_pixel_to_sky(x, y, (header["CRVAL1"], header["CRVAL2"]), (header["CRPIX1"], header["CRPIX2"]), cd, proj,
+                               header.get("LONPOLE", 180.0))
+    l, b = icrs_to_galactic(ra, dec)
+    pix = healpix_ang2pix_ring(nside, 0.5 * np.pi - b, l)
+    return np.asarray(sky_mean)[pix], np.asarray(sky_std)[pix]

@@ -10,6 +10,8 @@ import numpy as np
 import pytest
 from conftest import golden
 
+from oracle import restatement as ob
+
 import csromer_b200 as cs
 from csromer_b200.io import fits_lite
 from csromer_b200.transformers.flaggers import hampel, median_absolute_deviation
@@ -229,3 +231,102 @@ def test_device_cube_transposes_and_channel_statistics():
     got = out.cpu().numpy()
     np.testing.assert_array_equal(got[0].reshape(n, -1), F[:, :n].T)
     np.testing.assert_array_equal(got[1].reshape(n, -1), F[:, n:2 * n].T)
+
+
+# ---- device flaggers and the Galactic RM foreground ---------------------------------
+@pytest.mark.gpu
+def test_device_flaggers_match_the_reference_per_pixel():
+    """csr_flag_mean / csr_flag_hampel on a [P, m] sigma: every row that carries the golden sigma array reproduces the
+    reference's own outlier lists (tests/golden/next_rows.npz), random rows reproduce the host mirrors of the reference
+    functions, and MeanFlagger / HampelFlagger use the kernels for per-pixel sigma."""
+    import torch
+
+    import csromer_b200 as cs
+    from csromer_b200.transformers.flaggers.flagger import device_flag
+    from csromer_b200.transformers.flaggers.hampel_flagger import hampel
+    from csromer_b200.transformers.flaggers.mean_flagger import normal_flagging
+    g = golden("next_rows")
+    sigma = g["sigma"]
+    m, P = sigma.shape[0], 37
+    rng = np.random.RandomState(9)
+    sig = np.repeat(sigma[:, None], P, axis=1)
+    sig[:, 1::2] = 0.001 * (1.0 + 0.2 * rng.uniform(size=(m, P // 2)))      # odd pixels: their own noise levels
+    sig[rng.randint(0, m, 40), rng.randint(0, P // 2, 40) * 2 + 1] *= 5.0
+    for nsig, key in ((0.0, "mean_ns0_w_outliers"), (5.0, "mean_ns5_w_outliers")):
+        w, mask = device_flag(sig, np.ones(m), "mean", nsig)
+        for p in range(P):
+            expect = g[key] if p % 2 == 0 else normal_flagging(sig[:, p], None, nsig)[1]
+            np.testing.assert_array_equal(np.nonzero(mask[:, p])[0], expect)
+            assert (w[mask[:, p], p] == 0).all() and (w[~mask[:, p], p] == 1).all()
+    w, mask = device_flag(sig, np.ones(m), "hampel", 3.0, window=9)
+    for p in range(P):
+        expect = g["hampel_outliers"] if p % 2 == 0 else hampel(sig[:, p], 9, 3.0, False)[1]
+        np.testing.assert_array_equal(np.nonzero(mask[:, p])[0], expect)
+    # through the classes (zero-weighting of a per-pixel dataset), CUDA tensors stay on the device
+    ds = cs.Dataset(nu=g["nu"], sigma=sig, spectral_idx=0.7)
+    keep, out = cs.MeanFlagger(dataset=ds, nsigma=5.0).run()
+    np.testing.assert_array_equal(np.nonzero(out[:, 0])[0], g["mean_ns5_w_outliers"])
+    assert (ds.w[out] == 0).all() and (ds.w[~out] > 0).all()
+    ds = cs.Dataset(nu=g["nu"], sigma=sig, spectral_idx=0.7)
+    keep, out = cs.HampelFlagger(dataset=ds, nsigma=3.0, w=9).run()
+    np.testing.assert_array_equal(np.nonzero(out[:, 0])[0], g["hampel_outliers"])
+    wt, mt = device_flag(torch.as_tensor(sig, dtype=torch.float32).cuda(), torch.ones(m).cuda(), "mean", 5.0)
+    assert wt.is_cuda and mt.is_cuda and bool((mt.cpu().numpy() == device_flag(sig, np.ones(m), "mean", 5.0)[1]).all())
+
+
+@pytest.mark.gpu
+def test_galactic_rm_image_and_derotation():
+    """FaradaySky on a synthetic HEALPix map (value = pixel index: the gathered map IS the index chain): image lookup
+    against the oracle's restatement, both orderings, the reference's transposed argument order, position lookup, and the
+    result feeding Dataset.subtract_galacticrm's device twin."""
+    import csromer_b200 as cs
+    from csromer_b200 import _device as dv
+    nside = 64
+    npix = 12 * nside * nside
+    sky = cs.FaradaySky(data=(np.arange(npix, dtype=np.float32), 0.5 * np.arange(npix, dtype=np.float32)))
+    assert sky.nside == nside and sky.ordering == "ring"
+    for ctype, crval in (("RA---SIN", (150.0, -30.0)), ("RA---TAN", (10.0, 62.0)), ("RA---TAN", (266.4, -28.9))):
+        header = {"NAXIS1": 40, "NAXIS2": 28, "CRVAL1": crval[0], "CRVAL2": crval[1], "CRPIX1": 20.5, "CRPIX2": 14.0,
+                  "CDELT1": -0.25, "CDELT2": 0.25, "CTYPE1": ctype, "CTYPE2": ctype.replace("RA--", "DEC-"), "RADESYS": "ICRS"}
+        mean, std = sky.galactic_rm_image(header)
+        ref_mean, ref_std = ob.galactic_rm_image(np.arange(npix), 0.5 * np.arange(npix), nside, header)
+        assert mean.shape == (28, 40)
+        np.testing.assert_array_equal(mean.astype(np.int64), ref_mean)
+        np.testing.assert_array_equal(std, 0.5 * ref_mean)
+        assert len(np.unique(mean)) > 30            # the 10 x 7 degree field really crosses many map pixels
+    square = dict(header, NAXIS1=28)
+    swapped, _ = sky.galactic_rm_image(square, reference_axis_order=True)
+    np.testing.assert_array_equal(swapped, sky.galactic_rm_image(square)[0].T)
+    # positions: pixel centres map to themselves, in both frames and both orderings
+    pix = np.random.RandomState(2).randint(0, npix, 500)
+    theta, phi = ob.healpix_pix2ang_ring(nside, pix)
+    got, _ = sky.galactic_rm(ra=phi, dec=0.5 * np.pi - theta, frame="galactic")
+    np.testing.assert_array_equal(got.astype(np.int64), pix)
+    ra = np.radians(np.array([192.85948, 266.40499])), np.radians(np.array([27.12825, -28.93617]))
+    l, b = ob.icrs_to_galactic(*ra)
+    got, _ = sky.galactic_rm(ra=ra[0], dec=ra[1], frame="icrs")
+    np.testing.assert_array_equal(got.astype(np.int64), ob.healpix_ang2pix_ring(nside, 0.5 * np.pi - b, l))
+    # NESTED: the same sky position must land in the pixel whose nested index corresponds to the ring one
+    lib = cs._lib.load()
+    import torch
+    lon, lat = torch.as_tensor(phi).cuda(), torch.as_tensor(0.5 * np.pi - theta).cuda()
+    pr, pn = torch.empty(500, dtype=torch.int64).cuda(), torch.empty(500, dtype=torch.int64).cuda()
+    for nested, out in ((0, pr), (1, pn)):
+        cs._lib.check(lib.csr_healpix_lookup(None, None, nside, nested, dv.tptr(lon), dv.tptr(lat), 0, 500, None, None, dv.tptr(out),
+                                             dv.stream_ptr()), "csr_healpix_lookup")
+    np.testing.assert_array_equal(pr.cpu().numpy(), pix)
+    pn = pn.cpu().numpy()
+    assert len(np.unique(pn)) == len(np.unique(pix)) and (pn // (nside * nside) < 12).all()
+    north = np.cos(theta) > 2 / 3
+    assert (pn[north] // (nside * nside) < 4).all() and (pn[np.cos(theta) < -2 / 3] // (nside * nside) >= 8).all()
+    # the per-pixel foreground feeds the de-rotation (base/dataset.py:377-381)
+    nu = np.linspace(1.0e9, 2.0e9, 64)
+    header = {"NAXIS1": 6, "NAXIS2": 5, "CRVAL1": 150.0, "CRVAL2": -30.0, "CRPIX1": 3.0, "CRPIX2": 3.0, "CDELT1": -2.0,
+              "CDELT2": 2.0, "CTYPE1": "RA---SIN"}
+    small = cs.FaradaySky(data=(np.random.RandomState(3).normal(0, 30, npix).astype(np.float32), np.ones(npix, np.float32)))
+    rm, _ = small.galactic_rm_image(header)
+    src = cs.FaradayThinSource(nu=nu, s_nu=1.0, phi_gal=rm.reshape(-1).astype(np.float64), spectral_idx=0.0)
+    src.simulate()
+    before = np.asarray(src.data).copy()
+    src.subtract_galacticrm(rm.reshape(-1))
+    assert np.abs(np.asarray(src.data) - 1.0).max() < 1e-6 and np.abs(before - 1.0).max() > 0.5
