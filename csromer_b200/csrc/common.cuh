@@ -312,6 +312,7 @@ struct Options {
     int rescale;      // operand scales of z and r follow the row maxima (fp16 headroom in diverging runs)
     int pair3;        // three-product transforms on CTA pairs (cta_group::2, M = 256; each SM stages half of the B tile)
     int tma_epi;      // ... with the residual epilogue staged through shared memory (TMA loads of b, TMA stores of r)
+    int nufft;        // per-line-of-sight samplings: shared-memory NUFFT (nufft.cu) instead of the direct sums (nudft.cu)
 };
 Options& options();
 

@@ -199,8 +199,21 @@ static int check_grid(const csr_nu_sampling* s, int P, NuGrid* g) {
     return CSR_OK;
 }
 
+// the NUFFT path (nufft.cu): O(Nf log Nf) per line of sight in shared memory, used when the grid fits (n <= 8192) and the
+// option `nufft` is on; ~1e-6 of the result's scale away from these exact sums
+int nufft_grid_size(int n, int* logNf);
+int launch_nufft_forward(const double* a, int ldl, const int* m_count, int m, int n, double phi0, double dphi, const float* x, int ldx,
+                         const float* chan_scale, const float* row_scale, const float* sub, float* out, int ld_out, int P,
+                         cudaStream_t stream);
+int launch_nufft_adjoint(const double* a, int ldl, const int* m_count, int m, int n, double phi0, double dphi, const float* b, int ldb,
+                         const float* chan_scale, const float* row_scale, float* out, int ld_out, int P, cudaStream_t stream);
+static bool use_nufft(const NuGrid& g) { return options().nufft != 0 && nufft_grid_size(g.n, nullptr) > 0; }
+
 int launch_nudft_forward(const NuGrid& g, const float* x, int ldx, const float* chan_scale, const float* row_scale,
                          const float* sub, float* out, int ld_out, int P, cudaStream_t stream) {
+    if (use_nufft(g))
+        return launch_nufft_forward(g.a, g.ldl, g.m_count, g.m, g.n, g.phi0, g.dphi, x, ldx, chan_scale, row_scale, sub, out, ld_out, P,
+                                    stream);
     dim3 grid((g.m + NU_FWD_THREADS - 1) / NU_FWD_THREADS, P);
     nudft_forward_kernel<<<grid, NU_FWD_THREADS, 0, stream>>>(g, x, ldx, chan_scale, row_scale, sub, out, ld_out);
     CSR_LAUNCHED();
@@ -208,6 +221,8 @@ int launch_nudft_forward(const NuGrid& g, const float* x, int ldx, const float* 
 }
 int launch_nudft_adjoint(const NuGrid& g, const float* b, int ldb, const float* chan_scale, const float* row_scale,
                          float* out, int ld_out, int P, cudaStream_t stream) {
+    if (use_nufft(g))
+        return launch_nufft_adjoint(g.a, g.ldl, g.m_count, g.m, g.n, g.phi0, g.dphi, b, ldb, chan_scale, row_scale, out, ld_out, P, stream);
     dim3 grid((g.n + NU_ADJ_THREADS * NU_JB - 1) / (NU_ADJ_THREADS * NU_JB), P);
     nudft_adjoint_kernel<<<grid, NU_ADJ_THREADS, 0, stream>>>(g, b, ldb, chan_scale, row_scale, out, ld_out);
     CSR_LAUNCHED();

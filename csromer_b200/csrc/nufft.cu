@@ -1,0 +1,391 @@
+// nufft.cu -- K4n: the per-line-of-sight lambda^2 <-> phi transform as a non-uniform FFT, one CTA per line of sight,
+// everything between the global loads and stores in shared memory.
+//
+// Replaces the role pynufft plays in transformers/dfts/nufft.py:36-75 (plan, FFT, interpolate) for samplings that differ
+// from pixel to pixel, where no twiddle matrix can be shared (nudft.cu evaluates the same sums directly, O(m n), FP32-pipe
+// bound).  On the uniform grid phi_j = phi_c + j' dphi (j' = j - n/2) the operator is a trigonometric polynomial at the
+// non-uniform frequencies omega_i = 2 a_i dphi, a_i = lambda2_i - l2_ref:
+//   forward (type 2)  y_i = c_i sum_j' x_j' exp(+i omega_i j'),   adjoint (type 1)  F_j' = sum_i conj(c_i) b_i exp(-i omega_i j'),
+//   c_i = exp(2i a_i phi_c).
+// NUFFT with the "exponential of semicircle" kernel psi(t) = exp(beta (sqrt(1 - (2t/W)^2) - 1)), W taps, on a grid of
+// Nf = 2^q >= 2n points (Barnett, Magland & af Klinteberg 2019):
+//   type 2: u_j' = x_j' / psihat(j') -> FFT (+) of the zero-padded Nf-vector -> y_i = c_i sum_l U_{k0+l} psi(kappa_i - k0 - l)
+//   type 1: G_k = sum_i conj(c_i) b_i psi(kappa_i - k) -> FFT (-) -> F_j' = g_j' / psihat(j'),     kappa_i = omega_i Nf / 2 pi,
+// the exact adjoint of type 2 (same kernel, same grid), so FISTA sees a consistent operator pair.  W = 8, beta = 2.30 W
+// gives ~1e-7 aliasing error; the fp32 FFT (q <= 14 stages) leaves ~1e-6 of the result's scale -- inside the stated
+// 1e-5 transform tolerance, and checked against the exact kernels (tests/test_gpu_parity.py).
+//
+// Data movement: one line of sight reads 8 n + 8 m and writes 8 m (or 8 n) bytes of HBM per transform as 16-byte / fully
+// coalesced row accesses; the Nf-point complex FFT (128 KiB at n = 7968) never leaves shared memory: radix-2 butterflies
+// in place, decimation in frequency for type 2 (natural-order input, outputs addressed bit-reversed by the
+// interpolation) and decimation in time for type 1 (the spreading writes bit-reversed, the cropped output is natural), so
+// no separate permutation pass exists; twiddles come from a 64 KiB table built once per CTA.  Cost per line of sight:
+// 5 Nf log2 Nf = 1.1 MFLOP instead of 8 m n = 64 MFLOP.  Needs Nf <= 16384 (n <= 8192); longer grids stay on nudft.cu.
+#include <math.h>
+
+#include "plan.cuh"
+
+namespace csr {
+
+bool profile_start(cudaStream_t stream, cudaEvent_t* start, cudaEvent_t* stop);
+void profile_stop(int kind, cudaStream_t stream, cudaEvent_t start, cudaEvent_t stop);
+
+constexpr int NF_THREADS = 512;
+constexpr int NF_MAX = 16384;
+
+struct NufftGrid {
+    const double* a;     // [P, ldl]  lambda2 - l2_ref
+    int ldl;
+    const int* m_count;  // [P] or null
+    int m, n, Nf, logNf, W;
+    float beta;
+    double phic, dphi;    // phi of the centre cell j = n/2, cell size
+    const float* deconv;  // [n] 1 / psihat(j - n/2)
+};
+
+__device__ __forceinline__ float es_kernel(float t, float inv_half_w, float beta) {
+    const float u = t * inv_half_w, s = 1.f - u * u;
+    return s > 0.f ? expf(beta * (sqrtf(s) - 1.f)) : 0.f;
+}
+__device__ __forceinline__ float2 cmulf(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+__device__ __forceinline__ int brev(int i, int logn) { return (int)(__brev((unsigned)i) >> (32 - logn)); }
+// Skewed slot of twiddle k: a stage reads the table with a power-of-two stride (2^(logn - s) entries), which would put a
+// warp's 32 reads into one bank; one pad entry per 16, 256 and 4096 entries spreads every such stride over the banks.
+__host__ __device__ __forceinline__ int tw_slot(int k) { return k + (k >> 4) + (k >> 8) + (k >> 12); }
+
+// in-place FFT over d[0 .. N), N = 2^logn, tw[k] = exp(+2 pi i k / N) for k < N / 2 (skewed slots).  Two radix-2 stages
+// are fused into one radix-4 pass over registers (four loads, four stores and two twiddle loads per four points and two
+// stages: half the shared-memory traffic of radix-2, which is what bounds the transform); an odd logn starts / ends with
+// one radix-2 stage.
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ float2 mul_i(float2 a) { return make_float2(-a.y, a.x); }    // a * i
+__device__ __forceinline__ float2 mul_mi(float2 a) { return make_float2(a.y, -a.x); }   // a * (-i)
+
+// DIF: natural-order input -> bit-reversed output, exponent sign +
+__device__ __forceinline__ void fft_dif_plus(float2* d, const float2* tw, int logn) {
+    const int n = 1 << logn;
+    int s = logn;
+    if (logn & 1) {  // one radix-2 stage first
+        const int half = 1 << (s - 1);
+        for (int b = threadIdx.x; b < (n >> 1); b += NF_THREADS) {
+            const int pos = b & (half - 1), i0 = ((b >> (s - 1)) << s) + pos, i1 = i0 + half;
+            const float2 u = d[i0], v = d[i1], w = tw[tw_slot(pos << (logn - s))];
+            d[i0] = cadd(u, v);
+            d[i1] = cmulf(csub(u, v), w);
+        }
+        __syncthreads();
+        --s;
+    }
+    for (; s >= 2; s -= 2) {  // stages s and s - 1: blocks of 4 q points, q = 2^(s-2)
+        const int q = 1 << (s - 2);
+        for (int b = threadIdx.x; b < (n >> 2); b += NF_THREADS) {
+            const int pos = b & (q - 1), i0 = ((b >> (s - 2)) << s) + pos;
+            const float2 a0 = d[i0], a1 = d[i0 + q], a2 = d[i0 + 2 * q], a3 = d[i0 + 3 * q];
+            const float2 ws = tw[tw_slot(pos << (logn - s))];          // W_s^pos; W_s^(pos+q) = i W_s^pos
+            const float2 wt = tw[tw_slot(pos << (logn - s + 1))];      // W_(s-1)^pos
+            const float2 b0 = cadd(a0, a2), b2 = cmulf(csub(a0, a2), ws);
+            const float2 b1 = cadd(a1, a3), b3 = mul_i(cmulf(csub(a1, a3), ws));
+            d[i0] = cadd(b0, b1);
+            d[i0 + q] = cmulf(csub(b0, b1), wt);
+            d[i0 + 2 * q] = cadd(b2, b3);
+            d[i0 + 3 * q] = cmulf(csub(b2, b3), wt);
+        }
+        __syncthreads();
+    }
+}
+// DIT: bit-reversed input -> natural-order output, exponent sign -
+__device__ __forceinline__ void fft_dit_minus(float2* d, const float2* tw, int logn) {
+    const int n = 1 << logn;
+    int s = 1;
+    for (; s + 1 <= logn; s += 2) {  // stages s and s + 1: blocks of 4 q points, q = 2^(s-1)
+        const int q = 1 << (s - 1);
+        for (int b = threadIdx.x; b < (n >> 2); b += NF_THREADS) {
+            const int pos = b & (q - 1), i0 = ((b >> (s - 1)) << (s + 1)) + pos;
+            const float2 a0 = d[i0], a1 = d[i0 + q], a2 = d[i0 + 2 * q], a3 = d[i0 + 3 * q];
+            float2 w1 = tw[tw_slot(pos << (logn - s))];                // conj(W_s^pos)
+            float2 w2 = tw[tw_slot(pos << (logn - s - 1))];            // conj(W_(s+1)^pos); conj(W_(s+1)^(pos+q)) = -i times it
+            w1.y = -w1.y;
+            w2.y = -w2.y;
+            const float2 t1 = cmulf(a1, w1), t3 = cmulf(a3, w1);
+            const float2 b0 = cadd(a0, t1), b1 = csub(a0, t1), b2 = cadd(a2, t3), b3 = csub(a2, t3);
+            const float2 u2 = cmulf(b2, w2), u3 = mul_mi(cmulf(b3, w2));
+            d[i0] = cadd(b0, u2);
+            d[i0 + 2 * q] = csub(b0, u2);
+            d[i0 + q] = cadd(b1, u3);
+            d[i0 + 3 * q] = csub(b1, u3);
+        }
+        __syncthreads();
+    }
+    if (s == logn) {  // odd logn: the last radix-2 stage
+        const int half = 1 << (s - 1);
+        for (int b = threadIdx.x; b < (n >> 1); b += NF_THREADS) {
+            const int pos = b & (half - 1), i0 = ((b >> (s - 1)) << s) + pos, i1 = i0 + half;
+            float2 w = tw[tw_slot(pos << (logn - s))];
+            w.y = -w.y;
+            const float2 u = d[i0], v = cmulf(d[i1], w);
+            d[i0] = cadd(u, v);
+            d[i1] = csub(u, v);
+        }
+        __syncthreads();
+    }
+}
+
+__device__ __forceinline__ void build_twiddles(float2* tw, int Nf) {
+    for (int k = threadIdx.x; k < Nf / 2; k += NF_THREADS) {
+        float s, c;
+        sincospif(2.0f * (float)k / (float)Nf, &s, &c);  // (k / Nf is exact in fp32: both are small powers of two apart)
+        tw[tw_slot(k)] = make_float2(c, s);
+    }
+}
+
+// fractional grid position of channel i and its phase factor c_i
+__device__ __forceinline__ void channel_geometry(const NufftGrid& g, double a, double& kappa, float2& c) {
+    double t = a * g.dphi / 3.14159265358979323846;  // omega / 2 pi, in turns
+    t -= floor(t);
+    kappa = t * (double)g.Nf;
+    double pc = a * g.phic / 3.14159265358979323846;  // 2 a phi_c / 2 pi
+    pc -= rint(pc);
+    float s, cc;
+    sincospif(2.0f * (float)pc, &s, &cc);
+    c = make_float2(cc, s);
+}
+
+// out[p, i] = row_scale[p] chan_scale[p, i] y_i - sub[p, i]      (planar [Re | Im])
+__global__ void __launch_bounds__(NF_THREADS, 1)
+nufft_forward_kernel(NufftGrid g, const float* __restrict__ x, int ldx, const float* __restrict__ chan_scale,
+                     const float* __restrict__ row_scale, const float* __restrict__ sub, float* __restrict__ out, int ld_out, int P) {
+    extern __shared__ __align__(16) float2 nsm[];
+    float2* d = nsm;
+    float2* tw = nsm + g.Nf;
+    build_twiddles(tw, g.Nf);
+    const float inv_half_w = 2.f / (float)g.W;
+    const int half_n = g.n >> 1;
+    for (int p = blockIdx.x; p < P; p += gridDim.x) {
+        const float* xr = x + (size_t)p * ldx;
+        __syncthreads();  // (the previous line of sight has been read out; the twiddle table is complete)
+        // natural order: grid index k' <-> j' = k' (k' < Nf/2) or k' - Nf; phi cells j' in [-n/2, n - n/2)
+        for (int idx = threadIdx.x; idx < g.Nf; idx += NF_THREADS) {
+            const int jp = idx < (g.Nf >> 1) ? idx : idx - g.Nf;
+            const int j = jp + half_n;
+            float2 v = make_float2(0.f, 0.f);
+            if (j >= 0 && j < g.n) {
+                const float dc = __ldg(g.deconv + j);
+                v = make_float2(xr[j] * dc, xr[g.n + j] * dc);
+            }
+            d[idx] = v;
+        }
+        __syncthreads();
+        fft_dif_plus(d, tw, g.logNf);
+        const int mc = g.m_count ? min(g.m_count[p], g.m) : g.m;
+        const float rs = row_scale ? row_scale[p] : 1.f;
+        const double* ap = g.a + (size_t)p * g.ldl;
+        float* o = out + (size_t)p * ld_out;
+        for (int i = threadIdx.x; i < g.m; i += NF_THREADS) {
+            float2 y = make_float2(0.f, 0.f);
+            if (i < mc) {
+                double kappa;
+                float2 c;
+                channel_geometry(g, ap[i], kappa, c);
+                const int k0 = (int)ceil(kappa - 0.5 * (double)g.W);
+                float2 acc = make_float2(0.f, 0.f);
+                for (int l = 0; l < g.W; ++l) {
+                    const int k = k0 + l;
+                    const float wgt = es_kernel((float)(kappa - (double)k), inv_half_w, g.beta);
+                    const float2 u = d[brev(k & (g.Nf - 1), g.logNf)];
+                    acc.x = fmaf(wgt, u.x, acc.x);
+                    acc.y = fmaf(wgt, u.y, acc.y);
+                }
+                y = cmulf(acc, c);
+                const float cs = chan_scale ? chan_scale[(size_t)p * g.m + i] : 1.f;
+                y.x *= rs * cs;
+                y.y *= rs * cs;
+                if (sub) {
+                    y.x -= sub[(size_t)p * ld_out + i];
+                    y.y -= sub[(size_t)p * ld_out + g.m + i];
+                }
+            }
+            o[i] = y.x;
+            o[g.m + i] = y.y;
+        }
+    }
+}
+
+// out[p, j] = row_scale[p] sum_i chan_scale[p, i] b[p, i] exp(-2i a_i phi_j)
+__global__ void __launch_bounds__(NF_THREADS, 1)
+nufft_adjoint_kernel(NufftGrid g, const float* __restrict__ b, int ldb, const float* __restrict__ chan_scale,
+                     const float* __restrict__ row_scale, float* __restrict__ out, int ld_out, int P) {
+    extern __shared__ __align__(16) float2 nsm[];
+    float2* d = nsm;
+    float2* tw = nsm + g.Nf;
+    build_twiddles(tw, g.Nf);
+    const float inv_half_w = 2.f / (float)g.W;
+    const int half_n = g.n >> 1;
+    for (int p = blockIdx.x; p < P; p += gridDim.x) {
+        __syncthreads();
+        for (int idx = threadIdx.x; idx < g.Nf; idx += NF_THREADS) d[idx] = make_float2(0.f, 0.f);
+        __syncthreads();
+        const int mc = g.m_count ? min(g.m_count[p], g.m) : g.m;
+        const double* ap = g.a + (size_t)p * g.ldl;
+        const float* br = b + (size_t)p * ldb;
+        for (int i = threadIdx.x; i < mc; i += NF_THREADS) {
+            double kappa;
+            float2 c;
+            channel_geometry(g, ap[i], kappa, c);
+            const float cs = chan_scale ? chan_scale[(size_t)p * g.m + i] : 1.f;
+            const float2 v = cmulf(make_float2(br[i] * cs, br[g.m + i] * cs), make_float2(c.x, -c.y));
+            const int k0 = (int)ceil(kappa - 0.5 * (double)g.W);
+            for (int l = 0; l < g.W; ++l) {
+                const int k = k0 + l;
+                const float wgt = es_kernel((float)(kappa - (double)k), inv_half_w, g.beta);
+                float2* cell = d + brev(k & (g.Nf - 1), g.logNf);
+                atomicAdd(&cell->x, wgt * v.x);
+                atomicAdd(&cell->y, wgt * v.y);
+            }
+        }
+        __syncthreads();
+        fft_dit_minus(d, tw, g.logNf);
+        const float rs = row_scale ? row_scale[p] : 1.f;
+        float* o = out + (size_t)p * ld_out;
+        for (int j = threadIdx.x; j < g.n; j += NF_THREADS) {
+            const int jp = j - half_n;
+            const float2 v = d[jp & (g.Nf - 1)];
+            const float dc = __ldg(g.deconv + j) * rs;
+            o[j] = v.x * dc;
+            o[g.n + j] = v.y * dc;
+        }
+    }
+}
+
+// 1 / psihat(j') at xi = 2 pi j' / Nf:  psihat(xi) = int psi(t) cos(xi t) dt over |t| <= W/2; with t = (W/2) sin(theta) the
+// integrand is smooth, composite Simpson on 512 intervals is far below fp32 resolution
+__global__ void nufft_deconv_kernel(int n, int Nf, int W, double beta, float* __restrict__ deconv) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    const double kPi = 3.14159265358979323846;
+    const double xi = 2.0 * kPi * (double)(j - (n >> 1)) / (double)Nf, hw = 0.5 * (double)W;
+    const int S = 512;
+    const double h = kPi / S;
+    double acc = 0.0;
+    for (int q = 0; q <= S; ++q) {
+        const double th = -0.5 * kPi + q * h;
+        double st, ct;
+        sincos(th, &st, &ct);
+        const double f = exp(beta * (ct - 1.0)) * cos(xi * hw * st) * hw * ct;
+        acc += f * ((q == 0 || q == S) ? 1.0 : ((q & 1) ? 4.0 : 2.0));
+    }
+    deconv[j] = (float)(1.0 / (acc * h / 3.0));
+}
+
+// ---- host side ---------------------------------------------------------------------------------------------------------
+struct NufftPlanCache {
+    int n, Nf, W, device;
+    float* deconv;
+};
+static thread_local NufftPlanCache g_nufft_cache[4] = {};
+
+// Nf, log2 Nf for a grid of n cells, or 0 when the transform does not fit shared memory
+int nufft_grid_size(int n, int* logNf) {
+    int q = 1;
+    while ((1 << q) < 2 * n) ++q;
+    if ((1 << q) > NF_MAX || q < 6) return 0;
+    if (logNf) *logNf = q;
+    return 1 << q;
+}
+
+static int nufft_setup(int n, int W, cudaStream_t stream, NufftGrid* g) {
+    int device = 0;
+    CSR_CUDA(cudaGetDevice(&device));
+    int q = 0;
+    const int Nf = nufft_grid_size(n, &q);
+    CSR_REQUIRE(Nf > 0, "nufft: a grid of %d cells does not fit shared memory", n);
+    NufftPlanCache* slot = nullptr;
+    for (auto& c : g_nufft_cache)
+        if (c.deconv && c.n == n && c.Nf == Nf && c.W == W && c.device == device) slot = &c;
+    if (!slot) {
+        static thread_local int next = 0;
+        slot = &g_nufft_cache[next];
+        next = (next + 1) % 4;
+        if (slot->deconv) cudaFree(slot->deconv);
+        slot->deconv = nullptr;
+        CSR_CUDA(cudaMalloc(&slot->deconv, sizeof(float) * n));
+        slot->n = n;
+        slot->Nf = Nf;
+        slot->W = W;
+        slot->device = device;
+        nufft_deconv_kernel<<<(n + 127) / 128, 128, 0, stream>>>(n, Nf, W, 2.30 * W, slot->deconv);
+        CSR_LAUNCHED();
+    }
+    g->n = n;
+    g->Nf = Nf;
+    g->logNf = q;
+    g->W = W;
+    g->beta = 2.30f * (float)W;
+    g->deconv = slot->deconv;
+    return CSR_OK;
+}
+
+static int nufft_width() {
+    static const int w = getenv("CSR_NUFFT_W") ? atoi(getenv("CSR_NUFFT_W")) : 8;
+    return w < 2 ? 2 : (w > 16 ? 16 : w);
+}
+
+template <typename Kernel>
+static int nufft_configure(Kernel kernel, int Nf, int* grid, int P) {
+    const int smem = (int)sizeof(float2) * (Nf + tw_slot(Nf / 2) + 1);
+    CSR_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    int device = 0, sms = 0;
+    CSR_CUDA(cudaGetDevice(&device));
+    CSR_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+    int per_sm = 1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, NF_THREADS, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+    *grid = min(P, sms * per_sm);
+    return smem;
+}
+
+int launch_nufft_forward(const double* a, int ldl, const int* m_count, int m, int n, double phi0, double dphi, const float* x, int ldx,
+                         const float* chan_scale, const float* row_scale, const float* sub, float* out, int ld_out, int P,
+                         cudaStream_t stream) {
+    NufftGrid g = {};
+    int rc = nufft_setup(n, nufft_width(), stream, &g);
+    if (rc) return rc;
+    g.a = a;
+    g.ldl = ldl;
+    g.m_count = m_count;
+    g.m = m;
+    g.dphi = dphi;
+    g.phic = phi0 + (double)(n >> 1) * dphi;
+    int grid = 1;
+    const int smem = nufft_configure(nufft_forward_kernel, g.Nf, &grid, P);
+    if (smem < 0) return smem;
+    cudaEvent_t ev0, ev1;
+    const bool prof = profile_start(stream, &ev0, &ev1);
+    nufft_forward_kernel<<<grid, NF_THREADS, smem, stream>>>(g, x, ldx, chan_scale, row_scale, sub, out, ld_out, P);
+    CSR_LAUNCHED();
+    if (prof) profile_stop(14, stream, ev0, ev1);
+    return CSR_OK;
+}
+
+int launch_nufft_adjoint(const double* a, int ldl, const int* m_count, int m, int n, double phi0, double dphi, const float* b, int ldb,
+                         const float* chan_scale, const float* row_scale, float* out, int ld_out, int P, cudaStream_t stream) {
+    NufftGrid g = {};
+    int rc = nufft_setup(n, nufft_width(), stream, &g);
+    if (rc) return rc;
+    g.a = a;
+    g.ldl = ldl;
+    g.m_count = m_count;
+    g.m = m;
+    g.dphi = dphi;
+    g.phic = phi0 + (double)(n >> 1) * dphi;
+    int grid = 1;
+    const int smem = nufft_configure(nufft_adjoint_kernel, g.Nf, &grid, P);
+    if (smem < 0) return smem;
+    cudaEvent_t ev0, ev1;
+    const bool prof = profile_start(stream, &ev0, &ev1);
+    nufft_adjoint_kernel<<<grid, NF_THREADS, smem, stream>>>(g, b, ldb, chan_scale, row_scale, out, ld_out, P);
+    CSR_LAUNCHED();
+    if (prof) profile_stop(15, stream, ev0, ev1);
+    return CSR_OK;
+}
+
+}  // namespace csr

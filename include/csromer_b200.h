@@ -244,7 +244,7 @@ int csr_sparse_fill(const float* x, int ld, int ncols, int P, const long long* o
  * 5 fista-adjoint, 6 fused wavelet synthesis, 7 fused wavelet analysis + update, 8 fp16 screening adjoint,
  * 9 fp8 screening adjoint, 10 one-product plain adjoint (wavelet-domain screening), 11 wavelet analysis + update redo pass,
  * 12 tile selection / tile-list kernels of the screening, 13 end-of-iteration row update (incremental-screening clocks,
- * operand scales), 14 and 15 reserved] and clears the record. */
+ * operand scales), 14 / 15 shared-memory NUFFT forward / adjoint of the per-line-of-sight samplings] and clears the record. */
 #define CSR_PROFILE_KINDS 16
 int csr_profile(int enable);
 int csr_profile_collect(double* ms_by_kind, long long* count_by_kind);

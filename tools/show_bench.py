@@ -6,7 +6,7 @@ d = json.loads(open(sys.argv[1]).read().strip().splitlines()[-1])
 
 
 def kernels(rec):
-    for k, v in rec["roofline"]["per_kernel"].items():
+    for k, v in (rec.get("roofline") or {}).get("per_kernel", {}).items():
         extra = ""
         if "executed_frac" in v:
             extra += " exec %.0f TF (%.2f)" % (v["executed"], v["executed_frac"])
@@ -31,8 +31,9 @@ for name, sub in d.get("configs", {}).items():
 for name, p in d.get("parity", {}).items():
     if p:
         o = p.get("oracle", {})
-        print("parity %s: bit_equal %s dense %.0f LOS/s oracle %s ok %s" % (name, p["shortcuts_vs_dense"]["bit_equal"],
-              p["shortcuts_vs_dense"]["dense_los_per_s"], o.get("parity_max_rel"), p["ok"]))
+        sd = p.get("shortcuts_vs_dense", {})
+        print("parity %s: bit_equal %s dense %.0f LOS/s oracle %s ok %s %s" % (name, sd.get("bit_equal"), sd.get("dense_los_per_s", 0),
+              o.get("parity_max_rel"), p["ok"], {k: v for k, v in p.items() if k.startswith("nufft")}))
 if d.get("cpu_baseline"):
     print("cpu:", d["cpu_baseline"]["value"], d["cpu_baseline"]["kind"], d["cpu_baseline"]["cores"])
 print("peaks:", d["peaks"]["measured_in_run"])
