@@ -831,6 +831,28 @@ def run_k4(ctx, args, peaks, P=4096, keep=0.8):
     return rec, parity
 
 
+def free_workload(ctx, w):
+    """free the slab, the plan tables and the workspace before the next workload"""
+    from csromer_b200 import _device as dv
+    for plan in list(dv.DevicePlan._cache.values()):
+        plan.ws.buf = None
+        plan.close()
+    dv.DevicePlan._cache.clear()
+    del w
+    ctx.torch.cuda.empty_cache()
+
+
+def run_parity(ctx, name, args, headline):
+    """the in-run parity block of a workload, on a freshly built copy of its bench slab (same seeds).  Runs AFTER every timed
+    region of the run: the oracle is CPU work (BLAS threads, seconds of an idle GPU) and must not sit in front of a timing."""
+    slab = args.slab if (headline and args.slab) else WORKLOADS[name]["slab"]
+    w = Workload(ctx, name, slab, args.iters)
+    parity, _ = parity_check(ctx, w, args.parity_los if name != "c5" else min(args.parity_los, 4))
+    ctx.barrier()
+    free_workload(ctx, w)
+    return parity
+
+
 def run_workload(ctx, name, args, steps, warmup, peaks, headline):
     torch = ctx.torch
     slab = args.slab if (headline and args.slab) else WORKLOADS[name]["slab"]
@@ -849,22 +871,11 @@ def run_workload(ctx, name, args, steps, warmup, peaks, headline):
     if name == "c5":
         rec["step_size"] = w.step_size
         rec["full_cube_seconds_at_this_rate"] = 2048.0 * 2048.0 / value
-    parity = None
-    if not args.no_parity:
-        parity, _ = parity_check(ctx, w, args.parity_los if name != "c5" else min(args.parity_los, 4))
-        ctx.barrier()
     extra = {}
     if name == "c3" and headline:
         extra["e2e"], extra["final_cost_mean"] = e2e_c3(ctx, w, args)
-    # free the slab, the plan tables and the workspace before the next workload
-    from csromer_b200 import _device as dv
-    for plan in list(dv.DevicePlan._cache.values()):
-        plan.ws.buf = None
-        plan.close()
-    dv.DevicePlan._cache.clear()
-    del w
-    torch.cuda.empty_cache()
-    return rec, parity, extra
+    free_workload(ctx, w)
+    return rec, None, extra
 
 
 def run_ours(args):
@@ -910,17 +921,23 @@ def run_ours(args):
     barrier()
 
     head = args.workload
-    rec, parity, extra = run_workload(ctx, head, args, args.steps, args.warmup, peaks, True)
-    parities = {head: parity}
+    # phase 1: every timed region; phase 2: the parity blocks (CPU oracle work never precedes a timing)
+    rec, _, extra = run_workload(ctx, head, args, args.steps, args.warmup, peaks, True)
+    parities = {head: None}
     configs = {}
-    for name in [n for n in args.also.split(",") if n and n != head]:
+    others = [n for n in args.also.split(",") if n and n != head]
+    for name in others:
         if name == "k4":
-            configs[name], parities[name] = run_k4(ctx, args, peaks)
             continue
         sub_steps = max(1, min(args.steps, args.sub_steps))
-        sub, par, _ = run_workload(ctx, name, args, sub_steps, max(3, min(args.warmup, 3)), peaks, False)
-        configs[name] = sub
-        parities[name] = par
+        configs[name], _, _ = run_workload(ctx, name, args, sub_steps, max(3, min(args.warmup, 3)), peaks, False)
+    if "k4" in others:   # (its parity is part of the same function, after its timed region; it is the last timed one)
+        configs["k4"], parities["k4"] = run_k4(ctx, args, peaks)
+    if not args.no_parity:
+        parities[head] = run_parity(ctx, head, args, True)
+        for name in others:
+            if name != "k4":
+                parities[name] = run_parity(ctx, name, args, False)
 
     if ctx.rank == 0:
         cpu = None

@@ -313,6 +313,7 @@ struct Options {
     int pair3;        // three-product transforms on CTA pairs (cta_group::2, M = 256; each SM stages half of the B tile)
     int tma_epi;      // ... with the residual epilogue staged through shared memory (TMA loads of b, TMA stores of r)
     int nufft;        // per-line-of-sight samplings: shared-memory NUFFT (nufft.cu) instead of the direct sums (nudft.cu)
+    int fwd128;       // K-block-skipping forward transform on 128 x 128 tiles (four chunk accumulators in TMEM, b prefetched)
 };
 Options& options();
 

@@ -308,7 +308,18 @@ __device__ __forceinline__ void epilogue_tile(const GemmEpilogue& epi, const flo
                             __stcs(reinterpret_cast<unsigned int*>(epi.out_lo + row_off + col), *reinterpret_cast<const unsigned int*>(&l));
                         }
                     }
-                    if (flag_ptr != nullptr && quad == 0 && active && nonzero != flag_in) *flag_ptr = (unsigned char)nonzero;
+                    if (flag_ptr != nullptr && quad == 0 && active && nonzero != flag_in) {
+                        *flag_ptr = (unsigned char)nonzero;
+                        if (nonzero && epi.ext != nullptr) {  // a block turned on: the phi cells with state of this row grow
+                            const int nphi = epi.N >> 1, c1 = min(col0 + 127, epi.N - 1);
+                            int lo, hi;
+                            if (c1 < nphi) lo = col0, hi = c1;
+                            else if (col0 >= nphi) lo = col0 - nphi, hi = c1 - nphi;
+                            else lo = 0, hi = nphi - 1;  // the block that straddles the two halves
+                            atomicMin(&epi.ext[row].x, lo);
+                            atomicMax(&epi.ext[row].y, hi);
+                        }
+                    }
                     if (flag_ptr != nullptr) tile_nz |= active ? nonzero : flag_in;  // frozen rows keep their state
                 }
             }
@@ -1704,6 +1715,351 @@ dft_gemm_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_
     }
 }
 
+// ---- the K-block-skipping forward transform on 128 x 128 tiles -------------------------------------------------------
+// In the L1-sparse regime a forward tile multiplies ~9 of 249 K blocks: the kernel is bound by operand delivery and by its
+// residual epilogue, not by the tensor pipe, and in dft_gemm_kernel the two do not overlap -- the epilogue warps are the
+// ones that drain the 2-block accumulation chunks, TMEM holds two 128 x 256 accumulators, so the MMA side stalls after
+// two chunks while the epilogue of the previous tile runs (ncu: the epilogue warps spend 28 % of their time waiting for
+// chunks, 48 % in the epilogue).  With 128 output columns per tile TMEM holds FOUR chunk accumulators (the MMA side runs a
+// whole tile ahead), a K block stages 64 KiB (three stages instead of two), and an epilogue thread holds 64 accumulators,
+// which leaves registers for ALL of its b values: they are requested at the top of the tile and arrive while the K loop
+// runs, instead of four serial batches after it.  Same products, same window-aligned chunks, same epilogue arithmetic:
+// bit-identical to dft_gemm_kernel<EPI_RESID>.  (The operand traffic per output rises by a third -- the A tile is read once
+// per 128 instead of 256 columns -- which is why the dense transforms stay on the 256-column kernels.)
+constexpr int F1_BN = 128;
+constexpr int F1_STAGES = 3;
+constexpr int F1_STAGE_BYTES = 4 * A_TILE_BYTES;  // A_hi, A_lo, B_hi, B_lo: 4 x (128 rows x 128 B)
+constexpr int F1_EPW = 16;                        // epilogue warps: 4 TMEM lane quarters x 4 column quarters
+constexpr int F1_COLS = F1_BN / 4;                // accumulator columns per epilogue thread
+constexpr int F1_THREADS = 128 + 32 * F1_EPW;
+constexpr int F1_WARPS = 4 + F1_EPW;
+constexpr int F1_SMEM_BYTES = 1024 + F1_STAGES * F1_STAGE_BYTES + 256 + F1_WARPS * KMASK_WORDS * 4;
+static_assert(F1_SMEM_BYTES <= 232448, "shared memory budget exceeded");
+
+// (an epilogue thread of dft_gemm_kernel issues ~60 instructions per element with two warps per scheduler to hide their
+//  latencies; sixteen epilogue warps -- four per scheduler -- on 32-column fragments halve the time of the same code)
+__device__ __forceinline__ void tmem_ld_16x256b_x4(uint32_t taddr, float (&v)[16]) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.16x256b.x4.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void drain_chunk32(uint32_t taddr, float (&acc)[F1_COLS]) {
+#pragma unroll
+    for (int lh = 0; lh < 2; ++lh) {
+        float v[16];
+        tmem_ld_16x256b_x4(taddr + ((uint32_t)(16 * lh) << 16), v);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) acc[lh * 16 + j] += v[j];
+    }
+}
+
+// b values of this thread's 4 rows x 4 column pairs (requested before the K loop ends; zero where out of range)
+template <bool FAST>
+__device__ __forceinline__ void resid32_request(const GemmEpilogue& epi, int lane, int row0, int col0, float2 (&bv)[16]) {
+    const int quad = lane & 3;
+#pragma unroll
+    for (int ri = 0; ri < 4; ++ri) {  // ri = 2 lh + rh
+        const int row = row0 + (lane >> 2) + 8 * (ri & 1) + 16 * (ri >> 1);
+        const float2* bp = reinterpret_cast<const float2*>(epi.b + (size_t)row * epi.ld_out + col0 + 2 * quad);
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {
+            const bool ok = row < epi.P && (FAST || col0 + 8 * jj + 2 * quad < epi.N);
+            bv[ri * 4 + jj] = ok ? __ldcg(bp + 4 * jj) : make_float2(0.f, 0.f);
+        }
+    }
+}
+
+// EPI_RESID on a 32-row x 32-column fragment; same arithmetic, same bits as epilogue_tile<EPI_RESID>.  FAST: the 32
+// columns lie inside the matrix and inside one half of the row ([0, m) or [m, 2m)), m even, 8-byte aligned views.
+template <bool FAST>
+__device__ __forceinline__ void epilogue_resid32(const GemmEpilogue& epi, const float (&acc)[F1_COLS], const float2 (&bv)[16], int lane,
+                                                 int row0, int col0) {
+    const int quad = lane & 3;
+    const int cbase = col0 + 2 * quad;
+    const int chan0 = cbase >= epi.m ? cbase - epi.m : cbase;
+    const int c8 = cbase >= epi.m ? cbase - epi.m + (epi.ld8 >> 1) : cbase;
+    const bool cs_even = (epi.m & 1) == 0 && (reinterpret_cast<uintptr_t>(epi.chan_scale) & 7) == 0;
+#pragma unroll
+    for (int ri = 0; ri < 4; ++ri) {
+        const int lh = ri >> 1, rh = ri & 1;
+        const int row = row0 + (lane >> 2) + 8 * rh + 16 * lh;
+        const bool row_ok = row < epi.P;
+        float dsum = 0.f, rmax = 0.f;
+        if (row_ok) {
+            const float descale = kTwiddleDescale / __ldg(epi.a_scale + row);
+            const float oscale = __ldg(epi.out_scale + row);
+            const size_t row_off = (size_t)row * epi.ld_out;
+            const float* cs_row = epi.chan_scale ? epi.chan_scale + (epi.chan_per_pixel ? (size_t)row * epi.m : 0) : nullptr;
+            __half2* hp = reinterpret_cast<__half2*>(epi.out_hi + row_off + cbase);
+            __half2* lp = reinterpret_cast<__half2*>(epi.out_lo + row_off + cbase);
+            float2 cs[4];
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) {
+                cs[jj] = make_float2(1.f, 1.f);
+                if (FAST) {
+                    if (cs_row != nullptr) cs[jj] = __ldg(reinterpret_cast<const float2*>(cs_row + chan0) + 4 * jj);
+                } else {
+                    const int col = cbase + 8 * jj;
+                    if (cs_row != nullptr && col < epi.N) {
+                        const int c0 = col >= epi.m ? col - epi.m : col;
+                        if (cs_even) {
+                            cs[jj] = __ldg(reinterpret_cast<const float2*>(cs_row + c0));
+                        } else {
+                            const int c1 = col + 1 >= epi.m ? col + 1 - epi.m : col + 1;
+                            cs[jj] = make_float2(__ldg(cs_row + c0), __ldg(cs_row + c1));
+                        }
+                    }
+                }
+            }
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) {
+                const int col = cbase + 8 * jj;
+                if (!FAST && col >= epi.N) continue;
+                const int ai = lh * 16 + (jj * 2 + rh) * 2;
+                const float a0 = acc[ai] * descale, a1 = acc[ai + 1] * descale;
+                const float2 b = bv[ri * 4 + jj];
+                const float r0 = __fmaf_rn(cs[jj].x, a0, -b.x) * oscale, r1 = __fmaf_rn(cs[jj].y, a1, -b.y) * oscale;
+                const __half2 h = __floats2half2_rn(r0, r1);
+                const float2 hf = __half22float2(h);
+                const __half2 l = __floats2half2_rn(r0 - hf.x, r1 - hf.y);
+                hp[4 * jj] = h;
+                lp[4 * jj] = l;
+                dsum += fabsf(hf.x) + fabsf(hf.y);
+                rmax = fmaxf(rmax, fmaxf(fabsf(r0), fabsf(r1)));
+                if (epi.out8 != nullptr) {
+                    const float2 v8 = make_float2(hf.x * kOperandScale8, hf.y * kOperandScale8);
+                    if (fmaxf(fabsf(v8.x), fabsf(v8.y)) > 448.f) dsum = __int_as_float(0x7f800000);  // unscreenable row
+                    const __nv_fp8x2_storage_t pk = __nv_cvt_float2_to_fp8x2(v8, __NV_SATFINITE, __NV_E4M3);
+                    unsigned char* o8 = epi.out8 + (size_t)row * epi.ld8;
+                    if (FAST) {
+                        reinterpret_cast<__nv_fp8x2_storage_t*>(o8 + c8)[4 * jj] = pk;
+                    } else {
+                        const int h8 = epi.ld8 >> 1;
+                        if (epi.m & 1) {
+                            o8[col < epi.m ? col : col - epi.m + h8] = (unsigned char)(pk & 0xff);
+                            o8[col + 1 < epi.m ? col + 1 : col + 1 - epi.m + h8] = (unsigned char)(pk >> 8);
+                        } else {
+                            *reinterpret_cast<__nv_fp8x2_storage_t*>(o8 + (col < epi.m ? col : col - epi.m + h8)) = pk;
+                        }
+                    }
+                }
+            }
+        }
+        if (epi.abs_sum_out != nullptr) {  // kernel-uniform
+            dsum += __shfl_xor_sync(0xffffffffu, dsum, 1);
+            dsum += __shfl_xor_sync(0xffffffffu, dsum, 2);
+            if (quad == 0 && row_ok && dsum != 0.f) atomicAdd(epi.abs_sum_out + row, dsum);
+        }
+        if (epi.row_stat != nullptr) {  // kernel-uniform
+            rmax = fmaxf(rmax, __shfl_xor_sync(0xffffffffu, rmax, 1));
+            rmax = fmaxf(rmax, __shfl_xor_sync(0xffffffffu, rmax, 2));
+            if (quad == 0 && row_ok && rmax != 0.f)
+                atomicMax(reinterpret_cast<unsigned int*>(epi.row_stat + 4 * (size_t)row + 3), __float_as_uint(rmax));
+        }
+    }
+}
+
+__global__ void __launch_bounds__(F1_THREADS, 1)
+dft_fwd128_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
+                  const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo, int K, int MT, int NT,
+                  int chunk_kb, const GemmEpilogue epi) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* stage_base = smem;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + F1_STAGES * F1_STAGE_BYTES);
+    uint64_t* full = bars;                    // [F1_STAGES]
+    uint64_t* empty = bars + 4;               // [F1_STAGES]
+    uint64_t* tmem_full = bars + 8;           // [4]  one per chunk accumulator
+    uint64_t* tmem_empty = bars + 12;         // [4]
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 16);
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int total_tiles = MT * NT;
+    const int KB = (K + BK - 1) / BK;
+    uint32_t* my_mask = reinterpret_cast<uint32_t*>(smem + F1_STAGES * F1_STAGE_BYTES + 256) + warp * KMASK_WORDS;
+    const bool skip = epi.a_kflags != nullptr;
+    const int kwords = (KB + 1) >> 1;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&map_a_hi);
+        tma_prefetch_desc(&map_a_lo);
+        tma_prefetch_desc(&map_b_hi);
+        tma_prefetch_desc(&map_b_lo);
+        for (int s = 0; s < F1_STAGES; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], 1);
+        }
+        for (int b = 0; b < 4; ++b) {
+            mbar_init(&tmem_full[b], 1);
+            mbar_init(&tmem_empty[b], F1_EPW);
+        }
+        mbar_fence_init();
+    }
+    if (warp == 1) {
+        tmem_alloc(tmem_ptr, TMEM_COLS);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    // registers: 640 threads start with 96 each (61440 for the CTA); the four control warps drop to 40 and free 7168, the
+    // sixteen epilogue warps rise to 104 and take 4096 of them (setmaxnreg only moves registers inside the CTA's allocation:
+    // asking for more than the others gave up would wait forever)
+    if (warp < 4) {
+      asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+      if (warp == 0) {
+        // ===================== TMA producer =====================
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int ti = blockIdx.x; ti < total_tiles; ti += gridDim.x) {
+            int mt, nt;
+            tile_coords(ti, MT, NT, mt, nt);
+            if (skip) build_kmask(epi.a_kflags + (size_t)mt * epi.a_kflag_ld, kwords, KB, my_mask, lane);
+            if (lane == 0) {
+                for (int kb = skip ? next_active_kb(my_mask, 0, KB) : 0; kb < KB; kb = skip ? next_active_kb(my_mask, kb + 1, KB) : kb + 1) {
+                    mbar_wait(&empty[stage], phase ^ 1);
+                    uint8_t* sb = stage_base + stage * F1_STAGE_BYTES;
+                    mbar_arrive_expect_tx(&full[stage], F1_STAGE_BYTES);
+                    tma_load_2d(sb, &map_a_hi, &full[stage], kb * BK, mt * BM);
+                    tma_load_2d(sb + A_TILE_BYTES, &map_a_lo, &full[stage], kb * BK, mt * BM);
+                    tma_load_2d(sb + 2 * A_TILE_BYTES, &map_b_hi, &full[stage], kb * BK, nt * F1_BN);
+                    tma_load_2d(sb + 3 * A_TILE_BYTES, &map_b_lo, &full[stage], kb * BK, nt * F1_BN);
+                    if (++stage == F1_STAGES) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+            }
+            __syncwarp();
+        }
+      } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        constexpr uint32_t idesc = umma_idesc_f16(BM, F1_BN);
+        int stage = 0;
+        uint32_t phase = 0;
+        uint32_t chunk = 0;  // running chunk counter -> TMEM buffer = chunk & 3, parity = (chunk >> 2) & 1
+        unsigned long long issued = 0;
+        for (int ti = blockIdx.x; ti < total_tiles; ti += gridDim.x) {
+            if (skip) {
+                int mt, nt;
+                tile_coords(ti, MT, NT, mt, nt);
+                build_kmask(epi.a_kflags + (size_t)mt * epi.a_kflag_ld, kwords, KB, my_mask, lane);
+            }
+            if (lane == 0) {
+                int in_chunk = 0, cur_win = -1;
+                uint32_t d_tmem = 0;
+                for (int kb = skip ? next_active_kb(my_mask, 0, KB) : 0; kb < KB; kb = skip ? next_active_kb(my_mask, kb + 1, KB) : kb + 1) {
+                    const int win = kb / chunk_kb;
+                    if (in_chunk != 0 && win != cur_win) {
+                        umma_commit(&tmem_full[chunk & 3]);
+                        ++chunk;
+                        in_chunk = 0;
+                    }
+                    if (in_chunk == 0) {
+                        const int buf = chunk & 3;
+                        mbar_wait(&tmem_empty[buf], ((chunk >> 2) & 1) ^ 1);
+                        tc_fence_after();
+                        d_tmem = tmem_base + (uint32_t)(buf * F1_BN);
+                        cur_win = win;
+                    }
+                    mbar_wait(&full[stage], phase);
+                    tc_fence_after();
+                    const uint32_t sa_hi = smem_u32(stage_base + stage * F1_STAGE_BYTES);
+                    const uint32_t sa_lo = sa_hi + A_TILE_BYTES, sb_hi = sa_hi + 2 * A_TILE_BYTES, sb_lo = sa_hi + 3 * A_TILE_BYTES;
+#pragma unroll
+                    for (int k4 = 0; k4 < BK / 16; ++k4) {
+                        const uint64_t da_hi = umma_desc_sw128(sa_hi + k4 * 32), da_lo = umma_desc_sw128(sa_lo + k4 * 32);
+                        const uint64_t db_hi = umma_desc_sw128(sb_hi + k4 * 32), db_lo = umma_desc_sw128(sb_lo + k4 * 32);
+                        umma_f16(d_tmem, da_hi, db_hi, idesc, (in_chunk != 0 || k4 != 0) ? 1u : 0u);
+                        umma_f16(d_tmem, da_lo, db_hi, idesc, 1u);
+                        umma_f16(d_tmem, da_hi, db_lo, idesc, 1u);
+                    }
+                    issued += 3;  // (half units of 128 x 256 x 64)
+                    umma_commit(&empty[stage]);
+                    if (++stage == F1_STAGES) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                    ++in_chunk;
+                }
+                if (in_chunk != 0) {
+                    umma_commit(&tmem_full[chunk & 3]);
+                    ++chunk;
+                }
+            }
+            chunk = __shfl_sync(0xffffffffu, chunk, 0);
+        }
+        if (lane == 0 && epi.mma_count != nullptr && issued != 0) atomicAdd(epi.mma_count + epi.count_slot, (issued + 1) / 2);
+      }
+    } else {
+        // ===================== epilogue warps =====================
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
+        const int ew = warp - 4;
+        const int sub = warp & 3;        // TMEM lane quarter this warp may read (hardware rule: warp id mod 4)
+        const int cq = ew >> 2;          // which 32 of the tile's 128 columns
+        const bool fast_ok = (epi.m & 1) == 0 && (epi.ld_out & 1) == 0 &&
+                             ((reinterpret_cast<uintptr_t>(epi.b) | reinterpret_cast<uintptr_t>(epi.chan_scale)) & 7) == 0 &&
+                             ((reinterpret_cast<uintptr_t>(epi.out_hi) | reinterpret_cast<uintptr_t>(epi.out_lo)) & 3) == 0 &&
+                             (epi.out8 == nullptr || ((reinterpret_cast<uintptr_t>(epi.out8) | (uintptr_t)epi.ld8) & 1) == 0) &&
+                             epi.no_fast == 0;
+        uint32_t chunk = 0;
+        for (int ti = blockIdx.x; ti < total_tiles; ti += gridDim.x) {
+            int mt, nt;
+            tile_coords(ti, MT, NT, mt, nt);
+            const int erow0 = mt * BM + sub * 32, ecol0 = nt * F1_BN + cq * F1_COLS;
+            const bool fast = fast_ok && ecol0 + F1_COLS <= epi.N && (ecol0 + F1_COLS <= epi.m || ecol0 >= epi.m);  // (warp-uniform)
+            float2 bv[16];
+            if (fast) resid32_request<true>(epi, lane, erow0, ecol0, bv);  // in flight while the K loop runs
+            else resid32_request<false>(epi, lane, erow0, ecol0, bv);
+            float acc[F1_COLS];
+#pragma unroll
+            for (int j = 0; j < F1_COLS; ++j) acc[j] = 0.f;
+            int nchunks = (KB + chunk_kb - 1) / chunk_kb;
+            if (skip) {
+                build_kmask(epi.a_kflags + (size_t)mt * epi.a_kflag_ld, kwords, KB, my_mask, lane);
+                int c = 0;
+                if (lane == 0) {
+                    int cur_win = -1;
+                    for (int kb = next_active_kb(my_mask, 0, KB); kb < KB; kb = next_active_kb(my_mask, kb + 1, KB)) {
+                        const int win = kb / chunk_kb;
+                        c += (win != cur_win);
+                        cur_win = win;
+                    }
+                }
+                nchunks = __shfl_sync(0xffffffffu, c, 0);
+            }
+            for (int c = 0; c < nchunks; ++c, ++chunk) {
+                const int buf = chunk & 3;
+                mbar_wait(&tmem_full[buf], (chunk >> 2) & 1);
+                tc_fence_after();
+                drain_chunk32(tmem_base + ((uint32_t)(sub * 32) << 16) + (uint32_t)(buf * F1_BN + cq * F1_COLS), acc);
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tmem_empty[buf]);
+            }
+            if (fast) epilogue_resid32<true>(epi, acc, bv, lane, erow0, ecol0);
+            else epilogue_resid32<false>(epi, acc, bv, lane, erow0, ecol0);
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, TMEM_COLS);
+    }
+}
+
 // ---- host side --------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -2019,6 +2375,34 @@ int launch_dft_gemm(const csr_plan* plan, bool adjoint, const __half* a_hi, cons
         rc = cached_operand_map(&ma_lo, a_lo, P, K, ldk, 2);
     }
     if (rc) return rc;
+    // the K-block-skipping forward transform with its residual epilogue: 128 x 128 tiles (dft_fwd128_kernel)
+    if (options().fwd128 != 0 && !adjoint && epi.mode == EPI_RESID && epi.a_kflags != nullptr && epi.tile_list == nullptr &&
+        epi.debug == 0 && options().pair3 < 2 && epi.b != nullptr && (epi.ld_out & 1) == 0 &&
+        (reinterpret_cast<uintptr_t>(epi.b) & 7) == 0 && ((reinterpret_cast<uintptr_t>(epi.out_hi) | reinterpret_cast<uintptr_t>(epi.out_lo)) & 3) == 0) {
+        static bool configured = false;
+        if (!configured) {
+            CSR_CUDA(cudaFuncSetAttribute(dft_fwd128_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, F1_SMEM_BYTES));
+            configured = true;
+        }
+        const int MT = (P + BM - 1) / BM, NT = (epi.N + F1_BN - 1) / F1_BN;
+        ProfiledLaunch rec;
+        rec.kind = 2;
+        epi.count_slot = 2;
+        if (g_profile) {
+            CSR_CUDA(pooled_event(&rec.start));
+            CSR_CUDA(pooled_event(&rec.stop));
+            CSR_CUDA(cudaEventRecord(rec.start, stream));
+        }
+        dft_fwd128_kernel<<<min(MT * NT, plan->num_sms), F1_THREADS, F1_SMEM_BYTES, stream>>>(ma_hi, ma_lo, plan->map_fwd_hi_half,
+                                                                                            plan->map_fwd_lo_half, K, MT, NT,
+                                                                                            gemm_chunk_kb(false), epi);
+        CSR_LAUNCHED();
+        if (g_profile) {
+            CSR_CUDA(cudaEventRecord(rec.stop, stream));
+            g_profiled.push_back(rec);
+        }
+        return CSR_OK;
+    }
     // Three-product transforms of whole matrices on CTA pairs (a tile list names single tiles: those stay on one CTA each).
     // Measured on B200 (profiles/README.md, round 2): the dense transforms gain 8 % (operand delivery: 64 KiB per K block
     // and SM instead of 96); the K-block-skipping forward transform LOSES (0.27 -> 0.31 ms, 0.39 ms with the TMA-staged
@@ -2085,28 +2469,33 @@ __global__ void row_update_kernel(RowUpdate u, int P) {
     __syncwarp();
     if (lane < 4) rs[lane] = 0.f;
     if (u.incr.pathlen != nullptr) {
-        // phi cells with state: block b of the flags covers columns [128 b, 128 b + 127] of [Re (n) | Im (n)]
-        int lo = 0x7fffffff, hi = -1;
-        if (u.zero_flags != nullptr) {
-            const unsigned char* fl = u.zero_flags + (size_t)p * u.flag_ld;
-            for (int b = lane; b < u.flag_ld; b += 32) {
-                if (!fl[b]) continue;
-                const int c0 = 128 * b, c1 = min(128 * b + 127, 2 * u.n - 1);
-                if (c1 < u.n) {
-                    lo = min(lo, c0), hi = max(hi, c1);
-                } else if (c0 >= u.n) {
-                    lo = min(lo, c0 - u.n), hi = max(hi, c1 - u.n);
-                } else {  // the block that straddles the two halves: the last cells of Re and the first of Im
-                    lo = 0, hi = u.n - 1;
+        // Iteration 0 (the dense starting point does not count: nothing is recorded before iteration 1): the phi cells
+        // that hold state now, from the state flags -- block b covers columns [128 b, 128 b + 127] of [Re (n) | Im (n)].
+        // Later iterations: EPI_FISTA widens the range itself when a block turns on (GemmEpilogue::ext).
+        if (u.iter == 0) {
+            int lo = 0x7fffffff, hi = -1;
+            if (u.zero_flags != nullptr) {
+                const unsigned char* fl = u.zero_flags + (size_t)p * u.flag_ld;
+                for (int b = lane; b < u.flag_ld; b += 32) {
+                    if (!fl[b]) continue;
+                    const int c0 = 128 * b, c1 = min(128 * b + 127, 2 * u.n - 1);
+                    if (c1 < u.n) {
+                        lo = min(lo, c0), hi = max(hi, c1);
+                    } else if (c0 >= u.n) {
+                        lo = min(lo, c0 - u.n), hi = max(hi, c1 - u.n);
+                    } else {  // the block that straddles the two halves: the last cells of Re and the first of Im
+                        lo = 0, hi = u.n - 1;
+                    }
                 }
+            } else {
+                lo = 0, hi = u.n - 1;
             }
-        } else {
-            lo = 0, hi = u.n - 1;
-        }
 #pragma unroll
-        for (int sft = 16; sft > 0; sft >>= 1) {
-            lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, sft));
-            hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, sft));
+            for (int sft = 16; sft > 0; sft >>= 1) {
+                lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, sft));
+                hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, sft));
+            }
+            if (lane == 0) u.incr.ext[p] = make_int2(lo, hi);
         }
         if (lane == 0) {
             const float2 c = u.incr.crow[p];
@@ -2116,13 +2505,6 @@ __global__ void row_update_kernel(RowUpdate u, int P) {
             u.incr.rhat[p] = rr;
             u.incr.pathlen[p] += dz * 1.001f;
             u.incr.qclock[p] = ((float)(u.iter + 1) * u.noise[p] + rr) * 1.0001f;
-            int2 ex = u.incr.ext[p];
-            if (u.iter == 0) ex = make_int2(0x7fffffff, -1);   // (the dense starting point does not count: nothing is
-            if (lo <= hi) {                                     //  recorded before iteration 1)
-                ex.x = min(ex.x, lo);
-                ex.y = max(ex.y, hi);
-            }
-            u.incr.ext[p] = ex;
         }
     }
     if (u.rescale && lane == 0) {
@@ -2132,10 +2514,36 @@ __global__ void row_update_kernel(RowUpdate u, int P) {
         if (rmax_scaled >= 4096.f) u.rscale[p] = operand_scale(rmax_scaled / u.rscale[p]);
     }
 }
+// the same bookkeeping with one thread per line of sight (every iteration but the first)
+__global__ void row_update_thread_kernel(RowUpdate u, int P) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= P) return;
+    float4* rs = reinterpret_cast<float4*>(u.row_stat) + p;
+    const float4 st = *rs;                           // dz, ||z||_1, max |z|, max |r| (scaled)
+    *rs = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (u.incr.pathlen != nullptr) {
+        const float2 c = u.incr.crow[p];
+        const float a = 2.f * (c.x + c.y);
+        const float r_l1 = u.abs_sum ? u.abs_sum[p] / u.rscale[p] * 1.001f + a * st.x : 0.f;
+        const float rr = fmaxf(u.incr.rhat[p], a * st.y * (1.f / 4096.f) + r_l1 * (1.f / 524288.f));
+        u.incr.rhat[p] = rr;
+        u.incr.pathlen[p] += st.x * 1.001f;
+        u.incr.qclock[p] = ((float)(u.iter + 1) * u.noise[p] + rr) * 1.0001f;
+    }
+    if (u.rescale) {
+        const float zs = u.zscale_write[p];
+        u.zscale_read[p] = zs;
+        if (st.z * zs >= 4096.f) u.zscale_write[p] = operand_scale(st.z);
+        if (st.w >= 4096.f) u.rscale[p] = operand_scale(st.w / u.rscale[p]);
+    }
+}
 int launch_row_update(const RowUpdate& u, int P, cudaStream_t stream) {
     cudaEvent_t ev0, ev1;
     const bool prof = profile_start(stream, &ev0, &ev1);
-    row_update_kernel<<<(P * 32 + 255) / 256, 256, 0, stream>>>(u, P);
+    if (u.iter == 0 || (reinterpret_cast<uintptr_t>(u.row_stat) & 15) != 0)
+        row_update_kernel<<<(P * 32 + 255) / 256, 256, 0, stream>>>(u, P);
+    else
+        row_update_thread_kernel<<<(P + 255) / 256, 256, 0, stream>>>(u, P);
     CSR_LAUNCHED();
     if (prof) profile_stop(13, stream, ev0, ev1);
     return CSR_OK;
@@ -2182,56 +2590,40 @@ int launch_rmtf_envelope(const csr_plan* plan, const float* w, float* env, float
     return CSR_OK;
 }
 
-// one CTA walks the tiles in rasterised order and appends each to one of two lists (ordered compaction): per chunk of
-// 1024 tiles one ballot per warp, the 32 warp counts scanned by every warp with shuffles, one barrier
-__global__ void __launch_bounds__(1024)
+// every tile goes to one of two lists (tile ids in the rasterised numbering of tile_coords); the lists are short and their
+// order does not matter to the kernels that walk them, so tiles are appended with one atomic per warp (counts zeroed here
+// by the first thread of a preceding memset-free protocol: the caller zeroes them)
+__global__ void __launch_bounds__(256)
 split_tile_lists_kernel(const unsigned char* __restrict__ need, const unsigned char* __restrict__ exclude, int MT, int NT,
                         int* __restrict__ list_a, int* __restrict__ count_a, int* __restrict__ list_b,
                         int* __restrict__ count_b) {
-    __shared__ int warp_a[2][32], warp_b[2][32];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    int base_a = 0, base_b = 0;  // (every thread carries the running totals)
-    int buf = 0;
-    for (int t0 = 0; t0 < MT * NT; t0 += 1024, buf ^= 1) {
-        const int t = t0 + threadIdx.x;
-        bool a = false, b = false;
-        if (t < MT * NT) {
-            int mt, nt;
-            tile_coords(t, MT, NT, mt, nt);
-            a = need[(size_t)mt * NT + nt] != 0 && (exclude == nullptr || exclude[(size_t)mt * NT + nt] == 0);
-            b = !a && list_b != nullptr && (exclude == nullptr);
-        }
-        const unsigned ba = __ballot_sync(0xffffffffu, a), bb = __ballot_sync(0xffffffffu, b);
-        if (lane == 0) {
-            warp_a[buf][warp] = __popc(ba);
-            warp_b[buf][warp] = __popc(bb);
-        }
-        __syncthreads();  // (double-buffered counts: one barrier per chunk)
-        const int ca = warp_a[buf][lane], cb = warp_b[buf][lane];
-        int pa = lane < warp ? ca : 0, pb = lane < warp ? cb : 0, ta = ca, tb = cb;
-#pragma unroll
-        for (int sft = 16; sft > 0; sft >>= 1) {
-            pa += __shfl_xor_sync(0xffffffffu, pa, sft);
-            pb += __shfl_xor_sync(0xffffffffu, pb, sft);
-            ta += __shfl_xor_sync(0xffffffffu, ta, sft);
-            tb += __shfl_xor_sync(0xffffffffu, tb, sft);
-        }
-        if (a) list_a[base_a + pa + __popc(ba & ((1u << lane) - 1))] = t;
-        if (b) list_b[base_b + pb + __popc(bb & ((1u << lane) - 1))] = t;
-        base_a += ta;
-        base_b += tb;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x, lane = threadIdx.x & 31;
+    bool a = false, b = false;
+    if (t < MT * NT) {
+        int mt, nt;
+        tile_coords(t, MT, NT, mt, nt);
+        a = need[(size_t)mt * NT + nt] != 0 && (exclude == nullptr || exclude[(size_t)mt * NT + nt] == 0);
+        b = !a && list_b != nullptr && (exclude == nullptr);
     }
-    if (threadIdx.x == 0) {
-        *count_a = base_a;
-        if (count_b) *count_b = base_b;
+    const unsigned ba = __ballot_sync(0xffffffffu, a), bb = __ballot_sync(0xffffffffu, b);
+    int base_a = 0, base_b = 0;
+    if (lane == 0) {
+        if (ba) base_a = atomicAdd(count_a, __popc(ba));
+        if (bb) base_b = atomicAdd(count_b, __popc(bb));
     }
+    base_a = __shfl_sync(0xffffffffu, base_a, 0);
+    base_b = __shfl_sync(0xffffffffu, base_b, 0);
+    if (a) list_a[base_a + __popc(ba & ((1u << lane) - 1))] = t;
+    if (b) list_b[base_b + __popc(bb & ((1u << lane) - 1))] = t;
 }
 int launch_split_tile_lists(const unsigned char* need, const unsigned char* exclude, int P, int N, int* list_a, int* count_a,
                             int* list_b, int* count_b, cudaStream_t stream) {
     const int MT = (P + BM - 1) / BM, NT = (N + BN - 1) / BN;
     cudaEvent_t ev0, ev1;
     const bool prof = profile_start(stream, &ev0, &ev1);
-    split_tile_lists_kernel<<<1, 1024, 0, stream>>>(need, exclude, MT, NT, list_a, count_a, list_b, count_b);
+    CSR_CUDA(cudaMemsetAsync(count_a, 0, sizeof(int), stream));
+    if (count_b) CSR_CUDA(cudaMemsetAsync(count_b, 0, sizeof(int), stream));
+    split_tile_lists_kernel<<<(MT * NT + 255) / 256, 256, 0, stream>>>(need, exclude, MT, NT, list_a, count_a, list_b, count_b);
     CSR_LAUNCHED();
     if (prof) profile_stop(12, stream, ev0, ev1);
     return CSR_OK;

@@ -433,6 +433,7 @@ extern "C" int csr_fista(csr_plan* plan, csr_wavelet* wav, const csr_fista_args*
             e.out_lo = w.z_lo;
             e.out_scale = row_stats ? w.zscale_w : w.zscale;
             if (row_stats) e.row_stat = w.row_stat;
+            if (incr && it > 0) e.ext = w.ext;   // (iteration 0's end state is scanned by row_update_kernel)
             e.lambda0 = a.lambda0;
             e.noise = a.noise;
             e.iter_cap = a.iter_cap;

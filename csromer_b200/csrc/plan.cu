@@ -103,7 +103,8 @@ Options& options() {
                         getenv("CSR_NO_WAVELET_SCREEN") == nullptr, getenv("CSR_NO_SCREEN_INCR") == nullptr,
                         getenv("CSR_NO_RESCALE") == nullptr,
                         getenv("CSR_NO_PAIR3") != nullptr ? 0 : (getenv("CSR_PAIR3") != nullptr ? atoi(getenv("CSR_PAIR3")) : 1),
-                        getenv("CSR_NO_TMA_EPI") == nullptr, getenv("CSR_NO_NUFFT") == nullptr};
+                        getenv("CSR_NO_TMA_EPI") == nullptr, getenv("CSR_NO_NUFFT") == nullptr,
+                        getenv("CSR_FWD128") != nullptr};   // (measured: no faster than the 256-column kernel; off by default)
     return o;
 }
 }  // namespace csr
@@ -129,6 +130,7 @@ extern "C" int csr_set_option(const char* name, int value) {
     else if (!strcmp(name, "pair3")) o.pair3 = value;   // 0 off, 1 dense transforms only (default), 2 every whole-matrix transform
     else if (!strcmp(name, "tma_epi")) o.tma_epi = value != 0;
     else if (!strcmp(name, "nufft")) o.nufft = value != 0;
+    else if (!strcmp(name, "fwd128")) o.fwd128 = value != 0;
     else {
         set_error("csr_set_option: unknown option '%s'", name);
         return CSR_ERR_ARG;

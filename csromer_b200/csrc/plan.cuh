@@ -110,6 +110,7 @@ struct GemmEpilogue {
     const float* qclock;            // [P] additive row clock Q_p = it * noise_p + rhat_p (monotone)
     const float* rhat;              // [P] running maximum of the rounding allowance
     float2* expiry;                 // [MTg * NTs][64] per (tile, row): {X = margin - 2 rhat + Q as of the test, path length L0 then}
+    int2* ext;                      // EPI_FISTA: [P] phi cells with state (IncrState::ext), widened when a block turns on
     unsigned long long* mma_count;  // optional: [CSR_PROFILE_KINDS], slot count_slot += K blocks x products issued
     int count_slot;                 // profile kind of this launch (set by the launchers)
     int debug;                 // measurement aid (CSR_DEBUG_EPI): bit 0 skips epilogue loads, bit 1 skips stores

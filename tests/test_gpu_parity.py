@@ -234,6 +234,7 @@ def test_sparsity_shortcuts_are_bit_exact(nch, P, K, kw):
             _lib.set_option("rescale", incr)
             _lib.set_option("pair3", pair3)
             _lib.set_option("tma_epi", tma)
+            _lib.set_option("fwd128", incr)   # (the sparse forward transform on 128 x 128 tiles: on in some, off in others)
             _lib.set_option("zero_skip", zero_skip)
             _lib.set_option("k_skip", k_skip)
             _lib.set_option("screen", screen)
@@ -255,6 +256,7 @@ def test_sparsity_shortcuts_are_bit_exact(nch, P, K, kw):
         _lib.set_option("rescale", 1)
         _lib.set_option("pair3", 1)
         _lib.set_option("tma_epi", 1)
+        _lib.set_option("fwd128", 1)
     assert np.count_nonzero(results[0][0]) > 0 and np.count_nonzero(results[0][0]) < 0.2 * results[0][0].size
     for other in results[1:]:
         for a, b in zip(results[0], other):
