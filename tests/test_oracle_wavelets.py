@@ -69,3 +69,37 @@ def test_swt_shift_equivariance():
     b = ob.swt(np.roll(x, 5), bank, 4)
     for ca, cb in zip(a, b):
         np.testing.assert_allclose(np.roll(ca, 5), cb, atol=1e-12)
+
+
+def test_against_pywt_fixtures():
+    """the pin: fixtures produced by PyWavelets itself (oracle/make_golden_wavelets.py), when somebody could make them"""
+    import os
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "wavelets_pywt.npz")
+    if not os.path.exists(path):
+        pytest.skip("no pywt-produced fixtures (PyWavelets is not installed here): wavelet parity stays unpinned")
+    g = np.load(path)
+    for key in [k[:-5] for k in g.files if k.endswith("_meta")]:
+        kind, name, N, lev, norm = g[key + "_meta"]
+        bank = ob.filter_bank(str(name))
+        x = g[key + "_x"]
+        if kind == "swt":
+            cs = ob.swt(x, bank, int(lev), bool(int(norm)))
+            rec = ob.iswt(cs, bank, bool(int(norm)))
+        else:
+            cs = ob.wavedec_per(x, bank, int(lev))
+            rec = ob.waverec_per(cs, bank)
+        np.testing.assert_array_equal([len(c) for c in cs], g[key + "_sizes"])
+        np.testing.assert_allclose(np.concatenate(cs), g[key + "_flat"], rtol=0, atol=1e-12 * np.abs(g[key + "_flat"]).max())
+        np.testing.assert_allclose(rec[:len(g[key + "_rec"])], g[key + "_rec"], rtol=0, atol=1e-12 * np.abs(x).max())
+
+
+def test_closed_form_iswt_equals_the_literal_one():
+    """iswt_fast (one a-trous gather per level) == iswt (pywt's double loop over phases), every bank, odd level counts"""
+    rng = np.random.RandomState(0)
+    for name in ("db1", "coif2", "sym4", "bior2.2", "IUWT", "db3"):
+        for N, lev in ((256, None), (480, 3), (1536, None)):
+            bank = ob.filter_bank(name)
+            L = ob.swt_max_level(N) if lev is None else lev
+            cs = [rng.normal(size=(N, 3)) for _ in range(L + 1)]
+            for norm in (False, True):
+                np.testing.assert_allclose(ob.iswt_fast(cs, bank, norm), ob.iswt(cs, bank, norm), rtol=0, atol=1e-13)
