@@ -258,7 +258,15 @@ int csr_profile_collect(double* ms_by_kind, long long* count_by_kind);
  * runs), "sym" (the pair screening kernels decide +phi and -phi together when the phi grid is antisymmetric:
  * half the K), "screen16_pair" (per-pixel weights: one fp16 screening pass on CTA pairs instead of the
  * fp8 -> fp16 cascade), "wavelet_screen" (wavelet
- * bases: one-product gradient plus a rigorous bound away from the active coefficients, exact redo of what fails). */
+ * bases: one-product gradient plus a rigorous bound away from the active coefficients, exact redo of what fails),
+ * "screen_incr" (incremental screening: a screened tile is tested again only when the margin it recorded may be used up --
+ * RMTF-envelope bound on the drift of the gradient), "rescale" (the fp16 operand scales of z and r follow the row maxima:
+ * nothing changes while a run stays in range), "pair3" (0 / 1 / 2: three-product transforms on cta_group::2 CTA pairs --
+ * off / dense transforms only (default) / every whole-matrix transform), "tma_epi" (with pair3 = 2: residual epilogue staged
+ * through shared memory, TMA loads of b and TMA stores of r), "fwd128" (K-block-skipping forward transform on 128 x 128
+ * tiles with 16 epilogue warps; default 0).  One switch is NOT bit-neutral: "nufft" (default 1) runs the
+ * per-line-of-sight transforms (csr_nudft_*, csr_fista_nu) as shared-memory NUFFTs, ~1e-6 of the result's scale away from
+ * the direct sums that nufft = 0 evaluates. */
 int csr_set_option(const char* name, int value);
 
 /* number of kernels launched by this library on the calling thread since the last reset (bench accounting) */
