@@ -35,7 +35,8 @@ struct csr_plan {
 
 struct csr_wavelet {
     int device;
-    int kind;  // 0 = undecimated (swt), 1 = decimated (dwt, periodization)
+    int kind;  // 0 = undecimated (swt), 1 = decimated (dwt)
+    int ext;   // decimated only: 0 = periodization, 1.. = signal-extension mode (csr_wavelet_create: kind - 1)
     int F, levels, N, append_signal, norm;
     int ncoef;             // total coefficient length incl. appended signal
     int sizes[34];         // band lengths  [cA_L, cD_L, ..., cD_1]

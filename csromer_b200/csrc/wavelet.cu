@@ -96,6 +96,99 @@ __global__ void dwt_level_kernel(const float* __restrict__ x_in, int ld_in, int 
 
 // x[q], q in [0, 2*half): gather form of the periodization IDWT.  `keep` = number of leading samples of the
 // result the next level needs (waverec drops the last one when it is one too long); `add` as in iswt.
+// ---- decimated transform with the other PyWavelets signal-extension modes (dictionaries/discrete.py:37-39 hands
+// ``mode`` to pywt.wavedec): full convolution of the extended signal sampled at the odd positions,
+// cA[k] = sum_j lo[j] x_ext[2k + 1 - j], k < (N + F - 1)/2; the inverse is the extension-independent ("valid") part of the
+// up-sampled convolution, out[q] = sum_k cA[k] rlo[q + F - 2 - 2k] + cD[k] rhi[..], q < 2 Nc - F + 2.
+enum ExtMode { EXT_PER = 0, EXT_ZERO, EXT_CONSTANT, EXT_SYMMETRIC, EXT_REFLECT, EXT_PERIODIC, EXT_SMOOTH, EXT_ANTISYMMETRIC,
+               EXT_ANTIREFLECT, EXT_COUNT };
+
+__device__ __forceinline__ int floor_mod(int i, int p) {
+    int j = i % p;
+    return j < 0 ? j + p : j;
+}
+
+__device__ __forceinline__ float ext_sample(const float* __restrict__ x, int i, int N, int ext) {
+    if (i >= 0 && i < N) return x[i];
+    switch (ext) {
+        case EXT_ZERO: return 0.f;
+        case EXT_CONSTANT: return x[i < 0 ? 0 : N - 1];
+        case EXT_PERIODIC: return x[floor_mod(i, N)];
+        case EXT_SYMMETRIC: {
+            const int j = floor_mod(i, 2 * N);
+            return x[j < N ? j : 2 * N - 1 - j];
+        }
+        case EXT_ANTISYMMETRIC: {
+            const int j = floor_mod(i, 2 * N);
+            return j < N ? x[j] : -x[2 * N - 1 - j];
+        }
+        case EXT_REFLECT: {
+            if (N == 1) return x[0];
+            const int p = 2 * N - 2, j = floor_mod(i, p);
+            return x[j < N ? j : p - j];
+        }
+        case EXT_ANTIREFLECT: {
+            if (N == 1) return x[0];
+            const int p = 2 * N - 2, j = floor_mod(i, p), cyc = (i - j) / p;
+            const float base = j < N ? x[j] : 2.f * x[N - 1] - x[p - j];
+            return fmaf(2.f * (float)cyc, x[N - 1] - x[0], base);
+        }
+        case EXT_SMOOTH: {
+            if (N == 1) return x[0];
+            return i < 0 ? fmaf((float)i, x[1] - x[0], x[0]) : fmaf((float)(i - (N - 1)), x[N - 1] - x[N - 2], x[N - 1]);
+        }
+    }
+    return 0.f;
+}
+
+__global__ void dwt_ext_level_kernel(const float* __restrict__ x_in, int ld_in, int N, int ext, float* __restrict__ a_out,
+                                     int ld_a, float* __restrict__ d_out, int ld_d, const FilterPair f) {
+    const int nc = (N + f.F - 1) / 2;
+    const int k = blockIdx.y * blockDim.x + threadIdx.x;
+    if (k >= nc) return;
+    const int p = blockIdx.x;
+    const float* src = x_in + (size_t)p * ld_in;
+    float ca = 0.f, cd = 0.f;
+    const int top = 2 * k + 1;
+    if (top - (f.F - 1) >= 0 && top < N) {  // interior: no extension involved
+        for (int t = 0; t < f.F; ++t) {
+            const float v = src[top - t];
+            ca = fmaf(f.lo[t], v, ca);
+            cd = fmaf(f.hi[t], v, cd);
+        }
+    } else {
+        for (int t = 0; t < f.F; ++t) {
+            const float v = ext_sample(src, top - t, N, ext);
+            ca = fmaf(f.lo[t], v, ca);
+            cd = fmaf(f.hi[t], v, cd);
+        }
+    }
+    a_out[(size_t)p * ld_a + k] = ca;
+    d_out[(size_t)p * ld_d + k] = cd;
+}
+
+// out has ``keep`` <= 2 nc - F + 2 samples (the running approximation is cut to the next detail band's length, like waverec)
+__global__ void idwt_ext_level_kernel(const float* __restrict__ a_in, int ld_a, const float* __restrict__ d_in, int ld_d,
+                                      int nc, float* __restrict__ out, int ld_out, int keep,
+                                      const float* __restrict__ add, int ld_add, const FilterPair f) {
+    const int q = blockIdx.y * blockDim.x + threadIdx.x;
+    if (q >= keep) return;
+    const int p = blockIdx.x;
+    const float* a = a_in + (size_t)p * ld_a;
+    const float* d = d_in + (size_t)p * ld_d;
+    float acc = 0.f;
+    const int base = q + f.F - 2;  // tap t = base - 2k
+    for (int t = (base & 1); t < f.F; t += 2) {
+        const int k = (base - t) >> 1;
+        if (k >= 0 && k < nc) {
+            acc = fmaf(f.lo[t], a[k], acc);
+            acc = fmaf(f.hi[t], d[k], acc);
+        }
+    }
+    if (add) acc += add[(size_t)p * ld_add + q];
+    out[(size_t)p * ld_out + q] = acc;
+}
+
 __global__ void idwt_level_kernel(const float* __restrict__ a_in, int ld_a, const float* __restrict__ d_in, int ld_d,
                                   int half, float* __restrict__ out, int ld_out, int keep,
                                   const float* __restrict__ add, int ld_add, const FilterPair f) {
@@ -138,7 +231,8 @@ static FilterPair make_pair(const float* lo, const float* hi, int F) {
 // lines of sight on grid.x (limit 2^31 - 1), column blocks on grid.y
 static inline dim3 grid_for(int cols, int P) { return dim3(P, (cols + 255) / 256); }
 
-int wavelet_ld(const csr_wavelet* w) { return round_up(w->N, 8); }
+// pitch of the two scratch slabs: the longest intermediate band (extension modes: (N + F - 1)/2 may exceed N for tiny N)
+int wavelet_ld(const csr_wavelet* w) { return round_up(w->ext ? max(w->N, (w->N + w->F) / 2 + 1) : w->N, 8); }
 
 // ---- fused undecimated transforms: all levels of one tile of one line of sight in shared memory ---------------
 // A tile of T samples plus a halo of H = (F/2)(2^L - 1) samples on each side (the cumulative support of L a-trous
@@ -1037,10 +1131,14 @@ int wavelet_decompose(const csr_wavelet* w, const float* signal, int ld_sig, flo
         if (w->kind == 0) {
             swt_level_kernel<<<grid_for(N, P), 256, 0, stream>>>(cur, ld_cur, a_out, ld_a, d_out, ld_coef, N,
                                                                  1 << (lev - 1), f);
-        } else {
+        } else if (w->ext == 0) {
             dwt_level_kernel<<<grid_for((len + 1) / 2, P), 256, 0, stream>>>(cur, ld_cur, len, a_out, ld_a, d_out,
                                                                              ld_coef, f);
             len = (len + 1) / 2;
+        } else {
+            dwt_ext_level_kernel<<<grid_for((len + w->F - 1) / 2, P), 256, 0, stream>>>(cur, ld_cur, len, w->ext, a_out,
+                                                                                        ld_a, d_out, ld_coef, f);
+            len = (len + w->F - 1) / 2;
         }
         CSR_LAUNCHED();
         cur = a_out;
@@ -1090,8 +1188,12 @@ int wavelet_reconstruct(const csr_wavelet* w, const float* coef, int ld_coef, fl
         } else {
             const int half = w->sizes[band];  // cA (after trimming) and cD have this many samples
             const int keep = (lev == 1) ? N : w->sizes[band + 1];
-            idwt_level_kernel<<<grid_for(keep, P), 256, 0, stream>>>(cur, ld_cur, d_in, ld_coef, half, out, ld_out,
-                                                                     keep, add, ld_coef, f);
+            if (w->ext == 0)
+                idwt_level_kernel<<<grid_for(keep, P), 256, 0, stream>>>(cur, ld_cur, d_in, ld_coef, half, out, ld_out,
+                                                                         keep, add, ld_coef, f);
+            else
+                idwt_ext_level_kernel<<<grid_for(keep, P), 256, 0, stream>>>(cur, ld_cur, d_in, ld_coef, half, out, ld_out,
+                                                                             keep, add, ld_coef, f);
         }
         CSR_LAUNCHED();
         cur = out;
@@ -1108,7 +1210,11 @@ extern "C" int csr_wavelet_create(csr_wavelet** out, int kind, const double* dec
                                   const double* rec_lo, const double* rec_hi, int F, int level, int N,
                                   int append_signal, int norm, int device) {
     CSR_REQUIRE(out && dec_lo && dec_hi && rec_lo && rec_hi, "csr_wavelet_create: null pointer");
-    CSR_REQUIRE(kind == 0 || kind == 1, "csr_wavelet_create: kind must be 0 (undecimated) or 1 (decimated)");
+    CSR_REQUIRE(kind >= 0 && kind <= EXT_COUNT,
+                "csr_wavelet_create: kind must be 0 (undecimated), 1 (decimated, periodization) or 2..%d (decimated with "
+                "signal extension zero, constant, symmetric, reflect, periodic, smooth, antisymmetric, antireflect)", (int)EXT_COUNT);
+    const int ext = kind >= 1 ? kind - 1 : 0;
+    if (kind > 1) kind = 1;
     CSR_REQUIRE(F >= 2 && F <= 64 && F % 2 == 0, "csr_wavelet_create: filter length must be even and in [2, 64] (F=%d)", F);
     CSR_REQUIRE(N > 0 && level >= 0 && level <= 32, "csr_wavelet_create: bad N=%d or level=%d", N, level);
     if (kind == 0) CSR_REQUIRE(level == 0 || N % (1 << level) == 0, "csr_wavelet_create: N=%d is not a multiple of 2^%d", N, level);
@@ -1117,6 +1223,7 @@ extern "C" int csr_wavelet_create(csr_wavelet** out, int kind, const double* dec
     memset(w, 0, sizeof(*w));
     w->device = device;
     w->kind = kind;
+    w->ext = ext;
     w->F = F;
     w->levels = level;
     w->N = N;
@@ -1137,7 +1244,7 @@ extern "C" int csr_wavelet_create(csr_wavelet** out, int kind, const double* dec
     } else {
         int len = N;
         for (int lev = 1; lev <= level; ++lev) {
-            len = (len + 1) / 2;
+            len = ext ? (len + F - 1) / 2 : (len + 1) / 2;
             w->sizes[level - lev + 1] = len;
         }
         w->sizes[0] = len;

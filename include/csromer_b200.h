@@ -66,7 +66,9 @@ int csr_derotate(csr_plan* plan, float* data, const float* phi_gal, int P, void*
 
 /* ---- wavelet dictionaries (dictionaries/undecimated.py, dictionaries/discrete.py; PyWavelets semantics) --
  * kind: 0 = undecimated (pywt.swt/iswt, trim_approx=True), 1 = decimated (pywt.wavedec/waverec,
- * mode="periodization").  The transform acts on the real planar vector of length N = 2n as ONE signal
+ * mode="periodization"), 2..9 = decimated with the signal-extension mode discrete.py:37-39 passes on: 2 zero,
+ * 3 constant, 4 symmetric, 5 reflect, 6 periodic, 7 smooth, 8 antisymmetric, 9 antireflect (bands of
+ * (len + F - 1) / 2 samples per level; reconstruct returns the N samples of the signal).  The transform acts on the real planar vector of length N = 2n as ONE signal
  * (objectivefunction/priors/chi2.py:44-55).  Filters are HOST double arrays of length F (even). */
 int csr_wavelet_create(csr_wavelet** out, int kind, const double* dec_lo, const double* dec_hi,
                        const double* rec_lo, const double* rec_hi, int F, int level, int N, int append_signal,

@@ -340,13 +340,136 @@ def waverec_per(coeffs, bank):
     return a
 
 
+# ---- decimated transform with the other PyWavelets signal-extension modes ------------------------------------
+# dictionaries/discrete.py:37-39,80-89 hand ``self.mode`` to pywt.wavedec / pywt.waverec.  PyWavelets (a dependency that
+# is not vendored in the reference; pyproject pins no version, algorithm as of PyWavelets 1.x, pywt/_extensions/c/
+# convolution.template.c ``downsampling_convolution`` / ``upsampling_convolution_valid_sf``) computes, for every
+# non-periodization mode, the FULL convolution of the extended signal with the decomposition filter sampled at the odd
+# positions,  cA[k] = sum_j dec_lo[j] x_ext[2k + 1 - j],  k = 0 .. (N + F - 1)//2 - 1,  and reconstructs with the part of
+# the up-sampled convolution that does not depend on the extension ("valid"), 2 Nc - F + 2 samples.
+# Pinned: the PyWavelets documentation value of pywt.dwt([3,7,1,1,-2,5,4,6], 'db2') (default mode 'symmetric') in
+# tests/test_oracle_wavelets.py; the extensions themselves against numpy.pad (the correspondence pywt.pad documents).
+EXT_MODES = ("zero", "constant", "symmetric", "reflect", "periodic", "smooth", "antisymmetric", "antireflect")
+
+
+def ext_sample(x, i, mode):
+    """value of the extended signal at (array of) integer positions ``i`` (any distance outside [0, N)); axis 0 of x."""
+    x = np.asarray(x, dtype=np.float64)
+    N = x.shape[0]
+    i = np.asarray(i, dtype=np.int64)
+    inside = (i >= 0) & (i < N)
+    shape = (-1,) + (1,) * (x.ndim - 1)
+    if mode == "zero":
+        out = x[np.clip(i, 0, N - 1)] * inside.reshape(shape)
+    elif mode == "constant":
+        out = x[np.clip(i, 0, N - 1)]
+    elif mode == "periodic":
+        out = x[i % N]
+    elif mode in ("symmetric", "antisymmetric"):
+        j = i % (2 * N)
+        back = j >= N
+        out = x[np.where(back, 2 * N - 1 - j, j)]
+        if mode == "antisymmetric":
+            out = out * np.where(back, -1.0, 1.0).reshape(shape)
+    elif mode == "reflect":
+        if N == 1:
+            out = x[np.zeros_like(i)]
+        else:
+            p = 2 * N - 2
+            j = i % p
+            out = x[np.where(j >= N, p - j, j)]
+    elif mode == "antireflect":
+        if N == 1:
+            out = x[np.zeros_like(i)]
+        else:
+            p = 2 * N - 2
+            cyc = np.floor_divide(i, p)
+            j = i - cyc * p
+            back = j >= N
+            base = np.where(back.reshape(shape), 2.0 * x[N - 1] - x[np.where(back, p - j, 0)], x[np.where(back, 0, j)])
+            out = base + 2.0 * cyc.reshape(shape) * (x[N - 1] - x[0])
+    elif mode == "smooth":
+        if N == 1:
+            out = x[np.zeros_like(i)]
+        else:
+            left = x[0] + i.reshape(shape) * (x[1] - x[0])
+            right = x[N - 1] + (i - (N - 1)).reshape(shape) * (x[N - 1] - x[N - 2])
+            out = np.where((i < 0).reshape(shape), left, np.where((i >= N).reshape(shape), right, x[np.clip(i, 0, N - 1)]))
+    else:
+        raise ValueError("unknown signal extension mode %r" % (mode,))
+    return out
+
+
+def dwt_coeff_len(N, F, mode):
+    """pywt.dwt_coeff_len (dictionaries/discrete.py:20-22)."""
+    return (N + 1) // 2 if mode == "periodization" else (N + F - 1) // 2
+
+
+def _dwt_ext(x, f_lo, f_hi, mode):
+    """single-level DWT along axis 0 with signal extension ``mode`` (not periodization)."""
+    N, F = x.shape[0], f_lo.shape[0]
+    k = np.arange(dwt_coeff_len(N, F, mode))
+    cA = np.zeros((k.shape[0],) + x.shape[1:], dtype=np.float64)
+    cD = np.zeros_like(cA)
+    for j in range(F):
+        src = ext_sample(x, 2 * k + 1 - j, mode)
+        cA += f_lo[j] * src
+        cD += f_hi[j] * src
+    return cA, cD
+
+
+def _idwt_ext(cA, cD, rec_lo, rec_hi):
+    """single-level inverse for every non-periodization mode: out[q] = sum_k cA[k] rec_lo[q + F - 2 - 2k] + cD[k] rec_hi[..],
+    q = 0 .. 2 Nc - F + 1."""
+    Nc, F = cA.shape[0], rec_lo.shape[0]
+    out = np.zeros((2 * Nc - F + 2,) + cA.shape[1:], dtype=np.float64)
+    q = np.arange(out.shape[0])
+    shape = (-1,) + (1,) * (cA.ndim - 1)
+    for k in range(Nc):
+        t = q + F - 2 - 2 * k
+        ok = (t >= 0) & (t < F)
+        tt = np.clip(t, 0, F - 1)
+        out += (np.where(ok, rec_lo[tt], 0.0).reshape(shape) * cA[k] + np.where(ok, rec_hi[tt], 0.0).reshape(shape) * cD[k])
+    return out
+
+
+def wavedec_mode(x, bank, mode, level=None):
+    """pywt.wavedec(mode=...) along axis 0 -> [cA_L, cD_L, ..., cD_1] for any supported mode."""
+    if mode == "periodization":
+        return wavedec_per(x, bank, level)
+    dec_lo, dec_hi = bank[0], bank[1]
+    L = dwt_max_level(x.shape[0], dec_lo.shape[0]) if level is None else level
+    a = np.asarray(x, dtype=np.float64)
+    details = []
+    for _ in range(L):
+        a, d = _dwt_ext(a, dec_lo, dec_hi, mode)
+        details.append(d)
+    return [a] + details[::-1]
+
+
+def waverec_mode(coeffs, bank, mode):
+    """pywt.waverec(mode=...): the running approximation loses its last sample when it is one longer than the next detail
+    band (pywt/_multilevel.py waverec); an odd-length signal therefore comes back one sample longer, as in PyWavelets."""
+    if mode == "periodization":
+        return waverec_per(coeffs, bank)
+    rec_lo, rec_hi = bank[2], bank[3]
+    a = coeffs[0]
+    for d in coeffs[1:]:
+        if a.shape[0] == d.shape[0] + 1:
+            a = a[:-1]
+        a = _idwt_ext(a, d, rec_lo, rec_hi)
+    return a
+
+
 class WaveletDict:
     """Analysis/synthesis pair on the REAL planar vector [Re|Im] as ONE signal (objectivefunction/priors/
     chi2.py:44-55), coefficients flattened like pywt.ravel_coeffs, optional ``append_signal``
     (dictionaries/undecimated.py:84-85,143-169; discrete.py:42-43,71-82)."""
 
-    def __init__(self, name, kind="swt", level=None, norm=False, append_signal=False, fast_iswt=False):
+    def __init__(self, name, kind="swt", level=None, norm=False, append_signal=False, fast_iswt=False,
+                 mode="periodization"):
         self.bank = filter_bank(name)
+        self.mode = mode  # decimated transform only (pywt signal-extension mode)
         self.kind, self.level, self.norm, self.append_signal = kind, level, norm, append_signal
         self.fast_iswt = fast_iswt  # closed-form iswt (same values; see iswt_fast)
         self.shapes = None
@@ -354,7 +477,8 @@ class WaveletDict:
 
     def decompose(self, x):
         self.N = x.shape[0]
-        cs = swt(x, self.bank, self.level, self.norm) if self.kind == "swt" else wavedec_per(x, self.bank, self.level)
+        cs = swt(x, self.bank, self.level, self.norm) if self.kind == "swt" else \
+            wavedec_mode(x, self.bank, self.mode, self.level)
         self.shapes = [c.shape[0] for c in cs]
         flat = np.concatenate(cs, axis=0)
         return np.concatenate([x, flat], axis=0) if self.append_signal else flat
@@ -370,7 +494,7 @@ class WaveletDict:
         if self.kind == "swt":
             out = iswt_fast(cs, self.bank, self.norm) if self.fast_iswt else iswt(cs, self.bank, self.norm)
         else:
-            out = waverec_per(cs, self.bank)
+            out = waverec_mode(cs, self.bank, self.mode)[:self.N]
         return sig + out if sig is not None else out
 
 

@@ -673,6 +673,43 @@ def test_wavelet_transforms(name, kind, N, level, norm, app):
         w.reconstruct(c[:-1])
 
 
+@pytest.mark.parametrize("mode", ["zero", "constant", "symmetric", "reflect", "periodic", "smooth", "antisymmetric", "antireflect"])
+def test_decimated_wavelet_signal_extension_modes(mode):
+    """DiscreteWavelet(mode=...) hands the mode to pywt.wavedec / waverec (discrete.py:37-39,80-89): bands of
+    (len + F - 1) // 2 samples, the extension-independent part of the inverse; checked against the oracle's restatement
+    (pinned on the PyWavelets documentation value in tests/test_oracle_wavelets.py)."""
+    rng = np.random.RandomState(31)
+    for name, N, level, app in (("db2", 3136, None, False), ("coif2", 1000, 4, True), ("db1", 250, None, False), ("sym4", 37, 2, False),
+                                ("db4", 17, 1, False)):
+        x = rng.normal(size=(N, 7)).astype(np.float32)
+        w = cs.DiscreteWavelet(wavelet_name=name, wavelet_level=level, mode=mode, append_signal=app)
+        o = ob.WaveletDict(name, kind="dwt", level=level, append_signal=app, mode=mode)
+        c, co = w.decompose(x), o.decompose(x.astype(np.float64))
+        assert c.shape == co.shape and w.ncoeffs == co.shape[0] and w.n == N
+        sizes = [sh[0] for sh in w.coeff_shapes]
+        assert sizes == o.shapes and sizes[-1] == w.calculate_ncoeffs(x[:, 0])
+        tol = 2e-5 if mode in ("smooth", "antireflect") else 3e-6  # extrapolated edges are large next to the signal
+        assert rel(c, co) < tol
+        r = w.reconstruct(c)
+        assert r.shape == x.shape and rel(r, o.reconstruct(co)) < tol and rel(r, (2 if app else 1) * x) < tol
+    # the complex variants transform real and imaginary parts separately (discrete.py:46-68)
+    z = (rng.normal(size=200) + 1j * rng.normal(size=200)).astype(np.complex64)
+    w = cs.DiscreteWavelet(wavelet_name="db3", mode=mode)
+    cz = w.decompose_complex(z)
+    o = ob.WaveletDict("db3", kind="dwt", mode=mode)
+    assert rel(cz.real, o.decompose(z.real.astype(np.float64))) < 2e-5 and rel(w.reconstruct_complex(cz), z) < 2e-5
+
+
+def test_fista_in_a_symmetric_extension_wavelet_basis():
+    src, par = make_batch(200, 24, seed=22, mixed=True)
+    wav = cs.DiscreteWavelet(wavelet_name="db2", mode="symmetric")
+    owav = ob.WaveletDict("db2", kind="dwt", mode="symmetric")
+    cost, X, l1, lam0, noise = run_fista(src, par, 30, wav=wav)
+    ref = oracle_fista(src, par, 30, lam0, noise, owav=owav)
+    check_fista(src, X, cost, l1, ref)
+    assert rel(wav.reconstruct(X.data), owav.reconstruct(ref["x"])) < TOL_MODEL
+
+
 @pytest.mark.parametrize("name,N,level", [("db1", 4096, None), ("sym2", 3136, None), ("coif1", 3136, 4), ("db4", 15936, None),
                                           ("coif2", 15936, None), ("coif2", 63936, None), ("coif2", 1032, 3)])
 def test_wavelet_vec4_kernels_are_bit_exact(name, N, level):

@@ -183,8 +183,13 @@ def test_filter_banks_agree_with_oracle_tables():
 def test_wavelet_constructor_errors():
     with pytest.raises(TypeError):
         cs.UndecimatedWavelet(wavelet_name=3)
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(TypeError):
         cs.DiscreteWavelet(wavelet_name="db2", mode=None)
+    with pytest.raises(ValueError):
+        cs.DiscreteWavelet(wavelet_name="db2", mode="mirror")
+    for mode in ("periodization", "symmetric", "zero", "constant", "reflect", "periodic", "smooth", "antisymmetric", "antireflect"):
+        w = cs.DiscreteWavelet(wavelet_name="db2", mode=mode)
+        assert w.calculate_ncoeffs(np.zeros(9)) == (5 if mode == "periodization" else 6)  # pywt.dwt_coeff_len(9, 4, mode)
     with pytest.raises(NotImplementedError):
         cs.UndecimatedWavelet(wavelet_name="not-a-wavelet")
     w = cs.UndecimatedWavelet(wavelet_name="IUWT")

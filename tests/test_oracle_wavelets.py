@@ -103,3 +103,54 @@ def test_closed_form_iswt_equals_the_literal_one():
             cs = [rng.normal(size=(N, 3)) for _ in range(L + 1)]
             for norm in (False, True):
                 np.testing.assert_allclose(ob.iswt_fast(cs, bank, norm), ob.iswt(cs, bank, norm), rtol=0, atol=1e-13)
+
+
+# ---- decimated transform with signal-extension modes --------------------------------------------------------
+def test_dwt_symmetric_matches_the_pywavelets_documentation_value():
+    """PyWavelets' documentation (pywt.dwt, "Single level dwt"): ``pywt.dwt([3, 7, 1, 1, -2, 5, 4, 6], 'db2')`` with the
+    default mode 'symmetric' prints these ten numbers -- a known answer that pins the filter orientation, the odd-position
+    sampling and the band length (N + F - 1) // 2 of the restatement."""
+    bank = ob.filter_bank("db2")
+    cA, cD = ob._dwt_ext(np.array([3, 7, 1, 1, -2, 5, 4, 6.0]), bank[0], bank[1], "symmetric")
+    np.testing.assert_allclose(cA, [5.65685425, 7.39923721, 0.22414387, 3.33677403, 7.77817459], atol=5e-9)
+    np.testing.assert_allclose(cD, [-2.44948974, -1.60368225, -4.44140056, -0.41361256, 1.22474487], atol=5e-9)
+
+
+def test_signal_extensions_match_numpy_pad():
+    """pywt.pad documents the correspondence of its modes with numpy.pad (zero = constant, constant = edge, periodic = wrap,
+    antireflect = reflect with reflect_type='odd'); extensions longer than the signal keep following numpy's repetition."""
+    rng = np.random.default_rng(0)
+    kw = {"zero": dict(mode="constant"), "constant": dict(mode="edge"), "symmetric": dict(mode="symmetric"),
+          "reflect": dict(mode="reflect"), "periodic": dict(mode="wrap"), "antireflect": dict(mode="reflect", reflect_type="odd")}
+    for N in (1, 2, 5, 8):
+        x = rng.normal(size=N)
+        for mode, k in kw.items():
+            if N == 1 and mode in ("reflect", "antireflect"):
+                continue
+            for pad in (1, 3, max(N - 1, 1), 2 * N + 3):
+                np.testing.assert_allclose(ob.ext_sample(x, np.arange(-pad, N + pad), mode), np.pad(x, pad, **k), atol=1e-12)
+    x = np.array([1.0, 2.0, 4.0])
+    np.testing.assert_allclose(ob.ext_sample(x, np.arange(-2, 5), "smooth"), [-1, 0, 1, 2, 4, 6, 8])
+    np.testing.assert_allclose(ob.ext_sample(x, np.arange(-2, 5), "antisymmetric"), [-2, -1, 1, 2, 4, -4, -2])
+
+
+@pytest.mark.parametrize("mode", ob.EXT_MODES)
+def test_extension_modes_reconstruct_perfectly(mode):
+    rng = np.random.default_rng(1)
+    for name in ("db1", "db2", "coif2", "sym4"):
+        bank = ob.filter_bank(name)
+        F = bank[0].shape[0]
+        for N in (16, 17, 100, 3136):
+            x = rng.normal(size=(N, 2))
+            cs_ = ob.wavedec_mode(x, bank, mode)
+            n = N
+            for band in cs_[:0:-1]:      # cD_1 .. cD_L
+                n = ob.dwt_coeff_len(n, F, mode)
+                assert band.shape[0] == n
+            assert cs_[0].shape[0] == n
+            r = ob.waverec_mode(cs_, bank, mode)
+            assert r.shape[0] in (N, N + 1) and (N % 2 or r.shape[0] == N)
+            assert np.abs(r[:N] - x).max() < 5e-8  # filter tables hold ~1e-10; "smooth" extrapolates to large edge values
+    d = ob.WaveletDict("coif2", kind="dwt", mode=mode, append_signal=True)
+    x = rng.normal(size=(200, 3))
+    assert np.abs(d.reconstruct(d.decompose(x)) - 2 * x).max() < 1e-9
