@@ -21,6 +21,7 @@ EXPORTS = [
     "csr_peak", "csr_set_option", "csr_nudft_forward", "csr_nudft_adjoint", "csr_fista_nu_ws_bytes", "csr_fista_nu",
     "csr_pack_slab", "csr_unpack_slab", "csr_channel_stats", "csr_pack_planar", "csr_unpack_planar", "csr_sparse_count",
     "csr_sparse_fill", "csr_flag_mean", "csr_flag_hampel", "csr_galactic_rm_image", "csr_healpix_lookup",
+    "csr_debug_timeline",
 ]
 
 
@@ -115,6 +116,7 @@ def load():
     lib.csr_fista_nu.argtypes = [POINTER(NuSampling), c_void_p, POINTER(FistaArgs), c_void_p, c_size_t, c_void_p]
     lib.csr_profile.argtypes = [c_int]
     lib.csr_profile_collect.argtypes = [POINTER(c_double), POINTER(c_longlong)]
+    lib.csr_debug_timeline.argtypes = [POINTER(c_longlong), c_int]
     lib.csr_launch_count.argtypes = [c_int]
     lib.csr_launch_count.restype = c_longlong
     _lib = lib

@@ -314,6 +314,9 @@ struct Options {
     int tma_epi;      // ... with the residual epilogue staged through shared memory (TMA loads of b, TMA stores of r)
     int nufft;        // per-line-of-sight samplings: shared-memory NUFFT (nufft.cu) instead of the direct sums (nudft.cu)
     int fwd128;       // K-block-skipping forward transform on 128 x 128 tiles (four chunk accumulators in TMEM, b prefetched)
+    int fwd_group;    // delta-basis loop: forward tiles with at most this many active K blocks accumulate them as ONE chunk and
+                      // take the direct residual epilogue (NOT a same-bits switch: it changes how partial sums are grouped;
+                      // every run with the same value gives the same bits whichever exact shortcuts are on); 0 = off
 };
 Options& options();
 

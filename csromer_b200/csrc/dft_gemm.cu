@@ -57,7 +57,12 @@ constexpr int TMEM_COLS = 512;
 constexpr int KMASK_WORDS = 32;             // K-block activity bitmask: 32 x 32 bits, one bit per 128 K columns
 static_assert(KMASK_WORDS * 32 * 128 == kMaxSkipK, "bitmask capacity");
 constexpr int NUM_WARPS_TOTAL = 4 + EPI_WARPS;
-constexpr int SMEM_BYTES = 1024 /*alignment slack*/ + STAGES * STAGE_BYTES + 256 + NUM_WARPS_TOTAL * KMASK_WORDS * 4 + 16;
+constexpr int CS_SMEM_FLOATS = 2048;  // shared-memory copy of chan_scale for the residual epilogue (m <= 2048, shared weights)
+constexpr int XP_ROW_FLOATS = 64 + 8;  // transposing buffer of the direct residual epilogue: 8 rows x 64 columns per warp, rows
+                                       // padded by 32 bytes (conflict-free 8-byte fragment writes and 16-byte row reads)
+constexpr int XP_WARP_BYTES = 8 * XP_ROW_FLOATS * 4 + 32 * 8;  // ... + (descale, out_scale) of the warp's 32 rows
+constexpr int SMEM_MISC_BYTES = 256 + NUM_WARPS_TOTAL * KMASK_WORDS * 4 + 16;  // barriers, K masks, last_listed
+constexpr int SMEM_BYTES = 1024 /*alignment slack*/ + STAGES * STAGE_BYTES + SMEM_MISC_BYTES + CS_SMEM_FLOATS * 4 + EPI_WARPS * XP_WARP_BYTES;
 constexpr int RASTER_GROUP = 16;  // pixel tiles per rasterisation group (keeps A and B panels L2-resident)
 static_assert(SMEM_BYTES <= 232448, "shared memory budget exceeded");
 
@@ -431,6 +436,325 @@ __device__ __forceinline__ void epilogue_resid_fast(const GemmEpilogue& epi, con
     }
 }
 
+// The same epilogue as a two-deep software pipeline (dft_gemm_kernel<EPI_RESID>; ncu source page of the one-shot version:
+// two thirds of the epilogue warps' samples sit on the first use of the b values of each of the four row groups, 8 warps per
+// SM cannot hide four serial L2 / HBM round trips per tile).  A row group g = 2 lh + rh is the thread's 16 column pairs of
+// one row; resid_request() only issues its 16 loads, resid_compute() consumes them.  The kernel requests group 0
+// BEFORE it waits for the tile's accumulator chunks and group g + 1 before group g is computed.  The channel
+// factors (shared by all rows unless chan_per_pixel) come from a shared-memory copy made once per CTA.  RAGGED: the warp's 128
+// columns may cross m or end at N (m even): per-pair bounds and channel index.  Same arithmetic, same bits as
+// epilogue_tile<EPI_RESID>.
+template <bool RAGGED>
+__device__ __forceinline__ void resid_request(const GemmEpilogue& epi, int lane, int row0, int col0, int g, float2 (&in0)[16]) {
+    const int row = row0 + (lane >> 2) + 8 * (g & 1) + 16 * (g >> 1);
+    const int cbase = col0 + 2 * (lane & 3);
+    const float2* bp = reinterpret_cast<const float2*>(epi.b + (size_t)row * epi.ld_out + cbase);
+#pragma unroll
+    for (int jj = 0; jj < 16; ++jj) {
+        const bool ok = row < epi.P && (!RAGGED || cbase + 8 * jj < epi.N);
+        in0[jj] = ok ? __ldcg(bp + 4 * jj) : make_float2(0.f, 0.f);
+    }
+}
+
+template <bool RAGGED, bool CS_SMEM>
+__device__ __forceinline__ void resid_compute(const GemmEpilogue& epi, const float (&acc)[EPI_COLS], const float2 (&in0)[16], int lane,
+                                              int row0, int col0, int g, const float* cs_smem) {
+    const int quad = lane & 3;
+    const int lh = g >> 1, rh = g & 1;
+    const int cbase = col0 + 2 * quad;
+    const int h8 = epi.ld8 >> 1;
+    const int row = row0 + (lane >> 2) + 8 * rh + 16 * lh;
+    const bool row_ok = row < epi.P;
+    float dsum = 0.f, rmax = 0.f;
+    if (row_ok) {
+        const float descale = kTwiddleDescale / __ldg(epi.a_scale + row);
+        const float oscale = __ldg(epi.out_scale + row);
+        const size_t row_off = (size_t)row * epi.ld_out;
+        const float* cs_row = CS_SMEM ? cs_smem : (epi.chan_scale ? epi.chan_scale + (epi.chan_per_pixel ? (size_t)row * epi.m : 0) : nullptr);
+        __half2* hp = reinterpret_cast<__half2*>(epi.out_hi + row_off + cbase);
+        __half2* lp = reinterpret_cast<__half2*>(epi.out_lo + row_off + cbase);
+        unsigned char* o8 = epi.out8 ? epi.out8 + (size_t)row * epi.ld8 : nullptr;
+        const int chan_base = (!RAGGED && cbase >= epi.m) ? cbase - epi.m : cbase;
+#pragma unroll
+        for (int jj = 0; jj < 16; ++jj) {
+            const int col = cbase + 8 * jj;
+            if (RAGGED && col >= epi.N) continue;
+            const int chan = RAGGED ? (col >= epi.m ? col - epi.m : col) : chan_base + 8 * jj;
+            float2 cs = make_float2(1.f, 1.f);
+            if (CS_SMEM) cs = *reinterpret_cast<const float2*>(cs_smem + chan);
+            else if (cs_row != nullptr) cs = __ldg(reinterpret_cast<const float2*>(cs_row + chan));
+            const int ai = (((lh * 2 + (jj >> 3)) * 8 + (jj & 7)) * 2 + rh) * 2;
+            const float a0 = acc[ai] * descale, a1 = acc[ai + 1] * descale;
+            const float r0 = __fmaf_rn(cs.x, a0, -in0[jj].x) * oscale, r1 = __fmaf_rn(cs.y, a1, -in0[jj].y) * oscale;
+            const __half2 h = __floats2half2_rn(r0, r1);
+            const float2 hf = __half22float2(h);
+            const __half2 l = __floats2half2_rn(r0 - hf.x, r1 - hf.y);
+            hp[4 * jj] = h;
+            lp[4 * jj] = l;
+            dsum += fabsf(hf.x) + fabsf(hf.y);
+            rmax = fmaxf(rmax, fmaxf(fabsf(r0), fabsf(r1)));
+            if (o8 != nullptr) {  // kernel-uniform
+                const float2 v8 = make_float2(hf.x * kOperandScale8, hf.y * kOperandScale8);
+                if (fmaxf(fabsf(v8.x), fabsf(v8.y)) > 448.f) dsum = __int_as_float(0x7f800000);  // unscreenable row
+                // (fp8 rows are [first half | pad | second half | pad], halves ld8/2 apart: plan.cu)
+                *reinterpret_cast<__nv_fp8x2_storage_t*>(o8 + (col < epi.m ? col : col - epi.m + h8)) =
+                    __nv_cvt_float2_to_fp8x2(v8, __NV_SATFINITE, __NV_E4M3);
+            }
+        }
+    }
+    if (epi.abs_sum_out != nullptr) {  // kernel-uniform
+        dsum += __shfl_xor_sync(0xffffffffu, dsum, 1);
+        dsum += __shfl_xor_sync(0xffffffffu, dsum, 2);
+        if (quad == 0 && row_ok && dsum != 0.f) atomicAdd(epi.abs_sum_out + row, dsum);
+    }
+    if (epi.row_stat != nullptr) {  // kernel-uniform
+        rmax = fmaxf(rmax, __shfl_xor_sync(0xffffffffu, rmax, 1));
+        rmax = fmaxf(rmax, __shfl_xor_sync(0xffffffffu, rmax, 2));
+        if (quad == 0 && row_ok && rmax != 0.f)
+            atomicMax(reinterpret_cast<unsigned int*>(epi.row_stat + 4 * (size_t)row + 3), __float_as_uint(rmax));
+    }
+}
+
+// group 0 is in flight in ba when this is called (after the last accumulator chunk has been drained)
+template <bool RAGGED, bool CS_SMEM>
+__device__ __forceinline__ void resid_pipeline(const GemmEpilogue& epi, const float (&acc)[EPI_COLS], float2 (&ba)[16], float2 (&bb)[16],
+                                               int lane, int row0, int col0, const float* cs_smem) {
+    resid_request<RAGGED>(epi, lane, row0, col0, 1, bb);
+    resid_compute<RAGGED, CS_SMEM>(epi, acc, ba, lane, row0, col0, 0, cs_smem);
+    resid_request<RAGGED>(epi, lane, row0, col0, 2, ba);
+    resid_compute<RAGGED, CS_SMEM>(epi, acc, bb, lane, row0, col0, 1, cs_smem);
+    resid_request<RAGGED>(epi, lane, row0, col0, 3, bb);
+    resid_compute<RAGGED, CS_SMEM>(epi, acc, ba, lane, row0, col0, 2, cs_smem);
+    resid_compute<RAGGED, CS_SMEM>(epi, acc, bb, lane, row0, col0, 3, cs_smem);
+}
+
+// Sparse tiles (GemmEpilogue::group_sparse): the tile's few active K blocks were accumulated as ONE chunk, so there is no
+// register accumulator to keep.  The thread requests ALL its b values (64 float2) before it waits for the tensor core, then
+// reads the TMEM accumulator in four 16-row x 64-column pieces and finishes each piece from registers: no global-load latency
+// is left between the end of the K loop and the stores.  Values and summation order as in resid_compute (one chunk added to a
+// zero accumulator is the chunk itself).  The caller has waited for the accumulator; `release` is called after the last
+// TMEM read.
+template <bool RAGGED, bool CS_SMEM>
+__device__ __forceinline__ void resid_direct_request(const GemmEpilogue& epi, int lane, int row0, int col0, float2 (&bv)[64]) {
+    const int cbase = col0 + 2 * (lane & 3);
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+        const int row = row0 + (lane >> 2) + 8 * (g & 1) + 16 * (g >> 1);
+        const float2* bp = reinterpret_cast<const float2*>(epi.b + (size_t)row * epi.ld_out + cbase);
+#pragma unroll
+        for (int jj = 0; jj < 16; ++jj) {
+            const bool ok = row < epi.P && (!RAGGED || cbase + 8 * jj < epi.N);
+            bv[g * 16 + jj] = ok ? __ldcg(bp + 4 * jj) : make_float2(0.f, 0.f);
+        }
+    }
+}
+
+template <bool RAGGED, bool CS_SMEM, typename Release>
+__device__ __forceinline__ void resid_direct(const GemmEpilogue& epi, uint32_t taddr, const float2 (&bv)[64], int lane, int row0, int col0,
+                                             const float* cs_smem, Release release) {
+    const int quad = lane & 3;
+    const int cbase = col0 + 2 * quad;
+    const int h8 = epi.ld8 >> 1;
+    const int chan_base = (!RAGGED && cbase >= epi.m) ? cbase - epi.m : cbase;
+    float descale[4], oscale[4], dsum[4], rmax[4];
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+        const int row = row0 + (lane >> 2) + 8 * (g & 1) + 16 * (g >> 1);
+        const bool row_ok = row < epi.P;
+        descale[g] = row_ok ? kTwiddleDescale / __ldg(epi.a_scale + row) : 0.f;
+        oscale[g] = row_ok ? __ldg(epi.out_scale + row) : 0.f;
+        dsum[g] = 0.f;
+        rmax[g] = 0.f;
+    }
+#pragma unroll
+    for (int lh = 0; lh < 2; ++lh) {
+#pragma unroll
+        for (int ch = 0; ch < 2; ++ch) {
+            float v[32];
+            tmem_ld_16x256b_x8(taddr + ((uint32_t)(16 * lh) << 16) + (uint32_t)(64 * ch), v);
+            if (lh == 1 && ch == 1) release();
+#pragma unroll
+            for (int rh = 0; rh < 2; ++rh) {
+                const int g = lh * 2 + rh;
+                const int row = row0 + (lane >> 2) + 8 * rh + 16 * lh;
+                if (row >= epi.P) continue;
+                const size_t row_off = (size_t)row * epi.ld_out;
+                const float* cs_row = CS_SMEM ? cs_smem : (epi.chan_scale ? epi.chan_scale + (epi.chan_per_pixel ? (size_t)row * epi.m : 0) : nullptr);
+                __half2* hp = reinterpret_cast<__half2*>(epi.out_hi + row_off + cbase);
+                __half2* lp = reinterpret_cast<__half2*>(epi.out_lo + row_off + cbase);
+                unsigned char* o8 = epi.out8 ? epi.out8 + (size_t)row * epi.ld8 : nullptr;
+#pragma unroll
+                for (int j8 = 0; j8 < 8; ++j8) {
+                    const int jj = ch * 8 + j8;
+                    const int col = cbase + 8 * jj;
+                    if (RAGGED && col >= epi.N) continue;
+                    const int chan = RAGGED ? (col >= epi.m ? col - epi.m : col) : chan_base + 8 * jj;
+                    float2 cs = make_float2(1.f, 1.f);
+                    if (CS_SMEM) cs = *reinterpret_cast<const float2*>(cs_smem + chan);
+                    else if (cs_row != nullptr) cs = __ldg(reinterpret_cast<const float2*>(cs_row + chan));
+                    const float a0 = v[(j8 * 2 + rh) * 2] * descale[g], a1 = v[(j8 * 2 + rh) * 2 + 1] * descale[g];
+                    const float2 b = bv[g * 16 + jj];
+                    const float r0 = __fmaf_rn(cs.x, a0, -b.x) * oscale[g], r1 = __fmaf_rn(cs.y, a1, -b.y) * oscale[g];
+                    const __half2 h = __floats2half2_rn(r0, r1);
+                    const float2 hf = __half22float2(h);
+                    const __half2 l = __floats2half2_rn(r0 - hf.x, r1 - hf.y);
+                    hp[4 * jj] = h;
+                    lp[4 * jj] = l;
+                    dsum[g] += fabsf(hf.x) + fabsf(hf.y);
+                    rmax[g] = fmaxf(rmax[g], fmaxf(fabsf(r0), fabsf(r1)));
+                    if (o8 != nullptr) {  // kernel-uniform
+                        const float2 v8 = make_float2(hf.x * kOperandScale8, hf.y * kOperandScale8);
+                        if (fmaxf(fabsf(v8.x), fabsf(v8.y)) > 448.f) dsum[g] = __int_as_float(0x7f800000);  // unscreenable row
+                        *reinterpret_cast<__nv_fp8x2_storage_t*>(o8 + (col < epi.m ? col : col - epi.m + h8)) =
+                            __nv_cvt_float2_to_fp8x2(v8, __NV_SATFINITE, __NV_E4M3);
+                    }
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+        const int row = row0 + (lane >> 2) + 8 * (g & 1) + 16 * (g >> 1);
+        const bool row_ok = row < epi.P;
+        if (epi.abs_sum_out != nullptr) {  // kernel-uniform
+            float d = dsum[g];
+            d += __shfl_xor_sync(0xffffffffu, d, 1);
+            d += __shfl_xor_sync(0xffffffffu, d, 2);
+            if (quad == 0 && row_ok && d != 0.f) atomicAdd(epi.abs_sum_out + row, d);
+        }
+        if (epi.row_stat != nullptr) {  // kernel-uniform
+            float r = rmax[g];
+            r = fmaxf(r, __shfl_xor_sync(0xffffffffu, r, 1));
+            r = fmaxf(r, __shfl_xor_sync(0xffffffffu, r, 2));
+            if (quad == 0 && row_ok && r != 0.f)
+                atomicMax(reinterpret_cast<unsigned int*>(epi.row_stat + 4 * (size_t)row + 3), __float_as_uint(r));
+        }
+    }
+}
+
+// The direct epilogue with ROW-CONTIGUOUS global accesses.  In the accumulator fragment a warp-wide 8-byte access touches eight
+// rows (eight 32-byte sectors in eight cache lines): 64 loads and 192 stores of that shape per thread and tile keep the
+// load/store unit, not the memory, busy (ncu: the epilogue warps stall on the LSU queue while b arrives at 0.5 TB/s).  Here
+// every 8-row x 64-column sub-piece of the accumulator is transposed through a 2.3 KB shared-memory buffer of the warp so that
+// a lane owns 4 consecutive columns of a row: b arrives as 16-byte loads (two rows, four cache lines per warp access, all
+// requested before the wait for the tensor core), r_hi / r_lo leave as 8-byte and the fp8 copy as 4-byte stores -- a sixth of
+// the cache-line touches and half of the memory instructions.  Needs m % 4 == 0 and channel factors shared by all rows.
+// Element arithmetic as in resid_compute (same bits); the row sums feed bounds only.
+template <bool RAGGED, bool CS_SMEM, typename Wait, typename Release>
+__device__ __forceinline__ void resid_direct_rows(const GemmEpilogue& epi, uint32_t taddr, int lane, int row0, int col0, const float* cs_smem,
+                                                  float* xp, Wait wait_acc, Release release) {
+    const int lrow = lane >> 4;          // which of the two rows of an access
+    const int lcol = 4 * (lane & 15);    // first of the lane's 4 columns inside a 64-column piece
+    float2* rowbuf = reinterpret_cast<float2*>(xp + 8 * XP_ROW_FLOATS);
+    // every b value of the thread: [lh][ch][rh][i] -> row 16 lh + 8 rh + 2 i + lrow, columns 64 ch + lcol .. + 3
+    float4 bq[32];
+#pragma unroll
+    for (int lh = 0; lh < 2; ++lh)
+#pragma unroll
+        for (int ch = 0; ch < 2; ++ch)
+#pragma unroll
+            for (int rh = 0; rh < 2; ++rh)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int row = row0 + 16 * lh + 8 * rh + 2 * i + lrow, col = col0 + 64 * ch + lcol;
+                    const bool ok = row < epi.P && (!RAGGED || col < epi.N);
+                    bq[((lh * 2 + ch) * 2 + rh) * 4 + i] =
+                        ok ? __ldcg(reinterpret_cast<const float4*>(epi.b + (size_t)row * epi.ld_out + col)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+    {   // (descale, out_scale) of the warp's 32 rows
+        const int row = row0 + lane;
+        const bool row_ok = row < epi.P;
+        __syncwarp();
+        rowbuf[lane] = make_float2(row_ok ? kTwiddleDescale / __ldg(epi.a_scale + row) : 0.f, row_ok ? __ldg(epi.out_scale + row) : 0.f);
+    }
+    float4 csv[2];
+#pragma unroll
+    for (int ch = 0; ch < 2; ++ch) {
+        const int col = col0 + 64 * ch + lcol;
+        const int chan = col >= epi.m ? col - epi.m : col;
+        csv[ch] = make_float4(1.f, 1.f, 1.f, 1.f);
+        if (CS_SMEM && (!RAGGED || col < epi.N)) csv[ch] = *reinterpret_cast<const float4*>(cs_smem + chan);
+    }
+    const int h8 = epi.ld8 >> 1;
+    __syncwarp();
+    wait_acc();
+#pragma unroll
+    for (int lh = 0; lh < 2; ++lh) {
+        float dsum[8], rmax[8];  // per (rh, i): the lane's share of a row
+#pragma unroll
+        for (int k = 0; k < 8; ++k) dsum[k] = 0.f, rmax[k] = 0.f;
+#pragma unroll
+        for (int ch = 0; ch < 2; ++ch) {
+            float v[32];
+            tmem_ld_16x256b_x8(taddr + ((uint32_t)(16 * lh) << 16) + (uint32_t)(64 * ch), v);
+            if (lh == 1 && ch == 1) release();
+            const int col = col0 + 64 * ch + lcol;
+            const bool col_ok = !RAGGED || col < epi.N;
+            const int col8 = col < epi.m ? col : col - epi.m + h8;
+#pragma unroll
+            for (int rh = 0; rh < 2; ++rh) {
+                // fragment -> rows: thread T holds (row T/4, columns 8 j + 2 (T%4), + 1) of this sub-piece
+                __syncwarp();
+#pragma unroll
+                for (int j8 = 0; j8 < 8; ++j8)
+                    *reinterpret_cast<float2*>(xp + (lane >> 2) * XP_ROW_FLOATS + 8 * j8 + 2 * (lane & 3)) =
+                        make_float2(v[(j8 * 2 + rh) * 2], v[(j8 * 2 + rh) * 2 + 1]);
+                __syncwarp();
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int lr = 16 * lh + 8 * rh + 2 * i + lrow;  // row inside the warp's 32
+                    const int row = row0 + lr;
+                    const float4 a = *reinterpret_cast<const float4*>(xp + (2 * i + lrow) * XP_ROW_FLOATS + lcol);
+                    if (row >= epi.P || !col_ok) continue;
+                    const float2 sc = rowbuf[lr];  // (descale, out_scale)
+                    const float4 b = bq[((lh * 2 + ch) * 2 + rh) * 4 + i];
+                    const float r0 = __fmaf_rn(csv[ch].x, a.x * sc.x, -b.x) * sc.y, r1 = __fmaf_rn(csv[ch].y, a.y * sc.x, -b.y) * sc.y;
+                    const float r2 = __fmaf_rn(csv[ch].z, a.z * sc.x, -b.z) * sc.y, r3 = __fmaf_rn(csv[ch].w, a.w * sc.x, -b.w) * sc.y;
+                    const __half2 h01 = __floats2half2_rn(r0, r1), h23 = __floats2half2_rn(r2, r3);
+                    const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+                    const __half2 l01 = __floats2half2_rn(r0 - f01.x, r1 - f01.y), l23 = __floats2half2_rn(r2 - f23.x, r3 - f23.y);
+                    const size_t off = (size_t)row * epi.ld_out + col;
+                    uint2 hv, lv;
+                    hv.x = *reinterpret_cast<const unsigned int*>(&h01);
+                    hv.y = *reinterpret_cast<const unsigned int*>(&h23);
+                    lv.x = *reinterpret_cast<const unsigned int*>(&l01);
+                    lv.y = *reinterpret_cast<const unsigned int*>(&l23);
+                    *reinterpret_cast<uint2*>(epi.out_hi + off) = hv;
+                    *reinterpret_cast<uint2*>(epi.out_lo + off) = lv;
+                    const int k = rh * 4 + i;
+                    dsum[k] += (fabsf(f01.x) + fabsf(f01.y)) + (fabsf(f23.x) + fabsf(f23.y));
+                    rmax[k] = fmaxf(rmax[k], fmaxf(fmaxf(fabsf(r0), fabsf(r1)), fmaxf(fabsf(r2), fabsf(r3))));
+                    if (epi.out8 != nullptr) {  // kernel-uniform
+                        const float2 v01 = make_float2(f01.x * kOperandScale8, f01.y * kOperandScale8);
+                        const float2 v23 = make_float2(f23.x * kOperandScale8, f23.y * kOperandScale8);
+                        if (fmaxf(fmaxf(fabsf(v01.x), fabsf(v01.y)), fmaxf(fabsf(v23.x), fabsf(v23.y))) > 448.f)
+                            dsum[k] = __int_as_float(0x7f800000);  // unscreenable row
+                        const unsigned int p01 = __nv_cvt_float2_to_fp8x2(v01, __NV_SATFINITE, __NV_E4M3);
+                        const unsigned int p23 = __nv_cvt_float2_to_fp8x2(v23, __NV_SATFINITE, __NV_E4M3);
+                        *reinterpret_cast<unsigned int*>(epi.out8 + (size_t)row * epi.ld8 + col8) = p01 | (p23 << 16);
+                    }
+                }
+            }
+        }
+        // row totals: the 16 lanes that share a row
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int row = row0 + 16 * lh + 8 * (k >> 2) + 2 * (k & 3) + lrow;
+            float d = dsum[k], r = rmax[k];
+#pragma unroll
+            for (int sh = 1; sh < 16; sh <<= 1) {
+                d += __shfl_xor_sync(0xffffffffu, d, sh);
+                r = fmaxf(r, __shfl_xor_sync(0xffffffffu, r, sh));
+            }
+            if ((lane & 15) == 0 && row < epi.P) {
+                if (epi.abs_sum_out != nullptr && d != 0.f) atomicAdd(epi.abs_sum_out + row, d);
+                if (epi.row_stat != nullptr && r != 0.f)
+                    atomicMax(reinterpret_cast<unsigned int*>(epi.row_stat + 4 * (size_t)row + 3), __float_as_uint(r));
+            }
+        }
+    }
+}
+
 // ---- screening (exact) ----------------------------------------------------------------------------------------
 // A pixel tile x 256-column tile whose x and z are identically zero stays zero through the FISTA update iff
 // |step * g| <= step * lambda for every element.  Far from the sources g is a few noise sigmas and lambda is tens of
@@ -486,6 +810,21 @@ __device__ __forceinline__ bool screen_tile_fails(const GemmEpilogue& epi, const
     return fail;
 }
 
+__device__ __forceinline__ bool options_rows_ok(const GemmEpilogue& epi) {
+    return epi.no_rows == 0 && (reinterpret_cast<uintptr_t>(epi.b) & 15) == 0 &&
+           ((reinterpret_cast<uintptr_t>(epi.out_hi) | reinterpret_cast<uintptr_t>(epi.out_lo)) & 7) == 0 &&
+           (epi.out8 == nullptr || ((reinterpret_cast<uintptr_t>(epi.out8) | (uintptr_t)epi.ld8 | (uintptr_t)(epi.ld8 >> 1)) & 3) == 0);
+}
+
+// Measurement aid (CSR_TIMELINE=1, csr_debug_timeline): clock64 stamps of the three roles for the first kTimelineTiles tiles of
+// every CTA of the last residual forward launch -- [cta][tile][8]: producer start / last load issued, MMA first operand seen /
+// last commit issued, epilogue tile start / last chunk drained / body done, K blocks of the tile.
+constexpr int kTimelineTiles = 16;
+__device__ long long g_timeline[160 * kTimelineTiles * 8];
+#define TL_STAMP(slot)                                                                                          \
+    if (MODE == EPI_RESID && epi.timeline && tl_n < kTimelineTiles)                                             \
+        g_timeline[((size_t)blockIdx.x * kTimelineTiles + tl_n) * 8 + (slot)] = clock64();
+
 template <int MODE>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 dft_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
@@ -519,7 +858,11 @@ dft_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
     constexpr int B_OFFSET = ONE ? A_TILE_BYTES : 2 * A_TILE_BYTES;
     int* last_listed = reinterpret_cast<int*>(smem + STAGES * STAGE_BYTES + 256 + NUM_WARPS_TOTAL * KMASK_WORDS * 4);
     uint32_t* my_mask = reinterpret_cast<uint32_t*>(smem + STAGES * STAGE_BYTES + 256) + warp * KMASK_WORDS;
-    const bool skip = epi.a_kflags != nullptr;
+    const bool have_flags = epi.a_kflags != nullptr;
+    const bool skip = have_flags && epi.no_kskip == 0;
+    // sparse grouping (EPI_RESID): a tile with at most group_sparse active K blocks accumulates them as ONE chunk -- decided
+    // from the flags alone, so a run that walks every K block (no_kskip) groups, and rounds, exactly like one that skips
+    const int group_max = (MODE == EPI_RESID && have_flags) ? epi.group_sparse : 0;
     const int kwords = (KB + 1) >> 1;  // one flag word per 128 K columns = 2 K blocks
 
     if (warp == 0 && lane == 0) {
@@ -544,6 +887,11 @@ dft_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
         tmem_alloc(tmem_ptr, TMEM_COLS);
         tmem_relinquish();
     }
+    // residual epilogue: the channel factors shared by all lines of sight, once per CTA
+    float* cs_smem = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES + SMEM_MISC_BYTES);
+    const bool cs_in_smem = MODE == EPI_RESID && epi.chan_scale != nullptr && epi.chan_per_pixel == 0 && epi.m <= CS_SMEM_FLOATS;
+    if (cs_in_smem)
+        for (int i = threadIdx.x; i < epi.m; i += NUM_THREADS) cs_smem[i] = __ldg(epi.chan_scale + i);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -577,16 +925,21 @@ dft_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
                 if (IS_SCREEN && ti + (int)gridDim.x < total_tiles) quiet_next = tile_quiet(tile_id(ti + gridDim.x));
                 if (IS_SCREEN && !quiet) continue;  // tile with signal: left to the three-product kernel
                 if (skip) build_kmask(epi.a_kflags + (size_t)mt * epi.a_kflag_ld, kwords, KB, my_mask, lane);
+                const int tl_n = (ti - (int)blockIdx.x) / (int)gridDim.x;
                 if (lane == 0) {
+                    TL_STAMP(0);
                     // Pull the fp32 tiles the fused epilogue of THIS tile will read (z and x_old, or b) into L2 shortly
                     // before the K loop ends, so the epilogue's loads see L2 latency instead of HBM latency.  Not
                     // earlier: more than an L2's worth of data streams through per tile period and would evict them.
-                    const int pf_kb = max(0, KB - prefetch_lead);
+                    // (a K-block-skipping tile is a few blocks long and the producer runs a tile ahead: prefetch at once)
+                    const int pf_kb = skip ? 0 : max(0, KB - prefetch_lead);
+                    bool pf_due = true;
                     for (int kb = skip ? next_active_kb(my_mask, 0, KB) : 0; kb < KB;
                          kb = skip ? next_active_kb(my_mask, kb + 1, KB) : kb + 1) {
-                        if (kb == pf_kb) {
+                        if (pf_due && kb >= pf_kb) {
                             if (num_prefetch > 0) tma_prefetch_2d(&map_pf0, nt * BN, mt * BM);
                             if (num_prefetch > 1) tma_prefetch_2d(&map_pf1, nt * BN, mt * BM);
+                            pf_due = false;
                         }
                         mbar_wait(&empty[stage], phase ^ 1);
                         uint8_t* sb = stage_base + stage * STAGE_STRIDE;
@@ -600,6 +953,11 @@ dft_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
                             phase ^= 1;
                         }
                     }
+                    if (pf_due && skip) {  // (no active K block at all: the epilogue still reads b)
+                        if (num_prefetch > 0) tma_prefetch_2d(&map_pf0, nt * BN, mt * BM);
+                        if (num_prefetch > 1) tma_prefetch_2d(&map_pf1, nt * BN, mt * BM);
+                    }
+                    TL_STAMP(1);
                 }
                 __syncwarp();  // the mask slot is rewritten for the next tile
             }
@@ -621,19 +979,23 @@ dft_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
                 const bool quiet = quiet_next;
                 if (IS_SCREEN && ti + (int)gridDim.x < total_tiles) quiet_next = tile_quiet(tile_id(ti + gridDim.x));
                 if (IS_SCREEN && !quiet) continue;
-                if (skip) {
+                bool single = false;
+                if (skip || group_max > 0) {
                     int mt, nt;
                     tile_coords(tile_id(ti), MT, NT, mt, nt);
-                    build_kmask(epi.a_kflags + (size_t)mt * epi.a_kflag_ld, kwords, KB, my_mask, lane);
+                    const int nact = build_kmask(epi.a_kflags + (size_t)mt * epi.a_kflag_ld, kwords, KB, my_mask, lane);
+                    single = group_max > 0 && nact <= group_max;
                 }
+                const int tl_n = (ti - (int)blockIdx.x) / (int)gridDim.x;
                 if (lane == 0) {
                     // A chunk is the set of (active) K blocks inside one aligned window of `chunk_kb` blocks, so skipping
                     // zero blocks never changes how the others are grouped: bit-identical to the dense loop.
                     int in_chunk = 0, cur_win = -1;  // K blocks accumulated into the current chunk so far / its window
                     uint32_t d_tmem = 0;
+                    int tl_kb = 0;
                     for (int kb = skip ? next_active_kb(my_mask, 0, KB) : 0; kb < KB;
                          kb = skip ? next_active_kb(my_mask, kb + 1, KB) : kb + 1) {
-                        const int win = kb / chunk_kb;
+                        const int win = single ? 0 : kb / chunk_kb;
                         if (in_chunk != 0 && win != cur_win) {
                             umma_commit(&tmem_full[chunk & 1]);  // chunk accumulator complete
                             ++chunk;
@@ -648,6 +1010,7 @@ dft_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
                         }
                         mbar_wait(&full[stage], phase);
                         tc_fence_after();
+                        if (tl_kb++ == 0) { TL_STAMP(2); }
                         const uint32_t sa_hi = smem_u32(stage_base + stage * STAGE_STRIDE);
                         const uint32_t sa_lo = sa_hi + A_TILE_BYTES;
                         const uint32_t sb_hi = sa_hi + B_OFFSET;
@@ -680,6 +1043,9 @@ dft_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
                         umma_commit(&tmem_full[chunk & 1]);
                         ++chunk;
                     }
+                    TL_STAMP(3);
+                    if (MODE == EPI_RESID && epi.timeline && tl_n < kTimelineTiles)
+                        g_timeline[((size_t)blockIdx.x * kTimelineTiles + tl_n) * 8 + 7] = tl_kb;
                 }
                 chunk = __shfl_sync(0xffffffffu, chunk, 0);
             }
@@ -699,6 +1065,10 @@ dft_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
                                 (epi.out8 == nullptr || ((reinterpret_cast<uintptr_t>(epi.out8) | (uintptr_t)epi.ld8) & 1) == 0) &&
                                 true;
         const int half = ew >> 2;        // which 128 of the tile's 256 columns
+        // the direct epilogue with row-contiguous accesses: 16-byte views of b, 8-byte views of r_hi / r_lo, 4-byte views of the
+        // fp8 copy, a 4-column group never straddles m, channel factors shared by all rows (or none)
+        const bool rows_ok = MODE == EPI_RESID && resid_fast && (epi.m & 3) == 0 && (epi.ld_out & 3) == 0 && options_rows_ok(epi) &&
+                             (cs_in_smem || epi.chan_scale == nullptr);
         uint32_t chunk = 0;
         for (int ti = blockIdx.x; ti < total_tiles; ti += gridDim.x) {
             const int t = tile_id(ti);
@@ -712,18 +1082,90 @@ dft_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
 #pragma unroll
             for (int j = 0; j < EPI_COLS; ++j) acc[j] = 0.f;
             int nchunks = (KB + chunk_kb - 1) / chunk_kb;
-            if (skip) {  // count the windows that hold an active K block, exactly as the MMA thread walks them
-                build_kmask(epi.a_kflags + (size_t)mt * epi.a_kflag_ld, kwords, KB, my_mask, lane);
-                int c = 0;
-                if (lane == 0) {
-                    int cur_win = -1;
-                    for (int kb = next_active_kb(my_mask, 0, KB); kb < KB; kb = next_active_kb(my_mask, kb + 1, KB)) {
-                        const int win = kb / chunk_kb;
-                        c += (win != cur_win);
-                        cur_win = win;
+            const int tl_n = (ti - (int)blockIdx.x) / (int)gridDim.x;
+            if (ew == 0 && lane == 0) { TL_STAMP(4); }
+            const int ecol0 = nt * BN + half * EPI_COLS, erow0 = mt * BM + sub * 32;
+            const bool ragged = !(ecol0 + EPI_COLS <= epi.N && (ecol0 + EPI_COLS <= epi.m || ecol0 >= epi.m));  // (warp-uniform)
+            bool single = false;
+            if (skip || group_max > 0) {
+                const int nact = build_kmask(epi.a_kflags + (size_t)mt * epi.a_kflag_ld, kwords, KB, my_mask, lane);
+                single = group_max > 0 && nact <= group_max;
+                if (single) {
+                    nchunks = (skip && nact == 0) ? 0 : 1;
+                } else if (skip) {  // count the windows that hold an active K block, exactly as the MMA thread walks them
+                    int c = 0;
+                    if (lane == 0) {
+                        int cur_win = -1;
+                        for (int kb = next_active_kb(my_mask, 0, KB); kb < KB; kb = next_active_kb(my_mask, kb + 1, KB)) {
+                            const int win = kb / chunk_kb;
+                            c += (win != cur_win);
+                            cur_win = win;
+                        }
                     }
+                    nchunks = __shfl_sync(0xffffffffu, c, 0);
                 }
-                nchunks = __shfl_sync(0xffffffffu, c, 0);
+            }
+            if (MODE == EPI_RESID && resid_fast && single && nchunks == 1) {
+                // sparse tile: straight from TMEM, every b value requested before the wait (resid_direct)
+                if (ecol0 < epi.N) {
+                    float2 bv[64];
+                    const int buf = chunk & 1;
+                    const uint32_t taddr = tmem_base + ((uint32_t)(sub * 32) << 16) + (uint32_t)(buf * BN + half * EPI_COLS);
+                    auto release = [&]() {
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&tmem_empty[buf]);
+                    };
+                    auto wait_acc = [&]() {
+                        mbar_wait(&tmem_full[buf], (chunk >> 1) & 1);
+                        tc_fence_after();
+                        if (ew == 0 && lane == 0) { TL_STAMP(5); }
+                    };
+                    if (rows_ok) {  // row-contiguous global accesses (shared-memory transposition of the fragment)
+                        float* xp = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES + SMEM_MISC_BYTES + CS_SMEM_FLOATS * 4 + ew * XP_WARP_BYTES);
+                        if (cs_in_smem) {
+                            if (ragged) resid_direct_rows<true, true>(epi, taddr, lane, erow0, ecol0, cs_smem, xp, wait_acc, release);
+                            else resid_direct_rows<false, true>(epi, taddr, lane, erow0, ecol0, cs_smem, xp, wait_acc, release);
+                        } else {
+                            if (ragged) resid_direct_rows<true, false>(epi, taddr, lane, erow0, ecol0, nullptr, xp, wait_acc, release);
+                            else resid_direct_rows<false, false>(epi, taddr, lane, erow0, ecol0, nullptr, xp, wait_acc, release);
+                        }
+                    } else if (cs_in_smem) {
+                        if (ragged) {
+                            resid_direct_request<true, true>(epi, lane, erow0, ecol0, bv);
+                            wait_acc();
+                            resid_direct<true, true>(epi, taddr, bv, lane, erow0, ecol0, cs_smem, release);
+                        } else {
+                            resid_direct_request<false, true>(epi, lane, erow0, ecol0, bv);
+                            wait_acc();
+                            resid_direct<false, true>(epi, taddr, bv, lane, erow0, ecol0, cs_smem, release);
+                        }
+                    } else {
+                        if (ragged) {
+                            resid_direct_request<true, false>(epi, lane, erow0, ecol0, bv);
+                            wait_acc();
+                            resid_direct<true, false>(epi, taddr, bv, lane, erow0, ecol0, nullptr, release);
+                        } else {
+                            resid_direct_request<false, false>(epi, lane, erow0, ecol0, bv);
+                            wait_acc();
+                            resid_direct<false, false>(epi, taddr, bv, lane, erow0, ecol0, nullptr, release);
+                        }
+                    }
+                } else {  // columns beyond the matrix: nothing to write, the accumulator is released as soon as it is complete
+                    const int buf = chunk & 1;
+                    mbar_wait(&tmem_full[buf], (chunk >> 1) & 1);
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&tmem_empty[buf]);
+                }
+                ++chunk;
+                if (ew == 0 && lane == 0) { TL_STAMP(6); }
+                continue;
+            }
+            // residual epilogue, pipelined: the b values of the first row group travel while the K loop runs
+            float2 bva[16], bvb[16];
+            if (MODE == EPI_RESID && resid_fast) {
+                if (ragged) resid_request<true>(epi, lane, erow0, ecol0, 0, bva);
+                else resid_request<false>(epi, lane, erow0, ecol0, 0, bva);
             }
             for (int c = 0; c < nchunks; ++c, ++chunk) {
                 const int buf = chunk & 1;
@@ -734,18 +1176,26 @@ dft_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&tmem_empty[buf]);
             }
+            if (ew == 0 && lane == 0) { TL_STAMP(5); }
             if constexpr (IS_SCREEN) {
                 const bool fail = screen_tile_fails<F8>(epi, acc, lane, mt * BM + sub * 32, nt * BN + half * EPI_COLS, K);
                 if (__any_sync(0xffffffffu, fail)) {
                     if (lane == 0 && atomicMax(last_listed, ti) < ti) epi.out_list[atomicAdd(epi.out_count, 1)] = t;
                 }
+            } else if (MODE == EPI_RESID && resid_fast) {  // (kernel-uniform; the inner choices are warp-uniform)
+                if (ecol0 < epi.N) {
+                    if (cs_in_smem) {
+                        if (ragged) resid_pipeline<true, true>(epi, acc, bva, bvb, lane, erow0, ecol0, cs_smem);
+                        else resid_pipeline<false, true>(epi, acc, bva, bvb, lane, erow0, ecol0, cs_smem);
+                    } else {
+                        if (ragged) resid_pipeline<true, false>(epi, acc, bva, bvb, lane, erow0, ecol0, nullptr);
+                        else resid_pipeline<false, false>(epi, acc, bva, bvb, lane, erow0, ecol0, nullptr);
+                    }
+                }
             } else {
-                const int ecol0 = nt * BN + half * EPI_COLS;
-                if (MODE == EPI_RESID && resid_fast && ecol0 + EPI_COLS <= epi.N && (ecol0 + EPI_COLS <= epi.m || ecol0 >= epi.m))
-                    epilogue_resid_fast(epi, acc, lane, mt * BM + sub * 32, ecol0);  // (warp-uniform choice)
-                else
-                    epilogue_tile<MODE == EPI_PLAIN1 ? EPI_PLAIN : MODE>(epi, acc, lane, mt * BM + sub * 32, ecol0);
+                epilogue_tile<MODE == EPI_PLAIN1 ? EPI_PLAIN : MODE>(epi, acc, lane, erow0, ecol0);
             }
+            if (ew == 0 && lane == 0) { TL_STAMP(6); }
         }
     }
 
@@ -756,6 +1206,7 @@ dft_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
         tmem_dealloc(tmem_base, TMEM_COLS);
     }
 }
+#undef TL_STAMP
 
 
 // ---- fp8 screening on CTA pairs (cta_group::2) ---------------------------------------------------------------------
@@ -2356,7 +2807,11 @@ int launch_dft_gemm(const csr_plan* plan, bool adjoint, const __half* a_hi, cons
     GemmEpilogue epi = epi_in;
     static const int debug_flags = getenv("CSR_DEBUG_EPI") ? atoi(getenv("CSR_DEBUG_EPI")) : 0;  // measurement aid only
     epi.debug = debug_flags;
+    static const int timeline = getenv("CSR_TIMELINE") ? atoi(getenv("CSR_TIMELINE")) : 0;  // measurement aid only
+    epi.timeline = timeline;
     epi.no_fast = options().resid_fast == 0;
+    static const int no_rows = getenv("CSR_NO_RESID_ROWS") != nullptr;  // measurement aid: fragment-shaped direct epilogue
+    epi.no_rows = no_rows;
     const int K = adjoint ? 2 * plan->m : 2 * plan->n;
     const int ldk = adjoint ? plan->ld2m : plan->ld2n;
     epi.P = P;
@@ -2409,7 +2864,7 @@ int launch_dft_gemm(const csr_plan* plan, bool adjoint, const __half* a_hi, cons
     // epilogue: every 2-block accumulation chunk costs a cross-SM hand-shake, and a warp's four 4 KiB passes of dependent
     // bulk copies are latency bound), so the residual transform takes the pair kernel only in the dense regime or on request
     // (option pair3 = 2).
-    const bool pair_resid = options().pair3 >= 2 || epi.a_kflags == nullptr;
+    const bool pair_resid = options().pair3 >= 2 || epi.a_kflags == nullptr || (epi.no_kskip != 0 && epi.group_sparse == 0);
     if (options().pair3 != 0 && options().pair != 0 && P > BM && epi.tile_list == nullptr && epi.debug == 0 &&
         (epi.mode == EPI_PLAIN || (epi.mode == EPI_RESID && pair_resid))) {
         if (epi.mode == EPI_PLAIN) return launch_pair3<EPI_PLAIN, false>(plan, adjoint, ma_hi, ma_lo, ma_hi, ma_hi, ma_hi, P, epi, stream);
@@ -2439,6 +2894,13 @@ int launch_dft_gemm(const csr_plan* plan, bool adjoint, const __half* a_hi, cons
     return CSR_ERR_ARG;
 }
 
+
+extern "C" int csr_debug_timeline(long long* out, int cap) {
+    CSR_REQUIRE(out && cap > 0, "csr_debug_timeline: bad argument");
+    const size_t n = std::min((size_t)cap, sizeof(g_timeline) / sizeof(long long));
+    CSR_CUDA(cudaMemcpyFromSymbol(out, g_timeline, n * sizeof(long long)));
+    return (int)n;
+}
 
 // ---- helpers of the wavelet-domain screening (fista.cu) ------------------------------------------------------------
 // eps[p]: everything the two dropped products and the rounding of both evaluations can add to one output element of

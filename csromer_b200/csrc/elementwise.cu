@@ -255,6 +255,28 @@ int launch_block_flags(const float* z, int ld, int cols, int P, unsigned char* f
     return CSR_OK;
 }
 
+// tile_flags of the STATE (x or z non-zero), as the FISTA epilogue maintains them under zero_skip -- for runs without that
+// shortcut, so that the forward transform groups its K blocks identically in both (GemmEpilogue::group_sparse)
+__global__ void state_tile_flags_kernel(const float* __restrict__ x, const float* __restrict__ z, int ld, int cols, int flag_ld,
+                                        unsigned char* __restrict__ tile_flags) {
+    const int p = blockIdx.x;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int blk = warp; blk < flag_ld; blk += EW_THREADS / 32) {
+        int nz = 0;
+        for (int c = blk * 128 + lane; c < min(cols, blk * 128 + 128); c += 32)
+            nz |= (x[(size_t)p * ld + c] != 0.f) | (z[(size_t)p * ld + c] != 0.f);
+        nz = __any_sync(0xffffffffu, nz);
+        if (lane == 0 && nz) tile_flags[((size_t)(p >> 7) * flag_ld + blk) * 4 + ((p >> 5) & 3)] = 1;
+    }
+}
+int launch_state_tile_flags(const float* x, const float* z, int ld, int cols, int P, int flag_ld, unsigned int* tile_flags,
+                            cudaStream_t stream) {
+    CSR_CUDA(cudaMemsetAsync(tile_flags, 0, sizeof(unsigned int) * (size_t)((P + 127) / 128) * flag_ld, stream));
+    state_tile_flags_kernel<<<P, EW_THREADS, 0, stream>>>(x, z, ld, cols, flag_ld, reinterpret_cast<unsigned char*>(tile_flags));
+    CSR_LAUNCHED();
+    return CSR_OK;
+}
+
 // scale a [P, ld] fp32 matrix in place by a scalar (used for the delta / len(x) normalisation)
 __global__ void scale_vec_kernel(float* v, int n, float f) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;

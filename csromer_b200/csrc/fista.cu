@@ -25,6 +25,8 @@ int launch_coef_update(const float* grad, float* x, float* z, int ld, int ncoef,
                        const float* noise, const int* iter_cap, int iter, float step, float beta, float* delta,
                        cudaStream_t stream);
 int launch_scale_vec(float* v, int n, float f, cudaStream_t stream);
+int launch_state_tile_flags(const float* x, const float* z, int ld, int cols, int P, int flag_ld, unsigned int* tile_flags,
+                            cudaStream_t stream);
 int launch_block_flags(const float* z, int ld, int cols, int P, unsigned char* flags, int flag_ld,
                        unsigned int* tile_flags, cudaStream_t stream);
 int wavelet_ld(const csr_wavelet* w);
@@ -268,6 +270,10 @@ extern "C" int csr_fista(csr_plan* plan, csr_wavelet* wav, const csr_fista_args*
     // forward GEMM skips K blocks whose A tile is identically zero (exact); option k_skip = 0 keeps the dense K loop
     const bool k_skip = zero_skip && options().k_skip != 0;
     const bool use_kskip = !wav && k_skip && 2 * n <= kMaxSkipK;
+    // sparse tiles of the forward transform accumulate their few active K blocks as one chunk (dft_gemm.cu, group_sparse).
+    // The grouping is read off the state flags, so runs WITHOUT the shortcuts that maintain them compute the same flags with a
+    // kernel of their own: every combination of the exact shortcuts still produces the same bits.
+    const int fwd_group = (!wav && 2 * n <= kMaxSkipK && options().fwd128 == 0 && options().pair3 < 2) ? options().fwd_group : 0;
     // adjoint tiles whose state is zero are screened with one product first (exact); option screen = 0 turns it off
     const bool use_screen = !wav && zero_skip && options().screen != 0;
     // Per-pixel weights: the weighted residual (1/n) 1[w>0] E z - (w/(s k)) d stays signal-sized (the reference's
@@ -361,6 +367,13 @@ extern "C" int csr_fista(csr_plan* plan, csr_wavelet* wav, const csr_fista_args*
             if (use_kskip || (wav_kskip && it > 0)) {
                 e.a_kflags = w.tile_flags;
                 e.a_kflag_ld = w.flag_ld;
+            }
+            if (fwd_group > 0) {
+                if (!zero_skip && (rc = launch_state_tile_flags(x, w.z, ld2n, 2 * n, P, w.flag_ld, w.tile_flags, stream))) return rc;
+                e.a_kflags = w.tile_flags;
+                e.a_kflag_ld = w.flag_ld;
+                e.no_kskip = use_kskip ? 0 : 1;
+                e.group_sparse = fwd_group;
             }
             if (use_screen || wav_screen) {
                 CSR_CUDA(cudaMemsetAsync(w.screen_hdr, 0, sizeof(float) * ((size_t)P + 8), stream));

@@ -104,7 +104,8 @@ Options& options() {
                         getenv("CSR_NO_RESCALE") == nullptr,
                         getenv("CSR_NO_PAIR3") != nullptr ? 0 : (getenv("CSR_PAIR3") != nullptr ? atoi(getenv("CSR_PAIR3")) : 1),
                         getenv("CSR_NO_TMA_EPI") == nullptr, getenv("CSR_NO_NUFFT") == nullptr,
-                        getenv("CSR_FWD128") != nullptr};   // (measured: no faster than the 256-column kernel; off by default)
+                        getenv("CSR_FWD128") != nullptr,    // (measured: no faster than the 256-column kernel; off by default)
+                        getenv("CSR_FWD_GROUP") != nullptr ? atoi(getenv("CSR_FWD_GROUP")) : 16};
     return o;
 }
 }  // namespace csr
@@ -131,6 +132,7 @@ extern "C" int csr_set_option(const char* name, int value) {
     else if (!strcmp(name, "tma_epi")) o.tma_epi = value != 0;
     else if (!strcmp(name, "nufft")) o.nufft = value != 0;
     else if (!strcmp(name, "fwd128")) o.fwd128 = value != 0;
+    else if (!strcmp(name, "fwd_group")) o.fwd_group = value < 0 ? 0 : value;   // threshold in K blocks; 0 = off
     else {
         set_error("csr_set_option: unknown option '%s'", name);
         return CSR_ERR_ARG;

@@ -90,6 +90,9 @@ struct GemmEpilogue {
     // K-block skipping (any mode): word != 0 <=> the A tile (128 rows x 128 K columns) may hold non-zeros; null = dense
     const unsigned int* a_kflags;
     int a_kflag_ld;
+    int no_kskip;                   // 1 = the flags are there for group_sparse only: walk every K block
+    int group_sparse;               // EPI_RESID forward: tiles with at most this many active K blocks (by a_kflags) accumulate
+                                    // them as one chunk and take the direct epilogue (0 = window-aligned chunks everywhere)
     // Safe screening of the FISTA adjoint (exact, see dft_gemm.cu "screening"):
     float* abs_sum_out;             // EPI_RESID: [P] += sum_c |out_hi[p, c]| (atomicAdd; zeroed by the caller)
     unsigned char* out8;            // EPI_RESID: optional fp8 e4m3 copy of out_hi * kOperandScale8, pitch ld8
@@ -115,6 +118,8 @@ struct GemmEpilogue {
     unsigned long long* mma_count;  // optional: [CSR_PROFILE_KINDS], slot count_slot += K blocks x products issued
     int count_slot;                 // profile kind of this launch (set by the launchers)
     int debug;                 // measurement aid (CSR_DEBUG_EPI): bit 0 skips epilogue loads, bit 1 skips stores
+    int timeline;              // measurement aid (CSR_TIMELINE): the residual forward kernel records role time stamps
+    int no_rows;               // measurement aid (CSR_NO_RESID_ROWS): direct residual epilogue without the row transposition
     int no_fast;               // 1 = keep the general residual epilogue everywhere (option resid_fast = 0; same bits)
 };
 

@@ -250,6 +250,11 @@ int csr_sparse_fill(const float* x, int ld, int ncols, int P, const long long* o
 #define CSR_PROFILE_KINDS 16
 int csr_profile(int enable);
 int csr_profile_collect(double* ms_by_kind, long long* count_by_kind);
+/* measurement aid: with CSR_TIMELINE=1 in the environment the K-block-skipping residual forward kernel stamps clock64() per
+ * role and tile -- [CTA][first 16 tiles][8]: producer start, last load issued, first operand seen by the MMA thread, last MMA
+ * commit issued, epilogue start, last accumulator chunk drained, epilogue done, K blocks of the tile; copies up to `cap`
+ * values of the last such launch to the HOST array `out`, returns how many (tools/fwd_timeline.py). */
+int csr_debug_timeline(long long* out, int cap);
 
 /* run-time switches of the exact shortcuts, all default 1 (measurement / test aid; results are bit-identical either
  * way): "zero_skip" (FISTA epilogue skips blocks that are and stay zero), "k_skip" (forward GEMM skips K blocks whose

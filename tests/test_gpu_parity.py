@@ -226,15 +226,22 @@ def test_sparsity_shortcuts_are_bit_exact(nch, P, K, kw):
         # (sym: the pair kernels screen +phi and -phi together, half the K; pair = 1, sym = 0 is the plain pair kernel)
         # (incr: incremental screening -- a tile that passed is tested again only when its margin may be used up)
         # (pair3 / tma: the three-product transforms on CTA pairs, with the residual epilogue staged through shared memory)
-        for zero_skip, k_skip, screen, screen8, pair, sym, incr, pair3, tma in (
-                (1, 1, 1, 1, 1, 1, 1, 1, 1), (1, 1, 1, 1, 1, 1, 1, 2, 1), (1, 1, 1, 1, 1, 1, 1, 2, 0), (1, 1, 1, 1, 1, 1, 0, 0, 0),
-                (1, 1, 1, 1, 1, 0, 0, 2, 1), (1, 1, 1, 1, 0, 0, 0, 0, 0), (1, 1, 1, 0, 0, 0, 0, 0, 0), (1, 1, 0, 0, 0, 0, 0, 0, 0),
-                (1, 0, 1, 1, 1, 1, 1, 1, 1), (1, 0, 0, 0, 0, 0, 0, 0, 0), (0, 0, 0, 0, 1, 0, 0, 2, 1), (0, 0, 0, 0, 0, 0, 0, 0, 0)):
+        # (grp: sparse tiles of the forward transform accumulate their active K blocks as one chunk -- the one switch here that
+        #  regroups partial sums, so the runs form two families, with and without it; the forward kernels on 128 x 128 tiles
+        #  (f128) and on CTA pairs (pair3 = 2) do not group and belong to the second)
+        for zero_skip, k_skip, screen, screen8, pair, sym, incr, pair3, tma, f128, grp in (
+                (1, 1, 1, 1, 1, 1, 1, 1, 1, 0, 16), (1, 1, 1, 1, 1, 1, 0, 0, 0, 0, 16), (1, 1, 1, 1, 0, 0, 0, 0, 0, 0, 16),
+                (1, 1, 1, 0, 0, 0, 0, 0, 0, 0, 16), (1, 1, 0, 0, 0, 0, 0, 0, 0, 0, 16), (1, 0, 1, 1, 1, 1, 1, 1, 1, 0, 16),
+                (1, 0, 0, 0, 0, 0, 0, 0, 0, 0, 16), (0, 0, 0, 0, 1, 0, 0, 1, 1, 0, 16), (0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 16),
+                (1, 1, 1, 1, 1, 1, 1, 1, 1, 0, 0), (1, 1, 1, 1, 1, 1, 1, 2, 1, 0, 16), (1, 1, 1, 1, 1, 1, 1, 2, 0, 0, 16),
+                (1, 1, 1, 1, 1, 0, 0, 2, 1, 0, 16), (1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 16), (0, 0, 0, 0, 1, 0, 0, 2, 1, 0, 16),
+                (0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0)):
             _lib.set_option("screen_incr", incr)
             _lib.set_option("rescale", incr)
             _lib.set_option("pair3", pair3)
             _lib.set_option("tma_epi", tma)
-            _lib.set_option("fwd128", incr)   # (the sparse forward transform on 128 x 128 tiles: on in some, off in others)
+            _lib.set_option("fwd128", f128)
+            _lib.set_option("fwd_group", grp)
             _lib.set_option("zero_skip", zero_skip)
             _lib.set_option("k_skip", k_skip)
             _lib.set_option("screen", screen)
@@ -243,7 +250,8 @@ def test_sparsity_shortcuts_are_bit_exact(nch, P, K, kw):
             _lib.set_option("sym", sym)
             _lib.set_option("resid_fast", zero_skip and screen8)   # (the lean residual epilogue: off in the plainer combinations)
             cost, X, l1, lam0, noise = run_fista(src, par, K)
-            results.append((np.array(X.data, copy=True), np.array(cost, copy=True), np.array(src.model_data, copy=True)))
+            grouped = grp > 0 and f128 == 0 and pair3 < 2
+            results.append((grouped, np.array(X.data, copy=True), np.array(cost, copy=True), np.array(src.model_data, copy=True)))
     finally:
         _lib.set_option("zero_skip", 1)
         _lib.set_option("k_skip", 1)
@@ -256,11 +264,17 @@ def test_sparsity_shortcuts_are_bit_exact(nch, P, K, kw):
         _lib.set_option("rescale", 1)
         _lib.set_option("pair3", 1)
         _lib.set_option("tma_epi", 1)
-        _lib.set_option("fwd128", 1)
-    assert np.count_nonzero(results[0][0]) > 0 and np.count_nonzero(results[0][0]) < 0.2 * results[0][0].size
-    for other in results[1:]:
-        for a, b in zip(results[0], other):
-            np.testing.assert_array_equal(a, b)
+        _lib.set_option("fwd128", 0)
+        _lib.set_option("fwd_group", 16)
+    assert np.count_nonzero(results[0][1]) > 0 and np.count_nonzero(results[0][1]) < 0.2 * results[0][1].size
+    for family in (True, False):
+        runs = [r[1:] for r in results if r[0] == family]
+        assert len(runs) >= 7
+        for other in runs[1:]:
+            for a, b in zip(runs[0], other):
+                np.testing.assert_array_equal(a, b)
+    # the two families differ in rounding only
+    assert rel(results[0][1], results[-1][1]) < 1e-5
     ref = oracle_fista(src, par, K, lam0, noise)
     check_fista(src, X, cost, l1, ref)
 
