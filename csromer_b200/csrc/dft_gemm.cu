@@ -529,123 +529,32 @@ __device__ __forceinline__ void resid_pipeline(const GemmEpilogue& epi, const fl
 }
 
 // Sparse tiles (GemmEpilogue::group_sparse): the tile's few active K blocks were accumulated as ONE chunk, so there is no
-// register accumulator to keep.  The thread requests ALL its b values (64 float2) before it waits for the tensor core, then
-// reads the TMEM accumulator in four 16-row x 64-column pieces and finishes each piece from registers: no global-load latency
-// is left between the end of the K loop and the stores.  Values and summation order as in resid_compute (one chunk added to a
-// zero accumulator is the chunk itself).  The caller has waited for the accumulator; `release` is called after the last
-// TMEM read.
-template <bool RAGGED, bool CS_SMEM>
-__device__ __forceinline__ void resid_direct_request(const GemmEpilogue& epi, int lane, int row0, int col0, float2 (&bv)[64]) {
-    const int cbase = col0 + 2 * (lane & 3);
-#pragma unroll
-    for (int g = 0; g < 4; ++g) {
-        const int row = row0 + (lane >> 2) + 8 * (g & 1) + 16 * (g >> 1);
-        const float2* bp = reinterpret_cast<const float2*>(epi.b + (size_t)row * epi.ld_out + cbase);
-#pragma unroll
-        for (int jj = 0; jj < 16; ++jj) {
-            const bool ok = row < epi.P && (!RAGGED || cbase + 8 * jj < epi.N);
-            bv[g * 16 + jj] = ok ? __ldcg(bp + 4 * jj) : make_float2(0.f, 0.f);
-        }
-    }
-}
-
-template <bool RAGGED, bool CS_SMEM, typename Release>
-__device__ __forceinline__ void resid_direct(const GemmEpilogue& epi, uint32_t taddr, const float2 (&bv)[64], int lane, int row0, int col0,
-                                             const float* cs_smem, Release release) {
-    const int quad = lane & 3;
-    const int cbase = col0 + 2 * quad;
-    const int h8 = epi.ld8 >> 1;
-    const int chan_base = (!RAGGED && cbase >= epi.m) ? cbase - epi.m : cbase;
-    float descale[4], oscale[4], dsum[4], rmax[4];
-#pragma unroll
-    for (int g = 0; g < 4; ++g) {
-        const int row = row0 + (lane >> 2) + 8 * (g & 1) + 16 * (g >> 1);
-        const bool row_ok = row < epi.P;
-        descale[g] = row_ok ? kTwiddleDescale / __ldg(epi.a_scale + row) : 0.f;
-        oscale[g] = row_ok ? __ldg(epi.out_scale + row) : 0.f;
-        dsum[g] = 0.f;
-        rmax[g] = 0.f;
-    }
-#pragma unroll
-    for (int lh = 0; lh < 2; ++lh) {
-#pragma unroll
-        for (int ch = 0; ch < 2; ++ch) {
-            float v[32];
-            tmem_ld_16x256b_x8(taddr + ((uint32_t)(16 * lh) << 16) + (uint32_t)(64 * ch), v);
-            if (lh == 1 && ch == 1) release();
-#pragma unroll
-            for (int rh = 0; rh < 2; ++rh) {
-                const int g = lh * 2 + rh;
-                const int row = row0 + (lane >> 2) + 8 * rh + 16 * lh;
-                if (row >= epi.P) continue;
-                const size_t row_off = (size_t)row * epi.ld_out;
-                const float* cs_row = CS_SMEM ? cs_smem : (epi.chan_scale ? epi.chan_scale + (epi.chan_per_pixel ? (size_t)row * epi.m : 0) : nullptr);
-                __half2* hp = reinterpret_cast<__half2*>(epi.out_hi + row_off + cbase);
-                __half2* lp = reinterpret_cast<__half2*>(epi.out_lo + row_off + cbase);
-                unsigned char* o8 = epi.out8 ? epi.out8 + (size_t)row * epi.ld8 : nullptr;
-#pragma unroll
-                for (int j8 = 0; j8 < 8; ++j8) {
-                    const int jj = ch * 8 + j8;
-                    const int col = cbase + 8 * jj;
-                    if (RAGGED && col >= epi.N) continue;
-                    const int chan = RAGGED ? (col >= epi.m ? col - epi.m : col) : chan_base + 8 * jj;
-                    float2 cs = make_float2(1.f, 1.f);
-                    if (CS_SMEM) cs = *reinterpret_cast<const float2*>(cs_smem + chan);
-                    else if (cs_row != nullptr) cs = __ldg(reinterpret_cast<const float2*>(cs_row + chan));
-                    const float a0 = v[(j8 * 2 + rh) * 2] * descale[g], a1 = v[(j8 * 2 + rh) * 2 + 1] * descale[g];
-                    const float2 b = bv[g * 16 + jj];
-                    const float r0 = __fmaf_rn(cs.x, a0, -b.x) * oscale[g], r1 = __fmaf_rn(cs.y, a1, -b.y) * oscale[g];
-                    const __half2 h = __floats2half2_rn(r0, r1);
-                    const float2 hf = __half22float2(h);
-                    const __half2 l = __floats2half2_rn(r0 - hf.x, r1 - hf.y);
-                    hp[4 * jj] = h;
-                    lp[4 * jj] = l;
-                    dsum[g] += fabsf(hf.x) + fabsf(hf.y);
-                    rmax[g] = fmaxf(rmax[g], fmaxf(fabsf(r0), fabsf(r1)));
-                    if (o8 != nullptr) {  // kernel-uniform
-                        const float2 v8 = make_float2(hf.x * kOperandScale8, hf.y * kOperandScale8);
-                        if (fmaxf(fabsf(v8.x), fabsf(v8.y)) > 448.f) dsum[g] = __int_as_float(0x7f800000);  // unscreenable row
-                        *reinterpret_cast<__nv_fp8x2_storage_t*>(o8 + (col < epi.m ? col : col - epi.m + h8)) =
-                            __nv_cvt_float2_to_fp8x2(v8, __NV_SATFINITE, __NV_E4M3);
-                    }
-                }
-            }
-        }
-    }
-#pragma unroll
-    for (int g = 0; g < 4; ++g) {
-        const int row = row0 + (lane >> 2) + 8 * (g & 1) + 16 * (g >> 1);
-        const bool row_ok = row < epi.P;
-        if (epi.abs_sum_out != nullptr) {  // kernel-uniform
-            float d = dsum[g];
-            d += __shfl_xor_sync(0xffffffffu, d, 1);
-            d += __shfl_xor_sync(0xffffffffu, d, 2);
-            if (quad == 0 && row_ok && d != 0.f) atomicAdd(epi.abs_sum_out + row, d);
-        }
-        if (epi.row_stat != nullptr) {  // kernel-uniform
-            float r = rmax[g];
-            r = fmaxf(r, __shfl_xor_sync(0xffffffffu, r, 1));
-            r = fmaxf(r, __shfl_xor_sync(0xffffffffu, r, 2));
-            if (quad == 0 && row_ok && r != 0.f)
-                atomicMax(reinterpret_cast<unsigned int*>(epi.row_stat + 4 * (size_t)row + 3), __float_as_uint(r));
-        }
-    }
-}
-
-// The direct epilogue with ROW-CONTIGUOUS global accesses.  In the accumulator fragment a warp-wide 8-byte access touches eight
+// register accumulator to keep: the thread requests ALL its b values before it waits for the tensor core, then reads the TMEM
+// accumulator in four 16-row x 64-column pieces and finishes each from registers (one chunk added to a zero accumulator is the
+// chunk itself: same values as the chunked path would give for this grouping).  The caller passes the wait for the
+// accumulator and the release of the TMEM buffer (called after the last TMEM read).
+// Global accesses are ROW-CONTIGUOUS.  In the accumulator fragment a warp-wide 8-byte access touches eight
 // rows (eight 32-byte sectors in eight cache lines): 64 loads and 192 stores of that shape per thread and tile keep the
 // load/store unit, not the memory, busy (ncu: the epilogue warps stall on the LSU queue while b arrives at 0.5 TB/s).  Here
 // every 8-row x 64-column sub-piece of the accumulator is transposed through a 2.3 KB shared-memory buffer of the warp so that
 // a lane owns 4 consecutive columns of a row: b arrives as 16-byte loads (two rows, four cache lines per warp access, all
 // requested before the wait for the tensor core), r_hi / r_lo leave as 8-byte and the fp8 copy as 4-byte stores -- a sixth of
-// the cache-line touches and half of the memory instructions.  Needs m % 4 == 0 and channel factors shared by all rows.
+// the cache-line touches and half of the memory instructions.  Needs m % 4 == 0.
 // Element arithmetic as in resid_compute (same bits); the row sums feed bounds only.
-template <bool RAGGED, bool CS_SMEM, typename Wait, typename Release>
+template <bool CS_PP, typename Wait, typename Release>
 __device__ __forceinline__ void resid_direct_rows(const GemmEpilogue& epi, uint32_t taddr, int lane, int row0, int col0, const float* cs_smem,
                                                   float* xp, Wait wait_acc, Release release) {
+    constexpr bool RAGGED = true;  // (per-group column bound: m % 4 == 0, so a group of 4 columns is inside or outside)
+    const bool CS_SMEM = cs_smem != nullptr;
     const int lrow = lane >> 4;          // which of the two rows of an access
     const int lcol = 4 * (lane & 15);    // first of the lane's 4 columns inside a 64-column piece
     float2* rowbuf = reinterpret_cast<float2*>(xp + 8 * XP_ROW_FLOATS);
+    // (descale, out_scale) of the warp's 32 rows: requested first, stored after the b requests are out
+    float rs_a = 1.f, rs_o = 0.f;
+    if (row0 + lane < epi.P) {
+        rs_a = __ldg(epi.a_scale + row0 + lane);
+        rs_o = __ldg(epi.out_scale + row0 + lane);
+    }
     // every b value of the thread: [lh][ch][rh][i] -> row 16 lh + 8 rh + 2 i + lrow, columns 64 ch + lcol .. + 3
     float4 bq[32];
 #pragma unroll
@@ -661,12 +570,8 @@ __device__ __forceinline__ void resid_direct_rows(const GemmEpilogue& epi, uint3
                     bq[((lh * 2 + ch) * 2 + rh) * 4 + i] =
                         ok ? __ldcg(reinterpret_cast<const float4*>(epi.b + (size_t)row * epi.ld_out + col)) : make_float4(0.f, 0.f, 0.f, 0.f);
                 }
-    {   // (descale, out_scale) of the warp's 32 rows
-        const int row = row0 + lane;
-        const bool row_ok = row < epi.P;
-        __syncwarp();
-        rowbuf[lane] = make_float2(row_ok ? kTwiddleDescale / __ldg(epi.a_scale + row) : 0.f, row_ok ? __ldg(epi.out_scale + row) : 0.f);
-    }
+    __syncwarp();
+    rowbuf[lane] = make_float2(row0 + lane < epi.P ? kTwiddleDescale / rs_a : 0.f, rs_o);
     float4 csv[2];
 #pragma unroll
     for (int ch = 0; ch < 2; ++ch) {
@@ -676,6 +581,20 @@ __device__ __forceinline__ void resid_direct_rows(const GemmEpilogue& epi, uint3
         if (CS_SMEM && (!RAGGED || col < epi.N)) csv[ch] = *reinterpret_cast<const float4*>(cs_smem + chan);
     }
     const int h8 = epi.ld8 >> 1;
+    // channel factors of the pixel's own (chan_per_pixel): requested one sub-piece ahead, 4 x 16 bytes per lane
+    constexpr bool cs_pp = CS_PP;  // (channel factors from global memory: the pixel's own, or more than CS_SMEM_FLOATS shared ones)
+    float4 csn[4];
+    auto request_cs = [&](int lh, int ch, int rh) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int row = row0 + 16 * lh + 8 * rh + 2 * i + lrow, col = col0 + 64 * ch + lcol;
+            const int chan = col >= epi.m ? col - epi.m : col;
+            csn[i] = (row < epi.P && col < epi.N)
+                         ? __ldg(reinterpret_cast<const float4*>(epi.chan_scale + (epi.chan_per_pixel ? (size_t)row * epi.m : 0) + chan))
+                         : make_float4(1.f, 1.f, 1.f, 1.f);
+        }
+    };
+    if (cs_pp) request_cs(0, 0, 0);
     __syncwarp();
     wait_acc();
 #pragma unroll
@@ -700,6 +619,13 @@ __device__ __forceinline__ void resid_direct_rows(const GemmEpilogue& epi, uint3
                     *reinterpret_cast<float2*>(xp + (lane >> 2) * XP_ROW_FLOATS + 8 * j8 + 2 * (lane & 3)) =
                         make_float2(v[(j8 * 2 + rh) * 2], v[(j8 * 2 + rh) * 2 + 1]);
                 __syncwarp();
+                float4 csc[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) csc[i] = cs_pp ? csn[i] : csv[ch];
+                if (cs_pp && !(lh == 1 && ch == 1 && rh == 1)) {  // next sub-piece in processing order (lh, ch, rh)
+                    const int nx = (lh * 2 + ch) * 2 + rh + 1;
+                    request_cs(nx >> 2, (nx >> 1) & 1, nx & 1);
+                }
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     const int lr = 16 * lh + 8 * rh + 2 * i + lrow;  // row inside the warp's 32
@@ -708,8 +634,9 @@ __device__ __forceinline__ void resid_direct_rows(const GemmEpilogue& epi, uint3
                     if (row >= epi.P || !col_ok) continue;
                     const float2 sc = rowbuf[lr];  // (descale, out_scale)
                     const float4 b = bq[((lh * 2 + ch) * 2 + rh) * 4 + i];
-                    const float r0 = __fmaf_rn(csv[ch].x, a.x * sc.x, -b.x) * sc.y, r1 = __fmaf_rn(csv[ch].y, a.y * sc.x, -b.y) * sc.y;
-                    const float r2 = __fmaf_rn(csv[ch].z, a.z * sc.x, -b.z) * sc.y, r3 = __fmaf_rn(csv[ch].w, a.w * sc.x, -b.w) * sc.y;
+                    const float4 cf = csc[i];
+                    const float r0 = __fmaf_rn(cf.x, a.x * sc.x, -b.x) * sc.y, r1 = __fmaf_rn(cf.y, a.y * sc.x, -b.y) * sc.y;
+                    const float r2 = __fmaf_rn(cf.z, a.z * sc.x, -b.z) * sc.y, r3 = __fmaf_rn(cf.w, a.w * sc.x, -b.w) * sc.y;
                     const __half2 h01 = __floats2half2_rn(r0, r1), h23 = __floats2half2_rn(r2, r3);
                     const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
                     const __half2 l01 = __floats2half2_rn(r0 - f01.x, r1 - f01.y), l23 = __floats2half2_rn(r2 - f23.x, r3 - f23.y);
@@ -822,7 +749,7 @@ __device__ __forceinline__ bool options_rows_ok(const GemmEpilogue& epi) {
 constexpr int kTimelineTiles = 16;
 __device__ long long g_timeline[160 * kTimelineTiles * 8];
 #define TL_STAMP(slot)                                                                                          \
-    if (MODE == EPI_RESID && epi.timeline && tl_n < kTimelineTiles)                                             \
+    if (((MODE == EPI_RESID && epi.timeline == 1) || (MODE == EPI_FISTA && epi.timeline == 2)) && tl_n < kTimelineTiles) \
         g_timeline[((size_t)blockIdx.x * kTimelineTiles + tl_n) * 8 + (slot)] = clock64();
 
 template <int MODE>
@@ -1044,7 +971,7 @@ dft_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
                         ++chunk;
                     }
                     TL_STAMP(3);
-                    if (MODE == EPI_RESID && epi.timeline && tl_n < kTimelineTiles)
+                    if (((MODE == EPI_RESID && epi.timeline == 1) || (MODE == EPI_FISTA && epi.timeline == 2)) && tl_n < kTimelineTiles)
                         g_timeline[((size_t)blockIdx.x * kTimelineTiles + tl_n) * 8 + 7] = tl_kb;
                 }
                 chunk = __shfl_sync(0xffffffffu, chunk, 0);
@@ -1068,7 +995,7 @@ dft_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
         // the direct epilogue with row-contiguous accesses: 16-byte views of b, 8-byte views of r_hi / r_lo, 4-byte views of the
         // fp8 copy, a 4-column group never straddles m, channel factors shared by all rows (or none)
         const bool rows_ok = MODE == EPI_RESID && resid_fast && (epi.m & 3) == 0 && (epi.ld_out & 3) == 0 && options_rows_ok(epi) &&
-                             (cs_in_smem || epi.chan_scale == nullptr);
+                             (cs_in_smem || epi.chan_scale == nullptr || (reinterpret_cast<uintptr_t>(epi.chan_scale) & 15) == 0);
         uint32_t chunk = 0;
         for (int ti = blockIdx.x; ti < total_tiles; ti += gridDim.x) {
             const int t = tile_id(ti);
@@ -1105,10 +1032,9 @@ dft_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
                     nchunks = __shfl_sync(0xffffffffu, c, 0);
                 }
             }
-            if (MODE == EPI_RESID && resid_fast && single && nchunks == 1) {
-                // sparse tile: straight from TMEM, every b value requested before the wait (resid_direct)
+            if (MODE == EPI_RESID && rows_ok && single && nchunks == 1) {
+                // sparse tile: straight from TMEM, every b value requested before the wait (resid_direct_rows)
                 if (ecol0 < epi.N) {
-                    float2 bv[64];
                     const int buf = chunk & 1;
                     const uint32_t taddr = tmem_base + ((uint32_t)(sub * 32) << 16) + (uint32_t)(buf * BN + half * EPI_COLS);
                     auto release = [&]() {
@@ -1121,36 +1047,11 @@ dft_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
                         tc_fence_after();
                         if (ew == 0 && lane == 0) { TL_STAMP(5); }
                     };
-                    if (rows_ok) {  // row-contiguous global accesses (shared-memory transposition of the fragment)
-                        float* xp = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES + SMEM_MISC_BYTES + CS_SMEM_FLOATS * 4 + ew * XP_WARP_BYTES);
-                        if (cs_in_smem) {
-                            if (ragged) resid_direct_rows<true, true>(epi, taddr, lane, erow0, ecol0, cs_smem, xp, wait_acc, release);
-                            else resid_direct_rows<false, true>(epi, taddr, lane, erow0, ecol0, cs_smem, xp, wait_acc, release);
-                        } else {
-                            if (ragged) resid_direct_rows<true, false>(epi, taddr, lane, erow0, ecol0, nullptr, xp, wait_acc, release);
-                            else resid_direct_rows<false, false>(epi, taddr, lane, erow0, ecol0, nullptr, xp, wait_acc, release);
-                        }
-                    } else if (cs_in_smem) {
-                        if (ragged) {
-                            resid_direct_request<true, true>(epi, lane, erow0, ecol0, bv);
-                            wait_acc();
-                            resid_direct<true, true>(epi, taddr, bv, lane, erow0, ecol0, cs_smem, release);
-                        } else {
-                            resid_direct_request<false, true>(epi, lane, erow0, ecol0, bv);
-                            wait_acc();
-                            resid_direct<false, true>(epi, taddr, bv, lane, erow0, ecol0, cs_smem, release);
-                        }
-                    } else {
-                        if (ragged) {
-                            resid_direct_request<true, false>(epi, lane, erow0, ecol0, bv);
-                            wait_acc();
-                            resid_direct<true, false>(epi, taddr, bv, lane, erow0, ecol0, nullptr, release);
-                        } else {
-                            resid_direct_request<false, false>(epi, lane, erow0, ecol0, bv);
-                            wait_acc();
-                            resid_direct<false, false>(epi, taddr, bv, lane, erow0, ecol0, nullptr, release);
-                        }
-                    }
+                    float* xp = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES + SMEM_MISC_BYTES + CS_SMEM_FLOATS * 4 + ew * XP_WARP_BYTES);
+                    if (!cs_in_smem && epi.chan_scale != nullptr)
+                        resid_direct_rows<true>(epi, taddr, lane, erow0, ecol0, nullptr, xp, wait_acc, release);
+                    else
+                        resid_direct_rows<false>(epi, taddr, lane, erow0, ecol0, cs_in_smem ? cs_smem : nullptr, xp, wait_acc, release);
                 } else {  // columns beyond the matrix: nothing to write, the accumulator is released as soon as it is complete
                     const int buf = chunk & 1;
                     mbar_wait(&tmem_full[buf], (chunk >> 1) & 1);
@@ -2809,6 +2710,11 @@ int launch_dft_gemm(const csr_plan* plan, bool adjoint, const __half* a_hi, cons
     epi.debug = debug_flags;
     static const int timeline = getenv("CSR_TIMELINE") ? atoi(getenv("CSR_TIMELINE")) : 0;  // measurement aid only
     epi.timeline = timeline;
+    if ((timeline == 1 && epi.mode == EPI_RESID) || (timeline == 2 && epi.mode == EPI_FISTA)) {  // the record is of the last launch only
+        void* tl = nullptr;
+        CSR_CUDA(cudaGetSymbolAddress(&tl, g_timeline));
+        CSR_CUDA(cudaMemsetAsync(tl, 0, sizeof(g_timeline), stream));
+    }
     epi.no_fast = options().resid_fast == 0;
     static const int no_rows = getenv("CSR_NO_RESID_ROWS") != nullptr;  // measurement aid: fragment-shaped direct epilogue
     epi.no_rows = no_rows;

@@ -11,7 +11,7 @@ import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-os.environ.setdefault("CSR_TIMELINE", "1")
+os.environ.setdefault("CSR_TIMELINE", "1")   # 2 = the three-product adjoint with the FISTA epilogue instead
 import bench  # noqa: E402
 from csromer_b200 import _lib  # noqa: E402
 
@@ -30,6 +30,7 @@ n = 160 * 16 * 8
 buf = np.zeros(n, dtype=np.int64)
 got = ctx.lib.csr_debug_timeline(buf.ctypes.data_as(ctypes.POINTER(ctypes.c_longlong)), n)
 t = buf[:got].reshape(-1, 16, 8)[:148]
+print("CTAs with work:", int((t[:, 0, 6] > 0).sum()), " tiles per CTA (max):", int((t[:, :, 6] > 0).sum(axis=1).max()))
 print("tile  n  kblocks | prod_span  mma_wait_first  mma_span | epi_wait  epi_body | period(epi end to end)  [median clocks; x0.51 ns at 1965 MHz]")
 for k in range(10):
     v = t[:, k, :]
@@ -42,8 +43,10 @@ for k in range(10):
     print("%4d %3d %7.1f | %9d %15d %9d | %8d %9d | %8d" % (k, ok.sum(), np.mean(v[:, 7]), med(v[:, 1] - v[:, 0]), med(v[:, 2] - v[:, 0]),
           med(v[:, 3] - v[:, 2]), med(v[:, 5] - v[:, 4]), med(v[:, 6] - v[:, 5]), med(per)))
 # how far ahead of the epilogue the other roles run: producer start of tile k+1 minus epilogue end of tile k
-v0, v1 = t[:, 1, :], t[:, 2, :]
+v0, v1 = t[:, 0, :], t[:, 1, :]
 ok = (v1[:, 6] > 0)
-print("producer start of tile 2 minus epilogue end of tile 1 (median):", int(np.median(v1[ok, 0] - v0[ok, 6])))
-print("MMA last commit of tile 2 minus epilogue end of tile 1 (median):", int(np.median(v1[ok, 3] - v0[ok, 6])))
-print("epilogue start of tile 2 minus epilogue end of tile 1 (median):", int(np.median(v1[ok, 4] - v0[ok, 6])))
+if not ok.any():
+    sys.exit(0)
+print("producer start of tile 1 minus epilogue end of tile 0 (median):", int(np.median(v1[ok, 0] - v0[ok, 6])))
+print("MMA last commit of tile 1 minus epilogue end of tile 0 (median):", int(np.median(v1[ok, 3] - v0[ok, 6])))
+print("epilogue start of tile 1 minus epilogue end of tile 0 (median):", int(np.median(v1[ok, 4] - v0[ok, 6])))
