@@ -301,24 +301,39 @@ class DevicePlan:
 
     def fista(self, data, w, s, k, x, lambda0, noise, iters, step=1.0, norm_factor=1.0, wavelet=None,
               use_dirty_as_guess=False, want_dirty=True, want_model=True, want_delta=False, iter_cap=None,
-              want_mma_blocks=False):
+              want_mma_blocks=False, out=None):
         """Run the fused loop.  All tensors are fp32 on the device; ``x`` ([P, ldx]) is updated in place.
         Returns dict(f_dirty, model, residual, cost[P,2], delta[, mma_blocks]).  ``mma_blocks`` (measurement aid) is the
         number of 128 x 256 x 64 tensor-core blocks the in-loop GEMMs issued, by kind: [three-product, fp16 screening,
-        fp8 screening, unused] (3 per tile and K block when dense)."""
+        fp8 screening, unused] (3 per tile and K block when dense).  ``out``: the dict a previous call with the same shapes
+        and ``want_*`` flags returned -- its tensors are written again instead of new ones being allocated (a slab loop that
+        reuses its buffers repeats the call with identical arguments, which the library replays as one CUDA graph)."""
         P = data.shape[0]
         dev = self.device
-        out = dict(f_dirty=None, model=None, residual=None, cost=None, delta=None)
-        if want_dirty:
-            out["f_dirty"] = torch.empty((P, self.ld2n), dtype=torch.float32, device=dev)
-        if want_model:
-            out["model"] = torch.empty((P, self.ld2m), dtype=torch.float32, device=dev)
-            out["residual"] = torch.zeros((P, self.ld2m), dtype=torch.float32, device=dev)
-            out["cost"] = torch.empty((P, 2), dtype=torch.float32, device=dev)
-        if want_delta:
-            out["delta"] = torch.zeros((P,), dtype=torch.float32, device=dev)
-        if want_mma_blocks:
-            out["mma_blocks"] = torch.zeros((16,), dtype=torch.int64, device=dev)
+        if out is not None:
+            for key, want in (("f_dirty", want_dirty), ("model", want_model), ("residual", want_model), ("cost", want_model),
+                              ("delta", want_delta), ("mma_blocks", want_mma_blocks)):
+                t = out.get(key)
+                if (t is not None) != bool(want) or (t is not None and t.shape[0] != (16 if key == "mma_blocks" else P)):
+                    raise ValueError("out does not match this call (%s)" % key)
+            if want_model:
+                out["residual"].zero_()
+            if want_delta:
+                out["delta"].zero_()
+            if want_mma_blocks:
+                out["mma_blocks"].zero_()
+        else:
+            out = dict(f_dirty=None, model=None, residual=None, cost=None, delta=None)
+            if want_dirty:
+                out["f_dirty"] = torch.empty((P, self.ld2n), dtype=torch.float32, device=dev)
+            if want_model:
+                out["model"] = torch.empty((P, self.ld2m), dtype=torch.float32, device=dev)
+                out["residual"] = torch.zeros((P, self.ld2m), dtype=torch.float32, device=dev)
+                out["cost"] = torch.empty((P, 2), dtype=torch.float32, device=dev)
+            if want_delta:
+                out["delta"] = torch.zeros((P,), dtype=torch.float32, device=dev)
+            if want_mma_blocks:
+                out["mma_blocks"] = torch.zeros((16,), dtype=torch.int64, device=dev)
         whandle = wavelet.handle if wavelet is not None else None
         need = self.lib.csr_fista_ws_bytes(self.handle, whandle, P)
         ws = self.ws.get(need, dev)

@@ -132,8 +132,8 @@ def check(rc, what):
 def set_option(name, value):
     """toggle one of the exact shortcuts (``zero_skip``, ``k_skip``, ``screen``, ``screen8``, ``pair``, ``sym``,
     ``resid_fast``, ``screen16_pair``, ``fused_wavelet``, ``wavelet_vec4``, ``wavelet_screen``, ``screen_incr``, ``rescale``,
-    ``pair3``, ``tma_epi``, ``fwd128``; ``nufft`` switches the per-line-of-sight transforms between the NUFFT and the direct sums);
-    results do not change"""
+    ``pair3``, ``tma_epi``, ``fwd128``, ``graph``: results do not change; ``nufft`` switches the per-line-of-sight transforms
+    between the NUFFT and the direct sums, ``fwd_group`` sets how sparse forward tiles group their partial sums: last-bit changes)"""
     check(load().csr_set_option(name.encode(), int(value)), "csr_set_option")
 
 

@@ -13,6 +13,7 @@ namespace csr {
 // ---- host-side error handling ------------------------------------------------------------------------
 void set_error(const char* fmt, ...);
 long long& launch_counter();
+unsigned long long next_uid();
 
 #define CSR_CUDA(call)                                                                               \
     do {                                                                                             \
@@ -317,6 +318,7 @@ struct Options {
     int fwd_group;    // delta-basis loop: forward tiles with at most this many active K blocks accumulate them as ONE chunk and
                       // take the direct residual epilogue (NOT a same-bits switch: it changes how partial sums are grouped;
                       // every run with the same value gives the same bits whichever exact shortcuts are on); 0 = off
+    int graph;        // csr_fista: a call repeated with identical arguments is replayed as one CUDA graph
 };
 Options& options();
 

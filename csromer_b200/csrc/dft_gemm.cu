@@ -2489,6 +2489,7 @@ static cudaError_t pooled_event(cudaEvent_t* ev) {
     return cudaEventCreate(ev);
 }
 
+bool profile_enabled() { return g_profile; }
 // used by the wavelet launchers (kinds 6 = fused synthesis, 7 = fused analysis + update)
 bool profile_start(cudaStream_t stream, cudaEvent_t* start, cudaEvent_t* stop) {
     if (!g_profile) return false;

@@ -8,7 +8,10 @@
 // Wavelet basis, per iteration: synthesis -> split -> forward GEMM -> adjoint GEMM (plain) -> analysis ->
 // coefficient update.  No CPU fallback exists anywhere in this file.
 #include <math.h>
+#include <stdio.h>
 #include <stdlib.h>
+
+#include <vector>
 
 #include "plan.cuh"
 
@@ -183,6 +186,9 @@ static int transform(csr_plan* plan, bool adjoint, const float* in, const float*
     return launch_dft_gemm(plan, adjoint, t.a_hi, t.a_lo, P, e, stream);
 }
 
+struct FistaWs;
+static int fista_dispatch(csr_plan* plan, csr_wavelet* wav, const csr_fista_args& a, FistaWs& w, void* ws, size_t ws_bytes,
+                          cudaStream_t stream);
 }  // namespace csr
 
 using namespace csr;
@@ -226,6 +232,13 @@ extern "C" int csr_fista(csr_plan* plan, csr_wavelet* wav, const csr_fista_args*
     if (wav) CSR_REQUIRE(round_up(wav->ncoef, 8) == a.ldx, "csr_fista: wavelet basis needs ldx == round_up(ncoef, 8)");
     cudaStream_t stream = (cudaStream_t)stream_;
     CSR_CUDA(cudaSetDevice(plan->device));
+    return fista_dispatch(plan, wav, a, w, ws, ws_bytes, stream);
+}
+
+namespace csr {
+static int fista_run(csr_plan* plan, csr_wavelet* wav, const csr_fista_args& a, FistaWs& w, cudaStream_t stream) {
+    const int P = a.P, m = plan->m, n = plan->n;
+    const int ncoef = wav ? wav->ncoef : 2 * n;
     int rc;
     const int ld2m = plan->ld2m, ld2n = plan->ld2n, ldc = a.ldx;
     float* f_dirty = a.f_dirty ? a.f_dirty : w.f_dirty;
@@ -588,3 +601,99 @@ extern "C" int csr_fista(csr_plan* plan, csr_wavelet* wav, const csr_fista_args*
     }
     return CSR_OK;
 }
+
+// ---- CUDA-graph replay of a repeated call -----------------------------------------------------------------------------
+// A K = 100 call is ~1700 launches and memsets; between two of them the device idles for a few microseconds, about a tenth of a
+// C3 step.  Nothing the host does inside the loop depends on device results (tile lists, counts and clocks all live on the
+// device), so the SECOND call with identical arguments -- same plan, wavelet, pointers, sizes, iteration count and option
+// values: what a cube loop does with its slabs -- is captured into a graph, and that and every later one is a single graph
+// launch.  Keys hold the uid of the plan / wavelet, not just their addresses.  Profiling, the time-line aid and option graph = 0
+// keep the plain launches.
+bool profile_enabled();
+struct FistaGraph {
+    std::vector<unsigned char> key;
+    cudaGraphExec_t exec;
+    long long launches;
+    unsigned long long used;
+};
+static std::vector<FistaGraph> g_graphs;
+static std::vector<std::vector<unsigned char>> g_seen;
+static unsigned long long g_graph_clock = 0;
+
+static int fista_dispatch(csr_plan* plan, csr_wavelet* wav, const csr_fista_args& a, FistaWs& w, void* ws, size_t ws_bytes,
+                          cudaStream_t stream) {
+    static const bool timeline = getenv("CSR_TIMELINE") != nullptr;
+    static const bool verbose = getenv("CSR_DEBUG_GRAPH") != nullptr;
+    cudaStreamCaptureStatus capturing = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(stream, &capturing) != cudaSuccess) cudaGetLastError();
+    if (options().graph == 0 || a.iters < 2 || profile_enabled() || timeline || capturing != cudaStreamCaptureStatusNone)
+        return fista_run(plan, wav, a, w, stream);
+    std::vector<unsigned char> key(sizeof(a) + sizeof(Options) + 6 * sizeof(unsigned long long));
+    {
+        unsigned char* k = key.data();
+        memcpy(k, &a, sizeof(a));
+        k += sizeof(a);
+        memcpy(k, &options(), sizeof(Options));
+        k += sizeof(Options);
+        const unsigned long long extra[6] = {plan->uid, wav ? wav->uid : 0ull, (unsigned long long)(uintptr_t)ws, (unsigned long long)ws_bytes,
+                                             (unsigned long long)(uintptr_t)plan, (unsigned long long)(uintptr_t)wav};
+        memcpy(k, extra, sizeof(extra));
+    }
+    for (FistaGraph& g : g_graphs) {
+        if (g.key == key) {
+            g.used = ++g_graph_clock;
+            CSR_CUDA(cudaGraphLaunch(g.exec, stream));
+            launch_counter() += g.launches;
+            if (verbose) fprintf(stderr, "csr_fista: graph replay (%lld launches)\n", g.launches);
+            return CSR_OK;
+        }
+    }
+    bool seen = false;
+    for (const auto& k : g_seen) seen = seen || k == key;
+    if (!seen) {  // first call with these arguments: plain launches (a one-off call never pays for a capture)
+        if (g_seen.size() >= 16) g_seen.erase(g_seen.begin());
+        g_seen.push_back(key);
+        return fista_run(plan, wav, a, w, stream);
+    }
+    const long long before = launch_counter();
+    // (the legacy default stream cannot be captured: record on a stream of the library's own -- a graph is not tied to the stream
+    //  it was captured on -- and launch the result into the caller's)
+    static cudaStream_t cap_streams[64] = {};
+    cudaStream_t& cap = cap_streams[plan->device & 63];
+    if (cap == nullptr && cudaStreamCreateWithFlags(&cap, cudaStreamNonBlocking) != cudaSuccess) {
+        cap = nullptr;
+        cudaGetLastError();
+        return fista_run(plan, wav, a, w, stream);
+    }
+    if (cudaStreamBeginCapture(cap, cudaStreamCaptureModeRelaxed) != cudaSuccess) {
+        cudaGetLastError();
+        if (verbose) fprintf(stderr, "csr_fista: cudaStreamBeginCapture failed\n");
+        return fista_run(plan, wav, a, w, stream);
+    }
+    const int rc = fista_run(plan, wav, a, w, cap);
+    cudaGraph_t graph = nullptr;
+    const cudaError_t ce = cudaStreamEndCapture(cap, &graph);
+    const long long launches = launch_counter() - before;
+    cudaGraphExec_t exec = nullptr;
+    if (rc != CSR_OK || ce != cudaSuccess || graph == nullptr || cudaGraphInstantiate(&exec, graph, 0) != cudaSuccess) {
+        if (graph) cudaGraphDestroy(graph);
+        cudaGetLastError();
+        launch_counter() = before;
+        if (verbose) fprintf(stderr, "csr_fista: capture failed (rc %d, cuda %d)\n", rc, (int)ce);
+        if (rc != CSR_OK) return rc;
+        return fista_run(plan, wav, a, w, stream);  // (nothing has run yet: a capture only records)
+    }
+    cudaGraphDestroy(graph);
+    if (g_graphs.size() >= 8) {  // evict the least recently used
+        size_t lru = 0;
+        for (size_t i = 1; i < g_graphs.size(); ++i)
+            if (g_graphs[i].used < g_graphs[lru].used) lru = i;
+        cudaGraphExecDestroy(g_graphs[lru].exec);
+        g_graphs.erase(g_graphs.begin() + lru);
+    }
+    g_graphs.push_back({key, exec, launches, ++g_graph_clock});
+    if (verbose) fprintf(stderr, "csr_fista: captured a graph of %lld launches\n", launches);
+    CSR_CUDA(cudaGraphLaunch(exec, stream));
+    return CSR_OK;
+}
+}  // namespace csr

@@ -26,6 +26,10 @@ void set_error(const char* fmt, ...) {
     va_end(ap);
 }
 long long& launch_counter() { return g_launches; }
+unsigned long long next_uid() {
+    static unsigned long long uid = 0;
+    return ++uid;
+}
 
 // T[c, jj] (2m x 2n): rows = [Re chan | Im chan], cols = [Re phi | Im phi]:   [[cos, -sin], [sin, cos]]
 // one thread per (i, j); j fastest -> coalesced writes of the forward-orientation table.
@@ -105,7 +109,8 @@ Options& options() {
                         getenv("CSR_NO_PAIR3") != nullptr ? 0 : (getenv("CSR_PAIR3") != nullptr ? atoi(getenv("CSR_PAIR3")) : 1),
                         getenv("CSR_NO_TMA_EPI") == nullptr, getenv("CSR_NO_NUFFT") == nullptr,
                         getenv("CSR_FWD128") != nullptr,    // (measured: no faster than the 256-column kernel; off by default)
-                        getenv("CSR_FWD_GROUP") != nullptr ? atoi(getenv("CSR_FWD_GROUP")) : 16};
+                        getenv("CSR_FWD_GROUP") != nullptr ? atoi(getenv("CSR_FWD_GROUP")) : 16,
+                        getenv("CSR_NO_GRAPH") == nullptr};
     return o;
 }
 }  // namespace csr
@@ -132,6 +137,7 @@ extern "C" int csr_set_option(const char* name, int value) {
     else if (!strcmp(name, "tma_epi")) o.tma_epi = value != 0;
     else if (!strcmp(name, "nufft")) o.nufft = value != 0;
     else if (!strcmp(name, "fwd128")) o.fwd128 = value != 0;
+    else if (!strcmp(name, "graph")) o.graph = value != 0;
     else if (!strcmp(name, "fwd_group")) o.fwd_group = value < 0 ? 0 : value;   // threshold in K blocks; 0 = off
     else {
         set_error("csr_set_option: unknown option '%s'", name);
@@ -233,6 +239,7 @@ extern "C" int csr_plan_create(csr_plan** out, const double* lambda2, int m, dou
     CSR_CUDA(cudaSetDevice(device));
     csr_plan* p = new csr_plan();
     memset(p, 0, sizeof(*p));
+    p->uid = next_uid();
     p->device = device;
     p->m = m;
     p->n = n;

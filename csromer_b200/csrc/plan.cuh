@@ -3,6 +3,7 @@
 #include "common.cuh"
 
 struct csr_plan {
+    unsigned long long uid;  // unique per created plan (keys of the CUDA-graph cache: an address can be reused, a uid cannot)
     int device;
     int m, n;        // channels, Faraday-depth samples
     int ld2m, ld2n;  // row pitches (elements) of every [P, 2m] / [P, 2n] matrix, multiples of 8
@@ -34,6 +35,7 @@ struct csr_plan {
 };
 
 struct csr_wavelet {
+    unsigned long long uid;
     int device;
     int kind;  // 0 = undecimated (swt), 1 = decimated (dwt)
     int ext;   // decimated only: 0 = periodization, 1.. = signal-extension mode (csr_wavelet_create: kind - 1)

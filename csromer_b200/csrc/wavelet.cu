@@ -1221,6 +1221,7 @@ extern "C" int csr_wavelet_create(csr_wavelet** out, int kind, const double* dec
     *out = nullptr;
     csr_wavelet* w = new csr_wavelet();
     memset(w, 0, sizeof(*w));
+    w->uid = next_uid();
     w->device = device;
     w->kind = kind;
     w->ext = ext;

@@ -279,6 +279,58 @@ def test_sparsity_shortcuts_are_bit_exact(nch, P, K, kw):
     check_fista(src, X, cost, l1, ref)
 
 
+def test_repeated_call_is_replayed_as_a_cuda_graph():
+    """csr_fista called again with identical arguments (same buffers: `out=` reuse) is captured on the second call and
+    replayed as one CUDA graph from then on: same bits as plain launches, same launch accounting, new data honoured."""
+    import torch
+    from csromer_b200 import _device as dv
+    from csromer_b200 import _lib
+    src, par = make_batch(200, 150, seed=77, mixed=True)
+    dft = cs.NDFT1D(dataset=src, parameter=par)
+    plan = dft.device_plan()
+    dev = plan.device
+    data, _ = dv.pack_planar(src.data, plan.m, plan.ld2m, dev)
+    P, K = data.shape[0], 25
+    w = torch.as_tensor(np.asarray(src.w), dtype=torch.float32, device=dev)
+    s = torch.as_tensor(np.asarray(src.s), dtype=torch.float32, device=dev)
+    k = dv.per_pixel_vector(src.k, P, dev, "k")
+    lam = torch.full((P,), 40.0 * float(np.mean(src.theo_noise)), device=dev)
+    nz = lam / (2 * K)
+    lib = _lib.load()
+
+    def run(x, out=None):
+        lib.csr_launch_count(1)
+        o = plan.fista(data, w, s, k, x, lam, nz, K, use_dirty_as_guess=True, want_delta=True, out=out)
+        torch.cuda.synchronize()
+        return o, int(lib.csr_launch_count(0))
+
+    _lib.set_option("graph", 0)
+    try:
+        x0 = torch.zeros((P, plan.ld2n), device=dev)
+        ref, n_ref = run(x0)
+        ref = {key: t.clone() for key, t in ref.items() if t is not None}
+    finally:
+        _lib.set_option("graph", 1)
+    x = torch.zeros((P, plan.ld2n), device=dev)
+    out, counts = None, []
+    for call in range(4):      # plain, capture + launch, replay, replay
+        out, n = run(x, out)
+        counts.append(n)
+        assert torch.equal(x, x0), call
+        for key, t in ref.items():
+            if key == "delta":   # (sums of atomics: the order of the additions is not fixed)
+                assert torch.allclose(out[key], t, rtol=1e-4, atol=0), (call, key)
+            else:
+                assert torch.equal(out[key], t), (call, key)
+    assert counts == [n_ref] * 4 and 0 < torch.count_nonzero(x) < 0.2 * x.numel()
+    # a replay reads the buffers as they are now
+    data.mul_(0.5)
+    lam.mul_(0.5)
+    nz.mul_(0.5)
+    out, _ = run(x, out)
+    assert rel(x.cpu().numpy(), 0.5 * x0.cpu().numpy()) < 1e-5 and not torch.equal(x, x0)
+
+
 @pytest.mark.parametrize("per_pixel", [False, True])
 def test_incremental_screening_skips_work_and_keeps_the_bits(per_pixel):
     """incremental screening on a slab large enough for the pair kernels (P > 128): the screening GEMMs issue fewer
