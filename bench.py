@@ -10,9 +10,9 @@ north-star target: wavelet-regularised FISTA at the 4000-channel sampling), each
 per-kernel roofline and clocks; `parity` holds the in-run correctness checks of every workload AT BENCH SCALE.
 
 Workloads (K_fista = 100 iterations, lambda0 = 40 theo_noise, noise = lambda0 / 200):
-  c3  512 x 512 px x 1000 ch (JVLA 1.008-2.031 GHz), n_phi = 7968, shared lambda^2, delta-basis L1, slabs of 16384 LOS
+  c3  512 x 512 px x 1000 ch (JVLA 1.008-2.031 GHz), n_phi = 7968, shared lambda^2, delta-basis L1, slabs of 32768 LOS
   c4  1024 x 1024 px x 2000 ch, n_phi = 15968, per-pixel weights + 10-20 % flagged channels per pixel, per-pixel Galactic
-      RM removed on the device inside the step, delta-basis L1, slabs of 8192 LOS
+      RM removed on the device inside the step, delta-basis L1, slabs of 16384 LOS
   c5  2048 x 2048 px x 4000 ch (MeerKAT 0.9-1.67 GHz), n_phi = 31968, undecimated coif2 wavelet basis (L = 6, 447 552
       coefficients per LOS), step = 1 / lambda_max, slabs of 4096 LOS
 One STEP = one pass of the whole hot path (dirty spectrum + K iterations + final evaluate = 2 K + 2 transforms per line
@@ -54,10 +54,10 @@ if ROOT not in sys.path:
 SIGMA = 0.2 * 0.0035
 JVLA, MEERKAT = (1.008e9, 2.031e9), (0.9e9, 1.67e9)
 WORKLOADS = {
-    "c3": dict(m=1000, n=7968, slab=16384, band=JVLA, basis="delta", seed=1234,
+    "c3": dict(m=1000, n=7968, slab=32768, band=JVLA, basis="delta", seed=1234,
                text="C3: 512x512 px x 1000 ch cube (JVLA 1.008-2.031 GHz), shared lambda^2, n_phi=7968, delta-basis L1 FISTA, "
                     "exact DFT operator"),
-    "c4": dict(m=2000, n=15968, slab=8192, band=JVLA, basis="delta", seed=1235,
+    "c4": dict(m=2000, n=15968, slab=16384, band=JVLA, basis="delta", seed=1235,
                text="C4: 1024x1024 px x 2000 ch cube (JVLA 1.008-2.031 GHz), n_phi=15968, per-pixel weights and 10-20 % "
                     "flagged channels per pixel, per-pixel Galactic RM removed on the device inside the step, delta-basis "
                     "L1 FISTA, exact DFT operator"),
