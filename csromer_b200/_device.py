@@ -301,13 +301,15 @@ class DevicePlan:
 
     def fista(self, data, w, s, k, x, lambda0, noise, iters, step=1.0, norm_factor=1.0, wavelet=None,
               use_dirty_as_guess=False, want_dirty=True, want_model=True, want_delta=False, iter_cap=None,
-              want_mma_blocks=False, out=None):
+              want_mma_blocks=False, out=None, f_dirty_in=None):
         """Run the fused loop.  All tensors are fp32 on the device; ``x`` ([P, ldx]) is updated in place.
         Returns dict(f_dirty, model, residual, cost[P,2], delta[, mma_blocks]).  ``mma_blocks`` (measurement aid) is the
         number of 128 x 256 x 64 tensor-core blocks the in-loop GEMMs issued, by kind: [three-product, fp16 screening,
         fp8 screening, unused] (3 per tile and K block when dense).  ``out``: the dict a previous call with the same shapes
         and ``want_*`` flags returned -- its tensors are written again instead of new ones being allocated (a slab loop that
-        reuses its buffers repeats the call with identical arguments, which the library replays as one CUDA graph)."""
+        reuses its buffers repeats the call with identical arguments, which the library replays as one CUDA graph).
+        ``f_dirty_in``: planar ``[P, ld2n]`` dirty spectrum of these data and weights when the caller already has it
+        (``plan.adjoint``): the loop does not compute it again; with ``want_dirty=False`` it is returned as ``f_dirty``."""
         P = data.shape[0]
         dev = self.device
         if out is not None:
@@ -355,6 +357,12 @@ class DevicePlan:
         for key in ("f_dirty", "model", "residual", "cost", "delta"):
             setattr(a, key, out[key].data_ptr() if out[key] is not None else None)
         a.use_dirty_as_guess = int(bool(use_dirty_as_guess))
+        if f_dirty_in is not None:
+            if tuple(f_dirty_in.shape) != (P, self.ld2n) or f_dirty_in.dtype != torch.float32 or not f_dirty_in.is_contiguous():
+                raise ValueError("f_dirty_in must be a contiguous fp32 [P, ld2n] tensor")
+            a.f_dirty_in = f_dirty_in.data_ptr()
+            if out["f_dirty"] is None:
+                out["f_dirty"] = f_dirty_in
         _lib.check(self.lib.csr_fista(self.handle, whandle, ctypes.byref(a), tptr(ws), ws.numel(), stream_ptr()),
                    "csr_fista")
         return out

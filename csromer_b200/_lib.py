@@ -36,7 +36,7 @@ class FistaArgs(ctypes.Structure):
         ("data", c_void_p), ("w", c_void_p), ("s", c_void_p), ("k", c_void_p), ("x", c_void_p), ("ldx", c_int),
         ("lambda0", c_void_p), ("noise", c_void_p), ("iter_cap", c_void_p), ("f_dirty", c_void_p), ("model", c_void_p),
         ("residual", c_void_p), ("cost", c_void_p), ("delta", c_void_p), ("use_dirty_as_guess", c_int),
-        ("mma_blocks", c_void_p), ("s_per_pixel", c_int),
+        ("mma_blocks", c_void_p), ("s_per_pixel", c_int), ("f_dirty_in", c_void_p),
     ]
 
 

@@ -250,8 +250,13 @@ static int fista_run(csr_plan* plan, csr_wavelet* wav, const csr_fista_args& a, 
     if ((rc = launch_split_rows(w.b, ld2m, P, 2 * m, nullptr, 0, m, nullptr, 0, w.r_hi, w.r_lo, ld2m, w.rscale, 0, stream)))
         return rc;
 
-    // 2. dirty spectrum F_dirty = backward(data) = E^H b   (chi2.py:18-19)
-    {
+    // 2. dirty spectrum F_dirty = backward(data) = E^H b   (chi2.py:18-19) -- unless the caller already has it
+    if (a.f_dirty_in != nullptr) {
+        if (a.f_dirty != nullptr && a.f_dirty != a.f_dirty_in)
+            CSR_CUDA(cudaMemcpyAsync(a.f_dirty, a.f_dirty_in, sizeof(float) * (size_t)P * ld2n, cudaMemcpyDeviceToDevice, stream));
+        else
+            f_dirty = const_cast<float*>(a.f_dirty_in);
+    } else {
         GemmEpilogue e = {};
         e.mode = EPI_PLAIN;
         e.a_scale = w.rscale;

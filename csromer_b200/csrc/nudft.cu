@@ -316,6 +316,7 @@ extern "C" int csr_fista_nu(const csr_nu_sampling* s, csr_wavelet* wav, const cs
     if (rc) return rc;
     CSR_REQUIRE(a.iters >= 0 && a.data && a.w && a.s && a.k && a.x && a.lambda0 && a.noise, "csr_fista_nu: null input array");
     CSR_REQUIRE(a.w_per_pixel == 1 && a.s_per_pixel == 1, "csr_fista_nu: w and s must be per line of sight ([P, m])");
+    CSR_REQUIRE(a.f_dirty_in == nullptr, "csr_fista_nu: f_dirty_in is not supported");
     const int P = a.P, m = s->m, n = s->n;
     const int ld2m = round_up(2 * m, 8), ld2n = round_up(2 * n, 8);
     const int ncoef = wav ? wav->ncoef : 2 * n;

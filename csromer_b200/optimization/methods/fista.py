@@ -133,7 +133,17 @@ class FISTA(Optimizer):
             ncoef, ldx = 2 * plan.n, plan.ld2n
         if x0.shape[0] != ncoef:
             raise ValueError("guess_param.data has length %d, expected %d real values" % (x0.shape[0], ncoef))
-        x, xpix = dv.pack_real(x0, ncoef, ldx, dev)
+        # README.md:183-190 starts from F_dirty = dft.backward(dataset.data): when the guess is exactly that tensor (untouched,
+        # same dataset), its planar device copy is still at hand -- no transpose back, no second dirty spectrum in the loop
+        dirty_planar = None
+        if engine is None and like_torch and hasattr(op, "dirty_of") and hasattr(self.guess_param, "complex_source"):
+            dirty_planar = op.dirty_of(self.guess_param.complex_source())
+            if dirty_planar is not None and tuple(dirty_planar.shape) != (P, ldx):
+                dirty_planar = None
+        if dirty_planar is not None:
+            x = torch.empty((P, ldx), dtype=torch.float32, device=dev)
+        else:
+            x, xpix = dv.pack_real(x0, ncoef, ldx, dev)
         if x.shape[0] != P:
             if x.shape[0] == 1:
                 x = x.expand(P, ldx).contiguous()
@@ -145,8 +155,12 @@ class FISTA(Optimizer):
         if cap is not None:
             cap_t = torch.as_tensor(np.broadcast_to(cap.reshape(-1), (P,)).astype(np.int32)).to(dev)
 
-        out = plan.fista(data, w, s, k, x, lam_t, noise_t, iters, step=self.step, norm_factor=chi2.norm_factor,
-                         wavelet=engine, iter_cap=cap_t)
+        if dirty_planar is not None:
+            out = plan.fista(data, w, s, k, x, lam_t, noise_t, iters, step=self.step, norm_factor=chi2.norm_factor,
+                             iter_cap=cap_t, use_dirty_as_guess=True, want_dirty=False, f_dirty_in=dirty_planar)
+        else:
+            out = plan.fista(data, w, s, k, x, lam_t, noise_t, iters, step=self.step, norm_factor=chi2.norm_factor,
+                             wavelet=engine, iter_cap=cap_t)
 
         # side effects the reference leaves behind
         model_dev, resid_dev, like = out["model"], out["residual"], ds.data

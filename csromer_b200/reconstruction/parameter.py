@@ -6,6 +6,8 @@ wavelet coefficients.  As in the reference, assigning ``data`` overwrites ``n`` 
  -- operators therefore use ``len(parameter.phi)``, never ``parameter.n``.
 ``convolve`` (the restore step, parameter.py:139-169) runs on the GPU (``csrc/restore.cu``).
 """
+import weakref
+
 import numpy as np
 
 from ..utils import complex_to_real, next_power_2, real_to_complex
@@ -38,6 +40,7 @@ class Parameter:
     @data.setter
     def data(self, val):
         self._data = val
+        self._real_of = None
         if val is not None:
             self._n = len(val)
 
@@ -78,7 +81,25 @@ class Parameter:
     def complex_data_to_real(self):
         if not _is_complex(self._data):
             raise TypeError("Parameter data is not complex64")
-        self.data = complex_to_real(self._data)
+        src = self._data
+        self.data = complex_to_real(src)
+        if hasattr(src, "_version"):   # torch: remember which complex tensor this planar copy was made from (FISTA._run_fused)
+            self._real_of = (weakref.ref(src), src._version, weakref.ref(self._data), self._data._version)
+
+    def __getstate__(self):
+        state = dict(self.__dict__)
+        state["_real_of"] = None   # (weak references: not picklable, and meaningless in another process)
+        return state
+
+    def complex_source(self):
+        """the complex tensor ``data`` was made from by ``complex_data_to_real`` if neither has been modified since, else None"""
+        r = getattr(self, "_real_of", None)
+        if r is None:
+            return None
+        src, real = r[0](), r[2]()
+        if src is None or real is None or real is not self._data or src._version != r[1] or real._version != r[3]:
+            return None
+        return src
 
     def real_data_to_complex(self):
         if _is_complex(self._data):

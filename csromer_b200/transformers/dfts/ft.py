@@ -12,6 +12,8 @@ import copy
 from abc import ABCMeta, abstractmethod
 from dataclasses import dataclass
 
+import weakref
+
 import numpy as np
 import torch
 
@@ -72,8 +74,10 @@ class FT(metaclass=ABCMeta):
         s = np.asarray(ds.s, dtype=np.float64)
         return w, s
 
-    def _adjoint(self, b, row_scale_value):
-        """row_scale * E^H ((w/s) b) for ``b`` complex ``(m, *pix)``"""
+    def _adjoint(self, b, row_scale_value, remember=False):
+        """row_scale * E^H ((w/s) b) for ``b`` complex ``(m, *pix)``.  ``remember`` (backward of the dataset's own torch
+        data): the planar device result is kept next to the returned tensor, so that a FISTA run started from exactly this
+        dirty spectrum (README.md:183-190) neither transposes it back nor computes it a second time (``dirty_of``)."""
         plan = self.device_plan()
         if b is self.dataset.data and not isinstance(b, np.ndarray):    # one upload per dataset (Dataset.device_data)
             bt, pix = self.dataset.device_data(plan.device)
@@ -84,7 +88,27 @@ class FT(metaclass=ABCMeta):
         chan = self._channel_tensor(w / s_col, plan)
         row = self._row_tensor(row_scale_value, bt.shape[0], plan)
         out = plan.adjoint(bt, chan, row)
-        return dv.unpack_complex(out, plan.n, pix, like_torch=dv.is_torch(b))
+        res = dv.unpack_complex(out, plan.n, pix, like_torch=dv.is_torch(b))
+        self._dirty_cache = None
+        if remember and b is self.dataset.data and dv.is_torch(res):
+            ds = self.dataset
+            self._dirty_cache = dict(res=weakref.ref(res), version=res._version, planar=out, data=weakref.ref(b), data_version=b._version,
+                                     w=ds.w, s=ds.s, k=ds.k, plan=plan)
+        return res
+
+    def dirty_of(self, spectrum):
+        """the planar device copy of ``spectrum`` if that tensor is the untouched result of ``backward(dataset.data)`` for the
+        dataset as it is now, else None"""
+        c = getattr(self, "_dirty_cache", None)
+        if c is None or spectrum is None or c["res"]() is not spectrum or spectrum._version != c["version"]:
+            return None
+        ds = self.dataset
+        data = c["data"]()
+        if data is None or data is not ds.data or data._version != c["data_version"]:
+            return None
+        if ds.w is not c["w"] or ds.s is not c["s"] or ds.k is not c["k"] or self.device_plan() is not c["plan"]:
+            return None
+        return c["planar"]
 
     def _forward(self, x, normalized):
         plan = self.device_plan()

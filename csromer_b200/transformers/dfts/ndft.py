@@ -35,7 +35,7 @@ class NDFT1D(FT):
 
     def backward(self, b):
         """F_j = (1/k) sum_i (w_i / s_i) b_i exp(-2i (lambda2_i - l2_ref) phi_j)"""
-        return self._adjoint(b, 1.0 / np.asarray(self.dataset.k, dtype=np.float64))
+        return self._adjoint(b, 1.0 / np.asarray(self.dataset.k, dtype=np.float64), remember=True)
 
     def RMTF(self, phi_x=0.0):
         """adjoint of the weights themselves (ndft.py:38-43); |R(0)| = 1 when s == 1"""

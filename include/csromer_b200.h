@@ -131,6 +131,9 @@ typedef struct {
                                csr_profile_collect's numbering (three-product kinds issue 3 per tile and K block of 64
                                when dense, an fp8 K block of 128 counts 2); the executed-work side of the roofline */
     int s_per_pixel;        /* 1: s is [P, m] (per-line-of-sight samplings, csr_fista_nu); 0: [m] */
+    const float* f_dirty_in; /* optional [P, ld2n]: the dirty spectrum of THESE data and weights, already computed by
+                               csr_adjoint (what NDFT1D.backward(dataset.data) returned, README.md:183-186): the loop does
+                               not compute it again; with f_dirty == NULL it is also what F_dirty refers to afterwards */
 } csr_fista_args;
 
 size_t csr_fista_ws_bytes(const csr_plan* plan, const csr_wavelet* wav, int P);

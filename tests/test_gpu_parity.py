@@ -279,6 +279,45 @@ def test_sparsity_shortcuts_are_bit_exact(nch, P, K, kw):
     check_fista(src, X, cost, l1, ref)
 
 
+def test_fista_reuses_the_dirty_spectrum_it_was_started_from():
+    """README.md:183-190 with torch data: F_dirty = dft.backward(dataset.data) becomes the guess.  When the guess still is that
+    untouched tensor, the fused loop takes the planar device copy `backward` kept (no transpose back, no second dirty spectrum);
+    a guess of the same VALUES without that provenance takes the general path.  Same solution either way, and a modified
+    guess is honoured."""
+    import torch
+    src, par = make_batch(200, 140, seed=61, mixed=True)
+    K = 20
+    lam0 = 40.0 * np.asarray(src.theo_noise)
+    noise = lam0 / (2.0 * K)
+    results = []
+    for variant in ("provenance", "clone", "modified"):
+        ds = cs.Dataset(lambda2=src.lambda2, data=torch.as_tensor(np.asarray(src.data)), sigma=src.sigma, spectral_idx=1.0)
+        dft = cs.NDFT1D(dataset=ds, parameter=par)
+        f_dirty = dft.backward(ds.data)
+        guess = cs.Parameter(phi=par.phi, cellsize=par.cellsize)
+        guess.data = f_dirty
+        guess.complex_data_to_real()
+        assert dft.dirty_of(guess.complex_source()) is not None
+        if variant == "clone":
+            guess.data = guess.data.clone()
+            assert guess.complex_source() is None
+        elif variant == "modified":
+            guess.data[:, 0] = 0.0            # in place: the version counter of the tensor moves
+            assert guess.complex_source() is None
+        chi2, l1 = cs.Chi2(dft_obj=dft, F_dirty=f_dirty), cs.L1(reg=lam0.copy())
+        opt = cs.FISTA(guess_param=guess, F_obj=cs.OFunction([chi2, l1]), fx=chi2, gx=cs.OFunction([l1]), noise=noise, maxiter=K,
+                       verbose=False)
+        cost, X = opt.run()
+        reused = opt.device_outputs["f_dirty"] is dft._dirty_cache["planar"]
+        assert reused == (variant == "provenance")
+        results.append((X.data.cpu().numpy(), np.asarray(cost.cpu() if hasattr(cost, "cpu") else cost), ds.model_data.cpu().numpy()))
+    for a, b in zip(results[0], results[1]):
+        assert rel(a, b) < 2e-6
+    assert rel(results[0][0][:, 1:], results[2][0][:, 1:]) < 2e-6 and rel(results[0][0][:, 0], results[2][0][:, 0]) > 1e-3
+    ref = oracle_fista(src, par, K, lam0, noise)
+    assert rel(results[0][0], ref["x"]) < TOL_MODEL
+
+
 def test_repeated_call_is_replayed_as_a_cuda_graph():
     """csr_fista called again with identical arguments (same buffers: `out=` reuse) is captured on the second call and
     replayed as one CUDA graph from then on: same bits as plain launches, same launch accounting, new data honoured."""
