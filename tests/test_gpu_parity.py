@@ -215,7 +215,10 @@ def test_fista_delta_basis_batches(nch, P, K, kw):
     check_fista(src, X, cost, l1, ref)
 
 
-@pytest.mark.parametrize("nch,P,K,kw", [(200, 261, 30, dict(mixed=True)), (1000, 300, 20, {}), (203, 129, 25, dict(per_pixel_w=True, flags=0.1))])
+# (m = 200, 1000: the direct row-contiguous forward epilogue; 202: m % 4 != 0, sparse tiles stay on the pipelined fragment epilogue;
+#  203: odd m, the general epilogue; 204 with per-pixel weights: channel factors of the pixel's own in the direct epilogue)
+@pytest.mark.parametrize("nch,P,K,kw", [(200, 261, 30, dict(mixed=True)), (1000, 300, 20, {}), (203, 129, 25, dict(per_pixel_w=True, flags=0.1)),
+                                        (202, 140, 20, {}), (204, 150, 20, dict(per_pixel_w=True, flags=0.15))])
 def test_sparsity_shortcuts_are_bit_exact(nch, P, K, kw):
     """The epilogue's all-zero-block shortcut, the forward GEMM's K-block skipping and the one-product screening of
     the adjoint must not change a single bit."""
