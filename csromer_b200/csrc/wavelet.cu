@@ -73,16 +73,13 @@ __global__ void iswt_level_kernel(const float* __restrict__ a_in, int ld_a, cons
 }
 
 // ---- decimated, periodization ----------------------------------------------------------------------------
-__global__ void dwt_level_kernel(const float* __restrict__ x_in, int ld_in, int N, float* __restrict__ a_out, int ld_a,
-                                 float* __restrict__ d_out, int ld_d, const FilterPair f) {
+// one output pair of a level; `src` may be global or shared memory (the per-level kernels and the fused kernel share these
+// functions: same multiply-adds in the same order, same bits)
+__device__ __forceinline__ void dwt_per_sample(const float* src, int N, int o, const FilterPair& f, float& ca, float& cd) {
     const int Np = N + (N & 1);
-    const int half = Np / 2;
-    const int o = blockIdx.y * blockDim.x + threadIdx.x;
-    if (o >= half) return;
-    const int p = blockIdx.x;
-    const float* src = x_in + (size_t)p * ld_in;
     int idx = (2 * o + f.F / 2) % Np;
-    float ca = 0.f, cd = 0.f;
+    ca = 0.f;
+    cd = 0.f;
     for (int t = 0; t < f.F; ++t) {
         const float v = src[min(idx, N - 1)];  // index N (only when N is odd) repeats the last sample
         ca = fmaf(f.lo[t], v, ca);
@@ -90,6 +87,15 @@ __global__ void dwt_level_kernel(const float* __restrict__ x_in, int ld_in, int 
         idx -= 1;
         if (idx < 0) idx += Np;
     }
+}
+__global__ void dwt_level_kernel(const float* __restrict__ x_in, int ld_in, int N, float* __restrict__ a_out, int ld_a,
+                                 float* __restrict__ d_out, int ld_d, const FilterPair f) {
+    const int half = (N + (N & 1)) / 2;
+    const int o = blockIdx.y * blockDim.x + threadIdx.x;
+    if (o >= half) return;
+    const int p = blockIdx.x;
+    float ca, cd;
+    dwt_per_sample(x_in + (size_t)p * ld_in, N, o, f, ca, cd);
     a_out[(size_t)p * ld_a + o] = ca;
     d_out[(size_t)p * ld_d + o] = cd;
 }
@@ -141,14 +147,9 @@ __device__ __forceinline__ float ext_sample(const float* __restrict__ x, int i, 
     return 0.f;
 }
 
-__global__ void dwt_ext_level_kernel(const float* __restrict__ x_in, int ld_in, int N, int ext, float* __restrict__ a_out,
-                                     int ld_a, float* __restrict__ d_out, int ld_d, const FilterPair f) {
-    const int nc = (N + f.F - 1) / 2;
-    const int k = blockIdx.y * blockDim.x + threadIdx.x;
-    if (k >= nc) return;
-    const int p = blockIdx.x;
-    const float* src = x_in + (size_t)p * ld_in;
-    float ca = 0.f, cd = 0.f;
+__device__ __forceinline__ void dwt_ext_sample(const float* src, int N, int ext, int k, const FilterPair& f, float& ca, float& cd) {
+    ca = 0.f;
+    cd = 0.f;
     const int top = 2 * k + 1;
     if (top - (f.F - 1) >= 0 && top < N) {  // interior: no extension involved
         for (int t = 0; t < f.F; ++t) {
@@ -163,19 +164,21 @@ __global__ void dwt_ext_level_kernel(const float* __restrict__ x_in, int ld_in, 
             cd = fmaf(f.hi[t], v, cd);
         }
     }
+}
+__global__ void dwt_ext_level_kernel(const float* __restrict__ x_in, int ld_in, int N, int ext, float* __restrict__ a_out,
+                                     int ld_a, float* __restrict__ d_out, int ld_d, const FilterPair f) {
+    const int nc = (N + f.F - 1) / 2;
+    const int k = blockIdx.y * blockDim.x + threadIdx.x;
+    if (k >= nc) return;
+    const int p = blockIdx.x;
+    float ca, cd;
+    dwt_ext_sample(x_in + (size_t)p * ld_in, N, ext, k, f, ca, cd);
     a_out[(size_t)p * ld_a + k] = ca;
     d_out[(size_t)p * ld_d + k] = cd;
 }
 
 // out has ``keep`` <= 2 nc - F + 2 samples (the running approximation is cut to the next detail band's length, like waverec)
-__global__ void idwt_ext_level_kernel(const float* __restrict__ a_in, int ld_a, const float* __restrict__ d_in, int ld_d,
-                                      int nc, float* __restrict__ out, int ld_out, int keep,
-                                      const float* __restrict__ add, int ld_add, const FilterPair f) {
-    const int q = blockIdx.y * blockDim.x + threadIdx.x;
-    if (q >= keep) return;
-    const int p = blockIdx.x;
-    const float* a = a_in + (size_t)p * ld_a;
-    const float* d = d_in + (size_t)p * ld_d;
+__device__ __forceinline__ float idwt_ext_sample(const float* a, const float* d, int nc, int q, const FilterPair& f) {
     float acc = 0.f;
     const int base = q + f.F - 2;  // tap t = base - 2k
     for (int t = (base & 1); t < f.F; t += 2) {
@@ -185,19 +188,21 @@ __global__ void idwt_ext_level_kernel(const float* __restrict__ a_in, int ld_a, 
             acc = fmaf(f.hi[t], d[k], acc);
         }
     }
+    return acc;
+}
+__global__ void idwt_ext_level_kernel(const float* __restrict__ a_in, int ld_a, const float* __restrict__ d_in, int ld_d,
+                                      int nc, float* __restrict__ out, int ld_out, int keep,
+                                      const float* __restrict__ add, int ld_add, const FilterPair f) {
+    const int q = blockIdx.y * blockDim.x + threadIdx.x;
+    if (q >= keep) return;
+    const int p = blockIdx.x;
+    float acc = idwt_ext_sample(a_in + (size_t)p * ld_a, d_in + (size_t)p * ld_d, nc, q, f);
     if (add) acc += add[(size_t)p * ld_add + q];
     out[(size_t)p * ld_out + q] = acc;
 }
 
-__global__ void idwt_level_kernel(const float* __restrict__ a_in, int ld_a, const float* __restrict__ d_in, int ld_d,
-                                  int half, float* __restrict__ out, int ld_out, int keep,
-                                  const float* __restrict__ add, int ld_add, const FilterPair f) {
-    const int q = blockIdx.y * blockDim.x + threadIdx.x;
-    if (q >= keep) return;
-    const int p = blockIdx.x;
+__device__ __forceinline__ float idwt_per_sample(const float* a, const float* d, int half, int q, const FilterPair& f) {
     const int N = 2 * half;
-    const float* a = a_in + (size_t)p * ld_a;
-    const float* d = d_in + (size_t)p * ld_d;
     float acc = 0.f;
     const int base = q + f.F / 2 - 1;
     for (int t = (base & 1); t < f.F; t += 2) {  // (base - t) must be even
@@ -207,8 +212,97 @@ __global__ void idwt_level_kernel(const float* __restrict__ a_in, int ld_a, cons
         acc = fmaf(f.lo[t], a[o], acc);
         acc = fmaf(f.hi[t], d[o], acc);
     }
+    return acc;
+}
+__global__ void idwt_level_kernel(const float* __restrict__ a_in, int ld_a, const float* __restrict__ d_in, int ld_d,
+                                  int half, float* __restrict__ out, int ld_out, int keep,
+                                  const float* __restrict__ add, int ld_add, const FilterPair f) {
+    const int q = blockIdx.y * blockDim.x + threadIdx.x;
+    if (q >= keep) return;
+    const int p = blockIdx.x;
+    float acc = idwt_per_sample(a_in + (size_t)p * ld_a, d_in + (size_t)p * ld_d, half, q, f);
     if (add) acc += add[(size_t)p * ld_add + q];
     out[(size_t)p * ld_out + q] = acc;
+}
+
+// ---- decimated transform, all levels of one line of sight in ONE kernel ------------------------------------------------
+// The level-by-level path costs one launch and one round trip through HBM per level (12 levels for db2 at N = 15936).  Here a
+// CTA keeps the running approximation of its line of sight in shared memory (N + N/2 floats): the signal is read once, every
+// detail band is written once, the approximations never leave the SM.  Same sample functions as the per-level kernels: same bits.
+struct DwtBands {
+    int L, N, ext, base;     // levels, signal length, extension mode (0 = periodization), offset of the bands in a coefficient row
+    int sizes[34], offsets[34];
+};
+constexpr int DWT_FUSED_THREADS = 512;
+
+__global__ void __launch_bounds__(DWT_FUSED_THREADS)
+dwt_fused_kernel(const float* __restrict__ signal, int ld_sig, float* __restrict__ coef, int ld_coef, const DwtBands b, const FilterPair f,
+                 int append_signal) {
+    extern __shared__ float dwt_smem[];
+    const int p = blockIdx.x;
+    const int n1 = b.sizes[b.L];  // length of cD_1 = of the first approximation
+    float* cur = dwt_smem;        // [N]
+    float* nxt = dwt_smem + ((b.N + 3) & ~3);  // [n1]
+    const float* src = signal + (size_t)p * ld_sig;
+    float* row = coef + (size_t)p * ld_coef;
+    for (int i = threadIdx.x; i < b.N; i += blockDim.x) {
+        const float v = src[i];
+        cur[i] = v;
+        if (append_signal) row[i] = v;
+    }
+    __syncthreads();
+    int len = b.N;
+    (void)n1;
+    for (int lev = 1; lev <= b.L; ++lev) {
+        const int band = b.L - lev + 1;
+        const int nc = b.sizes[band];
+        float* d_out = row + b.base + b.offsets[band];
+        float* a_out = (lev == b.L) ? row + b.base + b.offsets[0] : nxt;
+        for (int k = threadIdx.x; k < nc; k += blockDim.x) {
+            float ca, cd;
+            if (b.ext == 0) dwt_per_sample(cur, len, k, f, ca, cd);
+            else dwt_ext_sample(cur, len, b.ext, k, f, ca, cd);
+            a_out[k] = ca;
+            d_out[k] = cd;
+        }
+        __syncthreads();
+        float* t = cur;
+        cur = nxt;
+        nxt = t;
+        len = nc;
+    }
+}
+
+__global__ void __launch_bounds__(DWT_FUSED_THREADS)
+idwt_fused_kernel(const float* __restrict__ coef, int ld_coef, float* __restrict__ signal, int ld_sig, const DwtBands b, const FilterPair f,
+                  int add_signal) {
+    extern __shared__ float dwt_smem[];
+    const int p = blockIdx.x;
+    const int n1 = b.sizes[b.L];
+    float* cur = dwt_smem;                      // [n1]
+    float* nxt = dwt_smem + ((n1 + 3) & ~3);    // [n1]
+    const float* row = coef + (size_t)p * ld_coef;
+    for (int i = threadIdx.x; i < b.sizes[0]; i += blockDim.x) cur[i] = row[b.base + b.offsets[0] + i];
+    __syncthreads();
+    for (int lev = b.L; lev >= 1; --lev) {
+        const int band = b.L - lev + 1;
+        const int half = b.sizes[band];
+        const int keep = (lev == 1) ? b.N : b.sizes[band + 1];
+        const float* d_in = row + b.base + b.offsets[band];
+        for (int q = threadIdx.x; q < keep; q += blockDim.x) {
+            float v = b.ext == 0 ? idwt_per_sample(cur, d_in, half, q, f) : idwt_ext_sample(cur, d_in, half, q, f);
+            if (lev == 1) {
+                if (add_signal) v += row[q];
+                signal[(size_t)p * ld_sig + q] = v;
+            } else {
+                nxt[q] = v;
+            }
+        }
+        __syncthreads();
+        float* t = cur;
+        cur = nxt;
+        nxt = t;
+    }
 }
 
 __global__ void copy_rows_kernel(const float* __restrict__ src, int ld_src, float* __restrict__ dst, int ld_dst,
@@ -1099,10 +1193,39 @@ int swt_analysis_fused(const csr_wavelet* w, const float* signal, int ld_sig, fl
 }
 
 // coefficient layout: [signal (N) if append_signal][cA_L][cD_L]...[cD_1]
+// the fused decimated kernels: all levels of a line of sight in shared memory (N + N/2 floats must fit)
+static DwtBands dwt_bands(const csr_wavelet* w) {
+    DwtBands b = {};
+    b.L = w->levels;
+    b.N = w->N;
+    b.ext = w->ext;
+    b.base = w->append_signal ? w->N : 0;
+    for (int i = 0; i <= w->levels; ++i) {
+        b.sizes[i] = w->sizes[i];
+        b.offsets[i] = w->offsets[i];
+    }
+    return b;
+}
+static size_t dwt_fused_smem(const csr_wavelet* w, bool analysis) {
+    const size_t n1 = (size_t)((w->sizes[w->levels] + 3) & ~3);
+    return sizeof(float) * (analysis ? (size_t)((w->N + 3) & ~3) + n1 : 2 * n1);
+}
+static bool dwt_fusable(const csr_wavelet* w) {
+    return w->kind == 1 && w->levels >= 1 && options().fused_wavelet != 0 && dwt_fused_smem(w, true) <= 200 * 1024;
+}
+
 int wavelet_decompose(const csr_wavelet* w, const float* signal, int ld_sig, float* coef, int ld_coef, int P,
                       float* ws, cudaStream_t stream) {
     if (wavelet_fusable(w) && options().fused_wavelet != 0)
         return swt_analysis_fused(w, signal, ld_sig, coef, ld_coef, P, nullptr, stream);
+    if (dwt_fusable(w)) {
+        const size_t smem = dwt_fused_smem(w, true);
+        CSR_CUDA(cudaFuncSetAttribute(dwt_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        dwt_fused_kernel<<<P, DWT_FUSED_THREADS, smem, stream>>>(signal, ld_sig, coef, ld_coef, dwt_bands(w),
+                                                                 make_pair(w->dec_lo, w->dec_hi, w->F), w->append_signal);
+        CSR_LAUNCHED();
+        return CSR_OK;
+    }
     const int N = w->N, L = w->levels;
     const int ldw = wavelet_ld(w);
     float* ping = ws;
@@ -1155,6 +1278,14 @@ int wavelet_reconstruct(const csr_wavelet* w, const float* coef, int ld_coef, fl
                         float* ws, cudaStream_t stream) {
     if (wavelet_fusable(w) && options().fused_wavelet != 0)
         return swt_synth_fused(w, coef, ld_coef, signal, ld_sig, nullptr, nullptr, 0, nullptr, P, nullptr, 0, nullptr, 0, stream);
+    if (dwt_fusable(w)) {
+        const size_t smem = dwt_fused_smem(w, false);
+        CSR_CUDA(cudaFuncSetAttribute(idwt_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        idwt_fused_kernel<<<P, DWT_FUSED_THREADS, smem, stream>>>(coef, ld_coef, signal, ld_sig, dwt_bands(w),
+                                                                  make_pair(w->rec_lo, w->rec_hi, w->F), w->append_signal);
+        CSR_LAUNCHED();
+        return CSR_OK;
+    }
     const int N = w->N, L = w->levels;
     const int ldw = wavelet_ld(w);
     float* ping = ws;

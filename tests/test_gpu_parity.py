@@ -808,6 +808,35 @@ def test_decimated_wavelet_signal_extension_modes(mode):
     assert rel(cz.real, o.decompose(z.real.astype(np.float64))) < 2e-5 and rel(w.reconstruct_complex(cz), z) < 2e-5
 
 
+@pytest.mark.parametrize("mode", ["periodization", "symmetric", "zero", "smooth"])
+def test_decimated_transform_fused_kernels_are_bit_exact(mode):
+    """all levels of the decimated transform in one launch (the running approximation stays in shared memory): same bits as the
+    level-by-level kernels, one launch per transform (two with append_signal's nothing extra: the copy is fused too)"""
+    from csromer_b200 import _lib
+    lib = _lib.load()
+    rng = np.random.RandomState(41)
+    for name, N, level, app in (("db2", 15936, None, False), ("coif2", 3136, None, True), ("sym4", 1001, 3, False), ("db1", 250, None, False)):
+        x = rng.normal(size=(N, 5)).astype(np.float32)
+        out = []
+        for fused in (1, 0):
+            _lib.set_option("fused_wavelet", fused)
+            try:
+                w = cs.DiscreteWavelet(wavelet_name=name, wavelet_level=level, mode=mode, append_signal=app)
+                lib.csr_launch_count(1)
+                c = w.decompose(x)
+                n_dec = int(lib.csr_launch_count(1))
+                r = w.reconstruct(c)
+                n_rec = int(lib.csr_launch_count(0))
+            finally:
+                _lib.set_option("fused_wavelet", 1)
+            out.append((c, r, n_dec, n_rec, len(w.coeff_shapes) - 1))
+        (c1, r1, d1, k1, L), (c0, r0, d0, k0, _) = out
+        np.testing.assert_array_equal(c1, c0)
+        np.testing.assert_array_equal(r1, r0)
+        # (+ the two transposes between the Python-side layout and the planar rows)
+        assert d0 - d1 == L - 1 + (1 if app else 0) and k0 - k1 == L - 1, (d1, d0, k1, k0, L)
+
+
 def test_fista_in_a_symmetric_extension_wavelet_basis():
     src, par = make_batch(200, 24, seed=22, mixed=True)
     wav = cs.DiscreteWavelet(wavelet_name="db2", mode="symmetric")
