@@ -205,6 +205,9 @@ int nufft_grid_size(int n, int* logNf);
 int launch_nufft_forward(const double* a, int ldl, const int* m_count, int m, int n, double phi0, double dphi, const float* x, int ldx,
                          const float* chan_scale, const float* row_scale, const float* sub, float* out, int ld_out, int P,
                          cudaStream_t stream);
+int launch_nufft_adjoint_fista(const double* a, int ldl, const int* m_count, int m, int n, double phi0, double dphi, const float* b, int ldb,
+                               float* x, float* z, int ld, const float* lambda0, const float* noise, const int* iter_cap, int iter,
+                               float step, float beta, float* delta, int P, cudaStream_t stream);
 int launch_nufft_adjoint(const double* a, int ldl, const int* m_count, int m, int n, double phi0, double dphi, const float* b, int ldb,
                          const float* chan_scale, const float* row_scale, float* out, int ld_out, int P, cudaStream_t stream);
 static bool use_nufft(const NuGrid& g) { return options().nufft != 0 && nufft_grid_size(g.n, nullptr) > 0; }
@@ -358,6 +361,12 @@ extern "C" int csr_fista_nu(const csr_nu_sampling* s, csr_wavelet* wav, const cs
         }
         // r = 1[w>0]/n (E z) - (w/(s k)) d ; g = E^H r          (chi2.py:49-52, dataset.py:374)
         if ((rc = launch_nudft_forward(g, zs, ld2n, w.amask, nullptr, w.b, w.r, ld2m, P, stream))) return rc;
+        if (!wav && use_nufft(g)) {   // the threshold / momentum update sits in the output stage of the adjoint NUFFT
+            if ((rc = launch_nufft_adjoint_fista(g.a, g.ldl, g.m_count, g.m, g.n, g.phi0, g.dphi, w.r, ld2m, x, w.z, ldc, a.lambda0, a.noise,
+                                                 a.iter_cap, it, a.step, beta, (last && a.delta) ? a.delta : nullptr, P, stream)))
+                return rc;
+            continue;
+        }
         if ((rc = launch_nudft_adjoint(g, w.r, ld2m, nullptr, nullptr, w.g, ld2n, P, stream))) return rc;
         const float* grad = w.g;
         if (wav) {

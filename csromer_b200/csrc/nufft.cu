@@ -30,8 +30,9 @@ namespace csr {
 bool profile_start(cudaStream_t stream, cudaEvent_t* start, cudaEvent_t* stop);
 void profile_stop(int kind, cudaStream_t stream, cudaEvent_t start, cudaEvent_t stop);
 
-constexpr int NF_THREADS = 512;
+constexpr int NF_THREADS = 1024;
 constexpr int NF_MAX = 16384;
+constexpr int NF_SPARSE_MAX = 96;   // non-zero cells up to which the forward transform sums over the cells directly
 
 struct NufftGrid {
     const double* a;     // [P, ldl]  lambda2 - l2_ref
@@ -41,6 +42,21 @@ struct NufftGrid {
     float beta;
     double phic, dphi;    // phi of the centre cell j = n/2, cell size
     const float* deconv;  // [n] 1 / psihat(j - n/2)
+};
+
+// optional FISTA update fused into the output stage of the adjoint transform (delta basis, csr_fista_nu): the value that would be
+// written as the gradient goes straight into u = z - step g, x = soft(u, step lambda), z = x + beta (x - x_old)
+// (fista.py:80-86, l1.py:30-32; the arithmetic of coef_update_kernel); x / z entries that do not change are not written
+struct NufftUpdate {
+    float* x;
+    float* z;
+    int ld;
+    const float* lambda0;
+    const float* noise;
+    const int* iter_cap;
+    int iter;
+    float step, beta;
+    float* delta;   // optional [P]: sum |x_new - x_old| of the line of sight
 };
 
 __device__ __forceinline__ float es_kernel(float t, float inv_half_w, float beta) {
@@ -154,16 +170,25 @@ __device__ __forceinline__ void channel_geometry(const NufftGrid& g, double a, d
 // out[p, i] = row_scale[p] chan_scale[p, i] y_i - sub[p, i]      (planar [Re | Im])
 __global__ void __launch_bounds__(NF_THREADS, 1)
 nufft_forward_kernel(NufftGrid g, const float* __restrict__ x, int ldx, const float* __restrict__ chan_scale,
-                     const float* __restrict__ row_scale, const float* __restrict__ sub, float* __restrict__ out, int ld_out, int P) {
+                     const float* __restrict__ row_scale, const float* __restrict__ sub, float* __restrict__ out, int ld_out, int P,
+                     int sparse_max) {
     extern __shared__ __align__(16) float2 nsm[];
     float2* d = nsm;
     float2* tw = nsm + g.Nf;
+    // sparse input: the non-zero cells of the line of sight, (j', Re, Im); with at most NF_SPARSE_MAX of them (an L1 iterate has
+    // a few dozen) the sum over THOSE cells is cheaper than any FFT and exact
+    float* const nz_base = reinterpret_cast<float*>(nsm + g.Nf + tw_slot(g.Nf / 2) + 1);   // [2][3 * NF_SPARSE_MAX]
+    float* nz_list = nz_base;
+    __shared__ int nz_count;
     build_twiddles(tw, g.Nf);
     const float inv_half_w = 2.f / (float)g.W;
     const int half_n = g.n >> 1;
     for (int p = blockIdx.x; p < P; p += gridDim.x) {
         const float* xr = x + (size_t)p * ldx;
+        nz_list = nz_base;
         __syncthreads();  // (the previous line of sight has been read out; the twiddle table is complete)
+        if (threadIdx.x == 0) nz_count = 0;
+        __syncthreads();
         // natural order: grid index k' <-> j' = k' (k' < Nf/2) or k' - Nf; phi cells j' in [-n/2, n - n/2)
         for (int idx = threadIdx.x; idx < g.Nf; idx += NF_THREADS) {
             const int jp = idx < (g.Nf >> 1) ? idx : idx - g.Nf;
@@ -171,12 +196,36 @@ nufft_forward_kernel(NufftGrid g, const float* __restrict__ x, int ldx, const fl
             float2 v = make_float2(0.f, 0.f);
             if (j >= 0 && j < g.n) {
                 const float dc = __ldg(g.deconv + j);
-                v = make_float2(xr[j] * dc, xr[g.n + j] * dc);
+                const float re = xr[j], im = xr[g.n + j];
+                v = make_float2(re * dc, im * dc);
+                if (sparse_max > 0 && (re != 0.f || im != 0.f)) {
+                    const int slot = atomicAdd(&nz_count, 1);
+                    if (slot < sparse_max) {
+                        nz_list[3 * slot] = (float)jp;
+                        nz_list[3 * slot + 1] = re;
+                        nz_list[3 * slot + 2] = im;
+                    }
+                }
             }
             d[idx] = v;
         }
         __syncthreads();
-        fft_dif_plus(d, tw, g.logNf);
+        const int nnz = nz_count;
+        const bool direct = sparse_max > 0 && nnz <= sparse_max;   // (CTA-uniform)
+        if (!direct) fft_dif_plus(d, tw, g.logNf);
+        if (direct) {   // the slots were handed out in arrival order: sort by cell, so that the sums below run in a fixed order
+            float* sorted = nz_list + 3 * NF_SPARSE_MAX;
+            if ((int)threadIdx.x < nnz) {
+                const float key = nz_list[3 * threadIdx.x];
+                int rank = 0;
+                for (int q = 0; q < nnz; ++q) rank += nz_list[3 * q] < key;
+                sorted[3 * rank] = key;
+                sorted[3 * rank + 1] = nz_list[3 * threadIdx.x + 1];
+                sorted[3 * rank + 2] = nz_list[3 * threadIdx.x + 2];
+            }
+            __syncthreads();
+            nz_list = sorted;
+        }
         const int mc = g.m_count ? min(g.m_count[p], g.m) : g.m;
         const float rs = row_scale ? row_scale[p] : 1.f;
         const double* ap = g.a + (size_t)p * g.ldl;
@@ -184,6 +233,21 @@ nufft_forward_kernel(NufftGrid g, const float* __restrict__ x, int ldx, const fl
         for (int i = threadIdx.x; i < g.m; i += NF_THREADS) {
             float2 y = make_float2(0.f, 0.f);
             if (i < mc) {
+                if (direct) {   // y_i = sum over the non-zero cells of x_j exp(2i a_i phi_j), phase reduced in fp64 turns
+                    const double a = ap[i];
+                    const double t0 = a * g.phic / 3.14159265358979323846, dt = a * g.dphi / 3.14159265358979323846;
+                    float2 acc = make_float2(0.f, 0.f);
+                    for (int q = 0; q < nnz; ++q) {
+                        double t = fma(dt, (double)nz_list[3 * q], t0);
+                        t -= rint(t);
+                        float sn, cs_;
+                        sincospif(2.0f * (float)t, &sn, &cs_);
+                        const float re = nz_list[3 * q + 1], im = nz_list[3 * q + 2];
+                        acc.x += re * cs_ - im * sn;
+                        acc.y += re * sn + im * cs_;
+                    }
+                    y = acc;
+                } else {
                 double kappa;
                 float2 c;
                 channel_geometry(g, ap[i], kappa, c);
@@ -197,6 +261,7 @@ nufft_forward_kernel(NufftGrid g, const float* __restrict__ x, int ldx, const fl
                     acc.y = fmaf(wgt, u.y, acc.y);
                 }
                 y = cmulf(acc, c);
+                }
                 const float cs = chan_scale ? chan_scale[(size_t)p * g.m + i] : 1.f;
                 y.x *= rs * cs;
                 y.y *= rs * cs;
@@ -214,7 +279,7 @@ nufft_forward_kernel(NufftGrid g, const float* __restrict__ x, int ldx, const fl
 // out[p, j] = row_scale[p] sum_i chan_scale[p, i] b[p, i] exp(-2i a_i phi_j)
 __global__ void __launch_bounds__(NF_THREADS, 1)
 nufft_adjoint_kernel(NufftGrid g, const float* __restrict__ b, int ldb, const float* __restrict__ chan_scale,
-                     const float* __restrict__ row_scale, float* __restrict__ out, int ld_out, int P) {
+                     const float* __restrict__ row_scale, float* __restrict__ out, int ld_out, int P, const NufftUpdate upd) {
     extern __shared__ __align__(16) float2 nsm[];
     float2* d = nsm;
     float2* tw = nsm + g.Nf;
@@ -246,13 +311,54 @@ nufft_adjoint_kernel(NufftGrid g, const float* __restrict__ b, int ldb, const fl
         __syncthreads();
         fft_dit_minus(d, tw, g.logNf);
         const float rs = row_scale ? row_scale[p] : 1.f;
-        float* o = out + (size_t)p * ld_out;
-        for (int j = threadIdx.x; j < g.n; j += NF_THREADS) {
-            const int jp = j - half_n;
-            const float2 v = d[jp & (g.Nf - 1)];
-            const float dc = __ldg(g.deconv + j) * rs;
-            o[j] = v.x * dc;
-            o[g.n + j] = v.y * dc;
+        if (upd.x == nullptr) {
+            float* o = out + (size_t)p * ld_out;
+            for (int j = threadIdx.x; j < g.n; j += NF_THREADS) {
+                const int jp = j - half_n;
+                const float2 v = d[jp & (g.Nf - 1)];
+                const float dc = __ldg(g.deconv + j) * rs;
+                o[j] = v.x * dc;
+                o[g.n + j] = v.y * dc;
+            }
+        } else {
+            const float l0 = upd.lambda0[p], nz = upd.noise[p];
+            const float lam = l0 - (float)upd.iter * nz;
+            const bool active = (nz < l0) && (upd.iter == 0 || lam > 0.f) && (!upd.iter_cap || upd.iter < upd.iter_cap[p]);
+            const float thr = upd.step * lam;
+            float* xr = upd.x + (size_t)p * upd.ld;
+            float* zr = upd.z + (size_t)p * upd.ld;
+            float dsum = 0.f;
+            if (active) {
+                for (int j = threadIdx.x; j < g.n; j += NF_THREADS) {
+                    const int jp = j - half_n;
+                    const float2 v = d[jp & (g.Nf - 1)];
+                    const float dc = __ldg(g.deconv + j) * rs;
+#pragma unroll
+                    for (int c = 0; c < 2; ++c) {
+                        const int col = c ? g.n + j : j;
+                        const float grad = (c ? v.y : v.x) * dc;
+                        const float zo = zr[col], xo = xr[col];
+                        const float u = zo - upd.step * grad;
+                        const float xn = copysignf(fmaxf(fabsf(u) - thr, 0.f), u);
+                        const float zn = xn + upd.beta * (xn - xo);
+                        if (__float_as_uint(xn) != __float_as_uint(xo)) xr[col] = xn;
+                        if (__float_as_uint(zn) != __float_as_uint(zo)) zr[col] = zn;
+                        dsum += fabsf(xn - xo);
+                    }
+                }
+            }
+            if (upd.delta != nullptr) {   // (CTA-uniform; a frozen line of sight keeps its value, like coef_update_kernel)
+                __shared__ float red[NF_THREADS / 32];
+#pragma unroll
+                for (int sh = 16; sh > 0; sh >>= 1) dsum += __shfl_xor_sync(0xffffffffu, dsum, sh);
+                if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = dsum;
+                __syncthreads();
+                if (threadIdx.x == 0 && active) {
+                    float t = 0.f;
+                    for (int q = 0; q < NF_THREADS / 32; ++q) t += red[q];
+                    upd.delta[p] = t;
+                }
+            }
         }
     }
 }
@@ -332,7 +438,7 @@ static int nufft_width() {
 
 template <typename Kernel>
 static int nufft_configure(Kernel kernel, int Nf, int* grid, int P) {
-    const int smem = (int)sizeof(float2) * (Nf + tw_slot(Nf / 2) + 1);
+    const int smem = (int)sizeof(float2) * (Nf + tw_slot(Nf / 2) + 1) + 2 * 3 * NF_SPARSE_MAX * (int)sizeof(float);
     CSR_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     int device = 0, sms = 0;
     CSR_CUDA(cudaGetDevice(&device));
@@ -360,14 +466,31 @@ int launch_nufft_forward(const double* a, int ldl, const int* m_count, int m, in
     if (smem < 0) return smem;
     cudaEvent_t ev0, ev1;
     const bool prof = profile_start(stream, &ev0, &ev1);
-    nufft_forward_kernel<<<grid, NF_THREADS, smem, stream>>>(g, x, ldx, chan_scale, row_scale, sub, out, ld_out, P);
+    static const int sparse_max = getenv("CSR_NUFFT_SPARSE") ? min(atoi(getenv("CSR_NUFFT_SPARSE")), NF_SPARSE_MAX) : NF_SPARSE_MAX;
+    nufft_forward_kernel<<<grid, NF_THREADS, smem, stream>>>(g, x, ldx, chan_scale, row_scale, sub, out, ld_out, P, sparse_max);
     CSR_LAUNCHED();
     if (prof) profile_stop(14, stream, ev0, ev1);
     return CSR_OK;
 }
 
+int launch_nufft_adjoint_update(const double* a, int ldl, const int* m_count, int m, int n, double phi0, double dphi, const float* b, int ldb,
+                                const float* chan_scale, const float* row_scale, float* out, int ld_out, int P, const NufftUpdate& upd,
+                                cudaStream_t stream);
 int launch_nufft_adjoint(const double* a, int ldl, const int* m_count, int m, int n, double phi0, double dphi, const float* b, int ldb,
                          const float* chan_scale, const float* row_scale, float* out, int ld_out, int P, cudaStream_t stream) {
+    NufftUpdate none = {};
+    return launch_nufft_adjoint_update(a, ldl, m_count, m, n, phi0, dphi, b, ldb, chan_scale, row_scale, out, ld_out, P, none, stream);
+}
+// ... with the FISTA update of (x, z) in its output stage (out is not written then)
+int launch_nufft_adjoint_fista(const double* a, int ldl, const int* m_count, int m, int n, double phi0, double dphi, const float* b, int ldb,
+                               float* x, float* z, int ld, const float* lambda0, const float* noise, const int* iter_cap, int iter,
+                               float step, float beta, float* delta, int P, cudaStream_t stream) {
+    NufftUpdate upd = {x, z, ld, lambda0, noise, iter_cap, iter, step, beta, delta};
+    return launch_nufft_adjoint_update(a, ldl, m_count, m, n, phi0, dphi, b, ldb, nullptr, nullptr, nullptr, 0, P, upd, stream);
+}
+int launch_nufft_adjoint_update(const double* a, int ldl, const int* m_count, int m, int n, double phi0, double dphi, const float* b, int ldb,
+                                const float* chan_scale, const float* row_scale, float* out, int ld_out, int P, const NufftUpdate& upd,
+                                cudaStream_t stream) {
     NufftGrid g = {};
     int rc = nufft_setup(n, nufft_width(), stream, &g);
     if (rc) return rc;
@@ -382,7 +505,7 @@ int launch_nufft_adjoint(const double* a, int ldl, const int* m_count, int m, in
     if (smem < 0) return smem;
     cudaEvent_t ev0, ev1;
     const bool prof = profile_start(stream, &ev0, &ev1);
-    nufft_adjoint_kernel<<<grid, NF_THREADS, smem, stream>>>(g, b, ldb, chan_scale, row_scale, out, ld_out, P);
+    nufft_adjoint_kernel<<<grid, NF_THREADS, smem, stream>>>(g, b, ldb, chan_scale, row_scale, out, ld_out, P, upd);
     CSR_LAUNCHED();
     if (prof) profile_stop(15, stream, ev0, ev1);
     return CSR_OK;
