@@ -329,21 +329,38 @@ nufft_adjoint_kernel(NufftGrid g, const float* __restrict__ b, int ldb, const fl
             float* zr = upd.z + (size_t)p * upd.ld;
             float dsum = 0.f;
             if (active) {
-                for (int j = threadIdx.x; j < g.n; j += NF_THREADS) {
-                    const int jp = j - half_n;
-                    const float2 v = d[jp & (g.Nf - 1)];
-                    const float dc = __ldg(g.deconv + j) * rs;
+                // four cells per thread and pass: all eight (x, z) pairs are requested before the first store (x and z may not be
+                // declared restrict against each other's stores, so a one-cell loop would serialise on its loads)
+                constexpr int NB = 4;
+                for (int j0 = threadIdx.x; j0 < g.n; j0 += NB * NF_THREADS) {
+                    float zo[NB][2], xo[NB][2], dc[NB];
 #pragma unroll
-                    for (int c = 0; c < 2; ++c) {
-                        const int col = c ? g.n + j : j;
-                        const float grad = (c ? v.y : v.x) * dc;
-                        const float zo = zr[col], xo = xr[col];
-                        const float u = zo - upd.step * grad;
-                        const float xn = copysignf(fmaxf(fabsf(u) - thr, 0.f), u);
-                        const float zn = xn + upd.beta * (xn - xo);
-                        if (__float_as_uint(xn) != __float_as_uint(xo)) xr[col] = xn;
-                        if (__float_as_uint(zn) != __float_as_uint(zo)) zr[col] = zn;
-                        dsum += fabsf(xn - xo);
+                    for (int q = 0; q < NB; ++q) {
+                        const int j = j0 + q * NF_THREADS;
+                        const bool ok = j < g.n;
+                        dc[q] = ok ? __ldg(g.deconv + j) * rs : 0.f;
+#pragma unroll
+                        for (int c = 0; c < 2; ++c) {
+                            zo[q][c] = ok ? __ldcg(zr + (c ? g.n + j : j)) : 0.f;
+                            xo[q][c] = ok ? __ldcg(xr + (c ? g.n + j : j)) : 0.f;
+                        }
+                    }
+#pragma unroll
+                    for (int q = 0; q < NB; ++q) {
+                        const int j = j0 + q * NF_THREADS;
+                        if (j >= g.n) continue;
+                        const float2 v = d[(j - half_n) & (g.Nf - 1)];
+#pragma unroll
+                        for (int c = 0; c < 2; ++c) {
+                            const int col = c ? g.n + j : j;
+                            const float grad = (c ? v.y : v.x) * dc[q];
+                            const float u = zo[q][c] - upd.step * grad;
+                            const float xn = copysignf(fmaxf(fabsf(u) - thr, 0.f), u);
+                            const float zn = xn + upd.beta * (xn - xo[q][c]);
+                            if (__float_as_uint(xn) != __float_as_uint(xo[q][c])) xr[col] = xn;
+                            if (__float_as_uint(zn) != __float_as_uint(zo[q][c])) zr[col] = zn;
+                            dsum += fabsf(xn - xo[q][c]);
+                        }
                     }
                 }
             }
