@@ -303,9 +303,17 @@ nufft_adjoint_kernel(NufftGrid g, const float* __restrict__ b, int ldb, const fl
             for (int l = 0; l < g.W; ++l) {
                 const int k = k0 + l;
                 const float wgt = es_kernel((float)(kappa - (double)k), inv_half_w, g.beta);
-                float2* cell = d + brev(k & (g.Nf - 1), g.logNf);
-                atomicAdd(&cell->x, wgt * v.x);
-                atomicAdd(&cell->y, wgt * v.y);
+                // (an fp32 atomicAdd on shared memory is a compare-and-swap loop: one 64-bit loop per cell instead of two 32-bit ones)
+                unsigned long long* cell = reinterpret_cast<unsigned long long*>(d + brev(k & (g.Nf - 1), g.logNf));
+                const float ax = wgt * v.x, ay = wgt * v.y;
+                unsigned long long seen = *cell, assumed;
+                do {
+                    assumed = seen;
+                    const float2 cur = make_float2(__uint_as_float((unsigned)(assumed & 0xffffffffull)), __uint_as_float((unsigned)(assumed >> 32)));
+                    const unsigned long long want = (unsigned long long)__float_as_uint(cur.x + ax) |
+                                                    ((unsigned long long)__float_as_uint(cur.y + ay) << 32);
+                    seen = atomicCAS(cell, assumed, want);
+                } while (seen != assumed);
             }
         }
         __syncthreads();
