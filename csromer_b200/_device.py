@@ -209,12 +209,33 @@ class SparseRows:
         return np.ascontiguousarray(out.T).reshape(self.shape)
 
 
+_small_cache = {}
+
+
+def small_to_device(arr, dtype, device):
+    """Host vector (per-channel weights, spectral factors, per-pixel k / lambda / noise) -> read-only device tensor, cached by
+    CONTENT.  A blocking host-to-device copy makes the host wait for everything queued on the stream before it: seven of them
+    per reconstruction (the same few KB every slab) kept a streaming loop from queueing the next slab's work while the current
+    one runs.  Arrays above 1 MB are not cached."""
+    a = np.ascontiguousarray(arr)
+    if a.nbytes > (1 << 20):
+        return torch.as_tensor(a, dtype=dtype).to(device)
+    key = (str(device), str(dtype), a.shape, a.dtype.str, hash(a.tobytes()))
+    t = _small_cache.get(key)
+    if t is None:
+        if len(_small_cache) >= 256:
+            _small_cache.pop(next(iter(_small_cache)))
+        t = torch.as_tensor(a, dtype=dtype).to(device)
+        _small_cache[key] = t
+    return t
+
+
 def per_pixel_vector(v, P, device, name):
-    """scalar or (P,)/pixel-shaped array -> fp32 [P] on the device."""
+    """scalar or (P,)/pixel-shaped array -> fp32 [P] on the device (read-only: small host arrays come from a content cache)."""
     if is_torch(v):
         t = v.to(device=device, dtype=torch.float32).reshape(-1)
     else:
-        t = torch.as_tensor(np.asarray(v, dtype=np.float64).reshape(-1), dtype=torch.float32).to(device)
+        t = small_to_device(np.asarray(v, dtype=np.float64).reshape(-1), torch.float32, device)
     if t.numel() == 1:
         t = t.expand(P).contiguous()
     if t.numel() != P:

@@ -123,7 +123,7 @@ class FISTA(Optimizer):
         P = data.shape[0]
         w = op._channel_tensor(ds.w, plan)
         s_host = np.asarray(ds.s, dtype=np.float64)
-        s = torch.as_tensor(s_host, dtype=torch.float32).to(dev) if s_host.ndim == 1 else op._channel_tensor(s_host, plan)
+        s = dv.small_to_device(s_host, torch.float32, dev) if s_host.ndim == 1 else op._channel_tensor(s_host, plan)
         k = dv.per_pixel_vector(ds.k, P, dev, "k")
         engine = None
         if wav is not None:
@@ -153,7 +153,7 @@ class FISTA(Optimizer):
         noise_t = dv.per_pixel_vector(noise, P, dev, "noise")
         cap_t = None
         if cap is not None:
-            cap_t = torch.as_tensor(np.broadcast_to(cap.reshape(-1), (P,)).astype(np.int32)).to(dev)
+            cap_t = dv.small_to_device(np.broadcast_to(cap.reshape(-1), (P,)).astype(np.int32), torch.int32, dev)
 
         if dirty_planar is not None:
             out = plan.fista(data, w, s, k, x, lam_t, noise_t, iters, step=self.step, norm_factor=chi2.norm_factor,

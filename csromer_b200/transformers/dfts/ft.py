@@ -62,8 +62,8 @@ class FT(metaclass=ABCMeta):
         """per-channel ``(m,)`` or per-pixel ``(m, *pix)`` host array -> fp32 ``[m]`` / ``[P, m]`` on the device"""
         v = np.asarray(values, dtype=np.float64)
         if v.ndim == 1:
-            return torch.as_tensor(v, dtype=torch.float32).to(plan.device)
-        return torch.as_tensor(v.reshape(plan.m, -1).T.copy(), dtype=torch.float32).to(plan.device)
+            return dv.small_to_device(v, torch.float32, plan.device)
+        return dv.small_to_device(v.reshape(plan.m, -1).T, torch.float32, plan.device)
 
     def _row_tensor(self, values, P, plan, name="k"):
         return dv.per_pixel_vector(values, P, plan.device, name)
