@@ -319,6 +319,7 @@ struct Options {
                       // take the direct residual epilogue (NOT a same-bits switch: it changes how partial sums are grouped;
                       // every run with the same value gives the same bits whichever exact shortcuts are on); 0 = off
     int graph;        // csr_fista: a call repeated with identical arguments is replayed as one CUDA graph
+    int fwd16;        // sparse forward tiles on dft_fwd_direct_kernel (sixteen epilogue warps); same bits
 };
 Options& options();
 

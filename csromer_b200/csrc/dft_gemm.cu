@@ -743,6 +743,10 @@ __device__ __forceinline__ bool options_rows_ok(const GemmEpilogue& epi) {
            (epi.out8 == nullptr || ((reinterpret_cast<uintptr_t>(epi.out8) | (uintptr_t)epi.ld8 | (uintptr_t)(epi.ld8 >> 1)) & 3) == 0);
 }
 
+// pixel tiles whose forward tiles go to dft_fwd_direct_kernel (written by tile_single_kernel; GemmEpilogue::skip_single)
+constexpr int kMaxSingleRt = 8192;
+__device__ unsigned char g_single_rt[kMaxSingleRt];
+
 // Measurement aid (CSR_TIMELINE=1, csr_debug_timeline): clock64 stamps of the three roles for the first kTimelineTiles tiles of
 // every CTA of the last residual forward launch -- [cta][tile][8]: producer start / last load issued, MMA first operand seen /
 // last commit issued, epilogue tile start / last chunk drained / body done, K blocks of the tile.
@@ -848,6 +852,7 @@ dft_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
                 const int t = tile_id(ti);
                 int mt, nt;
                 tile_coords(t, MT, NT, mt, nt);
+                if (MODE == EPI_RESID && epi.skip_single != 0 && g_single_rt[mt]) continue;   // dft_fwd_direct_kernel's
                 const bool quiet = quiet_next;  // (the next tile's state is fetched while this one streams)
                 if (IS_SCREEN && ti + (int)gridDim.x < total_tiles) quiet_next = tile_quiet(tile_id(ti + gridDim.x));
                 if (IS_SCREEN && !quiet) continue;  // tile with signal: left to the three-product kernel
@@ -906,6 +911,11 @@ dft_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
                 const bool quiet = quiet_next;
                 if (IS_SCREEN && ti + (int)gridDim.x < total_tiles) quiet_next = tile_quiet(tile_id(ti + gridDim.x));
                 if (IS_SCREEN && !quiet) continue;
+                if (MODE == EPI_RESID && epi.skip_single != 0) {
+                    int mt, nt;
+                    tile_coords(tile_id(ti), MT, NT, mt, nt);
+                    if (g_single_rt[mt]) continue;
+                }
                 bool single = false;
                 if (skip || group_max > 0) {
                     int mt, nt;
@@ -1001,6 +1011,7 @@ dft_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
             const int t = tile_id(ti);
             int mt, nt;
             tile_coords(t, MT, NT, mt, nt);
+            if (MODE == EPI_RESID && epi.skip_single != 0 && g_single_rt[mt]) continue;
             if (IS_SCREEN && !tile_quiet(t)) {  // hand the tile on to the next kernel of the cascade (one warp lists it)
                 if (lane == 0 && atomicMax(last_listed, ti) < ti) epi.out_list[atomicAdd(epi.out_count, 1)] = t;
                 continue;
@@ -2412,6 +2423,303 @@ dft_fwd128_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
     }
 }
 
+
+// ---- the direct residual epilogue on sixteen warps ---------------------------------------------------------------------
+// Sparse forward tiles (one accumulation chunk, GemmEpilogue::group_sparse) spend their time in the epilogue: with eight
+// epilogue warps -- two per scheduler -- the 2.7 k instructions a warp issues per tile run at a fifth of the issue rate (time
+// line: 16 k clocks of body, 10 k of requests against an MMA span of 19 k).  dft_fwd_direct_kernel processes ONLY those tiles
+// (single_rt[mt] = 1, written by tile_single_kernel from the K-block flags; dft_gemm_kernel<EPI_RESID> skips them) with sixteen
+// epilogue warps: a warp owns 32 rows x 64 columns, reads the accumulator straight from TMEM in two 16-row pieces, transposes
+// 4-row x 64-column sub-pieces through a 1.1 KB shared-memory buffer so that its global accesses are row-contiguous (16-byte
+// loads of b, 8-byte stores of r_hi / r_lo, 4-byte stores of the fp8 copy), and keeps four sub-pieces of b in flight.  Same
+// element arithmetic as resid_direct_rows: same bits.  Needs m % 4 == 0 and channel factors shared by all rows (or none).
+constexpr int D16_EPW = 16;
+constexpr int D16_THREADS = 128 + 32 * D16_EPW;
+constexpr int D16_XP_ROW = 64 + 8;                         // floats; rows padded by 32 bytes
+constexpr int D16_XP_BYTES = 4 * D16_XP_ROW * 4;           // 4 rows per sub-piece
+constexpr int D16_SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + 256 + 2 * KMASK_WORDS * 4 + D16_EPW * D16_XP_BYTES;
+static_assert(D16_SMEM_BYTES <= 232448, "shared memory budget exceeded");
+// single_rt[mt] = 1: the pixel tile has at most group_max active K blocks (and at least one when K blocks are skipped)
+__global__ void tile_single_kernel(const unsigned int* __restrict__ flags, int flag_ld, int kwords, int KB, int MT, int group_max, int skip) {
+    const int mt = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (mt >= MT) return;
+    const unsigned int* row = flags + (size_t)mt * flag_ld;
+    int count = 0;
+    unsigned int last = 0;
+    for (int w0 = 0; w0 < kwords; w0 += 32) {
+        const int idx = w0 + lane;
+        const unsigned int v = idx < kwords ? __ldcg(row + idx) : 0u;
+        if (idx == kwords - 1) last = v;
+        count += 2 * __popc(__ballot_sync(0xffffffffu, v != 0u));
+    }
+    last = __shfl_sync(0xffffffffu, last, (kwords - 1) & 31);
+    if ((KB & 1) && last != 0u) count -= 1;   // (the last flag word covers a single K block when KB is odd: build_kmask)
+    if (lane == 0) g_single_rt[mt] = (unsigned char)(count <= group_max && !(skip && count == 0));
+}
+
+__global__ void __launch_bounds__(D16_THREADS, 1)
+dft_fwd_direct_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
+                      const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo, int K, int MT, int NT,
+                      const GemmEpilogue epi) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* stage_base = smem;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+    uint64_t* full = bars;            // [STAGES]
+    uint64_t* empty = bars + 4;       // [STAGES]
+    uint64_t* tmem_full = bars + 8;   // [2]
+    uint64_t* tmem_empty = bars + 10; // [2]
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 12);
+    uint32_t* masks = reinterpret_cast<uint32_t*>(smem + STAGES * STAGE_BYTES + 256);
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int total_tiles = MT * NT;
+    const int KB = (K + BK - 1) / BK;
+    const bool skip = epi.no_kskip == 0;
+    const int kwords = (KB + 1) >> 1;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&map_a_hi);
+        tma_prefetch_desc(&map_a_lo);
+        tma_prefetch_desc(&map_b_hi);
+        tma_prefetch_desc(&map_b_lo);
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], 1);
+        }
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(&tmem_full[b], 1);
+            mbar_init(&tmem_empty[b], D16_EPW);
+        }
+        mbar_fence_init();
+    }
+    if (warp == 1) {
+        tmem_alloc(tmem_ptr, TMEM_COLS);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    // registers: 640 threads start with 96 each; the four control warps drop to 40 and free 7168, the sixteen epilogue warps rise
+    // to 104 and take 4096 of them (setmaxnreg only moves registers inside the CTA's allocation)
+    if (warp < 4) {
+      asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+      if (warp == 0) {
+        // ===================== TMA producer =====================
+        uint32_t* my_mask = masks;
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int ti = blockIdx.x; ti < total_tiles; ti += gridDim.x) {
+            int mt, nt;
+            tile_coords(ti, MT, NT, mt, nt);
+            if (!g_single_rt[mt]) continue;
+            if (skip) build_kmask(epi.a_kflags + (size_t)mt * epi.a_kflag_ld, kwords, KB, my_mask, lane);
+            if (lane == 0) {
+                for (int kb = skip ? next_active_kb(my_mask, 0, KB) : 0; kb < KB; kb = skip ? next_active_kb(my_mask, kb + 1, KB) : kb + 1) {
+                    mbar_wait(&empty[stage], phase ^ 1);
+                    uint8_t* sb = stage_base + stage * STAGE_BYTES;
+                    mbar_arrive_expect_tx(&full[stage], STAGE_BYTES);
+                    tma_load_2d(sb, &map_a_hi, &full[stage], kb * BK, mt * BM);
+                    tma_load_2d(sb + A_TILE_BYTES, &map_a_lo, &full[stage], kb * BK, mt * BM);
+                    tma_load_2d(sb + 2 * A_TILE_BYTES, &map_b_hi, &full[stage], kb * BK, nt * BN);
+                    tma_load_2d(sb + 2 * A_TILE_BYTES + B_TILE_BYTES, &map_b_lo, &full[stage], kb * BK, nt * BN);
+                    if (++stage == STAGES) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+            }
+            __syncwarp();
+        }
+      } else if (warp == 1) {
+        // ===================== MMA issuer: one accumulation chunk per tile =====================
+        uint32_t* my_mask = masks + KMASK_WORDS;
+        constexpr uint32_t idesc = umma_idesc_f16(BM, BN);
+        int stage = 0;
+        uint32_t phase = 0;
+        uint32_t tile_no = 0;  // -> TMEM buffer = tile_no & 1, parity = (tile_no >> 1) & 1
+        unsigned long long issued = 0;
+        for (int ti = blockIdx.x; ti < total_tiles; ti += gridDim.x) {
+            int mt, nt;
+            tile_coords(ti, MT, NT, mt, nt);
+            if (!g_single_rt[mt]) continue;
+            if (skip) build_kmask(epi.a_kflags + (size_t)mt * epi.a_kflag_ld, kwords, KB, my_mask, lane);
+            if (lane == 0) {
+                const int buf = tile_no & 1;
+                mbar_wait(&tmem_empty[buf], ((tile_no >> 1) & 1) ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(buf * BN);
+                int done = 0;
+                for (int kb = skip ? next_active_kb(my_mask, 0, KB) : 0; kb < KB; kb = skip ? next_active_kb(my_mask, kb + 1, KB) : kb + 1) {
+                    mbar_wait(&full[stage], phase);
+                    tc_fence_after();
+                    const uint32_t sa_hi = smem_u32(stage_base + stage * STAGE_BYTES);
+                    const uint32_t sa_lo = sa_hi + A_TILE_BYTES, sb_hi = sa_hi + 2 * A_TILE_BYTES, sb_lo = sb_hi + B_TILE_BYTES;
+#pragma unroll
+                    for (int k4 = 0; k4 < BK / 16; ++k4) {
+                        const uint64_t da_hi = umma_desc_sw128(sa_hi + k4 * 32), da_lo = umma_desc_sw128(sa_lo + k4 * 32);
+                        const uint64_t db_hi = umma_desc_sw128(sb_hi + k4 * 32), db_lo = umma_desc_sw128(sb_lo + k4 * 32);
+                        umma_f16(d_tmem, da_hi, db_hi, idesc, (done != 0 || k4 != 0) ? 1u : 0u);
+                        umma_f16(d_tmem, da_lo, db_hi, idesc, 1u);
+                        umma_f16(d_tmem, da_hi, db_lo, idesc, 1u);
+                    }
+                    issued += 3;
+                    umma_commit(&empty[stage]);
+                    if (++stage == STAGES) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                    ++done;
+                }
+                umma_commit(&tmem_full[buf]);
+            }
+            ++tile_no;
+        }
+        if (lane == 0 && epi.mma_count != nullptr && issued != 0) atomicAdd(epi.mma_count + epi.count_slot, issued);
+      }
+    } else {
+        // ===================== epilogue warps =====================
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
+        const int ew = warp - 4;
+        const int sub = warp & 3;        // TMEM lane quarter this warp may read (hardware rule: warp id mod 4)
+        const int cq = ew >> 2;          // which 64 of the tile's 256 columns
+        float* xp = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES + 256 + 2 * KMASK_WORDS * 4) + ew * (D16_XP_BYTES / 4);
+        const int lrow = lane >> 4;      // which of the two rows of an access
+        const int lcol = 4 * (lane & 15);
+        const int h8 = epi.ld8 >> 1;
+        uint32_t tile_no = 0;
+        for (int ti = blockIdx.x; ti < total_tiles; ti += gridDim.x) {
+            int mt, nt;
+            tile_coords(ti, MT, NT, mt, nt);
+            if (!g_single_rt[mt]) continue;
+            const int buf = tile_no & 1;
+            const uint32_t par = (tile_no >> 1) & 1;
+            ++tile_no;
+            const int row0 = mt * BM + sub * 32, col = nt * BN + cq * 64 + lcol;
+            const bool col_ok = col < epi.N;   // (N = 2 m, m % 4 == 0: a lane's four columns are inside or outside together)
+            if (nt * BN + cq * 64 >= epi.N) {  // the warp's columns lie beyond the matrix: release the accumulator and move on
+                mbar_wait(&tmem_full[buf], par);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tmem_empty[buf]);
+                continue;
+            }
+            const int chan = col >= epi.m ? col - epi.m : col;
+            const int col8 = col < epi.m ? col : col - epi.m + h8;
+            // row scalars of the warp's 32 rows: lane l holds row l's
+            float my_desc = 0.f, my_osc = 0.f;
+            if (row0 + lane < epi.P) {
+                my_desc = kTwiddleDescale / __ldg(epi.a_scale + row0 + lane);
+                my_osc = __ldg(epi.out_scale + row0 + lane);
+            }
+            const float4 cf = (epi.chan_scale != nullptr && col_ok) ? __ldg(reinterpret_cast<const float4*>(epi.chan_scale + chan))
+                                                                    : make_float4(1.f, 1.f, 1.f, 1.f);
+            // b: sub-step s = (lh, rh, hs) covers rows 16 lh + 8 rh + 4 hs + lrow + 2 i (i = 0, 1); four sub-steps in flight
+            float4 bq[4][2];
+            auto request_b = [&](int s, float4 (&dst)[2]) {
+                const int base = 16 * (s >> 2) + 8 * ((s >> 1) & 1) + 4 * (s & 1) + lrow;
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                    const int row = row0 + base + 2 * i;
+                    dst[i] = (row < epi.P && col_ok) ? __ldcg(reinterpret_cast<const float4*>(epi.b + (size_t)row * epi.ld_out + col))
+                                                     : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+            };
+#pragma unroll
+            for (int s = 0; s < 4; ++s) request_b(s, bq[s]);
+            mbar_wait(&tmem_full[buf], par);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(sub * 32) << 16) + (uint32_t)(buf * BN + cq * 64);
+#pragma unroll
+            for (int lh = 0; lh < 2; ++lh) {
+                float v[32];
+                tmem_ld_16x256b_x8(taddr + ((uint32_t)(16 * lh) << 16), v);
+                if (lh == 1) {   // the accumulator has been read: the MMA thread may reuse the buffer
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&tmem_empty[buf]);
+                }
+#pragma unroll
+                for (int rh = 0; rh < 2; ++rh) {
+#pragma unroll
+                    for (int hs = 0; hs < 2; ++hs) {
+                        const int s = (lh * 2 + rh) * 2 + hs;
+                        // fragment -> rows: thread T holds (row T/4, columns 8 j + 2 (T%4), + 1); rows 4 hs .. 4 hs + 3 of this pass
+                        __syncwarp();
+                        if ((lane >> 4) == hs) {
+#pragma unroll
+                            for (int j8 = 0; j8 < 8; ++j8)
+                                *reinterpret_cast<float2*>(xp + ((lane >> 2) & 3) * D16_XP_ROW + 8 * j8 + 2 * (lane & 3)) =
+                                    make_float2(v[(j8 * 2 + rh) * 2], v[(j8 * 2 + rh) * 2 + 1]);
+                        }
+                        __syncwarp();
+                        float dsum[2] = {0.f, 0.f}, rmax[2] = {0.f, 0.f};
+#pragma unroll
+                        for (int i = 0; i < 2; ++i) {
+                            const int lr = 16 * lh + 8 * rh + 4 * hs + lrow + 2 * i;   // row inside the warp's 32
+                            const int row = row0 + lr;
+                            const float4 a = *reinterpret_cast<const float4*>(xp + (lrow + 2 * i) * D16_XP_ROW + lcol);
+                            const float desc = __shfl_sync(0xffffffffu, my_desc, lr), osc = __shfl_sync(0xffffffffu, my_osc, lr);
+                            if (row >= epi.P || !col_ok) continue;
+                            const float4 b = bq[s & 3][i];
+                            const float r0 = __fmaf_rn(cf.x, a.x * desc, -b.x) * osc, r1 = __fmaf_rn(cf.y, a.y * desc, -b.y) * osc;
+                            const float r2 = __fmaf_rn(cf.z, a.z * desc, -b.z) * osc, r3 = __fmaf_rn(cf.w, a.w * desc, -b.w) * osc;
+                            const __half2 h01 = __floats2half2_rn(r0, r1), h23 = __floats2half2_rn(r2, r3);
+                            const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+                            const __half2 l01 = __floats2half2_rn(r0 - f01.x, r1 - f01.y), l23 = __floats2half2_rn(r2 - f23.x, r3 - f23.y);
+                            const size_t off = (size_t)row * epi.ld_out + col;
+                            uint2 hv, lv;
+                            hv.x = *reinterpret_cast<const unsigned int*>(&h01);
+                            hv.y = *reinterpret_cast<const unsigned int*>(&h23);
+                            lv.x = *reinterpret_cast<const unsigned int*>(&l01);
+                            lv.y = *reinterpret_cast<const unsigned int*>(&l23);
+                            *reinterpret_cast<uint2*>(epi.out_hi + off) = hv;
+                            *reinterpret_cast<uint2*>(epi.out_lo + off) = lv;
+                            dsum[i] = (fabsf(f01.x) + fabsf(f01.y)) + (fabsf(f23.x) + fabsf(f23.y));
+                            rmax[i] = fmaxf(fmaxf(fabsf(r0), fabsf(r1)), fmaxf(fabsf(r2), fabsf(r3)));
+                            if (epi.out8 != nullptr) {  // kernel-uniform
+                                const float2 v01 = make_float2(f01.x * kOperandScale8, f01.y * kOperandScale8);
+                                const float2 v23 = make_float2(f23.x * kOperandScale8, f23.y * kOperandScale8);
+                                if (fmaxf(fmaxf(fabsf(v01.x), fabsf(v01.y)), fmaxf(fabsf(v23.x), fabsf(v23.y))) > 448.f)
+                                    dsum[i] = __int_as_float(0x7f800000);  // unscreenable row
+                                const unsigned int p01 = __nv_cvt_float2_to_fp8x2(v01, __NV_SATFINITE, __NV_E4M3);
+                                const unsigned int p23 = __nv_cvt_float2_to_fp8x2(v23, __NV_SATFINITE, __NV_E4M3);
+                                *reinterpret_cast<unsigned int*>(epi.out8 + (size_t)row * epi.ld8 + col8) = p01 | (p23 << 16);
+                            }
+                        }
+                        if (s + 4 < 8) request_b(s + 4, bq[s & 3]);   // the slot is free: the sub-step four ahead
+                        // row totals of this sub-step's two rows per half warp: the 16 lanes that share a row
+#pragma unroll
+                        for (int i = 0; i < 2; ++i) {
+                            const int row = row0 + 16 * lh + 8 * rh + 4 * hs + lrow + 2 * i;
+                            float d = dsum[i], r = rmax[i];
+#pragma unroll
+                            for (int sh = 1; sh < 16; sh <<= 1) {
+                                d += __shfl_xor_sync(0xffffffffu, d, sh);
+                                r = fmaxf(r, __shfl_xor_sync(0xffffffffu, r, sh));
+                            }
+                            if ((lane & 15) == 0 && row < epi.P) {
+                                if (epi.abs_sum_out != nullptr && d != 0.f) atomicAdd(epi.abs_sum_out + row, d);
+                                if (epi.row_stat != nullptr && r != 0.f)
+                                    atomicMax(reinterpret_cast<unsigned int*>(epi.row_stat + 4 * (size_t)row + 3), __float_as_uint(r));
+                            }
+                        }
+                    }
+                }
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, TMEM_COLS);
+    }
+}
+
 // ---- host side --------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -2743,6 +3051,49 @@ int launch_dft_gemm(const csr_plan* plan, bool adjoint, const __half* a_hi, cons
         rc = cached_operand_map(&ma_lo, a_lo, P, K, ldk, 2);
     }
     if (rc) return rc;
+    // sparse forward tiles on the sixteen-epilogue-warp kernel, the others on dft_gemm_kernel<EPI_RESID> (which skips the former)
+    static const int fwd16_env = getenv("CSR_FWD16") ? atoi(getenv("CSR_FWD16")) : -1;
+    const int fwd16 = fwd16_env >= 0 ? fwd16_env : options().fwd16;
+    if (fwd16 != 0 && !adjoint && epi.mode == EPI_RESID && epi.group_sparse > 0 && epi.a_kflags != nullptr && epi.tile_list == nullptr &&
+        epi.debug == 0 && timeline == 0 && epi.no_fast == 0 && epi.chan_per_pixel == 0 && (plan->m & 3) == 0 && (epi.ld_out & 3) == 0 &&
+        (P + BM - 1) / BM <= kMaxSingleRt && epi.b != nullptr && (reinterpret_cast<uintptr_t>(epi.b) & 15) == 0 &&
+        (reinterpret_cast<uintptr_t>(epi.chan_scale) & 15) == 0 &&
+        ((reinterpret_cast<uintptr_t>(epi.out_hi) | reinterpret_cast<uintptr_t>(epi.out_lo)) & 7) == 0 &&
+        (epi.out8 == nullptr || ((reinterpret_cast<uintptr_t>(epi.out8) | (uintptr_t)epi.ld8 | (uintptr_t)(epi.ld8 >> 1)) & 3) == 0)) {
+        static bool configured = false;
+        if (!configured) {
+            CSR_CUDA(cudaFuncSetAttribute(dft_fwd_direct_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, D16_SMEM_BYTES));
+            CSR_CUDA(cudaFuncSetAttribute(dft_gemm_kernel<EPI_RESID>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+            configured = true;
+        }
+        const int MT = (P + BM - 1) / BM, NT = (epi.N + BN - 1) / BN, KB = (K + BK - 1) / BK;
+        ProfiledLaunch rec;
+        rec.kind = 2;
+        epi.count_slot = 2;
+        if (g_profile) {
+            CSR_CUDA(pooled_event(&rec.start));
+            CSR_CUDA(pooled_event(&rec.stop));
+            CSR_CUDA(cudaEventRecord(rec.start, stream));
+        }
+        tile_single_kernel<<<(MT + 7) / 8, 256, 0, stream>>>(epi.a_kflags, epi.a_kflag_ld, (KB + 1) >> 1, KB, MT, epi.group_sparse,
+                                                            epi.no_kskip == 0);
+        CSR_LAUNCHED();
+        GemmEpilogue rest = epi;
+        rest.skip_single = 1;
+        CUtensorMap none;
+        memset(&none, 0, sizeof(none));
+        dft_gemm_kernel<EPI_RESID><<<min(MT * NT, plan->num_sms), NUM_THREADS, SMEM_BYTES, stream>>>(
+            ma_hi, ma_lo, plan->map_fwd_hi, plan->map_fwd_lo, none, none, 0, 8, K, MT, NT, gemm_chunk_kb(false), rest);
+        CSR_LAUNCHED();
+        dft_fwd_direct_kernel<<<min(MT * NT, plan->num_sms), D16_THREADS, D16_SMEM_BYTES, stream>>>(ma_hi, ma_lo, plan->map_fwd_hi,
+                                                                                                  plan->map_fwd_lo, K, MT, NT, epi);
+        CSR_LAUNCHED();
+        if (g_profile) {
+            CSR_CUDA(cudaEventRecord(rec.stop, stream));
+            g_profiled.push_back(rec);
+        }
+        return CSR_OK;
+    }
     // the K-block-skipping forward transform with its residual epilogue: 128 x 128 tiles (dft_fwd128_kernel)
     if (options().fwd128 != 0 && !adjoint && epi.mode == EPI_RESID && epi.a_kflags != nullptr && epi.tile_list == nullptr &&
         epi.debug == 0 && options().pair3 < 2 && epi.b != nullptr && (epi.ld_out & 1) == 0 &&

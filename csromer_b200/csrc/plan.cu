@@ -110,7 +110,7 @@ Options& options() {
                         getenv("CSR_NO_TMA_EPI") == nullptr, getenv("CSR_NO_NUFFT") == nullptr,
                         getenv("CSR_FWD128") != nullptr,    // (measured: no faster than the 256-column kernel; off by default)
                         getenv("CSR_FWD_GROUP") != nullptr ? atoi(getenv("CSR_FWD_GROUP")) : 16,
-                        getenv("CSR_NO_GRAPH") == nullptr};
+                        getenv("CSR_NO_GRAPH") == nullptr, 0};
     return o;
 }
 }  // namespace csr
@@ -138,6 +138,7 @@ extern "C" int csr_set_option(const char* name, int value) {
     else if (!strcmp(name, "nufft")) o.nufft = value != 0;
     else if (!strcmp(name, "fwd128")) o.fwd128 = value != 0;
     else if (!strcmp(name, "graph")) o.graph = value != 0;
+    else if (!strcmp(name, "fwd16")) o.fwd16 = value != 0;
     else if (!strcmp(name, "fwd_group")) o.fwd_group = value < 0 ? 0 : value;   // threshold in K blocks; 0 = off
     else {
         set_error("csr_set_option: unknown option '%s'", name);

@@ -282,6 +282,25 @@ def test_sparsity_shortcuts_are_bit_exact(nch, P, K, kw):
     check_fista(src, X, cost, l1, ref)
 
 
+@pytest.mark.parametrize("nch,P,K", [(200, 300, 30), (1000, 261, 20)])
+def test_forward_tiles_on_sixteen_epilogue_warps_keep_the_bits(nch, P, K):
+    """option fwd16: the sparse forward tiles run on dft_fwd_direct_kernel (sixteen epilogue warps, 64 columns per warp), the
+    rest on dft_gemm_kernel<EPI_RESID>: same element arithmetic, same solution bit for bit"""
+    from csromer_b200 import _lib
+    src, par = make_batch(nch, P, seed=90 + P, mixed=True)
+    out = []
+    try:
+        for fwd16 in (0, 1):
+            _lib.set_option("fwd16", fwd16)
+            cost, X, l1, lam0, noise = run_fista(src, par, K)
+            out.append((np.array(X.data, copy=True), np.array(cost, copy=True), np.array(src.model_data, copy=True)))
+    finally:
+        _lib.set_option("fwd16", 0)
+    assert 0 < np.count_nonzero(out[0][0]) < 0.2 * out[0][0].size
+    for a, b in zip(out[0], out[1]):
+        np.testing.assert_array_equal(a, b)
+
+
 def test_fista_reuses_the_dirty_spectrum_it_was_started_from():
     """README.md:183-190 with torch data: F_dirty = dft.backward(dataset.data) becomes the guess.  When the guess still is that
     untouched tensor, the fused loop takes the planar device copy `backward` kept (no transpose back, no second dirty spectrum);
