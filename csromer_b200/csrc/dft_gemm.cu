@@ -746,6 +746,7 @@ __device__ __forceinline__ bool options_rows_ok(const GemmEpilogue& epi) {
 // pixel tiles whose forward tiles go to dft_fwd_direct_kernel (written by tile_single_kernel; GemmEpilogue::skip_single)
 constexpr int kMaxSingleRt = 8192;
 __device__ unsigned char g_single_rt[kMaxSingleRt];
+__device__ int g_rest_tiles;   // pixel tiles NOT marked (zeroed before tile_single_kernel): none -> dft_gemm_kernel<EPI_RESID> returns at once
 
 // Measurement aid (CSR_TIMELINE=1, csr_debug_timeline): clock64 stamps of the three roles for the first kTimelineTiles tiles of
 // every CTA of the last residual forward launch -- [cta][tile][8]: producer start / last load issued, MMA first operand seen /
@@ -762,6 +763,7 @@ dft_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
                 const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
                 const __grid_constant__ CUtensorMap map_pf0, const __grid_constant__ CUtensorMap map_pf1,
                 int num_prefetch, int prefetch_lead, int K, int MT, int NT, int chunk_kb, const GemmEpilogue epi) {
+    if (MODE == EPI_RESID && epi.skip_single != 0 && g_rest_tiles == 0) return;   // (kernel-uniform: every tile is the direct kernel's)
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* stage_base = smem;
@@ -2455,7 +2457,11 @@ __global__ void tile_single_kernel(const unsigned int* __restrict__ flags, int f
     }
     last = __shfl_sync(0xffffffffu, last, (kwords - 1) & 31);
     if ((KB & 1) && last != 0u) count -= 1;   // (the last flag word covers a single K block when KB is odd: build_kmask)
-    if (lane == 0) g_single_rt[mt] = (unsigned char)(count <= group_max && !(skip && count == 0));
+    if (lane == 0) {
+        const bool single = count <= group_max && !(skip && count == 0);
+        g_single_rt[mt] = (unsigned char)single;
+        if (!single) atomicAdd(&g_rest_tiles, 1);
+    }
 }
 
 __global__ void __launch_bounds__(D16_THREADS, 1)
@@ -3074,6 +3080,11 @@ int launch_dft_gemm(const csr_plan* plan, bool adjoint, const __half* a_hi, cons
             CSR_CUDA(pooled_event(&rec.start));
             CSR_CUDA(pooled_event(&rec.stop));
             CSR_CUDA(cudaEventRecord(rec.start, stream));
+        }
+        {
+            void* rest_ptr = nullptr;
+            CSR_CUDA(cudaGetSymbolAddress(&rest_ptr, g_rest_tiles));
+            CSR_CUDA(cudaMemsetAsync(rest_ptr, 0, sizeof(int), stream));
         }
         tile_single_kernel<<<(MT + 7) / 8, 256, 0, stream>>>(epi.a_kflags, epi.a_kflag_ld, (KB + 1) >> 1, KB, MT, epi.group_sparse,
                                                             epi.no_kskip == 0);

@@ -110,7 +110,7 @@ Options& options() {
                         getenv("CSR_NO_TMA_EPI") == nullptr, getenv("CSR_NO_NUFFT") == nullptr,
                         getenv("CSR_FWD128") != nullptr,    // (measured: no faster than the 256-column kernel; off by default)
                         getenv("CSR_FWD_GROUP") != nullptr ? atoi(getenv("CSR_FWD_GROUP")) : 16,
-                        getenv("CSR_NO_GRAPH") == nullptr, 0};
+                        getenv("CSR_NO_GRAPH") == nullptr, getenv("CSR_NO_FWD16") == nullptr};
     return o;
 }
 }  // namespace csr

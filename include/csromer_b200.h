@@ -274,7 +274,8 @@ int csr_debug_timeline(long long* out, int cap);
  * nothing changes while a run stays in range), "pair3" (0 / 1 / 2: three-product transforms on cta_group::2 CTA pairs --
  * off / dense transforms only (default) / every whole-matrix transform), "tma_epi" (with pair3 = 2: residual epilogue staged
  * through shared memory, TMA loads of b and TMA stores of r), "fwd128" (K-block-skipping forward transform on 128 x 128
- * tiles with 16 epilogue warps; default 0), "graph" (csr_fista: a call repeated with identical arguments -- the same plan,
+ * tiles with 16 epilogue warps; default 0), "fwd16" (delta-basis forward tiles that accumulate one chunk run on
+ * dft_fwd_direct_kernel, sixteen epilogue warps on 64-column pieces; default 1), "graph" (csr_fista: a call repeated with identical arguments -- the same plan,
  * buffers, sizes and option values, what a slab loop does -- is captured once and replayed as one CUDA graph; default 1).
  * Two switches are NOT bit-neutral: "nufft" (default 1) runs the per-line-of-sight transforms (csr_nudft_*, csr_fista_nu) as
  * shared-memory NUFFTs, ~1e-6 of the result's scale away from the direct sums that nufft = 0 evaluates; "fwd_group" (default

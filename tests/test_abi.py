@@ -63,7 +63,7 @@ def test_documented_options_are_accepted(built_library):
     doc = header[header.index("run-time switches of the exact shortcuts"):header.index("int csr_set_option")]
     names = re.findall(r'"(\w+)"', doc)
     assert {"zero_skip", "k_skip", "screen", "screen8", "pair", "sym", "resid_fast", "screen16_pair", "fused_wavelet",
-            "wavelet_vec4", "wavelet_screen", "screen_incr", "rescale", "pair3", "tma_epi", "fwd128", "nufft", "graph", "fwd_group"} <= set(names)
+            "wavelet_vec4", "wavelet_screen", "screen_incr", "rescale", "pair3", "tma_epi", "fwd128", "nufft", "graph", "fwd_group", "fwd16"} <= set(names)
     for name in names:
         assert lib.csr_set_option(name.encode(), 1) == 0, name
     assert lib.csr_set_option(b"no_such_option", 1) != 0 and b"unknown option" in lib.csr_last_error()

@@ -295,7 +295,7 @@ def test_forward_tiles_on_sixteen_epilogue_warps_keep_the_bits(nch, P, K):
             cost, X, l1, lam0, noise = run_fista(src, par, K)
             out.append((np.array(X.data, copy=True), np.array(cost, copy=True), np.array(src.model_data, copy=True)))
     finally:
-        _lib.set_option("fwd16", 0)
+        _lib.set_option("fwd16", 1)
     assert 0 < np.count_nonzero(out[0][0]) < 0.2 * out[0][0].size
     for a, b in zip(out[0], out[1]):
         np.testing.assert_array_equal(a, b)
