@@ -2464,6 +2464,7 @@ __global__ void tile_single_kernel(const unsigned int* __restrict__ flags, int f
     }
 }
 
+template <bool CS_PP>   // channel factors of the pixel's own ([P, m], requested like b) instead of shared ones
 __global__ void __launch_bounds__(D16_THREADS, 1)
 dft_fwd_direct_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                       const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo, int K, int MT, int NT,
@@ -2620,21 +2621,26 @@ dft_fwd_direct_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid
                 my_desc = kTwiddleDescale / __ldg(epi.a_scale + row0 + lane);
                 my_osc = __ldg(epi.out_scale + row0 + lane);
             }
-            const float4 cf = (epi.chan_scale != nullptr && col_ok) ? __ldg(reinterpret_cast<const float4*>(epi.chan_scale + chan))
-                                                                    : make_float4(1.f, 1.f, 1.f, 1.f);
-            // b: sub-step s = (lh, rh, hs) covers rows 16 lh + 8 rh + 4 hs + lrow + 2 i (i = 0, 1); four sub-steps in flight
-            float4 bq[4][2];
-            auto request_b = [&](int s, float4 (&dst)[2]) {
+            const float4 cf_shared = (!CS_PP && epi.chan_scale != nullptr && col_ok) ? __ldg(reinterpret_cast<const float4*>(epi.chan_scale + chan))
+                                                                                     : make_float4(1.f, 1.f, 1.f, 1.f);
+            // b (and the pixel's own channel factors): sub-step s = (lh, rh, hs) covers rows 16 lh + 8 rh + 4 hs + lrow + 2 i
+            // (i = 0, 1); DEPTH sub-steps in flight -- four of b alone, two of b and channel factors (the same registers)
+            constexpr int DEPTH = CS_PP ? 2 : 4;
+            float4 bq[DEPTH][2], cq_[CS_PP ? DEPTH : 1][2];
+            auto request_b = [&](int s, int slot) {
                 const int base = 16 * (s >> 2) + 8 * ((s >> 1) & 1) + 4 * (s & 1) + lrow;
 #pragma unroll
                 for (int i = 0; i < 2; ++i) {
                     const int row = row0 + base + 2 * i;
-                    dst[i] = (row < epi.P && col_ok) ? __ldcg(reinterpret_cast<const float4*>(epi.b + (size_t)row * epi.ld_out + col))
-                                                     : make_float4(0.f, 0.f, 0.f, 0.f);
+                    const bool ok = row < epi.P && col_ok;
+                    bq[slot][i] = ok ? __ldcg(reinterpret_cast<const float4*>(epi.b + (size_t)row * epi.ld_out + col)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (CS_PP)
+                        cq_[slot][i] = ok ? __ldcg(reinterpret_cast<const float4*>(epi.chan_scale + (size_t)row * epi.m + chan))
+                                          : make_float4(1.f, 1.f, 1.f, 1.f);
                 }
             };
 #pragma unroll
-            for (int s = 0; s < 4; ++s) request_b(s, bq[s]);
+            for (int s = 0; s < DEPTH; ++s) request_b(s, s);
             mbar_wait(&tmem_full[buf], par);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(sub * 32) << 16) + (uint32_t)(buf * BN + cq * 64);
@@ -2669,7 +2675,8 @@ dft_fwd_direct_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid
                             const float4 a = *reinterpret_cast<const float4*>(xp + (lrow + 2 * i) * D16_XP_ROW + lcol);
                             const float desc = __shfl_sync(0xffffffffu, my_desc, lr), osc = __shfl_sync(0xffffffffu, my_osc, lr);
                             if (row >= epi.P || !col_ok) continue;
-                            const float4 b = bq[s & 3][i];
+                            const float4 b = bq[s % DEPTH][i];
+                            const float4 cf = CS_PP ? cq_[CS_PP ? s % DEPTH : 0][i] : cf_shared;
                             const float r0 = __fmaf_rn(cf.x, a.x * desc, -b.x) * osc, r1 = __fmaf_rn(cf.y, a.y * desc, -b.y) * osc;
                             const float r2 = __fmaf_rn(cf.z, a.z * desc, -b.z) * osc, r3 = __fmaf_rn(cf.w, a.w * desc, -b.w) * osc;
                             const __half2 h01 = __floats2half2_rn(r0, r1), h23 = __floats2half2_rn(r2, r3);
@@ -2695,7 +2702,7 @@ dft_fwd_direct_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid
                                 *reinterpret_cast<unsigned int*>(epi.out8 + (size_t)row * epi.ld8 + col8) = p01 | (p23 << 16);
                             }
                         }
-                        if (s + 4 < 8) request_b(s + 4, bq[s & 3]);   // the slot is free: the sub-step four ahead
+                        if (s + DEPTH < 8) request_b(s + DEPTH, s % DEPTH);   // the slot is free: the sub-step DEPTH ahead
                         // row totals of this sub-step's two rows per half warp: the 16 lanes that share a row
 #pragma unroll
                         for (int i = 0; i < 2; ++i) {
@@ -3061,14 +3068,16 @@ int launch_dft_gemm(const csr_plan* plan, bool adjoint, const __half* a_hi, cons
     static const int fwd16_env = getenv("CSR_FWD16") ? atoi(getenv("CSR_FWD16")) : -1;
     const int fwd16 = fwd16_env >= 0 ? fwd16_env : options().fwd16;
     if (fwd16 != 0 && !adjoint && epi.mode == EPI_RESID && epi.group_sparse > 0 && epi.a_kflags != nullptr && epi.tile_list == nullptr &&
-        epi.debug == 0 && timeline == 0 && epi.no_fast == 0 && epi.chan_per_pixel == 0 && (plan->m & 3) == 0 && (epi.ld_out & 3) == 0 &&
+        epi.debug == 0 && timeline == 0 && epi.no_fast == 0 && (epi.chan_per_pixel == 0 || epi.chan_scale != nullptr) && (plan->m & 3) == 0 &&
+        (epi.ld_out & 3) == 0 &&
         (P + BM - 1) / BM <= kMaxSingleRt && epi.b != nullptr && (reinterpret_cast<uintptr_t>(epi.b) & 15) == 0 &&
         (reinterpret_cast<uintptr_t>(epi.chan_scale) & 15) == 0 &&
         ((reinterpret_cast<uintptr_t>(epi.out_hi) | reinterpret_cast<uintptr_t>(epi.out_lo)) & 7) == 0 &&
         (epi.out8 == nullptr || ((reinterpret_cast<uintptr_t>(epi.out8) | (uintptr_t)epi.ld8 | (uintptr_t)(epi.ld8 >> 1)) & 3) == 0)) {
         static bool configured = false;
         if (!configured) {
-            CSR_CUDA(cudaFuncSetAttribute(dft_fwd_direct_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, D16_SMEM_BYTES));
+            CSR_CUDA(cudaFuncSetAttribute(dft_fwd_direct_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, D16_SMEM_BYTES));
+            CSR_CUDA(cudaFuncSetAttribute(dft_fwd_direct_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, D16_SMEM_BYTES));
             CSR_CUDA(cudaFuncSetAttribute(dft_gemm_kernel<EPI_RESID>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
             configured = true;
         }
@@ -3096,8 +3105,12 @@ int launch_dft_gemm(const csr_plan* plan, bool adjoint, const __half* a_hi, cons
         dft_gemm_kernel<EPI_RESID><<<min(MT * NT, plan->num_sms), NUM_THREADS, SMEM_BYTES, stream>>>(
             ma_hi, ma_lo, plan->map_fwd_hi, plan->map_fwd_lo, none, none, 0, 8, K, MT, NT, gemm_chunk_kb(false), rest);
         CSR_LAUNCHED();
-        dft_fwd_direct_kernel<<<min(MT * NT, plan->num_sms), D16_THREADS, D16_SMEM_BYTES, stream>>>(ma_hi, ma_lo, plan->map_fwd_hi,
-                                                                                                  plan->map_fwd_lo, K, MT, NT, epi);
+        if (epi.chan_per_pixel != 0)
+            dft_fwd_direct_kernel<true><<<min(MT * NT, plan->num_sms), D16_THREADS, D16_SMEM_BYTES, stream>>>(ma_hi, ma_lo, plan->map_fwd_hi,
+                                                                                                            plan->map_fwd_lo, K, MT, NT, epi);
+        else
+            dft_fwd_direct_kernel<false><<<min(MT * NT, plan->num_sms), D16_THREADS, D16_SMEM_BYTES, stream>>>(ma_hi, ma_lo, plan->map_fwd_hi,
+                                                                                                             plan->map_fwd_lo, K, MT, NT, epi);
         CSR_LAUNCHED();
         if (g_profile) {
             CSR_CUDA(cudaEventRecord(rec.stop, stream));

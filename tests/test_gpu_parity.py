@@ -282,12 +282,13 @@ def test_sparsity_shortcuts_are_bit_exact(nch, P, K, kw):
     check_fista(src, X, cost, l1, ref)
 
 
-@pytest.mark.parametrize("nch,P,K", [(200, 300, 30), (1000, 261, 20)])
-def test_forward_tiles_on_sixteen_epilogue_warps_keep_the_bits(nch, P, K):
+@pytest.mark.parametrize("nch,P,K,kw", [(200, 300, 30, dict(mixed=True)), (1000, 261, 20, dict(mixed=True)),
+                                        (204, 290, 25, dict(per_pixel_w=True, flags=0.15))])
+def test_forward_tiles_on_sixteen_epilogue_warps_keep_the_bits(nch, P, K, kw):
     """option fwd16: the sparse forward tiles run on dft_fwd_direct_kernel (sixteen epilogue warps, 64 columns per warp), the
     rest on dft_gemm_kernel<EPI_RESID>: same element arithmetic, same solution bit for bit"""
     from csromer_b200 import _lib
-    src, par = make_batch(nch, P, seed=90 + P, mixed=True)
+    src, par = make_batch(nch, P, seed=90 + P, **kw)
     out = []
     try:
         for fwd16 in (0, 1):
