@@ -71,7 +71,8 @@ KIND_NAMES = ["plain_forward", "plain_adjoint", "resid_forward", "resid_adjoint"
 KERNEL_OF_KIND = {
     0: "dft_gemm_kernel<EPI_PLAIN> forward (three fp16 products, tcgen05 kind::f16)",
     1: "dft_gemm_kernel<EPI_PLAIN> adjoint (three fp16 products)",
-    2: "dft_gemm_kernel<EPI_RESID> forward + fused residual epilogue (K-block skipping)",
+    2: "forward + fused residual epilogue (K-block skipping): dft_fwd_direct_kernel on the sparse tiles (one accumulation chunk, "
+       "sixteen epilogue warps, row-contiguous global accesses) + dft_gemm_kernel<EPI_RESID> on the others, timed together",
     5: "dft_gemm_kernel<EPI_FISTA> adjoint + fused threshold / momentum epilogue on the listed tiles",
     6: "swt_synth_fused4_kernel (all synthesis levels + operand split, shared-memory staged)",
     7: "swt_analysis_fused4_kernel<UPDATE> (all analysis levels + threshold + momentum)",
