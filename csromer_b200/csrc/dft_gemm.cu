@@ -31,9 +31,18 @@
 //        0  fp8 screening                     3  fp8 screening, mirror-symmetric (+phi and -phi from half the K)
 //        1  fp16 plain adjoint (EPI_PLAIN1)   4  fp16 screening, mirror-symmetric
 //        2  fp16 screening                    5  fp16 plain adjoint, mirror-symmetric
-//   epilogue_resid_fast                                  the lean residual epilogue of interior column runs
-//   sym_quiet_kernel, split_tile_lists_kernel, pair_list_kernel, sym_pair_list_kernel, screen_eps_kernel   small helpers
-// and the host-side launchers with their tensor-map cache and per-launch CUDA-event profiling.
+//   dft_gemm_pair_kernel<MODE, TMA_EPI>                  the three-product transforms on CTA pairs (dense transforms; option pair3)
+//   dft_fwd_direct_kernel<CS_PP>                         the sparse tiles of the forward transform (one accumulation chunk, option
+//                                                        fwd_group): accumulator read straight from TMEM by SIXTEEN epilogue warps,
+//                                                        sub-pieces transposed through shared memory, row-contiguous global accesses
+//                                                        (tile_single_kernel marks those tiles; dft_gemm_kernel<EPI_RESID> keeps the rest)
+//   dft_fwd128_kernel                                    the forward transform on 128 x 128 tiles (experiment, option fwd128)
+//   epilogue_resid_fast, resid_request / resid_compute, resid_direct_rows   residual epilogues of dft_gemm_kernel<EPI_RESID>: lean,
+//                                                        software-pipelined over the row groups, direct (sparse tiles, eight warps)
+//   sym_select_kernel, row_update_kernel, rmtf_abs_kernel, suffix_max_kernel   incremental safe screening (margins, row clocks, envelope)
+//   split_tile_lists_kernel, pair_list_kernel, sym_pair_list_kernel, screen_eps_kernel   small helpers
+// and the host-side launchers with their tensor-map cache, per-launch CUDA-event profiling and the role time line
+// (CSR_TIMELINE, csr_debug_timeline).
 #include <stdlib.h>
 #include <string.h>
 

@@ -260,3 +260,34 @@ def test_make_mask_helpers_follow_the_reference():
     assert set(zip(*kept)) == set(zip(*np.where(expect))) and (1, 2) not in set(zip(*kept)) and (4, 5) in set(zip(*masked))
     kept2, _ = make_mask_faraday(I, P, Q, U, alpha, 0.3, 0.2)
     assert set(zip(*kept2)) == set(zip(*np.where(expect & ~np.isnan(alpha))))
+
+
+def test_parameter_remembers_which_complex_tensor_its_planar_copy_came_from():
+    """Parameter.complex_source(): the complex torch tensor `data` was made from by complex_data_to_real, as long as neither has
+    been modified (version counters) or replaced -- what lets FISTA reuse the planar device copy NDFT1D.backward kept."""
+    import torch
+    par = cs.Parameter()
+    z = torch.complex(torch.arange(6.0), -torch.arange(6.0))
+    par.data = z
+    assert par.complex_source() is None
+    par.complex_data_to_real()
+    assert par.data.shape == (12,) and par.complex_source() is z
+    par.data[3] = 7.0                      # in place: the version counter of the planar copy moves
+    assert par.complex_source() is None
+    par.data = z
+    par.complex_data_to_real()
+    z.mul_(2.0)                            # ... or the source's
+    assert par.complex_source() is None
+    par.data = z
+    par.complex_data_to_real()
+    par.data = par.data.clone()            # replaced
+    assert par.complex_source() is None
+    import copy, pickle
+    par.data = z
+    par.complex_data_to_real()
+    assert copy.deepcopy(par).data.shape == (12,)
+    assert pickle.loads(pickle.dumps(par)).complex_source() is None
+    npar = cs.Parameter()
+    npar.data = np.arange(4) + 1j * np.arange(4)
+    npar.complex_data_to_real()            # numpy arrays carry no version: never "the same"
+    assert npar.complex_source() is None
