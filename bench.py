@@ -471,7 +471,9 @@ def timed_steps(ctx, w, steps, warmup, first=0):
     roofline entries.  The event pairs cost about 7 % of a C3 step (1400 launches), so they stay out of the region `value`
     is timed on; `profiled_ms` is the duration of the second pass, the denominator of the kernels' shares."""
     torch, lib = ctx.torch, ctx.lib
-    for i in range(warmup):
+    # (the steps alternate between two slabs, and the library captures a call as a CUDA graph the second time it sees its
+    #  arguments: four untimed steps put both captures in front of the timed region whatever W the caller asked for)
+    for i in range(max(warmup, 4 + (warmup & 1))):
         w.step(first + i)
     ctx.barrier()
     sampler = ClockSampler(ctx.local)

@@ -752,10 +752,10 @@ __device__ __forceinline__ bool options_rows_ok(const GemmEpilogue& epi) {
            (epi.out8 == nullptr || ((reinterpret_cast<uintptr_t>(epi.out8) | (uintptr_t)epi.ld8 | (uintptr_t)(epi.ld8 >> 1)) & 3) == 0);
 }
 
-// pixel tiles whose forward tiles go to dft_fwd_direct_kernel (written by tile_single_kernel; GemmEpilogue::skip_single)
-constexpr int kMaxSingleRt = 8192;
-__device__ unsigned char g_single_rt[kMaxSingleRt];
-__device__ int g_rest_tiles;   // pixel tiles NOT marked (zeroed before tile_single_kernel): none -> dft_gemm_kernel<EPI_RESID> returns at once
+// GemmEpilogue::single_rt (per call, in the caller's workspace): [0 .. MT) one byte per pixel tile, 1 = its forward tiles go to
+// dft_fwd_direct_kernel (written by tile_single_kernel); then, 4-byte aligned, one int: the number of pixel tiles NOT marked
+// (zeroed before tile_single_kernel): none -> dft_gemm_kernel<EPI_RESID> returns at once
+__host__ __device__ __forceinline__ size_t single_rt_counter_offset(int MT) { return ((size_t)MT + 3) & ~(size_t)3; }
 
 // Measurement aid (CSR_TIMELINE=1, csr_debug_timeline): clock64 stamps of the three roles for the first kTimelineTiles tiles of
 // every CTA of the last residual forward launch -- [cta][tile][8]: producer start / last load issued, MMA first operand seen /
@@ -772,7 +772,9 @@ dft_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
                 const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
                 const __grid_constant__ CUtensorMap map_pf0, const __grid_constant__ CUtensorMap map_pf1,
                 int num_prefetch, int prefetch_lead, int K, int MT, int NT, int chunk_kb, const GemmEpilogue epi) {
-    if (MODE == EPI_RESID && epi.skip_single != 0 && g_rest_tiles == 0) return;   // (kernel-uniform: every tile is the direct kernel's)
+    if (MODE == EPI_RESID && epi.skip_single != 0 &&
+        *reinterpret_cast<const int*>(epi.single_rt + single_rt_counter_offset(MT)) == 0)
+        return;   // (kernel-uniform: every tile is the direct kernel's)
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* stage_base = smem;
@@ -863,7 +865,7 @@ dft_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
                 const int t = tile_id(ti);
                 int mt, nt;
                 tile_coords(t, MT, NT, mt, nt);
-                if (MODE == EPI_RESID && epi.skip_single != 0 && g_single_rt[mt]) continue;   // dft_fwd_direct_kernel's
+                if (MODE == EPI_RESID && epi.skip_single != 0 && epi.single_rt[mt]) continue;   // dft_fwd_direct_kernel's
                 const bool quiet = quiet_next;  // (the next tile's state is fetched while this one streams)
                 if (IS_SCREEN && ti + (int)gridDim.x < total_tiles) quiet_next = tile_quiet(tile_id(ti + gridDim.x));
                 if (IS_SCREEN && !quiet) continue;  // tile with signal: left to the three-product kernel
@@ -925,7 +927,7 @@ dft_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
                 if (MODE == EPI_RESID && epi.skip_single != 0) {
                     int mt, nt;
                     tile_coords(tile_id(ti), MT, NT, mt, nt);
-                    if (g_single_rt[mt]) continue;
+                    if (epi.single_rt[mt]) continue;
                 }
                 bool single = false;
                 if (skip || group_max > 0) {
@@ -1022,7 +1024,7 @@ dft_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
             const int t = tile_id(ti);
             int mt, nt;
             tile_coords(t, MT, NT, mt, nt);
-            if (MODE == EPI_RESID && epi.skip_single != 0 && g_single_rt[mt]) continue;
+            if (MODE == EPI_RESID && epi.skip_single != 0 && epi.single_rt[mt]) continue;
             if (IS_SCREEN && !tile_quiet(t)) {  // hand the tile on to the next kernel of the cascade (one warp lists it)
                 if (lane == 0 && atomicMax(last_listed, ti) < ti) epi.out_list[atomicAdd(epi.out_count, 1)] = t;
                 continue;
@@ -2451,7 +2453,8 @@ constexpr int D16_XP_BYTES = 4 * D16_XP_ROW * 4;           // 4 rows per sub-pie
 constexpr int D16_SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + 256 + 2 * KMASK_WORDS * 4 + D16_EPW * D16_XP_BYTES;
 static_assert(D16_SMEM_BYTES <= 232448, "shared memory budget exceeded");
 // single_rt[mt] = 1: the pixel tile has at most group_max active K blocks (and at least one when K blocks are skipped)
-__global__ void tile_single_kernel(const unsigned int* __restrict__ flags, int flag_ld, int kwords, int KB, int MT, int group_max, int skip) {
+__global__ void tile_single_kernel(const unsigned int* __restrict__ flags, int flag_ld, int kwords, int KB, int MT, int group_max, int skip,
+                                   unsigned char* __restrict__ single_rt) {
     const int mt = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (mt >= MT) return;
@@ -2468,8 +2471,8 @@ __global__ void tile_single_kernel(const unsigned int* __restrict__ flags, int f
     if ((KB & 1) && last != 0u) count -= 1;   // (the last flag word covers a single K block when KB is odd: build_kmask)
     if (lane == 0) {
         const bool single = count <= group_max && !(skip && count == 0);
-        g_single_rt[mt] = (unsigned char)single;
-        if (!single) atomicAdd(&g_rest_tiles, 1);
+        single_rt[mt] = (unsigned char)single;
+        if (!single) atomicAdd(reinterpret_cast<int*>(single_rt + single_rt_counter_offset(MT)), 1);
     }
 }
 
@@ -2531,7 +2534,7 @@ dft_fwd_direct_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid
         for (int ti = blockIdx.x; ti < total_tiles; ti += gridDim.x) {
             int mt, nt;
             tile_coords(ti, MT, NT, mt, nt);
-            if (!g_single_rt[mt]) continue;
+            if (!epi.single_rt[mt]) continue;
             if (skip) build_kmask(epi.a_kflags + (size_t)mt * epi.a_kflag_ld, kwords, KB, my_mask, lane);
             if (lane == 0) {
                 for (int kb = skip ? next_active_kb(my_mask, 0, KB) : 0; kb < KB; kb = skip ? next_active_kb(my_mask, kb + 1, KB) : kb + 1) {
@@ -2561,7 +2564,7 @@ dft_fwd_direct_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid
         for (int ti = blockIdx.x; ti < total_tiles; ti += gridDim.x) {
             int mt, nt;
             tile_coords(ti, MT, NT, mt, nt);
-            if (!g_single_rt[mt]) continue;
+            if (!epi.single_rt[mt]) continue;
             if (skip) build_kmask(epi.a_kflags + (size_t)mt * epi.a_kflag_ld, kwords, KB, my_mask, lane);
             if (lane == 0) {
                 const int buf = tile_no & 1;
@@ -2610,7 +2613,7 @@ dft_fwd_direct_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid
         for (int ti = blockIdx.x; ti < total_tiles; ti += gridDim.x) {
             int mt, nt;
             tile_coords(ti, MT, NT, mt, nt);
-            if (!g_single_rt[mt]) continue;
+            if (!epi.single_rt[mt]) continue;
             const int buf = tile_no & 1;
             const uint32_t par = (tile_no >> 1) & 1;
             ++tile_no;
@@ -3079,7 +3082,7 @@ int launch_dft_gemm(const csr_plan* plan, bool adjoint, const __half* a_hi, cons
     if (fwd16 != 0 && !adjoint && epi.mode == EPI_RESID && epi.group_sparse > 0 && epi.a_kflags != nullptr && epi.tile_list == nullptr &&
         epi.debug == 0 && timeline == 0 && epi.no_fast == 0 && (epi.chan_per_pixel == 0 || epi.chan_scale != nullptr) && (plan->m & 3) == 0 &&
         (epi.ld_out & 3) == 0 &&
-        (P + BM - 1) / BM <= kMaxSingleRt && epi.b != nullptr && (reinterpret_cast<uintptr_t>(epi.b) & 15) == 0 &&
+        epi.single_rt != nullptr && epi.b != nullptr && (reinterpret_cast<uintptr_t>(epi.b) & 15) == 0 &&
         (reinterpret_cast<uintptr_t>(epi.chan_scale) & 15) == 0 &&
         ((reinterpret_cast<uintptr_t>(epi.out_hi) | reinterpret_cast<uintptr_t>(epi.out_lo)) & 7) == 0 &&
         (epi.out8 == nullptr || ((reinterpret_cast<uintptr_t>(epi.out8) | (uintptr_t)epi.ld8 | (uintptr_t)(epi.ld8 >> 1)) & 3) == 0)) {
@@ -3099,13 +3102,9 @@ int launch_dft_gemm(const csr_plan* plan, bool adjoint, const __half* a_hi, cons
             CSR_CUDA(pooled_event(&rec.stop));
             CSR_CUDA(cudaEventRecord(rec.start, stream));
         }
-        {
-            void* rest_ptr = nullptr;
-            CSR_CUDA(cudaGetSymbolAddress(&rest_ptr, g_rest_tiles));
-            CSR_CUDA(cudaMemsetAsync(rest_ptr, 0, sizeof(int), stream));
-        }
+        CSR_CUDA(cudaMemsetAsync(epi.single_rt + single_rt_counter_offset(MT), 0, sizeof(int), stream));
         tile_single_kernel<<<(MT + 7) / 8, 256, 0, stream>>>(epi.a_kflags, epi.a_kflag_ld, (KB + 1) >> 1, KB, MT, epi.group_sparse,
-                                                            epi.no_kskip == 0);
+                                                            epi.no_kskip == 0, epi.single_rt);
         CSR_LAUNCHED();
         GemmEpilogue rest = epi;
         rest.skip_single = 1;

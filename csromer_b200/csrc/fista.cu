@@ -83,6 +83,7 @@ struct FistaWs {
     __half *r_hi, *r_lo, *z_hi, *z_lo;
     unsigned char* zero_flags;
     unsigned int* tile_flags;
+    unsigned char* single_rt;   // [MT] + one int: which pixel tiles the sixteen-warp forward kernel takes (dft_gemm.cu)
     int flag_ld;
     // safe screening of the adjoint (delta basis): [0] = number of listed tiles, [8 ...) = S_p per line of sight
     float* screen_hdr;
@@ -122,6 +123,7 @@ static FistaWs carve_fista(const csr_plan* plan, const csr_wavelet* wav, int P, 
     f.flag_ld = (2 * plan->n + 127) / 128;
     f.zero_flags = b.take<unsigned char>((size_t)P * f.flag_ld);
     f.tile_flags = b.take<unsigned int>((size_t)((P + BM - 1) / BM) * f.flag_ld);
+    f.single_rt = b.take<unsigned char>((size_t)((P + BM - 1) / BM) + 16);
     f.screen_hdr = b.take<float>((size_t)P + 8);
     f.tile_list = b.take<int>((size_t)((P + BM - 1) / BM) * ((2 * plan->n + BN - 1) / BN));
     f.tile_list2 = b.take<int>((size_t)((P + BM - 1) / BM) * ((2 * plan->n + BN - 1) / BN));
@@ -392,6 +394,7 @@ static int fista_run(csr_plan* plan, csr_wavelet* wav, const csr_fista_args& a, 
                 e.a_kflag_ld = w.flag_ld;
                 e.no_kskip = use_kskip ? 0 : 1;
                 e.group_sparse = fwd_group;
+                e.single_rt = w.single_rt;
             }
             if (use_screen || wav_screen) {
                 CSR_CUDA(cudaMemsetAsync(w.screen_hdr, 0, sizeof(float) * ((size_t)P + 8), stream));

@@ -93,7 +93,8 @@ struct GemmEpilogue {
     const unsigned int* a_kflags;
     int a_kflag_ld;
     int no_kskip;                   // 1 = the flags are there for group_sparse only: walk every K block
-    int skip_single;                // 1 = leave the pixel tiles marked in g_single_rt to dft_fwd_direct_kernel
+    int skip_single;                // 1 = leave the pixel tiles marked in single_rt to dft_fwd_direct_kernel
+    unsigned char* single_rt;       // scratch of the sixteen-warp forward path: [MT] marks + one int (dft_gemm.cu); null = not used
     int group_sparse;               // EPI_RESID forward: tiles with at most this many active K blocks (by a_kflags) accumulate
                                     // them as one chunk and take the direct epilogue (0 = window-aligned chunks everywhere)
     // Safe screening of the FISTA adjoint (exact, see dft_gemm.cu "screening"):
