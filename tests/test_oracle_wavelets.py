@@ -154,3 +154,18 @@ def test_extension_modes_reconstruct_perfectly(mode):
     d = ob.WaveletDict("coif2", kind="dwt", mode=mode, append_signal=True)
     x = rng.normal(size=(200, 3))
     assert np.abs(d.reconstruct(d.decompose(x)) - 2 * x).max() < 1e-9
+
+
+def test_multilevel_symmetric_matches_the_pywavelets_documentation_values():
+    """two more documented PyWavelets answers (default mode 'symmetric'): `pywt.wavedec([1..8], 'db1', level=2)` prints
+    cA2 = [5, 13], cD2 = [-2, -2], cD1 = [-0.70710678] * 4, and `pywt.dwt([1..6], 'db1')` prints
+    ([2.12132034, 4.94974747, 7.77817459], [-0.70710678] * 3)"""
+    bank = ob.filter_bank("db1")
+    cA2, cD2, cD1 = ob.wavedec_mode(np.arange(1.0, 9.0), bank, "symmetric", level=2)
+    np.testing.assert_allclose(cA2, [5.0, 13.0], atol=1e-12)
+    np.testing.assert_allclose(cD2, [-2.0, -2.0], atol=1e-12)
+    np.testing.assert_allclose(cD1, [-0.70710678] * 4, atol=5e-9)
+    cA, cD = ob.wavedec_mode(np.arange(1.0, 7.0), bank, "symmetric", level=1)
+    np.testing.assert_allclose(cA, [2.12132034, 4.94974747, 7.77817459], atol=5e-9)
+    np.testing.assert_allclose(cD, [-0.70710678] * 3, atol=5e-9)
+    np.testing.assert_allclose(ob.waverec_mode([cA2, cD2, cD1], bank, "symmetric"), np.arange(1.0, 9.0), atol=1e-12)
